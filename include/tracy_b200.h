@@ -1,0 +1,147 @@
+/* tracy_b200 -- C ABI of the B200-native Gotoh / decompose hot path.
+ *
+ * Drop-in boundary for the three call shapes that tracy's drivers use:
+ *
+ *   int gotohScore(a1, a2, AlignConfig<H,V>, DnaScore<int32_t>)          reference src/gotoh.h:12-14
+ *   int gotoh     (a1, a2, align&, AlignConfig<H,V>, DnaScore<int32_t>)  reference src/gotoh.h:71-73
+ *   bool decomposeAlleles(c, align, bc&, bp, rs&, dcp&)  -- its three sweeps  reference src/decompose.h:210-313
+ *
+ * The reference calls these one pair at a time from a single thread; this library takes BATCHES of independent
+ * pairs (plain pointers and sizes, no C++ or torch types) and runs them on one B200 with hand-written sm_100a
+ * kernels.  There is no CPU fallback: every entry point fails with TB_ERR_CUDA when no device is usable.
+ *
+ * Inputs are described as "arenas": one base pointer plus per-item element offsets and lengths, so that a
+ * 10^5..10^6-pair batch is a handful of large copies.  A profile item is the reference's layout, float[6][len]
+ * row-major (rows A,C,G,T,N,-; boost::multi_array C order, reference src/align.h:125); a sequence item is `len` chars.
+ *
+ * Results are bit-exact to the reference (scores, traceback strings) -- see DESIGN.md for the proof obligations.
+ */
+#ifndef TRACY_B200_H
+#define TRACY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tb_ctx tb_ctx; /* opaque: device, streams, scratch; used by one host thread at a time */
+
+enum {
+  TB_OK = 0,
+  TB_ERR_INVALID = 1,     /* bad argument (null pointer, negative length, capacity too small, ...) */
+  TB_ERR_CUDA = 2,        /* no usable device / CUDA runtime failure (tb_last_error has the text) */
+  TB_ERR_NOMEM = 3,       /* device or pinned-host allocation failed */
+  TB_ERR_UNSUPPORTED = 4  /* sizes/scores outside the range where int32 DP with inf=1e6 is well defined */
+};
+
+/* DnaScore<int32_t>(match, mismatch, gapopen, gapext), reference src/align.h:11-32. inf is fixed at 1000000. */
+typedef struct { int32_t match, mismatch, gap_open, gap_extend; } tb_score;
+
+/* AlignConfig<THorizontal, TVertical>, reference src/align.h:37-80: end gaps in the first/last ROW (h_free) or
+ * first/last COLUMN (v_free) cost nothing.  a1 indexes rows, a2 indexes columns. */
+typedef struct { int32_t h_free, v_free; } tb_align_config;
+
+enum { TB_MEM_HOST = 0, TB_MEM_DEVICE = 1 };
+
+/* One side of a batch. base: const float* (profiles) or const char* (sequences). off[i] is in ELEMENTS
+ * (floats / chars) from base; len[i] is the number of columns (profile) or characters (sequence). */
+typedef struct {
+  const void* base;
+  const int64_t* off;
+  const int32_t* len;
+} tb_arena;
+
+/* A batch of independent (a1[i], a2[i]) pairs. `mem` says where EVERY pointer handed to the call lives
+ * (arena bases, off/len arrays and the output arrays): TB_MEM_HOST (pinned recommended, see tb_host_alloc)
+ * or TB_MEM_DEVICE (already resident in HBM; no copies are made). */
+typedef struct {
+  tb_arena a1;     /* rows: the trace in align/decompose */
+  tb_arena a2;     /* columns: the reference window */
+  size_t npairs;
+  int32_t mem;
+} tb_batch;
+
+/* Traceback output. ops: npairs * ops_stride bytes; pair i's string starts at ops + i*ops_stride, holds
+ * ops_len[i] characters from {'s','h','v'} in START->END order, i.e. the reference's `btr` vector reversed --
+ * the order in which _createAlignment consumes it (src/gotoh.h:148-166, src/align.h:280-291):
+ *   's' both advance, 'h' gap in a1 (row 0 gets '-'), 'v' gap in a2 (row 1 gets '-').
+ * ops_stride must be >= max_i(len1[i] + len2[i]). */
+typedef struct {
+  int32_t* scores;     /* [npairs]  S[m][n], the value gotoh()/gotohScore() return */
+  uint8_t* ops;        /* may be NULL for score-only calls */
+  int64_t ops_stride;
+  int32_t* ops_len;    /* [npairs]; may be NULL iff ops is NULL */
+} tb_result;
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+int tb_ctx_create(tb_ctx** out, int device);
+void tb_ctx_destroy(tb_ctx* ctx);
+const char* tb_strerror(int code);
+const char* tb_last_error(const tb_ctx* ctx);       /* text of the last failure on this context */
+/* Pinned host memory for TB_MEM_HOST batches (plain malloc'd memory also works, only slower). */
+int tb_host_alloc(tb_ctx* ctx, void** out, size_t bytes);
+int tb_host_free(tb_ctx* ctx, void* p);
+/* Upper bound on device scratch the context may hold (bytes; 0 = default: a third of free HBM). */
+int tb_ctx_set_scratch_limit(tb_ctx* ctx, size_t bytes);
+/* Counters since context creation: kernels launched, bytes copied H2D and D2H by the library. */
+int tb_ctx_stats(const tb_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* Device time (CUDA events on the launching streams, milliseconds) of the kernels of the most recent call on this
+ * context: the packed 16x2 Gotoh kernel, the general int32 Gotoh kernel, the sweep kernel. Any pointer may be NULL. */
+int tb_ctx_last_kernel_ms(const tb_ctx* ctx, float* packed_ms, float* general_ms, float* sweep_ms);
+
+/* ---- gotohScore / gotoh ---------------------------------------------------------------------------------
+ * _ps : a1 = trace profile float[6][m], a2 = reference SEQUENCE. Semantics are those of the reference when it
+ *       aligns against _createProfile(std::string) (src/align.h:121-136), as src/sage.h:233-258,
+ *       src/indigo.h:228-236,302 and src/assemble.h:221-257 do: identical to _pp on the one-hot profile.
+ * _pp : both profiles (wild-type trace reference, assemble all-pairs, MSA merges; src/msa.h:39,116,258,293).
+ * _ss : both sequences, byte-equality scoring (src/align.h:96-101; src/indigo.h:359-387).
+ * Pass res->ops == NULL for the gotohScore() shape. Profile values must be finite. */
+int tb_gotoh_ps(tb_ctx* ctx, const tb_batch* batch, tb_score sc, tb_align_config ac, tb_result* res);
+int tb_gotoh_pp(tb_ctx* ctx, const tb_batch* batch, tb_score sc, tb_align_config ac, tb_result* res);
+int tb_gotoh_ss(tb_ctx* ctx, const tb_batch* batch, tb_score sc, tb_align_config ac, tb_result* res);
+
+/* Gapped alignment rows from a traceback string: what gotoh() leaves in `align` (src/align.h:196-223 for
+ * sequences, :254-293 for profiles: argmax channel, strict >, indices >= 4 print as 'N', never '-').
+ * kind: 0 = _pp, 1 = _ss, 2 = _ps. Host-side helper (O(L)); row0/row1 need ops_len bytes each. */
+int tb_rows_from_ops(int kind, const void* a1, int32_t len1, const void* a2, int32_t len2,
+                     const uint8_t* ops, int32_t ops_len, char* row0, char* row1);
+
+/* ---- decompose: the indel-shift sweeps of decomposeAlleles (src/decompose.h:210-224, :247-261, :288-313) ----
+ * For trace t the caller has already walked the alignment to the breakpoint (src/decompose.h:186-208), which
+ * fixes align_index[t] and var_index[t]. For every shift the kernel counts
+ *     #{ j : refrow[j] != primary[vi] and phaseRefAllele(primary[vi], secondary[vi], refrow[j]) == 'N' }
+ * over j = j0.., vi = vi0.. while j < L and vi < vi_end, with
+ *     deletions  d in [0,ndel):  j0 = align_index+d+1, vi0 = var_index          -> fref[d]
+ *     insertions i in [1,nins):  j0 = align_index+1,   vi0 = var_index+i        -> fins[i]   (fins[0] = fref[0])
+ *     grid (optional)            j0 = align_index+d+1, vi0 = var_index+i        -> grid[i*grid_stride + d]
+ * Strings are arenas of chars: refrow = align row 1 (the reference row incl. '-'), primary/secondary = basecalls. */
+typedef struct {
+  tb_arena refrow;      /* len = alignment length L */
+  tb_arena primary;     /* len = number of basecalls; secondary shares off/len layout */
+  const char* secondary_base;
+  const int32_t* vi_end;       /* bc.consensus.size() - trimRight */
+  const int32_t* align_index;  /* alignIndex */
+  const int32_t* var_index;    /* varIndex */
+  const int32_t* ndel;         /* number of deletion shifts to evaluate, <= out_stride */
+  const int32_t* nins;         /* number of insertion shifts to evaluate, <= out_stride */
+  size_t ntraces;
+  int32_t mem;
+} tb_sweep_batch;
+
+typedef struct {
+  int32_t* fref;        /* [ntraces * out_stride] */
+  int32_t* fins;        /* [ntraces * out_stride] */
+  int32_t out_stride;
+  int32_t* grid;        /* optional: [ntraces * out_stride * out_stride], row = insertion, col = deletion */
+} tb_sweep_result;
+
+int tb_decompose_sweep(tb_ctx* ctx, const tb_sweep_batch* batch, tb_sweep_result* res);
+
+const char* tb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRACY_B200_H */

@@ -1,0 +1,251 @@
+"""ctypes loaders for the two CPU oracles.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module; the product package tracy_b200 never does (tests/test_boundary.py greps for it).
+
+  port()  -> oracle/libgotoh_oracle.so   the plain-C restatement (oracle/gotoh_oracle.c)
+  ref()   -> oracle/_ref/libtracy_ref.so the unmodified reference headers (oracle/ref_bridge.cpp); None if absent
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_SC = [C.c_int] * 6  # hfree, vfree, match, mismatch, go, ge
+
+
+def build(force=False):
+    """Compile the C restatement, and the reference bridge when /root/reference exists (make decides)."""
+    so = os.path.join(_HERE, "libgotoh_oracle.so")
+    src = os.path.join(_HERE, "gotoh_oracle.c")
+    need = force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src)
+    ref_so = os.path.join(_HERE, "_ref", "libtracy_ref.so")
+    bridge = os.path.join(_HERE, "ref_bridge.cpp")
+    if os.path.isdir("/root/reference/src") and (force or not os.path.exists(ref_so) or os.path.getmtime(ref_so) < os.path.getmtime(bridge)):
+        need = True
+    if need:
+        subprocess.run(["make", "-s", "-C", _HERE, "all"], check=True)
+
+
+class _Port:
+    def __init__(self, path):
+        L = self.lib = C.CDLL(path)
+        L.orc_gotoh_score_pp.argtypes = [_f32p, C.c_long, _f32p, C.c_long] + _SC
+        L.orc_gotoh_score_pp.restype = C.c_int
+        L.orc_gotoh_pp.argtypes = [_f32p, C.c_long, _f32p, C.c_long] + _SC + [C.c_char_p, C.POINTER(C.c_long)]
+        L.orc_gotoh_pp.restype = C.c_int
+        L.orc_gotoh_ps.argtypes = [_f32p, C.c_long, C.c_char_p, C.c_long] + _SC + [C.c_char_p, C.POINTER(C.c_long)]
+        L.orc_gotoh_ps.restype = C.c_int
+        L.orc_gotoh_ss.argtypes = [C.c_char_p, C.c_long, C.c_char_p, C.c_long] + _SC + [C.c_char_p, C.POINTER(C.c_long)]
+        L.orc_gotoh_ss.restype = C.c_int
+        L.orc_rows_from_ops.argtypes = [C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_char_p, C.c_long, C.c_char_p, C.c_char_p]
+        L.orc_rows_from_ops.restype = None
+        L.orc_onehot_profile.argtypes = [C.c_char_p, C.c_long, _f32p]
+        L.orc_revcomp_profile.argtypes = [_f32p, C.c_long, _f32p]
+        L.orc_phase_ref_allele.argtypes = [C.c_char, C.c_char, C.c_char]
+        L.orc_phase_ref_allele.restype = C.c_char
+        L.orc_decompose_sweep.argtypes = [C.c_char_p, C.c_long, C.c_char_p, C.c_char_p, C.c_long, C.c_long, C.c_long,
+                                          C.c_int, C.c_int, _i32p, _i32p, C.c_void_p]
+        L.orc_decompose_sweep.restype = None
+        L.orc_bench_gotoh_ps.argtypes = [_f32p, C.c_char_p, C.c_int, C.c_long, C.c_long] + _SC + [C.c_int, _i32p]
+        L.orc_bench_gotoh_ps.restype = C.c_longlong
+
+    @staticmethod
+    def _prof(p):
+        p = np.ascontiguousarray(p, dtype=np.float32)
+        assert p.ndim == 2 and p.shape[0] == 6
+        return p
+
+    def gotoh_score_pp(self, p1, p2, hfree, vfree, sc):
+        p1, p2 = self._prof(p1), self._prof(p2)
+        return self.lib.orc_gotoh_score_pp(p1, p1.shape[1], p2, p2.shape[1], hfree, vfree, *sc)
+
+    def _run(self, fn, a, m, b, n, hfree, vfree, sc):
+        buf = C.create_string_buffer(m + n + 1)
+        L = C.c_long(0)
+        s = fn(a, m, b, n, hfree, vfree, *sc, buf, C.byref(L))
+        return s, buf.raw[: L.value]
+
+    def gotoh_pp(self, p1, p2, hfree, vfree, sc):
+        p1, p2 = self._prof(p1), self._prof(p2)
+        return self._run(self.lib.orc_gotoh_pp, p1, p1.shape[1], p2, p2.shape[1], hfree, vfree, sc)
+
+    def gotoh_ps(self, p1, seq, hfree, vfree, sc):
+        p1 = self._prof(p1)
+        return self._run(self.lib.orc_gotoh_ps, p1, p1.shape[1], bytes(seq), len(seq), hfree, vfree, sc)
+
+    def gotoh_ss(self, s1, s2, hfree, vfree, sc):
+        return self._run(self.lib.orc_gotoh_ss, bytes(s1), len(s1), bytes(s2), len(s2), hfree, vfree, sc)
+
+    def rows_from_ops(self, a, b, ops):
+        """a, b: both float[6][len] profiles or both bytes."""
+        L = len(ops)
+        r0, r1 = C.create_string_buffer(L + 1), C.create_string_buffer(L + 1)
+        if isinstance(a, (bytes, bytearray)):
+            ka, kb = C.create_string_buffer(bytes(a), len(a) + 1), C.create_string_buffer(bytes(b), len(b) + 1)
+            self.lib.orc_rows_from_ops(1, C.cast(ka, C.c_void_p), len(a), C.cast(kb, C.c_void_p), len(b), bytes(ops), L, r0, r1)
+        else:
+            a, b = self._prof(a), self._prof(b)
+            self.lib.orc_rows_from_ops(0, a.ctypes.data_as(C.c_void_p), a.shape[1], b.ctypes.data_as(C.c_void_p), b.shape[1], bytes(ops), L, r0, r1)
+        return r0.raw[:L], r1.raw[:L]
+
+    def onehot(self, seq):
+        out = np.zeros((6, len(seq)), np.float32)
+        self.lib.orc_onehot_profile(bytes(seq), len(seq), out)
+        return out
+
+    def revcomp_profile(self, p):
+        p = self._prof(p)
+        out = np.empty_like(p)
+        self.lib.orc_revcomp_profile(p, p.shape[1], out)
+        return out
+
+    def phase(self, pri, sec, r):
+        return self.lib.orc_phase_ref_allele(pri, sec, r)
+
+    def decompose_sweep(self, refrow, primary, secondary, vi_end, align_index, var_index, ndel, nins, grid=False):
+        fref = np.zeros(max(ndel, 1), np.int32)
+        fins = np.zeros(max(nins, 1), np.int32)
+        g = np.zeros((max(nins, 1), max(ndel, 1)), np.int32) if grid else None
+        self.lib.orc_decompose_sweep(bytes(refrow), len(refrow), bytes(primary), bytes(secondary), vi_end, align_index, var_index,
+                                     ndel, nins, fref, fins, g.ctypes.data_as(C.c_void_p) if grid else None)
+        return fref[:ndel], fins[:nins], (g[:nins, :ndel] if grid else None)
+
+    def bench_gotoh_ps(self, profs, seqs, m, n, hfree, vfree, sc, with_traceback=True):
+        profs = np.ascontiguousarray(profs, np.float32)
+        npairs = profs.shape[0]
+        scores = np.zeros(npairs, np.int32)
+        cells = self.lib.orc_bench_gotoh_ps(profs.reshape(-1), bytes(seqs), npairs, m, n, hfree, vfree, *sc, int(with_traceback), scores)
+        return cells, scores
+
+
+class _Ref:
+    """The reference's own code (unmodified headers) behind oracle/ref_bridge.cpp."""
+
+    def __init__(self, path):
+        L = self.lib = C.CDLL(path)
+        for name, a, b in (("pp", _f32p, _f32p), ("ps", _f32p, C.c_char_p), ("ss", C.c_char_p, C.c_char_p)):
+            f = getattr(L, "ref_gotoh_score_" + name)
+            f.argtypes = [a, C.c_int, b, C.c_int] + _SC
+            f.restype = C.c_int
+            g = getattr(L, "ref_gotoh_" + name)
+            g.argtypes = [a, C.c_int, b, C.c_int] + _SC + [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+            g.restype = C.c_int
+        L.ref_onehot_profile.argtypes = [C.c_char_p, C.c_int, _f32p]
+        L.ref_revcomp_profile.argtypes = [_f32p, C.c_int, _f32p]
+        L.ref_create_profile.argtypes = [_i32p, C.c_int, _i32p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int]
+        L.ref_create_profile.restype = C.c_int
+        L.ref_find_breakpoint.argtypes = [_f32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.ref_decompose_alleles.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_uint32, C.c_int, _i32p, C.c_int]
+        L.ref_decompose_alleles.restype = C.c_int
+        L.ref_bench_gotoh_ps.argtypes = [_f32p, C.c_char_p, C.c_int, C.c_int, C.c_int] + _SC + [C.c_int, _i32p]
+        L.ref_bench_gotoh_ps.restype = C.c_longlong
+
+    @staticmethod
+    def _conv(x):
+        if isinstance(x, (bytes, bytearray)):
+            return bytes(x), len(x)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[0] == 6
+        return x, x.shape[1]
+
+    @staticmethod
+    def _kind(a, b):
+        ka = "s" if isinstance(a, (bytes, bytearray)) else "p"
+        kb = "s" if isinstance(b, (bytes, bytearray)) else "p"
+        return ka + kb
+
+    def gotoh_score(self, a, b, hfree, vfree, sc):
+        f = getattr(self.lib, "ref_gotoh_score_" + self._kind(a, b))
+        (a, m), (b, n) = self._conv(a), self._conv(b)
+        return f(a, m, b, n, hfree, vfree, *sc)
+
+    def gotoh(self, a, b, hfree, vfree, sc):
+        """-> (score, row0, row1) exactly as the reference's gotoh() fills `align`."""
+        f = getattr(self.lib, "ref_gotoh_" + self._kind(a, b))
+        (a, m), (b, n) = self._conv(a), self._conv(b)
+        cap = m + n + 1
+        r0, r1 = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        L = C.c_int(0)
+        s = f(a, m, b, n, hfree, vfree, *sc, r0, r1, cap, C.byref(L))
+        assert L.value >= 0
+        return s, r0.raw[: L.value], r1.raw[: L.value]
+
+    def onehot(self, seq):
+        out = np.zeros((6, len(seq)), np.float32)
+        self.lib.ref_onehot_profile(bytes(seq), len(seq), out)
+        return out
+
+    def revcomp_profile(self, p):
+        p = np.ascontiguousarray(p, np.float32)
+        out = np.empty_like(p)
+        self.lib.ref_revcomp_profile(p, p.shape[1], out)
+        return out
+
+    def create_profile(self, acgt, bcpos, primary, secondary, trimleft=0, trimright=0):
+        acgt = np.ascontiguousarray(acgt, np.int32)
+        bcpos = np.ascontiguousarray(bcpos, np.int32)
+        nbc = len(bcpos)
+        out = np.zeros((6, nbc), np.float32)
+        n = self.lib.ref_create_profile(acgt.reshape(-1), acgt.shape[1], bcpos, bytes(primary), bytes(secondary), nbc, trimleft, trimright,
+                                        out.reshape(-1), nbc)
+        assert n >= 0
+        return np.ascontiguousarray(out.reshape(-1)[: 6 * n].reshape(6, n))
+
+    def find_breakpoint(self, prof):
+        prof = np.ascontiguousarray(prof, np.float32)
+        a, b, c, d = C.c_int(), C.c_int(), C.c_uint32(), C.c_float()
+        self.lib.ref_find_breakpoint(prof, prof.shape[1], C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return bool(a.value), bool(b.value), c.value, d.value
+
+    def decompose_alleles(self, row0, row1, primary, secondary, trim_left, trim_right, maxindel, madc, breakpoint, refslice_len):
+        nbc = len(primary)
+        pri = C.create_string_buffer(bytes(primary), nbc + 1)
+        sec = C.create_string_buffer(bytes(secondary), nbc + 1)
+        dcp = np.zeros(2 * 4096, np.int32)
+        n = self.lib.ref_decompose_alleles(bytes(row0), bytes(row1), len(row0), pri, sec, nbc, trim_left, trim_right, maxindel, madc,
+                                           breakpoint, refslice_len, dcp, 4096)
+        return pri.raw[:nbc], sec.raw[:nbc], dcp[: 2 * n].reshape(n, 2).copy()
+
+    def bench_gotoh_ps(self, profs, seqs, m, n, hfree, vfree, sc, with_traceback=True):
+        profs = np.ascontiguousarray(profs, np.float32)
+        npairs = profs.shape[0]
+        scores = np.zeros(npairs, np.int32)
+        cells = self.lib.ref_bench_gotoh_ps(profs.reshape(-1), bytes(seqs), npairs, m, n, hfree, vfree, *sc, int(with_traceback), scores)
+        return cells, scores
+
+
+_port = None
+_ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        build()
+        _port = _Port(os.path.join(_HERE, "libgotoh_oracle.so"))
+    return _port
+
+
+def ref():
+    """The reference build, or None where oracle/_ref was never built (it cannot be rebuilt without /root/reference)."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(_HERE, "_ref", "libtracy_ref.so")
+        if not os.path.exists(path):
+            return None
+        _ref = _Ref(path)
+    return _ref
+
+
+def ops_from_rows(row0, row1):
+    """Derive the s/h/v string from the reference's gapped rows (src/align.h:281-291)."""
+    out = bytearray()
+    for x, y in zip(row0, row1):
+        out.append(ord("h") if x == 0x2D else (ord("v") if y == 0x2D else ord("s")))
+    return bytes(out)

@@ -1,0 +1,279 @@
+"""Host-side Python layer over the C ABI (include/tracy_b200.h).
+
+Batch API (`Context.gotoh`, `Context.gotoh_device`, `Context.decompose_sweep`) plus single-pair mirrors of the
+reference's call shapes with the reference's names (`gotohScore`, `gotoh`, `DnaScore`, `AlignConfig`;
+reference src/gotoh.h:12-14, :71-73, src/align.h:11-50).  Everything here only marshals buffers; the DP runs in
+the CUDA library and nowhere else.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+
+PS, PP, SS = "ps", "pp", "ss"
+_KIND_ID = {PP: 0, SS: 1, PS: 2}
+
+
+class TracyError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tracy_b200 error {code}: {msg}")
+        self.code = code
+
+
+@dataclass
+class DnaScore:
+    """reference src/align.h:11-32 (the CLI always uses the 4-argument constructor, src/sage.h:166)."""
+    match: int = 5
+    mismatch: int = -4
+    go: int = -10
+    ge: int = -1
+
+    def c(self):
+        return capi.Score(self.match, self.mismatch, self.go, self.ge)
+
+
+@dataclass
+class AlignConfig:
+    """AlignConfig<THorizontal, TVertical>, reference src/align.h:37-80."""
+    horizontal: bool = False
+    vertical: bool = False
+
+    def c(self):
+        return capi.AlignConfig(int(self.horizontal), int(self.vertical))
+
+
+@dataclass
+class Arena:
+    """One side of a batch in host memory: flat `base` plus per-item element offsets and lengths."""
+    base: np.ndarray      # float32 (profiles) or uint8 (sequences), 1-D contiguous
+    off: np.ndarray       # int64[N]
+    len: np.ndarray       # int32[N]
+
+    @property
+    def n(self):
+        return len(self.off)
+
+
+def pack_profiles(items):
+    """list of float[6][len] arrays -> Arena (reference layout per item, row-major)."""
+    items = [np.ascontiguousarray(p, dtype=np.float32) for p in items]
+    for p in items:
+        if p.ndim != 2 or p.shape[0] != 6:
+            raise ValueError("a profile is float[6][len] (rows A,C,G,T,N,-)")
+    lens = np.array([p.shape[1] for p in items], np.int32)
+    sizes = 6 * lens.astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64) if len(items) else np.zeros(0, np.int64)
+    base = np.concatenate([p.reshape(-1) for p in items]) if len(items) else np.zeros(0, np.float32)
+    if base.size == 0:
+        base = np.zeros(1, np.float32)
+    return Arena(base, off, lens)
+
+
+def pack_seqs(items):
+    items = [bytes(s) for s in items]
+    lens = np.array([len(s) for s in items], np.int32)
+    off = np.concatenate([[0], np.cumsum(lens.astype(np.int64))[:-1]]).astype(np.int64) if len(items) else np.zeros(0, np.int64)
+    base = np.frombuffer(b"".join(items), np.uint8).copy() if sum(map(len, items)) else np.zeros(1, np.uint8)
+    return Arena(base, off, lens)
+
+
+def uniform_profiles(arr):
+    """float32[N][6][m] -> Arena without copying."""
+    arr = np.ascontiguousarray(arr, np.float32)
+    n, six, m = arr.shape
+    assert six == 6
+    return Arena(arr.reshape(-1), np.arange(n, dtype=np.int64) * (6 * m), np.full(n, m, np.int32))
+
+
+def uniform_seqs(arr):
+    """uint8[N][n] -> Arena without copying."""
+    arr = np.ascontiguousarray(arr, np.uint8)
+    n, k = arr.shape
+    return Arena(arr.reshape(-1), np.arange(n, dtype=np.int64) * k, np.full(n, k, np.int32))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """Owns one tb_ctx (one GPU). Not thread-safe, like the reference's functions it is used from one thread."""
+
+    def __init__(self, device=0):
+        self._lib = capi.lib()
+        h = C.c_void_p()
+        rc = self._lib.tb_ctx_create(C.byref(h), device)
+        if rc != capi.TB_OK:
+            raise TracyError(rc, self._lib.tb_strerror(rc).decode() + " (tb_ctx_create: is a B200 visible? there is no CPU fallback)")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tb_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != capi.TB_OK:
+            raise TracyError(rc, self._lib.tb_strerror(rc).decode() + ": " + self._lib.tb_last_error(self._h).decode())
+
+    def set_scratch_limit(self, nbytes):
+        self._check(self._lib.tb_ctx_set_scratch_limit(self._h, int(nbytes)))
+
+    def stats(self):
+        k, a, b = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.tb_ctx_stats(self._h, C.byref(k), C.byref(a), C.byref(b)))
+        return {"kernel_launches": k.value, "h2d_bytes": a.value, "d2h_bytes": b.value}
+
+    def last_kernel_ms(self):
+        p, g, s = C.c_float(), C.c_float(), C.c_float()
+        self._check(self._lib.tb_ctx_last_kernel_ms(self._h, C.byref(p), C.byref(g), C.byref(s)))
+        return {"packed_ms": p.value, "general_ms": g.value, "sweep_ms": s.value}
+
+    # ---- gotoh / gotohScore, batched -------------------------------------------------------------------
+    def _fn(self, kind):
+        return {PS: self._lib.tb_gotoh_ps, PP: self._lib.tb_gotoh_pp, SS: self._lib.tb_gotoh_ss}[kind]
+
+    def gotoh(self, kind, a1, a2, sc=DnaScore(3, -5, -10, -4), ac=AlignConfig(True, False), traceback=True, out=None):
+        """Batch of pairs in HOST memory. a1/a2: Arena (or lists of profiles / byte strings).
+        Returns (scores int32[N], ops uint8[N][stride] or None, ops_len int32[N] or None).
+        `out` may carry preallocated (scores, ops, ops_len) arrays (e.g. pinned)."""
+        if not isinstance(a1, Arena):
+            a1 = pack_seqs(a1) if kind == SS else pack_profiles(a1)
+        if not isinstance(a2, Arena):
+            a2 = pack_profiles(a2) if kind == PP else pack_seqs(a2)
+        n = a1.n
+        if a2.n != n:
+            raise ValueError("a1 and a2 must hold the same number of items")
+        if out is not None:
+            scores, ops, ops_len = out
+        else:
+            scores = np.zeros(n, np.int32)
+            ops = ops_len = None
+            if traceback:
+                stride = int((a1.len.astype(np.int64) + a2.len).max()) if n else 1
+                stride = max((stride + 15) // 16 * 16, 16)
+                ops = np.zeros((n, stride), np.uint8)
+                ops_len = np.zeros(n, np.int32)
+        b = capi.Batch(capi.Arena(_ptr(a1.base), _ptr(a1.off), _ptr(a1.len)),
+                       capi.Arena(_ptr(a2.base), _ptr(a2.off), _ptr(a2.len)), n, capi.TB_MEM_HOST)
+        r = capi.Result(_ptr(scores), _ptr(ops) if traceback else None, ops.shape[1] if traceback else 0,
+                        _ptr(ops_len) if traceback else None)
+        self._check(self._fn(kind)(self._h, C.byref(b), sc.c(), ac.c(), C.byref(r)))
+        return scores, ops, ops_len
+
+    def gotoh_device(self, kind, a1_base, a1_off, a1_len, a2_base, a2_off, a2_len, n, scores, ops=None, ops_stride=0, ops_len=None,
+                     sc=DnaScore(3, -5, -10, -4), ac=AlignConfig(True, False)):
+        """Everything already resident in HBM: arguments are raw device pointers (ints), e.g. torch tensor .data_ptr()."""
+        b = capi.Batch(capi.Arena(a1_base, a1_off, a1_len), capi.Arena(a2_base, a2_off, a2_len), n, capi.TB_MEM_DEVICE)
+        r = capi.Result(scores, ops, ops_stride, ops_len)
+        self._check(self._fn(kind)(self._h, C.byref(b), sc.c(), ac.c(), C.byref(r)))
+
+    # ---- decompose sweeps ---------------------------------------------------------------------------------
+    def decompose_sweep(self, refrows, primaries, secondaries, vi_end, align_index, var_index, ndel, nins, grid=False):
+        """Lists of byte strings (one per trace) plus per-trace ints. Returns (fref[N][S], fins[N][S], grid[N][S][S] | None)
+        with S = max(ndel, nins, 1); entries beyond a trace's ndel/nins are 0."""
+        ref = pack_seqs(refrows)
+        pri = pack_seqs(primaries)
+        sec = pack_seqs(secondaries)
+        if not np.array_equal(pri.len, sec.len):
+            raise ValueError("primary and secondary must have equal lengths")
+        n = ref.n
+        i32 = lambda x: np.ascontiguousarray(x, np.int32)
+        vi_end, align_index, var_index, ndel, nins = map(i32, (vi_end, align_index, var_index, ndel, nins))
+        S = int(max(1, ndel.max() if n else 1, nins.max() if n else 1))
+        fref = np.zeros((n, S), np.int32)
+        fins = np.zeros((n, S), np.int32)
+        g = np.zeros((n, S, S), np.int32) if grid else None
+        b = capi.SweepBatch(capi.Arena(_ptr(ref.base), _ptr(ref.off), _ptr(ref.len)), capi.Arena(_ptr(pri.base), _ptr(pri.off), _ptr(pri.len)),
+                            _ptr(sec.base), _ptr(vi_end), _ptr(align_index), _ptr(var_index), _ptr(ndel), _ptr(nins), n, capi.TB_MEM_HOST)
+        r = capi.SweepResult(_ptr(fref), _ptr(fins), S, _ptr(g) if grid else None)
+        self._check(self._lib.tb_decompose_sweep(self._h, C.byref(b), C.byref(r)))
+        for t in range(n):   # the kernel only writes the evaluated shifts; fins[0] = fref[0] by definition (src/decompose.h:248)
+            fref[t, ndel[t]:] = 0
+            fins[t, nins[t]:] = 0
+        return fref, fins, g
+
+    # ---- helpers ------------------------------------------------------------------------------------------
+    def rows_from_ops(self, kind, a1, a2, ops):
+        """Gapped rows as gotoh() leaves them in `align` (reference src/align.h:196-293)."""
+        return rows_from_ops(kind, a1, a2, ops)
+
+
+def rows_from_ops(kind, a1, a2, ops):
+    lib = capi.lib()
+    ops = np.frombuffer(bytes(ops), np.uint8)
+    L = len(ops)
+    r0, r1 = C.create_string_buffer(L + 1), C.create_string_buffer(L + 1)
+
+    def conv(x, is_prof):
+        if is_prof:
+            x = np.ascontiguousarray(x, np.float32)
+            return x, x.ctypes.data_as(C.c_void_p), x.shape[1]
+        x = np.frombuffer(bytes(x), np.uint8)
+        return x, x.ctypes.data_as(C.c_void_p), len(x)
+
+    k1, p1, l1 = conv(a1, kind != SS)
+    k2, p2, l2 = conv(a2, kind == PP)
+    rc = lib.tb_rows_from_ops(_KIND_ID[kind], p1, l1, p2, l2, ops.ctypes.data_as(C.c_void_p), L, C.cast(r0, C.c_void_p), C.cast(r1, C.c_void_p))
+    if rc != capi.TB_OK:
+        raise TracyError(rc, lib.tb_strerror(rc).decode())
+    return r0.raw[:L], r1.raw[:L]
+
+
+# ---- single-pair mirrors of the reference call shapes --------------------------------------------------------
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _kind_of(a1, a2):
+    s1 = isinstance(a1, (bytes, bytearray, str))
+    s2 = isinstance(a2, (bytes, bytearray, str))
+    if s1 and s2:
+        return SS
+    if not s1 and s2:
+        return PS
+    if not s1 and not s2:
+        return PP
+    raise TypeError("sequence x profile is not a pairing the reference instantiates")
+
+
+def _b(x):
+    return x.encode() if isinstance(x, str) else x
+
+
+def gotohScore(a1, a2, ac=AlignConfig(), sc=DnaScore(), ctx=None):
+    """int gotohScore(a1, a2, ac, sc) -- reference src/gotoh.h:12-14."""
+    ctx = ctx or default_context()
+    kind = _kind_of(a1, a2)
+    s, _, _ = ctx.gotoh(kind, [_b(a1)], [_b(a2)], sc, ac, traceback=False)
+    return int(s[0])
+
+
+def gotoh(a1, a2, ac=AlignConfig(), sc=DnaScore(), ctx=None):
+    """int gotoh(a1, a2, align, ac, sc) -- reference src/gotoh.h:71-73. Returns (score, (row0, row1))."""
+    ctx = ctx or default_context()
+    kind = _kind_of(a1, a2)
+    s, ops, ol = ctx.gotoh(kind, [_b(a1)], [_b(a2)], sc, ac, traceback=True)
+    o = bytes(ops[0, : ol[0]])
+    return int(s[0]), rows_from_ops(kind, _b(a1), _b(a2), o)

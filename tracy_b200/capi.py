@@ -1,0 +1,85 @@
+"""ctypes binding of include/tracy_b200.h. Loads the in-tree libtracy_b200.so and fails loudly if it is missing:
+there is no Python or CPU implementation of the hot path behind this module."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtracy_b200.so")
+
+TB_OK, TB_ERR_INVALID, TB_ERR_CUDA, TB_ERR_NOMEM, TB_ERR_UNSUPPORTED = range(5)
+TB_MEM_HOST, TB_MEM_DEVICE = 0, 1
+
+# every symbol include/tracy_b200.h declares (tests/test_boundary.py checks the header against this list)
+SYMBOLS = [
+    "tb_ctx_create", "tb_ctx_destroy", "tb_strerror", "tb_last_error", "tb_host_alloc", "tb_host_free",
+    "tb_ctx_set_scratch_limit", "tb_ctx_stats", "tb_ctx_last_kernel_ms", "tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss",
+    "tb_rows_from_ops", "tb_decompose_sweep", "tb_version",
+]
+
+
+class Score(C.Structure):
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32)]
+
+
+class AlignConfig(C.Structure):
+    _fields_ = [("h_free", C.c_int32), ("v_free", C.c_int32)]
+
+
+class Arena(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("off", C.c_void_p), ("len", C.c_void_p)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("a1", Arena), ("a2", Arena), ("npairs", C.c_size_t), ("mem", C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("scores", C.c_void_p), ("ops", C.c_void_p), ("ops_stride", C.c_int64), ("ops_len", C.c_void_p)]
+
+
+class SweepBatch(C.Structure):
+    _fields_ = [("refrow", Arena), ("primary", Arena), ("secondary_base", C.c_void_p), ("vi_end", C.c_void_p),
+                ("align_index", C.c_void_p), ("var_index", C.c_void_p), ("ndel", C.c_void_p), ("nins", C.c_void_p),
+                ("ntraces", C.c_size_t), ("mem", C.c_int32)]
+
+
+class SweepResult(C.Structure):
+    _fields_ = [("fref", C.c_void_p), ("fins", C.c_void_p), ("out_stride", C.c_int32), ("grid", C.c_void_p)]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library. Raises LibraryMissing when it has not been built (python -m tracy_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(f"{LIB_PATH} not found: build it with `python -m tracy_b200.build` (nvcc, sm_100a). "
+                             "tracy_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.tb_ctx_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.tb_ctx_destroy.argtypes = [vp]
+    L.tb_ctx_destroy.restype = None
+    L.tb_strerror.argtypes = [C.c_int]
+    L.tb_strerror.restype = C.c_char_p
+    L.tb_last_error.argtypes = [vp]
+    L.tb_last_error.restype = C.c_char_p
+    L.tb_host_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
+    L.tb_host_free.argtypes = [vp, vp]
+    L.tb_ctx_set_scratch_limit.argtypes = [vp, C.c_size_t]
+    L.tb_ctx_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.tb_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    for name in ("tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss"):
+        getattr(L, name).argtypes = [vp, C.POINTER(Batch), Score, AlignConfig, C.POINTER(Result)]
+    L.tb_rows_from_ops.argtypes = [C.c_int, vp, C.c_int32, vp, C.c_int32, vp, C.c_int32, vp, vp]
+    L.tb_decompose_sweep.argtypes = [vp, C.POINTER(SweepBatch), C.POINTER(SweepResult)]
+    L.tb_version.restype = C.c_char_p
+    _lib = L
+    return L

@@ -1,0 +1,566 @@
+// C ABI of tracy_b200 (include/tracy_b200.h): context, scratch sizing, host<->device staging, launches.
+// Host code only; the kernels live in gotoh_general.cu / gotoh_packed.cu / sweep.cu.
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/tracy_b200.h"
+#include "common.cuh"
+
+namespace tb {
+cudaError_t launch_gotoh_general(int mode, bool traceback, const GotohBatch& B, int blocks, cudaStream_t stream);
+cudaError_t gotoh_general_blocks_per_sm(int mode, bool traceback, int* out);
+int gotoh_general_warps_per_block();
+cudaError_t launch_gotoh_packed(bool traceback, const GotohBatch& B, int blocks, cudaStream_t stream);
+cudaError_t gotoh_packed_blocks_per_sm(bool traceback, int* out);
+int gotoh_packed_warps_per_block();
+bool gotoh_packed_eligible(int maxm, int maxn, int match, int mismatch, int go, int ge);
+unsigned long long gotoh_packed_ptr_words(int m, int n);
+
+
+cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
+}  // namespace tb
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaHostAlloc(&p, bytes + 256, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = bytes + 256;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Lane {   // one in-flight chunk of a TB_MEM_HOST batch
+  cudaStream_t stream = nullptr;
+  cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr;
+  DevBuf a, b, a_off, b_off, a_len, b_len, scores, ops, ops_len, status, counter;
+  DevBuf ptr, rowbuf, opsrev;
+  PinBuf meta;
+  bool timed = false, timed2 = false;
+};
+
+}  // namespace
+
+struct tb_ctx {
+  int device = 0;
+  int sms = 0;
+  size_t scratch_limit = 0;
+  std::string err;
+  Lane lanes[2];
+  uint64_t launches = 0, h2d = 0, d2h = 0;
+  float last_fast_ms = 0, last_general_ms = 0, last_sweep_ms = 0;
+  std::vector<int32_t> tmp_len1, tmp_len2;
+};
+
+namespace {
+
+int fail(tb_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+int cuda_fail(tb_ctx* c, cudaError_t e, const char* what) {
+  cudaGetLastError();
+  int code = (e == cudaErrorMemoryAllocation) ? TB_ERR_NOMEM : TB_ERR_CUDA;
+  return fail(c, code, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define TB_CUDA(ctx, call)                                   \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+  } while (0)
+
+struct Shape {            // maxima over (a slice of) a batch
+  int maxm = 0, maxn = 0, maxsum = 0;
+  unsigned long long gen_words = 0, packed_words = 0;
+};
+inline unsigned long long general_ptr_words(int m, int n) {
+  if (m <= 0 || n <= 0) return 0;
+  unsigned long long nb = (unsigned long long)(m + 511) / 512;
+  return nb * (unsigned long long)(n + 31) * 32ull;
+}
+void accumulate(Shape& s, const int32_t* l1, const int32_t* l2, size_t n, bool packed) {
+  for (size_t i = 0; i < n; ++i) {
+    const int m = l1[i], k = l2[i];
+    s.maxm = std::max(s.maxm, m);
+    s.maxn = std::max(s.maxn, k);
+    s.maxsum = std::max(s.maxsum, m + k);
+    s.gen_words = std::max(s.gen_words, general_ptr_words(m, k));
+    if (packed) s.packed_words = std::max(s.packed_words, tb::gotoh_packed_ptr_words(m, k));
+  }
+}
+
+struct Plan {
+  bool use_packed = false;
+  int blocks_packed = 0, blocks_general = 0;
+  unsigned slots = 0;                      // warp slots that own scratch
+  unsigned long long ptr_words = 0, rowbuf_elems = 0, ops_bytes = 0;
+};
+
+// Size the persistent grids and the per-slot scratch for a launch over `npairs` pairs with maxima `sh`.
+int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npairs, tb_score sc, Plan* out) {
+  Plan p;
+  int bps_g = 0;
+  TB_CUDA(ctx, tb::gotoh_general_blocks_per_sm(mode, traceback, &bps_g));
+  if (bps_g < 1) return fail(ctx, TB_ERR_CUDA, "general kernel does not fit on an SM");
+  const int wpb_g = tb::gotoh_general_warps_per_block();
+  p.use_packed = mode == tb::kModePS &&
+                 tb::gotoh_packed_eligible(sh.maxm, sh.maxn, sc.match, sc.mismatch, sc.gap_open, sc.gap_extend) &&
+                 getenv("TRACY_B200_NO_PACKED") == nullptr;
+  int bps_p = 0, wpb_p = 1;
+  if (p.use_packed) {
+    TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(traceback, &bps_p));
+    wpb_p = tb::gotoh_packed_warps_per_block();
+    if (bps_p < 1) p.use_packed = false;
+  }
+  unsigned long long warps_g = (unsigned long long)ctx->sms * bps_g * wpb_g;
+  unsigned long long warps_p = p.use_packed ? (unsigned long long)ctx->sms * bps_p * wpb_p : 0;
+  warps_g = std::min<unsigned long long>(warps_g, std::max<size_t>(npairs, 1));
+  warps_p = std::min<unsigned long long>(warps_p, std::max<size_t>(npairs, 1));
+
+  p.ptr_words = traceback ? std::max(sh.gen_words, sh.packed_words) : 0;
+  p.rowbuf_elems = 2ull * (unsigned long long)(sh.maxn + 1);
+  p.ops_bytes = traceback ? (((unsigned long long)sh.maxsum + 63) & ~63ull) : 0;
+  const unsigned long long per_slot = p.ptr_words * 8 + p.rowbuf_elems * 8 + p.ops_bytes;
+  size_t limit = ctx->scratch_limit;
+  if (limit == 0) {
+    size_t fr = 0, tot = 0;
+    TB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+    limit = fr / 3;
+  }
+  limit /= 2;   // two lanes may be in flight
+  unsigned long long max_slots = per_slot ? std::max<unsigned long long>(limit / per_slot, 1) : (1ull << 30);
+  warps_g = std::min(warps_g, max_slots);
+  warps_p = std::min(warps_p, max_slots);
+  p.blocks_general = (int)((warps_g + wpb_g - 1) / wpb_g);
+  p.blocks_packed = p.use_packed ? (int)((warps_p + wpb_p - 1) / wpb_p) : 0;
+  p.slots = (unsigned)std::max<unsigned long long>((unsigned long long)p.blocks_general * wpb_g,
+                                                   (unsigned long long)p.blocks_packed * wpb_p);
+  *out = p;
+  return TB_OK;
+}
+
+int reserve_scratch(tb_ctx* ctx, Lane& L, const Plan& p) {
+  TB_CUDA(ctx, L.ptr.reserve((size_t)(p.ptr_words * 8ull * p.slots)));
+  TB_CUDA(ctx, L.rowbuf.reserve((size_t)(p.rowbuf_elems * 8ull * p.slots)));
+  TB_CUDA(ctx, L.opsrev.reserve((size_t)(p.ops_bytes * p.slots)));
+  TB_CUDA(ctx, L.counter.reserve(64));
+  return TB_OK;
+}
+
+// Enqueue the DP kernels for one device-resident batch view on lane L's stream.
+int enqueue_gotoh(tb_ctx* ctx, Lane& L, int mode, bool traceback, tb::GotohBatch B, const Plan& p) {
+  B.ptr_scratch = L.ptr.as<unsigned long long>(); B.ptr_slot_words = p.ptr_words;
+  B.rowbuf = L.rowbuf.as<int2>(); B.rowbuf_slot = p.rowbuf_elems;
+  B.ops_scratch = L.opsrev.as<uint8_t>(); B.ops_slot = p.ops_bytes;
+  unsigned int* counters = L.counter.as<unsigned int>();
+  TB_CUDA(ctx, cudaMemsetAsync(counters, 0, 64, L.stream));
+  TB_CUDA(ctx, cudaMemsetAsync(B.status, 0, (size_t)B.npairs, L.stream));
+  L.timed = L.timed2 = false;
+  TB_CUDA(ctx, cudaEventRecord(L.k0, L.stream));
+  if (p.use_packed) {
+    B.counter = counters;
+    TB_CUDA(ctx, tb::launch_gotoh_packed(traceback, B, p.blocks_packed, L.stream));
+    ctx->launches++;
+    L.timed = true;
+  }
+  TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
+  B.counter = counters + 8;
+  TB_CUDA(ctx, tb::launch_gotoh_general(mode, traceback, B, p.blocks_general, L.stream));
+  ctx->launches++;
+  TB_CUDA(ctx, cudaEventRecord(L.k2, L.stream));
+  L.timed2 = true;
+  return TB_OK;
+}
+
+int collect_timing(tb_ctx* ctx, Lane& L) {
+  float ms = 0;
+  if (L.timed) { TB_CUDA(ctx, cudaEventElapsedTime(&ms, L.k0, L.k1)); ctx->last_fast_ms += ms; }
+  if (L.timed2) { TB_CUDA(ctx, cudaEventElapsedTime(&ms, L.k1, L.k2)); ctx->last_general_ms += ms; }
+  L.timed = L.timed2 = false;
+  return TB_OK;
+}
+
+size_t elem_size_a(int mode) { return mode == tb::kModeSS ? 1 : sizeof(float); }
+size_t elem_size_b(int mode) { return mode == tb::kModePP ? sizeof(float) : 1; }
+long long item_elems_a(int mode, int len) { return mode == tb::kModeSS ? len : 6ll * len; }
+long long item_elems_b(int mode, int len) { return mode == tb::kModePP ? 6ll * len : len; }
+
+int check_range(tb_ctx* ctx, const Shape& sh, tb_score sc) {
+  const long long maxabs = std::max(std::max(llabs((long long)sc.match), llabs((long long)sc.mismatch)),
+                                    std::max(llabs((long long)sc.gap_open), llabs((long long)sc.gap_extend)));
+  const long long bound = 2 * llabs((long long)sc.gap_open) + ((long long)sh.maxsum + 2) * maxabs;
+  if (bound >= 900000)
+    return fail(ctx, TB_ERR_UNSUPPORTED, "score range reaches the reference's inf sentinel (1e6): sizes x scores too large");
+  return TB_OK;
+}
+
+int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_align_config ac, tb_result* res) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (!batch || !res) return fail(ctx, TB_ERR_INVALID, "null batch/result");
+  const size_t np = batch->npairs;
+  ctx->last_fast_ms = ctx->last_general_ms = 0;
+  if (np == 0) return TB_OK;
+  if (np > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "npairs too large");
+  if (!batch->a1.base || !batch->a1.off || !batch->a1.len || !batch->a2.base || !batch->a2.off || !batch->a2.len || !res->scores)
+    return fail(ctx, TB_ERR_INVALID, "null arena/score pointer");
+  const bool traceback = res->ops != nullptr;
+  if (traceback && !res->ops_len) return fail(ctx, TB_ERR_INVALID, "ops given without ops_len");
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  // Lengths on the host (needed for validation and scratch sizing in both memory modes).
+  const int32_t *l1 = batch->a1.len, *l2 = batch->a2.len;
+  if (batch->mem == TB_MEM_DEVICE) {
+    ctx->tmp_len1.resize(np); ctx->tmp_len2.resize(np);
+    TB_CUDA(ctx, cudaMemcpy(ctx->tmp_len1.data(), batch->a1.len, np * 4, cudaMemcpyDeviceToHost));
+    TB_CUDA(ctx, cudaMemcpy(ctx->tmp_len2.data(), batch->a2.len, np * 4, cudaMemcpyDeviceToHost));
+    l1 = ctx->tmp_len1.data(); l2 = ctx->tmp_len2.data();
+  } else if (batch->mem != TB_MEM_HOST) {
+    return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST or TB_MEM_DEVICE");
+  }
+  for (size_t i = 0; i < np; ++i)
+    if (l1[i] < 0 || l2[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative length");
+  Shape all;
+  accumulate(all, l1, l2, np, mode == tb::kModePS);
+  if (traceback && res->ops_stride < all.maxsum) return fail(ctx, TB_ERR_INVALID, "ops_stride smaller than max(len1+len2)");
+  if (int rc = check_range(ctx, all, sc)) return rc;
+
+  tb::GotohBatch B{};
+  B.match = sc.match; B.mismatch = sc.mismatch; B.go = sc.gap_open; B.ge = sc.gap_extend;
+  B.hfree = ac.h_free != 0; B.vfree = ac.v_free != 0;
+  B.order = nullptr;
+
+  if (batch->mem == TB_MEM_DEVICE) {
+    Lane& L = ctx->lanes[0];
+    Plan plan;
+    if (int rc = make_plan(ctx, mode, traceback, all, np, sc, &plan)) return rc;
+    if (int rc = reserve_scratch(ctx, L, plan)) return rc;
+    TB_CUDA(ctx, L.status.reserve(np));
+    B.a_base = batch->a1.base; B.a_off = batch->a1.off; B.a_len = batch->a1.len;
+    B.b_base = batch->a2.base; B.b_off = batch->a2.off; B.b_len = batch->a2.len;
+    B.scores = res->scores; B.ops = res->ops; B.ops_stride = res->ops_stride; B.ops_len = res->ops_len;
+    B.status = L.status.as<uint8_t>(); B.npairs = (int)np;
+    if (int rc = enqueue_gotoh(ctx, L, mode, traceback, B, plan)) return rc;
+    TB_CUDA(ctx, cudaStreamSynchronize(L.stream));
+    return collect_timing(ctx, L);
+  }
+
+  // ---- TB_MEM_HOST: chunked, double-buffered H2D -> kernels -> D2H on two streams ----
+  Plan plan;
+  if (int rc = make_plan(ctx, mode, traceback, all, np, sc, &plan)) return rc;
+  size_t chunk = std::max<size_t>(std::min<size_t>(np, 2 * (size_t)plan.slots), std::min<size_t>(16384, (np + 7) / 8));
+  {  // keep a chunk's staged inputs around <= 768 MiB
+    const double per_pair = (double)item_elems_a(mode, all.maxm) * elem_size_a(mode) + (double)item_elems_b(mode, all.maxn) * elem_size_b(mode) +
+                            (traceback ? (double)res->ops_stride : 0.0);
+    const size_t cap = (size_t)std::max(1.0, (768.0 * 1024 * 1024) / std::max(per_pair, 1.0));
+    chunk = std::max<size_t>(1, std::min(chunk, cap));
+  }
+  const size_t esa = elem_size_a(mode), esb = elem_size_b(mode);
+  int rc_all = TB_OK;
+  size_t nchunks = (np + chunk - 1) / chunk;
+  for (size_t ci = 0; ci < nchunks && rc_all == TB_OK; ++ci) {
+    Lane& L = ctx->lanes[ci & 1];
+    TB_CUDA(ctx, cudaStreamSynchronize(L.stream));        // lane's previous chunk (ci-2) is done; its buffers are free
+    if (int rc = collect_timing(ctx, L)) return rc;
+    const size_t p0 = ci * chunk, cn = std::min(chunk, np - p0);
+    // extents of this chunk inside the caller's arenas
+    long long amin = LLONG_MAX, amax = LLONG_MIN, bmin = LLONG_MAX, bmax = LLONG_MIN;
+    for (size_t i = p0; i < p0 + cn; ++i) {
+      const long long ao = batch->a1.off[i], bo = batch->a2.off[i];
+      if (ao < 0 || bo < 0) return fail(ctx, TB_ERR_INVALID, "negative arena offset");
+      amin = std::min(amin, ao); amax = std::max(amax, ao + item_elems_a(mode, l1[i]));
+      bmin = std::min(bmin, bo); bmax = std::max(bmax, bo + item_elems_b(mode, l2[i]));
+    }
+    const size_t abytes = (size_t)(amax - amin) * esa, bbytes = (size_t)(bmax - bmin) * esb;
+    Shape sh;
+    accumulate(sh, l1 + p0, l2 + p0, cn, mode == tb::kModePS);
+    Plan cp;
+    if (int rc = make_plan(ctx, mode, traceback, sh, cn, sc, &cp)) return rc;
+    if (int rc = reserve_scratch(ctx, L, cp)) return rc;
+    TB_CUDA(ctx, L.a.reserve(abytes + 16)); TB_CUDA(ctx, L.b.reserve(bbytes + 16));
+    TB_CUDA(ctx, L.a_off.reserve(cn * 8)); TB_CUDA(ctx, L.b_off.reserve(cn * 8));
+    TB_CUDA(ctx, L.a_len.reserve(cn * 4)); TB_CUDA(ctx, L.b_len.reserve(cn * 4));
+    TB_CUDA(ctx, L.scores.reserve(cn * 4)); TB_CUDA(ctx, L.status.reserve(cn));
+    if (traceback) { TB_CUDA(ctx, L.ops.reserve(cn * (size_t)res->ops_stride)); TB_CUDA(ctx, L.ops_len.reserve(cn * 4)); }
+    TB_CUDA(ctx, L.meta.reserve(cn * 16));
+    int64_t* hoff = static_cast<int64_t*>(L.meta.p);
+    for (size_t i = 0; i < cn; ++i) { hoff[i] = batch->a1.off[p0 + i] - amin; hoff[cn + i] = batch->a2.off[p0 + i] - bmin; }
+
+    TB_CUDA(ctx, cudaMemcpyAsync(L.a.p, (const char*)batch->a1.base + (size_t)amin * esa, abytes, cudaMemcpyHostToDevice, L.stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(L.b.p, (const char*)batch->a2.base + (size_t)bmin * esb, bbytes, cudaMemcpyHostToDevice, L.stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(L.a_off.p, hoff, cn * 8, cudaMemcpyHostToDevice, L.stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(L.b_off.p, hoff + cn, cn * 8, cudaMemcpyHostToDevice, L.stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(L.a_len.p, l1 + p0, cn * 4, cudaMemcpyHostToDevice, L.stream));
+    TB_CUDA(ctx, cudaMemcpyAsync(L.b_len.p, l2 + p0, cn * 4, cudaMemcpyHostToDevice, L.stream));
+    ctx->h2d += abytes + bbytes + cn * 24;
+
+    tb::GotohBatch C = B;
+    C.a_base = L.a.p; C.a_off = L.a_off.as<int64_t>(); C.a_len = L.a_len.as<int32_t>();
+    C.b_base = L.b.p; C.b_off = L.b_off.as<int64_t>(); C.b_len = L.b_len.as<int32_t>();
+    C.scores = L.scores.as<int32_t>(); C.ops = traceback ? L.ops.as<uint8_t>() : nullptr;
+    C.ops_stride = res->ops_stride; C.ops_len = traceback ? L.ops_len.as<int32_t>() : nullptr;
+    C.status = L.status.as<uint8_t>(); C.npairs = (int)cn;
+    if (int rc = enqueue_gotoh(ctx, L, mode, traceback, C, cp)) return rc;
+
+    TB_CUDA(ctx, cudaMemcpyAsync(res->scores + p0, L.scores.p, cn * 4, cudaMemcpyDeviceToHost, L.stream));
+    ctx->d2h += cn * 4;
+    if (traceback) {
+      TB_CUDA(ctx, cudaMemcpyAsync(res->ops + p0 * (size_t)res->ops_stride, L.ops.p, cn * (size_t)res->ops_stride, cudaMemcpyDeviceToHost, L.stream));
+      TB_CUDA(ctx, cudaMemcpyAsync(res->ops_len + p0, L.ops_len.p, cn * 4, cudaMemcpyDeviceToHost, L.stream));
+      ctx->d2h += cn * (size_t)res->ops_stride + cn * 4;
+    }
+  }
+  for (int i = 0; i < 2; ++i) {
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->lanes[i].stream));
+    if (int rc = collect_timing(ctx, ctx->lanes[i])) return rc;
+  }
+  return rc_all;
+}
+
+char cons_char(const float* p, int len, int pos) {
+  // reference src/align.h:254-270: first strict maximum over the six rows, compared in double; >= 4 prints 'N'
+  int best = 0;
+  double bv = p[pos];
+  for (int k = 1; k < 6; ++k) {
+    const double v = p[(size_t)k * len + pos];
+    if (v > bv) { bv = v; best = k; }
+  }
+  return best < 4 ? "ACGT"[best] : 'N';
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tb_version(void) { return "tracy_b200 0.1 (hot path of tracy v0.9.1; sm_100a)"; }
+
+const char* tb_strerror(int code) {
+  switch (code) {
+    case TB_OK: return "ok";
+    case TB_ERR_INVALID: return "invalid argument";
+    case TB_ERR_CUDA: return "CUDA error / no usable device";
+    case TB_ERR_NOMEM: return "out of memory";
+    case TB_ERR_UNSUPPORTED: return "unsupported sizes or score values";
+  }
+  return "unknown error";
+}
+const char* tb_last_error(const tb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int tb_ctx_create(tb_ctx** out, int device) {
+  if (!out) return TB_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return TB_ERR_CUDA; }
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return TB_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return TB_ERR_CUDA; }
+  if (prop.major != 10) return TB_ERR_CUDA;   // sm_100a SASS only; there is no other code path
+  tb_ctx* c = new (std::nothrow) tb_ctx();
+  if (!c) return TB_ERR_NOMEM;
+  c->device = device;
+  c->sms = prop.multiProcessorCount;
+  for (int i = 0; i < 2; ++i) {
+    Lane& L = c->lanes[i];
+    if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&L.k0) != cudaSuccess ||
+        cudaEventCreate(&L.k1) != cudaSuccess || cudaEventCreate(&L.k2) != cudaSuccess) {
+      cudaGetLastError();
+      tb_ctx_destroy(c);
+      return TB_ERR_CUDA;
+    }
+  }
+  *out = c;
+  return TB_OK;
+}
+
+void tb_ctx_destroy(tb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < 2; ++i) {
+    Lane& L = c->lanes[i];
+    if (L.stream) cudaStreamSynchronize(L.stream);
+    DevBuf* bufs[] = {&L.a, &L.b, &L.a_off, &L.b_off, &L.a_len, &L.b_len, &L.scores, &L.ops, &L.ops_len, &L.status, &L.counter, &L.ptr, &L.rowbuf, &L.opsrev};
+    for (DevBuf* b : bufs) b->release();
+    L.meta.release();
+    if (L.k0) cudaEventDestroy(L.k0);
+    if (L.k1) cudaEventDestroy(L.k1);
+    if (L.k2) cudaEventDestroy(L.k2);
+    if (L.stream) cudaStreamDestroy(L.stream);
+  }
+  delete c;
+}
+
+int tb_host_alloc(tb_ctx* ctx, void** out, size_t bytes) {
+  if (!ctx || !out) return TB_ERR_INVALID;
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, TB_ERR_NOMEM, "cudaHostAlloc failed"); }
+  return TB_OK;
+}
+int tb_host_free(tb_ctx* ctx, void* p) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (p) TB_CUDA(ctx, cudaFreeHost(p));
+  return TB_OK;
+}
+int tb_ctx_set_scratch_limit(tb_ctx* ctx, size_t bytes) {
+  if (!ctx) return TB_ERR_INVALID;
+  ctx->scratch_limit = bytes;
+  return TB_OK;
+}
+int tb_ctx_stats(const tb_ctx* ctx, uint64_t* k, uint64_t* h2d, uint64_t* d2h) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (k) *k = ctx->launches;
+  if (h2d) *h2d = ctx->h2d;
+  if (d2h) *d2h = ctx->d2h;
+  return TB_OK;
+}
+int tb_ctx_last_kernel_ms(const tb_ctx* ctx, float* fast_ms, float* general_ms, float* sweep_ms) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (fast_ms) *fast_ms = ctx->last_fast_ms;
+  if (general_ms) *general_ms = ctx->last_general_ms;
+  if (sweep_ms) *sweep_ms = ctx->last_sweep_ms;
+  return TB_OK;
+}
+
+int tb_gotoh_ps(tb_ctx* ctx, const tb_batch* b, tb_score sc, tb_align_config ac, tb_result* r) { return run_gotoh(ctx, tb::kModePS, b, sc, ac, r); }
+int tb_gotoh_pp(tb_ctx* ctx, const tb_batch* b, tb_score sc, tb_align_config ac, tb_result* r) { return run_gotoh(ctx, tb::kModePP, b, sc, ac, r); }
+int tb_gotoh_ss(tb_ctx* ctx, const tb_batch* b, tb_score sc, tb_align_config ac, tb_result* r) { return run_gotoh(ctx, tb::kModeSS, b, sc, ac, r); }
+
+int tb_rows_from_ops(int kind, const void* a1, int32_t len1, const void* a2, int32_t len2, const uint8_t* ops, int32_t L, char* row0, char* row1) {
+  if (!ops || !row0 || !row1 || L < 0 || kind < 0 || kind > 2) return TB_ERR_INVALID;
+  int r = 0, c = 0;
+  for (int j = 0; j < L; ++j) {
+    char x = '-', y = '-';
+    if (ops[j] != 'h') {
+      if (r >= len1) return TB_ERR_INVALID;
+      x = kind == 1 ? ((const char*)a1)[r] : cons_char((const float*)a1, len1, r);
+      ++r;
+    }
+    if (ops[j] != 'v') {
+      if (c >= len2) return TB_ERR_INVALID;
+      if (kind == 0) y = cons_char((const float*)a2, len2, c);
+      else if (kind == 1) y = ((const char*)a2)[c];
+      else {   // one-hot profile of a sequence (src/align.h:121-136) seen through _profileConsChar
+        switch (((const char*)a2)[c]) {
+          case 'A': case 'a': y = 'A'; break;
+          case 'C': case 'c': y = 'C'; break;
+          case 'G': case 'g': y = 'G'; break;
+          case 'T': case 't': y = 'T'; break;
+          case 'N': case 'n': case '-': y = 'N'; break;
+          default: y = 'A'; break;   // all-zero column: no row exceeds p[0], index 0 wins
+        }
+      }
+      ++c;
+    }
+    row0[j] = x; row1[j] = y;
+  }
+  return TB_OK;
+}
+
+int tb_decompose_sweep(tb_ctx* ctx, const tb_sweep_batch* batch, tb_sweep_result* res) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (!batch || !res) return fail(ctx, TB_ERR_INVALID, "null batch/result");
+  ctx->last_sweep_ms = 0;
+  const size_t nt = batch->ntraces;
+  if (nt == 0) return TB_OK;
+  if (nt > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "ntraces too large");
+  if (!batch->refrow.base || !batch->refrow.off || !batch->refrow.len || !batch->primary.base || !batch->primary.off ||
+      !batch->primary.len || !batch->secondary_base || !batch->vi_end || !batch->align_index || !batch->var_index ||
+      !batch->ndel || !batch->nins || !res->fref || !res->fins || res->out_stride <= 0)
+    return fail(ctx, TB_ERR_INVALID, "null pointer in sweep batch/result");
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  Lane& L = ctx->lanes[0];
+  const int os = res->out_stride;
+  tb::SweepBatch S{};
+  S.out_stride = os;
+  if (batch->mem == TB_MEM_DEVICE) {
+    S.ref_base = (const char*)batch->refrow.base; S.ref_off = batch->refrow.off; S.ref_len = batch->refrow.len;
+    S.pri_base = (const char*)batch->primary.base; S.sec_base = batch->secondary_base; S.bc_off = batch->primary.off;
+    S.vi_end = batch->vi_end; S.align_index = batch->align_index; S.var_index = batch->var_index;
+    S.ndel = batch->ndel; S.nins = batch->nins;
+    S.fref = res->fref; S.fins = res->fins; S.grid = res->grid;
+    TB_CUDA(ctx, cudaEventRecord(L.k0, L.stream));
+    TB_CUDA(ctx, tb::launch_sweep(S, (int)nt, res->grid != nullptr, L.stream));
+    ctx->launches++;
+    TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(L.stream));
+    TB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_sweep_ms, L.k0, L.k1));
+    return TB_OK;
+  }
+  if (batch->mem != TB_MEM_HOST) return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST or TB_MEM_DEVICE");
+  // Host mode: strings are small (a few kB per trace); stage the whole batch in one go.
+  long long rmin = LLONG_MAX, rmax = LLONG_MIN, pmin = LLONG_MAX, pmax = LLONG_MIN;
+  for (size_t i = 0; i < nt; ++i) {
+    if (batch->refrow.len[i] < 0 || batch->primary.len[i] < 0 || batch->refrow.off[i] < 0 || batch->primary.off[i] < 0)
+      return fail(ctx, TB_ERR_INVALID, "negative offset/length");
+    if (batch->ndel[i] < 0 || batch->nins[i] < 0 || batch->ndel[i] > os || batch->nins[i] > os)
+      return fail(ctx, TB_ERR_INVALID, "ndel/nins outside [0, out_stride]");
+    rmin = std::min<long long>(rmin, batch->refrow.off[i]); rmax = std::max<long long>(rmax, batch->refrow.off[i] + batch->refrow.len[i]);
+    pmin = std::min<long long>(pmin, batch->primary.off[i]); pmax = std::max<long long>(pmax, batch->primary.off[i] + batch->primary.len[i]);
+  }
+  const size_t rbytes = (size_t)(rmax - rmin), pbytes = (size_t)(pmax - pmin);
+  // layout of the single staging buffer (device): ref | pri | sec | ref_off | bc_off | 6 x int32[nt]
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t o_ref = 0, o_pri = al(o_ref + rbytes), o_sec = al(o_pri + pbytes), o_roff = al(o_sec + pbytes),
+               o_boff = o_roff + nt * 8, o_i32 = o_boff + nt * 8, total = o_i32 + 6 * nt * 4;
+  TB_CUDA(ctx, L.a.reserve(total));
+  TB_CUDA(ctx, L.meta.reserve(nt * 16));
+  const size_t out_elems = nt * (size_t)os;
+  TB_CUDA(ctx, L.scores.reserve(2 * out_elems * 4));
+  if (res->grid) TB_CUDA(ctx, L.ops.reserve(out_elems * (size_t)os * 4));
+  char* d = L.a.as<char>();
+  int64_t* hoff = static_cast<int64_t*>(L.meta.p);
+  for (size_t i = 0; i < nt; ++i) { hoff[i] = batch->refrow.off[i] - rmin; hoff[nt + i] = batch->primary.off[i] - pmin; }
+  cudaStream_t st = L.stream;
+  TB_CUDA(ctx, cudaMemcpyAsync(d + o_ref, (const char*)batch->refrow.base + rmin, rbytes, cudaMemcpyHostToDevice, st));
+  TB_CUDA(ctx, cudaMemcpyAsync(d + o_pri, (const char*)batch->primary.base + pmin, pbytes, cudaMemcpyHostToDevice, st));
+  TB_CUDA(ctx, cudaMemcpyAsync(d + o_sec, batch->secondary_base + pmin, pbytes, cudaMemcpyHostToDevice, st));
+  TB_CUDA(ctx, cudaMemcpyAsync(d + o_roff, hoff, nt * 8, cudaMemcpyHostToDevice, st));
+  TB_CUDA(ctx, cudaMemcpyAsync(d + o_boff, hoff + nt, nt * 8, cudaMemcpyHostToDevice, st));
+  const int32_t* i32src[6] = {batch->refrow.len, batch->vi_end, batch->align_index, batch->var_index, batch->ndel, batch->nins};
+  for (int k = 0; k < 6; ++k) TB_CUDA(ctx, cudaMemcpyAsync(d + o_i32 + (size_t)k * nt * 4, i32src[k], nt * 4, cudaMemcpyHostToDevice, st));
+  ctx->h2d += rbytes + 2 * pbytes + nt * 16 + 6 * nt * 4;
+  S.ref_base = d + o_ref; S.pri_base = d + o_pri; S.sec_base = d + o_sec;
+  S.ref_off = (const int64_t*)(d + o_roff); S.bc_off = (const int64_t*)(d + o_boff);
+  const int32_t* i32 = (const int32_t*)(d + o_i32);
+  S.ref_len = i32; S.vi_end = i32 + nt; S.align_index = i32 + 2 * nt; S.var_index = i32 + 3 * nt; S.ndel = i32 + 4 * nt; S.nins = i32 + 5 * nt;
+  S.fref = L.scores.as<int32_t>(); S.fins = S.fref + out_elems; S.grid = res->grid ? L.ops.as<int32_t>() : nullptr;
+  TB_CUDA(ctx, cudaEventRecord(L.k0, st));
+  TB_CUDA(ctx, tb::launch_sweep(S, (int)nt, res->grid != nullptr, st));
+  ctx->launches++;
+  TB_CUDA(ctx, cudaEventRecord(L.k1, st));
+  TB_CUDA(ctx, cudaMemcpyAsync(res->fref, S.fref, out_elems * 4, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(ctx, cudaMemcpyAsync(res->fins, S.fins, out_elems * 4, cudaMemcpyDeviceToHost, st));
+  if (res->grid) TB_CUDA(ctx, cudaMemcpyAsync(res->grid, S.grid, out_elems * (size_t)os * 4, cudaMemcpyDeviceToHost, st));
+  ctx->d2h += 2 * out_elems * 4 + (res->grid ? out_elems * (size_t)os * 4 : 0);
+  TB_CUDA(ctx, cudaStreamSynchronize(st));
+  TB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_sweep_ms, L.k0, L.k1));
+  return TB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// Shared device-side definitions for the tracy_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tb {
+
+constexpr int kInf = 1000000;            // reference src/align.h:26,30
+constexpr int kRowsPerLane = 16;         // DP rows held in registers by one (virtual) lane
+constexpr unsigned kFull = 0xffffffffu;
+
+// Pointer nibble written per DP cell (4 bits, reference keeps four bitsets: src/gotoh.h:86-91,134-138).
+//   bit0 HOPEN  = reference bit1: H[r][c] was opened from S (open strictly better than extend)
+//   bit1 VOPEN  = reference bit2
+//   bit2 FROMH  = reference bit3: S[r][c] == H[r][c]
+//   bit3 VCAND  = S[r][c] == V[r][c] (general kernel) or V >= diagonal candidate (packed kernel); the walker
+//                 treats the cell as "from V" only when FROMH is clear, which makes both encodings equal to
+//                 reference bit4 (src/gotoh.h:135).
+enum : unsigned { kHOpen = 1u, kVOpen = 2u, kFromH = 4u, kVCand = 8u };
+
+enum : int { kModePS = 0, kModePP = 1, kModeSS = 2 };
+
+// Device view of one batch (all pointers are device pointers).
+struct GotohBatch {
+  const void* a_base; const int64_t* a_off; const int32_t* a_len;
+  const void* b_base; const int64_t* b_off; const int32_t* b_len;
+  int32_t* scores; uint8_t* ops; int64_t ops_stride; int32_t* ops_len;
+  const int32_t* order;     // optional processing order (largest first); nullptr = identity
+  uint8_t* status;          // per pair: 0 = pending, 1 = done (written by whichever kernel finished it)
+  int npairs;
+  int match, mismatch, go, ge;
+  int hfree, vfree;
+  // per-warp-slot scratch
+  unsigned long long* ptr_scratch; unsigned long long ptr_slot_words;  // packed pointer nibbles
+  int2* rowbuf; unsigned long long rowbuf_slot;                        // 2 x (maxn+1) band-boundary rows (S,V)
+  uint8_t* ops_scratch; unsigned long long ops_slot;                   // reversed traceback string
+  unsigned int* counter;                                               // work-queue head
+};
+
+// Device view of a decompose-sweep batch (sweep.cu).
+struct SweepBatch {
+  const char* ref_base; const int64_t* ref_off; const int32_t* ref_len;
+  const char* pri_base; const char* sec_base; const int64_t* bc_off;
+  const int32_t* vi_end; const int32_t* align_index; const int32_t* var_index;
+  const int32_t* ndel; const int32_t* nins;
+  int32_t* fref; int32_t* fins; int32_t* grid; int out_stride;
+};
+
+// reference src/align.h:121-136: A,C,G,T,N (case-insensitive) -> 0..4; '-' and everything else contribute
+// nothing to _score (row 5 is never read, src/align.h:113-114) -> class 5.
+__device__ __forceinline__ int base_class(unsigned char ch) {
+  switch (ch) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    case 'N': case 'n': return 4;
+    default: return 5;
+  }
+}
+
+// Substitution score of a trace-profile row against a one-hot reference column of class b
+// (reference src/align.h:112-116 specialised as in SURVEY appendix A.3): every k2 != b term is +-0 and
+// x*1.0f == x, so only the five k2 == b terms survive, accumulated in k1 order with separately rounded
+// multiply and add (no FMA: the reference build has none) and C truncation.
+__device__ __forceinline__ int sub_onehot(const float p[5], int b, float fmatch, float fmismatch) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int k1 = 0; k1 < 5; ++k1) acc = __fadd_rn(acc, __fmul_rn(p[k1], k1 == b ? fmatch : fmismatch));
+  return __float2int_rz(acc);
+}
+
+// General 5x5 profile-profile score, reference src/align.h:112-116 literally: ((p1*p2)*w) summed k1-outer.
+__device__ __forceinline__ int sub_profile(const float p1[5], const float p2[5], float fmatch, float fmismatch) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int k1 = 0; k1 < 5; ++k1)
+#pragma unroll
+    for (int k2 = 0; k2 < 5; ++k2)
+      acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(p1[k1], p2[k2]), k1 == k2 ? fmatch : fmismatch));
+  return __float2int_rz(acc);
+}
+
+// ---- pointer scratch layout -------------------------------------------------------------------------------
+// A band is nv*16 DP rows; virtual lane v owns rows band*nv*16 + 16v + 1 .. +16 and at step `st` works on column
+// c = st - v + 1 (a systolic skew), so one warp-step writes one contiguous 256 B (nv=32) or 512 B (nv=64) line.
+// Index of the 64-bit word holding the 16 nibbles of (band, st, v):
+__device__ __forceinline__ unsigned long long ptr_word_index(int nv, int T, int band, int st, int v) {
+  unsigned long long line = (unsigned long long)band * (unsigned)T + (unsigned)st;
+  return nv == 32 ? line * 32ull + (unsigned)v : line * 64ull + (unsigned)(v & 31) * 2u + (unsigned)(v >> 5);
+}
+
+// Warp-cooperative traceback (reference src/gotoh.h:144-167). All lanes run the state machine in lock-step; a
+// window of 32 consecutive steps of the current virtual lane is kept in registers (one 64-bit word per lane) so
+// that diagonal and horizontal runs cost one gather per <=32 cells instead of one dependent HBM read per cell.
+// Emits the reversed string into ops_rev and returns its length.
+__device__ __forceinline__ int walk_traceback(const unsigned long long* __restrict__ ptr, int nv, int T, int m, int n,
+                                              uint8_t* __restrict__ ops_rev, int lane) {
+  const int bh = nv * kRowsPerLane;
+  int r = m, c = n, state = 0, k = 0;
+  int wband = -1, wv = -1, wst0 = -(1 << 30);
+  unsigned wlo = 0, whi = 0;
+  unsigned mych = 0;
+  while (r > 0 || c > 0) {
+    unsigned op;
+    if (r == 0) { op = 'h'; --c; }          // row 0 is all 'h' (only FROMH is ever set there)
+    else if (c == 0) { op = 'v'; --r; }     // column 0 is all 'v'
+    else {
+      const int band = (r - 1) / bh, rr = (r - 1) - band * bh;
+      const int v = rr >> 4, i = rr & 15, st = c - 1 + v;
+      if (band != wband || v != wv || st > wst0 || st < wst0 - 31) {
+        wband = band; wv = v; wst0 = st;
+        const int s2 = st - lane;
+        unsigned long long w = 0;
+        if (s2 >= v) w = ptr[ptr_word_index(nv, T, band, s2, v)];
+        wlo = (unsigned)w; whi = (unsigned)(w >> 32);
+      }
+      const int src = wst0 - st;
+      const unsigned lo = __shfl_sync(kFull, wlo, src), hi = __shfl_sync(kFull, whi, src);
+      const unsigned nib = ((i < 8 ? lo : hi) >> (4 * (i & 7))) & 15u;
+      if (state == 0) {
+        if (nib & kFromH) { state = 1; continue; }
+        if (nib & kVCand) { state = 2; continue; }
+        op = 's'; --r; --c;
+      } else if (state == 1) {
+        if (nib & kHOpen) state = 0;
+        op = 'h'; --c;
+      } else {
+        if (nib & kVOpen) state = 0;
+        op = 'v'; --r;
+      }
+    }
+    if (lane == (k & 31)) mych = op;
+    ++k;
+    if ((k & 31) == 0) ops_rev[k - 32 + lane] = (uint8_t)mych;
+  }
+  if ((k & 31) != 0 && lane < (k & 31)) ops_rev[(k & ~31) + lane] = (uint8_t)mych;
+  return k;
+}
+
+}  // namespace tb

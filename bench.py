@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS of the batched Gotoh fill + traceback on synthetic 1 kb x 4 kb trace/window pairs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--pairs P]
+
+One "step" = one pass of the hot path (tb_gotoh_ps with traceback, reference src/gotoh.h:71-174) over one batch of
+P pairs per GPU (BASELINE.json configs[1]: P = 100 000, m = 1000, n = 4000, scores 3/-5/-10/-4, AlignConfig<true,false>).
+Prints ONE JSON line (rank 0):
+  value        whole-job GCUPS (sum of m*n over all ranks' pairs / max-over-ranks device time), inputs resident in HBM
+  e2e          same metric through the public host-buffer call (Context.gotoh / tb_gotoh_ps with TB_MEM_HOST): pinned
+               host inputs -> H2D -> kernels -> D2H of scores + traceback strings, all inside the timed region
+  roofline     dominant kernel: algorithmic bytes (0.5075 B/cell) / CUDA-event kernel time vs measured HBM peak
+  cpu_baseline tracy's own gotoh() (oracle/_ref, unmodified reference headers) on this box's host cores, bounded sample
+`--impl reference` times only that CPU path (rank 0; other ranks exit 0).
+For N > 1 launch under torchrun (one rank per GPU); pairs are independent so ranks shard the batch with no data-path
+collective; the timed step ends with the one all-gather of scores the north star names.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "GCUPS (Gotoh DP cells/s), batched fill + traceback, 1 kb trace profiles x 4 kb reference windows"
+SC = (3, -5, -10, -4)
+HFREE, VFREE = 1, 0
+
+
+def algorithmic_bytes_per_pair(m, n):
+    """SURVEY.md section 8d / DESIGN.md: inputs + 4-bit pointer stream written once + pointers read on the walk + ops + score."""
+    return 16 * m + n + ((m + 1) * (n + 1) + 1) // 2 + (m + n) // 2 + (m + n) + 4
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def gen_batch_into(prof_out, win_out, m, n, seed, chunk=5000):
+    """Config-2 generator (tracy_b200/synth.py) written chunk-wise into preallocated (pinned) host arrays."""
+    from tracy_b200 import synth
+    P = prof_out.shape[0]
+    for lo in range(0, P, chunk):
+        hi = min(P, lo + chunk)
+        p, w = synth.align_batch(hi - lo, m, n, seed=seed + 7919 * (lo // chunk))
+        prof_out[lo:hi] = p
+        win_out[lo:hi] = w
+
+
+# ---- the CPU reference arm ------------------------------------------------------------------------------------
+def cpu_reference_gcups(m, n, pairs_per_thread, threads, repeats=1, seed=4242):
+    """tracy's gotoh() (fill + bitsets + traceback + _createAlignment) on `threads` host threads, each running the
+    reference single-threaded path over its own pairs (ctypes releases the GIL). Returns (gcups, seconds, kind)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import loader
+    from tracy_b200 import synth
+    impl, kind = loader.ref(), "reference"
+    if impl is None:
+        impl, kind = loader.port(), "port"
+    total = pairs_per_thread * threads
+    prof, win = synth.align_batch(total, m, n, seed=seed)
+    parts = [(np.ascontiguousarray(prof[t * pairs_per_thread:(t + 1) * pairs_per_thread]),
+              bytes(np.ascontiguousarray(win[t * pairs_per_thread:(t + 1) * pairs_per_thread]).reshape(-1))) for t in range(threads)]
+
+    def work(part):
+        cells, _ = impl.bench_gotoh_ps(part[0], part[1], m, n, HFREE, VFREE, SC, True)
+        return cells
+
+    best = None
+    with ThreadPoolExecutor(threads) as ex:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            cells = sum(ex.map(work, parts))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return cells / best / 1e9, best, kind, total
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, args.cpu_threads or cores))
+    ppt = args.cpu_pairs_per_thread
+    for _ in range(args.warmup and 1):
+        cpu_reference_gcups(args.m, args.n, 1, threads)
+    vals, secs = [], []
+    kind = total = None
+    for _ in range(args.steps):
+        g, s, kind, total = cpu_reference_gcups(args.m, args.n, ppt, threads)
+        vals.append(g); secs.append(s)
+    v = float(np.mean(vals))
+    sample = f"{total} pairs of {args.m}x{args.n} per step ({ppt} per thread x {threads} threads), gotoh() with traceback + _createAlignment"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(secs) * 1e3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"batched Gotoh fill+traceback (tb_gotoh_ps): {args.pairs} pairs/GPU of {args.m} bp trace profile x {args.n} bp reference window "
+                        f"(BASELINE.json configs[1]), scores 3/-5/-10/-4, AlignConfig<true,false>",
+            "pairs_per_gpu": args.pairs, "m": args.m, "n": args.n, "traceback": True, "sharding": f"{world} x independent pair ranges, no data-path collective"
+            + ("; one all-gather of scores per step" if world > 1 else ""),
+            "l2": "inputs (2.8 GB/GPU) and the pointer scratch (GBs) exceed the 126 MB L2; no explicit flush"}
+
+
+# ---- the B200 arm ----------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import tracy_b200
+    from tracy_b200 import AlignConfig, DnaScore
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; tracy_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = tracy_b200.Context(local_rank)
+    P, m, n = args.pairs, args.m, args.n
+    stride = (m + n + 15) // 16 * 16
+    sc, ac = DnaScore(*SC), AlignConfig(bool(HFREE), bool(VFREE))
+
+    # pinned host staging (inputs and outputs of the e2e call)
+    h_prof = torch.empty((P, 6, m), dtype=torch.float32, pin_memory=True)
+    h_win = torch.empty((P, n), dtype=torch.uint8, pin_memory=True)
+    h_scores = torch.empty(P, dtype=torch.int32, pin_memory=True)
+    h_ops = torch.empty((P, stride), dtype=torch.uint8, pin_memory=True)
+    h_len = torch.empty(P, dtype=torch.int32, pin_memory=True)
+    t0 = time.perf_counter()
+    gen_batch_into(h_prof.numpy(), h_win.numpy(), m, n, seed=44 + 1000003 * rank)
+    gen_s = time.perf_counter() - t0
+    a1 = tracy_b200.uniform_profiles(h_prof.numpy())
+    a2 = tracy_b200.uniform_seqs(h_win.numpy())
+
+    # device-resident copies for the `value` leg
+    dev = torch.device("cuda", local_rank)
+    d_prof, d_win = h_prof.to(dev), h_win.to(dev)
+    d_aoff, d_alen = torch.from_numpy(a1.off).to(dev), torch.from_numpy(a1.len).to(dev)
+    d_boff, d_blen = torch.from_numpy(a2.off).to(dev), torch.from_numpy(a2.len).to(dev)
+    d_scores = torch.zeros(P, dtype=torch.int32, device=dev)
+    d_ops = torch.zeros((P, stride), dtype=torch.uint8, device=dev)
+    d_len = torch.zeros(P, dtype=torch.int32, device=dev)
+    counts = [P] * world
+    g_scores = torch.empty(P * world, dtype=torch.int32, device=dev) if world > 1 else None
+    if world > 1:   # the one broadcast the north star names: shared reference bytes, once, outside the steps
+        ref_blob = d_win[: min(P, 1024)].clone()
+        dist.broadcast(ref_blob, src=0)
+
+    def device_step():
+        ctx.gotoh_device("ps", d_prof.data_ptr(), d_aoff.data_ptr(), d_alen.data_ptr(), d_win.data_ptr(), d_boff.data_ptr(), d_blen.data_ptr(), P,
+                         d_scores.data_ptr(), d_ops.data_ptr(), stride, d_len.data_ptr(), sc, ac)
+        ms = ctx.last_call_ms()
+        k = ctx.last_kernel_ms()
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_gather_into_tensor(g_scores, d_scores)
+            e1.record()
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms, k
+
+    def host_step():
+        ctx.gotoh("ps", a1, a2, sc, ac, traceback=True, out=(h_scores.numpy(), h_ops.numpy(), h_len.numpy()))
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(args.warmup):
+        device_step()
+    st0 = ctx.stats()
+    sampler = ClockSampler(local_rank)
+    sync()
+    sampler.start()
+    w0 = time.perf_counter()
+    dev_ms, kern = 0.0, {"packed_ms": 0.0, "general_ms": 0.0}
+    for _ in range(args.steps):
+        ms, k = device_step()
+        dev_ms += ms
+        for key in kern:
+            kern[key] += k[key]
+    sync()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    st1 = ctx.stats()
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+
+    # ---- e2e: host buffers through the public call ----
+    for _ in range(min(args.warmup, 2)):
+        host_step()
+    se0 = ctx.stats()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
+    sync()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    se1 = ctx.stats()
+
+    # spot parity inside the bench: device leg and host leg agree, and a few pairs match the CPU oracle
+    assert torch.equal(d_scores.cpu(), h_scores), "device-resident and host-buffer legs disagree"
+    chk = {"pairs_checked_vs_oracle": 0}
+    if rank == 0:
+        from oracle import loader
+        port = loader.port()
+        ops_h, len_h = h_ops.numpy(), h_len.numpy()
+        for i in range(0, P, max(1, P // 4))[:4]:
+            ws, wops = port.gotoh_ps(h_prof.numpy()[i], bytes(h_win.numpy()[i]), HFREE, VFREE, SC)
+            assert int(h_scores[i]) == ws and bytes(ops_h[i, : len_h[i]]) == wops, f"bench parity: pair {i} differs from the oracle"
+            chk["pairs_checked_vs_oracle"] += 1
+    checksum = int(h_scores.numpy().astype(np.int64).sum())
+
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, e2e_ms = t.tolist()
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cells_step = float(P) * m * n * world
+    value = cells_step * args.steps / (dev_ms * 1e-3) / 1e9
+    e2e_val = cells_step * args.steps / (e2e_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peaks()
+    dom = "packed_ms" if kern["packed_ms"] >= kern["general_ms"] else "general_ms"
+    dom_name = {"packed_ms": "gotoh_packed_kernel<traceback>", "general_ms": "gotoh_general_kernel<PS,traceback>"}[dom]
+    k_ms = kern[dom] / args.steps
+    bytes_launch = float(algorithmic_bytes_per_pair(m, n)) * P
+    achieved = bytes_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(float(P) * m * n),
+            "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": bytes_launch,
+            "note": "integer DP: the binding limit is the INT32 ALU issue rate (DESIGN.md), HBM fraction is reported as the contract asks"}
+    out = {
+        "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": workload_config(args, world),
+        "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": (se1["h2d_bytes"] - se0["h2d_bytes"]) // args.steps, "d2h_bytes_per_step": (se1["d2h_bytes"] - se0["d2h_bytes"]) // args.steps},
+        "gpu_launches": launches, "roofline": roof, "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
+        "kernel_ms": {k: v / args.steps for k, v in kern.items()}, "parity": dict(chk, score_checksum=checksum), "gen_seconds": gen_s,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        threads = max(1, min(cores, args.cpu_threads or cores))
+        g, s, kind, total = cpu_reference_gcups(m, n, args.cpu_pairs_per_thread, threads)
+        out["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind, "seconds": s,
+                               "sample": f"{total} pairs of {m}x{n} ({args.cpu_pairs_per_thread} per thread x {threads} threads), tracy gotoh() with traceback"}
+    print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic(cells_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json holds bytes per DP cell of that capture; scaled here to this launch's cells), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["dram_bytes_per_cell"]) * cells_per_launch
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=100000, help="pairs per GPU per step")
+    ap.add_argument("--m", type=int, default=1000)
+    ap.add_argument("--n", type=int, default=4000)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--cpu-pairs-per-thread", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

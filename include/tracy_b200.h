@@ -91,6 +91,10 @@ int tb_ctx_stats(const tb_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_byt
  * context: the packed 16x2 Gotoh kernel, the general int32 Gotoh kernel, the sweep kernel. Any pointer may be NULL. */
 int tb_ctx_last_kernel_ms(const tb_ctx* ctx, float* packed_ms, float* general_ms, float* sweep_ms);
 
+/* Device time (CUDA events on the launching stream) of the whole most recent TB_MEM_DEVICE tb_gotoh_* call: queue reset,
+ * kernels and traceback, first enqueue to last. 0 for TB_MEM_HOST calls (two streams overlap there; use a host clock). */
+int tb_ctx_last_call_ms(const tb_ctx* ctx, float* device_ms);
+
 /* ---- gotohScore / gotoh ---------------------------------------------------------------------------------
  * _ps : a1 = trace profile float[6][m], a2 = reference SEQUENCE. Semantics are those of the reference when it
  *       aligns against _createProfile(std::string) (src/align.h:121-136), as src/sage.h:233-258,

@@ -144,6 +144,11 @@ class Context:
         self._check(self._lib.tb_ctx_last_kernel_ms(self._h, C.byref(p), C.byref(g), C.byref(s)))
         return {"packed_ms": p.value, "general_ms": g.value, "sweep_ms": s.value}
 
+    def last_call_ms(self):
+        v = C.c_float()
+        self._check(self._lib.tb_ctx_last_call_ms(self._h, C.byref(v)))
+        return v.value
+
     # ---- gotoh / gotohScore, batched -------------------------------------------------------------------
     def _fn(self, kind):
         return {PS: self._lib.tb_gotoh_ps, PP: self._lib.tb_gotoh_pp, SS: self._lib.tb_gotoh_ss}[kind]

@@ -58,7 +58,7 @@ struct PinBuf {
 
 struct Lane {   // one in-flight chunk of a TB_MEM_HOST batch
   cudaStream_t stream = nullptr;
-  cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr;
+  cudaEvent_t c0 = nullptr, k0 = nullptr, k1 = nullptr, k2 = nullptr;   // c0: start of a device-mode call; k*: kernel brackets
   DevBuf a, b, a_off, b_off, a_len, b_len, scores, ops, ops_len, status, counter;
   DevBuf ptr, rowbuf, opsrev;
   PinBuf meta;
@@ -74,7 +74,7 @@ struct tb_ctx {
   std::string err;
   Lane lanes[2];
   uint64_t launches = 0, h2d = 0, d2h = 0;
-  float last_fast_ms = 0, last_general_ms = 0, last_sweep_ms = 0;
+  float last_fast_ms = 0, last_general_ms = 0, last_sweep_ms = 0, last_call_ms = 0;
   std::vector<int32_t> tmp_len1, tmp_len2;
 };
 
@@ -179,6 +179,7 @@ int enqueue_gotoh(tb_ctx* ctx, Lane& L, int mode, bool traceback, tb::GotohBatch
   B.rowbuf = L.rowbuf.as<int2>(); B.rowbuf_slot = p.rowbuf_elems;
   B.ops_scratch = L.opsrev.as<uint8_t>(); B.ops_slot = p.ops_bytes;
   unsigned int* counters = L.counter.as<unsigned int>();
+  TB_CUDA(ctx, cudaEventRecord(L.c0, L.stream));
   TB_CUDA(ctx, cudaMemsetAsync(counters, 0, 64, L.stream));
   TB_CUDA(ctx, cudaMemsetAsync(B.status, 0, (size_t)B.npairs, L.stream));
   L.timed = L.timed2 = false;
@@ -224,7 +225,7 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   if (!ctx) return TB_ERR_INVALID;
   if (!batch || !res) return fail(ctx, TB_ERR_INVALID, "null batch/result");
   const size_t np = batch->npairs;
-  ctx->last_fast_ms = ctx->last_general_ms = 0;
+  ctx->last_fast_ms = ctx->last_general_ms = ctx->last_call_ms = 0;
   if (np == 0) return TB_OK;
   if (np > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "npairs too large");
   if (!batch->a1.base || !batch->a1.off || !batch->a1.len || !batch->a2.base || !batch->a2.off || !batch->a2.len || !res->scores)
@@ -267,6 +268,7 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     B.status = L.status.as<uint8_t>(); B.npairs = (int)np;
     if (int rc = enqueue_gotoh(ctx, L, mode, traceback, B, plan)) return rc;
     TB_CUDA(ctx, cudaStreamSynchronize(L.stream));
+    TB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_call_ms, L.c0, L.k2));
     return collect_timing(ctx, L);
   }
 
@@ -387,7 +389,8 @@ int tb_ctx_create(tb_ctx** out, int device) {
   c->sms = prop.multiProcessorCount;
   for (int i = 0; i < 2; ++i) {
     Lane& L = c->lanes[i];
-    if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&L.k0) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&L.c0) != cudaSuccess ||
+        cudaEventCreate(&L.k0) != cudaSuccess ||
         cudaEventCreate(&L.k1) != cudaSuccess || cudaEventCreate(&L.k2) != cudaSuccess) {
       cudaGetLastError();
       tb_ctx_destroy(c);
@@ -407,6 +410,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     DevBuf* bufs[] = {&L.a, &L.b, &L.a_off, &L.b_off, &L.a_len, &L.b_len, &L.scores, &L.ops, &L.ops_len, &L.status, &L.counter, &L.ptr, &L.rowbuf, &L.opsrev};
     for (DevBuf* b : bufs) b->release();
     L.meta.release();
+    if (L.c0) cudaEventDestroy(L.c0);
     if (L.k0) cudaEventDestroy(L.k0);
     if (L.k1) cudaEventDestroy(L.k1);
     if (L.k2) cudaEventDestroy(L.k2);
@@ -444,6 +448,12 @@ int tb_ctx_last_kernel_ms(const tb_ctx* ctx, float* fast_ms, float* general_ms, 
   if (fast_ms) *fast_ms = ctx->last_fast_ms;
   if (general_ms) *general_ms = ctx->last_general_ms;
   if (sweep_ms) *sweep_ms = ctx->last_sweep_ms;
+  return TB_OK;
+}
+
+int tb_ctx_last_call_ms(const tb_ctx* ctx, float* device_ms) {
+  if (!ctx || !device_ms) return TB_ERR_INVALID;
+  *device_ms = ctx->last_call_ms;
   return TB_OK;
 }
 

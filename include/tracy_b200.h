@@ -95,6 +95,10 @@ int tb_ctx_last_kernel_ms(const tb_ctx* ctx, float* packed_ms, float* general_ms
  * kernels and traceback, first enqueue to last. 0 for TB_MEM_HOST calls (two streams overlap there; use a host clock). */
 int tb_ctx_last_call_ms(const tb_ctx* ctx, float* device_ms);
 
+/* Number of pairs of the most recent tb_gotoh_ps call that the packed 16x2 kernel completed; the rest (shapes or score
+ * ranges outside its exact range) went through the general int32 kernel. Results are identical either way. */
+int tb_ctx_last_packed_pairs(const tb_ctx* ctx, uint64_t* pairs);
+
 /* ---- gotohScore / gotoh ---------------------------------------------------------------------------------
  * _ps : a1 = trace profile float[6][m], a2 = reference SEQUENCE. Semantics are those of the reference when it
  *       aligns against _createProfile(std::string) (src/align.h:121-136), as src/sage.h:233-258,

@@ -1,0 +1,115 @@
+"""GPU parity tests of the packed 16x2 kernel (gotoh_packed.cu): bit-exact against the oracle and against the general
+int32 kernel (TRACY_B200_NO_PACKED=1 disables the packed launch), over the shapes that stress its layout: one and two
+half-bands, several 1024-row passes, windows shorter than the 32-column half-band lag, all end-gap configurations,
+profiles with exact ties and MSA-style columns, reference strings with N / lower case / foreign characters, and
+pairs that must fall through to the general kernel (score range too wide for 15-bit fields)."""
+import os
+
+import numpy as np
+import pytest
+
+import tracy_b200
+from oracle import loader
+from tracy_b200 import AlignConfig, DnaScore, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(ctx, A, Bs, sc, ac, traceback=True):
+    os.environ.pop("TRACY_B200_NO_PACKED", None)
+    r1 = ctx.gotoh("ps", A, Bs, DnaScore(*sc), ac, traceback=traceback)
+    packed = ctx.last_packed_pairs()
+    os.environ["TRACY_B200_NO_PACKED"] = "1"
+    try:
+        r2 = ctx.gotoh("ps", A, Bs, DnaScore(*sc), ac, traceback=traceback)
+        assert ctx.last_packed_pairs() == 0
+    finally:
+        os.environ.pop("TRACY_B200_NO_PACKED", None)
+    assert np.array_equal(r1[0], r2[0])
+    if traceback:
+        assert np.array_equal(r1[2], r2[2])
+        for i in range(len(A)):
+            assert bytes(r1[1][i, : r1[2][i]]) == bytes(r2[1][i, : r2[2][i]]), i
+    return r1, packed
+
+
+SHAPES = [(1, 1), (1, 40), (5, 3), (16, 16), (17, 31), (33, 32), (100, 33), (511, 64), (512, 200), (513, 90), (600, 1),
+          (1000, 31), (1024, 300), (1025, 77), (1500, 260), (2049, 40), (300, 1500), (1000, 1300)]
+
+
+@pytest.mark.parametrize("hf,vf", [(1, 0), (0, 0), (1, 1), (0, 1)])
+def test_packed_shapes_vs_oracle(ctx, oracle_port, hf, vf):
+    rng = np.random.default_rng(100 + 2 * hf + vf)
+    sc = (3, -5, -10, -4)
+    A, Bs = [], []
+    for k, (m, n) in enumerate(SHAPES):
+        a = synth.random_profile(rng, m, ["trace", "ties", "msa"][k % 3])
+        cons = bytes(b"ACGT"[int(x)] for x in np.argmax(a[:4], axis=0))
+        b = synth.mutate_seq(rng, (cons * (n // m + 1))[:n], 0.05, 0.04) if k % 2 == 0 else synth.random_seq(rng, n, b"ACGTNacgtn-RY")
+        b = (b or b"A")
+        A.append(a); Bs.append(b)
+    (s, ops, ol), packed = _both(ctx, A, Bs, sc, AlignConfig(bool(hf), bool(vf)))
+    assert packed == len(A), "every one of these pairs is inside the packed kernel's exact range"
+    for i in range(len(A)):
+        ws, wops = oracle_port.gotoh_ps(A[i], Bs[i], hf, vf, sc)
+        assert (int(s[i]), bytes(ops[i, : ol[i]])) == (ws, wops), (SHAPES[i], hf, vf)
+    (s2, _, _), _ = _both(ctx, A, Bs, sc, AlignConfig(bool(hf), bool(vf)), traceback=False)
+    assert np.array_equal(s, s2)
+
+
+@pytest.mark.parametrize("sc", [(5, -4, -10, -1), (1, -1, -2, -1), (4, -4, -6, 0), (2, -7, 0, -3), (3, -5, -10, -4), (0, 0, 0, 0), (-1, -2, -3, -1)])
+def test_packed_scores_fuzz(ctx, oracle_port, sc):
+    rng = np.random.default_rng(abs(hash(sc)) % 1000)
+    A, Bs = [], []
+    for it in range(48):
+        m = int(rng.integers(1, 1200 if it % 8 == 0 else 150))
+        n = int(rng.integers(1, 900 if it % 8 == 0 else 200))
+        A.append(synth.random_profile(rng, m, ["ties", "trace", "msa"][it % 3]))
+        Bs.append(synth.random_seq(rng, n, b"ACGTN" if it % 5 == 0 else b"ACGT"))
+    for hf, vf in ((1, 0), (1, 1)):
+        (s, ops, ol), packed = _both(ctx, A, Bs, sc, AlignConfig(bool(hf), bool(vf)))
+        assert packed > 0
+        for i in range(len(A)):
+            ws, wops = oracle_port.gotoh_ps(A[i], Bs[i], hf, vf, sc)
+            assert (int(s[i]), bytes(ops[i, : ol[i]])) == (ws, wops), (sc, i)
+
+
+def test_packed_falls_through_when_range_too_wide(ctx, oracle_port):
+    """Unnormalised profile values (|sub| large) and big gap scores do not fit 15-bit fields: the packed kernel must
+    decline those pairs and the general kernel must finish them, in the same call."""
+    rng = np.random.default_rng(9)
+    A, Bs = [], []
+    for it in range(12):
+        a = synth.random_profile(rng, 200, "trace")
+        if it % 2 == 0:
+            a = a * np.float32(40.0)       # substitution scores up to +-200 -> 200 rows x 200 overflows 15 bits
+        A.append(a); Bs.append(synth.random_seq(rng, 300))
+    sc = (3, -5, -10, -4)
+    (s, ops, ol), packed = _both(ctx, A, Bs, sc, AlignConfig(True, False))
+    assert 0 < packed < len(A)
+    for i in range(len(A)):
+        ws, wops = oracle_port.gotoh_ps(A[i], Bs[i], 1, 0, sc)
+        assert (int(s[i]), bytes(ops[i, : ol[i]])) == (ws, wops), i
+    # gap scores beyond the packed kernel's host-side limits: whole batch on the general kernel
+    sc2 = (3, -5, -700, -4)
+    s2, ops2, ol2 = ctx.gotoh("ps", A[1::2], Bs[1::2], DnaScore(*sc2), AlignConfig(True, False))
+    assert ctx.last_packed_pairs() == 0
+    for i, (a, b) in enumerate(zip(A[1::2], Bs[1::2])):
+        assert (int(s2[i]), bytes(ops2[i, : ol2[i]])) == oracle_port.gotoh_ps(a, b, 1, 0, sc2)
+
+
+def test_packed_config2_full_shape(ctx, oracle_port):
+    """BASELINE configs[1] shape through the packed kernel: 256 pairs of 1000 x 4000, 8 exhaustively vs the oracle."""
+    m, n, N = 1000, 4000, 256
+    prof, win = synth.align_batch(N, m, n, seed=45)
+    a1, a2 = tracy_b200.uniform_profiles(prof), tracy_b200.uniform_seqs(win)
+    s, ops, ol = ctx.gotoh("ps", a1, a2, DnaScore(3, -5, -10, -4), AlignConfig(True, False))
+    assert ctx.last_packed_pairs() == N
+    for i in range(0, N, 32):
+        assert (int(s[i]), bytes(ops[i, : ol[i]])) == oracle_port.gotoh_ps(prof[i], bytes(win[i]), 1, 0, (3, -5, -10, -4)), i
+    os.environ["TRACY_B200_NO_PACKED"] = "1"
+    try:
+        s2, ops2, ol2 = ctx.gotoh("ps", a1, a2, DnaScore(3, -5, -10, -4), AlignConfig(True, False))
+    finally:
+        os.environ.pop("TRACY_B200_NO_PACKED", None)
+    assert np.array_equal(s, s2) and np.array_equal(ol, ol2) and np.array_equal(ops, ops2)

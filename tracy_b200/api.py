@@ -149,6 +149,11 @@ class Context:
         self._check(self._lib.tb_ctx_last_call_ms(self._h, C.byref(v)))
         return v.value
 
+    def last_packed_pairs(self):
+        v = C.c_uint64()
+        self._check(self._lib.tb_ctx_last_packed_pairs(self._h, C.byref(v)))
+        return v.value
+
     # ---- gotoh / gotohScore, batched -------------------------------------------------------------------
     def _fn(self, kind):
         return {PS: self._lib.tb_gotoh_ps, PP: self._lib.tb_gotoh_pp, SS: self._lib.tb_gotoh_ss}[kind]

@@ -61,7 +61,7 @@ struct Lane {   // one in-flight chunk of a TB_MEM_HOST batch
   cudaEvent_t c0 = nullptr, k0 = nullptr, k1 = nullptr, k2 = nullptr;   // c0: start of a device-mode call; k*: kernel brackets
   DevBuf a, b, a_off, b_off, a_len, b_len, scores, ops, ops_len, status, counter;
   DevBuf ptr, rowbuf, opsrev;
-  PinBuf meta;
+  PinBuf meta, cnt;
   bool timed = false, timed2 = false;
 };
 
@@ -75,6 +75,7 @@ struct tb_ctx {
   Lane lanes[2];
   uint64_t launches = 0, h2d = 0, d2h = 0;
   float last_fast_ms = 0, last_general_ms = 0, last_sweep_ms = 0, last_call_ms = 0;
+  uint64_t last_packed_pairs = 0;
   std::vector<int32_t> tmp_len1, tmp_len2;
 };
 
@@ -196,6 +197,8 @@ int enqueue_gotoh(tb_ctx* ctx, Lane& L, int mode, bool traceback, tb::GotohBatch
   ctx->launches++;
   TB_CUDA(ctx, cudaEventRecord(L.k2, L.stream));
   L.timed2 = true;
+  TB_CUDA(ctx, L.cnt.reserve(64));
+  TB_CUDA(ctx, cudaMemcpyAsync(L.cnt.p, counters, 64, cudaMemcpyDeviceToHost, L.stream));
   return TB_OK;
 }
 
@@ -203,6 +206,7 @@ int collect_timing(tb_ctx* ctx, Lane& L) {
   float ms = 0;
   if (L.timed) { TB_CUDA(ctx, cudaEventElapsedTime(&ms, L.k0, L.k1)); ctx->last_fast_ms += ms; }
   if (L.timed2) { TB_CUDA(ctx, cudaEventElapsedTime(&ms, L.k1, L.k2)); ctx->last_general_ms += ms; }
+  if (L.timed && L.cnt.p) ctx->last_packed_pairs += static_cast<const unsigned int*>(L.cnt.p)[1];
   L.timed = L.timed2 = false;
   return TB_OK;
 }
@@ -226,6 +230,7 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   if (!batch || !res) return fail(ctx, TB_ERR_INVALID, "null batch/result");
   const size_t np = batch->npairs;
   ctx->last_fast_ms = ctx->last_general_ms = ctx->last_call_ms = 0;
+  ctx->last_packed_pairs = 0;
   if (np == 0) return TB_OK;
   if (np > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "npairs too large");
   if (!batch->a1.base || !batch->a1.off || !batch->a1.len || !batch->a2.base || !batch->a2.off || !batch->a2.len || !res->scores)
@@ -409,7 +414,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     if (L.stream) cudaStreamSynchronize(L.stream);
     DevBuf* bufs[] = {&L.a, &L.b, &L.a_off, &L.b_off, &L.a_len, &L.b_len, &L.scores, &L.ops, &L.ops_len, &L.status, &L.counter, &L.ptr, &L.rowbuf, &L.opsrev};
     for (DevBuf* b : bufs) b->release();
-    L.meta.release();
+    L.meta.release(); L.cnt.release();
     if (L.c0) cudaEventDestroy(L.c0);
     if (L.k0) cudaEventDestroy(L.k0);
     if (L.k1) cudaEventDestroy(L.k1);
@@ -454,6 +459,12 @@ int tb_ctx_last_kernel_ms(const tb_ctx* ctx, float* fast_ms, float* general_ms, 
 int tb_ctx_last_call_ms(const tb_ctx* ctx, float* device_ms) {
   if (!ctx || !device_ms) return TB_ERR_INVALID;
   *device_ms = ctx->last_call_ms;
+  return TB_OK;
+}
+
+int tb_ctx_last_packed_pairs(const tb_ctx* ctx, uint64_t* pairs) {
+  if (!ctx || !pairs) return TB_ERR_INVALID;
+  *pairs = ctx->last_packed_pairs;
   return TB_OK;
 }
 

@@ -1,9 +1,339 @@
-// placeholder until the packed kernel lands: never eligible, so the general kernel handles everything
+// Packed 16x2 Gotoh kernel: the fast path for profile x reference-string pairs (tb_gotoh_ps).
+//
+// Same systolic layout as the general kernel (one warp per pair, lane l owns 16 consecutive DP rows, bottom row handed
+// to lane l+1 by shuffle), but every 32-bit register carries TWO DP cells as biased unsigned 16-bit fields:
+//   lo field = a row of half-band A (rows base+1 .. base+512),  hi field = the same row of half-band B (base+513 .. base+1024),
+// with B running 32 columns behind A, so that lane 31's bottom row of A is exactly what lane 0 needs as the top of B one
+// step later: the hand-over is the same rotating shuffle. One pass therefore covers 1024 DP rows in n+63 steps.
+//
+// Why this shape (measured on B200, profiles/microbench): the DP is bound by the ALU pipe (0.5 warp-instr/clk/SMSP:
+// VIMNMX*, VIADDMNMX, HSET2, PRMT, LOP3 all live there) while the FMA pipe (IMAD, HFMA2) idles. Per packed word (2 cells):
+//   ALU: 2x VIADDMNMX.U16x2 (H, V), 1x VIMNMX3.U16x2 (S), 4x HSET2.BF (the four pointer flags as 1.0/0.0)
+//   FMA: 4x IMAD.IADD (gap extensions, diagonal + substitution), 4x HFMA2 (acc = 2*acc + flag: bit packing on the idle pipe)
+// Values are kept below 0x7c00 so that the fp16 compare of the raw bit patterns is the integer compare (positive halves
+// order like their bits); accumulating from 4.0 leaves the 8 flag bits of two rows in the low mantissa byte of each half.
+//
+// Exactness: fields hold true_value + bias; all adds are exact while no field leaves [0, 65535], which the per-pair range
+// check guarantees (otherwise the pair is left to the general int32 kernel through GotohBatch::status). The reference's
+// -inf (src/align.h:26, never wins, consumed once at row/column 0) becomes a field value below every real value.
+// Recurrences and tie-breaks: src/gotoh.h:103-138 literally (see gotoh_general.cu).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+
 namespace tb {
-cudaError_t launch_gotoh_packed(bool, const GotohBatch&, int, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t gotoh_packed_blocks_per_sm(bool, int* out) { *out = 0; return cudaSuccess; }
-int gotoh_packed_warps_per_block() { return 1; }
-bool gotoh_packed_eligible(int, int, int, int, int, int) { return false; }
-unsigned long long gotoh_packed_ptr_words(int, int) { return 0; }
+
+constexpr int kPkWarps = 4;                       // warps per block
+constexpr int kPkRows = 1024;                     // DP rows per pass (two 512-row half-bands)
+constexpr int kPkTabWords = 6 * 512;              // one half-band table: [class][q][lane][4] 32-bit entries
+constexpr int kPkSmemWordsPerWarp = 2 * kPkTabWords;
+constexpr int kPkNeg = 2048;                      // field value standing in for the reference's -inf
+constexpr int kPkMaxField = 0x7bff - 16;          // largest field value for which fp16 compare == integer compare
+
+__device__ __forceinline__ unsigned pk_plain(int hi, int lo) { return (unsigned)(hi * 65536 + lo); }      // for 32-bit adds
+__device__ __forceinline__ unsigned pk_dpx(int hi, int lo) { return ((unsigned)hi << 16) | ((unsigned)lo & 0xffffu); }  // per-half adds
+__device__ __forceinline__ unsigned pk_flag_gt(unsigned a, unsigned b) {
+  const __half2 r = __hgt2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const unsigned*>(&r);
 }
+__device__ __forceinline__ unsigned pk_flag_eq(unsigned a, unsigned b) {
+  const __half2 r = __heq2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const unsigned*>(&r);
+}
+__device__ __forceinline__ unsigned pk_push(unsigned acc, unsigned flag) {   // acc = 2*acc + flag, per half, on the FMA pipe
+  const __half2 two = __floats2half2_rn(2.0f, 2.0f);
+  const __half2 r = __hfma2(*reinterpret_cast<const __half2*>(&acc), two, *reinterpret_cast<const __half2*>(&flag));
+  return *reinterpret_cast<const unsigned*>(&r);
+}
+
+// Pointer scratch of the packed kernel: per (pass, step) one 512 B line = 32 lanes x uint4.
+// Lane l's uint4 holds the nibbles of its 16 rows x 2 half-bands: word j = rows 4j..4j+3; byte (b + 2*half) with b = (row>>1)&1;
+// even rows in the high nibble. Nibble bits: 8 HOPEN, 4 VOPEN, 2 FROMH, 1 VCAND.
+__host__ __device__ inline unsigned long long packed_ptr_words_impl(int m, int n) {
+  if (m <= 0 || n <= 0) return 0;
+  const unsigned long long npass = (unsigned long long)(m + kPkRows - 1) / kPkRows;
+  return npass * (unsigned long long)(n + 63) * 64ull;   // in 8-byte words
+}
+
+__device__ __forceinline__ int walk_traceback_packed(const uint4* __restrict__ ptr, int T, int m, int n,
+                                                     uint8_t* __restrict__ ops_rev, int lane) {
+  int r = m, c = n, state = 0, k = 0;
+  int wpass = -1, wv = -1, wst0 = -(1 << 30);
+  uint4 wq = make_uint4(0, 0, 0, 0);
+  unsigned mych = 0;
+  while (r > 0 || c > 0) {
+    unsigned op;
+    if (r == 0) { op = 'h'; --c; }
+    else if (c == 0) { op = 'v'; --r; }
+    else {
+      const int pass = (r - 1) >> 10, rr = (r - 1) & 1023;
+      const int half = rr >> 9, l = (rr & 511) >> 4, i = rr & 15, v = l + 32 * half, st = c - 1 + v;
+      if (pass != wpass || v != wv || st > wst0 || st < wst0 - 31) {
+        wpass = pass; wv = v; wst0 = st;
+        const int s2 = st - lane;
+        wq = make_uint4(0, 0, 0, 0);
+        if (s2 >= v) wq = ptr[((unsigned long long)pass * (unsigned)T + (unsigned)s2) * 32ull + (unsigned)l];
+      }
+      const int j = i >> 2;
+      const unsigned mine = j == 0 ? wq.x : j == 1 ? wq.y : j == 2 ? wq.z : wq.w;
+      const unsigned w = __shfl_sync(kFull, mine, wst0 - st);
+      const unsigned byte = (w >> (8 * (((i >> 1) & 1) + 2 * half))) & 0xffu;
+      const unsigned nib = (i & 1) ? (byte & 15u) : (byte >> 4);
+      if (state == 0) {
+        if (nib & 2u) { state = 1; continue; }
+        if (nib & 1u) { state = 2; continue; }
+        op = 's'; --r; --c;
+      } else if (state == 1) {
+        if (nib & 8u) state = 0;
+        op = 'h'; --c;
+      } else {
+        if (nib & 4u) state = 0;
+        op = 'v'; --r;
+      }
+    }
+    if (lane == (k & 31)) mych = op;
+    ++k;
+    if ((k & 31) == 0) ops_rev[k - 32 + lane] = (uint8_t)mych;
+  }
+  if ((k & 31) != 0 && lane < (k & 31)) ops_rev[(k & ~31) + lane] = (uint8_t)mych;
+  return k;
+}
+
+template <bool TRACEBACK>
+__global__ void __launch_bounds__(kPkWarps * 32)
+gotoh_packed_kernel(const GotohBatch B) {
+  extern __shared__ int smem_pk[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned slot = blockIdx.x * kPkWarps + wib;
+  int* const tabA = smem_pk + wib * kPkSmemWordsPerWarp;
+  int* const tabB = tabA + kPkTabWords;
+  const float fmatch = (float)B.match, fmismatch = (float)B.mismatch;
+  const int go = B.go, ge = B.ge, goe = B.go + B.ge;
+  const bool hfree = B.hfree != 0, vfree = B.vfree != 0;
+
+  uint4* const ptr = TRACEBACK ? reinterpret_cast<uint4*>(B.ptr_scratch + (unsigned long long)slot * B.ptr_slot_words) : nullptr;
+  unsigned* const rowbuf0 = reinterpret_cast<unsigned*>(B.rowbuf + (unsigned long long)slot * B.rowbuf_slot);
+  uint8_t* const ops_rev = TRACEBACK ? B.ops_scratch + (unsigned long long)slot * B.ops_slot : nullptr;
+
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = (int)atomicAdd(B.counter, 1u);
+    q = __shfl_sync(kFull, q, 0);
+    if (q >= B.npairs) break;
+    const int pi = B.order ? B.order[q] : q;
+    const int m = B.a_len[pi], n = B.b_len[pi];
+    if (m == 0 || n == 0) continue;                      // degenerate shapes: general kernel
+    const float* const a = (const float*)B.a_base + B.a_off[pi];
+    const unsigned char* const b = (const unsigned char*)B.b_base + B.b_off[pi];
+
+    // ---- per-pair range check (decides whether 16-bit biased fields are exact for this pair) ----
+    int smin = 0, smax = 0;
+    for (int r0 = lane; r0 < m; r0 += 32) {
+      float p[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) p[k] = a[(size_t)k * m + r0];
+#pragma unroll
+      for (int cls = 0; cls < 5; ++cls) {
+        const int s = sub_onehot(p, cls, fmatch, fmismatch);
+        smin = min(smin, s); smax = max(smax, s);
+      }
+    }
+    smin = __reduce_min_sync(kFull, smin); smax = __reduce_max_sync(kFull, smax);
+    const int npass = (m + kPkRows - 1) / kPkRows;
+    // lowest real value: all-gap path to the far corner, one more open+extend, the 32 run-in/run-out columns, slack
+    const long long lb = 2ll * go + goe + (long long)(npass * kPkRows + n + 34) * ge - 16 + 32ll * goe + 32ll * min(smin, 0);
+    const long long bias_ll = (long long)kPkNeg + 64 - lb;
+    const long long ub = (long long)max(smax, 0) * min(m, n) + 32ll * max(smax, 0);
+    if (bias_ll + ub > kPkMaxField || smin < -16384 || smax > 16384) continue;   // leave status 0: the general kernel takes it
+    const int bias = (int)bias_ll;
+
+    const int T = n + 63;
+    uint8_t* const ops_out = TRACEBACK ? B.ops + (long long)pi * B.ops_stride : nullptr;
+    const int rr_m = (m - 1) & (kPkRows - 1);                // where row m lives in the last pass
+    const int m_half = rr_m >> 9, m_lane = (rr_m & 511) >> 4, m_i = rr_m & 15;
+    unsigned score_word = 0;
+
+    for (int pass = 0; pass < npass; ++pass) {
+      const int base = pass * kPkRows;
+      const unsigned* const top = rowbuf0 + (unsigned long long)(pass & 1) * (unsigned)(n + 1);
+      unsigned* const bot = rowbuf0 + (unsigned long long)((pass + 1) & 1) * (unsigned)(n + 1);
+      const bool more = pass + 1 < npass;
+
+      // ---- substitution tables of this pass: A = half-band A (plain), B = half-band B (pre-shifted into the high half) ----
+      __syncwarp();
+      for (int rr = lane; rr < kPkRows; rr += 32) {
+        const int r0 = base + rr;                              // 0-based row of a1
+        const int half = rr >> 9, rb = rr & 511, l = rb >> 4, i = rb & 15;
+        const int at = (i >> 2) * 128 + l * 4 + (i & 3);
+        float p[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) p[k] = r0 < m ? a[(size_t)k * m + r0] : 0.0f;
+        int* const tab = half ? tabB : tabA;
+#pragma unroll
+        for (int cls = 0; cls < 5; ++cls) {
+          const int s = r0 < m ? sub_onehot(p, cls, fmatch, fmismatch) : 0;
+          tab[cls * 512 + at] = half ? s * 65536 : s;
+        }
+        tab[5 * 512 + at] = 0;
+      }
+      __syncwarp();
+
+      // ---- per-lane state ----
+      const int rtop_lo = base + lane * kRowsPerLane, rtop_hi = rtop_lo + 512;   // DP row just above the lane's rows
+      unsigned sl[kRowsPerLane], hh[kRowsPerLane], hge[kRowsPerLane], hgoe[kRowsPerLane];
+#pragma unroll
+      for (int i = 0; i < kRowsPerLane; ++i) {
+        const int rlo = rtop_lo + i + 1, rhi = rtop_hi + i + 1;
+        sl[i] = pk_dpx((vfree ? 0 : go + rhi * ge) + bias, (vfree ? 0 : go + rlo * ge) + bias);   // S[r][0], src/gotoh.h:121
+        hh[i] = pk_dpx(kPkNeg, kPkNeg);                                                             // H[r][0] = -inf, src/gotoh.h:120
+        const bool flo = hfree && rlo == m, fhi = hfree && rhi == m;                               // src/align.h:67-80
+        hge[i] = pk_plain(fhi ? 0 : ge, flo ? 0 : ge);
+        hgoe[i] = pk_dpx(fhi ? 0 : goe, flo ? 0 : goe);
+      }
+      const int d0_lo = (rtop_lo == 0 ? 0 : (vfree ? 0 : go + rtop_lo * ge)) + bias;               // S[rtop][0]
+      const int d0_hi = (vfree ? 0 : go + rtop_hi * ge) + bias;
+      unsigned diag = pk_dpx(d0_hi, d0_lo);
+      unsigned bs = pk_dpx(bias, bias), bv = pk_dpx(kPkNeg, kPkNeg);
+      unsigned cur = 5u | (5u << 8);                          // column classes (lo | hi << 8); 5 = padding, scores 0
+      unsigned tchunk = 0; int cchunk = 5;
+
+      for (int st = 0; st < T; ++st) {
+        if ((st & 31) == 0) {   // lane 0's feed for the next 32 columns (top boundary row + column classes), coalesced
+          const int cc = st + 1 + lane;
+          if (pass == 0) tchunk = pk_dpx(kPkNeg, (hfree ? 0 : go + cc * ge) + bias);               // src/gotoh.h:113-118
+          else tchunk = cc <= n ? top[cc] : pk_dpx(kPkNeg, bias);
+          cchunk = cc <= n ? base_class(b[cc - 1]) : 5;
+        }
+        const int src = (lane + 31) & 31;
+        unsigned us = __shfl_sync(kFull, bs, src), uv = __shfl_sync(kFull, bv, src);
+        const unsigned rc = __shfl_sync(kFull, cur, src);
+        const unsigned fsv = __shfl_sync(kFull, tchunk, st & 31);
+        const unsigned fcl = (unsigned)__shfl_sync(kFull, cchunk, st & 31);
+        cur = rc;
+        if (lane == 0) {
+          us = __byte_perm(fsv, us, 0x5410);                  // lo: top row S, hi: lane 31's half-band-A bottom S
+          uv = __byte_perm(fsv, uv, 0x5432);
+          cur = fcl | ((rc & 0xffu) << 8);
+        }
+
+        const int c_lo = st - lane + 1, c_hi = c_lo - 32;
+        if (c_lo >= 1 && c_lo <= n + 32) {
+          if (c_lo == 33) {     // half-band B starts now: discard what the run-in steps left in the high halves
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+              const int rhi = rtop_hi + i + 1;
+              sl[i] = (sl[i] & 0xffffu) | ((unsigned)((vfree ? 0 : go + rhi * ge) + bias) << 16);
+              hh[i] = (hh[i] & 0xffffu) | ((unsigned)kPkNeg << 16);
+            }
+            diag = (diag & 0xffffu) | ((unsigned)d0_hi << 16);
+          }
+          // vertical gap costs depend on the column (src/align.h:52-65): last column is free when vfree
+          const int vge_lo = vfree && c_lo == n ? 0 : ge, vge_hi = vfree && c_hi == n ? 0 : ge;
+          const int vgoe_lo = vfree && c_lo == n ? 0 : goe, vgoe_hi = vfree && c_hi == n ? 0 : goe;
+          const unsigned vge = pk_plain(vge_hi, vge_lo), vgoe = pk_dpx(vgoe_hi, vgoe_lo);
+
+          const uint4* const pa = reinterpret_cast<const uint4*>(tabA + (cur & 0xffu) * 512) + lane;
+          const uint4* const pb = reinterpret_cast<const uint4*>(tabB + (cur >> 8) * 512) + lane;
+          unsigned subw[kRowsPerLane];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 x = pa[j * 32], y = pb[j * 32];
+            subw[4 * j + 0] = x.x + y.x; subw[4 * j + 1] = x.y + y.y; subw[4 * j + 2] = x.z + y.z; subw[4 * j + 3] = x.w + y.w;
+          }
+
+          const unsigned next_diag = us;
+          unsigned d = diag;
+          unsigned acc[8];
+#pragma unroll
+          for (int i = 0; i < kRowsPerLane; ++i) {
+            const unsigned hext = hh[i] + hge[i];
+            const unsigned hn = __viaddmax_u16x2(sl[i], hgoe[i], hext);      // src/gotoh.h:129
+            const unsigned vext = uv + vge;
+            const unsigned vn = __viaddmax_u16x2(us, vgoe, vext);            // src/gotoh.h:130
+            const unsigned t = d + subw[i];
+            const unsigned s = __vimax3_u16x2(t, hn, vn);                    // src/gotoh.h:131
+            if (TRACEBACK) {
+              unsigned ac = (i & 1) ? acc[i >> 1] : 0x44004400u;             // 4.0 | 4.0
+              ac = pk_push(ac, pk_flag_gt(hn, hext));                        // HOPEN, src/gotoh.h:137
+              ac = pk_push(ac, pk_flag_gt(vn, vext));                        // VOPEN, src/gotoh.h:138
+              ac = pk_push(ac, pk_flag_eq(s, hn));                           // FROMH, src/gotoh.h:134
+              ac = pk_push(ac, pk_flag_eq(s, vn));                           // VCAND, src/gotoh.h:135 (walker applies the else)
+              acc[i >> 1] = ac;
+            }
+            d = sl[i];
+            sl[i] = s; hh[i] = hn; us = s; uv = vn;
+          }
+          diag = next_diag;
+          bs = us; bv = uv;
+          if (TRACEBACK) {
+            uint4 w;
+            w.x = __byte_perm(acc[0], acc[1], 0x6240); w.y = __byte_perm(acc[2], acc[3], 0x6240);
+            w.z = __byte_perm(acc[4], acc[5], 0x6240); w.w = __byte_perm(acc[6], acc[7], 0x6240);
+            ptr[((unsigned long long)pass * (unsigned)T + (unsigned)st) * 32ull + (unsigned)lane] = w;
+          }
+          if (more && lane == 31 && c_hi >= 1 && c_hi <= n) bot[c_hi] = __byte_perm(bs, bv, 0x7632);   // S | V << 16 of row base+1024
+          if (!more && lane == m_lane && (m_half ? c_hi : c_lo) == n) {      // S[m][n] passes through this lane now
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) if (i == m_i) score_word = sl[i];
+          }
+        }
+      }
+      __syncwarp();
+    }
+
+    const unsigned sw = __shfl_sync(kFull, score_word, m_lane);
+    const int score = (int)(m_half ? sw >> 16 : sw & 0xffffu) - bias;
+
+    if (TRACEBACK) {
+      __syncwarp();
+      const int L = walk_traceback_packed(ptr, T, m, n, ops_rev, lane);
+      __syncwarp();
+      for (int j = lane; j < L; j += 32) ops_out[j] = ops_rev[L - 1 - j];
+      if (lane == 0) B.ops_len[pi] = L;
+    }
+    if (lane == 0) { B.scores[pi] = score; B.status[pi] = 1; atomicAdd(B.counter + 1, 1u); }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+static size_t packed_smem_bytes() { return (size_t)kPkWarps * kPkSmemWordsPerWarp * sizeof(int); }
+int gotoh_packed_warps_per_block() { return kPkWarps; }
+unsigned long long gotoh_packed_ptr_words(int m, int n) { return packed_ptr_words_impl(m, n); }
+
+// Host-side plausibility (the kernel re-checks every pair with its real substitution range): standard non-positive gap
+// scores, and the largest shape of the batch fits the 15-bit field range assuming |sub| <= max(|match|, |mismatch|).
+bool gotoh_packed_eligible(int maxm, int maxn, int match, int mismatch, int go, int ge) {
+  if (go > 0 || ge > 0 || maxm <= 0 || maxn <= 0) return false;
+  if (go < -512 || ge < -512 || match > 4096 || match < -4096 || mismatch > 4096 || mismatch < -4096) return false;   // kPkNeg + goe must stay >= 0
+  return true;   // per-pair decision is made on the device; ineligible pairs fall through to the general kernel
+}
+
+cudaError_t launch_gotoh_packed(bool traceback, const GotohBatch& B, int blocks, cudaStream_t stream) {
+  const size_t smem = packed_smem_bytes();
+  cudaError_t e;
+  if (traceback) {
+    e = cudaFuncSetAttribute(gotoh_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gotoh_packed_kernel<true><<<blocks, kPkWarps * 32, smem, stream>>>(B);
+  } else {
+    e = cudaFuncSetAttribute(gotoh_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    gotoh_packed_kernel<false><<<blocks, kPkWarps * 32, smem, stream>>>(B);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t gotoh_packed_blocks_per_sm(bool traceback, int* out) {
+  const size_t smem = packed_smem_bytes();
+  cudaError_t e;
+  if (traceback) {
+    e = cudaFuncSetAttribute(gotoh_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, gotoh_packed_kernel<true>, kPkWarps * 32, smem);
+  }
+  e = cudaFuncSetAttribute(gotoh_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, gotoh_packed_kernel<false>, kPkWarps * 32, smem);
+}
+
+}  // namespace tb

@@ -45,7 +45,7 @@ def test_packed_shapes_vs_oracle(ctx, oracle_port, hf, vf):
     for k, (m, n) in enumerate(SHAPES):
         a = synth.random_profile(rng, m, ["trace", "ties", "msa"][k % 3])
         cons = bytes(b"ACGT"[int(x)] for x in np.argmax(a[:4], axis=0))
-        b = synth.mutate_seq(rng, (cons * (n // m + 1))[:n], 0.05, 0.04) if k % 2 == 0 else synth.random_seq(rng, n, b"ACGTNacgtn-RY")
+        b = synth.mutate_seq(rng, (cons * (n // m + 1))[:n], 0.05, 0.04) if k % 2 == 0 else synth.random_seq(rng, n, b"ACGTNacgtn")
         b = (b or b"A")
         A.append(a); Bs.append(b)
     (s, ops, ol), packed = _both(ctx, A, Bs, sc, AlignConfig(bool(hf), bool(vf)))
@@ -96,6 +96,18 @@ def test_packed_falls_through_when_range_too_wide(ctx, oracle_port):
     assert ctx.last_packed_pairs() == 0
     for i, (a, b) in enumerate(zip(A[1::2], Bs[1::2])):
         assert (int(s2[i]), bytes(ops2[i, : ol2[i]])) == oracle_port.gotoh_ps(a, b, 1, 0, sc2)
+
+
+def test_foreign_reference_characters_fall_through(ctx, oracle_port):
+    """Reference characters outside ACGTN score 0 against every channel (src/align.h:121-136): the packed kernel's
+    tables carry five classes only, so such pairs go to the general kernel; mixed batches stay correct."""
+    rng = np.random.default_rng(31)
+    A = [synth.random_profile(rng, 150 + 10 * i, "trace") for i in range(10)]
+    Bs = [synth.random_seq(rng, 400, b"ACGT-RYK" if i % 2 else b"ACGTN") for i in range(10)]
+    (s, ops, ol), packed = _both(ctx, A, Bs, (3, -5, -10, -4), AlignConfig(True, False))
+    assert packed == 5
+    for i in range(10):
+        assert (int(s[i]), bytes(ops[i, : ol[i]])) == oracle_port.gotoh_ps(A[i], Bs[i], 1, 0, (3, -5, -10, -4)), i
 
 
 def test_packed_config2_full_shape(ctx, oracle_port):

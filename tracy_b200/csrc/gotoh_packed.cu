@@ -23,9 +23,9 @@
 
 namespace tb {
 
-constexpr int kPkWarps = 4;                       // warps per block
+constexpr int kPkWarps = 2;                       // warps per block (40 KB of tables per block: five blocks per SM)
 constexpr int kPkRows = 1024;                     // DP rows per pass (two 512-row half-bands)
-constexpr int kPkTabWords = 6 * 512;              // one half-band table: [class][q][lane][4] 32-bit entries
+constexpr int kPkTabWords = 5 * 512;              // one half-band table: [class A,C,G,T,N][q][lane][4] 32-bit entries
 constexpr int kPkSmemWordsPerWarp = 2 * kPkTabWords;
 constexpr int kPkNeg = 2048;                      // field value standing in for the reference's -inf
 constexpr int kPkMaxField = 0x7bff - 16;          // largest field value for which fp16 compare == integer compare
@@ -110,6 +110,7 @@ gotoh_packed_kernel(const GotohBatch B) {
   const float fmatch = (float)B.match, fmismatch = (float)B.mismatch;
   const int go = B.go, ge = B.ge, goe = B.go + B.ge;
   const bool hfree = B.hfree != 0, vfree = B.vfree != 0;
+  const int src = (lane + 31) & 31;
 
   uint4* const ptr = TRACEBACK ? reinterpret_cast<uint4*>(B.ptr_scratch + (unsigned long long)slot * B.ptr_slot_words) : nullptr;
   unsigned* const rowbuf0 = reinterpret_cast<unsigned*>(B.rowbuf + (unsigned long long)slot * B.rowbuf_slot);
@@ -127,7 +128,7 @@ gotoh_packed_kernel(const GotohBatch B) {
     const unsigned char* const b = (const unsigned char*)B.b_base + B.b_off[pi];
 
     // ---- per-pair range check (decides whether 16-bit biased fields are exact for this pair) ----
-    int smin = 0, smax = 0;
+    int smin = 0, smax = 0, foreign = 0;
     for (int r0 = lane; r0 < m; r0 += 32) {
       float p[5];
 #pragma unroll
@@ -138,12 +139,14 @@ gotoh_packed_kernel(const GotohBatch B) {
         smin = min(smin, s); smax = max(smax, s);
       }
     }
+    for (int j = lane; j < n; j += 32) foreign |= base_class(b[j]) == 5;   // characters outside ACGTN score 0: general kernel
     smin = __reduce_min_sync(kFull, smin); smax = __reduce_max_sync(kFull, smax);
+    if (__any_sync(kFull, foreign)) continue;
     const int npass = (m + kPkRows - 1) / kPkRows;
     // lowest real value: all-gap path to the far corner, one more open+extend, the 32 run-in/run-out columns, slack
-    const long long lb = 2ll * go + goe + (long long)(npass * kPkRows + n + 34) * ge - 16 + 32ll * goe + 32ll * min(smin, 0);
+    const long long lb = 2ll * go + 2ll * goe + (long long)(npass * kPkRows + n + 34) * ge - 16 + 32ll * goe + 34ll * min(smin, 0);
     const long long bias_ll = (long long)kPkNeg + 64 - lb;
-    const long long ub = (long long)max(smax, 0) * min(m, n) + 32ll * max(smax, 0);
+    const long long ub = (long long)max(smax, 0) * min(m, n) + 34ll * max(smax, 0);
     if (bias_ll + ub > kPkMaxField || smin < -16384 || smax > 16384) continue;   // leave status 0: the general kernel takes it
     const int bias = (int)bias_ll;
 
@@ -159,7 +162,8 @@ gotoh_packed_kernel(const GotohBatch B) {
       unsigned* const bot = rowbuf0 + (unsigned long long)((pass + 1) & 1) * (unsigned)(n + 1);
       const bool more = pass + 1 < npass;
 
-      // ---- substitution tables of this pass: A = half-band A (plain), B = half-band B (pre-shifted into the high half) ----
+      // ---- substitution tables of this pass, entries in per-half form: A = half-band A in the low half, B = half-band B
+      //      in the high half, so that A | B is the packed addend of one word ----
       __syncwarp();
       for (int rr = lane; rr < kPkRows; rr += 32) {
         const int r0 = base + rr;                              // 0-based row of a1
@@ -171,10 +175,9 @@ gotoh_packed_kernel(const GotohBatch B) {
         int* const tab = half ? tabB : tabA;
 #pragma unroll
         for (int cls = 0; cls < 5; ++cls) {
-          const int s = r0 < m ? sub_onehot(p, cls, fmatch, fmismatch) : 0;
-          tab[cls * 512 + at] = half ? s * 65536 : s;
+          const unsigned s = (unsigned)(r0 < m ? sub_onehot(p, cls, fmatch, fmismatch) : 0) & 0xffffu;
+          tab[cls * 512 + at] = (int)(half ? s << 16 : s);
         }
-        tab[5 * 512 + at] = 0;
       }
       __syncwarp();
 
@@ -194,26 +197,40 @@ gotoh_packed_kernel(const GotohBatch B) {
       const int d0_hi = (vfree ? 0 : go + rtop_hi * ge) + bias;
       unsigned diag = pk_dpx(d0_hi, d0_lo);
       unsigned bs = pk_dpx(bias, bias), bv = pk_dpx(kPkNeg, kPkNeg);
-      unsigned cur = 5u | (5u << 8);                          // column classes (lo | hi << 8); 5 = padding, scores 0
-      unsigned tchunk = 0; int cchunk = 5;
 
-      for (int st = 0; st < T; ++st) {
-        if ((st & 31) == 0) {   // lane 0's feed for the next 32 columns (top boundary row + column classes), coalesced
-          const int cc = st + 1 + lane;
-          if (pass == 0) tchunk = pk_dpx(kPkNeg, (hfree ? 0 : go + cc * ge) + bias);               // src/gotoh.h:113-118
-          else tchunk = cc <= n ? top[cc] : pk_dpx(kPkNeg, bias);
-          cchunk = cc <= n ? base_class(b[cc - 1]) : 5;
-        }
-        const int src = (lane + 31) & 31;
+      // lane 0's feed (top boundary row S|V<<16 and column class), double-buffered 32 columns at a time
+      auto feed_sv = [&](int cc) -> unsigned {
+        if (pass == 0) return pk_dpx(kPkNeg, (hfree ? 0 : go + cc * ge) + bias);                   // src/gotoh.h:113-118
+        return cc <= n ? top[cc] : pk_dpx(kPkNeg, bias);
+      };
+      auto feed_cls = [&](int cc) -> unsigned { return cc <= n ? (unsigned)base_class(b[cc - 1]) : 0u; };
+      unsigned tchunk = feed_sv(1 + lane), cchunk = feed_cls(1 + lane);
+      unsigned tnext = feed_sv(33 + lane), cnext = feed_cls(33 + lane);
+      // column classes of this lane for the coming step (lo | hi << 8); columns outside 1..n use class 0 (never read back)
+      unsigned cur = 0;
+      { const unsigned f0 = __shfl_sync(kFull, cchunk, 0); if (lane == 0) cur = f0; }
+      uint4* pw = TRACEBACK ? ptr + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
+
+      for (int st = 0; st < T; ++st, pw += 32) {
+        // substitution scores of this step's columns (issued first: shared-memory latency hides under the shuffles)
+        const uint4* const pa = reinterpret_cast<const uint4*>(tabA + (cur & 0xffu) * 512) + lane;
+        const uint4* const pb = reinterpret_cast<const uint4*>(tabB + (cur >> 8) * 512) + lane;
+        uint4 xa[4], xb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { xa[j] = pa[j * 32]; xb[j] = pb[j * 32]; }
+
         unsigned us = __shfl_sync(kFull, bs, src), uv = __shfl_sync(kFull, bv, src);
-        const unsigned rc = __shfl_sync(kFull, cur, src);
         const unsigned fsv = __shfl_sync(kFull, tchunk, st & 31);
-        const unsigned fcl = (unsigned)__shfl_sync(kFull, cchunk, st & 31);
-        cur = rc;
         if (lane == 0) {
           us = __byte_perm(fsv, us, 0x5410);                  // lo: top row S, hi: lane 31's half-band-A bottom S
           uv = __byte_perm(fsv, uv, 0x5432);
-          cur = fcl | ((rc & 0xffu) << 8);
+        }
+        // classes for the next step: rotate, lane 0 takes the next column from the feed
+        if ((st & 31) == 31) { tchunk = tnext; cchunk = cnext; tnext = feed_sv(st + 34 + lane); cnext = feed_cls(st + 34 + lane); }
+        {
+          const unsigned rc = __shfl_sync(kFull, cur, src);
+          const unsigned fcl = __shfl_sync(kFull, cchunk, (st + 1) & 31);
+          cur = lane == 0 ? (fcl | ((rc & 0xffu) << 8)) : rc;
         }
 
         const int c_lo = st - lane + 1, c_hi = c_lo - 32;
@@ -230,28 +247,28 @@ gotoh_packed_kernel(const GotohBatch B) {
           // vertical gap costs depend on the column (src/align.h:52-65): last column is free when vfree
           const int vge_lo = vfree && c_lo == n ? 0 : ge, vge_hi = vfree && c_hi == n ? 0 : ge;
           const int vgoe_lo = vfree && c_lo == n ? 0 : goe, vgoe_hi = vfree && c_hi == n ? 0 : goe;
-          const unsigned vge = pk_plain(vge_hi, vge_lo), vgoe = pk_dpx(vgoe_hi, vgoe_lo);
+          const unsigned vge_p = pk_plain(vge_hi, vge_lo), vge_d = pk_dpx(vge_hi, vge_lo), vgoe_p = pk_plain(vgoe_hi, vgoe_lo);
 
-          const uint4* const pa = reinterpret_cast<const uint4*>(tabA + (cur & 0xffu) * 512) + lane;
-          const uint4* const pb = reinterpret_cast<const uint4*>(tabB + (cur >> 8) * 512) + lane;
           unsigned subw[kRowsPerLane];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 x = pa[j * 32], y = pb[j * 32];
-            subw[4 * j + 0] = x.x + y.x; subw[4 * j + 1] = x.y + y.y; subw[4 * j + 2] = x.z + y.z; subw[4 * j + 3] = x.w + y.w;
+            subw[4 * j + 0] = xa[j].x + xb[j].x; subw[4 * j + 1] = xa[j].y + xb[j].y;
+            subw[4 * j + 2] = xa[j].z + xb[j].z; subw[4 * j + 3] = xa[j].w + xb[j].w;
           }
 
+          // V[r][c] = max(S[r-1][c] + goe, V[r-1][c] + ge) with S[r-1][c] = max(g, V[r-1][c]) and goe <= ge collapses to
+          // V[r][c] = max(g[r-1] + goe, V[r-1][c] + ge): one DPX op per row on the serial chain (g = max(diag + sub, H)).
           const unsigned next_diag = us;
           unsigned d = diag;
+          unsigned vext = uv + vge_p;
+          unsigned vn = __viaddmax_u16x2(uv, vge_d, us + vgoe_p);            // src/gotoh.h:130 for the lane's first row
           unsigned acc[8];
 #pragma unroll
           for (int i = 0; i < kRowsPerLane; ++i) {
             const unsigned hext = hh[i] + hge[i];
             const unsigned hn = __viaddmax_u16x2(sl[i], hgoe[i], hext);      // src/gotoh.h:129
-            const unsigned vext = uv + vge;
-            const unsigned vn = __viaddmax_u16x2(us, vgoe, vext);            // src/gotoh.h:130
-            const unsigned t = d + subw[i];
-            const unsigned s = __vimax3_u16x2(t, hn, vn);                    // src/gotoh.h:131
+            const unsigned g = __viaddmax_u16x2(d, subw[i], hn);             // max(diag + sub, H)
+            const unsigned s = __vmaxu2(g, vn);                              // src/gotoh.h:131
             if (TRACEBACK) {
               unsigned ac = (i & 1) ? acc[i >> 1] : 0x44004400u;             // 4.0 | 4.0
               ac = pk_push(ac, pk_flag_gt(hn, hext));                        // HOPEN, src/gotoh.h:137
@@ -261,7 +278,10 @@ gotoh_packed_kernel(const GotohBatch B) {
               acc[i >> 1] = ac;
             }
             d = sl[i];
-            sl[i] = s; hh[i] = hn; us = s; uv = vn;
+            sl[i] = s; hh[i] = hn;
+            us = s; uv = vn;
+            vext = vn + vge_p;
+            vn = __viaddmax_u16x2(vn, vge_d, g + vgoe_p);                    // next row's V
           }
           diag = next_diag;
           bs = us; bv = uv;
@@ -269,7 +289,7 @@ gotoh_packed_kernel(const GotohBatch B) {
             uint4 w;
             w.x = __byte_perm(acc[0], acc[1], 0x6240); w.y = __byte_perm(acc[2], acc[3], 0x6240);
             w.z = __byte_perm(acc[4], acc[5], 0x6240); w.w = __byte_perm(acc[6], acc[7], 0x6240);
-            ptr[((unsigned long long)pass * (unsigned)T + (unsigned)st) * 32ull + (unsigned)lane] = w;
+            *pw = w;
           }
           if (more && lane == 31 && c_hi >= 1 && c_hi <= n) bot[c_hi] = __byte_perm(bs, bv, 0x7632);   // S | V << 16 of row base+1024
           if (!more && lane == m_lane && (m_half ? c_hi : c_lo) == n) {      // S[m][n] passes through this lane now

@@ -55,47 +55,73 @@ __host__ __device__ inline unsigned long long packed_ptr_words_impl(int m, int n
   return npass * (unsigned long long)(n + 63) * 64ull;   // in 8-byte words
 }
 
+// Nibble of DP row `row` (0..15 inside the lane block) of half-band `half` from a lane's uint4.
+__device__ __forceinline__ unsigned pk_nibble(const uint4& w, int row, int half) {
+  const int j = row >> 2;
+  const unsigned x = j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w;
+  const unsigned byte = (x >> (8 * (((row >> 1) & 1) + 2 * half))) & 0xffu;
+  return (row & 1) ? (byte & 15u) : (byte >> 4);
+}
+
+// Warp-cooperative traceback (reference src/gotoh.h:144-167) that consumes whole RUNS per iteration instead of one cell:
+// the 32 lanes hold the pointer words of 32 consecutive steps of the current virtual lane (one gather), so
+//   state 'h': the HOPEN bits of up to 32 cells to the left are one ballot        (the free end-gap run along row m)
+//   state 's': the diagonal inside the 16-row lane block is one ballot (cell (r-j, c-j) sits in step st-j, row i-j)
+//   state 'v': the VOPEN bits of the rows above in the same column are one ballot (all in one lane's word)
+// Row 0 and column 0 are closed forms. Emits the reversed string into ops_rev and returns its length.
 __device__ __forceinline__ int walk_traceback_packed(const uint4* __restrict__ ptr, int T, int m, int n,
                                                      uint8_t* __restrict__ ops_rev, int lane) {
   int r = m, c = n, state = 0, k = 0;
   int wpass = -1, wv = -1, wst0 = -(1 << 30);
   uint4 wq = make_uint4(0, 0, 0, 0);
-  unsigned mych = 0;
   while (r > 0 || c > 0) {
-    unsigned op;
-    if (r == 0) { op = 'h'; --c; }
-    else if (c == 0) { op = 'v'; --r; }
-    else {
-      const int pass = (r - 1) >> 10, rr = (r - 1) & 1023;
-      const int half = rr >> 9, l = (rr & 511) >> 4, i = rr & 15, v = l + 32 * half, st = c - 1 + v;
-      if (pass != wpass || v != wv || st > wst0 || st < wst0 - 31) {
-        wpass = pass; wv = v; wst0 = st;
-        const int s2 = st - lane;
-        wq = make_uint4(0, 0, 0, 0);
-        if (s2 >= v) wq = ptr[((unsigned long long)pass * (unsigned)T + (unsigned)s2) * 32ull + (unsigned)l];
-      }
-      const int j = i >> 2;
-      const unsigned mine = j == 0 ? wq.x : j == 1 ? wq.y : j == 2 ? wq.z : wq.w;
-      const unsigned w = __shfl_sync(kFull, mine, wst0 - st);
-      const unsigned byte = (w >> (8 * (((i >> 1) & 1) + 2 * half))) & 0xffu;
-      const unsigned nib = (i & 1) ? (byte & 15u) : (byte >> 4);
-      if (state == 0) {
-        if (nib & 2u) { state = 1; continue; }
-        if (nib & 1u) { state = 2; continue; }
-        op = 's'; --r; --c;
-      } else if (state == 1) {
-        if (nib & 8u) state = 0;
-        op = 'h'; --c;
-      } else {
-        if (nib & 4u) state = 0;
-        op = 'v'; --r;
-      }
+    if (r == 0) { for (int j = lane; j < c; j += 32) ops_rev[k + j] = 'h'; k += c; break; }   // row 0: only FROMH is ever set
+    if (c == 0) { for (int j = lane; j < r; j += 32) ops_rev[k + j] = 'v'; k += r; break; }   // column 0
+    const int pass = (r - 1) >> 10, rr = (r - 1) & 1023;
+    const int half = rr >> 9, l = (rr & 511) >> 4, i = rr & 15, v = l + 32 * half, st = c - 1 + v;
+    if (pass != wpass || v != wv || st > wst0 || st < wst0 - 31) {
+      wpass = pass; wv = v; wst0 = st;
+      const int s2 = st - lane;
+      wq = make_uint4(0, 0, 0, 0);
+      if (s2 >= v) wq = ptr[((unsigned long long)pass * (unsigned)T + (unsigned)s2) * 32ull + (unsigned)l];
     }
-    if (lane == (k & 31)) mych = op;
-    ++k;
-    if ((k & 31) == 0) ops_rev[k - 32 + lane] = (uint8_t)mych;
+    const int off = wst0 - st, j = lane - off;            // this lane looks at the j-th cell of the run (j >= 0)
+    unsigned char ch;
+    int run;
+    if (state == 1) {
+      const int cnt = min(32 - off, c);
+      const unsigned hit = __ballot_sync(kFull, j >= 0 && j < cnt && (pk_nibble(wq, i, half) & 8u));
+      const int first = hit ? __ffs(hit) - 1 - off : -1;
+      run = first >= 0 ? first + 1 : cnt;
+      ch = 'h';
+      c -= run;
+      if (first >= 0) state = 0;
+    } else if (state == 0) {
+      const int cnt = min(min(32 - off, c), i + 1);
+      const unsigned nib = (j >= 0 && j < cnt) ? pk_nibble(wq, i - j, half) : 0u;
+      const unsigned brk = __ballot_sync(kFull, (nib & 3u) != 0u);
+      run = brk ? __ffs(brk) - 1 - off : cnt;
+      ch = 's';
+      r -= run; c -= run;
+      if (run < cnt) {                                     // the cell that stopped the diagonal decides the gap state
+        const unsigned nb = __shfl_sync(kFull, nib, off + run);
+        state = (nb & 2u) ? 1 : 2;
+      }
+    } else {
+      uint4 w;                                             // the column's 16 rows live in the one lane that holds step st
+      w.x = __shfl_sync(kFull, wq.x, off); w.y = __shfl_sync(kFull, wq.y, off);
+      w.z = __shfl_sync(kFull, wq.z, off); w.w = __shfl_sync(kFull, wq.w, off);
+      const int cnt = i + 1;
+      const unsigned hit = __ballot_sync(kFull, lane < cnt && (pk_nibble(w, i - min(lane, i), half) & 4u));
+      const int first = hit ? __ffs(hit) - 1 : -1;
+      run = first >= 0 ? first + 1 : cnt;
+      ch = 'v';
+      r -= run;
+      if (first >= 0) state = 0;
+    }
+    if (lane < run) ops_rev[k + lane] = ch;
+    k += run;
   }
-  if ((k & 31) != 0 && lane < (k & 31)) ops_rev[(k & ~31) + lane] = (uint8_t)mych;
   return k;
 }
 

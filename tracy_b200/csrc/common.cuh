@@ -90,51 +90,67 @@ __device__ __forceinline__ unsigned long long ptr_word_index(int nv, int T, int 
   return nv == 32 ? line * 32ull + (unsigned)v : line * 64ull + (unsigned)(v & 31) * 2u + (unsigned)(v >> 5);
 }
 
-// Warp-cooperative traceback (reference src/gotoh.h:144-167). All lanes run the state machine in lock-step; a
-// window of 32 consecutive steps of the current virtual lane is kept in registers (one 64-bit word per lane) so
-// that diagonal and horizontal runs cost one gather per <=32 cells instead of one dependent HBM read per cell.
-// Emits the reversed string into ops_rev and returns its length.
+// Warp-cooperative traceback (reference src/gotoh.h:144-167) over the general kernel's pointer layout. The 32 lanes
+// hold the 64-bit pointer words of 32 consecutive steps of the current lane block (one gather) and whole RUNS are
+// consumed per iteration: a horizontal run is one ballot over HOPEN bits, the diagonal inside the 16-row block is one
+// ballot (cell (r-j, c-j) sits in step st-j, row i-j), a vertical run is one ballot over the 16 nibbles of one word.
+// Row 0 and column 0 are closed forms. Emits the reversed string into ops_rev and returns its length.
+__device__ __forceinline__ unsigned ptr_nibble(unsigned lo, unsigned hi, int row) {
+  return ((row < 8 ? lo : hi) >> (4 * (row & 7))) & 15u;
+}
 __device__ __forceinline__ int walk_traceback(const unsigned long long* __restrict__ ptr, int nv, int T, int m, int n,
                                               uint8_t* __restrict__ ops_rev, int lane) {
   const int bh = nv * kRowsPerLane;
   int r = m, c = n, state = 0, k = 0;
   int wband = -1, wv = -1, wst0 = -(1 << 30);
   unsigned wlo = 0, whi = 0;
-  unsigned mych = 0;
   while (r > 0 || c > 0) {
-    unsigned op;
-    if (r == 0) { op = 'h'; --c; }          // row 0 is all 'h' (only FROMH is ever set there)
-    else if (c == 0) { op = 'v'; --r; }     // column 0 is all 'v'
-    else {
-      const int band = (r - 1) / bh, rr = (r - 1) - band * bh;
-      const int v = rr >> 4, i = rr & 15, st = c - 1 + v;
-      if (band != wband || v != wv || st > wst0 || st < wst0 - 31) {
-        wband = band; wv = v; wst0 = st;
-        const int s2 = st - lane;
-        unsigned long long w = 0;
-        if (s2 >= v) w = ptr[ptr_word_index(nv, T, band, s2, v)];
-        wlo = (unsigned)w; whi = (unsigned)(w >> 32);
-      }
-      const int src = wst0 - st;
-      const unsigned lo = __shfl_sync(kFull, wlo, src), hi = __shfl_sync(kFull, whi, src);
-      const unsigned nib = ((i < 8 ? lo : hi) >> (4 * (i & 7))) & 15u;
-      if (state == 0) {
-        if (nib & kFromH) { state = 1; continue; }
-        if (nib & kVCand) { state = 2; continue; }
-        op = 's'; --r; --c;
-      } else if (state == 1) {
-        if (nib & kHOpen) state = 0;
-        op = 'h'; --c;
-      } else {
-        if (nib & kVOpen) state = 0;
-        op = 'v'; --r;
-      }
+    if (r == 0) { for (int j = lane; j < c; j += 32) ops_rev[k + j] = 'h'; k += c; break; }   // row 0: only FROMH is ever set
+    if (c == 0) { for (int j = lane; j < r; j += 32) ops_rev[k + j] = 'v'; k += r; break; }   // column 0
+    const int band = (r - 1) / bh, rr = (r - 1) - band * bh;
+    const int v = rr >> 4, i = rr & 15, st = c - 1 + v;
+    if (band != wband || v != wv || st > wst0 || st < wst0 - 31) {
+      wband = band; wv = v; wst0 = st;
+      const int s2 = st - lane;
+      unsigned long long w = 0;
+      if (s2 >= v) w = ptr[ptr_word_index(nv, T, band, s2, v)];
+      wlo = (unsigned)w; whi = (unsigned)(w >> 32);
     }
-    if (lane == (k & 31)) mych = op;
-    ++k;
-    if ((k & 31) == 0) ops_rev[k - 32 + lane] = (uint8_t)mych;
+    const int off = wst0 - st, j = lane - off;            // this lane looks at the j-th cell of the run (j >= 0)
+    unsigned char ch;
+    int run;
+    if (state == 1) {
+      const int cnt = min(32 - off, c);
+      const unsigned hit = __ballot_sync(kFull, j >= 0 && j < cnt && (ptr_nibble(wlo, whi, i) & kHOpen));
+      const int first = hit ? __ffs(hit) - 1 - off : -1;
+      run = first >= 0 ? first + 1 : cnt;
+      ch = 'h';
+      c -= run;
+      if (first >= 0) state = 0;
+    } else if (state == 0) {
+      const int cnt = min(min(32 - off, c), i + 1);
+      const unsigned nib = (j >= 0 && j < cnt) ? ptr_nibble(wlo, whi, i - j) : 0u;
+      const unsigned brk = __ballot_sync(kFull, (nib & (kFromH | kVCand)) != 0u);
+      run = brk ? __ffs(brk) - 1 - off : cnt;
+      ch = 's';
+      r -= run; c -= run;
+      if (run < cnt) {                                     // the cell that stopped the diagonal decides the gap state
+        const unsigned nb = __shfl_sync(kFull, nib, off + run);
+        state = (nb & kFromH) ? 1 : 2;
+      }
+    } else {
+      const unsigned lo = __shfl_sync(kFull, wlo, off), hi = __shfl_sync(kFull, whi, off);
+      const int cnt = i + 1;
+      const unsigned hit = __ballot_sync(kFull, lane < cnt && (ptr_nibble(lo, hi, i - min(lane, i)) & kVOpen));
+      const int first = hit ? __ffs(hit) - 1 : -1;
+      run = first >= 0 ? first + 1 : cnt;
+      ch = 'v';
+      r -= run;
+      if (first >= 0) state = 0;
+    }
+    if (lane < run) ops_rev[k + lane] = ch;
+    k += run;
   }
-  if ((k & 31) != 0 && lane < (k & 31)) ops_rev[(k & ~31) + lane] = (uint8_t)mych;
   return k;
 }
 

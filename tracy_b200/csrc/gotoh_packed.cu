@@ -125,7 +125,7 @@ __device__ __forceinline__ int walk_traceback_packed(const uint4* __restrict__ p
   return k;
 }
 
-template <bool TRACEBACK>
+template <bool TRACEBACK, bool VFREE>
 __global__ void __launch_bounds__(kPkWarps * 32)
 gotoh_packed_kernel(const GotohBatch B) {
   extern __shared__ int smem_pk[];
@@ -135,8 +135,11 @@ gotoh_packed_kernel(const GotohBatch B) {
   int* const tabB = tabA + kPkTabWords;
   const float fmatch = (float)B.match, fmismatch = (float)B.mismatch;
   const int go = B.go, ge = B.ge, goe = B.go + B.ge;
-  const bool hfree = B.hfree != 0, vfree = B.vfree != 0;
+  const bool hfree = B.hfree != 0;
+  constexpr bool vfree = VFREE;
   const int src = (lane + 31) & 31;
+  // lane 0 splices the feed into the rotated words, every other lane takes the rotated word as is: one PRMT either way
+  const unsigned sel_us = lane == 0 ? 0x5410u : 0x7654u, sel_uv = lane == 0 ? 0x5432u : 0x7654u, sel_cl = lane == 0 ? 0x3340u : 0x7654u;
 
   uint4* const ptr = TRACEBACK ? reinterpret_cast<uint4*>(B.ptr_scratch + (unsigned long long)slot * B.ptr_slot_words) : nullptr;
   unsigned* const rowbuf0 = reinterpret_cast<unsigned*>(B.rowbuf + (unsigned long long)slot * B.rowbuf_slot);
@@ -235,6 +238,7 @@ gotoh_packed_kernel(const GotohBatch B) {
       // column classes of this lane for the coming step (lo | hi << 8); columns outside 1..n use class 0 (never read back)
       unsigned cur = 0;
       { const unsigned f0 = __shfl_sync(kFull, cchunk, 0); if (lane == 0) cur = f0; }
+      const int cap_st = lane == m_lane ? n - 1 + lane + 32 * m_half : -1;
       uint4* pw = TRACEBACK ? ptr + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
 
       for (int st = 0; st < T; ++st, pw += 32) {
@@ -245,22 +249,15 @@ gotoh_packed_kernel(const GotohBatch B) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { xa[j] = pa[j * 32]; xb[j] = pb[j * 32]; }
 
-        unsigned us = __shfl_sync(kFull, bs, src), uv = __shfl_sync(kFull, bv, src);
         const unsigned fsv = __shfl_sync(kFull, tchunk, st & 31);
-        if (lane == 0) {
-          us = __byte_perm(fsv, us, 0x5410);                  // lo: top row S, hi: lane 31's half-band-A bottom S
-          uv = __byte_perm(fsv, uv, 0x5432);
-        }
+        unsigned us = __byte_perm(fsv, __shfl_sync(kFull, bs, src), sel_us);    // lane 0: lo = top row S, hi = lane 31's half-band-A bottom S
+        unsigned uv = __byte_perm(fsv, __shfl_sync(kFull, bv, src), sel_uv);
         // classes for the next step: rotate, lane 0 takes the next column from the feed
         if ((st & 31) == 31) { tchunk = tnext; cchunk = cnext; tnext = feed_sv(st + 34 + lane); cnext = feed_cls(st + 34 + lane); }
-        {
-          const unsigned rc = __shfl_sync(kFull, cur, src);
-          const unsigned fcl = __shfl_sync(kFull, cchunk, (st + 1) & 31);
-          cur = lane == 0 ? (fcl | ((rc & 0xffu) << 8)) : rc;
-        }
+        cur = __byte_perm(__shfl_sync(kFull, cchunk, (st + 1) & 31), __shfl_sync(kFull, cur, src), sel_cl);
 
         const int c_lo = st - lane + 1, c_hi = c_lo - 32;
-        if (c_lo >= 1 && c_lo <= n + 32) {
+        if ((unsigned)(c_lo - 1) < (unsigned)(n + 32)) {
           if (c_lo == 33) {     // half-band B starts now: discard what the run-in steps left in the high halves
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
@@ -317,8 +314,8 @@ gotoh_packed_kernel(const GotohBatch B) {
             w.z = __byte_perm(acc[4], acc[5], 0x6240); w.w = __byte_perm(acc[6], acc[7], 0x6240);
             *pw = w;
           }
-          if (more && lane == 31 && c_hi >= 1 && c_hi <= n) bot[c_hi] = __byte_perm(bs, bv, 0x7632);   // S | V << 16 of row base+1024
-          if (!more && lane == m_lane && (m_half ? c_hi : c_lo) == n) {      // S[m][n] passes through this lane now
+          if (more) { if (lane == 31 && c_hi >= 1 && c_hi <= n) bot[c_hi] = __byte_perm(bs, bv, 0x7632); }   // S | V << 16 of row base+1024
+          else if (st == cap_st) {                                            // S[m][n] passes through this lane now
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) if (i == m_i) score_word = sl[i];
           }
@@ -354,32 +351,37 @@ bool gotoh_packed_eligible(int maxm, int maxn, int match, int mismatch, int go, 
   return true;   // per-pair decision is made on the device; ineligible pairs fall through to the general kernel
 }
 
-cudaError_t launch_gotoh_packed(bool traceback, const GotohBatch& B, int blocks, cudaStream_t stream) {
+template <bool TB_, bool VF_>
+static cudaError_t packed_launch_one(const GotohBatch& B, int blocks, cudaStream_t stream) {
   const size_t smem = packed_smem_bytes();
-  cudaError_t e;
-  if (traceback) {
-    e = cudaFuncSetAttribute(gotoh_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    gotoh_packed_kernel<true><<<blocks, kPkWarps * 32, smem, stream>>>(B);
-  } else {
-    e = cudaFuncSetAttribute(gotoh_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    gotoh_packed_kernel<false><<<blocks, kPkWarps * 32, smem, stream>>>(B);
-  }
+  cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  gotoh_packed_kernel<TB_, VF_><<<blocks, kPkWarps * 32, smem, stream>>>(B);
   return cudaGetLastError();
+}
+template <bool TB_, bool VF_>
+static cudaError_t packed_occ_one(int* out) {
+  const size_t smem = packed_smem_bytes();
+  cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, gotoh_packed_kernel<TB_, VF_>, kPkWarps * 32, smem);
+}
+
+cudaError_t launch_gotoh_packed(bool traceback, const GotohBatch& B, int blocks, cudaStream_t stream) {
+  const bool vf = B.vfree != 0;
+  if (traceback) return vf ? packed_launch_one<true, true>(B, blocks, stream) : packed_launch_one<true, false>(B, blocks, stream);
+  return vf ? packed_launch_one<false, true>(B, blocks, stream) : packed_launch_one<false, false>(B, blocks, stream);
 }
 
 cudaError_t gotoh_packed_blocks_per_sm(bool traceback, int* out) {
-  const size_t smem = packed_smem_bytes();
-  cudaError_t e;
-  if (traceback) {
-    e = cudaFuncSetAttribute(gotoh_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, gotoh_packed_kernel<true>, kPkWarps * 32, smem);
-  }
-  e = cudaFuncSetAttribute(gotoh_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the four instantiations differ by a handful of registers; size the grid by the tightest one
+  int a = 0, b = 0;
+  cudaError_t e = traceback ? packed_occ_one<true, true>(&a) : packed_occ_one<false, true>(&a);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, gotoh_packed_kernel<false>, kPkWarps * 32, smem);
+  e = traceback ? packed_occ_one<true, false>(&b) : packed_occ_one<false, false>(&b);
+  if (e != cudaSuccess) return e;
+  *out = a < b ? a : b;
+  return cudaSuccess;
 }
 
 }  // namespace tb

@@ -172,10 +172,12 @@ gotoh_packed_kernel(const GotohBatch B) {
     smin = __reduce_min_sync(kFull, smin); smax = __reduce_max_sync(kFull, smax);
     if (__any_sync(kFull, foreign)) continue;
     const int npass = (m + kPkRows - 1) / kPkRows;
-    // lowest real value: all-gap path to the far corner, one more open+extend, the 32 run-in/run-out columns, slack
-    const long long lb = 2ll * go + 2ll * goe + (long long)(npass * kPkRows + n + 34) * ge - 16 + 32ll * goe + 34ll * min(smin, 0);
+    // lowest value any field can take: all-gap path to the far corner, one more open+extend, and up to 63 run-in /
+    // run-out steps in which a half-band computes unread cells from in-range inputs (each step moves a value by at
+    // most |goe| down or smax up), plus slack
+    const long long lb = 2ll * go + 2ll * goe + (long long)(npass * kPkRows + n + 100) * ge - 16 + 72ll * goe + 72ll * min(smin, 0);
     const long long bias_ll = (long long)kPkNeg + 64 - lb;
-    const long long ub = (long long)max(smax, 0) * min(m, n) + 34ll * max(smax, 0);
+    const long long ub = (long long)max(smax, 0) * min(m, n) + 72ll * max(smax, 0);
     if (bias_ll + ub > kPkMaxField || smin < -16384 || smax > 16384) continue;   // leave status 0: the general kernel takes it
     const int bias = (int)bias_ll;
 
@@ -257,15 +259,19 @@ gotoh_packed_kernel(const GotohBatch B) {
         cur = __byte_perm(__shfl_sync(kFull, cchunk, (st + 1) & 31), __shfl_sync(kFull, cur, src), sel_cl);
 
         const int c_lo = st - lane + 1, c_hi = c_lo - 32;
-        if ((unsigned)(c_lo - 1) < (unsigned)(n + 32)) {
-          if (c_lo == 33) {     // half-band B starts now: discard what the run-in steps left in the high halves
+        {
+          // Every lane runs every step (no divergent guard): before a half-band's first column and after its last one the
+          // lane computes cells nobody reads; the state a half-band starts from is installed when its column 1 arrives.
+          if (c_lo == 1 || c_lo == 33) {
+            const unsigned keep = c_lo == 1 ? 0xffff0000u : 0x0000ffffu;
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
-              const int rhi = rtop_hi + i + 1;
-              sl[i] = (sl[i] & 0xffffu) | ((unsigned)((vfree ? 0 : go + rhi * ge) + bias) << 16);
-              hh[i] = (hh[i] & 0xffffu) | ((unsigned)kPkNeg << 16);
+              const int rlo = rtop_lo + i + 1, rhi = rtop_hi + i + 1;
+              const unsigned init = pk_dpx((vfree ? 0 : go + rhi * ge) + bias, (vfree ? 0 : go + rlo * ge) + bias);
+              sl[i] = (sl[i] & keep) | (init & ~keep);
+              hh[i] = (hh[i] & keep) | (pk_dpx(kPkNeg, kPkNeg) & ~keep);
             }
-            diag = (diag & 0xffffu) | ((unsigned)d0_hi << 16);
+            diag = (diag & keep) | (pk_dpx(d0_hi, d0_lo) & ~keep);
           }
           // vertical gap costs depend on the column (src/align.h:52-65): last column is free when vfree
           const int vge_lo = vfree && c_lo == n ? 0 : ge, vge_hi = vfree && c_hi == n ? 0 : ge;

@@ -16,8 +16,8 @@ namespace tb {
 cudaError_t launch_gotoh_general(int mode, bool traceback, const GotohBatch& B, int blocks, cudaStream_t stream);
 cudaError_t gotoh_general_blocks_per_sm(int mode, bool traceback, int* out);
 int gotoh_general_warps_per_block();
-cudaError_t launch_gotoh_packed(bool traceback, const GotohBatch& B, int blocks, cudaStream_t stream);
-cudaError_t gotoh_packed_blocks_per_sm(bool traceback, int* out);
+cudaError_t launch_gotoh_packed(bool traceback, int classes, const GotohBatch& B, int blocks, cudaStream_t stream);
+cudaError_t gotoh_packed_blocks_per_sm(bool traceback, int classes, int* out);
 int gotoh_packed_warps_per_block();
 bool gotoh_packed_eligible(int maxm, int maxn, int match, int mismatch, int go, int ge);
 unsigned long long gotoh_packed_ptr_words(int m, int n);
@@ -118,7 +118,7 @@ void accumulate(Shape& s, const int32_t* l1, const int32_t* l2, size_t n, bool p
 
 struct Plan {
   bool use_packed = false;
-  int blocks_packed = 0, blocks_general = 0;
+  int blocks_packed = 0, blocks_packed5 = 0, blocks_general = 0;   // packed: 4-class (ACGT) and 5-class (ACGTN) instantiations
   unsigned slots = 0;                      // warp slots that own scratch
   unsigned long long ptr_words = 0, rowbuf_elems = 0, ops_bytes = 0;
 };
@@ -133,16 +133,19 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
   p.use_packed = mode == tb::kModePS &&
                  tb::gotoh_packed_eligible(sh.maxm, sh.maxn, sc.match, sc.mismatch, sc.gap_open, sc.gap_extend) &&
                  getenv("TRACY_B200_NO_PACKED") == nullptr;
-  int bps_p = 0, wpb_p = 1;
+  int bps_p = 0, bps_p5 = 0, wpb_p = 1;
   if (p.use_packed) {
-    TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(traceback, &bps_p));
+    TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(traceback, 4, &bps_p));
+    TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(traceback, 5, &bps_p5));
     wpb_p = tb::gotoh_packed_warps_per_block();
-    if (bps_p < 1) p.use_packed = false;
+    if (bps_p < 1 || bps_p5 < 1) p.use_packed = false;
   }
   unsigned long long warps_g = (unsigned long long)ctx->sms * bps_g * wpb_g;
   unsigned long long warps_p = p.use_packed ? (unsigned long long)ctx->sms * bps_p * wpb_p : 0;
+  unsigned long long warps_p5 = p.use_packed ? (unsigned long long)ctx->sms * bps_p5 * wpb_p : 0;
   warps_g = std::min<unsigned long long>(warps_g, std::max<size_t>(npairs, 1));
   warps_p = std::min<unsigned long long>(warps_p, std::max<size_t>(npairs, 1));
+  warps_p5 = std::min<unsigned long long>(warps_p5, std::max<size_t>(npairs, 1));
 
   p.ptr_words = traceback ? std::max(sh.gen_words, sh.packed_words) : 0;
   p.rowbuf_elems = 2ull * (unsigned long long)(sh.maxn + 1);
@@ -158,10 +161,12 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
   unsigned long long max_slots = per_slot ? std::max<unsigned long long>(limit / per_slot, 1) : (1ull << 30);
   warps_g = std::min(warps_g, max_slots);
   warps_p = std::min(warps_p, max_slots);
+  warps_p5 = std::min(warps_p5, max_slots);
   p.blocks_general = (int)((warps_g + wpb_g - 1) / wpb_g);
   p.blocks_packed = p.use_packed ? (int)((warps_p + wpb_p - 1) / wpb_p) : 0;
+  p.blocks_packed5 = p.use_packed ? (int)((warps_p5 + wpb_p - 1) / wpb_p) : 0;
   p.slots = (unsigned)std::max<unsigned long long>((unsigned long long)p.blocks_general * wpb_g,
-                                                   (unsigned long long)p.blocks_packed * wpb_p);
+                                                   (unsigned long long)std::max(p.blocks_packed, p.blocks_packed5) * wpb_p);
   *out = p;
   return TB_OK;
 }
@@ -186,9 +191,11 @@ int enqueue_gotoh(tb_ctx* ctx, Lane& L, int mode, bool traceback, tb::GotohBatch
   L.timed = L.timed2 = false;
   TB_CUDA(ctx, cudaEventRecord(L.k0, L.stream));
   if (p.use_packed) {
-    B.counter = counters;
-    TB_CUDA(ctx, tb::launch_gotoh_packed(traceback, B, p.blocks_packed, L.stream));
-    ctx->launches++;
+    B.counter = counters;           // [0] queue head, [1] pairs completed by the packed kernels
+    TB_CUDA(ctx, tb::launch_gotoh_packed(traceback, 4, B, p.blocks_packed, L.stream));
+    B.counter = counters + 2;       // second queue head; its completion count lands in counters[3]
+    TB_CUDA(ctx, tb::launch_gotoh_packed(traceback, 5, B, p.blocks_packed5, L.stream));
+    ctx->launches += 2;
     L.timed = true;
   }
   TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
@@ -206,7 +213,7 @@ int collect_timing(tb_ctx* ctx, Lane& L) {
   float ms = 0;
   if (L.timed) { TB_CUDA(ctx, cudaEventElapsedTime(&ms, L.k0, L.k1)); ctx->last_fast_ms += ms; }
   if (L.timed2) { TB_CUDA(ctx, cudaEventElapsedTime(&ms, L.k1, L.k2)); ctx->last_general_ms += ms; }
-  if (L.timed && L.cnt.p) ctx->last_packed_pairs += static_cast<const unsigned int*>(L.cnt.p)[1];
+  if (L.timed && L.cnt.p) ctx->last_packed_pairs += static_cast<const unsigned int*>(L.cnt.p)[1] + static_cast<const unsigned int*>(L.cnt.p)[3];
   L.timed = L.timed2 = false;
   return TB_OK;
 }

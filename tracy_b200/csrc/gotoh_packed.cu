@@ -25,8 +25,8 @@ namespace tb {
 
 constexpr int kPkWarps = 2;                       // warps per block (40 KB of tables per block: five blocks per SM)
 constexpr int kPkRows = 1024;                     // DP rows per pass (two 512-row half-bands)
-constexpr int kPkTabWords = 5 * 512;              // one half-band table: [class A,C,G,T,N][q][lane][4] 32-bit entries
-constexpr int kPkSmemWordsPerWarp = 2 * kPkTabWords;
+// One half-band table: [class][q][lane][4] 32-bit entries = 2 KB per class. Two instantiations: CLASSES = 4 (A,C,G,T:
+// 16 KB per warp, 12 warps per SM) for windows without N, CLASSES = 5 (A,C,G,T,N: 20 KB per warp, 10 warps per SM).
 constexpr int kPkNeg = 2048;                      // field value standing in for the reference's -inf
 constexpr int kPkMaxField = 0x7bff - 16;          // largest field value for which fp16 compare == integer compare
 
@@ -125,9 +125,10 @@ __device__ __forceinline__ int walk_traceback_packed(const uint4* __restrict__ p
   return k;
 }
 
-template <bool TRACEBACK, bool VFREE>
+template <bool TRACEBACK, bool VFREE, int CLASSES>
 __global__ void __launch_bounds__(kPkWarps * 32)
 gotoh_packed_kernel(const GotohBatch B) {
+  constexpr int kPkTabWords = CLASSES * 512, kPkSmemWordsPerWarp = 2 * kPkTabWords;
   extern __shared__ int smem_pk[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned slot = blockIdx.x * kPkWarps + wib;
@@ -151,6 +152,7 @@ gotoh_packed_kernel(const GotohBatch B) {
     q = __shfl_sync(kFull, q, 0);
     if (q >= B.npairs) break;
     const int pi = B.order ? B.order[q] : q;
+    if (B.status[pi]) continue;                          // finished by an earlier kernel of this call
     const int m = B.a_len[pi], n = B.b_len[pi];
     if (m == 0 || n == 0) continue;                      // degenerate shapes: general kernel
     const float* const a = (const float*)B.a_base + B.a_off[pi];
@@ -168,7 +170,7 @@ gotoh_packed_kernel(const GotohBatch B) {
         smin = min(smin, s); smax = max(smax, s);
       }
     }
-    for (int j = lane; j < n; j += 32) foreign |= base_class(b[j]) == 5;   // characters outside ACGTN score 0: general kernel
+    for (int j = lane; j < n; j += 32) foreign |= base_class(b[j]) >= CLASSES;   // characters outside ACGTN score 0: general kernel
     smin = __reduce_min_sync(kFull, smin); smax = __reduce_max_sync(kFull, smax);
     if (__any_sync(kFull, foreign)) continue;
     const int npass = (m + kPkRows - 1) / kPkRows;
@@ -205,7 +207,7 @@ gotoh_packed_kernel(const GotohBatch B) {
         for (int k = 0; k < 5; ++k) p[k] = r0 < m ? a[(size_t)k * m + r0] : 0.0f;
         int* const tab = half ? tabB : tabA;
 #pragma unroll
-        for (int cls = 0; cls < 5; ++cls) {
+        for (int cls = 0; cls < CLASSES; ++cls) {
           const unsigned s = (unsigned)(r0 < m ? sub_onehot(p, cls, fmatch, fmismatch) : 0) & 0xffffu;
           tab[cls * 512 + at] = (int)(half ? s << 16 : s);
         }
@@ -345,46 +347,59 @@ gotoh_packed_kernel(const GotohBatch B) {
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
-static size_t packed_smem_bytes() { return (size_t)kPkWarps * kPkSmemWordsPerWarp * sizeof(int); }
+static size_t packed_smem_bytes(int classes) { return (size_t)kPkWarps * 2 * classes * 512 * sizeof(int); }
 int gotoh_packed_warps_per_block() { return kPkWarps; }
 unsigned long long gotoh_packed_ptr_words(int m, int n) { return packed_ptr_words_impl(m, n); }
 
 // Host-side plausibility (the kernel re-checks every pair with its real substitution range): standard non-positive gap
-// scores, and the largest shape of the batch fits the 15-bit field range assuming |sub| <= max(|match|, |mismatch|).
+// scores small enough that kPkNeg + goe stays a valid field. The per-pair decision is made on the device; pairs the
+// packed kernels decline fall through to the general kernel.
 bool gotoh_packed_eligible(int maxm, int maxn, int match, int mismatch, int go, int ge) {
   if (go > 0 || ge > 0 || maxm <= 0 || maxn <= 0) return false;
-  if (go < -512 || ge < -512 || match > 4096 || match < -4096 || mismatch > 4096 || mismatch < -4096) return false;   // kPkNeg + goe must stay >= 0
-  return true;   // per-pair decision is made on the device; ineligible pairs fall through to the general kernel
+  if (go < -512 || ge < -512 || match > 4096 || match < -4096 || mismatch > 4096 || mismatch < -4096) return false;
+  return true;
 }
 
-template <bool TB_, bool VF_>
+template <bool TB_, bool VF_, int CL_>
 static cudaError_t packed_launch_one(const GotohBatch& B, int blocks, cudaStream_t stream) {
-  const size_t smem = packed_smem_bytes();
-  cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = packed_smem_bytes(CL_);
+  cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_, CL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gotoh_packed_kernel<TB_, VF_><<<blocks, kPkWarps * 32, smem, stream>>>(B);
+  gotoh_packed_kernel<TB_, VF_, CL_><<<blocks, kPkWarps * 32, smem, stream>>>(B);
   return cudaGetLastError();
 }
-template <bool TB_, bool VF_>
+template <bool TB_, bool VF_, int CL_>
 static cudaError_t packed_occ_one(int* out) {
-  const size_t smem = packed_smem_bytes();
-  cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = packed_smem_bytes(CL_);
+  cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_, CL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, gotoh_packed_kernel<TB_, VF_>, kPkWarps * 32, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, gotoh_packed_kernel<TB_, VF_, CL_>, kPkWarps * 32, smem);
 }
 
-cudaError_t launch_gotoh_packed(bool traceback, const GotohBatch& B, int blocks, cudaStream_t stream) {
+// classes: 4 (windows over ACGT) or 5 (ACGTN)
+cudaError_t launch_gotoh_packed(bool traceback, int classes, const GotohBatch& B, int blocks, cudaStream_t stream) {
   const bool vf = B.vfree != 0;
-  if (traceback) return vf ? packed_launch_one<true, true>(B, blocks, stream) : packed_launch_one<true, false>(B, blocks, stream);
-  return vf ? packed_launch_one<false, true>(B, blocks, stream) : packed_launch_one<false, false>(B, blocks, stream);
+  if (classes == 4) {
+    if (traceback) return vf ? packed_launch_one<true, true, 4>(B, blocks, stream) : packed_launch_one<true, false, 4>(B, blocks, stream);
+    return vf ? packed_launch_one<false, true, 4>(B, blocks, stream) : packed_launch_one<false, false, 4>(B, blocks, stream);
+  }
+  if (traceback) return vf ? packed_launch_one<true, true, 5>(B, blocks, stream) : packed_launch_one<true, false, 5>(B, blocks, stream);
+  return vf ? packed_launch_one<false, true, 5>(B, blocks, stream) : packed_launch_one<false, false, 5>(B, blocks, stream);
 }
 
-cudaError_t gotoh_packed_blocks_per_sm(bool traceback, int* out) {
-  // the four instantiations differ by a handful of registers; size the grid by the tightest one
+cudaError_t gotoh_packed_blocks_per_sm(bool traceback, int classes, int* out) {
+  // the VFREE instantiations differ by a handful of registers; size the grid by the tighter one
   int a = 0, b = 0;
-  cudaError_t e = traceback ? packed_occ_one<true, true>(&a) : packed_occ_one<false, true>(&a);
-  if (e != cudaSuccess) return e;
-  e = traceback ? packed_occ_one<true, false>(&b) : packed_occ_one<false, false>(&b);
+  cudaError_t e;
+  if (classes == 4) {
+    e = traceback ? packed_occ_one<true, true, 4>(&a) : packed_occ_one<false, true, 4>(&a);
+    if (e != cudaSuccess) return e;
+    e = traceback ? packed_occ_one<true, false, 4>(&b) : packed_occ_one<false, false, 4>(&b);
+  } else {
+    e = traceback ? packed_occ_one<true, true, 5>(&a) : packed_occ_one<false, true, 5>(&a);
+    if (e != cudaSuccess) return e;
+    e = traceback ? packed_occ_one<true, false, 5>(&b) : packed_occ_one<false, false, 5>(&b);
+  }
   if (e != cudaSuccess) return e;
   *out = a < b ? a : b;
   return cudaSuccess;

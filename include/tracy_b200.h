@@ -147,6 +147,38 @@ typedef struct {
 
 int tb_decompose_sweep(tb_ctx* ctx, const tb_sweep_batch* batch, tb_sweep_result* res);
 
+/* ---- profile construction either side of the DP -----------------------------------------------------------------
+ * createProfile(Trace, BaseCalls, p, trimleft, trimright), reference src/profile.h:21-52, for a batch of traces (GPU).
+ * trace item t: int32 samples [4][nsamples] row-major (channels A,C,G,T = Trace::traceACGT), trace.len[t] = nsamples.
+ * bcpos item t: int32 basecall positions (BaseCalls::bcPos); primary/secondary share its off/len (chars).
+ * Output item t: float[6][sz] at out_base + out_off[t] with sz = nbc - (trim_left + trim_right) (no trimming when the two
+ * sum to >= nbc, as the reference does); sz is written to out_len[t]. The caller sizes every item for 6 * nbc floats. */
+typedef struct {
+  tb_arena trace;
+  tb_arena bcpos;
+  const char* primary_base;
+  const char* secondary_base;
+  const int32_t* trim_left;    /* [ntraces] or NULL (= 0) */
+  const int32_t* trim_right;   /* [ntraces] or NULL (= 0) */
+  size_t ntraces;
+  int32_t mem;                 /* TB_MEM_HOST or TB_MEM_DEVICE, for every pointer of the call incl. the outputs */
+} tb_profile_batch;
+int tb_create_profile(tb_ctx* ctx, const tb_profile_batch* batch, float* out_base, const int64_t* out_off, int32_t* out_len);
+
+/* reverseComplementProfile(p, out), reference src/profile.h:74-90, for a batch of float[6][len] profiles (GPU).
+ * `in` and the outputs live in `mem`; output item i goes to out_base + out_off[i] (6 * len[i] floats). */
+int tb_revcomp_profile(tb_ctx* ctx, const tb_arena* in, size_t n, int32_t mem, float* out_base, const int64_t* out_off);
+
+/* trimReferenceSlice(c, align, rs), reference src/fmindex.h:429-463 (host, O(L); it sits between two DP calls):
+ * from the gapped rows of gotoh(trace, refslice) compute the sub-slice [*ri, *ri + *risize) of the reference slice that
+ * the trace covers, padded by trim_left / trim_right, and the updated rs.pos (forward: += ri; reverse: += the tail). */
+int tb_trim_reference_slice(const char* row0, const char* row1, int32_t L, int32_t refslice_len, int32_t forward, uint32_t pos,
+                            int32_t trim_left, int32_t trim_right, int32_t* ri, int32_t* risize, uint32_t* new_pos);
+
+/* findBreakpoint(ptrace, bp), reference src/decompose.h:7-56 (host, double arithmetic kept literal): profile float[6][len]
+ * -> TraceBreakpoint {indelshift, traceleft, breakpoint, bestDiff}. */
+int tb_find_breakpoint(const float* profile, int32_t len, int32_t* indelshift, int32_t* traceleft, uint32_t* breakpoint, float* best_diff);
+
 const char* tb_version(void);
 
 #ifdef __cplusplus

@@ -145,6 +145,59 @@ class _Ref:
         L.ref_decompose_alleles.restype = C.c_int
         L.ref_bench_gotoh_ps.argtypes = [_f32p, C.c_char_p, C.c_int, C.c_int, C.c_int] + _SC + [C.c_int, _i32p]
         L.ref_bench_gotoh_ps.restype = C.c_longlong
+        L.ref_trim_reference_slice.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int, C.c_int,
+                                               C.c_char_p, C.c_int]
+        L.ref_trim_reference_slice.restype = C.c_int
+        L.ref_profile_from_alignment.argtypes = [C.c_char_p, C.c_int, C.c_int, _f32p]
+        _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+        _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        L.ref_rev_seq_based_on_dist.argtypes = [_f32p, _i64p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        L.ref_msa.argtypes = [_f32p, _i64p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int,
+                              np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), _i32p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ref_msa.restype = C.c_int
+
+    def trim_reference_slice(self, row0, row1, refslice, forward, pos, trim_left, trim_right):
+        out = C.create_string_buffer(len(refslice) + 1)
+        p = C.c_uint32(pos)
+        n = self.lib.ref_trim_reference_slice(bytes(row0), bytes(row1), len(row0), bytes(refslice), len(refslice), int(forward), C.byref(p),
+                                              trim_left, trim_right, out, len(refslice) + 1)
+        assert n >= 0
+        return out.raw[:n], p.value
+
+    def profile_from_alignment(self, rows):
+        rows = np.ascontiguousarray(rows, np.uint8)
+        out = np.zeros((6, rows.shape[1]), np.float32)
+        self.lib.ref_profile_from_alignment(rows.tobytes(), rows.shape[0], rows.shape[1], out)
+        return out
+
+    @staticmethod
+    def _pack(profiles):
+        profiles = [np.ascontiguousarray(p, np.float32) for p in profiles]
+        lens = np.array([p.shape[1] for p in profiles], np.int32)
+        off = np.concatenate([[0], np.cumsum(6 * lens.astype(np.int64))[:-1]]).astype(np.int64)
+        return np.concatenate([p.reshape(-1) for p in profiles]), off, lens
+
+    def rev_seq_based_on_dist(self, profiles, fwd, sc):
+        base, off, lens = self._pack(profiles)
+        f = np.array([1 if x else 0 for x in fwd], np.uint8)
+        self.lib.ref_rev_seq_based_on_dist(base, off, lens, len(profiles), *sc, f)
+        return [bool(x) for x in f]
+
+    def msa(self, profiles, sc, fraction_called=0.5):
+        base, off, lens = self._pack(profiles)
+        n = len(profiles)
+        cap = n * int(lens.astype(np.int64).sum()) + 16
+        rows = C.create_string_buffer(cap)
+        seqidx = np.zeros(n, np.uint32)
+        dist = np.zeros(n * n, np.int32)
+        ncap = int(lens.astype(np.int64).sum()) + 16
+        g, cs, q = C.create_string_buffer(ncap), C.create_string_buffer(ncap), C.create_string_buffer(ncap)
+        cl, nr = C.c_int(0), C.c_int(0)
+        ncol = self.lib.ref_msa(base, off, lens, n, *sc, fraction_called, rows, cap, seqidx, dist, g, cs, q, C.byref(cl), C.byref(nr))
+        assert ncol >= 0
+        nrow = nr.value
+        align = np.frombuffer(rows.raw[: nrow * ncol], np.uint8).reshape(nrow, ncol).copy()
+        return dict(rows=align, seqidx=seqidx[:nrow].copy(), dist=dist.reshape(n, n), gapped=g.raw[:ncol], cons=cs.raw[: cl.value], qual=q.raw[: cl.value])
 
     @staticmethod
     def _conv(x):

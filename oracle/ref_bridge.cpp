@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- not part of the shipped product path.
 //
-// extern "C" bridge over the UNMODIFIED tracy headers in /root/reference/src (abif.h, align.h,
-// gotoh.h, profile.h, decompose.h), compiled with the reference's own flags
+// extern "C" bridge over the UNMODIFIED tracy headers in /root/reference/src (abif.h, scf.h, align.h,
+// gotoh.h, fmindex.h, profile.h, decompose.h, msa.h), compiled with the reference's own flags
 // (Makefile:26,51: -std=c++17 -O3 -fno-tree-vectorize -DNDEBUG, no -march => no FMA) against the
 // container-only Boost stand-ins in oracle/shim/.  Output goes to oracle/_ref/libtracy_ref.so
 // (git-ignored; it travels to the GPU box).  Only tests/, __graft_entry__.smoke() and bench.py's
@@ -15,34 +15,20 @@
 #include <vector>
 #include <utility>
 
-#include "abif.h"      // Trace, BaseCalls, iupac()            (reference, unmodified)
-#include "align.h"     // DnaScore, AlignConfig, _createProfile (reference, unmodified)
-#include "gotoh.h"     // gotohScore, gotoh                     (reference, unmodified)
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sdsl/suffix_arrays.hpp>   // vendored header-only sdsl-lite under the reference tree (fmindex.h names sdsl::count)
 
-namespace tracy {
-// fmindex.h cannot be included (it pulls in htslib and heavy Boost); decompose.h and profile.h only need
-// these two plain records from it (field names as in src/fmindex.h:28-37 and :51-56).
-struct ReferenceSlice {
-  bool forward;
-  int32_t filetype;
-  uint32_t kmersupport;
-  uint32_t pos;
-  std::string chr;
-  std::string refslice;
-  ReferenceSlice() : forward(true), filetype(-1), kmersupport(0), pos(0) {}
-};
-struct TraceBreakpoint {
-  bool indelshift;
-  bool traceleft;
-  uint32_t breakpoint;
-  float bestDiff;
-};
-// profile.h:60-72 has a createProfile(TConfig, ReferenceSlice, ...) overload that names readab/basecall;
-// both are declared in abif.h, so the header compiles as is.
-}  // namespace tracy
-
-#include "profile.h"    // createProfile, reverseComplementProfile (reference, unmodified)
-#include "decompose.h"  // findBreakpoint, decomposeAlleles, ...    (reference, unmodified)
+#include "tracy_boost_stubs.hpp"    // container-only stand-ins for boost string/path/timestamp helpers (no algorithms)
+#include "abif.h"      // Trace, BaseCalls, iupac()                       (reference, unmodified)
+#include "scf.h"       // traceFormat (named by fmindex.h)                (reference, unmodified)
+#include "align.h"     // DnaScore, AlignConfig, _createProfile           (reference, unmodified)
+#include "gotoh.h"     // gotohScore, gotoh                               (reference, unmodified)
+#include "fmindex.h"   // ReferenceSlice, TraceBreakpoint, trimReferenceSlice (reference, unmodified; htslib/sdsl only declared)
+#include "profile.h"   // createProfile, reverseComplementProfile         (reference, unmodified)
+#include "decompose.h" // findBreakpoint, decomposeAlleles, ...           (reference, unmodified)
+#include "msa.h"       // distanceMatrix, upgma, palign, consensus, revSeqBasedOnDist, msa (reference, unmodified)
 
 namespace {
 typedef boost::multi_array<float, 2> TProfile;
@@ -183,6 +169,73 @@ int ref_decompose_alleles(const char* row0, const char* row1, int L, char* prima
   int n = (int)table.size();
   for (int i = 0; i < n && i < dcp_cap; ++i) { dcp[2 * i] = table[i].first; dcp[2 * i + 1] = table[i].second; }
   return n;
+}
+
+// trimReferenceSlice (src/fmindex.h:429-463): returns the trimmed slice in out (capacity cap), *pos updated.
+int ref_trim_reference_slice(const char* row0, const char* row1, int L, const char* refslice, int reflen, int forward, uint32_t* pos,
+                             int trimLeft, int trimRight, char* out, int cap) {
+  TAlign al(boost::extents[2][L]);
+  for (int j = 0; j < L; ++j) { al[0][j] = row0[j]; al[1][j] = row1[j]; }
+  tracy::ReferenceSlice rs; rs.refslice.assign(refslice, refslice + reflen); rs.forward = forward != 0; rs.pos = *pos;
+  SweepCfg c; c.trimLeft = (uint16_t)trimLeft; c.trimRight = (uint16_t)trimRight; c.maxindel = 0; c.madc = 0;
+  tracy::trimReferenceSlice(c, al, rs);
+  *pos = rs.pos;
+  int n = (int)rs.refslice.size();
+  if (n > cap) return -n;
+  std::memcpy(out, rs.refslice.data(), n);
+  return n;
+}
+
+// _createProfile(char MSA -> profile) (src/align.h:138-180). rows: nrow x ncol chars row-major.
+void ref_profile_from_alignment(const char* rows, int nrow, int ncol, float* out /*[6][ncol]*/) {
+  TAlign al(boost::extents[nrow][ncol]);
+  for (int i = 0; i < nrow; ++i) for (int j = 0; j < ncol; ++j) al[i][j] = rows[(size_t)i * ncol + j];
+  TProfile p; tracy::_createProfile(al, p);
+  for (int k = 0; k < 6; ++k) for (int j = 0; j < ncol; ++j) out[(size_t)k * ncol + j] = p[k][j];
+}
+
+namespace {
+struct MsaCfg { tracy::DnaScore<int32_t> aliscore; float fractionCalled; MsaCfg(int a, int b, int c, int d, float f) : aliscore(a, b, c, d), fractionCalled(f) {} };
+typedef std::vector<TProfile> TProfiles;
+void load_profiles(const float* base, const int64_t* off, const int32_t* len, int n, TProfiles& out) {
+  out.resize(n);
+  for (int i = 0; i < n; ++i) load_profile(base + off[i], len[i], out[i]);
+}
+}  // namespace
+
+// revSeqBasedOnDist (src/msa.h:243-328): fwd[i] in/out (1 = forward). The progress dots it prints go to stdout as upstream.
+void ref_rev_seq_based_on_dist(const float* base, const int64_t* off, const int32_t* len, int n, int match, int mismatch, int go, int ge,
+                               uint8_t* fwd) {
+  TProfiles seq; load_profiles(base, off, len, n, seq);
+  std::vector<bool> f(n);
+  for (int i = 0; i < n; ++i) f[i] = fwd[i] != 0;
+  MsaCfg c(match, mismatch, go, ge, 0.5f);
+  tracy::revSeqBasedOnDist(c, seq, f);
+  for (int i = 0; i < n; ++i) fwd[i] = f[i];
+}
+
+// msa (src/msa.h:330-368) followed by consensus (src/msa.h:162-239). Outputs: the alignment rows (nrow x ncol, row-major,
+// capacity cap chars), the leaf order seqidx[nrow], the distance matrix d[n][n] (upper triangle as distanceMatrix fills it),
+// gapped consensus / consensus / quality strings. Returns ncol (or -needed when cap is too small).
+int ref_msa(const float* base, const int64_t* off, const int32_t* len, int n, int match, int mismatch, int go, int ge, float fractionCalled,
+            char* rows, int cap, uint32_t* seqidx, int32_t* dist, char* gapped, char* cons, char* qual, int* conslen, int* nrow_out) {
+  TProfiles sps; load_profiles(base, off, len, n, sps);
+  MsaCfg c(match, mismatch, go, ge, fractionCalled);
+  boost::multi_array<int32_t, 2> d(boost::extents[2 * n + 1][2 * n + 1]);
+  for (int i = 0; i < 2 * n + 1; ++i) for (int j = 0; j < 2 * n + 1; ++j) d[i][j] = -1;
+  tracy::distanceMatrix(c, sps, d);
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) dist[(size_t)i * n + j] = j > i ? d[i][j] : 0;
+  TAlign al; std::vector<uint32_t> sidx;
+  tracy::msa(c, sps, al, sidx);
+  const int nrow = (int)al.shape()[0], ncol = (int)al.shape()[1];
+  *nrow_out = nrow;
+  if ((long long)nrow * ncol > cap) return -(nrow * ncol);
+  for (int i = 0; i < nrow; ++i) { for (int j = 0; j < ncol; ++j) rows[(size_t)i * ncol + j] = al[i][j]; seqidx[i] = sidx[i]; }
+  std::string g, cs, q;
+  tracy::consensus(c, al, g, cs, q, false);
+  std::memcpy(gapped, g.data(), g.size()); std::memcpy(cons, cs.data(), cs.size()); std::memcpy(qual, q.data(), q.size());
+  *conslen = (int)cs.size();
+  return ncol;
 }
 
 // Timed CPU baseline helper: runs `npairs` profile-x-sequence gotoh() calls back to back (the reference's

@@ -218,6 +218,44 @@ class Context:
             fins[t, nins[t]:] = 0
         return fref, fins, g
 
+    # ---- profile construction (reference src/profile.h) -------------------------------------------------------
+    def create_profile(self, traces, bcpos, primary, secondary, trim_left=None, trim_right=None):
+        """createProfile(Trace, BaseCalls, p, trimleft, trimright) for a batch (reference src/profile.h:21-52).
+        traces: list of int32[4][nsamples] (Trace::traceACGT); bcpos: list of int32[nbc]; primary/secondary: byte strings.
+        Returns a list of float32[6][sz] profiles."""
+        n = len(traces)
+        tr = [np.ascontiguousarray(t, np.int32) for t in traces]
+        for t in tr:
+            if t.ndim != 2 or t.shape[0] != 4:
+                raise ValueError("a trace is int32[4][nsamples] (channels A,C,G,T)")
+        bp = [np.ascontiguousarray(b, np.int32) for b in bcpos]
+        tlen = np.array([t.shape[1] for t in tr], np.int32)
+        toff = np.concatenate([[0], np.cumsum(4 * tlen.astype(np.int64))[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        tbase = np.concatenate([t.reshape(-1) for t in tr]) if n else np.zeros(1, np.int32)
+        pri, sec = pack_seqs(primary), pack_seqs(secondary)
+        blen = np.array([len(b) for b in bp], np.int32)
+        if not (np.array_equal(pri.len, blen) and np.array_equal(sec.len, blen)):
+            raise ValueError("bcpos, primary and secondary must have one entry per basecall")
+        bbase = np.concatenate(bp) if n and blen.sum() else np.zeros(1, np.int32)
+        ooff = np.concatenate([[0], np.cumsum(6 * blen.astype(np.int64))[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        out = np.zeros(max(int(6 * blen.astype(np.int64).sum()), 1), np.float32)
+        olen = np.zeros(max(n, 1), np.int32)
+        tl = None if trim_left is None else np.ascontiguousarray(np.broadcast_to(trim_left, (n,)), np.int32)
+        trr = None if trim_right is None else np.ascontiguousarray(np.broadcast_to(trim_right, (n,)), np.int32)
+        b = capi.ProfileBatch(capi.Arena(_ptr(tbase), _ptr(toff), _ptr(tlen)), capi.Arena(_ptr(bbase), _ptr(pri.off), _ptr(blen)),
+                              _ptr(pri.base), _ptr(sec.base), _ptr(tl), _ptr(trr), n, capi.TB_MEM_HOST)
+        self._check(self._lib.tb_create_profile(self._h, C.byref(b), _ptr(out), _ptr(ooff), _ptr(olen)))
+        return [out[ooff[i]: ooff[i] + 6 * olen[i]].reshape(6, olen[i]).copy() for i in range(n)]
+
+    def revcomp_profile(self, profiles):
+        """reverseComplementProfile for a batch of float[6][len] profiles (reference src/profile.h:74-90)."""
+        a = profiles if isinstance(profiles, Arena) else pack_profiles(profiles)
+        out = np.zeros(max(int(6 * a.len.astype(np.int64).sum()), 1), np.float32)
+        ooff = np.concatenate([[0], np.cumsum(6 * a.len.astype(np.int64))[:-1]]).astype(np.int64) if a.n else np.zeros(0, np.int64)
+        arena = capi.Arena(_ptr(a.base), _ptr(a.off), _ptr(a.len))
+        self._check(self._lib.tb_revcomp_profile(self._h, C.byref(arena), a.n, capi.TB_MEM_HOST, _ptr(out), _ptr(ooff)))
+        return [out[ooff[i]: ooff[i] + 6 * a.len[i]].reshape(6, a.len[i]).copy() for i in range(a.n)]
+
     # ---- helpers ------------------------------------------------------------------------------------------
     def rows_from_ops(self, kind, a1, a2, ops):
         """Gapped rows as gotoh() leaves them in `align` (reference src/align.h:196-293)."""
@@ -243,6 +281,29 @@ def rows_from_ops(kind, a1, a2, ops):
     if rc != capi.TB_OK:
         raise TracyError(rc, lib.tb_strerror(rc).decode())
     return r0.raw[:L], r1.raw[:L]
+
+
+def trim_reference_slice(row0, row1, refslice, forward=True, pos=0, trim_left=0, trim_right=0):
+    """trimReferenceSlice(c, align, rs), reference src/fmindex.h:429-463. Returns (trimmed refslice, new pos)."""
+    lib = capi.lib()
+    row0, row1, refslice = bytes(row0), bytes(row1), bytes(refslice)
+    ri, rsz, npos = C.c_int32(), C.c_int32(), C.c_uint32()
+    rc = lib.tb_trim_reference_slice(row0, row1, len(row0), len(refslice), int(bool(forward)), pos, trim_left, trim_right,
+                                     C.byref(ri), C.byref(rsz), C.byref(npos))
+    if rc != capi.TB_OK:
+        raise TracyError(rc, lib.tb_strerror(rc).decode())
+    return refslice[ri.value: ri.value + rsz.value], npos.value
+
+
+def find_breakpoint(profile):
+    """findBreakpoint(ptrace, bp), reference src/decompose.h:7-56 -> dict(indelshift, traceleft, breakpoint, bestDiff)."""
+    lib = capi.lib()
+    p = np.ascontiguousarray(profile, np.float32)
+    a, b, c, d = C.c_int32(), C.c_int32(), C.c_uint32(), C.c_float()
+    rc = lib.tb_find_breakpoint(p.ctypes.data_as(C.c_void_p), p.shape[1], C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+    if rc != capi.TB_OK:
+        raise TracyError(rc, lib.tb_strerror(rc).decode())
+    return dict(indelshift=bool(a.value), traceleft=bool(b.value), breakpoint=c.value, bestDiff=d.value)
 
 
 # ---- single-pair mirrors of the reference call shapes --------------------------------------------------------

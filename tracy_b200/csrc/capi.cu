@@ -1,6 +1,7 @@
 // C ABI of tracy_b200 (include/tracy_b200.h): context, scratch sizing, host<->device staging, launches.
 // Host code only; the kernels live in gotoh_general.cu / gotoh_packed.cu / sweep.cu.
 #include <algorithm>
+#include <cmath>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +25,9 @@ unsigned long long gotoh_packed_ptr_words(int m, int n);
 
 
 cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
+cudaError_t launch_create_profile(const ProfileBatch& P, int ntraces, cudaStream_t stream);
+cudaError_t launch_revcomp_profile(const float* in_base, const int64_t* in_off, const int32_t* len, float* out_base, const int64_t* out_off,
+                                   int n, cudaStream_t stream);
 }  // namespace tb
 
 namespace {
@@ -588,6 +592,183 @@ int tb_decompose_sweep(tb_ctx* ctx, const tb_sweep_batch* batch, tb_sweep_result
   ctx->d2h += 2 * out_elems * 4 + (res->grid ? out_elems * (size_t)os * 4 : 0);
   TB_CUDA(ctx, cudaStreamSynchronize(st));
   TB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_sweep_ms, L.k0, L.k1));
+  return TB_OK;
+}
+
+// ---- profile construction ---------------------------------------------------------------------------------------
+namespace {
+// Stream-ordered staging of one host array (freed by the caller after the stream drains).
+struct Staged {
+  std::vector<void*> bufs;
+  cudaStream_t st;
+  explicit Staged(cudaStream_t s) : st(s) {}
+  ~Staged() { for (void* p : bufs) cudaFreeAsync(p, st); }
+  cudaError_t alloc(void** out, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 1, st);
+    if (e == cudaSuccess) bufs.push_back(*out);
+    return e;
+  }
+  cudaError_t up(void** out, const void* src, size_t bytes) {
+    cudaError_t e = alloc(out, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(*out, src, bytes, cudaMemcpyHostToDevice, st);
+  }
+};
+}  // namespace
+
+int tb_create_profile(tb_ctx* ctx, const tb_profile_batch* b, float* out_base, const int64_t* out_off, int32_t* out_len) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (!b || !out_base || !out_off || !out_len) return fail(ctx, TB_ERR_INVALID, "null batch/output");
+  const size_t nt = b->ntraces;
+  if (nt == 0) return TB_OK;
+  if (nt > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "ntraces too large");
+  if (!b->trace.base || !b->trace.off || !b->trace.len || !b->bcpos.base || !b->bcpos.off || !b->bcpos.len || !b->primary_base || !b->secondary_base)
+    return fail(ctx, TB_ERR_INVALID, "null pointer in profile batch");
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  Lane& L = ctx->lanes[0];
+  cudaStream_t st = L.stream;
+  tb::ProfileBatch P{};
+  if (b->mem == TB_MEM_DEVICE) {
+    P.trace_base = (const int32_t*)b->trace.base; P.trace_off = b->trace.off; P.trace_len = b->trace.len;
+    P.bcpos_base = (const int32_t*)b->bcpos.base; P.pri_base = b->primary_base; P.sec_base = b->secondary_base;
+    P.bc_off = b->bcpos.off; P.bc_len = b->bcpos.len; P.trim_left = b->trim_left; P.trim_right = b->trim_right;
+    P.out_base = out_base; P.out_off = out_off; P.out_len = out_len;
+    TB_CUDA(ctx, tb::launch_create_profile(P, (int)nt, st));
+    ctx->launches++;
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    return TB_OK;
+  }
+  if (b->mem != TB_MEM_HOST) return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST or TB_MEM_DEVICE");
+  long long tmax = 0, bmax = 0, omax = 0;
+  for (size_t i = 0; i < nt; ++i) {
+    if (b->trace.len[i] < 0 || b->bcpos.len[i] < 0 || b->trace.off[i] < 0 || b->bcpos.off[i] < 0 || out_off[i] < 0)
+      return fail(ctx, TB_ERR_INVALID, "negative offset/length");
+    tmax = std::max<long long>(tmax, b->trace.off[i] + 4ll * b->trace.len[i]);
+    bmax = std::max<long long>(bmax, b->bcpos.off[i] + b->bcpos.len[i]);
+    omax = std::max<long long>(omax, out_off[i] + 6ll * b->bcpos.len[i]);
+  }
+  {
+    Staged S(st);
+    void *d_tr, *d_bp, *d_pri, *d_sec, *d_toff, *d_tlen, *d_boff, *d_blen, *d_tl = nullptr, *d_trr = nullptr, *d_out, *d_ooff, *d_olen;
+    TB_CUDA(ctx, S.up(&d_tr, b->trace.base, (size_t)tmax * 4)); TB_CUDA(ctx, S.up(&d_bp, b->bcpos.base, (size_t)bmax * 4));
+    TB_CUDA(ctx, S.up(&d_pri, b->primary_base, (size_t)bmax)); TB_CUDA(ctx, S.up(&d_sec, b->secondary_base, (size_t)bmax));
+    TB_CUDA(ctx, S.up(&d_toff, b->trace.off, nt * 8)); TB_CUDA(ctx, S.up(&d_tlen, b->trace.len, nt * 4));
+    TB_CUDA(ctx, S.up(&d_boff, b->bcpos.off, nt * 8)); TB_CUDA(ctx, S.up(&d_blen, b->bcpos.len, nt * 4));
+    if (b->trim_left) TB_CUDA(ctx, S.up(&d_tl, b->trim_left, nt * 4));
+    if (b->trim_right) TB_CUDA(ctx, S.up(&d_trr, b->trim_right, nt * 4));
+    TB_CUDA(ctx, S.up(&d_ooff, out_off, nt * 8));
+    TB_CUDA(ctx, S.alloc(&d_out, (size_t)omax * 4)); TB_CUDA(ctx, S.alloc(&d_olen, nt * 4));
+    ctx->h2d += (size_t)tmax * 4 + (size_t)bmax * 6 + nt * 32;
+    P.trace_base = (const int32_t*)d_tr; P.trace_off = (const int64_t*)d_toff; P.trace_len = (const int32_t*)d_tlen;
+    P.bcpos_base = (const int32_t*)d_bp; P.pri_base = (const char*)d_pri; P.sec_base = (const char*)d_sec;
+    P.bc_off = (const int64_t*)d_boff; P.bc_len = (const int32_t*)d_blen; P.trim_left = (const int32_t*)d_tl; P.trim_right = (const int32_t*)d_trr;
+    P.out_base = (float*)d_out; P.out_off = (const int64_t*)d_ooff; P.out_len = (int32_t*)d_olen;
+    TB_CUDA(ctx, tb::launch_create_profile(P, (int)nt, st));
+    ctx->launches++;
+    TB_CUDA(ctx, cudaMemcpyAsync(out_len, d_olen, nt * 4, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    // items may be sparse in the caller's output arena: copy each item's 6 * sz floats back
+    for (size_t i = 0; i < nt; ++i)
+      TB_CUDA(ctx, cudaMemcpyAsync(out_base + out_off[i], (const float*)d_out + out_off[i], (size_t)6 * out_len[i] * 4, cudaMemcpyDeviceToHost, st));
+    ctx->d2h += (size_t)omax * 4 + nt * 4;
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return TB_OK;
+}
+
+int tb_revcomp_profile(tb_ctx* ctx, const tb_arena* in, size_t n, int32_t mem, float* out_base, const int64_t* out_off) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (!in || !out_base || !out_off) return fail(ctx, TB_ERR_INVALID, "null input/output");
+  if (n == 0) return TB_OK;
+  if (n > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "too many profiles");
+  if (!in->base || !in->off || !in->len) return fail(ctx, TB_ERR_INVALID, "null arena pointer");
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->lanes[0].stream;
+  if (mem == TB_MEM_DEVICE) {
+    TB_CUDA(ctx, tb::launch_revcomp_profile((const float*)in->base, in->off, in->len, out_base, out_off, (int)n, st));
+    ctx->launches++;
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    return TB_OK;
+  }
+  if (mem != TB_MEM_HOST) return fail(ctx, TB_ERR_INVALID, "mem must be TB_MEM_HOST or TB_MEM_DEVICE");
+  long long imax = 0, omax = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (in->len[i] < 0 || in->off[i] < 0 || out_off[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative offset/length");
+    imax = std::max<long long>(imax, in->off[i] + 6ll * in->len[i]);
+    omax = std::max<long long>(omax, out_off[i] + 6ll * in->len[i]);
+  }
+  {
+    Staged S(st);
+    void *d_in, *d_ioff, *d_len, *d_ooff, *d_out;
+    TB_CUDA(ctx, S.up(&d_in, in->base, (size_t)imax * 4)); TB_CUDA(ctx, S.up(&d_ioff, in->off, n * 8));
+    TB_CUDA(ctx, S.up(&d_len, in->len, n * 4)); TB_CUDA(ctx, S.up(&d_ooff, out_off, n * 8));
+    TB_CUDA(ctx, S.alloc(&d_out, (size_t)omax * 4));
+    TB_CUDA(ctx, tb::launch_revcomp_profile((const float*)d_in, (const int64_t*)d_ioff, (const int32_t*)d_len, (float*)d_out, (const int64_t*)d_ooff, (int)n, st));
+    ctx->launches++;
+    for (size_t i = 0; i < n; ++i)
+      TB_CUDA(ctx, cudaMemcpyAsync(out_base + out_off[i], (const float*)d_out + out_off[i], (size_t)6 * in->len[i] * 4, cudaMemcpyDeviceToHost, st));
+    ctx->h2d += (size_t)imax * 4 + n * 20; ctx->d2h += (size_t)omax * 4;
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return TB_OK;
+}
+
+int tb_trim_reference_slice(const char* row0, const char* row1, int32_t L, int32_t refslice_len, int32_t forward, uint32_t pos,
+                            int32_t trim_left, int32_t trim_right, int32_t* ri_out, int32_t* risize_out, uint32_t* new_pos) {
+  if (!row0 || !row1 || L < 0 || refslice_len < 0 || !ri_out || !risize_out || !new_pos) return TB_ERR_INVALID;
+  // reference src/fmindex.h:432-446: ri = reference characters before the first trace column; [s, e) = trace extent
+  uint32_t ri = 0;
+  int32_t s = -1, e = -1;
+  for (int32_t j = 0; j < L; ++j) {
+    if (row0[j] != '-') { if (s == -1) s = j; e = j + 1; }
+    if (s == -1 && row1[j] != '-') ++ri;
+  }
+  uint32_t risize = 0;
+  for (int32_t j = s; j < e; ++j) if (row1[j] != '-') ++risize;
+  const uint32_t tl = (uint16_t)trim_left, tr = (uint16_t)trim_right;       // config fields are uint16_t (src/sage.h:37-56)
+  if (ri >= tl) { ri -= tl; risize += tl; }                                  // src/fmindex.h:447-450
+  if (ri + risize + tr < (uint32_t)refslice_len) risize += tr;               // src/fmindex.h:451
+  // std::string::substr(ri, risize) clamps the length to the end of the slice (and throws when ri > size)
+  if (ri > (uint32_t)refslice_len) return TB_ERR_INVALID;
+  const uint32_t eff = std::min<uint32_t>(risize, (uint32_t)refslice_len - ri);
+  *ri_out = (int32_t)ri; *risize_out = (int32_t)eff;
+  if (forward) *new_pos = pos + ri;                                          // src/fmindex.h:454
+  else {
+    const int32_t offset = refslice_len - (int32_t)ri - (int32_t)risize;    // uses the UNclamped risize, as the reference does
+    *new_pos = offset < 0 ? pos : pos + (uint32_t)offset;                    // src/fmindex.h:455-462 (warning text not reproduced)
+  }
+  return TB_OK;
+}
+
+int tb_find_breakpoint(const float* p, int32_t len, int32_t* indelshift, int32_t* traceleft, uint32_t* breakpoint, float* best_diff) {
+  if (!p || len < 0 || !indelshift || !traceleft || !breakpoint || !best_diff) return TB_ERR_INVALID;
+  std::vector<double> sig((size_t)len);
+  for (int32_t j = 0; j < len; ++j) {                                        // src/decompose.h:11-24
+    double best = 0.001, snd = 0.001;
+    for (int i = 0; i < 6; ++i) {
+      const float v = p[(size_t)i * len + j];
+      if (v > best) { snd = best; best = v; }
+      else if (v > snd) snd = v;
+    }
+    sig[j] = best - snd;
+  }
+  float bestDiff = 0;                                                        // TraceBreakpoint::bestDiff is a float (src/fmindex.h:55)
+  bool left_flag = true;
+  uint32_t bp = 0;
+  const uint32_t w = 25, n = (uint32_t)len;
+  if (w < n) {
+    for (uint32_t i = w; i < n - w; ++i) {                                   // src/decompose.h:31-47
+      double ls = 0; for (uint32_t k = i - w; k < i; ++k) ls += sig[k];
+      const double left = ls / (double)w;
+      double rs = 0; for (uint32_t k = i; k < i + w; ++k) rs += sig[k];
+      const double right = rs / (double)w;
+      const double diff = std::abs(right - left);
+      if (diff > bestDiff) { bp = i; bestDiff = (float)diff; left_flag = !(left < right); }
+    }
+  }
+  int shift = 1;
+  if (bestDiff < 0.25) { shift = 0; bp = n; left_flag = true; bestDiff = 0; } // src/decompose.h:49-55
+  *indelshift = shift; *traceleft = left_flag ? 1 : 0; *breakpoint = bp; *best_diff = bestDiff;
   return TB_OK;
 }
 

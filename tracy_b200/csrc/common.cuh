@@ -46,6 +46,14 @@ struct SweepBatch {
   int32_t* fref; int32_t* fins; int32_t* grid; int out_stride;
 };
 
+// Device view of a createProfile batch (profile_ops.cu).
+struct ProfileBatch {
+  const int32_t* trace_base; const int64_t* trace_off; const int32_t* trace_len;   // item = int32[4][nsamples]
+  const int32_t* bcpos_base; const char* pri_base; const char* sec_base; const int64_t* bc_off; const int32_t* bc_len;
+  const int32_t* trim_left; const int32_t* trim_right;                              // may be nullptr
+  float* out_base; const int64_t* out_off; int32_t* out_len;
+};
+
 // reference src/align.h:121-136: A,C,G,T,N (case-insensitive) -> 0..4; '-' and everything else contribute
 // nothing to _score (row 5 is never read, src/align.h:113-114) -> class 5.
 __device__ __forceinline__ int base_class(unsigned char ch) {

@@ -295,19 +295,21 @@ def run_b200(args, rank, world, local_rank):
     e2e_val = cells_step * args.steps / (e2e_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
     dom = "packed_ms" if kern["packed_ms"] >= kern["general_ms"] else "general_ms"
-    dom_name = {"packed_ms": "gotoh_packed_kernel<traceback>", "general_ms": "gotoh_general_kernel<PS,traceback>"}[dom]
+    dom_name = {"packed_ms": "gotoh_packed_kernel<traceback, vfree=0, classes=4>", "general_ms": "gotoh_general_kernel<PS,traceback>"}[dom]
     k_ms = kern[dom] / args.steps
     bytes_launch = float(algorithmic_bytes_per_pair(m, n)) * P
     achieved = bytes_launch / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roof = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(float(P) * m * n),
             "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": bytes_launch,
-            "note": "integer DP: the binding limit is the INT32 ALU issue rate (DESIGN.md), HBM fraction is reported as the contract asks"}
+            "note": "integer DP: the binding limit is the ALU/FMA pipe issue rate (DESIGN.md section 4), HBM fraction is reported as the contract asks",
+            "packed_pairs_last_step": ctx.last_packed_pairs()}
     out = {
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": (se1["h2d_bytes"] - se0["h2d_bytes"]) // args.steps, "d2h_bytes_per_step": (se1["d2h_bytes"] - se0["d2h_bytes"]) // args.steps},
+                "h2d_bytes_per_step": world * (se1["h2d_bytes"] - se0["h2d_bytes"]) // args.steps,      # every rank moves the same amount
+                "d2h_bytes_per_step": world * (se1["d2h_bytes"] - se0["d2h_bytes"]) // args.steps},
         "gpu_launches": launches, "roofline": roof, "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
         "kernel_ms": {k: v / args.steps for k, v in kern.items()}, "parity": dict(chk, score_checksum=checksum), "gen_seconds": gen_s,
     }

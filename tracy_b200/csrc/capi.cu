@@ -17,8 +17,8 @@ namespace tb {
 cudaError_t launch_gotoh_general(int mode, bool traceback, const GotohBatch& B, int blocks, cudaStream_t stream);
 cudaError_t gotoh_general_blocks_per_sm(int mode, bool traceback, int* out);
 int gotoh_general_warps_per_block();
-cudaError_t launch_gotoh_packed(bool traceback, int classes, const GotohBatch& B, int blocks, cudaStream_t stream);
-cudaError_t gotoh_packed_blocks_per_sm(bool traceback, int classes, int* out);
+cudaError_t launch_gotoh_packed(int tbmode, int classes, const GotohBatch& B, int blocks, cudaStream_t stream);
+cudaError_t gotoh_packed_blocks_per_sm(int tbmode, int classes, int* out);
 int gotoh_packed_warps_per_block();
 bool gotoh_packed_eligible(int maxm, int maxn, int match, int mismatch, int go, int ge);
 unsigned long long gotoh_packed_ptr_words(int m, int n);
@@ -122,6 +122,7 @@ void accumulate(Shape& s, const int32_t* l1, const int32_t* l2, size_t n, bool p
 
 struct Plan {
   bool use_packed = false;
+  int tbmode = 0;                          // packed kernel traceback mode: 0 none, 1 flags, 2 checkpoints (default)
   int blocks_packed = 0, blocks_packed5 = 0, blocks_general = 0;   // packed: 4-class (ACGT) and 5-class (ACGTN) instantiations
   unsigned slots = 0;                      // warp slots that own scratch
   unsigned long long ptr_words = 0, rowbuf_elems = 0, ops_bytes = 0;
@@ -139,8 +140,10 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
                  getenv("TRACY_B200_NO_PACKED") == nullptr;
   int bps_p = 0, bps_p5 = 0, wpb_p = 1;
   if (p.use_packed) {
-    TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(traceback, 4, &bps_p));
-    TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(traceback, 5, &bps_p5));
+    const char* mode_env = getenv("TRACY_B200_TB_MODE");   // "flags" selects the pointer-flag fill (kept for comparison / profiling)
+    p.tbmode = !traceback ? 0 : (mode_env && std::strcmp(mode_env, "flags") == 0) ? 1 : 2;
+    TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(p.tbmode, 4, &bps_p));
+    TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(p.tbmode, 5, &bps_p5));
     wpb_p = tb::gotoh_packed_warps_per_block();
     if (bps_p < 1 || bps_p5 < 1) p.use_packed = false;
   }
@@ -196,9 +199,9 @@ int enqueue_gotoh(tb_ctx* ctx, Lane& L, int mode, bool traceback, tb::GotohBatch
   TB_CUDA(ctx, cudaEventRecord(L.k0, L.stream));
   if (p.use_packed) {
     B.counter = counters;           // [0] queue head, [1] pairs completed by the packed kernels
-    TB_CUDA(ctx, tb::launch_gotoh_packed(traceback, 4, B, p.blocks_packed, L.stream));
+    TB_CUDA(ctx, tb::launch_gotoh_packed(p.tbmode, 4, B, p.blocks_packed, L.stream));
     B.counter = counters + 2;       // second queue head; its completion count lands in counters[3]
-    TB_CUDA(ctx, tb::launch_gotoh_packed(traceback, 5, B, p.blocks_packed5, L.stream));
+    TB_CUDA(ctx, tb::launch_gotoh_packed(p.tbmode, 5, B, p.blocks_packed5, L.stream));
     ctx->launches += 2;
     L.timed = true;
   }

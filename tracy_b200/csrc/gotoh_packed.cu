@@ -29,6 +29,9 @@ constexpr int kPkRows = 1024;                     // DP rows per pass (two 512-r
 // 16 KB per warp, 12 warps per SM) for windows without N, CLASSES = 5 (A,C,G,T,N: 20 KB per warp, 10 warps per SM).
 constexpr int kPkNeg = 2048;                      // field value standing in for the reference's -inf
 constexpr int kPkMaxField = 0x7bff - 16;          // largest field value for which fp16 compare == integer compare
+constexpr int kPkTileWords = 128;                 // 512 B of shared memory per warp: one 16 x 32 tile of pointer nibbles
+// Traceback modes of the packed kernel: none (gotohScore), pointer flags for every cell, or checkpoints + tile recompute.
+enum : int { kTbNone = 0, kTbFlags = 1, kTbCkpt = 2 };
 
 __device__ __forceinline__ unsigned pk_plain(int hi, int lo) { return (unsigned)(hi * 65536 + lo); }      // for 32-bit adds
 __device__ __forceinline__ unsigned pk_dpx(int hi, int lo) { return ((unsigned)hi << 16) | ((unsigned)lo & 0xffffu); }  // per-half adds
@@ -125,15 +128,154 @@ __device__ __forceinline__ int walk_traceback_packed(const uint4* __restrict__ p
   return k;
 }
 
-template <bool TRACEBACK, bool VFREE, int CLASSES>
+// ---- checkpointed traceback (TBMODE == kTbCkpt) -------------------------------------------------------------------
+// The fill stores no pointer flags. It stores (a) every step, every lane: the packed (S, V) of the bottom rows of the lane's
+// two 16-row blocks, and (b) every 32 steps: the lane's 16 packed (S, H) words. That makes every (16-row block x 32-column)
+// tile recomputable on its own: left edge from (b) (or the column-0 initialisation), top edge from (a) of the block
+// above. The walk recomputes only the tiles the path crosses -- rows <= the current row, columns <= the current column of
+// the tile -- as a 16-lane wavefront in the same biased integer domain as the fill (one field per register), writes the
+// 4-bit pointers of that sub-tile to shared memory and walks them. About 3 % of the cells are computed twice; in exchange
+// the fill drops half of its instructions (4 HSET2 + 4 HFMA2 + 1 IMAD of 17 per word) and a quarter of its HBM writes.
+struct PkPair {
+  const float* a; const unsigned char* b;
+  int m, n, T, NQ, go, ge, goe, bias;
+  bool hfree, vfree;
+  float fmatch, fmismatch;
+};
+
+__device__ __forceinline__ int pk_field(unsigned w, int half) { return (int)(half ? w >> 16 : w & 0xffffu); }
+
+__device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __restrict__ rowck, const uint4* __restrict__ colck,
+                                                unsigned char* __restrict__ fl, uint8_t* __restrict__ ops_rev, int lane) {
+  const int m = P.m, n = P.n, T = P.T, go = P.go, ge = P.ge, goe = P.goe, bias = P.bias;
+  int r = m, c = n, state = 0, k = 0;
+  unsigned mych = 0;
+  auto emit = [&](unsigned op) {                                    // one character; a full batch of 32 is one coalesced store
+    if (lane == (k & 31)) mych = op;
+    ++k;
+    if ((k & 31) == 0) ops_rev[k - 32 + lane] = (uint8_t)mych;
+  };
+  auto flush = [&]() { if ((k & 31) != 0 && lane < (k & 31)) ops_rev[(k & ~31) + lane] = (uint8_t)mych; };
+  while (r > 0 || c > 0) {
+    if (r == 0 || c == 0) {                                         // row 0 is all 'h', column 0 all 'v'
+      flush();
+      const int cnt = r == 0 ? c : r;
+      const unsigned char ch = r == 0 ? 'h' : 'v';
+      for (int j = lane; j < cnt; j += 32) ops_rev[k + j] = ch;
+      k += cnt;
+      mych = 0;
+      // the tail batch (if any) now sits in memory already; make flush() below a no-op for it
+      __syncwarp();
+      return k;
+    }
+    // ---- the tile that holds (r, c): block rows R0+1..R0+16, columns cL+1..c ----
+    const int pass = (r - 1) >> 10, rr = (r - 1) & 1023;
+    const int half = rr >> 9, l = (rr & 511) >> 4, icur = rr & 15, v = l + 32 * half;
+    const int R0 = pass * 1024 + 512 * half + 16 * l;
+    const int base_c = 32 - l - 32 * half;                          // column checkpoint q of this block sits at column base_c + 32 q
+    int qp = (c - 1 - base_c) >> 5;                                 // floor: the last checkpoint strictly left of column c
+    int cL = base_c + 32 * qp;
+    if (cL < 1) { cL = 0; qp = -1; }                                // before the block's first checkpoint: start from column 0
+    const int W = c - cL, nr = icur + 1;                            // sub-tile: nr rows x W columns (W <= 32)
+    const int ri = R0 + lane + 1;                                   // this lane's DP row (lanes 0..15)
+    // left edge
+    int s_left, h_left;
+    if (cL == 0 || lane >= 16) {
+      s_left = (P.vfree ? 0 : go + ri * ge) + bias;                 // src/gotoh.h:121
+      h_left = kPkNeg;                                              // src/gotoh.h:120
+    } else {
+      const unsigned* cw = reinterpret_cast<const unsigned*>(colck);
+      const unsigned long long qb = ((unsigned long long)pass * (unsigned)P.NQ + (unsigned)qp) * 8ull;
+      const int ws = lane, wh = 16 + lane;
+      s_left = pk_field(cw[((qb + (unsigned)(ws >> 2)) * 32ull + (unsigned)l) * 4ull + (unsigned)(ws & 3)], half);
+      h_left = pk_field(cw[((qb + (unsigned)(wh >> 2)) * 32ull + (unsigned)l) * 4ull + (unsigned)(wh & 3)], half);
+    }
+    // top edge: lane j holds column cL + 1 + j of the row above the block; d0 = that row at column cL
+    const int vb = v > 0 ? v - 1 : 63, pb = v > 0 ? pass : pass - 1;
+    auto top_at = [&](int col, int& ts, int& tv) {
+      if (R0 == 0) { ts = (col == 0 ? 0 : (P.hfree ? 0 : go + col * ge)) + bias; tv = kPkNeg; }        // src/gotoh.h:109-118
+      else if (col == 0) { ts = (P.vfree ? 0 : go + R0 * ge) + bias; tv = kPkNeg; }
+      else {
+        const uint2 e = rowck[((unsigned long long)pb * (unsigned)T + (unsigned)(col - 1 + vb)) * 32ull + (unsigned)(vb & 31)];
+        ts = pk_field(e.x, vb >> 5); tv = pk_field(e.y, vb >> 5);
+      }
+    };
+    int top_s = 0, top_v = 0, d0s, d0v;
+    const int mycol = cL + 1 + lane;
+    if (lane < W) top_at(mycol, top_s, top_v);
+    top_at(cL, d0s, d0v);
+    const int cls_reg = (lane < W) ? base_class(P.b[mycol - 1]) : 0;
+    // this row's substitution scores and horizontal gap costs
+    int sub0 = 0, sub1 = 0, sub2 = 0, sub3 = 0, sub4 = 0;
+    if (lane < 16 && ri <= m) {
+      float p[5];
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) p[kk] = P.a[(size_t)kk * m + ri - 1];
+      sub0 = sub_onehot(p, 0, P.fmatch, P.fmismatch); sub1 = sub_onehot(p, 1, P.fmatch, P.fmismatch);
+      sub2 = sub_onehot(p, 2, P.fmatch, P.fmismatch); sub3 = sub_onehot(p, 3, P.fmatch, P.fmismatch);
+      sub4 = sub_onehot(p, 4, P.fmatch, P.fmismatch);
+    }
+    const bool hfr = P.hfree && ri == m;                            // src/align.h:67-80
+    const int hge_i = hfr ? 0 : ge, hgoe_i = hfr ? 0 : goe;
+    int diag = __shfl_up_sync(kFull, s_left, 1);
+    if (lane == 0) diag = d0s;
+    int cur_s = 0, cur_v = 0;
+    const int nt = W + nr - 1;
+    for (int t = 0; t < nt; ++t) {
+      const int j = t - lane;
+      int up_s = __shfl_up_sync(kFull, cur_s, 1), up_v = __shfl_up_sync(kFull, cur_v, 1);
+      const int jj = min(max(j, 0), 31);
+      const int ts = __shfl_sync(kFull, top_s, jj), tv = __shfl_sync(kFull, top_v, jj), cl = __shfl_sync(kFull, cls_reg, jj);
+      if (lane == 0) { up_s = ts; up_v = tv; }
+      if (lane < nr && j >= 0 && j < W) {
+        const int col = cL + 1 + j;
+        const bool vfr = P.vfree && col == n;                        // src/align.h:52-65
+        const int vge_c = vfr ? 0 : ge, vgoe_c = vfr ? 0 : goe;
+        const int sub = cl == 0 ? sub0 : cl == 1 ? sub1 : cl == 2 ? sub2 : cl == 3 ? sub3 : sub4;
+        const int hext = h_left + hge_i, hn = max(s_left + hgoe_i, hext);          // src/gotoh.h:129
+        const int vext = up_v + vge_c, vn = max(up_s + vgoe_c, vext);              // src/gotoh.h:130
+        const int s = max(max(diag + sub, hn), vn);                                // src/gotoh.h:131
+        const unsigned nib = (hn != hext ? 8u : 0u) | (vn != vext ? 4u : 0u) | (s == hn ? 2u : 0u) | (s == vn ? 1u : 0u);
+        fl[lane * 32 + j] = (unsigned char)nib;
+        diag = up_s; s_left = s; h_left = hn; cur_s = s; cur_v = vn;
+      }
+    }
+    __syncwarp();
+    // ---- walk inside the sub-tile (reference src/gotoh.h:144-167) ----
+    for (;;) {
+      if (r == 0 || c == 0) break;
+      const int ii = r - R0 - 1, jj = c - cL - 1;
+      if (ii < 0 || jj < 0) break;
+      const unsigned nib = fl[ii * 32 + jj];
+      if (state == 0) {
+        if (nib & 2u) { state = 1; continue; }
+        if (nib & 1u) { state = 2; continue; }
+        emit('s'); --r; --c;
+      } else if (state == 1) {
+        if (nib & 8u) state = 0;
+        emit('h'); --c;
+      } else {
+        if (nib & 4u) state = 0;
+        emit('v'); --r;
+      }
+    }
+    __syncwarp();
+  }
+  flush();
+  return k;
+}
+
+template <int TBMODE, bool VFREE, int CLASSES>
 __global__ void __launch_bounds__(kPkWarps * 32)
 gotoh_packed_kernel(const GotohBatch B) {
-  constexpr int kPkTabWords = CLASSES * 512, kPkSmemWordsPerWarp = 2 * kPkTabWords;
+  constexpr bool TRACEBACK = TBMODE != kTbNone, FLAGS = TBMODE == kTbFlags, CKPT = TBMODE == kTbCkpt;
+  constexpr int kPkTabWords = CLASSES * 512, kPkSmemWordsPerWarp = 2 * kPkTabWords + kPkTileWords;
   extern __shared__ int smem_pk[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned slot = blockIdx.x * kPkWarps + wib;
   int* const tabA = smem_pk + wib * kPkSmemWordsPerWarp;
   int* const tabB = tabA + kPkTabWords;
+  unsigned char* const tile_fl = reinterpret_cast<unsigned char*>(tabB + kPkTabWords);   // 16 x 32 pointer nibbles of one tile (CKPT)
   const float fmatch = (float)B.match, fmismatch = (float)B.mismatch;
   const int go = B.go, ge = B.ge, goe = B.go + B.ge;
   const bool hfree = B.hfree != 0;
@@ -183,7 +325,10 @@ gotoh_packed_kernel(const GotohBatch B) {
     if (bias_ll + ub > kPkMaxField || smin < -16384 || smax > 16384) continue;   // leave status 0: the general kernel takes it
     const int bias = (int)bias_ll;
 
-    const int T = n + 63;
+    const int T = n + 63, NQ = T / 32 + 1;
+    // CKPT scratch of one pair inside the pointer slot: row checkpoints uint2[npass][T][32], then column checkpoints uint4[npass][NQ][8][32]
+    uint2* const rowck = CKPT ? reinterpret_cast<uint2*>(ptr) : nullptr;
+    uint4* const colck = CKPT ? ptr + (unsigned long long)npass * (unsigned)T * 16ull : nullptr;
     uint8_t* const ops_out = TRACEBACK ? B.ops + (long long)pi * B.ops_stride : nullptr;
     const int rr_m = (m - 1) & (kPkRows - 1);                // where row m lives in the last pass
     const int m_half = rr_m >> 9, m_lane = (rr_m & 511) >> 4, m_i = rr_m & 15;
@@ -243,9 +388,10 @@ gotoh_packed_kernel(const GotohBatch B) {
       unsigned cur = 0;
       { const unsigned f0 = __shfl_sync(kFull, cchunk, 0); if (lane == 0) cur = f0; }
       const int cap_st = lane == m_lane ? n - 1 + lane + 32 * m_half : -1;
-      uint4* pw = TRACEBACK ? ptr + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
+      uint4* pw = FLAGS ? ptr + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
+      uint2* prow = CKPT ? rowck + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
 
-      for (int st = 0; st < T; ++st, pw += 32) {
+      for (int st = 0; st < T; ++st, pw += 32, prow += 32) {
         // substitution scores of this step's columns (issued first: shared-memory latency hides under the shuffles)
         const uint4* const pa = reinterpret_cast<const uint4*>(tabA + (cur & 0xffu) * 512) + lane;
         const uint4* const pb = reinterpret_cast<const uint4*>(tabB + (cur >> 8) * 512) + lane;
@@ -300,7 +446,7 @@ gotoh_packed_kernel(const GotohBatch B) {
             const unsigned hn = __viaddmax_u16x2(sl[i], hgoe[i], hext);      // src/gotoh.h:129
             const unsigned g = __viaddmax_u16x2(d, subw[i], hn);             // max(diag + sub, H)
             const unsigned s = __vmaxu2(g, vn);                              // src/gotoh.h:131
-            if (TRACEBACK) {
+            if (FLAGS) {
               unsigned ac = (i & 1) ? acc[i >> 1] : 0x44004400u;             // 4.0 | 4.0
               ac = pk_push(ac, pk_flag_gt(hn, hext));                        // HOPEN, src/gotoh.h:137
               ac = pk_push(ac, pk_flag_gt(vn, vext));                        // VOPEN, src/gotoh.h:138
@@ -311,16 +457,27 @@ gotoh_packed_kernel(const GotohBatch B) {
             d = sl[i];
             sl[i] = s; hh[i] = hn;
             us = s; uv = vn;
-            vext = vn + vge_p;
+            if (FLAGS) vext = vn + vge_p;
             vn = __viaddmax_u16x2(vn, vge_d, g + vgoe_p);                    // next row's V
           }
           diag = next_diag;
           bs = us; bv = uv;
-          if (TRACEBACK) {
+          if (FLAGS) {
             uint4 w;
             w.x = __byte_perm(acc[0], acc[1], 0x6240); w.y = __byte_perm(acc[2], acc[3], 0x6240);
             w.z = __byte_perm(acc[4], acc[5], 0x6240); w.w = __byte_perm(acc[6], acc[7], 0x6240);
             *pw = w;
+          }
+          if (CKPT) {
+            *prow = make_uint2(bs, bv);                                       // bottom row (S, V) of both half-band blocks at this step
+            if ((st & 31) == 31) {                                            // the lane's 16 rows (S, H) every 32 columns
+              uint4* pc = colck + (((unsigned long long)pass * (unsigned)NQ + (unsigned)(st >> 5)) * 8ull) * 32ull + (unsigned)lane;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                pc[k4 * 32] = make_uint4(sl[4 * k4], sl[4 * k4 + 1], sl[4 * k4 + 2], sl[4 * k4 + 3]);
+                pc[(4 + k4) * 32] = make_uint4(hh[4 * k4], hh[4 * k4 + 1], hh[4 * k4 + 2], hh[4 * k4 + 3]);
+              }
+            }
           }
           if (more) { if (lane == 31 && c_hi >= 1 && c_hi <= n) bot[c_hi] = __byte_perm(bs, bv, 0x7632); }   // S | V << 16 of row base+1024
           else if (st == cap_st) {                                            // S[m][n] passes through this lane now
@@ -337,7 +494,15 @@ gotoh_packed_kernel(const GotohBatch B) {
 
     if (TRACEBACK) {
       __syncwarp();
-      const int L = walk_traceback_packed(ptr, T, m, n, ops_rev, lane);
+      int L;
+      if (CKPT) {
+        PkPair pp;
+        pp.a = a; pp.b = b; pp.m = m; pp.n = n; pp.T = T; pp.NQ = NQ; pp.go = go; pp.ge = ge; pp.goe = goe; pp.bias = bias;
+        pp.hfree = hfree; pp.vfree = vfree; pp.fmatch = fmatch; pp.fmismatch = fmismatch;
+        L = walk_traceback_ckpt(pp, rowck, colck, tile_fl, ops_rev, lane);
+      } else {
+        L = walk_traceback_packed(ptr, T, m, n, ops_rev, lane);
+      }
       __syncwarp();
       for (int j = lane; j < L; j += 32) ops_out[j] = ops_rev[L - 1 - j];
       if (lane == 0) B.ops_len[pi] = L;
@@ -347,7 +512,7 @@ gotoh_packed_kernel(const GotohBatch B) {
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
-static size_t packed_smem_bytes(int classes) { return (size_t)kPkWarps * 2 * classes * 512 * sizeof(int); }
+static size_t packed_smem_bytes(int classes) { return (size_t)kPkWarps * (2 * classes * 512 + kPkTileWords) * sizeof(int); }
 int gotoh_packed_warps_per_block() { return kPkWarps; }
 unsigned long long gotoh_packed_ptr_words(int m, int n) { return packed_ptr_words_impl(m, n); }
 
@@ -360,7 +525,7 @@ bool gotoh_packed_eligible(int maxm, int maxn, int match, int mismatch, int go, 
   return true;
 }
 
-template <bool TB_, bool VF_, int CL_>
+template <int TB_, bool VF_, int CL_>
 static cudaError_t packed_launch_one(const GotohBatch& B, int blocks, cudaStream_t stream) {
   const size_t smem = packed_smem_bytes(CL_);
   cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_, CL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -368,7 +533,7 @@ static cudaError_t packed_launch_one(const GotohBatch& B, int blocks, cudaStream
   gotoh_packed_kernel<TB_, VF_, CL_><<<blocks, kPkWarps * 32, smem, stream>>>(B);
   return cudaGetLastError();
 }
-template <bool TB_, bool VF_, int CL_>
+template <int TB_, bool VF_, int CL_>
 static cudaError_t packed_occ_one(int* out) {
   const size_t smem = packed_smem_bytes(CL_);
   cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_, CL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -376,30 +541,32 @@ static cudaError_t packed_occ_one(int* out) {
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, gotoh_packed_kernel<TB_, VF_, CL_>, kPkWarps * 32, smem);
 }
 
-// classes: 4 (windows over ACGT) or 5 (ACGTN)
-cudaError_t launch_gotoh_packed(bool traceback, int classes, const GotohBatch& B, int blocks, cudaStream_t stream) {
+#define TB_PK_DISPATCH(FN, ...)                                                                       \
+  do {                                                                                                \
+    if (classes == 4) {                                                                               \
+      if (tbmode == kTbNone) return vf ? FN<kTbNone, true, 4>(__VA_ARGS__) : FN<kTbNone, false, 4>(__VA_ARGS__);     \
+      if (tbmode == kTbFlags) return vf ? FN<kTbFlags, true, 4>(__VA_ARGS__) : FN<kTbFlags, false, 4>(__VA_ARGS__);  \
+      return vf ? FN<kTbCkpt, true, 4>(__VA_ARGS__) : FN<kTbCkpt, false, 4>(__VA_ARGS__);             \
+    }                                                                                                 \
+    if (tbmode == kTbNone) return vf ? FN<kTbNone, true, 5>(__VA_ARGS__) : FN<kTbNone, false, 5>(__VA_ARGS__);       \
+    if (tbmode == kTbFlags) return vf ? FN<kTbFlags, true, 5>(__VA_ARGS__) : FN<kTbFlags, false, 5>(__VA_ARGS__);    \
+    return vf ? FN<kTbCkpt, true, 5>(__VA_ARGS__) : FN<kTbCkpt, false, 5>(__VA_ARGS__);               \
+  } while (0)
+
+// tbmode: 0 score only, 1 pointer flags for every cell, 2 checkpoints + tile recompute. classes: 4 (ACGT) or 5 (ACGTN).
+cudaError_t launch_gotoh_packed(int tbmode, int classes, const GotohBatch& B, int blocks, cudaStream_t stream) {
   const bool vf = B.vfree != 0;
-  if (classes == 4) {
-    if (traceback) return vf ? packed_launch_one<true, true, 4>(B, blocks, stream) : packed_launch_one<true, false, 4>(B, blocks, stream);
-    return vf ? packed_launch_one<false, true, 4>(B, blocks, stream) : packed_launch_one<false, false, 4>(B, blocks, stream);
-  }
-  if (traceback) return vf ? packed_launch_one<true, true, 5>(B, blocks, stream) : packed_launch_one<true, false, 5>(B, blocks, stream);
-  return vf ? packed_launch_one<false, true, 5>(B, blocks, stream) : packed_launch_one<false, false, 5>(B, blocks, stream);
+  TB_PK_DISPATCH(packed_launch_one, B, blocks, stream);
 }
 
-cudaError_t gotoh_packed_blocks_per_sm(bool traceback, int classes, int* out) {
+static cudaError_t packed_occ_dispatch(int tbmode, int classes, bool vf, int* out) { TB_PK_DISPATCH(packed_occ_one, out); }
+
+cudaError_t gotoh_packed_blocks_per_sm(int tbmode, int classes, int* out) {
   // the VFREE instantiations differ by a handful of registers; size the grid by the tighter one
   int a = 0, b = 0;
-  cudaError_t e;
-  if (classes == 4) {
-    e = traceback ? packed_occ_one<true, true, 4>(&a) : packed_occ_one<false, true, 4>(&a);
-    if (e != cudaSuccess) return e;
-    e = traceback ? packed_occ_one<true, false, 4>(&b) : packed_occ_one<false, false, 4>(&b);
-  } else {
-    e = traceback ? packed_occ_one<true, true, 5>(&a) : packed_occ_one<false, true, 5>(&a);
-    if (e != cudaSuccess) return e;
-    e = traceback ? packed_occ_one<true, false, 5>(&b) : packed_occ_one<false, false, 5>(&b);
-  }
+  cudaError_t e = packed_occ_dispatch(tbmode, classes, true, &a);
+  if (e != cudaSuccess) return e;
+  e = packed_occ_dispatch(tbmode, classes, false, &b);
   if (e != cudaSuccess) return e;
   *out = a < b ? a : b;
   return cudaSuccess;

@@ -55,7 +55,10 @@ __device__ __forceinline__ unsigned pk_push(unsigned acc, unsigned flag) {   // 
 __host__ __device__ inline unsigned long long packed_ptr_words_impl(int m, int n) {
   if (m <= 0 || n <= 0) return 0;
   const unsigned long long npass = (unsigned long long)(m + kPkRows - 1) / kPkRows;
-  return npass * (unsigned long long)(n + 63) * 64ull;   // in 8-byte words
+  // flags mode: one 512 B line per step. Checkpoint mode: 256 B per step of row checkpoints + 4 KB per 32 steps of column
+  // checkpoints (<= 128 B per step amortised, plus one extra block) + 64 B per step of the last row: also within 512 B per step
+  // once the extra column-checkpoint block is added.
+  return (npass * (unsigned long long)(n + 63) + 8ull) * 64ull;   // in 8-byte words
 }
 
 // Nibble of DP row `row` (0..15 inside the lane block) of half-band `half` from a lane's uint4.
@@ -146,27 +149,49 @@ struct PkPair {
 __device__ __forceinline__ int pk_field(unsigned w, int half) { return (int)(half ? w >> 16 : w & 0xffffu); }
 
 __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __restrict__ rowck, const uint4* __restrict__ colck,
-                                                unsigned char* __restrict__ fl, uint8_t* __restrict__ ops_rev, int lane) {
+                                                const unsigned* __restrict__ lastrow, unsigned char* __restrict__ fl,
+                                                uint8_t* __restrict__ ops_rev, int lane) {
   const int m = P.m, n = P.n, T = P.T, go = P.go, ge = P.ge, goe = P.goe, bias = P.bias;
   int r = m, c = n, state = 0, k = 0;
-  unsigned mych = 0;
-  auto emit = [&](unsigned op) {                                    // one character; a full batch of 32 is one coalesced store
-    if (lane == (k & 31)) mych = op;
-    ++k;
-    if ((k & 31) == 0) ops_rev[k - 32 + lane] = (uint8_t)mych;
+  auto put = [&](unsigned char ch, int run) {                       // run <= 32 equal characters, one coalesced store
+    if (lane < run) ops_rev[k + lane] = ch;
+    k += run;
   };
-  auto flush = [&]() { if ((k & 31) != 0 && lane < (k & 31)) ops_rev[(k & ~31) + lane] = (uint8_t)mych; };
+
+  // ---- the free end-gap run along the last row (hfree): a closed form instead of ~(n - m) / 32 tile recomputes ----
+  // On row m both horizontal gap costs are 0 (src/align.h:67-80), so H[m][c] = max(S[m][c'] : c' < c) and bit1 of (m, c) is
+  // set exactly when S[m][c-1] is a strict new prefix maximum (src/gotoh.h:137). If S[m][n] == H[m][n] the walk enters
+  // state 'h' at (m, n) and runs left until the last strict prefix maximum before column n, i.e. the FIRST column p that
+  // attains max(S[m][0..n-1]); it emits n - p times 'h' and continues in state 's' at (m, p). S[m][.] was stored by the fill.
+  if (lastrow != nullptr && n >= 1) {
+    const int m_half = ((m - 1) & 1023) >> 9, m_i = (m - 1) & 15, m_v = (((m - 1) & 511) >> 4) + 32 * m_half;
+    const unsigned* row = lastrow + m_i;                            // 16 words per step; step of column c is c - 1 + m_v
+    auto s_at = [&](int col) -> int {
+      if (col == 0) return (P.vfree ? 0 : go + m * ge) + bias;      // S[m][0], src/gotoh.h:121
+      return pk_field(row[(size_t)(col - 1 + m_v) * 16], m_half);
+    };
+    int best = -1, bestc = 0;                                       // max over columns 0..n-1, first column on ties
+    for (int col = lane; col < n; col += 32) { const int x = s_at(col); if (x > best) { best = x; bestc = col; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ob = __shfl_xor_sync(kFull, best, o), oc = __shfl_xor_sync(kFull, bestc, o);
+      if (ob > best || (ob == best && oc < bestc)) { best = ob; bestc = oc; }
+    }
+    if (s_at(n) == best) {                                          // bit3 of (m, n): S == H (src/gotoh.h:134)
+      const int cnt = n - bestc;
+      for (int j = lane; j < cnt; j += 32) ops_rev[k + j] = 'h';
+      k += cnt;
+      c = bestc;
+    }
+  }
+
   while (r > 0 || c > 0) {
     if (r == 0 || c == 0) {                                         // row 0 is all 'h', column 0 all 'v'
-      flush();
       const int cnt = r == 0 ? c : r;
       const unsigned char ch = r == 0 ? 'h' : 'v';
       for (int j = lane; j < cnt; j += 32) ops_rev[k + j] = ch;
       k += cnt;
-      mych = 0;
-      // the tail batch (if any) now sits in memory already; make flush() below a no-op for it
-      __syncwarp();
-      return k;
+      break;
     }
     // ---- the tile that holds (r, c): block rows R0+1..R0+16, columns cL+1..c ----
     const int pass = (r - 1) >> 10, rr = (r - 1) & 1023;
@@ -241,27 +266,38 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
       }
     }
     __syncwarp();
-    // ---- walk inside the sub-tile (reference src/gotoh.h:144-167) ----
+    // ---- walk inside the sub-tile, one run per iteration (reference src/gotoh.h:144-167) ----
     for (;;) {
       if (r == 0 || c == 0) break;
       const int ii = r - R0 - 1, jj = c - cL - 1;
       if (ii < 0 || jj < 0) break;
-      const unsigned nib = fl[ii * 32 + jj];
-      if (state == 0) {
-        if (nib & 2u) { state = 1; continue; }
-        if (nib & 1u) { state = 2; continue; }
-        emit('s'); --r; --c;
-      } else if (state == 1) {
-        if (nib & 8u) state = 0;
-        emit('h'); --c;
-      } else {
-        if (nib & 4u) state = 0;
-        emit('v'); --r;
+      int run;
+      if (state == 0) {                                             // diagonal: lane t looks at cell (ii - t, jj - t)
+        const int cnt = min(ii, jj) + 1;
+        const unsigned nib = lane < cnt ? fl[(ii - lane) * 32 + (jj - lane)] : 0u;
+        const unsigned brk = __ballot_sync(kFull, (nib & 3u) != 0u);
+        run = brk ? __ffs(brk) - 1 : cnt;
+        put('s', run);
+        r -= run; c -= run;
+        if (run < cnt) state = (__shfl_sync(kFull, nib, run) & 2u) ? 1 : 2;   // the cell that stopped the diagonal
+      } else if (state == 1) {                                      // horizontal: lane t looks at cell (ii, jj - t)
+        const int cnt = jj + 1;
+        const unsigned hit = __ballot_sync(kFull, lane < cnt && (fl[ii * 32 + (jj - min(lane, jj))] & 8u));
+        run = hit ? __ffs(hit) : cnt;                               // the cell with bit1 set is consumed, then state 's'
+        put('h', run);
+        c -= run;
+        if (hit) state = 0;
+      } else {                                                      // vertical: lane t looks at cell (ii - t, jj)
+        const int cnt = ii + 1;
+        const unsigned hit = __ballot_sync(kFull, lane < cnt && (fl[(ii - min(lane, ii)) * 32 + jj] & 4u));
+        run = hit ? __ffs(hit) : cnt;
+        put('v', run);
+        r -= run;
+        if (hit) state = 0;
       }
     }
     __syncwarp();
   }
-  flush();
   return k;
 }
 
@@ -329,6 +365,7 @@ gotoh_packed_kernel(const GotohBatch B) {
     // CKPT scratch of one pair inside the pointer slot: row checkpoints uint2[npass][T][32], then column checkpoints uint4[npass][NQ][8][32]
     uint2* const rowck = CKPT ? reinterpret_cast<uint2*>(ptr) : nullptr;
     uint4* const colck = CKPT ? ptr + (unsigned long long)npass * (unsigned)T * 16ull : nullptr;
+    uint4* const lastrow = CKPT ? colck + (unsigned long long)npass * (unsigned)NQ * 256ull : nullptr;   // uint4[T][4]: row-m lane's S words
     uint8_t* const ops_out = TRACEBACK ? B.ops + (long long)pi * B.ops_stride : nullptr;
     const int rr_m = (m - 1) & (kPkRows - 1);                // where row m lives in the last pass
     const int m_half = rr_m >> 9, m_lane = (rr_m & 511) >> 4, m_i = rr_m & 15;
@@ -388,6 +425,7 @@ gotoh_packed_kernel(const GotohBatch B) {
       unsigned cur = 0;
       { const unsigned f0 = __shfl_sync(kFull, cchunk, 0); if (lane == 0) cur = f0; }
       const int cap_st = lane == m_lane ? n - 1 + lane + 32 * m_half : -1;
+      const bool lastrow_lane = CKPT && !more && hfree && lane == m_lane;
       uint4* pw = FLAGS ? ptr + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
       uint2* prow = CKPT ? rowck + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
 
@@ -469,6 +507,11 @@ gotoh_packed_kernel(const GotohBatch B) {
             *pw = w;
           }
           if (CKPT) {
+            if (lastrow_lane) {                                               // the lane that owns row m keeps its 16 S words of every step
+              uint4* pl = lastrow + (size_t)st * 4;
+              pl[0] = make_uint4(sl[0], sl[1], sl[2], sl[3]); pl[1] = make_uint4(sl[4], sl[5], sl[6], sl[7]);
+              pl[2] = make_uint4(sl[8], sl[9], sl[10], sl[11]); pl[3] = make_uint4(sl[12], sl[13], sl[14], sl[15]);
+            }
             *prow = make_uint2(bs, bv);                                       // bottom row (S, V) of both half-band blocks at this step
             if ((st & 31) == 31) {                                            // the lane's 16 rows (S, H) every 32 columns
               uint4* pc = colck + (((unsigned long long)pass * (unsigned)NQ + (unsigned)(st >> 5)) * 8ull) * 32ull + (unsigned)lane;
@@ -499,7 +542,7 @@ gotoh_packed_kernel(const GotohBatch B) {
         PkPair pp;
         pp.a = a; pp.b = b; pp.m = m; pp.n = n; pp.T = T; pp.NQ = NQ; pp.go = go; pp.ge = ge; pp.goe = goe; pp.bias = bias;
         pp.hfree = hfree; pp.vfree = vfree; pp.fmatch = fmatch; pp.fmismatch = fmismatch;
-        L = walk_traceback_ckpt(pp, rowck, colck, tile_fl, ops_rev, lane);
+        L = walk_traceback_ckpt(pp, rowck, colck, hfree ? reinterpret_cast<const unsigned*>(lastrow) : nullptr, tile_fl, ops_rev, lane);
       } else {
         L = walk_traceback_packed(ptr, T, m, n, ops_rev, lane);
       }

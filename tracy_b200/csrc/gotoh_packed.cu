@@ -29,7 +29,7 @@ constexpr int kPkRows = 1024;                     // DP rows per pass (two 512-r
 // 16 KB per warp, 12 warps per SM) for windows without N, CLASSES = 5 (A,C,G,T,N: 20 KB per warp, 10 warps per SM).
 constexpr int kPkNeg = 2048;                      // field value standing in for the reference's -inf
 constexpr int kPkMaxField = 0x7bff - 16;          // largest field value for which fp16 compare == integer compare
-constexpr int kPkTileWords = 128;                 // 512 B of shared memory per warp: one 16 x 32 tile of pointer nibbles
+constexpr int kPkTileWords = 0;                   // (no per-warp shared memory besides the tables)
 // Traceback modes of the packed kernel: none (gotohScore), pointer flags for every cell, or checkpoints + tile recompute.
 enum : int { kTbNone = 0, kTbFlags = 1, kTbCkpt = 2 };
 
@@ -58,7 +58,7 @@ __host__ __device__ inline unsigned long long packed_ptr_words_impl(int m, int n
   // flags mode: one 512 B line per step. Checkpoint mode: 256 B per step of row checkpoints + 4 KB per 32 steps of column
   // checkpoints (<= 128 B per step amortised, plus one extra block) + 64 B per step of the last row: also within 512 B per step
   // once the extra column-checkpoint block is added.
-  return (npass * (unsigned long long)(n + 63) + 8ull) * 64ull;   // in 8-byte words
+  return (npass * (unsigned long long)(n + 63) + 48ull) * 64ull;   // in 8-byte words (+ 16 KB span scratch + slack)
 }
 
 // Nibble of DP row `row` (0..15 inside the lane block) of half-band `half` from a lane's uint4.
@@ -131,14 +131,43 @@ __device__ __forceinline__ int walk_traceback_packed(const uint4* __restrict__ p
   return k;
 }
 
+// Substitution tables of one pass (rows base+1 .. base+1024), entries in per-half form: A = half-band A in the low half,
+// B = half-band B in the high half, so that A | B is the packed addend of one word. Layout [class][q][lane][4].
+template <int CLASSES>
+__device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const float* a, int m, int base, float fmatch, float fmismatch, int lane) {
+  __syncwarp();
+  for (int rr = lane; rr < kPkRows; rr += 32) {
+    const int r0 = base + rr;                              // 0-based row of a1
+    const int half = rr >> 9, rb = rr & 511, l = rb >> 4, i = rb & 15;
+    const int at = (i >> 2) * 128 + l * 4 + (i & 3);
+    float p[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) p[k] = r0 < m ? a[(size_t)k * m + r0] : 0.0f;
+    int* const tab = half ? tabB : tabA;
+#pragma unroll
+    for (int cls = 0; cls < CLASSES; ++cls) {
+      const unsigned s = (unsigned)(r0 < m ? sub_onehot(p, cls, fmatch, fmismatch) : 0) & 0xffffu;
+      tab[cls * 512 + at] = (int)(half ? s << 16 : s);
+    }
+  }
+  __syncwarp();
+}
+
 // ---- checkpointed traceback (TBMODE == kTbCkpt) -------------------------------------------------------------------
 // The fill stores no pointer flags. It stores (a) every step, every lane: the packed (S, V) of the bottom rows of the lane's
 // two 16-row blocks, and (b) every 32 steps: the lane's 16 packed (S, H) words. That makes every (16-row block x 32-column)
-// tile recomputable on its own: left edge from (b) (or the column-0 initialisation), top edge from (a) of the block
-// above. The walk recomputes only the tiles the path crosses -- rows <= the current row, columns <= the current column of
-// the tile -- as a 16-lane wavefront in the same biased integer domain as the fill (one field per register), writes the
-// 4-bit pointers of that sub-tile to shared memory and walks them. About 3 % of the cells are computed twice; in exchange
-// the fill drops half of its instructions (4 HSET2 + 4 HFMA2 + 1 IMAD of 17 per word) and a quarter of its HBM writes.
+// tile recomputable on its own: left edge from (b) (or the column-0 initialisation), top edge from (a) of the block above.
+//
+// The walk proceeds in ROUNDS. A round gives each of the 32 lanes one block and a 64-column span that starts on one of the
+// block's checkpoint columns, and every lane recomputes its span serially with the fill's own per-row instruction sequence
+// (flags included), all lanes in lock-step -- the recompute runs at full SIMT efficiency. Spans are chosen by speculation:
+//   * diagonal round (state 's' / 'v'): lane k takes the k-th block above the current one, around the column where a
+//     pure diagonal from the current cell would cross it (>= 8 columns of slack either side);
+//   * horizontal round (state 'h'): all lanes take the current block, consecutive spans to the left (2048 columns).
+// The 4-bit pointers of every span go to a 16 KB scratch (64-bit word per column: 16 rows x 4 bits); the walk then consumes
+// them run by run with ballots, exactly like the flag walkers. When the path leaves the speculated spans (a long indel, a
+// change of pass) the next round is planned from the cell reached, so every round consumes at least one cell.
+// Cost at 1000 x 4000: ~5 rounds x ~20 k instructions against 1.44 M for flag extraction in every cell.
 struct PkPair {
   const float* a; const unsigned char* b;
   int m, n, T, NQ, go, ge, goe, bias;
@@ -146,44 +175,28 @@ struct PkPair {
   float fmatch, fmismatch;
 };
 
-__device__ __forceinline__ int pk_field(unsigned w, int half) { return (int)(half ? w >> 16 : w & 0xffffu); }
+constexpr int kPkSpan = 64;                      // columns per lane per round
 
+__device__ __forceinline__ unsigned pk_dup(unsigned field) { return field * 0x10001u; }   // the same value in both halves
+
+// 4-bit pointer of row `row` (0..15) from a span word: byte row>>1, even rows in the high nibble
+__device__ __forceinline__ unsigned pk_span_nibble(unsigned long long w, int row) {
+  const unsigned byte = (unsigned)(w >> (8 * (row >> 1))) & 0xffu;
+  return (row & 1) ? (byte & 15u) : (byte >> 4);
+}
+
+template <int CLASSES>
 __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __restrict__ rowck, const uint4* __restrict__ colck,
-                                                const unsigned* __restrict__ lastrow, unsigned char* __restrict__ fl,
+                                                unsigned long long* __restrict__ span, int* tabA, int* tabB, int tab_pass,
                                                 uint8_t* __restrict__ ops_rev, int lane) {
   const int m = P.m, n = P.n, T = P.T, go = P.go, ge = P.ge, goe = P.goe, bias = P.bias;
+  const bool vfree = P.vfree, hfree = P.hfree;
   int r = m, c = n, state = 0, k = 0;
   auto put = [&](unsigned char ch, int run) {                       // run <= 32 equal characters, one coalesced store
     if (lane < run) ops_rev[k + lane] = ch;
     k += run;
   };
-
-  // ---- the free end-gap run along the last row (hfree): a closed form instead of ~(n - m) / 32 tile recomputes ----
-  // On row m both horizontal gap costs are 0 (src/align.h:67-80), so H[m][c] = max(S[m][c'] : c' < c) and bit1 of (m, c) is
-  // set exactly when S[m][c-1] is a strict new prefix maximum (src/gotoh.h:137). If S[m][n] == H[m][n] the walk enters
-  // state 'h' at (m, n) and runs left until the last strict prefix maximum before column n, i.e. the FIRST column p that
-  // attains max(S[m][0..n-1]); it emits n - p times 'h' and continues in state 's' at (m, p). S[m][.] was stored by the fill.
-  if (lastrow != nullptr && n >= 1) {
-    const int m_half = ((m - 1) & 1023) >> 9, m_i = (m - 1) & 15, m_v = (((m - 1) & 511) >> 4) + 32 * m_half;
-    const unsigned* row = lastrow + m_i;                            // 16 words per step; step of column c is c - 1 + m_v
-    auto s_at = [&](int col) -> int {
-      if (col == 0) return (P.vfree ? 0 : go + m * ge) + bias;      // S[m][0], src/gotoh.h:121
-      return pk_field(row[(size_t)(col - 1 + m_v) * 16], m_half);
-    };
-    int best = -1, bestc = 0;                                       // max over columns 0..n-1, first column on ties
-    for (int col = lane; col < n; col += 32) { const int x = s_at(col); if (x > best) { best = x; bestc = col; } }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const int ob = __shfl_xor_sync(kFull, best, o), oc = __shfl_xor_sync(kFull, bestc, o);
-      if (ob > best || (ob == best && oc < bestc)) { best = ob; bestc = oc; }
-    }
-    if (s_at(n) == best) {                                          // bit3 of (m, n): S == H (src/gotoh.h:134)
-      const int cnt = n - bestc;
-      for (int j = lane; j < cnt; j += 32) ops_rev[k + j] = 'h';
-      k += cnt;
-      c = bestc;
-    }
-  }
+  bool first_round = true;
 
   while (r > 0 || c > 0) {
     if (r == 0 || c == 0) {                                         // row 0 is all 'h', column 0 all 'v'
@@ -193,107 +206,189 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
       k += cnt;
       break;
     }
-    // ---- the tile that holds (r, c): block rows R0+1..R0+16, columns cL+1..c ----
-    const int pass = (r - 1) >> 10, rr = (r - 1) & 1023;
-    const int half = rr >> 9, l = (rr & 511) >> 4, icur = rr & 15, v = l + 32 * half;
-    const int R0 = pass * 1024 + 512 * half + 16 * l;
-    const int base_c = 32 - l - 32 * half;                          // column checkpoint q of this block sits at column base_c + 32 q
-    int qp = (c - 1 - base_c) >> 5;                                 // floor: the last checkpoint strictly left of column c
-    int cL = base_c + 32 * qp;
-    if (cL < 1) { cL = 0; qp = -1; }                                // before the block's first checkpoint: start from column 0
-    const int W = c - cL, nr = icur + 1;                            // sub-tile: nr rows x W columns (W <= 32)
-    const int ri = R0 + lane + 1;                                   // this lane's DP row (lanes 0..15)
-    // left edge
-    int s_left, h_left;
-    if (cL == 0 || lane >= 16) {
-      s_left = (P.vfree ? 0 : go + ri * ge) + bias;                 // src/gotoh.h:121
-      h_left = kPkNeg;                                              // src/gotoh.h:120
+    // ================= plan one round from (r, c, state) =================
+    const int pass = (r - 1) >> 10, rr0 = (r - 1) & 1023;
+    const int v0 = ((rr0 >> 9) << 5) + ((rr0 & 511) >> 4), i0 = rr0 & 15;       // current block (0..63) and row inside it
+    if (pass != tab_pass) { pk_build_tables<CLASSES>(tabA, tabB, P.a, m, pass * kPkRows, P.fmatch, P.fmismatch, lane); tab_pass = pass; }
+    // the free end-gap row almost always starts with a long horizontal run: look left first there
+    const bool horizontal = state == 1 || (first_round && hfree && r == m && state == 0);
+    first_round = false;
+    int vk, cA;                                                     // this lane's block and the checkpoint column its span starts after
+    bool act;
+    if (horizontal) {
+      vk = v0;
+      const int base_c = 32 - (vk & 31) - 32 * (vk >> 5);
+      const int cB0 = base_c + 32 * (((c - base_c) + 31) >> 5);    // first checkpoint column >= c
+      cA = cB0 - kPkSpan * (lane + 1);
+      act = cA + kPkSpan >= 1;
     } else {
+      vk = v0 - lane;
+      act = vk >= 0;
+      if (!act) vk = 0;
+      const int base_c = 32 - (vk & 31) - 32 * (vk >> 5);
+      const int e = c + 15 - i0 - 16 * lane;                        // column where a pure diagonal crosses this block's bottom row
+      cA = base_c + 32 * ((e - 24 - base_c) >> 5);                  // last checkpoint column <= e - 24
+    }
+    const int half = vk >> 5, l = vk & 31;
+    const int base_c = 32 - l - 32 * half;
+    int qa = (cA - base_c) >> 5;                                    // checkpoint index of column cA (cA is on the grid)
+    if (cA < 1) { cA = 0; qa = -1; }                                // before the block's first checkpoint: start from column 0
+    const int R0 = pass * kPkRows + 512 * half + 16 * l;            // DP row just above the block
+    // ---- left edge (both halves of every word carry the same value; the half that is not this block's runs with sub = 0) ----
+    unsigned sl[kRowsPerLane], hh[kRowsPerLane], hge[kRowsPerLane], hgoe[kRowsPerLane];
+    {
       const unsigned* cw = reinterpret_cast<const unsigned*>(colck);
-      const unsigned long long qb = ((unsigned long long)pass * (unsigned)P.NQ + (unsigned)qp) * 8ull;
-      const int ws = lane, wh = 16 + lane;
-      s_left = pk_field(cw[((qb + (unsigned)(ws >> 2)) * 32ull + (unsigned)l) * 4ull + (unsigned)(ws & 3)], half);
-      h_left = pk_field(cw[((qb + (unsigned)(wh >> 2)) * 32ull + (unsigned)l) * 4ull + (unsigned)(wh & 3)], half);
-    }
-    // top edge: lane j holds column cL + 1 + j of the row above the block; d0 = that row at column cL
-    const int vb = v > 0 ? v - 1 : 63, pb = v > 0 ? pass : pass - 1;
-    auto top_at = [&](int col, int& ts, int& tv) {
-      if (R0 == 0) { ts = (col == 0 ? 0 : (P.hfree ? 0 : go + col * ge)) + bias; tv = kPkNeg; }        // src/gotoh.h:109-118
-      else if (col == 0) { ts = (P.vfree ? 0 : go + R0 * ge) + bias; tv = kPkNeg; }
-      else {
-        const uint2 e = rowck[((unsigned long long)pb * (unsigned)T + (unsigned)(col - 1 + vb)) * 32ull + (unsigned)(vb & 31)];
-        ts = pk_field(e.x, vb >> 5); tv = pk_field(e.y, vb >> 5);
-      }
-    };
-    int top_s = 0, top_v = 0, d0s, d0v;
-    const int mycol = cL + 1 + lane;
-    if (lane < W) top_at(mycol, top_s, top_v);
-    top_at(cL, d0s, d0v);
-    const int cls_reg = (lane < W) ? base_class(P.b[mycol - 1]) : 0;
-    // this row's substitution scores and horizontal gap costs
-    int sub0 = 0, sub1 = 0, sub2 = 0, sub3 = 0, sub4 = 0;
-    if (lane < 16 && ri <= m) {
-      float p[5];
+      const unsigned long long qb = ((unsigned long long)pass * (unsigned)P.NQ + (unsigned)max(qa, 0)) * 8ull;
 #pragma unroll
-      for (int kk = 0; kk < 5; ++kk) p[kk] = P.a[(size_t)kk * m + ri - 1];
-      sub0 = sub_onehot(p, 0, P.fmatch, P.fmismatch); sub1 = sub_onehot(p, 1, P.fmatch, P.fmismatch);
-      sub2 = sub_onehot(p, 2, P.fmatch, P.fmismatch); sub3 = sub_onehot(p, 3, P.fmatch, P.fmismatch);
-      sub4 = sub_onehot(p, 4, P.fmatch, P.fmismatch);
-    }
-    const bool hfr = P.hfree && ri == m;                            // src/align.h:67-80
-    const int hge_i = hfr ? 0 : ge, hgoe_i = hfr ? 0 : goe;
-    int diag = __shfl_up_sync(kFull, s_left, 1);
-    if (lane == 0) diag = d0s;
-    int cur_s = 0, cur_v = 0;
-    const int nt = W + nr - 1;
-    for (int t = 0; t < nt; ++t) {
-      const int j = t - lane;
-      int up_s = __shfl_up_sync(kFull, cur_s, 1), up_v = __shfl_up_sync(kFull, cur_v, 1);
-      const int jj = min(max(j, 0), 31);
-      const int ts = __shfl_sync(kFull, top_s, jj), tv = __shfl_sync(kFull, top_v, jj), cl = __shfl_sync(kFull, cls_reg, jj);
-      if (lane == 0) { up_s = ts; up_v = tv; }
-      if (lane < nr && j >= 0 && j < W) {
-        const int col = cL + 1 + j;
-        const bool vfr = P.vfree && col == n;                        // src/align.h:52-65
-        const int vge_c = vfr ? 0 : ge, vgoe_c = vfr ? 0 : goe;
-        const int sub = cl == 0 ? sub0 : cl == 1 ? sub1 : cl == 2 ? sub2 : cl == 3 ? sub3 : sub4;
-        const int hext = h_left + hge_i, hn = max(s_left + hgoe_i, hext);          // src/gotoh.h:129
-        const int vext = up_v + vge_c, vn = max(up_s + vgoe_c, vext);              // src/gotoh.h:130
-        const int s = max(max(diag + sub, hn), vn);                                // src/gotoh.h:131
-        const unsigned nib = (hn != hext ? 8u : 0u) | (vn != vext ? 4u : 0u) | (s == hn ? 2u : 0u) | (s == vn ? 1u : 0u);
-        fl[lane * 32 + j] = (unsigned char)nib;
-        diag = up_s; s_left = s; h_left = hn; cur_s = s; cur_v = vn;
+      for (int i = 0; i < kRowsPerLane; ++i) {
+        const int ri = R0 + i + 1;
+        unsigned sv = (unsigned)((vfree ? 0 : go + ri * ge) + bias), hv = (unsigned)kPkNeg;      // src/gotoh.h:120-121
+        if (qa >= 0) {
+          const unsigned ws = cw[((qb + (unsigned)(i >> 2)) * 32ull + (unsigned)l) * 4ull + (unsigned)(i & 3)];
+          const unsigned wh = cw[((qb + (unsigned)(4 + (i >> 2))) * 32ull + (unsigned)l) * 4ull + (unsigned)(i & 3)];
+          sv = half ? ws >> 16 : ws & 0xffffu; hv = half ? wh >> 16 : wh & 0xffffu;
+        }
+        sl[i] = pk_dup(sv); hh[i] = pk_dup(hv);
+        const bool fr = hfree && ri == m;                           // src/align.h:67-80
+        hge[i] = pk_plain(fr ? 0 : ge, fr ? 0 : ge);
+        hgoe[i] = pk_dpx(fr ? 0 : goe, fr ? 0 : goe);
       }
+    }
+    // ---- top edge reader: (S, V) of the row above the block at column col, duplicated into both halves ----
+    const int vb = vk > 0 ? vk - 1 : 63, pb = vk > 0 ? pass : pass - 1;
+    const uint2* const top_base = rowck + ((unsigned long long)max(pb, 0) * (unsigned)T + (unsigned)vb) * 32ull + (unsigned)(vb & 31);
+    const int vbh = vb >> 5;
+    auto top_load = [&](int col) -> uint2 {                         // raw checkpoint entry (only meaningful when R0 > 0 and col >= 1)
+      const int cc = min(max(col, 1), n);
+      return top_base[(unsigned long long)(cc - 1) * 32ull];
+    };
+    auto top_fix = [&](uint2 e, int col, unsigned& ts, unsigned& tv) {
+      if (R0 == 0) { ts = (unsigned)((col == 0 ? 0 : (hfree ? 0 : go + col * ge)) + bias); tv = (unsigned)kPkNeg; }   // src/gotoh.h:109-118
+      else if (col == 0) { ts = (unsigned)((vfree ? 0 : go + R0 * ge) + bias); tv = (unsigned)kPkNeg; }
+      else { ts = vbh ? e.x >> 16 : e.x & 0xffffu; tv = vbh ? e.y >> 16 : e.y & 0xffffu; }
+      ts = pk_dup(ts); tv = pk_dup(tv);
+    };
+    auto cls_load = [&](int col) -> unsigned { return (unsigned)base_class(P.b[min(max(col, 1), n) - 1]); };
+    unsigned diag, dv_unused;
+    top_fix(top_load(cA), cA, diag, dv_unused);
+    const int* const tab = half ? tabB : tabA;
+    unsigned long long* const myspan = span + (size_t)lane * kPkSpan;
+    // prefetch ring: the top-edge entries and window characters of the next four columns
+    uint2 tq[4]; unsigned cq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { tq[u] = top_load(cA + 1 + u); cq[u] = cls_load(cA + 1 + u); }
+    for (int jc = 0; jc < kPkSpan; jc += 4) {
+      uint2 tn[4]; unsigned cn[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { tn[u] = top_load(cA + 5 + jc + u); cn[u] = cls_load(cA + 5 + jc + u); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int col = cA + 1 + jc + u;
+        unsigned us, uv;
+        top_fix(tq[u], col, us, uv);
+        const unsigned cl = min(cq[u], (unsigned)(CLASSES - 1));
+        const uint4* const pt = reinterpret_cast<const uint4*>(tab + cl * 512) + l;
+        unsigned subw[kRowsPerLane];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const uint4 x = pt[j * 32]; subw[4 * j] = x.x; subw[4 * j + 1] = x.y; subw[4 * j + 2] = x.z; subw[4 * j + 3] = x.w; }
+        const bool vf = vfree && col == n;                          // src/align.h:52-65
+        const int vge_i = vf ? 0 : ge, vgoe_i = vf ? 0 : goe;
+        const unsigned vge_p = pk_plain(vge_i, vge_i), vge_d = pk_dpx(vge_i, vge_i), vgoe_p = pk_plain(vgoe_i, vgoe_i);
+        const unsigned next_diag = us;
+        unsigned d = diag;
+        unsigned vext = uv + vge_p;
+        unsigned vn = __viaddmax_u16x2(uv, vge_d, us + vgoe_p);
+        unsigned acc[8];
+#pragma unroll
+        for (int i = 0; i < kRowsPerLane; ++i) {                    // the fill's row sequence, flags as in kTbFlags
+          const unsigned hext = hh[i] + hge[i];
+          const unsigned hn = __viaddmax_u16x2(sl[i], hgoe[i], hext);
+          const unsigned g = __viaddmax_u16x2(d, subw[i], hn);
+          const unsigned sN = __vmaxu2(g, vn);
+          unsigned ac = (i & 1) ? acc[i >> 1] : 0x44004400u;
+          ac = pk_push(ac, pk_flag_gt(hn, hext));
+          ac = pk_push(ac, pk_flag_gt(vn, vext));
+          ac = pk_push(ac, pk_flag_eq(sN, hn));
+          ac = pk_push(ac, pk_flag_eq(sN, vn));
+          acc[i >> 1] = ac;
+          d = sl[i];
+          sl[i] = sN; hh[i] = hn;
+          vext = vn + vge_p;
+          vn = __viaddmax_u16x2(vn, vge_d, g + vgoe_p);
+        }
+        diag = next_diag;
+        // low mantissa byte of this block's half of each accumulator = rows (2a, 2a+1)
+        const unsigned sel = half ? 0x6262u : 0x4040u;
+        const unsigned w01 = __byte_perm(acc[0], acc[1], sel), w23 = __byte_perm(acc[2], acc[3], sel);
+        const unsigned w45 = __byte_perm(acc[4], acc[5], sel), w67 = __byte_perm(acc[6], acc[7], sel);
+        const unsigned lo = __byte_perm(w01, w23, 0x5410), hi = __byte_perm(w45, w67, 0x5410);
+        myspan[jc + u] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { tq[u] = tn[u]; cq[u] = cn[u]; }
     }
     __syncwarp();
-    // ---- walk inside the sub-tile, one run per iteration (reference src/gotoh.h:144-167) ----
+
+    // ================= walk through the spans of this round =================
+    int wk = -1, wc0 = 0, wcA = 0;                                  // window: lane t holds the word of column wc0 - t of span wk
+    unsigned long long ww = 0;
     for (;;) {
       if (r == 0 || c == 0) break;
-      const int ii = r - R0 - 1, jj = c - cL - 1;
-      if (ii < 0 || jj < 0) break;
+      if (((r - 1) >> 10) != pass) break;                           // next pass: other tables, new round
+      const int rr = (r - 1) & 1023;
+      const int v = ((rr >> 9) << 5) + ((rr & 511) >> 4), i = rr & 15;
+      int sk;                                                       // lane (span) that should hold column c of block v
+      if (horizontal) {
+        if (v != v0) break;
+        const int bc = 32 - (v0 & 31) - 32 * (v0 >> 5);
+        const int cB0 = bc + 32 * (((__shfl_sync(kFull, c, 0) - bc) + 31) >> 5);   // (uniform; c is warp-uniform)
+        sk = -1;                                                    // located below from the spans' cA values
+        (void)cB0;
+      } else {
+        sk = v0 - v;
+        if (sk < 0 || sk > 31) break;
+      }
+      if (horizontal) {
+        // spans are consecutive: span t covers (cA_t, cA_t + 64]; find the one that holds c
+        const unsigned hit = __ballot_sync(kFull, act && c > cA && c <= cA + kPkSpan);
+        if (!hit) break;
+        sk = __ffs(hit) - 1;
+      }
+      const int scA = __shfl_sync(kFull, cA, sk);
+      const bool sact = __shfl_sync(kFull, (int)act, sk) != 0;
+      if (!sact || c <= scA || c > scA + kPkSpan) break;            // the path left what was speculated: plan again from here
+      if (sk != wk || c > wc0 || c < wc0 - 31) {                    // load a window: 32 columns ending at c
+        wk = sk; wc0 = c; wcA = scA;
+        const int cc = c - lane;
+        ww = cc > scA ? span[(size_t)sk * kPkSpan + (cc - scA - 1)] : 0ull;
+      }
+      const int off = wc0 - c, j = lane - off;                      // this lane looks at the j-th cell of the run (j >= 0)
+      const int avail = min(32 - off, c - wcA);                     // columns left in the window and in the span
       int run;
-      if (state == 0) {                                             // diagonal: lane t looks at cell (ii - t, jj - t)
-        const int cnt = min(ii, jj) + 1;
-        const unsigned nib = lane < cnt ? fl[(ii - lane) * 32 + (jj - lane)] : 0u;
-        const unsigned brk = __ballot_sync(kFull, (nib & 3u) != 0u);
-        run = brk ? __ffs(brk) - 1 : cnt;
-        put('s', run);
-        r -= run; c -= run;
-        if (run < cnt) state = (__shfl_sync(kFull, nib, run) & 2u) ? 1 : 2;   // the cell that stopped the diagonal
-      } else if (state == 1) {                                      // horizontal: lane t looks at cell (ii, jj - t)
-        const int cnt = jj + 1;
-        const unsigned hit = __ballot_sync(kFull, lane < cnt && (fl[ii * 32 + (jj - min(lane, jj))] & 8u));
-        run = hit ? __ffs(hit) : cnt;                               // the cell with bit1 set is consumed, then state 's'
+      if (state == 1) {
+        const int cnt = avail;
+        const unsigned hitm = __ballot_sync(kFull, j >= 0 && j < cnt && (pk_span_nibble(ww, i) & 8u));
+        const int first = hitm ? __ffs(hitm) - 1 - off : -1;
+        run = first >= 0 ? first + 1 : cnt;
         put('h', run);
         c -= run;
-        if (hit) state = 0;
-      } else {                                                      // vertical: lane t looks at cell (ii - t, jj)
-        const int cnt = ii + 1;
-        const unsigned hit = __ballot_sync(kFull, lane < cnt && (fl[(ii - min(lane, ii)) * 32 + jj] & 4u));
-        run = hit ? __ffs(hit) : cnt;
+        if (first >= 0) state = 0;
+      } else if (state == 0) {
+        const int cnt = min(avail, i + 1);
+        const unsigned nib = (j >= 0 && j < cnt) ? pk_span_nibble(ww, i - j) : 0u;
+        const unsigned brk = __ballot_sync(kFull, (nib & 3u) != 0u);
+        run = brk ? __ffs(brk) - 1 - off : cnt;
+        put('s', run);
+        r -= run; c -= run;
+        if (run < cnt) state = (__shfl_sync(kFull, nib, off + run) & 2u) ? 1 : 2;
+      } else {
+        const unsigned long long w0 = __shfl_sync(kFull, ww, off);  // the column's 16 rows live in one word
+        const int cnt = i + 1;
+        const unsigned hitm = __ballot_sync(kFull, lane < cnt && (pk_span_nibble(w0, i - min(lane, i)) & 4u));
+        run = hitm ? __ffs(hitm) : cnt;
         put('v', run);
         r -= run;
-        if (hit) state = 0;
+        if (hitm) state = 0;
       }
     }
     __syncwarp();
@@ -302,7 +397,7 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
 }
 
 template <int TBMODE, bool VFREE, int CLASSES>
-__global__ void __launch_bounds__(kPkWarps * 32)
+__global__ void __launch_bounds__(kPkWarps * 32, CLASSES == 4 ? 6 : 5)   // 12 / 10 warps per SM: what the tables allow
 gotoh_packed_kernel(const GotohBatch B) {
   constexpr bool TRACEBACK = TBMODE != kTbNone, FLAGS = TBMODE == kTbFlags, CKPT = TBMODE == kTbCkpt;
   constexpr int kPkTabWords = CLASSES * 512, kPkSmemWordsPerWarp = 2 * kPkTabWords + kPkTileWords;
@@ -311,7 +406,6 @@ gotoh_packed_kernel(const GotohBatch B) {
   const unsigned slot = blockIdx.x * kPkWarps + wib;
   int* const tabA = smem_pk + wib * kPkSmemWordsPerWarp;
   int* const tabB = tabA + kPkTabWords;
-  unsigned char* const tile_fl = reinterpret_cast<unsigned char*>(tabB + kPkTabWords);   // 16 x 32 pointer nibbles of one tile (CKPT)
   const float fmatch = (float)B.match, fmismatch = (float)B.mismatch;
   const int go = B.go, ge = B.ge, goe = B.go + B.ge;
   const bool hfree = B.hfree != 0;
@@ -365,7 +459,7 @@ gotoh_packed_kernel(const GotohBatch B) {
     // CKPT scratch of one pair inside the pointer slot: row checkpoints uint2[npass][T][32], then column checkpoints uint4[npass][NQ][8][32]
     uint2* const rowck = CKPT ? reinterpret_cast<uint2*>(ptr) : nullptr;
     uint4* const colck = CKPT ? ptr + (unsigned long long)npass * (unsigned)T * 16ull : nullptr;
-    uint4* const lastrow = CKPT ? colck + (unsigned long long)npass * (unsigned)NQ * 256ull : nullptr;   // uint4[T][4]: row-m lane's S words
+    unsigned long long* const span = CKPT ? reinterpret_cast<unsigned long long*>(colck + (unsigned long long)npass * (unsigned)NQ * 256ull) : nullptr;   // 32 x 64 span words
     uint8_t* const ops_out = TRACEBACK ? B.ops + (long long)pi * B.ops_stride : nullptr;
     const int rr_m = (m - 1) & (kPkRows - 1);                // where row m lives in the last pass
     const int m_half = rr_m >> 9, m_lane = (rr_m & 511) >> 4, m_i = rr_m & 15;
@@ -377,24 +471,7 @@ gotoh_packed_kernel(const GotohBatch B) {
       unsigned* const bot = rowbuf0 + (unsigned long long)((pass + 1) & 1) * (unsigned)(n + 1);
       const bool more = pass + 1 < npass;
 
-      // ---- substitution tables of this pass, entries in per-half form: A = half-band A in the low half, B = half-band B
-      //      in the high half, so that A | B is the packed addend of one word ----
-      __syncwarp();
-      for (int rr = lane; rr < kPkRows; rr += 32) {
-        const int r0 = base + rr;                              // 0-based row of a1
-        const int half = rr >> 9, rb = rr & 511, l = rb >> 4, i = rb & 15;
-        const int at = (i >> 2) * 128 + l * 4 + (i & 3);
-        float p[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) p[k] = r0 < m ? a[(size_t)k * m + r0] : 0.0f;
-        int* const tab = half ? tabB : tabA;
-#pragma unroll
-        for (int cls = 0; cls < CLASSES; ++cls) {
-          const unsigned s = (unsigned)(r0 < m ? sub_onehot(p, cls, fmatch, fmismatch) : 0) & 0xffffu;
-          tab[cls * 512 + at] = (int)(half ? s << 16 : s);
-        }
-      }
-      __syncwarp();
+      pk_build_tables<CLASSES>(tabA, tabB, a, m, base, fmatch, fmismatch, lane);
 
       // ---- per-lane state ----
       const int rtop_lo = base + lane * kRowsPerLane, rtop_hi = rtop_lo + 512;   // DP row just above the lane's rows
@@ -425,7 +502,6 @@ gotoh_packed_kernel(const GotohBatch B) {
       unsigned cur = 0;
       { const unsigned f0 = __shfl_sync(kFull, cchunk, 0); if (lane == 0) cur = f0; }
       const int cap_st = lane == m_lane ? n - 1 + lane + 32 * m_half : -1;
-      const bool lastrow_lane = CKPT && !more && hfree && lane == m_lane;
       uint4* pw = FLAGS ? ptr + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
       uint2* prow = CKPT ? rowck + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
 
@@ -507,11 +583,6 @@ gotoh_packed_kernel(const GotohBatch B) {
             *pw = w;
           }
           if (CKPT) {
-            if (lastrow_lane) {                                               // the lane that owns row m keeps its 16 S words of every step
-              uint4* pl = lastrow + (size_t)st * 4;
-              pl[0] = make_uint4(sl[0], sl[1], sl[2], sl[3]); pl[1] = make_uint4(sl[4], sl[5], sl[6], sl[7]);
-              pl[2] = make_uint4(sl[8], sl[9], sl[10], sl[11]); pl[3] = make_uint4(sl[12], sl[13], sl[14], sl[15]);
-            }
             *prow = make_uint2(bs, bv);                                       // bottom row (S, V) of both half-band blocks at this step
             if ((st & 31) == 31) {                                            // the lane's 16 rows (S, H) every 32 columns
               uint4* pc = colck + (((unsigned long long)pass * (unsigned)NQ + (unsigned)(st >> 5)) * 8ull) * 32ull + (unsigned)lane;
@@ -542,7 +613,7 @@ gotoh_packed_kernel(const GotohBatch B) {
         PkPair pp;
         pp.a = a; pp.b = b; pp.m = m; pp.n = n; pp.T = T; pp.NQ = NQ; pp.go = go; pp.ge = ge; pp.goe = goe; pp.bias = bias;
         pp.hfree = hfree; pp.vfree = vfree; pp.fmatch = fmatch; pp.fmismatch = fmismatch;
-        L = walk_traceback_ckpt(pp, rowck, colck, hfree ? reinterpret_cast<const unsigned*>(lastrow) : nullptr, tile_fl, ops_rev, lane);
+        L = walk_traceback_ckpt<CLASSES>(pp, rowck, colck, span, tabA, tabB, npass - 1, ops_rev, lane);
       } else {
         L = walk_traceback_packed(ptr, T, m, n, ops_rev, lane);
       }

@@ -134,8 +134,11 @@ __device__ __forceinline__ int walk_traceback_packed(const uint4* __restrict__ p
 // Substitution tables of one pass (rows base+1 .. base+1024), entries in per-half form: A = half-band A in the low half,
 // B = half-band B in the high half, so that A | B is the packed addend of one word. Layout [class][q][lane][4].
 template <int CLASSES>
-__device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const float* a, int m, int base, float fmatch, float fmismatch, int lane) {
+__device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const float* a, int m, int base, float fmatch, float fmismatch, int lane,
+                                                int* smin_io = nullptr, int* smax_io = nullptr) {
+  int smin = 0, smax = 0;
   __syncwarp();
+#pragma unroll 4
   for (int rr = lane; rr < kPkRows; rr += 32) {
     const int r0 = base + rr;                              // 0-based row of a1
     const int half = rr >> 9, rb = rr & 511, l = rb >> 4, i = rb & 15;
@@ -145,12 +148,15 @@ __device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const floa
     for (int k = 0; k < 5; ++k) p[k] = r0 < m ? a[(size_t)k * m + r0] : 0.0f;
     int* const tab = half ? tabB : tabA;
 #pragma unroll
-    for (int cls = 0; cls < CLASSES; ++cls) {
-      const unsigned s = (unsigned)(r0 < m ? sub_onehot(p, cls, fmatch, fmismatch) : 0) & 0xffffu;
-      tab[cls * 512 + at] = (int)(half ? s << 16 : s);
+    for (int cls = 0; cls < 5; ++cls) {                    // the range check always covers all five classes
+      const int sv = r0 < m ? sub_onehot(p, cls, fmatch, fmismatch) : 0;
+      smin = min(smin, sv); smax = max(smax, sv);
+      const unsigned s = (unsigned)sv & 0xffffu;
+      if (cls < CLASSES) tab[cls * 512 + at] = (int)(half ? s << 16 : s);
     }
   }
   __syncwarp();
+  if (smin_io) { *smin_io = min(*smin_io, smin); *smax_io = max(*smax_io, smax); }
 }
 
 // ---- checkpointed traceback (TBMODE == kTbCkpt) -------------------------------------------------------------------
@@ -268,7 +274,7 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
       else { ts = vbh ? e.x >> 16 : e.x & 0xffffu; tv = vbh ? e.y >> 16 : e.y & 0xffffu; }
       ts = pk_dup(ts); tv = pk_dup(tv);
     };
-    auto cls_load = [&](int col) -> unsigned { return (unsigned)base_class(P.b[min(max(col, 1), n) - 1]); };
+    auto cls_load = [&](int col) -> unsigned { return (unsigned)P.b[min(max(col, 1), n) - 1]; };   // raw character; classified at use
     unsigned diag, dv_unused;
     top_fix(top_load(cA), cA, diag, dv_unused);
     const int* const tab = half ? tabB : tabA;
@@ -286,7 +292,7 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
         const int col = cA + 1 + jc + u;
         unsigned us, uv;
         top_fix(tq[u], col, us, uv);
-        const unsigned cl = min(cq[u], (unsigned)(CLASSES - 1));
+        const unsigned cl = min((unsigned)base_class((unsigned char)cq[u]), (unsigned)(CLASSES - 1));
         const uint4* const pt = reinterpret_cast<const uint4*>(tab + cl * 512) + l;
         unsigned subw[kRowsPerLane];
 #pragma unroll
@@ -432,7 +438,8 @@ gotoh_packed_kernel(const GotohBatch B) {
 
     // ---- per-pair range check (decides whether 16-bit biased fields are exact for this pair) ----
     int smin = 0, smax = 0, foreign = 0;
-    for (int r0 = lane; r0 < m; r0 += 32) {
+    pk_build_tables<CLASSES>(tabA, tabB, a, m, 0, fmatch, fmismatch, lane, &smin, &smax);   // pass 0's tables double as the range scan
+    for (int r0 = kPkRows + lane; r0 < m; r0 += 32) {                                       // rows of later passes
       float p[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) p[k] = a[(size_t)k * m + r0];
@@ -442,7 +449,13 @@ gotoh_packed_kernel(const GotohBatch B) {
         smin = min(smin, s); smax = max(smax, s);
       }
     }
-    for (int j = lane; j < n; j += 32) foreign |= base_class(b[j]) >= CLASSES;   // characters outside ACGTN score 0: general kernel
+    for (int j0 = 0; j0 < n; j0 += 256) {                                  // characters outside ACGT(N) score 0: general kernel
+      unsigned char ch[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int j = j0 + 32 * u + lane; ch[u] = j < n ? b[j] : (unsigned char)'A'; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) foreign |= base_class(ch[u]) >= CLASSES;
+    }
     smin = __reduce_min_sync(kFull, smin); smax = __reduce_max_sync(kFull, smax);
     if (__any_sync(kFull, foreign)) continue;
     const int npass = (m + kPkRows - 1) / kPkRows;
@@ -471,7 +484,7 @@ gotoh_packed_kernel(const GotohBatch B) {
       unsigned* const bot = rowbuf0 + (unsigned long long)((pass + 1) & 1) * (unsigned)(n + 1);
       const bool more = pass + 1 < npass;
 
-      pk_build_tables<CLASSES>(tabA, tabB, a, m, base, fmatch, fmismatch, lane);
+      if (pass > 0) pk_build_tables<CLASSES>(tabA, tabB, a, m, base, fmatch, fmismatch, lane);
 
       // ---- per-lane state ----
       const int rtop_lo = base + lane * kRowsPerLane, rtop_hi = rtop_lo + 512;   // DP row just above the lane's rows
@@ -618,7 +631,13 @@ gotoh_packed_kernel(const GotohBatch B) {
         L = walk_traceback_packed(ptr, T, m, n, ops_rev, lane);
       }
       __syncwarp();
-      for (int j = lane; j < L; j += 32) ops_out[j] = ops_rev[L - 1 - j];
+      for (int j0 = 0; j0 < L; j0 += 256) {                                 // reverse into the caller's buffer, 8 loads in flight
+        uint8_t ch[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int j = j0 + 32 * u + lane; ch[u] = j < L ? ops_rev[L - 1 - j] : (uint8_t)0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int j = j0 + 32 * u + lane; if (j < L) ops_out[j] = ch[u]; }
+      }
       if (lane == 0) B.ops_len[pi] = L;
     }
     if (lane == 0) { B.scores[pi] = score; B.status[pi] = 1; atomicAdd(B.counter + 1, 1u); }

@@ -110,6 +110,48 @@ def test_foreign_reference_characters_fall_through(ctx, oracle_port):
         assert (int(s[i]), bytes(ops[i, : ol[i]])) == oracle_port.gotoh_ps(A[i], Bs[i], 1, 0, (3, -5, -10, -4)), i
 
 
+def test_checkpoint_and_flag_tracebacks_agree(ctx, oracle_port):
+    """The packed kernel has two traceback implementations: checkpoints + tile recompute (default) and pointer flags for
+    every cell (TRACY_B200_TB_MODE=flags). Same strings on shapes that stress the round planner: long free end-gap runs
+    (horizontal rounds), long internal gaps (speculation misses), several passes, tiny windows, every end-gap config."""
+    rng = np.random.default_rng(77)
+    A, Bs = [], []
+    for it in range(40):
+        m = int(rng.integers(1, 2300 if it % 10 == 0 else 700))
+        core = synth.random_seq(rng, m)
+        a = synth.profile_from_seq(rng, core, 0.35)
+        kind = it % 5
+        if kind == 0:      # trace inside a long window: long horizontal runs on both ends
+            b = synth.random_seq(rng, int(rng.integers(0, 2500))) + synth.mutate_seq(rng, core, 0.02, 0.01) + synth.random_seq(rng, int(rng.integers(0, 2500)))
+        elif kind == 1:    # a big deletion / insertion in the middle: the diagonal speculation must miss and re-plan
+            cut = m // 2
+            b = synth.mutate_seq(rng, core[:cut], 0.02, 0.01) + synth.random_seq(rng, int(rng.integers(40, 400))) + synth.mutate_seq(rng, core[cut:], 0.02, 0.01)
+        elif kind == 2:
+            b = synth.mutate_seq(rng, core[: m // 3] + core[2 * m // 3:], 0.02, 0.01) or b"A"
+        elif kind == 3:
+            b = synth.random_seq(rng, int(rng.integers(1, 70)))
+        else:
+            b = synth.mutate_seq(rng, core, 0.1, 0.08) or b"A"
+        A.append(a); Bs.append(b or b"A")
+    for hf, vf in ((1, 0), (0, 0), (1, 1), (0, 1)):
+        ac = AlignConfig(bool(hf), bool(vf))
+        os.environ.pop("TRACY_B200_TB_MODE", None)
+        s1, o1, l1 = ctx.gotoh("ps", A, Bs, DnaScore(3, -5, -10, -4), ac)
+        packed = ctx.last_packed_pairs()
+        assert packed >= len(A) - 4          # the longest traces against the longest windows exceed the 15-bit range
+        os.environ["TRACY_B200_TB_MODE"] = "flags"
+        try:
+            s2, o2, l2 = ctx.gotoh("ps", A, Bs, DnaScore(3, -5, -10, -4), ac)
+            assert ctx.last_packed_pairs() == packed
+        finally:
+            os.environ.pop("TRACY_B200_TB_MODE", None)
+        assert np.array_equal(s1, s2) and np.array_equal(l1, l2)
+        for i in range(len(A)):
+            assert bytes(o1[i, : l1[i]]) == bytes(o2[i, : l2[i]]), (hf, vf, i)
+        for i in range(0, len(A), 3):
+            assert (int(s1[i]), bytes(o1[i, : l1[i]])) == oracle_port.gotoh_ps(A[i], Bs[i], hf, vf, (3, -5, -10, -4)), (hf, vf, i)
+
+
 def test_packed_config2_full_shape(ctx, oracle_port):
     """BASELINE configs[1] shape through the packed kernel: 256 pairs of 1000 x 4000, 8 exhaustively vs the oracle."""
     m, n, N = 1000, 4000, 256

@@ -301,6 +301,7 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     const size_t cap = (size_t)std::max(1.0, (768.0 * 1024 * 1024) / std::max(per_pair, 1.0));
     chunk = std::max<size_t>(1, std::min(chunk, cap));
   }
+  if (const char* ce = getenv("TRACY_B200_CHUNK")) { const long v = atol(ce); if (v > 0) chunk = std::min<size_t>((size_t)v, np); }   // tuning knob
   const size_t esa = elem_size_a(mode), esb = elem_size_b(mode);
   int rc_all = TB_OK;
   size_t nchunks = (np + chunk - 1) / chunk;

@@ -1,0 +1,63 @@
+"""Throughput of the other entry points / BASELINE.json configs (not the headline bench): device time from the library's
+CUDA events where available, otherwise host clock around the host-buffer call. Prints one JSON object."""
+import json, sys, time, os
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import tracy_b200
+from tracy_b200 import AlignConfig, DnaScore, synth, msa
+
+ctx = tracy_b200.Context(0)
+sc = DnaScore(3, -5, -10, -4)
+out = {}
+
+def timed(fn, reps=3):
+    fn()
+    best = 1e9
+    for _ in range(reps):
+        t0 = time.perf_counter(); fn(); best = min(best, time.perf_counter() - t0)
+    return best
+
+# config 2 shape, score only (gotohScore: orientation picks)
+N, m, n = 20000, 1000, 4000
+prof, win = synth.align_batch(N, m, n, seed=44)
+a1, a2 = tracy_b200.uniform_profiles(prof), tracy_b200.uniform_seqs(win)
+t = timed(lambda: ctx.gotoh("ps", a1, a2, sc, AlignConfig(True, False), traceback=False))
+k = ctx.last_kernel_ms()
+out["ps_score_only_1000x4000"] = {"pairs": N, "host_call_gcups": N * m * n / t / 1e9, "kernel_gcups": N * m * n / ((k["packed_ms"] + k["general_ms"]) * 1e-3) / 1e9}
+
+# string x string with traceback (allele alignments of decompose)
+N2 = 4000
+seqs = [bytes(b"ACGT"[x] for x in np.random.default_rng(i).integers(0, 4, 1000)) for i in range(64)]
+S1 = [seqs[i % 64] for i in range(N2)]
+S2 = [bytes(win[i]) for i in range(N2)]
+t = timed(lambda: ctx.gotoh("ss", S1, S2, sc, AlignConfig(True, False)))
+k = ctx.last_kernel_ms()
+out["ss_traceback_1000x4000"] = {"pairs": N2, "kernel_gcups": N2 * 1000 * 4000 / (k["general_ms"] * 1e-3) / 1e9}
+
+# config 4: all-pairs profile x profile, score only (distance matrix) and with traceback
+rng = np.random.default_rng(5)
+NT, L = 256, 900
+contig = synth.random_seq(rng, 115 * NT + L)
+profs = [synth.profile_from_seq(rng, contig[115 * i: 115 * i + L], 0.3) for i in range(NT)]
+ii, jj = np.triu_indices(NT, 1)
+A = tracy_b200.pack_profiles([profs[i] for i in ii]); B = tracy_b200.pack_profiles([profs[j] for j in jj])
+t = timed(lambda: ctx.gotoh("pp", A, B, sc, AlignConfig(True, True), traceback=False), reps=2)
+k = ctx.last_kernel_ms()
+out["pp_all_pairs_score_900x900"] = {"pairs": len(ii), "kernel_gcups": len(ii) * L * L / (k["general_ms"] * 1e-3) / 1e9, "host_call_s": t}
+sub = 4096
+A2 = tracy_b200.pack_profiles([profs[i] for i in ii[:sub]]); B2 = tracy_b200.pack_profiles([profs[j] for j in jj[:sub]])
+t = timed(lambda: ctx.gotoh("pp", A2, B2, sc, AlignConfig(True, True)), reps=2)
+k = ctx.last_kernel_ms()
+out["pp_traceback_900x900"] = {"pairs": sub, "kernel_gcups": sub * L * L / (k["general_ms"] * 1e-3) / 1e9}
+
+# config 3: decompose sweeps, 10k traces, maxindel 30
+NTd = 10000
+ref = [synth.random_seq(rng, 1100, b"ACGT-") for _ in range(64)]
+pri = [synth.random_seq(rng, 1000, b"ACGTN") for _ in range(64)]
+sec = [synth.random_seq(rng, 1000, b"ACGTRYSWKMN") for _ in range(64)]
+R = [ref[i % 64] for i in range(NTd)]; P = [pri[i % 64] for i in range(NTd)]; S = [sec[i % 64] for i in range(NTd)]
+t = timed(lambda: ctx.decompose_sweep(R, P, S, [950] * NTd, [300] * NTd, [310] * NTd, [30] * NTd, [30] * NTd), reps=2)
+out["decompose_sweep_10k_traces_pm30"] = {"traces": NTd, "kernel_ms": ctx.last_kernel_ms()["sweep_ms"], "host_call_s": t,
+                                          "compared_columns_per_s": NTd * 59 * 650 / (ctx.last_kernel_ms()["sweep_ms"] * 1e-3)}
+print(json.dumps(out, indent=1))

@@ -89,6 +89,19 @@ __device__ __forceinline__ int sub_profile(const float p1[5], const float p2[5],
   return __float2int_rz(acc);
 }
 
+// The same sum restricted to channels A,C,G,T: exact whenever the N rows (k = 4) of BOTH profiles are zero for the columns
+// involved, because every skipped term is (+-0 * w) = +-0 and adding +-0 never changes an accumulator that started at +0
+// (SURVEY appendix A.3). Profiles made by createProfile always have a zero N row (src/profile.h:37).
+__device__ __forceinline__ int sub_profile4(const float p1[5], const float p2[5], float fmatch, float fmismatch) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2)
+      acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(p1[k1], p2[k2]), k1 == k2 ? fmatch : fmismatch));
+  return __float2int_rz(acc);
+}
+
 // ---- pointer scratch layout -------------------------------------------------------------------------------
 // A band is nv*16 DP rows; virtual lane v owns rows band*nv*16 + 16v + 1 .. +16 and at step `st` works on column
 // c = st - v + 1 (a systolic skew), so one warp-step writes one contiguous 256 B (nv=32) or 512 B (nv=64) line.

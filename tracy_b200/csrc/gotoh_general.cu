@@ -111,6 +111,15 @@ gotoh_general_kernel(const GotohBatch B) {
       continue;
     }
 
+    // profile x profile: when the N rows of both inputs are all zero (every trace profile) the 9 terms with k1 = 4 or
+    // k2 = 4 are exact zeros and are skipped (sub_profile4); decided per pair, so the branch is warp-uniform.
+    [[maybe_unused]] bool nzero = false;
+    if constexpr (MODE == kModePP) {
+      bool nz = false;
+      for (int j = lane; j < m; j += 32) nz |= ((const float*)a)[(size_t)4 * m + j] != 0.0f;
+      for (int j = lane; j < n; j += 32) nz |= ((const float*)b)[(size_t)4 * n + j] != 0.0f;
+      nzero = !__any_sync(kFull, nz);
+    }
     const int nb = (m + kGenBand - 1) / kGenBand;
     const int T = n + 31;                       // steps per band
     // Row 0 of the matrix feeds band 0 (src/gotoh.h:113-118): S = horizontal end gap, V = -inf.
@@ -204,7 +213,7 @@ gotoh_general_kernel(const GotohBatch B) {
               float p1[5];
 #pragma unroll
               for (int k = 0; k < 5; ++k) p1[k] = tab_f[k * kGenBand + i * 32 + lane];
-              sub = sub_profile(p1, p2, fmatch, fmismatch);
+              sub = nzero ? sub_profile4(p1, p2, fmatch, fmismatch) : sub_profile(p1, p2, fmatch, fmismatch);
             }
             const int hext = hh[i] + hge[i];
             const int hn = max(sl[i] + hgo[i], hext);          // src/gotoh.h:129

@@ -145,6 +145,7 @@ class _Ref:
         L.ref_decompose_alleles.restype = C.c_int
         L.ref_bench_gotoh_ps.argtypes = [_f32p, C.c_char_p, C.c_int, C.c_int, C.c_int] + _SC + [C.c_int, _i32p]
         L.ref_bench_gotoh_ps.restype = C.c_longlong
+        L.ref_reverse_complement.argtypes = [C.c_char_p, C.c_int]
         L.ref_trim_reference_slice.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int, C.c_int,
                                                C.c_char_p, C.c_int]
         L.ref_trim_reference_slice.restype = C.c_int
@@ -155,6 +156,11 @@ class _Ref:
         L.ref_msa.argtypes = [_f32p, _i64p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int,
                               np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), _i32p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ref_msa.restype = C.c_int
+
+    def reverse_complement(self, seq):
+        buf = C.create_string_buffer(bytes(seq), len(seq) + 1)
+        self.lib.ref_reverse_complement(buf, len(seq))
+        return buf.raw[: len(seq)]
 
     def trim_reference_slice(self, row0, row1, refslice, forward, pos, trim_left, trim_right):
         out = C.create_string_buffer(len(refslice) + 1)

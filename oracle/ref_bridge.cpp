@@ -186,6 +186,13 @@ int ref_trim_reference_slice(const char* row0, const char* row1, int L, const ch
   return n;
 }
 
+// reverseComplement(std::string&) (src/fmindex.h:11-26), in place.
+void ref_reverse_complement(char* seq, int n) {
+  std::string s(seq, seq + n);
+  tracy::reverseComplement(s);
+  std::memcpy(seq, s.data(), n);
+}
+
 // _createProfile(char MSA -> profile) (src/align.h:138-180). rows: nrow x ncol chars row-major.
 void ref_profile_from_alignment(const char* rows, int nrow, int ncol, float* out /*[6][ncol]*/) {
   TAlign al(boost::extents[nrow][ncol]);

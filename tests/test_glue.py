@@ -94,3 +94,19 @@ def run_msa_case(ctx, idx):
     assert np.array_equal(rows, GOLD[f"ms_rows{idx}"])
     gapped, cs, qs = msa.consensus(rows, 0.5, False)
     assert gapped == bytes(GOLD[f"ms_gapped{idx}"]) and cs == bytes(GOLD[f"ms_cons{idx}"]) and qs == bytes(GOLD[f"ms_qual{idx}"])
+
+
+def test_reverse_complement_seq(oracle_ref):
+    """drivers.reverse_complement_seq against reverseComplement(std::string&) (src/fmindex.h:11-26), incl. its quirk for
+    characters outside ACGTN; the three fixed cases were produced by the reference."""
+    from tracy_b200 import drivers
+    fixed = {b"ACGTNRacg": b"CGTTNACGT", b"": b"", b"AAxCC-GT": b"ACxGG-TT"}
+    for k, v in fixed.items():
+        assert drivers.reverse_complement_seq(k) == v
+    if oracle_ref is None:
+        pytest.skip("reference build not present")
+    rng = np.random.default_rng(4)
+    alphabet = np.frombuffer(b"ACGTNacgtnRYX-", np.uint8)
+    for _ in range(100):
+        s = bytes(alphabet[rng.integers(0, len(alphabet), int(rng.integers(0, 60)))])
+        assert drivers.reverse_complement_seq(s) == oracle_ref.reverse_complement(s), s

@@ -76,3 +76,65 @@ def test_exclude_unmatched(ctx, oracle_port):
                 break
         want.append(hit)
     assert keep == want and want == [True, True, True, True, False]
+
+
+def test_align_batch_matches_reference_sequence(ctx, oracle_port, oracle_ref):
+    """drivers.align_batch = the DP sequence of sage() for FASTA references (src/sage.h:233-260, :311), all traces in three
+    batched GPU calls. Checked against the same sequence composed from the CPU oracle one trace at a time (and, where the
+    reference build is present, from tracy's own headers with its reverseComplementProfile(one-hot) formulation)."""
+    from tracy_b200 import drivers
+    rng = np.random.default_rng(2024)
+    trimmed, full, refs = [], [], []
+    for t in range(12):
+        nref = int(rng.integers(400, 1500))
+        ref = synth.random_seq(rng, nref, b"ACGTN" if t % 4 == 0 else b"ACGT")
+        st, ln = int(rng.integers(0, nref - 300)), int(rng.integers(150, 300))
+        core = synth.mutate_seq(rng, ref[st: st + ln].replace(b"N", b"A"), 0.02, 0.01)
+        p = synth.profile_from_seq(rng, core, 0.3)
+        if t % 2:                                              # trace sequenced from the other strand
+            p = np.ascontiguousarray(p[[3, 2, 1, 0, 4, 5], ::-1])
+        tl, tr_ = int(rng.integers(0, 20)), int(rng.integers(0, 20))
+        full.append(p); trimmed.append(np.ascontiguousarray(p[:, tl: p.shape[1] - tr_])); refs.append(ref)
+    got = drivers.align_batch(ctx, trimmed, full, refs, DnaScore(*SC), 50, 50)
+    assert any(g["forward"] for g in got) and not all(g["forward"] for g in got)
+    for i, g in enumerate(got):
+        rc = drivers.reverse_complement_seq(refs[i])
+        if oracle_ref is not None:                             # tracy's own formulation of the two orientation scores
+            fwdp = oracle_ref.onehot(refs[i])
+            gs_f = oracle_ref.gotoh_score(trimmed[i], fwdp, 1, 0, SC)
+            gs_r = oracle_ref.gotoh_score(trimmed[i], oracle_ref.revcomp_profile(fwdp), 1, 0, SC)
+        else:
+            gs_f = oracle_port.gotoh_ps(trimmed[i], refs[i], 1, 0, SC)[0]
+            gs_r = oracle_port.gotoh_ps(trimmed[i], rc, 1, 0, SC)[0]
+        fw = gs_f > gs_r
+        pref = refs[i] if fw else rc
+        _, ops = oracle_port.gotoh_ps(trimmed[i], pref, 1, 0, SC)
+        r0 = bytes(0x2D if o == ord("h") else 0x58 for o in ops); r1 = bytes(0x2D if o == ord("v") else 0x58 for o in ops)
+        if oracle_ref is not None:
+            sl, pos = oracle_ref.trim_reference_slice(r0, r1, pref, fw, 0, 50, 50)
+        else:
+            sl, pos = tracy_b200.trim_reference_slice(r0, r1, pref, fw, 0, 50, 50)
+        sc2, ops2 = oracle_port.gotoh_ps(full[i], sl, 1, 0, SC)
+        rows = oracle_port.rows_from_ops(full[i], oracle_port.onehot(sl), ops2)
+        assert (g["forward"], g["refslice"], g["pos"], g["score"], g["row0"], g["row1"]) == (fw, sl, pos, sc2, rows[0], rows[1]), i
+
+
+def test_assemble_denovo_recovers_contig(ctx):
+    """drivers.assemble_denovo on overlapping traces of one contig, half of them reverse-complemented: the consensus
+    equals the planted contig region covered by >= fraction_called of the traces, up to the global strand."""
+    from tracy_b200 import drivers
+    rng = np.random.default_rng(99)
+    contig = synth.random_seq(rng, 700)
+    profs = []
+    for t in range(10):
+        st = 50 * t
+        p = synth.profile_from_seq(rng, contig[st: st + 250], 0.25)
+        if t % 3 == 1:
+            p = np.ascontiguousarray(p[[3, 2, 1, 0, 4, 5], ::-1])
+        profs.append(p)
+    profs.append(synth.profile_from_seq(rng, synth.random_seq(rng, 200), 0.25))    # a stray trace
+    r = drivers.assemble_denovo(ctx, profs, DnaScore(*SC), 0.5, 0.1)
+    assert 10 not in r["kept"] and len(r["kept"]) == 10
+    cons = r["consensus"]
+    assert len(cons) >= 650
+    assert cons in contig or drivers.reverse_complement_seq(cons) in contig

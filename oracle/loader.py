@@ -146,6 +146,9 @@ class _Ref:
         L.ref_bench_gotoh_ps.argtypes = [_f32p, C.c_char_p, C.c_int, C.c_int, C.c_int] + _SC + [C.c_int, _i32p]
         L.ref_bench_gotoh_ps.restype = C.c_longlong
         L.ref_reverse_complement.argtypes = [C.c_char_p, C.c_int]
+        L.ref_find_homozygous_breakpoint.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.ref_find_homozygous_breakpoint.restype = C.c_int
+        L.ref_generate_secondary_decomposed.argtypes = [_i32p, C.c_int, _i32p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p]
         L.ref_trim_reference_slice.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int, C.c_int,
                                                C.c_char_p, C.c_int]
         L.ref_trim_reference_slice.restype = C.c_int
@@ -156,6 +159,17 @@ class _Ref:
         L.ref_msa.argtypes = [_f32p, _i64p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int,
                               np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), _i32p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ref_msa.restype = C.c_int
+
+    def find_homozygous_breakpoint(self, row0, row1):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_uint32(), C.c_float()
+        ok = self.lib.ref_find_homozygous_breakpoint(bytes(row0), bytes(row1), len(row0), C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return (bool(a.value), bool(b.value), c.value, d.value) if ok else None
+
+    def generate_secondary_decomposed(self, acgt, bcpos, primary, secondary):
+        acgt = np.ascontiguousarray(acgt, np.int32); bcpos = np.ascontiguousarray(bcpos, np.int32)
+        out = C.create_string_buffer(len(primary) + 1)
+        self.lib.ref_generate_secondary_decomposed(acgt.reshape(-1), acgt.shape[1], bcpos, bytes(primary), bytes(secondary), len(primary), out)
+        return out.raw[: len(primary)]
 
     def reverse_complement(self, seq):
         buf = C.create_string_buffer(bytes(seq), len(seq) + 1)

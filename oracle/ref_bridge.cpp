@@ -186,6 +186,29 @@ int ref_trim_reference_slice(const char* row0, const char* row1, int L, const ch
   return n;
 }
 
+// findHomozygousBreakpoint (src/decompose.h:59-128): returns 0 when the reference function returns false.
+int ref_find_homozygous_breakpoint(const char* row0, const char* row1, int L, int* indelshift, int* traceleft, uint32_t* breakpoint, float* bestDiff) {
+  TAlign al(boost::extents[2][L]);
+  for (int j = 0; j < L; ++j) { al[0][j] = row0[j]; al[1][j] = row1[j]; }
+  tracy::TraceBreakpoint bp; bp.indelshift = false; bp.traceleft = true; bp.breakpoint = 0; bp.bestDiff = 0;
+  const bool ok = tracy::findHomozygousBreakpoint(al, bp);
+  *indelshift = bp.indelshift; *traceleft = bp.traceleft; *breakpoint = bp.breakpoint; *bestDiff = bp.bestDiff;
+  return ok ? 1 : 0;
+}
+
+// generateSecondaryDecomposed (src/decompose.h:378-410): out receives bc.secDecompose (nbc chars).
+void ref_generate_secondary_decomposed(const int32_t* acgt, int nsamples, const int32_t* bcpos, const char* primary, const char* secondary,
+                                       int nbc, char* out) {
+  tracy::Trace tr; tracy::BaseCalls bc;
+  tr.traceACGT.resize(4);
+  for (int k = 0; k < 4; ++k) tr.traceACGT[k].assign(acgt + (size_t)k * nsamples, acgt + (size_t)(k + 1) * nsamples);
+  bc.bcPos.assign(bcpos, bcpos + nbc);
+  bc.primary.assign(primary, primary + nbc);
+  bc.secondary.assign(secondary, secondary + nbc);
+  tracy::generateSecondaryDecomposed(tr, bc);
+  std::memcpy(out, bc.secDecompose.data(), nbc);
+}
+
 // reverseComplement(std::string&) (src/fmindex.h:11-26), in place.
 void ref_reverse_complement(char* seq, int n) {
   std::string s(seq, seq + n);

@@ -134,3 +134,30 @@ def test_decompose_golden_modes_covered(oracle_port):
         modes.add(decompose.decompose_alleles(c["row0"], c["row1"], c["pri"], c["sec"], c["trimL"], c["trimR"], c["maxindel"], c["madc"],
                                               c["bp"], c["nref"], sweep)[3]["mode"])
     assert {"del", "ins"} <= modes, modes
+
+
+def test_decompose_alleles_batch_lockstep(oracle_port, capsys):
+    """decompose_alleles_batch runs every trace's decomposeAlleles in lock-step with ONE sweep call per phase; with the
+    sweeps served by the CPU oracle it must reproduce the golden outputs of all cases at once."""
+    class Ctx:
+        calls = 0
+
+        def decompose_sweep(self, refrows, pris, secs, vi_end, ai, vi, ndel, nins, grid=False):
+            Ctx.calls += 1
+            S = int(max(1, max(ndel), max(nins)))
+            n = len(refrows)
+            fref, fins = np.zeros((n, S), np.int32), np.zeros((n, S), np.int32)
+            g = np.zeros((n, S, S), np.int32) if grid else None
+            for t in range(n):
+                a, b, c = oracle_port.decompose_sweep(refrows[t], pris[t], secs[t], vi_end[t], ai[t], vi[t], ndel[t], nins[t], grid)
+                fref[t, : ndel[t]] = a
+                fins[t, : nins[t]] = b
+                if grid:
+                    g[t, : nins[t], : ndel[t]] = c
+            return fref, fins, g
+    items = [dict(row0=c["row0"], row1=c["row1"], primary=c["pri"], secondary=c["sec"], trim_left=c["trimL"], trim_right=c["trimR"],
+                  maxindel=c["maxindel"], madc=c["madc"], breakpoint=c["bp"], refslice_len=c["nref"]) for c in DGOLD]
+    res = decompose.decompose_alleles_batch(Ctx(), items)
+    assert Ctx.calls <= 2                      # the indel sweep for everybody, the ins x del grid for those without a candidate
+    for c, (pri, sec, dcp, info) in zip(DGOLD, res):
+        assert pri == c["pri_out"] and sec == c["sec_out"] and np.array_equal(dcp, c["dcp"])

@@ -115,13 +115,57 @@ def decompose_alleles(row0, row1, primary, secondary, trim_left, trim_right, max
     primary/secondary: basecall strings (bytes). `sweep(refrow, pri, sec, vi_end, align_index, var_index, ndel, nins, grid)`
     returns (fref[ndel], fins[nins], grid[nins][ndel] | None).
     Returns (primary', secondary', dcp int32[k][2], info dict)."""
+    gen = _decompose_gen(row0, row1, primary, secondary, trim_left, trim_right, maxindel, madc, breakpoint, refslice_len, ncons)
+    try:
+        req = next(gen)
+        while True:
+            req = gen.send(sweep(*req))
+    except StopIteration as done:
+        return done.value
+
+
+def decompose_alleles_batch(ctx, items):
+    """decomposeAlleles for MANY traces with the sweeps of all of them in one GPU call per phase (the indel sweep for every
+    trace; then the ins x del grid for the traces that found no candidate, reference src/decompose.h:288-313).
+    items: list of dicts with the keyword arguments of decompose_alleles (without `sweep`). Returns one result tuple each."""
+    gens = [_decompose_gen(it["row0"], it["row1"], it["primary"], it["secondary"], it["trim_left"], it["trim_right"], it["maxindel"],
+                           it["madc"], it["breakpoint"], it["refslice_len"], it.get("ncons")) for it in items]
+    results = [None] * len(items)
+    pending = {}
+    for i, g in enumerate(gens):
+        try:
+            pending[i] = next(g)
+        except StopIteration as done:
+            results[i] = done.value
+    while pending:
+        idx = sorted(pending)
+        for want_grid in (False, True):
+            sel = [i for i in idx if i in pending and pending[i][8] == want_grid]
+            if not sel:
+                continue
+            req = [pending[i] for i in sel]
+            fref, fins, grid = ctx.decompose_sweep([r[0] for r in req], [r[1] for r in req], [r[2] for r in req], [r[3] for r in req],
+                                                   [r[4] for r in req], [r[5] for r in req], [r[6] for r in req], [r[7] for r in req], grid=want_grid)
+            for k, i in enumerate(sel):
+                nd, ni = req[k][6], req[k][7]
+                ans = (fref[k, :nd], fins[k, :ni], grid[k, :ni, :nd] if want_grid else None)
+                try:
+                    pending[i] = gens[i].send(ans)
+                except StopIteration as done:
+                    results[i] = done.value
+                    del pending[i]
+    return results
+
+
+def _decompose_gen(row0, row1, primary, secondary, trim_left, trim_right, maxindel, madc, breakpoint, refslice_len, ncons=None):
+    """decomposeAlleles as a generator: yields the arguments of each sweep it needs and is sent the result."""
     pri, sec = bytearray(primary), bytearray(secondary)
     ncons = len(primary) if ncons is None else ncons
     align_index, var_index, ref_pointer = walk_to_breakpoint(row0, row1, pri, sec, trim_left, breakpoint)
     bp_abs = (breakpoint + trim_left) & _U32
     ndel, nins, vi_end, maxdel, maxins = sweep_extents(ncons, refslice_len, ref_pointer, trim_right, bp_abs, maxindel)
 
-    fref, fins, _ = sweep(bytes(row1), bytes(pri), bytes(sec), vi_end, align_index, var_index, ndel, nins, False)
+    fref, fins, _ = yield (bytes(row1), bytes(pri), bytes(sec), vi_end, align_index, var_index, ndel, nins, False)
     fref = [int(x) for x in fref[:ndel]]
     fins = [int(x) for x in fins[:nins]]
     fins[0] = fref[0]                                         # src/decompose.h:248
@@ -155,7 +199,7 @@ def decompose_alleles(row0, row1, primary, secondary, trim_left, trim_right, max
         best_ins = best_del = 0
         best_fr = 1000
         if gi > 0 and gd > 0:
-            _, _, grid = sweep(refrow, bytes(pri), bytes(sec), vi_end, align_index, var_index, gd, gi, True)
+            _, _, grid = yield (refrow, bytes(pri), bytes(sec), vi_end, align_index, var_index, gd, gi, True)
             for ins in range(gi):
                 prev = 0
                 for d in range(gd):

@@ -1,6 +1,7 @@
 """Batch drivers: the DP sequences of tracy's subcommand drivers, run for MANY traces at once.
 
   align_batch      sage()     for single-FASTA references   reference src/sage.h:222-260, :311
+  decompose_batch  indigo()   for single-FASTA references   reference src/indigo.h:190-388
   assemble_denovo  assemble() de novo branch                reference src/assemble.h:418-471
 
 Everything between the file readers and the file writers of those drivers: orientation pick, semi-global alignment of the
@@ -10,8 +11,8 @@ host logic of tracy_b200.api / tracy_b200.msa. File formats, basecalling and the
 """
 import numpy as np
 
-from . import msa
-from .api import PS, AlignConfig, DnaScore, rows_from_ops, trim_reference_slice
+from . import decompose, msa
+from .api import PS, SS, AlignConfig, DnaScore, find_breakpoint, rows_from_ops, trim_reference_slice
 
 _SEMIGLOBAL = AlignConfig(True, False)          # AlignConfig<true, false>, src/sage.h:165
 _COMP = {ord("A"): ord("T"), ord("C"): ord("G"), ord("G"): ord("C"), ord("T"): ord("A"), ord("N"): ord("N")}
@@ -63,6 +64,137 @@ def align_batch(ctx, trimmed_profiles, full_profiles, references, sc=DnaScore(3,
     for i in range(n):
         row0, row1 = rows_from_ops(PS, full_profiles[i], slices[i], bytes(ops2[i, : ol2[i]]))
         out.append(dict(forward=forward[i], refslice=slices[i], pos=pos[i], score=int(score[i]), row0=row0, row1=row1))
+    return out
+
+
+def trimmed_seq(s, ltrim, rtrim):
+    """trimmedSeq, reference src/abif.h:68-75."""
+    s = bytes(s)
+    if ltrim + rtrim + 1 >= len(s):
+        return s
+    return s[ltrim: len(s) - rtrim]
+
+
+def find_homozygous_breakpoint(row0, row1):
+    """findHomozygousBreakpoint(align, bp), reference src/decompose.h:59-128: breakpoint of a homozygous indel from the
+    mismatch density either side of every alignment column. Returns None where the reference returns false, else
+    dict(indelshift, traceleft, breakpoint, bestDiff). bestDiff is a float in the reference (compared as double)."""
+    row0, row1 = bytes(row0), bytes(row1)
+    L = len(row0)
+    gap = 0x2D
+    start = end = var_index = 0
+    for j in range(L):
+        if row0[j] != gap and row1[j] != gap:
+            start = j
+            break
+        if row0[j] != gap:
+            var_index += 1
+    for j in range(L - 1, -1, -1):
+        if row0[j] != gap and row1[j] != gap:
+            end = j
+            break
+    w = 25
+    if start >= end or end < start + 2 * w:
+        return None
+    mism = np.frombuffer(row0, np.uint8) != np.frombuffer(row1, np.uint8)
+    csum = np.concatenate([[0], np.cumsum(mism)])
+    best = np.float32(0)
+    traceleft, bp = True, 0
+    for i in range(start, start + w):
+        if row0[i] != gap:
+            var_index += 1
+    for i in range(start + w, end - w):
+        if row0[i] != gap:
+            var_index += 1
+        left = float(csum[i] - csum[i - w]) / float(w)
+        right = float(csum[i + w] - csum[i]) / float(w)
+        diff = abs(right - left)
+        if diff > float(best):
+            bp, best, traceleft = var_index, np.float32(diff), left < right
+    indelshift = True
+    if float(best) < 0.25:
+        indelshift, bp, traceleft, best = False, var_index, True, np.float32(0)
+    return dict(indelshift=indelshift, traceleft=traceleft, breakpoint=bp, bestDiff=float(best))
+
+
+def generate_secondary_decomposed(trace, bcpos, primary, secondary):
+    """generateSecondaryDecomposed(tr, bc), reference src/decompose.h:378-410: the second allele as plain nucleotides; an
+    IUPAC pair is resolved to its higher peak (strict '>' for the first base of the pair)."""
+    pair = {ord("R"): (0, 2, b"AG"), ord("Y"): (1, 3, b"CT"), ord("S"): (1, 2, b"CG"), ord("W"): (0, 3, b"AT"), ord("K"): (2, 3, b"GT"),
+            ord("M"): (0, 1, b"AC")}
+    pri, sec = bytes(primary), bytes(secondary)
+    out = bytearray(len(sec))
+    for i in range(min(len(pri), len(sec))):
+        if pri[i] == sec[i]:
+            out[i] = pri[i]
+        elif sec[i] in b"ACGT":
+            out[i] = sec[i]
+        elif sec[i] in pair:
+            a, b, ch = pair[sec[i]]
+            out[i] = ch[0] if trace[a][bcpos[i]] > trace[b][bcpos[i]] else ch[1]
+        else:
+            out[i] = ord("N")
+    return bytes(out)
+
+
+def decompose_batch(ctx, traces, bcpos, primaries, secondaries, references, sc=DnaScore(3, -5, -10, -4), trim_left=50, trim_right=50,
+                    maxindel=1000, madc=5):
+    """`tracy decompose` against single-FASTA references for a batch of basecalled traces: the DP sequence of indigo()
+    (reference src/indigo.h:190-388) with every stage batched over the traces.
+
+    traces: int32[4][nsamples] each; bcpos / primaries / secondaries: BaseCalls::bcPos / primary / secondary.
+    Returns one dict per trace, or None where indigo() gives up (alignment below its score threshold, no usable homozygous
+    breakpoint): forward, refslice, score, row0/row1 (trimmed trace vs reference), breakpoint dict, primary / secondary after
+    decomposeAlleles, secDecompose, decomp table, align1 / align2 / align3 = (score, row0, row1, refslice, pos)."""
+    n = len(traces)
+    refs = [bytes(r) for r in references]
+    rc = [reverse_complement_seq(r) for r in refs]
+    prof = ctx.create_profile(traces, bcpos, primaries, secondaries, trim_left, trim_right)        # src/indigo.h:190-192
+    bps = [find_breakpoint(p) for p in prof]                                                        # src/indigo.h:195-196
+    s = ctx.gotoh(PS, prof + prof, refs + rc, sc, _SEMIGLOBAL, traceback=False)[0]                  # src/indigo.h:235-236
+    forward = [bool(s[i] > s[n + i]) for i in range(n)]
+    rsl = [refs[i] if forward[i] else rc[i] for i in range(n)]
+    ali, ops, ol = ctx.gotoh(PS, prof, rsl, sc, _SEMIGLOBAL)                                        # src/indigo.h:302
+    out = [None] * n
+    items, live = [], []
+    for i in range(n):
+        seqsize = float(prof[i].shape[1])
+        if int(ali[i]) <= seqsize * 0.35 * sc.match + seqsize * (1 - 0.35) * sc.mismatch:           # src/indigo.h:303-309
+            continue
+        row0, row1 = rows_from_ops(PS, prof[i], rsl[i], bytes(ops[i, : ol[i]]))
+        bp = bps[i]
+        if not bp["indelshift"]:                                                                    # src/indigo.h:314-317
+            bp = find_homozygous_breakpoint(row0, row1)
+            if bp is None:
+                continue
+        out[i] = dict(forward=forward[i], refslice=rsl[i], score=int(ali[i]), row0=row0, row1=row1, breakpoint=bp)
+        items.append(dict(row0=row0, row1=row1, primary=bytes(primaries[i]), secondary=bytes(secondaries[i]), trim_left=trim_left,
+                          trim_right=trim_right, maxindel=maxindel, madc=madc, breakpoint=bp["breakpoint"], refslice_len=len(rsl[i])))
+        live.append(i)
+    for i, (pri, sec, dcp, info) in zip(live, decompose.decompose_alleles_batch(ctx, items)):       # src/indigo.h:340
+        out[i].update(primary=pri, secondary=sec, decomp=dcp, decompose_mode=info["mode"])
+        out[i]["secDecompose"] = generate_secondary_decomposed(traces[i], bcpos[i], pri, sec)       # src/indigo.h:344
+    if not live:
+        return out
+    # allele-specific alignments (src/indigo.h:355-388): string x string, two semi-global rounds and one global
+    pris = [trimmed_seq(out[i]["primary"], trim_left, trim_right) for i in live]
+    secs = [trimmed_seq(out[i]["secDecompose"], trim_left, trim_right) for i in live]
+    refl = [out[i]["refslice"] for i in live]
+    _, o1, l1 = ctx.gotoh(SS, pris + secs, refl + refl, sc, _SEMIGLOBAL)
+    sl = []
+    for k in range(2 * len(live)):
+        i = live[k % len(live)]
+        r0, r1 = _gap_rows(o1[k, : l1[k]])
+        sl.append(trim_reference_slice(r0, r1, refl[k % len(live)], out[i]["forward"], 0, trim_left, trim_right))
+    s2, o2, l2 = ctx.gotoh(SS, pris + secs, [x[0] for x in sl], sc, _SEMIGLOBAL)
+    s3, o3, l3 = ctx.gotoh(SS, pris, secs, sc, AlignConfig(False, False))
+    nl = len(live)
+    for k, i in enumerate(live):
+        for name, kk, q in (("align1", k, pris[k]), ("align2", nl + k, secs[k])):
+            rows = rows_from_ops(SS, q, sl[kk][0], bytes(o2[kk, : l2[kk]]))
+            out[i][name] = dict(score=int(s2[kk]), row0=rows[0], row1=rows[1], refslice=sl[kk][0], pos=sl[kk][1])
+        rows = rows_from_ops(SS, pris[k], secs[k], bytes(o3[k, : l3[k]]))
+        out[i]["align3"] = dict(score=int(s3[k]), row0=rows[0], row1=rows[1], refslice=secs[k], pos=0)
     return out
 
 

@@ -19,6 +19,8 @@
 // Recurrences and tie-breaks: src/gotoh.h:103-138 literally (see gotoh_general.cu).
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tb {
@@ -509,16 +511,20 @@ gotoh_packed_kernel(const GotohBatch B) {
         return cc <= n ? top[cc] : pk_dpx(kPkNeg, bias);
       };
       auto feed_cls = [&](int cc) -> unsigned { return cc <= n ? (unsigned)base_class(b[cc - 1]) : 0u; };
-      unsigned tchunk = feed_sv(1 + lane), cchunk = feed_cls(1 + lane);
-      unsigned tnext = feed_sv(33 + lane), cnext = feed_cls(33 + lane);
+      // chunk q of the boundary row covers columns 32q+1.., chunk q of the classes covers columns 32q+2.. (the class a step
+      // fetches is the one of its NEXT column), so both chunks roll over together after every 32nd step
+      unsigned tchunk = feed_sv(1 + lane), cchunk = feed_cls(2 + lane);
+      unsigned tnext = feed_sv(33 + lane), cnext = feed_cls(34 + lane);
       // column classes of this lane for the coming step (lo | hi << 8); columns outside 1..n use class 0 (never read back)
-      unsigned cur = 0;
-      { const unsigned f0 = __shfl_sync(kFull, cchunk, 0); if (lane == 0) cur = f0; }
+      unsigned cur = lane == 0 ? feed_cls(1) : 0u;
       const int cap_st = lane == m_lane ? n - 1 + lane + 32 * m_half : -1;
       uint4* pw = FLAGS ? ptr + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
       uint2* prow = CKPT ? rowck + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
 
-      for (int st = 0; st < T; ++st, pw += 32, prow += 32) {
+      // One step of the systolic array. EDGE = true adds the rare per-lane events (a half-band's first column, the cell
+      // S[m][n] passing through); the chunk loop below only uses that variant for the chunks in which they can occur.
+      auto do_step = [&](const int st, auto edge_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
         // substitution scores of this step's columns (issued first: shared-memory latency hides under the shuffles)
         const uint4* const pa = reinterpret_cast<const uint4*>(tabA + (cur & 0xffu) * 512) + lane;
         const uint4* const pb = reinterpret_cast<const uint4*>(tabB + (cur >> 8) * 512) + lane;
@@ -530,14 +536,13 @@ gotoh_packed_kernel(const GotohBatch B) {
         unsigned us = __byte_perm(fsv, __shfl_sync(kFull, bs, src), sel_us);    // lane 0: lo = top row S, hi = lane 31's half-band-A bottom S
         unsigned uv = __byte_perm(fsv, __shfl_sync(kFull, bv, src), sel_uv);
         // classes for the next step: rotate, lane 0 takes the next column from the feed
-        if ((st & 31) == 31) { tchunk = tnext; cchunk = cnext; tnext = feed_sv(st + 34 + lane); cnext = feed_cls(st + 34 + lane); }
-        cur = __byte_perm(__shfl_sync(kFull, cchunk, (st + 1) & 31), __shfl_sync(kFull, cur, src), sel_cl);
+        cur = __byte_perm(__shfl_sync(kFull, cchunk, st & 31), __shfl_sync(kFull, cur, src), sel_cl);
 
         const int c_lo = st - lane + 1, c_hi = c_lo - 32;
         {
           // Every lane runs every step (no divergent guard): before a half-band's first column and after its last one the
           // lane computes cells nobody reads; the state a half-band starts from is installed when its column 1 arrives.
-          if (c_lo == 1 || c_lo == 33) {
+          if (EDGE && (c_lo == 1 || c_lo == 33)) {
             const unsigned keep = c_lo == 1 ? 0xffff0000u : 0x0000ffffu;
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) {
@@ -595,21 +600,28 @@ gotoh_packed_kernel(const GotohBatch B) {
             w.z = __byte_perm(acc[4], acc[5], 0x6240); w.w = __byte_perm(acc[6], acc[7], 0x6240);
             *pw = w;
           }
-          if (CKPT) {
-            *prow = make_uint2(bs, bv);                                       // bottom row (S, V) of both half-band blocks at this step
-            if ((st & 31) == 31) {                                            // the lane's 16 rows (S, H) every 32 columns
-              uint4* pc = colck + (((unsigned long long)pass * (unsigned)NQ + (unsigned)(st >> 5)) * 8ull) * 32ull + (unsigned)lane;
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                pc[k4 * 32] = make_uint4(sl[4 * k4], sl[4 * k4 + 1], sl[4 * k4 + 2], sl[4 * k4 + 3]);
-                pc[(4 + k4) * 32] = make_uint4(hh[4 * k4], hh[4 * k4 + 1], hh[4 * k4 + 2], hh[4 * k4 + 3]);
-              }
-            }
-          }
+          if (CKPT) *prow = make_uint2(bs, bv);                               // bottom row (S, V) of both half-band blocks at this step
           if (more) { if (lane == 31 && c_hi >= 1 && c_hi <= n) bot[c_hi] = __byte_perm(bs, bv, 0x7632); }   // S | V << 16 of row base+1024
-          else if (st == cap_st) {                                            // S[m][n] passes through this lane now
+          else if (EDGE && st == cap_st) {                                    // S[m][n] passes through this lane now
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) if (i == m_i) score_word = sl[i];
+          }
+        }
+        pw += 32; prow += 32;
+      };
+
+      for (int st0 = 0; st0 < T; st0 += 32) {
+        const int st1 = min(T, st0 + 32);
+        if (st0 < 64 || st1 >= n) { for (int st = st0; st < st1; ++st) do_step(st, std::true_type()); }
+        else { for (int st = st0; st < st1; ++st) do_step(st, std::false_type()); }
+        // roll the feed chunks over; checkpoint the lane's 16 rows (S, H) every 32 columns
+        tchunk = tnext; cchunk = cnext; tnext = feed_sv(st0 + 65 + lane); cnext = feed_cls(st0 + 66 + lane);
+        if (CKPT && st1 == st0 + 32) {
+          uint4* pc = colck + (((unsigned long long)pass * (unsigned)NQ + (unsigned)(st0 >> 5)) * 8ull) * 32ull + (unsigned)lane;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            pc[k4 * 32] = make_uint4(sl[4 * k4], sl[4 * k4 + 1], sl[4 * k4 + 2], sl[4 * k4 + 3]);
+            pc[(4 + k4) * 32] = make_uint4(hh[4 * k4], hh[4 * k4 + 1], hh[4 * k4 + 2], hh[4 * k4 + 3]);
           }
         }
       }

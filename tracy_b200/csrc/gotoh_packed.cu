@@ -420,8 +420,10 @@ gotoh_packed_kernel(const GotohBatch B) {
   constexpr bool vfree = VFREE;
   const int src = (lane + 31) & 31;
   // lane 0 splices the feed into the rotated words, every other lane takes the rotated word as is: one PRMT either way
-  const unsigned sel_us = lane == 0 ? 0x5410u : 0x7654u, sel_uv = lane == 0 ? 0x5432u : 0x7654u, sel_cl = lane == 0 ? 0x3340u : 0x7654u;
+  const unsigned sel_us = lane == 0 ? 0x5410u : 0x7654u, sel_uv = lane == 0 ? 0x5432u : 0x7654u, sel_cl = lane == 0 ? 0x5410u : 0x7654u;
 
+  const char* const tabA_lane = reinterpret_cast<const char*>(tabA) + lane * 16;
+  const char* const tabB_lane = reinterpret_cast<const char*>(tabB) + lane * 16;
   uint4* const ptr = TRACEBACK ? reinterpret_cast<uint4*>(B.ptr_scratch + (unsigned long long)slot * B.ptr_slot_words) : nullptr;
   unsigned* const rowbuf0 = reinterpret_cast<unsigned*>(B.rowbuf + (unsigned long long)slot * B.rowbuf_slot);
   uint8_t* const ops_rev = TRACEBACK ? B.ops_scratch + (unsigned long long)slot * B.ops_slot : nullptr;
@@ -510,12 +512,13 @@ gotoh_packed_kernel(const GotohBatch B) {
         if (pass == 0) return pk_dpx(kPkNeg, (hfree ? 0 : go + cc * ge) + bias);                   // src/gotoh.h:113-118
         return cc <= n ? top[cc] : pk_dpx(kPkNeg, bias);
       };
-      auto feed_cls = [&](int cc) -> unsigned { return cc <= n ? (unsigned)base_class(b[cc - 1]) : 0u; };
+      auto feed_cls = [&](int cc) -> unsigned { return cc <= n ? (unsigned)base_class(b[cc - 1]) << 11 : 0u; };   // byte offset of the class's 2 KB table block
       // chunk q of the boundary row covers columns 32q+1.., chunk q of the classes covers columns 32q+2.. (the class a step
       // fetches is the one of its NEXT column), so both chunks roll over together after every 32nd step
       unsigned tchunk = feed_sv(1 + lane), cchunk = feed_cls(2 + lane);
       unsigned tnext = feed_sv(33 + lane), cnext = feed_cls(34 + lane);
-      // column classes of this lane for the coming step (lo | hi << 8); columns outside 1..n use class 0 (never read back)
+      // table offsets of this lane's two column classes for the coming step (lo16: half-band A, hi16: half-band B);
+      // columns outside 1..n use class 0 (never read back)
       unsigned cur = lane == 0 ? feed_cls(1) : 0u;
       const int cap_st = lane == m_lane ? n - 1 + lane + 32 * m_half : -1;
       uint4* pw = FLAGS ? ptr + (unsigned long long)pass * (unsigned)T * 32ull + (unsigned)lane : nullptr;
@@ -523,11 +526,11 @@ gotoh_packed_kernel(const GotohBatch B) {
 
       // One step of the systolic array. EDGE = true adds the rare per-lane events (a half-band's first column, the cell
       // S[m][n] passing through); the chunk loop below only uses that variant for the chunks in which they can occur.
-      auto do_step = [&](const int st, auto edge_tag) {
-        constexpr bool EDGE = decltype(edge_tag)::value;
+      auto do_step = [&](const int st, auto edge_tag, auto more_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value, MORE = decltype(more_tag)::value;
         // substitution scores of this step's columns (issued first: shared-memory latency hides under the shuffles)
-        const uint4* const pa = reinterpret_cast<const uint4*>(tabA + (cur & 0xffu) * 512) + lane;
-        const uint4* const pb = reinterpret_cast<const uint4*>(tabB + (cur >> 8) * 512) + lane;
+        const uint4* const pa = reinterpret_cast<const uint4*>(tabA_lane + (cur & 0xffffu));
+        const uint4* const pb = reinterpret_cast<const uint4*>(tabB_lane + (cur >> 16));
         uint4 xa[4], xb[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { xa[j] = pa[j * 32]; xb[j] = pb[j * 32]; }
@@ -601,7 +604,7 @@ gotoh_packed_kernel(const GotohBatch B) {
             *pw = w;
           }
           if (CKPT) *prow = make_uint2(bs, bv);                               // bottom row (S, V) of both half-band blocks at this step
-          if (more) { if (lane == 31 && c_hi >= 1 && c_hi <= n) bot[c_hi] = __byte_perm(bs, bv, 0x7632); }   // S | V << 16 of row base+1024
+          if (MORE) { if (lane == 31 && c_hi >= 1 && c_hi <= n) bot[c_hi] = __byte_perm(bs, bv, 0x7632); }   // S | V << 16 of row base+1024
           else if (EDGE && st == cap_st) {                                    // S[m][n] passes through this lane now
 #pragma unroll
             for (int i = 0; i < kRowsPerLane; ++i) if (i == m_i) score_word = sl[i];
@@ -612,8 +615,14 @@ gotoh_packed_kernel(const GotohBatch B) {
 
       for (int st0 = 0; st0 < T; st0 += 32) {
         const int st1 = min(T, st0 + 32);
-        if (st0 < 64 || st1 >= n) { for (int st = st0; st < st1; ++st) do_step(st, std::true_type()); }
-        else { for (int st = st0; st < st1; ++st) do_step(st, std::false_type()); }
+        if (more) {                       // not the last pass of a tall pair: every step also hands its bottom row to the next pass
+          for (int st = st0; st < st1; ++st) do_step(st, std::true_type(), std::true_type());
+        } else if (st0 < 64 || st1 >= n) {
+          for (int st = st0; st < st1; ++st) do_step(st, std::true_type(), std::false_type());
+        } else {
+#pragma unroll 2
+          for (int st = st0; st < st1; ++st) do_step(st, std::false_type(), std::false_type());
+        }
         // roll the feed chunks over; checkpoint the lane's 16 rows (S, H) every 32 columns
         tchunk = tnext; cchunk = cnext; tnext = feed_sv(st0 + 65 + lane); cnext = feed_cls(st0 + 66 + lane);
         if (CKPT && st1 == st0 + 32) {

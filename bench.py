@@ -305,7 +305,8 @@ def run_b200(args, rank, world, local_rank):
             "packed_pairs_last_step": ctx.last_packed_pairs()}
     out = {
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16x2",            # biased unsigned 16-bit DP cells, two per 32-bit register (int32 in the general kernel)
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": world * (se1["h2d_bytes"] - se0["h2d_bytes"]) // args.steps,      # every rank moves the same amount

@@ -165,6 +165,20 @@ typedef struct {
 } tb_profile_batch;
 int tb_create_profile(tb_ctx* ctx, const tb_profile_batch* batch, float* out_base, const int64_t* out_off, int32_t* out_len);
 
+/* basecall(Trace, BaseCalls, sigratio), reference src/abif.h:408-511 (peak(): :77-97), for a batch of traces (GPU).
+ * trace item t: int32 samples [4][nsamples]; ploc item t: the trace file's basecall positions (Trace::basecallpos).
+ * Outputs per trace at element offset out_off[t] (capacity ploc.len[t] each): BaseCalls::bcPos, primary, secondary,
+ * consensus; positions with an empty peak window are dropped as in the reference, the count goes to out_len[t].
+ * estimateQualities() is not part of this call. `mem` applies to every pointer incl. the outputs. */
+typedef struct {
+  tb_arena trace;
+  tb_arena ploc;
+  size_t ntraces;
+  int32_t mem;
+} tb_basecall_batch;
+int tb_basecall(tb_ctx* ctx, const tb_basecall_batch* batch, float sigratio, int32_t* bcpos_out, char* primary_out, char* secondary_out,
+                char* consensus_out, const int64_t* out_off, int32_t* out_len);
+
 /* reverseComplementProfile(p, out), reference src/profile.h:74-90, for a batch of float[6][len] profiles (GPU).
  * `in` and the outputs live in `mem`; output item i goes to out_base + out_off[i] (6 * len[i] floats). */
 int tb_revcomp_profile(tb_ctx* ctx, const tb_arena* in, size_t n, int32_t mem, float* out_base, const int64_t* out_off);

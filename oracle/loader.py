@@ -146,6 +146,8 @@ class _Ref:
         L.ref_bench_gotoh_ps.argtypes = [_f32p, C.c_char_p, C.c_int, C.c_int, C.c_int] + _SC + [C.c_int, _i32p]
         L.ref_bench_gotoh_ps.restype = C.c_longlong
         L.ref_reverse_complement.argtypes = [C.c_char_p, C.c_int]
+        L.ref_basecall.argtypes = [_i32p, C.c_int, _i32p, C.c_int, C.c_float, _i32p, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.ref_basecall.restype = C.c_int
         L.ref_find_homozygous_breakpoint.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         L.ref_find_homozygous_breakpoint.restype = C.c_int
         L.ref_generate_secondary_decomposed.argtypes = [_i32p, C.c_int, _i32p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p]
@@ -159,6 +161,14 @@ class _Ref:
         L.ref_msa.argtypes = [_f32p, _i64p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int,
                               np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), _i32p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ref_msa.restype = C.c_int
+
+    def basecall(self, acgt, ploc, sigratio=0.33):
+        acgt = np.ascontiguousarray(acgt, np.int32); ploc = np.ascontiguousarray(ploc, np.int32)
+        n = len(ploc)
+        pos = np.zeros(max(n, 1), np.int32)
+        p, s, c = (C.create_string_buffer(n + 1) for _ in range(3))
+        k = self.lib.ref_basecall(acgt.reshape(-1), acgt.shape[1], ploc, n, sigratio, pos, p, s, c)
+        return dict(bcPos=pos[:k].copy(), primary=p.raw[:k], secondary=s.raw[:k], consensus=c.raw[:k])
 
     def find_homozygous_breakpoint(self, row0, row1):
         a, b, c, d = C.c_int(), C.c_int(), C.c_uint32(), C.c_float()

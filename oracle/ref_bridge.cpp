@@ -186,6 +186,19 @@ int ref_trim_reference_slice(const char* row0, const char* row1, int L, const ch
   return n;
 }
 
+// basecall(Trace, BaseCalls, sigratio) (src/abif.h:408-511): outputs have capacity nploc; returns the number of basecalls.
+int ref_basecall(const int32_t* acgt, int nsamples, const int32_t* ploc, int nploc, float sigratio, int32_t* bcpos, char* primary,
+                 char* secondary, char* consensus) {
+  tracy::Trace tr; tracy::BaseCalls bc;
+  tr.traceACGT.resize(4);
+  for (int k = 0; k < 4; ++k) tr.traceACGT[k].assign(acgt + (size_t)k * nsamples, acgt + (size_t)(k + 1) * nsamples);
+  tr.basecallpos.assign(ploc, ploc + nploc);
+  tracy::basecall(tr, bc, sigratio);
+  const int n = (int)bc.bcPos.size();
+  for (int i = 0; i < n; ++i) { bcpos[i] = bc.bcPos[i]; primary[i] = bc.primary[i]; secondary[i] = bc.secondary[i]; consensus[i] = bc.consensus[i]; }
+  return n;
+}
+
 // findHomozygousBreakpoint (src/decompose.h:59-128): returns 0 when the reference function returns false.
 int ref_find_homozygous_breakpoint(const char* row0, const char* row1, int L, int* indelshift, int* traceleft, uint32_t* breakpoint, float* bestDiff) {
   TAlign al(boost::extents[2][L]);

@@ -138,3 +138,23 @@ def test_assemble_denovo_recovers_contig(ctx):
     cons = r["consensus"]
     assert len(cons) >= 650
     assert cons in contig or drivers.reverse_complement_seq(cons) in contig
+
+
+def test_basecall_golden(ctx):
+    """tb_basecall (device basecall(), reference src/abif.h:408-511) against the reference's calls on synthetic
+    chromatograms: positions, primary / secondary / consensus strings, dropped empty windows; then straight into
+    tb_create_profile."""
+    Gb = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "basecall_golden.npz"))
+    n = int(Gb["n"])
+    by_ratio = {}
+    for i in range(n):
+        by_ratio.setdefault(float(Gb[f"ratio{i}"]), []).append(i)
+    for ratio, idx in by_ratio.items():
+        res = ctx.basecall([Gb[f"tr{i}"] for i in idx], [Gb[f"ploc{i}"] for i in idx], ratio)
+        for i, r in zip(idx, res):
+            assert np.array_equal(r["bcPos"], Gb[f"pos{i}"]), i
+            for k in ("primary", "secondary", "consensus"):
+                assert r[k] == bytes(Gb[f"{k}{i}"]), (i, k)
+        profs = ctx.create_profile([Gb[f"tr{i}"] for i in idx], [r["bcPos"] for r in res], [r["primary"] for r in res], [r["secondary"] for r in res])
+        for p, r in zip(profs, res):
+            assert p.shape == (6, len(r["bcPos"])) and np.isfinite(p).all()

@@ -247,6 +247,31 @@ class Context:
         self._check(self._lib.tb_create_profile(self._h, C.byref(b), _ptr(out), _ptr(ooff), _ptr(olen)))
         return [out[ooff[i]: ooff[i] + 6 * olen[i]].reshape(6, olen[i]).copy() for i in range(n)]
 
+    def basecall(self, traces, ploc, sigratio=0.33):
+        """basecall(Trace, BaseCalls, sigratio) for a batch (reference src/abif.h:408-511). traces: list of int32[4][nsamples];
+        ploc: the trace files' basecall positions (Trace::basecallpos). Returns a list of dicts bcPos / primary / secondary /
+        consensus (estimateQualities is not part of the device path)."""
+        n = len(traces)
+        tr = [np.ascontiguousarray(t, np.int32) for t in traces]
+        pl = [np.ascontiguousarray(p, np.int32) for p in ploc]
+        tlen = np.array([t.shape[1] for t in tr], np.int32)
+        toff = np.concatenate([[0], np.cumsum(4 * tlen.astype(np.int64))[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        tbase = np.concatenate([t.reshape(-1) for t in tr]) if n else np.zeros(1, np.int32)
+        plen = np.array([len(p) for p in pl], np.int32)
+        poff = np.concatenate([[0], np.cumsum(plen.astype(np.int64))[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        pbase = np.concatenate(pl) if n and plen.sum() else np.zeros(1, np.int32)
+        tot = max(int(plen.astype(np.int64).sum()), 1)
+        o_pos = np.zeros(tot, np.int32)
+        o_pri, o_sec, o_con = (np.zeros(tot, np.uint8) for _ in range(3))
+        o_len = np.zeros(max(n, 1), np.int32)
+        b = capi.BasecallBatch(capi.Arena(_ptr(tbase), _ptr(toff), _ptr(tlen)), capi.Arena(_ptr(pbase), _ptr(poff), _ptr(plen)), n, capi.TB_MEM_HOST)
+        self._check(self._lib.tb_basecall(self._h, C.byref(b), float(sigratio), _ptr(o_pos), _ptr(o_pri), _ptr(o_sec), _ptr(o_con), _ptr(poff), _ptr(o_len)))
+        out = []
+        for i in range(n):
+            sl = slice(int(poff[i]), int(poff[i]) + int(o_len[i]))
+            out.append(dict(bcPos=o_pos[sl].copy(), primary=o_pri[sl].tobytes(), secondary=o_sec[sl].tobytes(), consensus=o_con[sl].tobytes()))
+        return out
+
     def revcomp_profile(self, profiles):
         """reverseComplementProfile for a batch of float[6][len] profiles (reference src/profile.h:74-90)."""
         a = profiles if isinstance(profiles, Arena) else pack_profiles(profiles)

@@ -14,7 +14,7 @@ SYMBOLS = [
     "tb_ctx_create", "tb_ctx_destroy", "tb_strerror", "tb_last_error", "tb_host_alloc", "tb_host_free",
     "tb_ctx_set_scratch_limit", "tb_ctx_stats", "tb_ctx_last_kernel_ms", "tb_ctx_last_call_ms", "tb_ctx_last_packed_pairs", "tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss",
     "tb_rows_from_ops", "tb_decompose_sweep", "tb_version", "tb_create_profile", "tb_revcomp_profile", "tb_trim_reference_slice",
-    "tb_find_breakpoint",
+    "tb_find_breakpoint", "tb_basecall",
 ]
 
 
@@ -51,6 +51,10 @@ class SweepResult(C.Structure):
 class ProfileBatch(C.Structure):
     _fields_ = [("trace", Arena), ("bcpos", Arena), ("primary_base", C.c_void_p), ("secondary_base", C.c_void_p),
                 ("trim_left", C.c_void_p), ("trim_right", C.c_void_p), ("ntraces", C.c_size_t), ("mem", C.c_int32)]
+
+
+class BasecallBatch(C.Structure):
+    _fields_ = [("trace", Arena), ("ploc", Arena), ("ntraces", C.c_size_t), ("mem", C.c_int32)]
 
 
 class LibraryMissing(RuntimeError):
@@ -90,6 +94,7 @@ def lib():
     L.tb_decompose_sweep.argtypes = [vp, C.POINTER(SweepBatch), C.POINTER(SweepResult)]
     L.tb_version.restype = C.c_char_p
     L.tb_create_profile.argtypes = [vp, C.POINTER(ProfileBatch), vp, vp, vp]
+    L.tb_basecall.argtypes = [vp, C.POINTER(BasecallBatch), C.c_float, vp, vp, vp, vp, vp, vp]
     L.tb_revcomp_profile.argtypes = [vp, C.POINTER(Arena), C.c_size_t, C.c_int32, vp, vp]
     L.tb_trim_reference_slice.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.c_int32,
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]

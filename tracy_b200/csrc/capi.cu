@@ -26,6 +26,7 @@ unsigned long long gotoh_packed_ptr_words(int m, int n);
 
 cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
 cudaError_t launch_create_profile(const ProfileBatch& P, int ntraces, cudaStream_t stream);
+cudaError_t launch_basecall(const BasecallBatch& P, int ntraces, cudaStream_t stream);
 cudaError_t launch_revcomp_profile(const float* in_base, const int64_t* in_off, const int32_t* len, float* out_base, const int64_t* out_off,
                                    int n, cudaStream_t stream);
 }  // namespace tb
@@ -675,6 +676,70 @@ int tb_create_profile(tb_ctx* ctx, const tb_profile_batch* b, float* out_base, c
     for (size_t i = 0; i < nt; ++i)
       TB_CUDA(ctx, cudaMemcpyAsync(out_base + out_off[i], (const float*)d_out + out_off[i], (size_t)6 * out_len[i] * 4, cudaMemcpyDeviceToHost, st));
     ctx->d2h += (size_t)omax * 4 + nt * 4;
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return TB_OK;
+}
+
+int tb_basecall(tb_ctx* ctx, const tb_basecall_batch* b, float sigratio, int32_t* bcpos_out, char* primary_out, char* secondary_out,
+                char* consensus_out, const int64_t* out_off, int32_t* out_len) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (!b || !bcpos_out || !primary_out || !secondary_out || !consensus_out || !out_off || !out_len) return fail(ctx, TB_ERR_INVALID, "null batch/output");
+  const size_t nt = b->ntraces;
+  if (nt == 0) return TB_OK;
+  if (nt > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "ntraces too large");
+  if (!b->trace.base || !b->trace.off || !b->trace.len || !b->ploc.base || !b->ploc.off || !b->ploc.len) return fail(ctx, TB_ERR_INVALID, "null arena pointer");
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->lanes[0].stream;
+  tb::BasecallBatch P{};
+  P.sigratio = sigratio;
+  if (b->mem == TB_MEM_DEVICE) {
+    P.trace_base = (const int32_t*)b->trace.base; P.trace_off = b->trace.off; P.trace_len = b->trace.len;
+    P.ploc_base = (const int32_t*)b->ploc.base; P.ploc_off = b->ploc.off; P.ploc_len = b->ploc.len;
+    P.bcpos_out = bcpos_out; P.pri_out = primary_out; P.sec_out = secondary_out; P.con_out = consensus_out; P.out_off = out_off; P.out_len = out_len;
+    TB_CUDA(ctx, tb::launch_basecall(P, (int)nt, st));
+    ctx->launches++;
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    return TB_OK;
+  }
+  if (b->mem != TB_MEM_HOST) return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST or TB_MEM_DEVICE");
+  long long tmax = 0, pmax = 0, omax = 0;
+  for (size_t i = 0; i < nt; ++i) {
+    if (b->trace.len[i] < 2 || b->ploc.len[i] < 0 || b->trace.off[i] < 0 || b->ploc.off[i] < 0 || out_off[i] < 0)
+      return fail(ctx, TB_ERR_INVALID, "negative offset/length (a trace needs at least 2 samples)");
+    for (int32_t j = 0; j < b->ploc.len[i]; ++j) {
+      const int32_t v = ((const int32_t*)b->ploc.base)[b->ploc.off[i] + j];
+      if (v < 0 || v >= b->trace.len[i]) return fail(ctx, TB_ERR_INVALID, "basecall position outside the trace");
+    }
+    tmax = std::max<long long>(tmax, b->trace.off[i] + 4ll * b->trace.len[i]);
+    pmax = std::max<long long>(pmax, b->ploc.off[i] + b->ploc.len[i]);
+    omax = std::max<long long>(omax, out_off[i] + b->ploc.len[i]);
+  }
+  {
+    Staged S(st);
+    void *d_tr, *d_pl, *d_toff, *d_tlen, *d_poff, *d_plen, *d_ooff, *d_olen, *d_pos, *d_pri, *d_sec, *d_con;
+    TB_CUDA(ctx, S.up(&d_tr, b->trace.base, (size_t)tmax * 4)); TB_CUDA(ctx, S.up(&d_pl, b->ploc.base, (size_t)pmax * 4));
+    TB_CUDA(ctx, S.up(&d_toff, b->trace.off, nt * 8)); TB_CUDA(ctx, S.up(&d_tlen, b->trace.len, nt * 4));
+    TB_CUDA(ctx, S.up(&d_poff, b->ploc.off, nt * 8)); TB_CUDA(ctx, S.up(&d_plen, b->ploc.len, nt * 4));
+    TB_CUDA(ctx, S.up(&d_ooff, out_off, nt * 8));
+    TB_CUDA(ctx, S.alloc(&d_olen, nt * 4)); TB_CUDA(ctx, S.alloc(&d_pos, (size_t)omax * 4));
+    TB_CUDA(ctx, S.alloc(&d_pri, (size_t)omax)); TB_CUDA(ctx, S.alloc(&d_sec, (size_t)omax)); TB_CUDA(ctx, S.alloc(&d_con, (size_t)omax));
+    P.trace_base = (const int32_t*)d_tr; P.trace_off = (const int64_t*)d_toff; P.trace_len = (const int32_t*)d_tlen;
+    P.ploc_base = (const int32_t*)d_pl; P.ploc_off = (const int64_t*)d_poff; P.ploc_len = (const int32_t*)d_plen;
+    P.bcpos_out = (int32_t*)d_pos; P.pri_out = (char*)d_pri; P.sec_out = (char*)d_sec; P.con_out = (char*)d_con;
+    P.out_off = (const int64_t*)d_ooff; P.out_len = (int32_t*)d_olen;
+    TB_CUDA(ctx, tb::launch_basecall(P, (int)nt, st));
+    ctx->launches++;
+    TB_CUDA(ctx, cudaMemcpyAsync(out_len, d_olen, nt * 4, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    for (size_t i = 0; i < nt; ++i) {
+      const size_t o = (size_t)out_off[i], c = (size_t)out_len[i];
+      TB_CUDA(ctx, cudaMemcpyAsync(bcpos_out + o, (const int32_t*)d_pos + o, c * 4, cudaMemcpyDeviceToHost, st));
+      TB_CUDA(ctx, cudaMemcpyAsync(primary_out + o, (const char*)d_pri + o, c, cudaMemcpyDeviceToHost, st));
+      TB_CUDA(ctx, cudaMemcpyAsync(secondary_out + o, (const char*)d_sec + o, c, cudaMemcpyDeviceToHost, st));
+      TB_CUDA(ctx, cudaMemcpyAsync(consensus_out + o, (const char*)d_con + o, c, cudaMemcpyDeviceToHost, st));
+    }
+    ctx->h2d += (size_t)tmax * 4 + (size_t)pmax * 4 + nt * 32; ctx->d2h += (size_t)omax * 7 + nt * 4;
     TB_CUDA(ctx, cudaStreamSynchronize(st));
   }
   return TB_OK;

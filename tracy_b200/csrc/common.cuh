@@ -54,6 +54,14 @@ struct ProfileBatch {
   float* out_base; const int64_t* out_off; int32_t* out_len;
 };
 
+// Device view of a basecall batch (profile_ops.cu).
+struct BasecallBatch {
+  const int32_t* trace_base; const int64_t* trace_off; const int32_t* trace_len;    // item = int32[4][nsamples]
+  const int32_t* ploc_base; const int64_t* ploc_off; const int32_t* ploc_len;       // Trace::basecallpos
+  int32_t* bcpos_out; char* pri_out; char* sec_out; char* con_out; const int64_t* out_off; int32_t* out_len;
+  float sigratio;
+};
+
 // reference src/align.h:121-136: A,C,G,T,N (case-insensitive) -> 0..4; '-' and everything else contribute
 // nothing to _score (row 5 is never read, src/align.h:113-114) -> class 5.
 __device__ __forceinline__ int base_class(unsigned char ch) {

@@ -61,14 +61,29 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+struct Plan {
+  bool use_packed = false;
+  int tbmode = 0;                          // packed kernel traceback mode: 0 none, 1 flags, 2 checkpoints (default)
+  int blocks_packed = 0, blocks_packed5 = 0, blocks_general = 0;   // packed: 4-class (ACGT) and 5-class (ACGTN) instantiations
+  unsigned slots = 0;                      // warp slots that own scratch
+  unsigned long long ptr_words = 0, rowbuf_elems = 0, ops_bytes = 0;
+};
+
 struct Lane {   // one in-flight chunk of a TB_MEM_HOST batch
   cudaStream_t stream = nullptr;
   cudaEvent_t c0 = nullptr, k0 = nullptr, k1 = nullptr, k2 = nullptr;   // c0: start of a device-mode call; k*: kernel brackets
-  DevBuf a, b, a_off, b_off, a_len, b_len, scores, ops, ops_len, status, counter;
+  cudaEvent_t h0 = nullptr, d1 = nullptr;                               // host-mode chunk: before its H2D, after its D2H (TRACY_B200_TRACE)
+  DevBuf a, b, meta_d, scores, ops, ops_len, status, counter;
   DevBuf ptr, rowbuf, opsrev;
   PinBuf meta, cnt;
   bool timed = false, timed2 = false;
+  cudaEvent_t kend = nullptr;        // the event after the last kernel enqueued for the lane's current call/chunk
+  tb::GotohBatch view{};             // what enqueue_gotoh launched on (finish_gotoh's stage 2 reuses it)
+  Plan plan; int mode = 0; bool traceback = false;
+  long chunk = -1;   // index of the host-mode chunk in flight on this lane (-1: none)
+  size_t p0 = 0;     // its first pair
 };
+constexpr int kLanes = 4;   // lanes that exist; a TB_MEM_HOST batch keeps `nlanes` (default 3) chunks in flight: copying in, computing, copying out
 
 }  // namespace
 
@@ -77,7 +92,8 @@ struct tb_ctx {
   int sms = 0;
   size_t scratch_limit = 0;
   std::string err;
-  Lane lanes[2];
+  Lane lanes[kLanes];
+  cudaEvent_t t0 = nullptr;   // start of a host-mode call (timeline origin for TRACY_B200_TRACE)
   uint64_t launches = 0, h2d = 0, d2h = 0;
   float last_fast_ms = 0, last_general_ms = 0, last_sweep_ms = 0, last_call_ms = 0;
   uint64_t last_packed_pairs = 0;
@@ -121,13 +137,6 @@ void accumulate(Shape& s, const int32_t* l1, const int32_t* l2, size_t n, bool p
   }
 }
 
-struct Plan {
-  bool use_packed = false;
-  int tbmode = 0;                          // packed kernel traceback mode: 0 none, 1 flags, 2 checkpoints (default)
-  int blocks_packed = 0, blocks_packed5 = 0, blocks_general = 0;   // packed: 4-class (ACGT) and 5-class (ACGTN) instantiations
-  unsigned slots = 0;                      // warp slots that own scratch
-  unsigned long long ptr_words = 0, rowbuf_elems = 0, ops_bytes = 0;
-};
 
 // Size the persistent grids and the per-slot scratch for a launch over `npairs` pairs with maxima `sh`.
 int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npairs, tb_score sc, Plan* out) {
@@ -165,7 +174,7 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
     TB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
     limit = fr / 3;
   }
-  limit /= 2;   // two lanes may be in flight
+  limit /= 3;   // up to three lanes hold scratch at a time by default
   unsigned long long max_slots = per_slot ? std::max<unsigned long long>(limit / per_slot, 1) : (1ull << 30);
   warps_g = std::min(warps_g, max_slots);
   warps_p = std::min(warps_p, max_slots);
@@ -188,6 +197,11 @@ int reserve_scratch(tb_ctx* ctx, Lane& L, const Plan& p) {
 }
 
 // Enqueue the DP kernels for one device-resident batch view on lane L's stream.
+// Stage 1 is ONE kernel: the 4-class packed kernel when the batch is eligible for it (it completes every pair whose
+// window is pure ACGT and whose score range fits 16 bits), the general kernel otherwise. Whether stage 2 is needed --
+// the 5-class packed kernel and the general kernel over the pairs stage 1 left -- is read from the completion counter
+// after the stream has drained: persistent grids fill every SM, so empty follow-up launches on the same stream would
+// have to wait for the NEXT chunk's kernel (another lane) to retire and would serialise the lanes.
 int enqueue_gotoh(tb_ctx* ctx, Lane& L, int mode, bool traceback, tb::GotohBatch B, const Plan& p) {
   B.ptr_scratch = L.ptr.as<unsigned long long>(); B.ptr_slot_words = p.ptr_words;
   B.rowbuf = L.rowbuf.as<int2>(); B.rowbuf_slot = p.rowbuf_elems;
@@ -197,23 +211,53 @@ int enqueue_gotoh(tb_ctx* ctx, Lane& L, int mode, bool traceback, tb::GotohBatch
   TB_CUDA(ctx, cudaMemsetAsync(counters, 0, 64, L.stream));
   TB_CUDA(ctx, cudaMemsetAsync(B.status, 0, (size_t)B.npairs, L.stream));
   L.timed = L.timed2 = false;
-  TB_CUDA(ctx, cudaEventRecord(L.k0, L.stream));
   if (p.use_packed) {
-    B.counter = counters;           // [0] queue head, [1] pairs completed by the packed kernels
+    TB_CUDA(ctx, cudaEventRecord(L.k0, L.stream));
+    B.counter = counters;           // [0] queue head, [1] pairs completed by the packed kernel
     TB_CUDA(ctx, tb::launch_gotoh_packed(p.tbmode, 4, B, p.blocks_packed, L.stream));
-    B.counter = counters + 2;       // second queue head; its completion count lands in counters[3]
-    TB_CUDA(ctx, tb::launch_gotoh_packed(p.tbmode, 5, B, p.blocks_packed5, L.stream));
-    ctx->launches += 2;
+    TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
     L.timed = true;
+    L.kend = L.k1;
+  } else {
+    TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
+    B.counter = counters + 8;
+    TB_CUDA(ctx, tb::launch_gotoh_general(mode, traceback, B, p.blocks_general, L.stream));
+    TB_CUDA(ctx, cudaEventRecord(L.k2, L.stream));
+    L.timed2 = true;
+    L.kend = L.k2;
   }
-  TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
-  B.counter = counters + 8;
-  TB_CUDA(ctx, tb::launch_gotoh_general(mode, traceback, B, p.blocks_general, L.stream));
   ctx->launches++;
-  TB_CUDA(ctx, cudaEventRecord(L.k2, L.stream));
-  L.timed2 = true;
   TB_CUDA(ctx, L.cnt.reserve(64));
   TB_CUDA(ctx, cudaMemcpyAsync(L.cnt.p, counters, 64, cudaMemcpyDeviceToHost, L.stream));
+  L.view = B; L.plan = p; L.mode = mode; L.traceback = traceback;
+  return TB_OK;
+}
+
+int collect_timing(tb_ctx* ctx, Lane& L);
+
+// After the lane's stream has drained: run stage 2 when the packed kernel left pairs behind. *ran says whether it did
+// (the caller then repeats its D2H of the results).
+int finish_gotoh(tb_ctx* ctx, Lane& L, bool* ran) {
+  *ran = false;
+  if (!L.plan.use_packed || !L.timed) return TB_OK;
+  const unsigned int* cnt = static_cast<const unsigned int*>(L.cnt.p);
+  if (cnt[1] >= (unsigned)L.view.npairs) return TB_OK;
+  if (int rc = collect_timing(ctx, L)) return rc;          // stage 1's events are about to be re-recorded
+  unsigned int* counters = L.counter.as<unsigned int>();
+  tb::GotohBatch B = L.view;
+  TB_CUDA(ctx, cudaEventRecord(L.k0, L.stream));
+  B.counter = counters + 2;       // second queue head; its completion count lands in counters[3]
+  TB_CUDA(ctx, tb::launch_gotoh_packed(L.plan.tbmode, 5, B, L.plan.blocks_packed5, L.stream));
+  TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
+  B.counter = counters + 8;
+  TB_CUDA(ctx, tb::launch_gotoh_general(L.mode, L.traceback, B, L.plan.blocks_general, L.stream));
+  TB_CUDA(ctx, cudaEventRecord(L.k2, L.stream));
+  ctx->launches += 2;
+  L.timed = L.timed2 = true;
+  L.kend = L.k2;
+  TB_CUDA(ctx, cudaMemsetAsync(counters + 1, 0, 4, L.stream));   // stage 1's count is already in last_packed_pairs
+  TB_CUDA(ctx, cudaMemcpyAsync(L.cnt.p, counters, 64, cudaMemcpyDeviceToHost, L.stream));
+  *ran = true;
   return TB_OK;
 }
 
@@ -288,29 +332,77 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     B.status = L.status.as<uint8_t>(); B.npairs = (int)np;
     if (int rc = enqueue_gotoh(ctx, L, mode, traceback, B, plan)) return rc;
     TB_CUDA(ctx, cudaStreamSynchronize(L.stream));
-    TB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_call_ms, L.c0, L.k2));
+    bool again = false;
+    if (int rc = finish_gotoh(ctx, L, &again)) return rc;
+    if (again) TB_CUDA(ctx, cudaStreamSynchronize(L.stream));
+    TB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_call_ms, L.c0, L.kend));
     return collect_timing(ctx, L);
   }
 
-  // ---- TB_MEM_HOST: chunked, double-buffered H2D -> kernels -> D2H on two streams ----
+  // ---- TB_MEM_HOST: chunks pipelined over kLanes streams, each H2D -> kernels -> D2H ----
   Plan plan;
   if (int rc = make_plan(ctx, mode, traceback, all, np, sc, &plan)) return rc;
-  size_t chunk = std::max<size_t>(std::min<size_t>(np, 2 * (size_t)plan.slots), std::min<size_t>(16384, (np + 7) / 8));
-  {  // keep a chunk's staged inputs around <= 768 MiB
+  // A chunk is a whole number of waves of the persistent grid (pairs of one batch cost about the same, so a
+  // chunk then ends without a tail of idle warp slots), about an eighth of the batch, inputs <= 768 MiB.
+  const size_t wave = std::max<size_t>(plan.slots, 1);
+  size_t chunk = std::max<size_t>(2 * wave, std::min<size_t>(16384, (np + 7) / 8));
+  chunk = std::max<size_t>(1, chunk / wave) * wave;
+  {
     const double per_pair = (double)item_elems_a(mode, all.maxm) * elem_size_a(mode) + (double)item_elems_b(mode, all.maxn) * elem_size_b(mode) +
                             (traceback ? (double)res->ops_stride : 0.0);
     const size_t cap = (size_t)std::max(1.0, (768.0 * 1024 * 1024) / std::max(per_pair, 1.0));
-    chunk = std::max<size_t>(1, std::min(chunk, cap));
+    if (chunk > cap) chunk = cap >= wave ? cap / wave * wave : cap;
   }
-  if (const char* ce = getenv("TRACY_B200_CHUNK")) { const long v = atol(ce); if (v > 0) chunk = std::min<size_t>((size_t)v, np); }   // tuning knob
+  chunk = std::min(chunk, np);
+  bool ramp = chunk >= 4 * wave;   // the first chunks are 1, 2 and 4 waves so that the kernels start after a short first copy
+  if (const char* ce = getenv("TRACY_B200_CHUNK")) { const long v = atol(ce); if (v > 0) { chunk = std::min<size_t>((size_t)v, np); ramp = false; } }   // tuning knob
+  const bool trace = getenv("TRACY_B200_TRACE") != nullptr;   // per-chunk timeline on stderr (profiles/)
   const size_t esa = elem_size_a(mode), esb = elem_size_b(mode);
-  int rc_all = TB_OK;
-  size_t nchunks = (np + chunk - 1) / chunk;
-  for (size_t ci = 0; ci < nchunks && rc_all == TB_OK; ++ci) {
-    Lane& L = ctx->lanes[ci & 1];
-    TB_CUDA(ctx, cudaStreamSynchronize(L.stream));        // lane's previous chunk (ci-2) is done; its buffers are free
-    if (int rc = collect_timing(ctx, L)) return rc;
-    const size_t p0 = ci * chunk, cn = std::min(chunk, np - p0);
+  // Profile rows 5 ('-') never enter _score (k < 5, src/align.h:112-116): when the a1 items are equally long and
+  // back to back, copy rows 0..4 of each item only (one strided DMA), a sixth less H2D traffic.
+  bool a_rows5 = mode != tb::kModeSS && np > 1 && getenv("TRACY_B200_FULL_ROWS") == nullptr;
+  for (size_t i = 1; a_rows5 && i < np; ++i)
+    a_rows5 = l1[i] == l1[0] && batch->a1.off[i] == batch->a1.off[0] + (int64_t)i * 6 * l1[0];
+  if (a_rows5 && l1[0] == 0) a_rows5 = false;
+  int nlanes = 3;
+  if (const char* le = getenv("TRACY_B200_LANES")) nlanes = std::max(1, std::min(kLanes, atoi(le)));   // tuning knob
+  TB_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->lanes[0].stream));
+  for (int i = 0; i < kLanes; ++i) ctx->lanes[i].chunk = -1;
+  auto copy_out = [&](Lane& L, size_t p0, size_t cn) -> int {
+    TB_CUDA(ctx, cudaMemcpyAsync(res->scores + p0, L.scores.p, cn * 4, cudaMemcpyDeviceToHost, L.stream));
+    ctx->d2h += cn * 4;
+    if (traceback) {
+      TB_CUDA(ctx, cudaMemcpyAsync(res->ops + p0 * (size_t)res->ops_stride, L.ops.p, cn * (size_t)res->ops_stride, cudaMemcpyDeviceToHost, L.stream));
+      TB_CUDA(ctx, cudaMemcpyAsync(res->ops_len + p0, L.ops_len.p, cn * 4, cudaMemcpyDeviceToHost, L.stream));
+      ctx->d2h += cn * (size_t)res->ops_stride + cn * 4;
+    }
+    return TB_OK;
+  };
+  auto retire = [&](Lane& L) -> int {   // wait for the lane's chunk, fold its timing in
+    TB_CUDA(ctx, cudaStreamSynchronize(L.stream));
+    if (L.chunk >= 0) {
+      bool again = false;
+      if (int rc = finish_gotoh(ctx, L, &again)) return rc;
+      if (again) {                      // pairs the packed kernel left: stage 2 ran, fetch the results again
+        if (int rc = copy_out(L, L.p0, (size_t)L.view.npairs)) return rc;
+        if (trace) TB_CUDA(ctx, cudaEventRecord(L.d1, L.stream));
+        TB_CUDA(ctx, cudaStreamSynchronize(L.stream));
+      }
+    }
+    if (trace && L.chunk >= 0) {
+      float th0 = 0, tk0 = 0, tk2 = 0, td1 = 0;
+      cudaEventElapsedTime(&th0, ctx->t0, L.h0); cudaEventElapsedTime(&tk0, ctx->t0, L.timed ? L.k0 : L.k1);
+      cudaEventElapsedTime(&tk2, ctx->t0, L.kend); cudaEventElapsedTime(&td1, ctx->t0, L.d1);
+      fprintf(stderr, "tracy_b200 chunk %ld lane %d: h2d %.2f..%.2f kernels ..%.2f d2h ..%.2f ms\n", L.chunk, (int)(&L - ctx->lanes), th0, tk0, tk2, td1);
+    }
+    L.chunk = -1;
+    return collect_timing(ctx, L);
+  };
+  size_t nchunks = 0;
+  for (size_t ci = 0, p0 = 0; p0 < np; ++ci, ++nchunks) {
+    Lane& L = ctx->lanes[ci % nlanes];
+    if (int rc = retire(L)) return rc;                    // chunk ci-nlanes is done; its buffers are free
+    const size_t cn = std::min(ramp && ci < 3 ? (wave << ci) : chunk, np - p0);
     // extents of this chunk inside the caller's arenas
     long long amin = LLONG_MAX, amax = LLONG_MIN, bmin = LLONG_MAX, bmax = LLONG_MIN;
     for (size_t i = p0; i < p0 + cn; ++i) {
@@ -320,49 +412,51 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
       bmin = std::min(bmin, bo); bmax = std::max(bmax, bo + item_elems_b(mode, l2[i]));
     }
     const size_t abytes = (size_t)(amax - amin) * esa, bbytes = (size_t)(bmax - bmin) * esb;
-    Shape sh;
-    accumulate(sh, l1 + p0, l2 + p0, cn, mode == tb::kModePS);
-    Plan cp;
-    if (int rc = make_plan(ctx, mode, traceback, sh, cn, sc, &cp)) return rc;
+    Plan cp = plan;                                       // scratch per slot sized for the batch maxima, once
+    if (cn < (size_t)plan.slots)
+      if (int rc = make_plan(ctx, mode, traceback, all, cn, sc, &cp)) return rc;
     if (int rc = reserve_scratch(ctx, L, cp)) return rc;
     TB_CUDA(ctx, L.a.reserve(abytes + 16)); TB_CUDA(ctx, L.b.reserve(bbytes + 16));
-    TB_CUDA(ctx, L.a_off.reserve(cn * 8)); TB_CUDA(ctx, L.b_off.reserve(cn * 8));
-    TB_CUDA(ctx, L.a_len.reserve(cn * 4)); TB_CUDA(ctx, L.b_len.reserve(cn * 4));
     TB_CUDA(ctx, L.scores.reserve(cn * 4)); TB_CUDA(ctx, L.status.reserve(cn));
     if (traceback) { TB_CUDA(ctx, L.ops.reserve(cn * (size_t)res->ops_stride)); TB_CUDA(ctx, L.ops_len.reserve(cn * 4)); }
-    TB_CUDA(ctx, L.meta.reserve(cn * 16));
+    // offsets and lengths of the chunk go through ONE pinned block and one copy: [a_off | b_off | a_len | b_len]
+    TB_CUDA(ctx, L.meta.reserve(cn * 24)); TB_CUDA(ctx, L.meta_d.reserve(cn * 24));
     int64_t* hoff = static_cast<int64_t*>(L.meta.p);
+    int32_t* hlen = reinterpret_cast<int32_t*>(hoff + 2 * cn);
     for (size_t i = 0; i < cn; ++i) { hoff[i] = batch->a1.off[p0 + i] - amin; hoff[cn + i] = batch->a2.off[p0 + i] - bmin; }
+    std::memcpy(hlen, l1 + p0, cn * 4); std::memcpy(hlen + cn, l2 + p0, cn * 4);
 
-    TB_CUDA(ctx, cudaMemcpyAsync(L.a.p, (const char*)batch->a1.base + (size_t)amin * esa, abytes, cudaMemcpyHostToDevice, L.stream));
+    if (trace) TB_CUDA(ctx, cudaEventRecord(L.h0, L.stream));
+    if (a_rows5) {
+      const size_t pitch = (size_t)6 * l1[0] * 4, width = (size_t)5 * l1[0] * 4;
+      TB_CUDA(ctx, cudaMemcpy2DAsync(L.a.p, pitch, (const char*)batch->a1.base + (size_t)amin * esa, pitch, width, cn, cudaMemcpyHostToDevice, L.stream));
+      ctx->h2d += width * cn;
+    } else {
+      TB_CUDA(ctx, cudaMemcpyAsync(L.a.p, (const char*)batch->a1.base + (size_t)amin * esa, abytes, cudaMemcpyHostToDevice, L.stream));
+      ctx->h2d += abytes;
+    }
     TB_CUDA(ctx, cudaMemcpyAsync(L.b.p, (const char*)batch->a2.base + (size_t)bmin * esb, bbytes, cudaMemcpyHostToDevice, L.stream));
-    TB_CUDA(ctx, cudaMemcpyAsync(L.a_off.p, hoff, cn * 8, cudaMemcpyHostToDevice, L.stream));
-    TB_CUDA(ctx, cudaMemcpyAsync(L.b_off.p, hoff + cn, cn * 8, cudaMemcpyHostToDevice, L.stream));
-    TB_CUDA(ctx, cudaMemcpyAsync(L.a_len.p, l1 + p0, cn * 4, cudaMemcpyHostToDevice, L.stream));
-    TB_CUDA(ctx, cudaMemcpyAsync(L.b_len.p, l2 + p0, cn * 4, cudaMemcpyHostToDevice, L.stream));
-    ctx->h2d += abytes + bbytes + cn * 24;
+    TB_CUDA(ctx, cudaMemcpyAsync(L.meta_d.p, hoff, cn * 24, cudaMemcpyHostToDevice, L.stream));
+    ctx->h2d += bbytes + cn * 24;
 
     tb::GotohBatch C = B;
-    C.a_base = L.a.p; C.a_off = L.a_off.as<int64_t>(); C.a_len = L.a_len.as<int32_t>();
-    C.b_base = L.b.p; C.b_off = L.b_off.as<int64_t>(); C.b_len = L.b_len.as<int32_t>();
+    int64_t* doff = L.meta_d.as<int64_t>();
+    int32_t* dlen = reinterpret_cast<int32_t*>(doff + 2 * cn);
+    C.a_base = L.a.p; C.a_off = doff; C.a_len = dlen;
+    C.b_base = L.b.p; C.b_off = doff + cn; C.b_len = dlen + cn;
     C.scores = L.scores.as<int32_t>(); C.ops = traceback ? L.ops.as<uint8_t>() : nullptr;
     C.ops_stride = res->ops_stride; C.ops_len = traceback ? L.ops_len.as<int32_t>() : nullptr;
     C.status = L.status.as<uint8_t>(); C.npairs = (int)cn;
     if (int rc = enqueue_gotoh(ctx, L, mode, traceback, C, cp)) return rc;
+    L.chunk = (long)ci; L.p0 = p0;
 
-    TB_CUDA(ctx, cudaMemcpyAsync(res->scores + p0, L.scores.p, cn * 4, cudaMemcpyDeviceToHost, L.stream));
-    ctx->d2h += cn * 4;
-    if (traceback) {
-      TB_CUDA(ctx, cudaMemcpyAsync(res->ops + p0 * (size_t)res->ops_stride, L.ops.p, cn * (size_t)res->ops_stride, cudaMemcpyDeviceToHost, L.stream));
-      TB_CUDA(ctx, cudaMemcpyAsync(res->ops_len + p0, L.ops_len.p, cn * 4, cudaMemcpyDeviceToHost, L.stream));
-      ctx->d2h += cn * (size_t)res->ops_stride + cn * 4;
-    }
+    if (int rc = copy_out(L, p0, cn)) return rc;
+    if (trace) TB_CUDA(ctx, cudaEventRecord(L.d1, L.stream));
+    p0 += cn;
   }
-  for (int i = 0; i < 2; ++i) {
-    TB_CUDA(ctx, cudaStreamSynchronize(ctx->lanes[i].stream));
-    if (int rc = collect_timing(ctx, ctx->lanes[i])) return rc;
-  }
-  return rc_all;
+  for (size_t k = 0; k < (size_t)nlanes; ++k)            // retire in issue order
+    if (int rc = retire(ctx->lanes[(nchunks + k) % nlanes])) return rc;
+  return TB_OK;
 }
 
 char cons_char(const float* p, int len, int pos) {
@@ -408,10 +502,11 @@ int tb_ctx_create(tb_ctx** out, int device) {
   if (!c) return TB_ERR_NOMEM;
   c->device = device;
   c->sms = prop.multiProcessorCount;
-  for (int i = 0; i < 2; ++i) {
+  if (cudaEventCreate(&c->t0) != cudaSuccess) { cudaGetLastError(); delete c; return TB_ERR_CUDA; }
+  for (int i = 0; i < kLanes; ++i) {
     Lane& L = c->lanes[i];
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&L.c0) != cudaSuccess ||
-        cudaEventCreate(&L.k0) != cudaSuccess ||
+        cudaEventCreate(&L.k0) != cudaSuccess || cudaEventCreate(&L.h0) != cudaSuccess || cudaEventCreate(&L.d1) != cudaSuccess ||
         cudaEventCreate(&L.k1) != cudaSuccess || cudaEventCreate(&L.k2) != cudaSuccess) {
       cudaGetLastError();
       tb_ctx_destroy(c);
@@ -425,16 +520,19 @@ int tb_ctx_create(tb_ctx** out, int device) {
 void tb_ctx_destroy(tb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  for (int i = 0; i < 2; ++i) {
+  if (c->t0) cudaEventDestroy(c->t0);
+  for (int i = 0; i < kLanes; ++i) {
     Lane& L = c->lanes[i];
     if (L.stream) cudaStreamSynchronize(L.stream);
-    DevBuf* bufs[] = {&L.a, &L.b, &L.a_off, &L.b_off, &L.a_len, &L.b_len, &L.scores, &L.ops, &L.ops_len, &L.status, &L.counter, &L.ptr, &L.rowbuf, &L.opsrev};
+    DevBuf* bufs[] = {&L.a, &L.b, &L.meta_d, &L.scores, &L.ops, &L.ops_len, &L.status, &L.counter, &L.ptr, &L.rowbuf, &L.opsrev};
     for (DevBuf* b : bufs) b->release();
     L.meta.release(); L.cnt.release();
     if (L.c0) cudaEventDestroy(L.c0);
     if (L.k0) cudaEventDestroy(L.k0);
     if (L.k1) cudaEventDestroy(L.k1);
     if (L.k2) cudaEventDestroy(L.k2);
+    if (L.h0) cudaEventDestroy(L.h0);
+    if (L.d1) cudaEventDestroy(L.d1);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   delete c;

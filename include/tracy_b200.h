@@ -193,6 +193,44 @@ int tb_trim_reference_slice(const char* row0, const char* row1, int32_t L, int32
  * -> TraceBreakpoint {indelshift, traceleft, breakpoint, bestDiff}. */
 int tb_find_breakpoint(const float* profile, int32_t len, int32_t* indelshift, int32_t* traceleft, uint32_t* breakpoint, float* best_diff);
 
+/* ---- reference anchoring: scanSequence / findMaxFreq / getReferenceSlice, reference src/fmindex.h:173-326 ----------
+ * tracy anchors a trace by counting and locating every k-mer of its consensus in an FM-index (sdsl csa_wt) of the
+ * reference text. Only count() and locate() results enter the algorithm and both are functions of the text, so the index
+ * here is built for HBM: every text position keyed by its next 16 characters (4 bits each), radix-sorted, plus a
+ * directory over 12-mer prefixes -- 13 bytes per text character on the device.
+ * text: what tracy indexes -- the upper-cased sequence(s), a multi-sequence genome joined and ended by '\n' as
+ * `tracy index` dumps it (src/index.h:104-121), the one sequence of a FASTA reference (src/fmindex.h:160) or the
+ * wild-type trace's primary calls (:130). Bytes outside ACGTN / RYSWKMBDHV / '\n' -> TB_ERR_UNSUPPORTED.
+ * The device copy of the text (tb_index_info) can be used directly as the a2 arena base of tb_gotoh_ps. */
+typedef struct tb_index tb_index;
+int tb_index_build(tb_ctx* ctx, const char* text, int64_t text_len, int32_t mem, tb_index** out);
+int tb_index_destroy(tb_ctx* ctx, tb_index* idx);
+int tb_index_info(const tb_index* idx, int64_t* text_len, uint64_t* device_bytes, const char** device_text);
+
+/* c.trimLeft, c.trimRight, c.kmer (1..16), c.minKmerSupport (src/sage.h:41-43, :66-101) */
+typedef struct { int32_t trim_left, trim_right, kmer, min_kmer_support; } tb_anchor_config;
+/* Per trace: anchored = getReferenceSlice's return value; forward / kmersupport = rs.forward / rs.kmersupport; bestpos =
+ * `bestPos` in text coordinates (src/fmindex.h:257-284; 0 when not anchored). pass (optional, may be NULL): 1 = decided by
+ * the unique-k-mer pass, 4 = by the non-unique pass (src/fmindex.h:262-268), 0 = not anchored. */
+typedef struct {
+  uint8_t* anchored;
+  uint8_t* forward;
+  uint32_t* kmersupport;
+  int64_t* bestpos;
+  uint8_t* pass;
+} tb_anchor_result;
+/* consensus: arena of chars (BaseCalls::consensus per trace, each shorter than 65536). `mem` applies to the arena and
+ * to the result arrays. */
+int tb_anchor(tb_ctx* ctx, const tb_index* idx, const tb_arena* consensus, size_t ntraces, int32_t mem, tb_anchor_config cfg,
+              tb_anchor_result* res);
+/* Device time (CUDA events) of the unique-pass kernel of the most recent tb_anchor call. */
+int tb_ctx_last_anchor_ms(const tb_ctx* ctx, float* unique_ms);
+/* getReferenceSlice's slice arithmetic (src/fmindex.h:286-299, host): bestpos -> sequence index (seqlen[i] = sequence
+ * length + 1 for a '\n'-joined genome, src/fmindex.h:247; the plain length for a single FASTA / wild-type reference),
+ * position inside it, and the slice [slicestart, sliceend) = position -/+ maxindel (+ consensus length) clipped. */
+int tb_reference_slice(int64_t bestpos, const uint32_t* seqlen, int32_t nseq, int32_t conslen, int32_t maxindel,
+                       int32_t* refindex, uint32_t* chrpos, uint32_t* slicestart, uint32_t* sliceend);
+
 const char* tb_version(void);
 
 #ifdef __cplusplus

@@ -54,6 +54,31 @@ class _Port:
         L.orc_bench_gotoh_ps.argtypes = [_f32p, C.c_char_p, C.c_int, C.c_long, C.c_long] + _SC + [C.c_int, _i32p]
         L.orc_bench_gotoh_ps.restype = C.c_longlong
 
+        _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+        L.orc_scan_sequence.argtypes = [C.c_char_p, C.c_longlong, C.c_char_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, C.c_longlong,
+                                        C.POINTER(C.c_longlong), C.POINTER(C.c_uint)]
+        L.orc_scan_sequence.restype = C.c_longlong
+        L.orc_anchor.argtypes = [C.c_char_p, C.c_longlong, C.c_char_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, C.c_longlong,
+                                 C.POINTER(C.c_int), C.POINTER(C.c_uint), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+        L.orc_anchor.restype = C.c_int
+
+    def scan_sequence(self, text, cons, trim_left, trim_right, kmer, unique):
+        """scanSequence + findMaxFreq of one strand -> (sorted hits int64[], gpos, freq)."""
+        cap = max(1, len(cons)) * (1 if unique else 1000)
+        hits = np.zeros(cap, np.int64)
+        g, f = C.c_longlong(0), C.c_uint(0)
+        n = self.lib.orc_scan_sequence(bytes(text), len(text), bytes(cons), len(cons), trim_left, trim_right, kmer, int(unique), hits, cap, C.byref(g), C.byref(f))
+        return hits[:n].copy(), int(g.value), int(f.value)
+
+    def anchor(self, text, cons, trim_left, trim_right, kmer, min_support):
+        """getReferenceSlice's decision -> (anchored, forward, kmersupport, bestpos, pass)."""
+        cap = max(1, len(cons)) * 1000
+        scratch = np.zeros(cap, np.int64)
+        fw, ks, bp, ps = C.c_int(1), C.c_uint(0), C.c_longlong(0), C.c_int(0)
+        ok = self.lib.orc_anchor(bytes(text), len(text), bytes(cons), len(cons), trim_left, trim_right, kmer, min_support, scratch, cap,
+                                 C.byref(fw), C.byref(ks), C.byref(bp), C.byref(ps))
+        return bool(ok), bool(fw.value), int(ks.value), int(bp.value), int(ps.value)
+
     @staticmethod
     def _prof(p):
         p = np.ascontiguousarray(p, dtype=np.float32)
@@ -161,6 +186,51 @@ class _Ref:
         L.ref_msa.argtypes = [_f32p, _i64p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_int,
                               np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), _i32p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ref_msa.restype = C.c_int
+
+        L.ref_fm_build.argtypes = [C.c_char_p, C.c_longlong]
+        L.ref_fm_build.restype = C.c_void_p
+        L.ref_fm_free.argtypes = [C.c_void_p]
+        L.ref_fm_count.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.ref_fm_count.restype = C.c_longlong
+        L.ref_scan_sequence.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, C.c_longlong,
+                                        C.POINTER(C.c_longlong), C.POINTER(C.c_uint)]
+        L.ref_scan_sequence.restype = C.c_longlong
+        L.ref_set_genome.argtypes = [C.c_char_p, C.c_char_p]
+        L.ref_get_reference_slice.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.c_char_p, C.c_int]
+        L.ref_get_reference_slice.restype = C.c_int
+
+    # ---- anchoring: the reference's sdsl FM-index and src/fmindex.h:173-326 ----
+    def fm_build(self, text):
+        """construct_im(csa_wt<>, text, 1) -> opaque handle (free with fm_free)."""
+        return self.lib.ref_fm_build(bytes(text), len(text))
+
+    def fm_free(self, h):
+        self.lib.ref_fm_free(h)
+
+    def fm_count(self, h, pat):
+        return int(self.lib.ref_fm_count(h, bytes(pat), len(pat)))
+
+    def scan_sequence(self, h, cons, trim_left, trim_right, kmer, unique):
+        cap = max(1, len(cons)) * (1 if unique else 1000)
+        hits = np.zeros(cap, np.int64)
+        g, f = C.c_longlong(0), C.c_uint(0)
+        n = self.lib.ref_scan_sequence(h, bytes(cons), len(cons), trim_left, trim_right, kmer, int(unique), hits, cap, C.byref(g), C.byref(f))
+        return hits[:n].copy(), int(g.value), int(f.value)
+
+    def set_genome(self, names, seqs):
+        """Hand the in-memory faidx stand-in its sequences (getReferenceSlice with filetype 0 fetches from it)."""
+        self.lib.ref_set_genome(b"\n".join(names), b"\n".join(seqs))
+
+    def get_reference_slice(self, h, filetype, cons, trim_left, trim_right, kmer, maxindel, min_support, refslice=b""):
+        """getReferenceSlice -> dict(ok, forward, kmersupport, pos, chr, refslice)."""
+        cap = max(len(refslice), len(cons) + 2 * maxindel + 16)
+        buf = C.create_string_buffer(bytes(refslice), cap + 1)
+        rl, fw, ks, pos = C.c_int(len(refslice)), C.c_int(1), C.c_uint(0), C.c_uint(0)
+        chrb = C.create_string_buffer(256)
+        ok = self.lib.ref_get_reference_slice(h, filetype, bytes(cons), len(cons), trim_left, trim_right, kmer, maxindel, min_support, buf, cap,
+                                              C.byref(rl), C.byref(fw), C.byref(ks), C.byref(pos), chrb, 256)
+        return dict(ok=bool(ok), forward=bool(fw.value), kmersupport=int(ks.value), pos=int(pos.value), chr=chrb.value, refslice=buf.raw[: min(rl.value, cap)])
 
     def basecall(self, acgt, ploc, sigratio=0.33):
         acgt = np.ascontiguousarray(acgt, np.int32); ploc = np.ascontiguousarray(ploc, np.int32)

@@ -12,6 +12,8 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <sstream>
+#include <cstdlib>
 #include <vector>
 #include <utility>
 
@@ -62,6 +64,38 @@ int export_align(TAlign const& al, char* row0, char* row1, int cap) {
 }
 struct SweepCfg { uint16_t trimLeft, trimRight; uint16_t maxindel; uint16_t madc; };
 }  // namespace
+
+// In-memory stand-in for the six htslib faidx calls getReferenceSlice makes (src/fmindex.h:243-304). htslib cannot be
+// built in this container; these hold a genome the test handed over and keep faidx.c's documented behaviour:
+// faidx_fetch_seq returns [beg, end] INCLUSIVE, end clipped to len-1, beg clipped to [0, len] (htslib faidx.c:914-991).
+struct faidx_t { std::vector<std::string> names, seqs; };
+namespace { faidx_t g_genome; }
+extern "C" {
+faidx_t* fai_load(const char*) { return new faidx_t(g_genome); }
+void fai_destroy(faidx_t* f) { delete f; }
+int faidx_nseq(const faidx_t* f) { return (int)f->names.size(); }
+const char* faidx_iseq(const faidx_t* f, int i) { return f->names[i].c_str(); }
+int faidx_seq_len(const faidx_t* f, const char* seq) {
+  for (size_t i = 0; i < f->names.size(); ++i) if (f->names[i] == seq) return (int)f->seqs[i].size();
+  return -1;
+}
+char* faidx_fetch_seq(const faidx_t* f, const char* c_name, int beg, int end, int* len) {
+  for (size_t i = 0; i < f->names.size(); ++i) {
+    if (f->names[i] != c_name) continue;
+    long long L = (long long)f->seqs[i].size(), b = beg, e = end;
+    if (e < b) b = e;
+    if (b < 0) b = 0; else if (L <= b) b = L;
+    if (e < 0) e = 0; else if (L <= e) e = L - 1;
+    long long n = e + 1 - b; if (n < 0) n = 0;
+    char* out = (char*)malloc((size_t)n + 1);
+    memcpy(out, f->seqs[i].data() + b, (size_t)n); out[n] = 0;
+    *len = (int)n;
+    return out;
+  }
+  *len = -2;
+  return NULL;
+}
+}
 
 extern "C" {
 
@@ -295,6 +329,58 @@ long long ref_bench_gotoh_ps(const float* profs, const char* seqs, int npairs, i
     cells += (long long)m * n;
   }
   return cells;
+}
+
+
+// ---- anchoring: the reference's FM-index (sdsl csa_wt, as src/sage.h / src/indigo.h declare it) ---------------------
+struct AnchorCfg { boost::filesystem::path genome; uint16_t trimLeft, trimRight, kmer, maxindel, minKmerSupport; };
+void* ref_fm_build(const char* text, long long n) {
+  sdsl::csa_wt<>* fm = new sdsl::csa_wt<>();
+  std::string t(text, text + n);
+  sdsl::construct_im(*fm, t.c_str(), 1);                 // src/fmindex.h:131,160
+  return fm;
+}
+void ref_fm_free(void* h) { delete static_cast<sdsl::csa_wt<>*>(h); }
+long long ref_fm_count(void* h, const char* pat, int len) {
+  std::string p(pat, pat + len);
+  return (long long)sdsl::count(*static_cast<sdsl::csa_wt<>*>(h), p.begin(), p.end());
+}
+// scanSequence + findMaxFreq of one strand (src/fmindex.h:203-232, :173-198); hits are returned sorted as findMaxFreq leaves them
+long long ref_scan_sequence(void* h, const char* cons, int len, int trimLeft, int trimRight, int kmer, int unique,
+                            long long* hits, long long cap, long long* gpos, unsigned* freq) {
+  std::vector<int64_t> hv;
+  tracy::scanSequence(*static_cast<sdsl::csa_wt<>*>(h), std::string(cons, cons + len), (uint16_t)trimLeft, (uint16_t)trimRight, (uint16_t)kmer, hv, unique != 0);
+  int64_t g = 0;
+  *freq = tracy::findMaxFreq(hv, g);
+  *gpos = g;
+  for (size_t i = 0; i < hv.size() && (long long)i < cap; ++i) hits[i] = hv[i];
+  return (long long)hv.size();
+}
+// the genome the faidx stand-in serves: names/sequences as a '\n'-joined text and '\n'-joined names
+void ref_set_genome(const char* names, const char* text) {
+  g_genome.names.clear(); g_genome.seqs.clear();
+  std::stringstream a(names), b(text);
+  std::string x;
+  while (std::getline(a, x)) g_genome.names.push_back(x);
+  while (std::getline(b, x)) g_genome.seqs.push_back(x);
+}
+// getReferenceSlice (src/fmindex.h:236-326). filetype 0: indexed genome (uses the faidx stand-in); 1: single FASTA
+// (refslice_io holds the whole sequence on entry). Returns the function's bool; refslice_io receives rs.refslice.
+int ref_get_reference_slice(void* h, int filetype, const char* cons, int len, int trimLeft, int trimRight, int kmer, int maxindel,
+                            int minKmerSupport, char* refslice_io, int cap, int* refslice_len, int* forward, unsigned* kmersupport,
+                            unsigned* pos, char* chr_out, int chr_cap) {
+  AnchorCfg c; c.genome = boost::filesystem::path("mem"); c.trimLeft = trimLeft; c.trimRight = trimRight; c.kmer = kmer; c.maxindel = maxindel; c.minKmerSupport = minKmerSupport;
+  tracy::BaseCalls bc; bc.consensus = std::string(cons, cons + len);
+  tracy::ReferenceSlice rs; rs.filetype = filetype;
+  if (filetype) rs.refslice = std::string(refslice_io, refslice_io + *refslice_len);
+  std::streambuf* old = std::cerr.rdbuf(nullptr);        // "Couldn't anchor ..." goes to stderr in the reference
+  bool ok = tracy::getReferenceSlice(c, *static_cast<sdsl::csa_wt<>*>(h), bc, rs);
+  std::cerr.rdbuf(old);
+  *forward = rs.forward; *kmersupport = rs.kmersupport; *pos = rs.pos;
+  int L = (int)rs.refslice.size(); if (L > cap) L = cap;
+  memcpy(refslice_io, rs.refslice.data(), (size_t)L); *refslice_len = (int)rs.refslice.size();
+  snprintf(chr_out, (size_t)chr_cap, "%s", rs.chr.c_str());
+  return ok ? 1 : 0;
 }
 
 }  // extern "C"

@@ -154,6 +154,35 @@ class Context:
         self._check(self._lib.tb_ctx_last_packed_pairs(self._h, C.byref(v)))
         return v.value
 
+    # ---- reference anchoring (reference src/fmindex.h:173-326) -------------------------------------------------
+    def build_index(self, text):
+        """Index of the reference text for anchor(): `text` is what tracy indexes (upper-cased; a multi-sequence genome joined and
+        ended by b"\n", src/index.h:104-121). Returns a KmerIndex (close() it, or let the Context outlive it)."""
+        text = np.frombuffer(bytes(text), np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text, np.uint8)
+        h = C.c_void_p()
+        self._check(self._lib.tb_index_build(self._h, _ptr(text), text.size, capi.TB_MEM_HOST, C.byref(h)))
+        return KmerIndex(self, h)
+
+    def anchor(self, index, consensus, trim_left=50, trim_right=50, kmer=15, min_kmer_support=3):
+        """scanSequence + findMaxFreq + the orientation rule of getReferenceSlice for a batch of consensus strings.
+        Returns dict of arrays: anchored (bool), forward (bool), kmersupport (uint32), bestpos (int64), pass_ (uint8)."""
+        cons = consensus if isinstance(consensus, Arena) else pack_seqs(consensus)
+        n = cons.n
+        out = dict(anchored=np.zeros(n, np.uint8), forward=np.ones(n, np.uint8), kmersupport=np.zeros(n, np.uint32),
+                   bestpos=np.zeros(n, np.int64), pass_=np.zeros(n, np.uint8))
+        a = capi.Arena(_ptr(cons.base), _ptr(cons.off), _ptr(cons.len))
+        r = capi.AnchorResult(_ptr(out["anchored"]), _ptr(out["forward"]), _ptr(out["kmersupport"]), _ptr(out["bestpos"]), _ptr(out["pass_"]))
+        self._check(self._lib.tb_anchor(self._h, index._h, C.byref(a), n, capi.TB_MEM_HOST,
+                                        capi.AnchorConfig(trim_left, trim_right, kmer, min_kmer_support), C.byref(r)))
+        out["anchored"] = out["anchored"].astype(bool)
+        out["forward"] = out["forward"].astype(bool)
+        return out
+
+    def last_anchor_ms(self):
+        v = C.c_float()
+        self._check(self._lib.tb_ctx_last_anchor_ms(self._h, C.byref(v)))
+        return v.value
+
     # ---- gotoh / gotohScore, batched -------------------------------------------------------------------
     def _fn(self, kind):
         return {PS: self._lib.tb_gotoh_ps, PP: self._lib.tb_gotoh_pp, SS: self._lib.tb_gotoh_ss}[kind]
@@ -306,6 +335,34 @@ def rows_from_ops(kind, a1, a2, ops):
     if rc != capi.TB_OK:
         raise TracyError(rc, lib.tb_strerror(rc).decode())
     return r0.raw[:L], r1.raw[:L]
+
+
+class KmerIndex:
+    """Device-resident sorted k-mer index of one reference text (tb_index)."""
+
+    def __init__(self, ctx, h):
+        self._ctx, self._h = ctx, h
+        n, b, t = C.c_int64(), C.c_uint64(), C.c_void_p()
+        ctx._lib.tb_index_info(h, C.byref(n), C.byref(b), C.byref(t))
+        self.text_len, self.device_bytes, self.device_text = n.value, b.value, t.value
+
+    def close(self):
+        if self._h and getattr(self._ctx, "_h", None):
+            self._ctx._lib.tb_index_destroy(self._ctx._h, self._h)
+        self._h = None
+
+
+def reference_slice(bestpos, seqlen, conslen, maxindel=1000):
+    """Slice arithmetic of getReferenceSlice (reference src/fmindex.h:286-299): -> (refindex, chrpos, slicestart, sliceend).
+    seqlen: per sequence, length + 1 for a b"\n"-joined genome (src/fmindex.h:247), the plain length for a single sequence.
+    For an indexed genome the reference then fetches [slicestart, min(sliceend, len - 1)] INCLUSIVE (htslib faidx_fetch_seq)."""
+    lib = capi.lib()
+    sl = np.ascontiguousarray(seqlen, np.uint32)
+    ri, cp, s0, s1 = C.c_int32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = lib.tb_reference_slice(int(bestpos), _ptr(sl), sl.size, conslen, maxindel, C.byref(ri), C.byref(cp), C.byref(s0), C.byref(s1))
+    if rc != capi.TB_OK:
+        raise TracyError(rc, lib.tb_strerror(rc).decode())
+    return ri.value, cp.value, s0.value, s1.value
 
 
 def trim_reference_slice(row0, row1, refslice, forward=True, pos=0, trim_left=0, trim_right=0):

@@ -14,7 +14,8 @@ SYMBOLS = [
     "tb_ctx_create", "tb_ctx_destroy", "tb_strerror", "tb_last_error", "tb_host_alloc", "tb_host_free",
     "tb_ctx_set_scratch_limit", "tb_ctx_stats", "tb_ctx_last_kernel_ms", "tb_ctx_last_call_ms", "tb_ctx_last_packed_pairs", "tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss",
     "tb_rows_from_ops", "tb_decompose_sweep", "tb_version", "tb_create_profile", "tb_revcomp_profile", "tb_trim_reference_slice",
-    "tb_find_breakpoint", "tb_basecall",
+    "tb_find_breakpoint", "tb_basecall", "tb_index_build", "tb_index_destroy", "tb_index_info", "tb_anchor", "tb_ctx_last_anchor_ms",
+    "tb_reference_slice",
 ]
 
 
@@ -55,6 +56,14 @@ class ProfileBatch(C.Structure):
 
 class BasecallBatch(C.Structure):
     _fields_ = [("trace", Arena), ("ploc", Arena), ("ntraces", C.c_size_t), ("mem", C.c_int32)]
+
+
+class AnchorConfig(C.Structure):
+    _fields_ = [("trim_left", C.c_int32), ("trim_right", C.c_int32), ("kmer", C.c_int32), ("min_kmer_support", C.c_int32)]
+
+
+class AnchorResult(C.Structure):
+    _fields_ = [("anchored", C.c_void_p), ("forward", C.c_void_p), ("kmersupport", C.c_void_p), ("bestpos", C.c_void_p), ("pass_", C.c_void_p)]
 
 
 class LibraryMissing(RuntimeError):
@@ -99,5 +108,12 @@ def lib():
     L.tb_trim_reference_slice.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.c_int32,
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
     L.tb_find_breakpoint.argtypes = [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    L.tb_index_build.argtypes = [vp, vp, C.c_int64, C.c_int32, C.POINTER(vp)]
+    L.tb_index_destroy.argtypes = [vp, vp]
+    L.tb_index_info.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(vp)]
+    L.tb_anchor.argtypes = [vp, vp, C.POINTER(Arena), C.c_size_t, C.c_int32, AnchorConfig, C.POINTER(AnchorResult)]
+    L.tb_ctx_last_anchor_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.tb_reference_slice.argtypes = [C.c_int64, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32),
+                                     C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     _lib = L
     return L

@@ -25,6 +25,13 @@ unsigned long long gotoh_packed_ptr_words(int m, int n);
 
 
 cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
+cudaError_t index_sort_temp_bytes(long long n, size_t* bytes);
+cudaError_t index_build(const unsigned char* text, long long n, unsigned long long* keys_in, unsigned* pos_in, unsigned long long* keys_out,
+                        unsigned* pos_out, void* temp, size_t temp_bytes, unsigned* dir_lo, unsigned* dir_hi, int* invalid, cudaStream_t st);
+unsigned index_dir_entries();
+cudaError_t launch_anchor_unique(const KmerIndexView& X, const AnchorBatch& A, int ntraces, unsigned tsize, cudaStream_t st);
+cudaError_t launch_anchor_count(const KmerIndexView& X, const AnchorBatch& A, int ntodo, cudaStream_t st);
+cudaError_t launch_anchor_fill(const KmerIndexView& X, const AnchorBatch& A, int ntodo, long long table_elems, cudaStream_t st);
 cudaError_t launch_create_profile(const ProfileBatch& P, int ntraces, cudaStream_t stream);
 cudaError_t launch_basecall(const BasecallBatch& P, int ntraces, cudaStream_t stream);
 cudaError_t launch_revcomp_profile(const float* in_base, const int64_t* in_off, const int32_t* len, float* out_base, const int64_t* out_off,
@@ -95,7 +102,7 @@ struct tb_ctx {
   Lane lanes[kLanes];
   cudaEvent_t t0 = nullptr;   // start of a host-mode call (timeline origin for TRACY_B200_TRACE)
   uint64_t launches = 0, h2d = 0, d2h = 0;
-  float last_fast_ms = 0, last_general_ms = 0, last_sweep_ms = 0, last_call_ms = 0;
+  float last_fast_ms = 0, last_general_ms = 0, last_sweep_ms = 0, last_call_ms = 0, last_anchor_ms = 0;
   uint64_t last_packed_pairs = 0;
   std::vector<int32_t> tmp_len1, tmp_len2;
 };
@@ -940,3 +947,223 @@ int tb_find_breakpoint(const float* p, int32_t len, int32_t* indelshift, int32_t
 }
 
 }  // extern "C"
+
+// ---- reference anchoring (kernels in anchor.cu) -----------------------------------------
+struct tb_index {
+  int device = 0;
+  long long n = 0;
+  unsigned char* text = nullptr;
+  unsigned long long* keys = nullptr;
+  unsigned* pos = nullptr;
+  unsigned* dir_lo = nullptr;
+  unsigned* dir_hi = nullptr;
+  size_t bytes = 0;
+};
+
+int tb_index_destroy(tb_ctx* ctx, tb_index* idx) {
+  if (!idx) return TB_OK;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(idx->text); cudaFree(idx->keys); cudaFree(idx->pos); cudaFree(idx->dir_lo); cudaFree(idx->dir_hi);
+  delete idx;
+  return TB_OK;
+}
+
+int tb_index_build(tb_ctx* ctx, const char* text, int64_t text_len, int32_t mem, tb_index** out) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (!text || !out || text_len <= 0) return fail(ctx, TB_ERR_INVALID, "null/empty text");
+  if (text_len >= (int64_t)UINT_MAX) return fail(ctx, TB_ERR_UNSUPPORTED, "text longer than 2^32-2 characters");
+  if (mem != TB_MEM_HOST && mem != TB_MEM_DEVICE) return fail(ctx, TB_ERR_INVALID, "mem must be TB_MEM_HOST or TB_MEM_DEVICE");
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->lanes[0].stream;
+  const long long n = text_len;
+  tb_index* X = new (std::nothrow) tb_index();
+  if (!X) return fail(ctx, TB_ERR_NOMEM, "out of host memory");
+  X->device = ctx->device; X->n = n;
+  unsigned long long* keys_in = nullptr; unsigned* pos_in = nullptr; void* temp = nullptr; int* d_invalid = nullptr;
+  size_t temp_bytes = 0;
+  const unsigned nd = tb::index_dir_entries();
+  auto cleanup = [&](int rc) { cudaFree(keys_in); cudaFree(pos_in); cudaFree(temp); cudaFree(d_invalid); if (rc != TB_OK) { tb_index_destroy(ctx, X); } return rc; };
+#define TB_IDX(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cleanup(cuda_fail(ctx, e__, #call)); } while (0)
+  TB_IDX(tb::index_sort_temp_bytes(n, &temp_bytes));
+  TB_IDX(cudaMalloc(&X->text, (size_t)n + 64));
+  TB_IDX(cudaMalloc(&X->keys, (size_t)n * 8)); TB_IDX(cudaMalloc(&X->pos, (size_t)n * 4));
+  TB_IDX(cudaMalloc(&X->dir_lo, (size_t)nd * 4)); TB_IDX(cudaMalloc(&X->dir_hi, (size_t)nd * 4));
+  TB_IDX(cudaMalloc(&keys_in, (size_t)n * 8)); TB_IDX(cudaMalloc(&pos_in, (size_t)n * 4));
+  TB_IDX(cudaMalloc(&temp, temp_bytes ? temp_bytes : 1)); TB_IDX(cudaMalloc(&d_invalid, 4));
+  TB_IDX(cudaMemcpyAsync(X->text, text, (size_t)n, mem == TB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+  if (mem == TB_MEM_HOST) ctx->h2d += (size_t)n;
+  TB_IDX(tb::index_build(X->text, n, keys_in, pos_in, X->keys, X->pos, temp, temp_bytes, X->dir_lo, X->dir_hi, d_invalid, st));
+  ctx->launches += 3;
+  int invalid = 0;
+  TB_IDX(cudaMemcpyAsync(&invalid, d_invalid, 4, cudaMemcpyDeviceToHost, st));
+  TB_IDX(cudaStreamSynchronize(st));
+#undef TB_IDX
+  if (invalid) return cleanup(fail(ctx, TB_ERR_UNSUPPORTED, "text holds a byte outside ACGTN, the IUPAC codes RYSWKMBDHV and '\\n'"));
+  X->bytes = (size_t)n * 13 + (size_t)nd * 8;
+  *out = X;
+  return cleanup(TB_OK);
+}
+
+int tb_index_info(const tb_index* idx, int64_t* text_len, uint64_t* device_bytes, const char** device_text) {
+  if (!idx) return TB_ERR_INVALID;
+  if (text_len) *text_len = idx->n;
+  if (device_bytes) *device_bytes = idx->bytes;
+  if (device_text) *device_text = reinterpret_cast<const char*>(idx->text);
+  return TB_OK;
+}
+
+namespace {
+unsigned next_pow2(unsigned long long v) { unsigned long long p = 2; while (p < v) p <<= 1; return (unsigned)std::min<unsigned long long>(p, 1ull << 31); }
+
+// Global-table path over the traces in `todo` (host list): count -> size the tables -> fill -> decide. Updates the
+// device result arrays in A; the caller re-reads `pass`.
+int anchor_global_pass(tb_ctx* ctx, const tb::KmerIndexView& X, tb::AnchorBatch A, const std::vector<int32_t>& todo, bool nonunique, cudaStream_t st) {
+  const size_t budget_elems = (size_t)1 << 27;            // 128 Mi slots (1.5 GB of keys + counts) per sub-batch
+  size_t done = 0;
+  while (done < todo.size()) {
+    Staged S(st);
+    // count on a window of traces, then cut it where the tables exceed the budget
+    const size_t wn = std::min<size_t>(todo.size() - done, 65536);
+    void *d_todo, *d_tot;
+    TB_CUDA(ctx, S.up(&d_todo, todo.data() + done, wn * 4));
+    TB_CUDA(ctx, S.alloc(&d_tot, wn * 16));
+    TB_CUDA(ctx, cudaMemsetAsync(d_tot, 0, wn * 16, st));
+    A.todo = (const int32_t*)d_todo; A.totals = (unsigned long long*)d_tot; A.nonunique = nonunique;
+    TB_CUDA(ctx, tb::launch_anchor_count(X, A, (int)wn, st));
+    ctx->launches++;
+    std::vector<unsigned long long> tot(2 * wn);
+    TB_CUDA(ctx, cudaMemcpyAsync(tot.data(), d_tot, wn * 16, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<long long> off; std::vector<unsigned> size;
+    size_t elems = 0, take = 0;
+    for (; take < wn; ++take) {
+      const unsigned s0 = next_pow2(2 * tot[2 * take]), s1 = next_pow2(2 * tot[2 * take + 1]);
+      if (take > 0 && elems + s0 + s1 > budget_elems) break;
+      off.push_back((long long)elems); size.push_back(s0); elems += s0;
+      off.push_back((long long)elems); size.push_back(s1); elems += s1;
+    }
+    void *d_off, *d_size, *d_keys, *d_cnt;
+    TB_CUDA(ctx, S.up(&d_off, off.data(), off.size() * 8)); TB_CUDA(ctx, S.up(&d_size, size.data(), size.size() * 4));
+    TB_CUDA(ctx, S.alloc(&d_keys, elems * 8)); TB_CUDA(ctx, S.alloc(&d_cnt, elems * 4));
+    A.tab_keys = (long long*)d_keys; A.tab_cnt = (unsigned*)d_cnt; A.tab_off = (const long long*)d_off; A.tab_size = (const unsigned*)d_size;
+    TB_CUDA(ctx, tb::launch_anchor_fill(X, A, (int)take, (long long)elems, st));
+    ctx->launches += 3;
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    done += take;
+  }
+  return TB_OK;
+}
+}  // namespace
+
+int tb_anchor(tb_ctx* ctx, const tb_index* idx, const tb_arena* cons, size_t ntraces, int32_t mem, tb_anchor_config cfg, tb_anchor_result* res) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (!idx || !cons || !res) return fail(ctx, TB_ERR_INVALID, "null index/arena/result");
+  if (ntraces == 0) return TB_OK;
+  if (ntraces > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "ntraces too large");
+  if (!cons->base || !cons->off || !cons->len || !res->anchored || !res->forward || !res->kmersupport || !res->bestpos)
+    return fail(ctx, TB_ERR_INVALID, "null pointer in anchoring call");
+  if (cfg.kmer < 1 || cfg.kmer > 16) return fail(ctx, TB_ERR_UNSUPPORTED, "kmer must be 1..16 (index depth is 16 characters)");
+  if (cfg.trim_left < 0 || cfg.trim_right < 0 || cfg.trim_left > 65535 || cfg.trim_right > 65535 || cfg.min_kmer_support < 0)
+    return fail(ctx, TB_ERR_INVALID, "trim/support out of range");
+  if (mem != TB_MEM_HOST && mem != TB_MEM_DEVICE) return fail(ctx, TB_ERR_INVALID, "mem must be TB_MEM_HOST or TB_MEM_DEVICE");
+  if (idx->device != ctx->device) return fail(ctx, TB_ERR_INVALID, "index lives on another device");
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  Lane& L = ctx->lanes[0];
+  cudaStream_t st = L.stream;
+  const size_t nt = ntraces;
+  std::vector<int32_t> hlen_dev;
+  const int32_t* hlen = cons->len;
+  if (mem == TB_MEM_DEVICE) {
+    hlen_dev.resize(nt);
+    TB_CUDA(ctx, cudaMemcpy(hlen_dev.data(), cons->len, nt * 4, cudaMemcpyDeviceToHost));
+    hlen = hlen_dev.data();
+  }
+  int maxlen = 0;
+  for (size_t i = 0; i < nt; ++i) {
+    if (hlen[i] < 0 || hlen[i] > 65535) return fail(ctx, TB_ERR_UNSUPPORTED, "consensus length outside 0..65535 (the reference scans with a uint16 index)");
+    maxlen = std::max(maxlen, hlen[i]);
+  }
+  tb::KmerIndexView X{idx->keys, idx->pos, idx->n, idx->dir_lo, idx->dir_hi};
+  tb::AnchorBatch A{};
+  A.trim_left = cfg.trim_left; A.trim_right = cfg.trim_right; A.kmer = cfg.kmer; A.min_support = cfg.min_kmer_support;
+  Staged S(st);
+  void *d_pass = nullptr;
+  uint8_t *o_anch = res->anchored, *o_fwd = res->forward; uint32_t* o_sup = res->kmersupport; int64_t* o_pos = res->bestpos;
+  if (mem == TB_MEM_DEVICE) {
+    A.cons_base = (const char*)cons->base; A.cons_off = cons->off; A.cons_len = cons->len;
+    A.anchored = o_anch; A.forward = o_fwd; A.kmersupport = o_sup; A.bestpos = o_pos;
+    if (res->pass) d_pass = res->pass; else TB_CUDA(ctx, S.alloc(&d_pass, nt));
+  } else {
+    long long cmax = 0;
+    for (size_t i = 0; i < nt; ++i) {
+      if (cons->off[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative arena offset");
+      cmax = std::max<long long>(cmax, cons->off[i] + hlen[i]);
+    }
+    void *d_c, *d_off, *d_len, *d_a, *d_f, *d_s, *d_p;
+    TB_CUDA(ctx, S.up(&d_c, cons->base, (size_t)std::max<long long>(cmax, 1))); TB_CUDA(ctx, S.up(&d_off, cons->off, nt * 8)); TB_CUDA(ctx, S.up(&d_len, cons->len, nt * 4));
+    TB_CUDA(ctx, S.alloc(&d_a, nt)); TB_CUDA(ctx, S.alloc(&d_f, nt)); TB_CUDA(ctx, S.alloc(&d_s, nt * 4)); TB_CUDA(ctx, S.alloc(&d_p, nt * 8));
+    TB_CUDA(ctx, S.alloc(&d_pass, nt));
+    ctx->h2d += (size_t)cmax + nt * 12;
+    A.cons_base = (const char*)d_c; A.cons_off = (const int64_t*)d_off; A.cons_len = (const int32_t*)d_len;
+    A.anchored = (uint8_t*)d_a; A.forward = (uint8_t*)d_f; A.kmersupport = (uint32_t*)d_s; A.bestpos = (int64_t*)d_p;
+  }
+  A.pass = (uint8_t*)d_pass;
+  // shared-memory tables sized for the longest scan of the batch: two slots per k-mer, 1024..8192 slots (12 B each)
+  const unsigned tsize = std::min(std::max(next_pow2(2ull * (unsigned)maxlen), 1024u), 8192u);
+  TB_CUDA(ctx, cudaEventRecord(L.k0, st));
+  TB_CUDA(ctx, tb::launch_anchor_unique(X, A, (int)nt, tsize, st));
+  ctx->launches++;
+  TB_CUDA(ctx, cudaEventRecord(L.k1, st));
+  std::vector<uint8_t> pass(nt);
+  TB_CUDA(ctx, cudaMemcpyAsync(pass.data(), d_pass, nt, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(ctx, cudaStreamSynchronize(st));
+  TB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_anchor_ms, L.k0, L.k1));
+  std::vector<int32_t> todo;
+  for (size_t i = 0; i < nt; ++i) if (pass[i] == 3) todo.push_back((int32_t)i);
+  if (!todo.empty()) {                                    // scans too long for shared-memory tables: unique pass on global tables
+    if (int rc = anchor_global_pass(ctx, X, A, todo, false, st)) return rc;
+    TB_CUDA(ctx, cudaMemcpyAsync(pass.data(), d_pass, nt, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  todo.clear();
+  for (size_t i = 0; i < nt; ++i) if (pass[i] == 2) todo.push_back((int32_t)i);
+  if (!todo.empty())                                      // "Try using non-unique matches", src/fmindex.h:262-268
+    if (int rc = anchor_global_pass(ctx, X, A, todo, true, st)) return rc;
+  if (mem == TB_MEM_HOST) {
+    TB_CUDA(ctx, cudaMemcpyAsync(o_anch, A.anchored, nt, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaMemcpyAsync(o_fwd, A.forward, nt, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaMemcpyAsync(o_sup, A.kmersupport, nt * 4, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaMemcpyAsync(o_pos, A.bestpos, nt * 8, cudaMemcpyDeviceToHost, st));
+    if (res->pass) TB_CUDA(ctx, cudaMemcpyAsync(res->pass, d_pass, nt, cudaMemcpyDeviceToHost, st));
+    ctx->d2h += nt * 15;
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return TB_OK;
+}
+
+int tb_ctx_last_anchor_ms(const tb_ctx* ctx, float* unique_ms) {
+  if (!ctx || !unique_ms) return TB_ERR_INVALID;
+  *unique_ms = ctx->last_anchor_ms;
+  return TB_OK;
+}
+
+// getReferenceSlice's slice arithmetic, reference src/fmindex.h:286-299 (host).
+int tb_reference_slice(int64_t bestpos, const uint32_t* seqlen, int32_t nseq, int32_t conslen, int32_t maxindel,
+                       int32_t* refindex, uint32_t* chrpos_out, uint32_t* slicestart, uint32_t* sliceend) {
+  if (!seqlen || nseq <= 0 || conslen < 0 || maxindel < 0 || !refindex || !slicestart || !sliceend) return TB_ERR_INVALID;
+  int64_t cumsum = 0;
+  int32_t ri = 0;
+  for (; bestpos >= cumsum + (int64_t)seqlen[ri]; ++ri) {
+    cumsum += seqlen[ri];
+    if (ri + 1 >= nseq) return TB_ERR_INVALID;            // the reference would run off seqlen here
+  }
+  const int64_t chrpos_signed = bestpos - cumsum;
+  const uint32_t chrpos = chrpos_signed > 0 ? (uint32_t)chrpos_signed : 0;
+  uint32_t s0 = 0, s1 = seqlen[ri];
+  if (chrpos > (uint32_t)maxindel) s0 = chrpos - (uint32_t)maxindel;
+  const uint32_t tmpend = chrpos + (uint32_t)conslen + (uint32_t)maxindel;
+  if (tmpend < seqlen[ri]) s1 = tmpend;
+  *refindex = ri; *slicestart = s0; *sliceend = s1;
+  if (chrpos_out) *chrpos_out = chrpos;
+  return TB_OK;
+}

@@ -62,6 +62,23 @@ struct BasecallBatch {
   float sigratio;
 };
 
+// Device view of the sorted k-mer index and of an anchoring batch (anchor.cu).
+struct KmerIndexView {
+  const unsigned long long* keys; const unsigned* pos; long long n;
+  const unsigned* dir_lo; const unsigned* dir_hi;
+};
+struct AnchorBatch {
+  const char* cons_base; const int64_t* cons_off; const int32_t* cons_len;
+  int trim_left, trim_right, kmer, min_support;
+  // per trace results
+  uint8_t* anchored; uint8_t* forward; uint32_t* kmersupport; int64_t* bestpos; uint8_t* pass;
+  // global-table path
+  const int32_t* todo;              // trace ids to process (nullptr: blockIdx.x is the trace)
+  long long* tab_keys; unsigned* tab_cnt; const long long* tab_off; const unsigned* tab_size;   // per (todo slot, strand)
+  unsigned long long* totals;       // per (todo slot, strand): number of hits the scan will push
+  int nonunique;
+};
+
 // reference src/align.h:121-136: A,C,G,T,N (case-insensitive) -> 0..4; '-' and everything else contribute
 // nothing to _score (row 5 is never read, src/align.h:113-114) -> class 5.
 __device__ __forceinline__ int base_class(unsigned char ch) {

@@ -5,9 +5,11 @@
 // src/index.h:104-121, src/fmindex.h:130,160) two things only: count(kmer) and locate(kmer). Both are functions of
 // the TEXT, not of the index structure, so the B200 index is the layout HBM likes instead: every text position i with
 // the 16 characters that follow it packed into one 64-bit key (4 bits per character, a sequence end pads with 0), all
-// positions radix-sorted by key. count(pattern) for |pattern| <= 16 is the width of a key range, locate() the position
-// column of that range. A directory over the first 12 characters (when they are all A/C/G/T) narrows the binary search
-// to a few probes. 12 bytes per text position (37 GB for a 3.1 Gbp genome -- HBM-resident on a 180 GB part).
+// positions radix-sorted by key and stored as 16-byte records {key, position}. count(pattern) for |pattern| <= 16 is the
+// width of a key range, locate() the position column of that range. A directory over the first d characters (d = 8..14 by
+// text size, when they are all A/C/G/T) hands back a bucket of a few records, which is read with independent 16-byte
+// loads: a unique k-mer costs one directory access plus one or two 64-byte DRAM granules, no dependent probe chain.
+// 16 bytes per text position + 8 * 4^d (52 GB for a 3.1 Gbp genome -- HBM-resident on a 180 GB part).
 //
 // Per trace one block scans both strands: k-mer -> key range -> hit (position - k) -> a shared-memory hash table of
 // hit counts -> findMaxFreq (the smallest most frequent value) -> the reference's orientation rule. Traces that fail
@@ -20,8 +22,7 @@
 namespace tb {
 
 constexpr int kIdxDepth = 16;                 // characters per key
-constexpr int kDirChars = 12;                 // directory prefix length (2 bits per character)
-constexpr unsigned kDirSize = 1u << (2 * kDirChars);
+constexpr int kBucketScan = 8;                // buckets up to this many records are read in one go
 constexpr long long kEmpty = LLONG_MIN;       // free hash slot (a hit is position - k, never near INT64_MIN)
 
 // 4-bit alphabet: 0 = end of sequence / padding; the IUPAC letters tracy's texts and consensus strings can hold.
@@ -65,29 +66,39 @@ __global__ void __launch_bounds__(256) index_keys_kernel(const unsigned char* __
   pos[i] = (unsigned)i;
 }
 
-__device__ __forceinline__ long long lower_bound_key(const unsigned long long* __restrict__ keys, long long lo, long long hi,
-                                                     unsigned long long k) {
-  while (lo < hi) {                                       // first index with keys[idx] >= k
+__device__ __forceinline__ unsigned long long rec_key(const uint4* __restrict__ rec, long long i) {
+  const uint2 k = __ldg(reinterpret_cast<const uint2*>(rec + i));
+  return ((unsigned long long)k.y << 32) | k.x;
+}
+__device__ __forceinline__ long long lower_bound_rec(const uint4* __restrict__ rec, long long lo, long long hi, unsigned long long k) {
+  while (lo < hi) {                                       // first index with key >= k
     const long long mid = (lo + hi) >> 1;
-    if (__ldg(keys + mid) < k) lo = mid + 1; else hi = mid;
+    if (rec_key(rec, mid) < k) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
 
-// Directory: for every 12-mer over A,C,G,T (2 bits each) the sorted range of keys that start with it.
-__global__ void __launch_bounds__(256) index_dir_kernel(const unsigned long long* __restrict__ keys, long long n,
-                                                        unsigned* __restrict__ dir_lo, unsigned* __restrict__ dir_hi) {
+// sorted (key, position) columns -> 16-byte records
+__global__ void __launch_bounds__(256) index_records_kernel(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ pos,
+                                                            long long n, uint4* __restrict__ rec) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  rec[i] = make_uint4((unsigned)k, (unsigned)(k >> 32), pos[i], 0u);
+}
+
+// Directory: for every d-mer over A,C,G,T (2 bits each, first character in the top bits) the sorted range of records
+// whose key starts with it.
+__global__ void __launch_bounds__(256) index_dir_kernel(const uint4* __restrict__ rec, long long n, int d, uint2* __restrict__ dir) {
   const unsigned b = blockIdx.x * 256u + threadIdx.x;
-  if (b >= kDirSize) return;
+  if (b >= (1u << (2 * d))) return;
   unsigned long long k = 0;
-#pragma unroll
-  for (int j = kDirChars - 1; j >= 0; --j) k = (k << 4) | (((b >> (2 * j)) & 3u) + 1u);
-  const int pad = 4 * (kIdxDepth - kDirChars);
+  for (int j = d - 1; j >= 0; --j) k = (k << 4) | (((b >> (2 * j)) & 3u) + 1u);
+  const int pad = 4 * (kIdxDepth - d);
   const unsigned long long klo = k << pad, khi = klo | ((1ull << pad) - 1ull);
-  const long long lo = lower_bound_key(keys, 0, n, klo);
-  const long long hi = khi == ~0ull ? n : lower_bound_key(keys, lo, n, khi + 1ull);
-  dir_lo[b] = (unsigned)lo;
-  dir_hi[b] = (unsigned)hi;
+  const long long lo = lower_bound_rec(rec, 0, n, klo);
+  const long long hi = lower_bound_rec(rec, lo, n, khi + 1ull);   // d <= 14: khi + 1 cannot wrap
+  dir[b] = make_uint2((unsigned)lo, (unsigned)hi);
 }
 
 
@@ -106,12 +117,14 @@ __device__ __forceinline__ unsigned char strand_char(const char* __restrict__ s,
 }
 
 // The k-mer starting at k of one strand (reference src/fmindex.h:205-232): returns false when it is skipped (an 'N' in
-// the window); otherwise the sorted-key range [lo, hi) of its occurrences (pattern = substr(k, kmer), shorter at the end).
+// the window); otherwise the sorted range [lo, hi) of its occurrences (pattern = substr(k, kmer), shorter at the end)
+// and, when the range is not empty, the text position of its first record.
 __device__ __forceinline__ bool kmer_range(const KmerIndexView& X, const char* __restrict__ s, int len, int strand, int k, int kmer,
-                                           long long* lo_out, long long* hi_out) {
+                                           long long* lo_out, long long* hi_out, unsigned* pos_out) {
   const int l = min(kmer, len - k);
+  const int d = X.dir_chars;
   unsigned long long key = 0;
-  bool findable = true, acgt12 = l >= kDirChars;
+  bool findable = true, in_dir = l >= d;
   unsigned dirb = 0;
   for (int j = 0; j < l; ++j) {
     const unsigned char ch = strand_char(s, len, strand, k + j);
@@ -119,17 +132,40 @@ __device__ __forceinline__ bool kmer_range(const KmerIndexView& X, const char* _
     const unsigned c = code4(ch);
     if (c == 0) findable = false;                         // a byte no indexed text contains: count() is 0
     key = (key << 4) | c;
-    if (j < kDirChars) { if (c >= 1 && c <= 4) dirb = (dirb << 2) | (c - 1); else acgt12 = false; }
+    if (j < d) { if (c >= 1 && c <= 4) dirb = (dirb << 2) | (c - 1); else in_dir = false; }
   }
+  *pos_out = 0;
   if (!findable) { *lo_out = *hi_out = 0; return true; }
-  const int pad = 4 * (kIdxDepth - l);
-  const unsigned long long klo = pad >= 64 ? 0ull : key << pad;
-  const unsigned long long khi = klo | (pad >= 64 ? ~0ull : ((1ull << pad) - 1ull));
+  const int pad = 4 * (kIdxDepth - l);                    // l >= 1: pad <= 60
+  const unsigned long long klo = key << pad, khi = klo | ((1ull << pad) - 1ull);
   long long a = 0, b = X.n;
-  if (acgt12) { a = __ldg(X.dir_lo + dirb); b = __ldg(X.dir_hi + dirb); }
-  const long long lo = lower_bound_key(X.keys, a, b, klo);
-  const long long hi = khi == ~0ull ? b : lower_bound_key(X.keys, lo, b, khi + 1ull);
+  if (in_dir) { const uint2 e = __ldg(X.dir + dirb); a = e.x; b = e.y; }
+  while (b - a > kBucketScan) {                           // narrow while the probe falls outside the match range
+    const long long mid = (a + b) >> 1;
+    const unsigned long long km = rec_key(X.rec, mid);
+    if (km < klo) a = mid + 1; else if (km > khi) b = mid; else break;
+  }
+  if (b - a <= kBucketScan) {                             // the whole bucket with independent loads
+    uint4 r[kBucketScan];
+#pragma unroll
+    for (int j = 0; j < kBucketScan; ++j) r[j] = a + j < b ? __ldg(X.rec + a + j) : make_uint4(~0u, ~0u, 0u, 0u);
+    int below = 0, upto = 0;
+    unsigned p = 0;
+#pragma unroll
+    for (int j = kBucketScan - 1; j >= 0; --j) {
+      const unsigned long long kj = ((unsigned long long)r[j].y << 32) | r[j].x;
+      const bool live = a + j < b;
+      below += live && kj < klo;
+      upto += live && kj <= khi;
+      if (live && kj >= klo) p = r[j].z;                  // ends as the position of the first record >= klo
+    }
+    *lo_out = a + below; *hi_out = a + upto; *pos_out = p;
+    return true;
+  }
+  const long long lo = lower_bound_rec(X.rec, a, b, klo);
+  const long long hi = khi == ~0ull ? b : lower_bound_rec(X.rec, lo, b, khi + 1ull);
   *lo_out = lo; *hi_out = hi;
+  if (hi > lo) *pos_out = __ldg(&X.rec[lo].z);
   return true;
 }
 
@@ -212,8 +248,9 @@ __global__ void __launch_bounds__(256) anchor_unique_kernel(const KmerIndexView 
     __syncthreads();
     for (int k = k0 + (int)threadIdx.x; k < k1; k += blockDim.x) {
       long long lo, hi;
-      if (!kmer_range(X, s, len, strand, k, A.kmer, &lo, &hi)) continue;
-      if (hi - lo == 1) table_insert(tkeys, tcnt, tsize - 1, (long long)__ldg(X.pos + lo) - (long long)k);
+      unsigned p0;
+      if (!kmer_range(X, s, len, strand, k, A.kmer, &lo, &hi, &p0)) continue;
+      if (hi - lo == 1) table_insert(tkeys, tcnt, tsize - 1, (long long)p0 - (long long)k);
     }
     __syncthreads();
     table_mode(tkeys, tcnt, tsize, &s_freq[strand], &s_pos[strand], s_cnt, s_key);
@@ -239,7 +276,8 @@ __global__ void __launch_bounds__(256) anchor_count_kernel(const KmerIndexView X
   unsigned long long mine = 0;
   for (int k = k0 + (int)threadIdx.x; k < k1; k += blockDim.x) {
     long long lo, hi;
-    if (!kmer_range(X, s, len, strand, k, A.kmer, &lo, &hi)) continue;
+    unsigned p0;
+    if (!kmer_range(X, s, len, strand, k, A.kmer, &lo, &hi, &p0)) continue;
     const long long occs = hi - lo;
     if (A.nonunique ? (occs > 0 && occs < 1000) : occs == 1) mine += (unsigned long long)occs;
   }
@@ -260,10 +298,11 @@ __global__ void __launch_bounds__(256) anchor_fill_kernel(const KmerIndexView X,
   strand_range(len, strand, A.trim_left, A.trim_right, &k0, &k1);
   for (int k = k0 + (int)threadIdx.x; k < k1; k += blockDim.x) {
     long long lo, hi;
-    if (!kmer_range(X, s, len, strand, k, A.kmer, &lo, &hi)) continue;
+    unsigned p0;
+    if (!kmer_range(X, s, len, strand, k, A.kmer, &lo, &hi, &p0)) continue;
     const long long occs = hi - lo;
     if (!(A.nonunique ? (occs > 0 && occs < 1000) : occs == 1)) continue;
-    for (long long j = lo; j < hi; ++j) table_insert(tkeys, tcnt, mask, (long long)__ldg(X.pos + j) - (long long)k);
+    for (long long j = lo; j < hi; ++j) table_insert(tkeys, tcnt, mask, (long long)__ldg(&X.rec[j].z) - (long long)k);
   }
 }
 
@@ -303,21 +342,29 @@ cudaError_t index_sort_temp_bytes(long long n, size_t* bytes) {
   return cub::DeviceRadixSort::SortPairs(nullptr, *bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
                                          (const unsigned*)nullptr, (unsigned*)nullptr, n, 0, 64);
 }
-// keys_in/pos_in are filled from the text, sorted into keys_out/pos_out, then the directory is built over keys_out.
-cudaError_t index_build(const unsigned char* text, long long n, unsigned long long* keys_in, unsigned* pos_in,
-                        unsigned long long* keys_out, unsigned* pos_out, void* temp, size_t temp_bytes,
-                        unsigned* dir_lo, unsigned* dir_hi, int* invalid, cudaStream_t st) {
+// Directory depth for a text of n characters: the smallest d in 8..14 whose 4^d buckets hold <= 8 records on average.
+int index_dir_chars(long long n) {
+  int d = 8;
+  while (d < 14 && (1ll << (2 * d)) * kBucketScan < n) ++d;
+  return d;
+}
+// keys_a/pos_a are filled from the text and sorted into keys_b/pos_b (scratch, freed by the caller), from which the
+// records and then the directory are built.
+cudaError_t index_build(const unsigned char* text, long long n, unsigned long long* keys_a, unsigned* pos_a,
+                        unsigned long long* keys_b, unsigned* pos_b, void* temp, size_t temp_bytes,
+                        uint4* rec, uint2* dir, int dir_chars, int* invalid, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(invalid, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   const long long blocks = (n + 255) / 256;
-  index_keys_kernel<<<(unsigned)blocks, 256, 0, st>>>(text, n, keys_in, pos_in, invalid);
+  index_keys_kernel<<<(unsigned)blocks, 256, 0, st>>>(text, n, keys_a, pos_a, invalid);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, pos_in, pos_out, n, 0, 64, st);
+  e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_a, keys_b, pos_a, pos_b, n, 0, 64, st);
   if (e != cudaSuccess) return e;
-  index_dir_kernel<<<kDirSize / 256, 256, 0, st>>>(keys_out, n, dir_lo, dir_hi);
+  index_records_kernel<<<(unsigned)blocks, 256, 0, st>>>(keys_b, pos_b, n, rec);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  index_dir_kernel<<<(1u << (2 * dir_chars)) / 256, 256, 0, st>>>(rec, n, dir_chars, dir);
   return cudaGetLastError();
 }
-unsigned index_dir_entries() { return kDirSize; }
 
 cudaError_t launch_anchor_unique(const KmerIndexView& X, const AnchorBatch& A, int ntraces, unsigned tsize, cudaStream_t st) {
   const size_t smem = (size_t)tsize * 12;

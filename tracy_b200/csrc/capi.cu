@@ -26,9 +26,9 @@ unsigned long long gotoh_packed_ptr_words(int m, int n);
 
 cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
 cudaError_t index_sort_temp_bytes(long long n, size_t* bytes);
-cudaError_t index_build(const unsigned char* text, long long n, unsigned long long* keys_in, unsigned* pos_in, unsigned long long* keys_out,
-                        unsigned* pos_out, void* temp, size_t temp_bytes, unsigned* dir_lo, unsigned* dir_hi, int* invalid, cudaStream_t st);
-unsigned index_dir_entries();
+cudaError_t index_build(const unsigned char* text, long long n, unsigned long long* keys_a, unsigned* pos_a, unsigned long long* keys_b,
+                        unsigned* pos_b, void* temp, size_t temp_bytes, uint4* rec, uint2* dir, int dir_chars, int* invalid, cudaStream_t st);
+int index_dir_chars(long long n);
 cudaError_t launch_anchor_unique(const KmerIndexView& X, const AnchorBatch& A, int ntraces, unsigned tsize, cudaStream_t st);
 cudaError_t launch_anchor_count(const KmerIndexView& X, const AnchorBatch& A, int ntodo, cudaStream_t st);
 cudaError_t launch_anchor_fill(const KmerIndexView& X, const AnchorBatch& A, int ntodo, long long table_elems, cudaStream_t st);
@@ -953,17 +953,16 @@ struct tb_index {
   int device = 0;
   long long n = 0;
   unsigned char* text = nullptr;
-  unsigned long long* keys = nullptr;
-  unsigned* pos = nullptr;
-  unsigned* dir_lo = nullptr;
-  unsigned* dir_hi = nullptr;
+  uint4* rec = nullptr;
+  uint2* dir = nullptr;
+  int dir_chars = 0;
   size_t bytes = 0;
 };
 
 int tb_index_destroy(tb_ctx* ctx, tb_index* idx) {
   if (!idx) return TB_OK;
   if (ctx) cudaSetDevice(ctx->device);
-  cudaFree(idx->text); cudaFree(idx->keys); cudaFree(idx->pos); cudaFree(idx->dir_lo); cudaFree(idx->dir_hi);
+  cudaFree(idx->text); cudaFree(idx->rec); cudaFree(idx->dir);
   delete idx;
   return TB_OK;
 }
@@ -979,27 +978,32 @@ int tb_index_build(tb_ctx* ctx, const char* text, int64_t text_len, int32_t mem,
   tb_index* X = new (std::nothrow) tb_index();
   if (!X) return fail(ctx, TB_ERR_NOMEM, "out of host memory");
   X->device = ctx->device; X->n = n;
-  unsigned long long* keys_in = nullptr; unsigned* pos_in = nullptr; void* temp = nullptr; int* d_invalid = nullptr;
+  unsigned long long *keys_a = nullptr, *keys_b = nullptr; unsigned *pos_a = nullptr, *pos_b = nullptr; void* temp = nullptr; int* d_invalid = nullptr;
   size_t temp_bytes = 0;
-  const unsigned nd = tb::index_dir_entries();
-  auto cleanup = [&](int rc) { cudaFree(keys_in); cudaFree(pos_in); cudaFree(temp); cudaFree(d_invalid); if (rc != TB_OK) { tb_index_destroy(ctx, X); } return rc; };
+  X->dir_chars = tb::index_dir_chars(n);
+  const size_t nd = (size_t)1 << (2 * X->dir_chars);
+  auto cleanup = [&](int rc) {
+    cudaFree(keys_a); cudaFree(pos_a); cudaFree(keys_b); cudaFree(pos_b); cudaFree(temp); cudaFree(d_invalid);
+    if (rc != TB_OK) tb_index_destroy(ctx, X);
+    return rc;
+  };
 #define TB_IDX(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cleanup(cuda_fail(ctx, e__, #call)); } while (0)
   TB_IDX(tb::index_sort_temp_bytes(n, &temp_bytes));
   TB_IDX(cudaMalloc(&X->text, (size_t)n + 64));
-  TB_IDX(cudaMalloc(&X->keys, (size_t)n * 8)); TB_IDX(cudaMalloc(&X->pos, (size_t)n * 4));
-  TB_IDX(cudaMalloc(&X->dir_lo, (size_t)nd * 4)); TB_IDX(cudaMalloc(&X->dir_hi, (size_t)nd * 4));
-  TB_IDX(cudaMalloc(&keys_in, (size_t)n * 8)); TB_IDX(cudaMalloc(&pos_in, (size_t)n * 4));
+  TB_IDX(cudaMalloc(&X->rec, (size_t)n * 16)); TB_IDX(cudaMalloc(&X->dir, nd * 8));
+  TB_IDX(cudaMalloc(&keys_a, (size_t)n * 8)); TB_IDX(cudaMalloc(&pos_a, (size_t)n * 4));
+  TB_IDX(cudaMalloc(&keys_b, (size_t)n * 8)); TB_IDX(cudaMalloc(&pos_b, (size_t)n * 4));
   TB_IDX(cudaMalloc(&temp, temp_bytes ? temp_bytes : 1)); TB_IDX(cudaMalloc(&d_invalid, 4));
   TB_IDX(cudaMemcpyAsync(X->text, text, (size_t)n, mem == TB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
   if (mem == TB_MEM_HOST) ctx->h2d += (size_t)n;
-  TB_IDX(tb::index_build(X->text, n, keys_in, pos_in, X->keys, X->pos, temp, temp_bytes, X->dir_lo, X->dir_hi, d_invalid, st));
-  ctx->launches += 3;
+  TB_IDX(tb::index_build(X->text, n, keys_a, pos_a, keys_b, pos_b, temp, temp_bytes, X->rec, X->dir, X->dir_chars, d_invalid, st));
+  ctx->launches += 4;
   int invalid = 0;
   TB_IDX(cudaMemcpyAsync(&invalid, d_invalid, 4, cudaMemcpyDeviceToHost, st));
   TB_IDX(cudaStreamSynchronize(st));
 #undef TB_IDX
   if (invalid) return cleanup(fail(ctx, TB_ERR_UNSUPPORTED, "text holds a byte outside ACGTN, the IUPAC codes RYSWKMBDHV and '\\n'"));
-  X->bytes = (size_t)n * 13 + (size_t)nd * 8;
+  X->bytes = (size_t)n * 17 + nd * 8;
   *out = X;
   return cleanup(TB_OK);
 }
@@ -1083,7 +1087,7 @@ int tb_anchor(tb_ctx* ctx, const tb_index* idx, const tb_arena* cons, size_t ntr
     if (hlen[i] < 0 || hlen[i] > 65535) return fail(ctx, TB_ERR_UNSUPPORTED, "consensus length outside 0..65535 (the reference scans with a uint16 index)");
     maxlen = std::max(maxlen, hlen[i]);
   }
-  tb::KmerIndexView X{idx->keys, idx->pos, idx->n, idx->dir_lo, idx->dir_hi};
+  tb::KmerIndexView X{idx->rec, idx->n, idx->dir, idx->dir_chars};
   tb::AnchorBatch A{};
   A.trim_left = cfg.trim_left; A.trim_right = cfg.trim_right; A.kmer = cfg.kmer; A.min_support = cfg.min_kmer_support;
   Staged S(st);

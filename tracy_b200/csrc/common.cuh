@@ -64,8 +64,10 @@ struct BasecallBatch {
 
 // Device view of the sorted k-mer index and of an anchoring batch (anchor.cu).
 struct KmerIndexView {
-  const unsigned long long* keys; const unsigned* pos; long long n;
-  const unsigned* dir_lo; const unsigned* dir_hi;
+  const uint4* rec;       // sorted records {key low, key high, text position, 0}
+  long long n;
+  const uint2* dir;       // [4^dir_chars] record range [x, y) per A/C/G/T prefix
+  int dir_chars;
 };
 struct AnchorBatch {
   const char* cons_base; const int64_t* cons_off; const int32_t* cons_len;

@@ -9,14 +9,6 @@ from test_anchor import COMP, api_revcomp, expected, load_anchor_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
-    import tracy_b200
-    c = tracy_b200.Context(0)
-    yield c
-    c.close()
-
-
 def test_anchor_matches_reference_goldens(ctx):
     g = load_anchor_golden()
     idx = ctx.build_index(g["text"])
@@ -113,3 +105,32 @@ def test_index_rejects_foreign_bytes(ctx):
             ctx.anchor(idx, [b"ACGTACGTACGTACGTACGT"], 0, 0, 17, 3)      # kmer beyond the index depth
         finally:
             idx.close()
+
+
+def test_align_genome_batch_golden(ctx):
+    """samples -> basecall -> createProfile -> anchor -> gotoh -> trimReferenceSlice -> gotoh, all through the library,
+    against sage() for an indexed genome composed from the reference's own functions (make_golden_align_genome.py)."""
+    import os
+    from conftest import ROOT
+    from tracy_b200 import DnaScore, drivers
+    G = np.load(os.path.join(ROOT, "tests", "golden", "align_genome_golden.npz"))
+    n = int(G["n"])
+    tl, trr, kmer, maxindel, ms = (int(x) for x in G["cfg"])
+    text = bytes(G["text"])
+    seqs = text[:-1].split(b"\n")
+    traces, ploc = [G[f"tr{i}"] for i in range(n)], [G[f"ploc{i}"] for i in range(n)]
+    bc = ctx.basecall(traces, ploc, 0.33)
+    args = ([b["bcPos"] for b in bc], [b["primary"] for b in bc], [b["secondary"] for b in bc])
+    full = ctx.create_profile(traces, *args, trim_left=0, trim_right=0)
+    trimmed = ctx.create_profile(traces, *args, trim_left=tl, trim_right=trr)
+    idx = ctx.build_index(text)
+    res = drivers.align_genome_batch(ctx, idx, seqs, [b["consensus"] for b in bc], trimmed, full, DnaScore(3, -5, -10, -4), tl, trr, kmer, ms, maxindel)
+    idx.close()
+    for i, r in enumerate(res):
+        if not int(G[f"ok{i}"]):
+            assert r is None, i
+            continue
+        assert r is not None, i
+        assert [int(r["forward"]), r["chr"], r["kmersupport"], r["pos"], r["score"]] == [int(x) for x in G[f"meta{i}"]], i
+        for k in ("refslice", "row0", "row1"):
+            assert r[k] == bytes(G[f"{k}{i}"]), (i, k)

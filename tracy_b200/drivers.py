@@ -1,6 +1,7 @@
 """Batch drivers: the DP sequences of tracy's subcommand drivers, run for MANY traces at once.
 
   align_batch      sage()     for single-FASTA references   reference src/sage.h:222-260, :311
+  align_genome_batch  sage()  for an indexed genome         reference src/sage.h:216-222, :258-260, :311; src/fmindex.h:236-326
   decompose_batch  indigo()   for single-FASTA references   reference src/indigo.h:190-388
   assemble_denovo  assemble() de novo branch                reference src/assemble.h:418-471
 
@@ -12,7 +13,7 @@ host logic of tracy_b200.api / tracy_b200.msa. File formats, basecalling and the
 import numpy as np
 
 from . import decompose, msa
-from .api import PS, SS, AlignConfig, DnaScore, find_breakpoint, rows_from_ops, trim_reference_slice
+from .api import PS, SS, AlignConfig, DnaScore, find_breakpoint, reference_slice, rows_from_ops, trim_reference_slice
 
 _SEMIGLOBAL = AlignConfig(True, False)          # AlignConfig<true, false>, src/sage.h:165
 _COMP = {ord("A"): ord("T"), ord("C"): ord("G"), ord("G"): ord("C"), ord("T"): ord("A"), ord("N"): ord("N")}
@@ -64,6 +65,43 @@ def align_batch(ctx, trimmed_profiles, full_profiles, references, sc=DnaScore(3,
     for i in range(n):
         row0, row1 = rows_from_ops(PS, full_profiles[i], slices[i], bytes(ops2[i, : ol2[i]]))
         out.append(dict(forward=forward[i], refslice=slices[i], pos=pos[i], score=int(score[i]), row0=row0, row1=row1))
+    return out
+
+
+def align_genome_batch(ctx, index, seqs, consensus, trimmed_profiles, full_profiles, sc=DnaScore(3, -5, -10, -4), trim_left=50,
+                       trim_right=50, kmer=15, min_kmer_support=3, maxindel=1000):
+    """`tracy align` against an INDEXED GENOME for a batch of traces (reference src/sage.h:216-222, :258-260, :311).
+
+    index: Context.build_index over b"\n".join(seqs) + b"\n" (what `tracy index` dumps); seqs: the genome's sequences;
+    consensus: BaseCalls::consensus per trace; trimmed_profiles / full_profiles as in align_batch.
+    getReferenceSlice (k-mer anchoring on the GPU, then the slice arithmetic and htslib's inclusive fetch), the semi-global
+    alignment of the trimmed trace, trimReferenceSlice and the final alignment. Returns one dict per trace, or None where
+    the reference prints "Couldn't anchor the Sanger trace" and gives up."""
+    n = len(consensus)
+    a = ctx.anchor(index, consensus, trim_left, trim_right, kmer, min_kmer_support)
+    seqlen = [len(x) + 1 for x in seqs]                                    # src/fmindex.h:247
+    live, pref, meta = [], [], []
+    for i in range(n):
+        if not a["anchored"][i]:
+            continue
+        ri, _, s0, s1 = reference_slice(int(a["bestpos"][i]), seqlen, len(consensus[i]), maxindel)
+        sl = bytes(seqs[ri][s0: min(s1, len(seqs[ri]) - 1) + 1]).upper()   # faidx_fetch_seq is end-inclusive; to_upper_copy :302
+        fw = bool(a["forward"][i])
+        live.append(i); pref.append(sl if fw else reverse_complement_seq(sl)); meta.append((ri, s0, fw))
+    out = [None] * n
+    if not live:
+        return out
+    _, ops, ol = ctx.gotoh(PS, [trimmed_profiles[i] for i in live], pref, sc, _SEMIGLOBAL)
+    slices, pos = [], []
+    for j, i in enumerate(live):
+        r0, r1 = _gap_rows(ops[j, : ol[j]])
+        sl, p = trim_reference_slice(r0, r1, pref[j], meta[j][2], meta[j][1], trim_left, trim_right)
+        slices.append(sl); pos.append(p)
+    score, ops2, ol2 = ctx.gotoh(PS, [full_profiles[i] for i in live], slices, sc, _SEMIGLOBAL)
+    for j, i in enumerate(live):
+        row0, row1 = rows_from_ops(PS, full_profiles[i], slices[j], bytes(ops2[j, : ol2[j]]))
+        out[i] = dict(forward=meta[j][2], chr=meta[j][0], kmersupport=int(a["kmersupport"][i]), refslice=slices[j], pos=pos[j],
+                      score=int(score[j]), row0=row0, row1=row1)
     return out
 
 

@@ -231,6 +231,23 @@ int tb_ctx_last_anchor_ms(const tb_ctx* ctx, float* unique_ms);
 int tb_reference_slice(int64_t bestpos, const uint32_t* seqlen, int32_t nseq, int32_t conslen, int32_t maxindel,
                        int32_t* refindex, uint32_t* chrpos, uint32_t* slicestart, uint32_t* sliceend);
 
+/* allelicFraction(c, tr, bc), reference src/decompose.h:412-617, for a batch of traces (GPU, FP64, bit-exact): the
+ * fractions (bestI, bestJ) of the two alleles fitted to the peak heights at the positions where primary and secDecompose
+ * differ, by the reference's exhaustive 0.01-grid search (first grid point in i-j-k order with the smallest squared error;
+ * (0.5, 0.5) when nothing beats that start value). trace / bcpos as in tb_create_profile; primary and secdecompose share
+ * bcpos' off/len (BaseCalls::primary, BaseCalls::secDecompose after generateSecondaryDecomposed). */
+typedef struct {
+  tb_arena trace;
+  tb_arena bcpos;
+  const char* primary_base;
+  const char* secdecompose_base;
+  int32_t trim_left, trim_right;   /* c.trimLeft, c.trimRight */
+  size_t ntraces;
+  int32_t mem;
+} tb_fraction_batch;
+int tb_allelic_fraction(tb_ctx* ctx, const tb_fraction_batch* batch, double* a1, double* a2);
+int tb_ctx_last_fraction_ms(const tb_ctx* ctx, float* ms);
+
 const char* tb_version(void);
 
 #ifdef __cplusplus

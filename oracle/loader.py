@@ -200,6 +200,14 @@ class _Ref:
                                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.c_char_p, C.c_int]
         L.ref_get_reference_slice.restype = C.c_int
 
+    def allelic_fraction(self, acgt, bcpos, primary, secdecompose, trim_left, trim_right):
+        """allelicFraction(c, tr, bc), src/decompose.h:412-617 -> (bestI, bestJ)."""
+        acgt = np.ascontiguousarray(acgt, np.int32); bcpos = np.ascontiguousarray(bcpos, np.int32)
+        a, b = C.c_double(0), C.c_double(0)
+        self.lib.ref_allelic_fraction.argtypes = [_i32p, C.c_int, _i32p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        self.lib.ref_allelic_fraction(acgt.reshape(-1), acgt.shape[1], bcpos, bytes(primary), bytes(secdecompose), len(bcpos), trim_left, trim_right, C.byref(a), C.byref(b))
+        return a.value, b.value
+
     # ---- anchoring: the reference's sdsl FM-index and src/fmindex.h:173-326 ----
     def fm_build(self, text):
         """construct_im(csa_wt<>, text, 1) -> opaque handle (free with fm_free)."""

@@ -332,6 +332,21 @@ long long ref_bench_gotoh_ps(const float* profs, const char* seqs, int npairs, i
 }
 
 
+// allelicFraction(c, tr, bc), src/decompose.h:412-617
+void ref_allelic_fraction(const int32_t* acgt, int nsamples, const int32_t* bcpos, const char* primary, const char* secdecompose, int nbc,
+                          int trimLeft, int trimRight, double* a1, double* a2) {
+  tracy::Trace tr;
+  tr.traceACGT.resize(4);
+  for (int k = 0; k < 4; ++k) tr.traceACGT[k].assign(acgt + (size_t)k * nsamples, acgt + (size_t)(k + 1) * nsamples);
+  tracy::BaseCalls bc;
+  bc.bcPos.assign(bcpos, bcpos + nbc);
+  bc.primary = std::string(primary, primary + nbc);
+  bc.secDecompose = std::string(secdecompose, secdecompose + nbc);
+  SweepCfg c; c.trimLeft = trimLeft; c.trimRight = trimRight; c.maxindel = 0; c.madc = 0;
+  std::pair<double, double> r = tracy::allelicFraction(c, tr, bc);
+  *a1 = r.first; *a2 = r.second;
+}
+
 // ---- anchoring: the reference's FM-index (sdsl csa_wt, as src/sage.h / src/indigo.h declare it) ---------------------
 struct AnchorCfg { boost::filesystem::path genome; uint16_t trimLeft, trimRight, kmer, maxindel, minKmerSupport; };
 void* ref_fm_build(const char* text, long long n) {

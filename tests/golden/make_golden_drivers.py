@@ -71,6 +71,8 @@ def reference_decompose(ref, tr, pos, pri, sec, refseq, tl, trr, maxindel, madc)
     def tseq(s):
         return s if tl + trr + 1 >= len(s) else s[tl: len(s) - trr]
     out = dict(forward=fw, refslice=rsl, score=score, row0=r0, row1=r1, bp=np.array(bp, np.float64), primary=p2, secondary=s2, secDecompose=sd, decomp=dcp)
+    # allelicFraction (src/indigo.h:350); short reads that trimmedSeq() leaves untrimmed index bcPos out of bounds in the reference
+    out["frac"] = np.array(ref.allelic_fraction(tr, pos, p2, sd, tl, trr) if tl + trr + 1 < len(p2) else (0.5, 0.5), np.float64)
     for name, q in (("align1", tseq(p2)), ("align2", tseq(sd))):
         _, a0, a1 = ref.gotoh(q, rsl, 1, 0, SC)
         sl, npos = ref.trim_reference_slice(a0, a1, rsl, fw, 0, tl, trr)
@@ -110,6 +112,7 @@ def main():
         for k in ("refslice", "row0", "row1", "primary", "secondary", "secDecompose"):
             d[f"{k}{i}"] = np.frombuffer(want[k], np.uint8)
         d[f"decomp{i}"] = want["decomp"].astype(np.int32)
+        d[f"frac{i}"] = want["frac"]
         for name in ("align1", "align2", "align3"):
             sc_, a0, a1, sl, npos = want[name]
             d[f"{name}_s{i}"] = np.array([sc_, npos], np.int64)

@@ -36,6 +36,7 @@ def test_decompose_batch_golden(ctx, capsys):
             for k in ("refslice", "row0", "row1", "primary", "secondary", "secDecompose"):
                 assert r[k] == bytes(G[f"{k}{i}"]), (i, k)
             assert np.array_equal(r["decomp"], G[f"decomp{i}"]), i
+            assert np.array(r["allele_fractions"], np.float64).tobytes() == G[f"frac{i}"].tobytes(), (i, r["allele_fractions"], G[f"frac{i}"])
             for name in ("align1", "align2", "align3"):
                 a = r[name]
                 assert [a["score"], a["pos"]] == [int(x) for x in G[f"{name}_s{i}"]], (i, name)

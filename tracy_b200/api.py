@@ -276,6 +276,25 @@ class Context:
         self._check(self._lib.tb_create_profile(self._h, C.byref(b), _ptr(out), _ptr(ooff), _ptr(olen)))
         return [out[ooff[i]: ooff[i] + 6 * olen[i]].reshape(6, olen[i]).copy() for i in range(n)]
 
+    def allelic_fraction(self, traces, bcpos, primary, secdecompose, trim_left=50, trim_right=50):
+        """allelicFraction(c, tr, bc) for a batch (reference src/decompose.h:412-617) -> float64[N][2] = (bestI, bestJ)."""
+        n = len(traces)
+        tr = [np.ascontiguousarray(t, np.int32) for t in traces]
+        bp = [np.ascontiguousarray(b, np.int32) for b in bcpos]
+        tlen = np.array([t.shape[1] for t in tr], np.int32)
+        toff = np.concatenate([[0], np.cumsum(4 * tlen.astype(np.int64))[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        tbase = np.concatenate([t.reshape(-1) for t in tr]) if n else np.zeros(1, np.int32)
+        pri, sec = pack_seqs(primary), pack_seqs(secdecompose)
+        blen = np.array([len(b) for b in bp], np.int32)
+        if not (np.array_equal(pri.len, blen) and np.array_equal(sec.len, blen)):
+            raise ValueError("bcpos, primary and secdecompose must have one entry per basecall")
+        bbase = np.concatenate(bp) if n and blen.sum() else np.zeros(1, np.int32)
+        out = np.zeros((2, max(n, 1)), np.float64)
+        b = capi.FractionBatch(capi.Arena(_ptr(tbase), _ptr(toff), _ptr(tlen)), capi.Arena(_ptr(bbase), _ptr(pri.off), _ptr(blen)),
+                               _ptr(pri.base), _ptr(sec.base), trim_left, trim_right, n, capi.TB_MEM_HOST)
+        self._check(self._lib.tb_allelic_fraction(self._h, C.byref(b), _ptr(out[0]), _ptr(out[1])))
+        return np.ascontiguousarray(out[:, :n].T)
+
     def basecall(self, traces, ploc, sigratio=0.33):
         """basecall(Trace, BaseCalls, sigratio) for a batch (reference src/abif.h:408-511). traces: list of int32[4][nsamples];
         ploc: the trace files' basecall positions (Trace::basecallpos). Returns a list of dicts bcPos / primary / secondary /

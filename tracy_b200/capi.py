@@ -15,7 +15,7 @@ SYMBOLS = [
     "tb_ctx_set_scratch_limit", "tb_ctx_stats", "tb_ctx_last_kernel_ms", "tb_ctx_last_call_ms", "tb_ctx_last_packed_pairs", "tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss",
     "tb_rows_from_ops", "tb_decompose_sweep", "tb_version", "tb_create_profile", "tb_revcomp_profile", "tb_trim_reference_slice",
     "tb_find_breakpoint", "tb_basecall", "tb_index_build", "tb_index_destroy", "tb_index_info", "tb_anchor", "tb_ctx_last_anchor_ms",
-    "tb_reference_slice",
+    "tb_reference_slice", "tb_allelic_fraction", "tb_ctx_last_fraction_ms",
 ]
 
 
@@ -64,6 +64,11 @@ class AnchorConfig(C.Structure):
 
 class AnchorResult(C.Structure):
     _fields_ = [("anchored", C.c_void_p), ("forward", C.c_void_p), ("kmersupport", C.c_void_p), ("bestpos", C.c_void_p), ("pass_", C.c_void_p)]
+
+
+class FractionBatch(C.Structure):
+    _fields_ = [("trace", Arena), ("bcpos", Arena), ("primary_base", C.c_void_p), ("secdecompose_base", C.c_void_p),
+                ("trim_left", C.c_int32), ("trim_right", C.c_int32), ("ntraces", C.c_size_t), ("mem", C.c_int32)]
 
 
 class LibraryMissing(RuntimeError):
@@ -115,5 +120,7 @@ def lib():
     L.tb_ctx_last_anchor_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.tb_reference_slice.argtypes = [C.c_int64, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32),
                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.tb_allelic_fraction.argtypes = [vp, C.POINTER(FractionBatch), vp, vp]
+    L.tb_ctx_last_fraction_ms.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = L
     return L

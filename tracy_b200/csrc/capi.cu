@@ -25,6 +25,7 @@ unsigned long long gotoh_packed_ptr_words(int m, int n);
 
 
 cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
+cudaError_t launch_allelic_fraction(const FractionBatch& F, int ntraces, int maxD, cudaStream_t st);
 cudaError_t index_sort_temp_bytes(long long n, size_t* bytes);
 cudaError_t index_build(const unsigned char* text, long long n, unsigned long long* keys_a, unsigned* pos_a, unsigned long long* keys_b,
                         unsigned* pos_b, void* temp, size_t temp_bytes, uint4* rec, uint2* dir, int dir_chars, int* invalid, cudaStream_t st);
@@ -102,7 +103,7 @@ struct tb_ctx {
   Lane lanes[kLanes];
   cudaEvent_t t0 = nullptr;   // start of a host-mode call (timeline origin for TRACY_B200_TRACE)
   uint64_t launches = 0, h2d = 0, d2h = 0;
-  float last_fast_ms = 0, last_general_ms = 0, last_sweep_ms = 0, last_call_ms = 0, last_anchor_ms = 0;
+  float last_fast_ms = 0, last_general_ms = 0, last_sweep_ms = 0, last_call_ms = 0, last_anchor_ms = 0, last_fraction_ms = 0;
   uint64_t last_packed_pairs = 0;
   std::vector<int32_t> tmp_len1, tmp_len2;
 };
@@ -1169,5 +1170,88 @@ int tb_reference_slice(int64_t bestpos, const uint32_t* seqlen, int32_t nseq, in
   if (tmpend < seqlen[ri]) s1 = tmpend;
   *refindex = ri; *slicestart = s0; *sliceend = s1;
   if (chrpos_out) *chrpos_out = chrpos;
+  return TB_OK;
+}
+
+// ---- allelicFraction (kernel in fraction.cu) ---------------------------------------------
+int tb_allelic_fraction(tb_ctx* ctx, const tb_fraction_batch* b, double* a1, double* a2) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (!b || !a1 || !a2) return fail(ctx, TB_ERR_INVALID, "null batch/output");
+  const size_t nt = b->ntraces;
+  if (nt == 0) return TB_OK;
+  if (nt > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "ntraces too large");
+  if (!b->trace.base || !b->trace.off || !b->trace.len || !b->bcpos.base || !b->bcpos.off || !b->bcpos.len || !b->primary_base || !b->secdecompose_base)
+    return fail(ctx, TB_ERR_INVALID, "null pointer in fraction batch");
+  if (b->trim_left < 0 || b->trim_right < 0) return fail(ctx, TB_ERR_INVALID, "negative trim");
+  if (b->mem != TB_MEM_HOST && b->mem != TB_MEM_DEVICE) return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST or TB_MEM_DEVICE");
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->lanes[0].stream;
+  // the grid values exactly as `for (double i = 0; i <= 1; i += 0.01)` produces them (src/decompose.h:581-585)
+  std::vector<double> grid;
+  for (double v = 0; v <= 1; v += 0.01) grid.push_back(v);
+  if (grid.size() > 101) return fail(ctx, TB_ERR_CUDA, "unexpected grid length");
+  std::vector<int32_t> hl;
+  const int32_t* bl = b->bcpos.len;
+  const int32_t* tl = b->trace.len;
+  std::vector<int32_t> hl2;
+  if (b->mem == TB_MEM_DEVICE) {
+    hl.resize(nt); hl2.resize(nt);
+    TB_CUDA(ctx, cudaMemcpy(hl.data(), b->bcpos.len, nt * 4, cudaMemcpyDeviceToHost));
+    TB_CUDA(ctx, cudaMemcpy(hl2.data(), b->trace.len, nt * 4, cudaMemcpyDeviceToHost));
+    bl = hl.data(); tl = hl2.data();
+  }
+  int maxD = 1;
+  for (size_t i = 0; i < nt; ++i) {
+    if (bl[i] < 0 || tl[i] < 0 || (bl[i] > 0 && tl[i] == 0)) return fail(ctx, TB_ERR_INVALID, "negative length / empty trace");
+    maxD = std::max(maxD, bl[i]);
+  }
+  if ((size_t)4 * maxD * 9 + 16 > 200 * 1024) return fail(ctx, TB_ERR_UNSUPPORTED, "more than 5600 basecalls in one trace");
+  Staged S(st);
+  tb::FractionBatch F{};
+  F.trim_left = b->trim_left; F.trim_right = b->trim_right; F.ngrid = (int)grid.size();
+  void *d_grid, *d_status;
+  TB_CUDA(ctx, S.up(&d_grid, grid.data(), grid.size() * 8));
+  TB_CUDA(ctx, S.alloc(&d_status, nt));
+  F.grid = (const double*)d_grid; F.status = (uint8_t*)d_status;
+  if (b->mem == TB_MEM_DEVICE) {
+    F.trace_base = (const int32_t*)b->trace.base; F.trace_off = b->trace.off; F.trace_len = b->trace.len;
+    F.bcpos_base = (const int32_t*)b->bcpos.base; F.bc_off = b->bcpos.off; F.bc_len = b->bcpos.len;
+    F.pri_base = b->primary_base; F.sec_base = b->secdecompose_base; F.a1 = a1; F.a2 = a2;
+  } else {
+    long long tmax = 0, bmax = 0;
+    for (size_t i = 0; i < nt; ++i) {
+      if (b->trace.off[i] < 0 || b->bcpos.off[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative offset");
+      tmax = std::max<long long>(tmax, b->trace.off[i] + 4ll * tl[i]);
+      bmax = std::max<long long>(bmax, b->bcpos.off[i] + bl[i]);
+    }
+    void *d_tr, *d_bp, *d_pri, *d_sec, *d_toff, *d_tlen, *d_boff, *d_blen, *d_a1, *d_a2;
+    TB_CUDA(ctx, S.up(&d_tr, b->trace.base, (size_t)std::max(tmax, 1ll) * 4)); TB_CUDA(ctx, S.up(&d_bp, b->bcpos.base, (size_t)std::max(bmax, 1ll) * 4));
+    TB_CUDA(ctx, S.up(&d_pri, b->primary_base, (size_t)std::max(bmax, 1ll))); TB_CUDA(ctx, S.up(&d_sec, b->secdecompose_base, (size_t)std::max(bmax, 1ll)));
+    TB_CUDA(ctx, S.up(&d_toff, b->trace.off, nt * 8)); TB_CUDA(ctx, S.up(&d_tlen, b->trace.len, nt * 4));
+    TB_CUDA(ctx, S.up(&d_boff, b->bcpos.off, nt * 8)); TB_CUDA(ctx, S.up(&d_blen, b->bcpos.len, nt * 4));
+    TB_CUDA(ctx, S.alloc(&d_a1, nt * 8)); TB_CUDA(ctx, S.alloc(&d_a2, nt * 8));
+    ctx->h2d += (size_t)tmax * 4 + (size_t)bmax * 6 + nt * 24;
+    F.trace_base = (const int32_t*)d_tr; F.trace_off = (const int64_t*)d_toff; F.trace_len = (const int32_t*)d_tlen;
+    F.bcpos_base = (const int32_t*)d_bp; F.bc_off = (const int64_t*)d_boff; F.bc_len = (const int32_t*)d_blen;
+    F.pri_base = (const char*)d_pri; F.sec_base = (const char*)d_sec; F.a1 = (double*)d_a1; F.a2 = (double*)d_a2;
+  }
+  Lane& L = ctx->lanes[0];
+  TB_CUDA(ctx, cudaEventRecord(L.k0, st));
+  TB_CUDA(ctx, tb::launch_allelic_fraction(F, (int)nt, maxD, st));
+  ctx->launches++;
+  TB_CUDA(ctx, cudaEventRecord(L.k1, st));
+  if (b->mem == TB_MEM_HOST) {
+    TB_CUDA(ctx, cudaMemcpyAsync(a1, F.a1, nt * 8, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaMemcpyAsync(a2, F.a2, nt * 8, cudaMemcpyDeviceToHost, st));
+    ctx->d2h += nt * 16;
+  }
+  TB_CUDA(ctx, cudaStreamSynchronize(st));
+  TB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_fraction_ms, L.k0, L.k1));
+  return TB_OK;
+}
+
+int tb_ctx_last_fraction_ms(const tb_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return TB_ERR_INVALID;
+  *ms = ctx->last_fraction_ms;
   return TB_OK;
 }

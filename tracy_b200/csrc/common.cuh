@@ -62,6 +62,15 @@ struct BasecallBatch {
   float sigratio;
 };
 
+// Device view of an allelicFraction batch (fraction.cu).
+struct FractionBatch {
+  const int32_t* trace_base; const int64_t* trace_off; const int32_t* trace_len;   // item = int32[4][nsamples]
+  const int32_t* bcpos_base; const char* pri_base; const char* sec_base; const int64_t* bc_off; const int32_t* bc_len;
+  int trim_left, trim_right;
+  const double* grid; int ngrid;                                                    // 0, 0.01, ... as the reference's loop accumulates them
+  double* a1; double* a2; uint8_t* status;
+};
+
 // Device view of the sorted k-mer index and of an anchoring batch (anchor.cu).
 struct KmerIndexView {
   const uint4* rec;       // sorted records {key low, key high, text position, 0}

@@ -215,6 +215,16 @@ def decompose_batch(ctx, traces, bcpos, primaries, secondaries, references, sc=D
     if not live:
         return out
     # allele-specific alignments (src/indigo.h:355-388): string x string, two semi-global rounds and one global
+    # allelicFraction (src/indigo.h:350): the 0.01-grid fit of the two alleles' signal shares, one GPU call for all traces;
+    # the reference indexes bcPos[i + trimLeft] even when trimmedSeq() left a short read untrimmed (out of bounds there), so
+    # such reads keep the start value
+    fit = [i for i in live if trim_left + trim_right + 1 < len(out[i]["primary"])]
+    fr = ctx.allelic_fraction([traces[i] for i in fit], [bcpos[i] for i in fit], [out[i]["primary"] for i in fit],
+                              [out[i]["secDecompose"] for i in fit], trim_left, trim_right) if fit else []
+    for i in live:
+        out[i]["allele_fractions"] = (0.5, 0.5)
+    for i, f in zip(fit, fr):
+        out[i]["allele_fractions"] = (float(f[0]), float(f[1]))
     pris = [trimmed_seq(out[i]["primary"], trim_left, trim_right) for i in live]
     secs = [trimmed_seq(out[i]["secDecompose"], trim_left, trim_right) for i in live]
     refl = [out[i]["refslice"] for i in live]

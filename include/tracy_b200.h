@@ -248,6 +248,29 @@ typedef struct {
 int tb_allelic_fraction(tb_ctx* ctx, const tb_fraction_batch* batch, double* a1, double* a2);
 int tb_ctx_last_fraction_ms(const tb_ctx* ctx, float* ms);
 
+/* ---- trace-file ingest: traceFormat / readab / readscf, reference src/scf.h:19-35, src/abif.h:286-405, src/scf.h:38-102 ----
+ * `files` is a HOST buffer holding the bytes of nfiles trace files (file i = files[off[i] .. off[i]+len[i])).
+ * tb_trace_scan walks the directories only (host) so that the caller can size the outputs; tb_trace_unpack ships the raw
+ * bytes to the GPU and decodes there (big-endian int16 -> int32, FWO_ channel order, SCF 3.x delta-delta decoding).
+ * Outputs per file, laid out as tb_basecall / tb_create_profile read them: samples int32[4][nsamples] at samples_off[i]
+ * (channels A,C,G,T = Trace::traceACGT), and at bc_off[i] nbasecalls entries each of Trace::basecallpos (int32), Trace::qual,
+ * Trace::basecalls1 and Trace::basecalls2 (replaceNonDna applied; '\0' padding where the file has no such string, as
+ * std::string::resize leaves it). Files with format < 0 or status != 0 are skipped by tb_trace_unpack. */
+enum { TB_TRACE_OK = 0, TB_TRACE_TRUNCATED = 1, TB_TRACE_DUPLICATE = 2, TB_TRACE_RAGGED = 3 };
+typedef struct {
+  int32_t format;       /* traceFormat(): 0 ABIF, 1 SCF, -1 unknown */
+  int32_t ok;           /* what readab() / readscf() return (0: "File lacks basecalls!", SCF below 3.0, ...) */
+  int32_t status;       /* TB_TRACE_OK, or why this library will not unpack the file: directory or data beyond the end of the
+                           file, a record the reference would append twice, channels of different lengths */
+  int32_t nsamples;     /* per channel */
+  int32_t nbasecalls;   /* after the reference cut every per-base vector to the shortest one (src/abif.h:379-388) */
+} tb_trace_info;
+int tb_trace_scan(const uint8_t* files, const int64_t* off, const int64_t* len, size_t nfiles, tb_trace_info* info);
+/* out_mem says where samples / ploc / qual / basecalls1 / basecalls2 live; off, len, samples_off, bc_off are host arrays. */
+int tb_trace_unpack(tb_ctx* ctx, const uint8_t* files, const int64_t* off, const int64_t* len, size_t nfiles, int32_t out_mem,
+                    int32_t* samples, const int64_t* samples_off, int32_t* ploc, uint8_t* qual, char* basecalls1, char* basecalls2,
+                    const int64_t* bc_off);
+
 const char* tb_version(void);
 
 #ifdef __cplusplus

@@ -200,6 +200,27 @@ class _Ref:
                                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.c_char_p, C.c_int]
         L.ref_get_reference_slice.restype = C.c_int
 
+    def read_trace(self, path):
+        """traceFormat + readab / readscf on a file -> dict(format, ok, samples [list of 4 int32 arrays], basecallpos, qual, basecalls1, basecalls2)."""
+        L = self.lib
+        L.ref_trace_load.argtypes = [C.c_char_p] + [C.POINTER(C.c_int)] * 6
+        L.ref_trace_load.restype = C.c_int
+        fmt, nb, n1, n2, nq = (C.c_int(0) for _ in range(5))
+        ns4 = (C.c_int * 4)()
+        ok = L.ref_trace_load(os.fsencode(path), C.byref(fmt), ns4, C.byref(nb), C.byref(n1), C.byref(n2), C.byref(nq))
+        ns = [int(x) for x in ns4]
+        samples = np.zeros(max(sum(ns), 1), np.int32)
+        ploc = np.zeros(max(nb.value, 1), np.int32)
+        qual = np.zeros(max(nq.value, 1), np.uint8)
+        b1, b2 = C.create_string_buffer(n1.value + 1), C.create_string_buffer(n2.value + 1)
+        L.ref_trace_get.argtypes = [_i32p, _i32p, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_char_p, C.c_char_p]
+        L.ref_trace_get(samples, ploc, qual, b1, b2)
+        chans, o = [], 0
+        for k in range(4):
+            chans.append(samples[o:o + ns[k]].copy()); o += ns[k]
+        return dict(format=fmt.value, ok=bool(ok), samples=chans, basecallpos=ploc[:nb.value].copy(), qual=qual[:nq.value].copy(),
+                    basecalls1=b1.raw[:n1.value], basecalls2=b2.raw[:n2.value])
+
     def allelic_fraction(self, acgt, bcpos, primary, secdecompose, trim_left, trim_right):
         """allelicFraction(c, tr, bc), src/decompose.h:412-617 -> (bestI, bestJ)."""
         acgt = np.ascontiguousarray(acgt, np.int32); bcpos = np.ascontiguousarray(bcpos, np.int32)

@@ -332,6 +332,30 @@ long long ref_bench_gotoh_ps(const float* profs, const char* seqs, int npairs, i
 }
 
 
+// traceFormat / readab / readscf (src/scf.h:19-35, src/abif.h:286-405, src/scf.h:38-102) on a file path. The parsed Trace
+// is kept until the next load; ref_trace_get copies it out (channels [4][ns[0]] -- callers check the four sizes first).
+static tracy::Trace g_trace;
+int ref_trace_load(const char* path, int* format, int* ns4, int* nb, int* nb1, int* nb2, int* nq) {
+  g_trace = tracy::Trace();
+  *format = tracy::traceFormat(path);
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  bool ok = false;
+  if (*format == 0) ok = tracy::readab(path, g_trace);
+  else if (*format == 1) ok = tracy::readscf(path, g_trace);
+  std::cerr.rdbuf(old);
+  for (int k = 0; k < 4; ++k) ns4[k] = k < (int)g_trace.traceACGT.size() ? (int)g_trace.traceACGT[k].size() : 0;
+  *nb = (int)g_trace.basecallpos.size(); *nb1 = (int)g_trace.basecalls1.size(); *nb2 = (int)g_trace.basecalls2.size(); *nq = (int)g_trace.qual.size();
+  return ok ? 1 : 0;
+}
+void ref_trace_get(int32_t* samples, int32_t* ploc, uint8_t* qual, char* b1, char* b2) {
+  size_t o = 0;
+  for (size_t k = 0; k < g_trace.traceACGT.size(); ++k) { for (int32_t v : g_trace.traceACGT[k]) samples[o++] = v; }
+  for (size_t i = 0; i < g_trace.basecallpos.size(); ++i) ploc[i] = g_trace.basecallpos[i];
+  for (size_t i = 0; i < g_trace.qual.size(); ++i) qual[i] = g_trace.qual[i];
+  memcpy(b1, g_trace.basecalls1.data(), g_trace.basecalls1.size());
+  memcpy(b2, g_trace.basecalls2.data(), g_trace.basecalls2.size());
+}
+
 // allelicFraction(c, tr, bc), src/decompose.h:412-617
 void ref_allelic_fraction(const int32_t* acgt, int nsamples, const int32_t* bcpos, const char* primary, const char* secdecompose, int nbc,
                           int trimLeft, int trimRight, double* a1, double* a2) {

@@ -276,6 +276,39 @@ class Context:
         self._check(self._lib.tb_create_profile(self._h, C.byref(b), _ptr(out), _ptr(ooff), _ptr(olen)))
         return [out[ooff[i]: ooff[i] + 6 * olen[i]].reshape(6, olen[i]).copy() for i in range(n)]
 
+    def read_traces(self, files):
+        """traceFormat + readab / readscf for a batch of trace files given as bytes (reference src/scf.h:19-102, src/abif.h:286-405);
+        the samples are decoded on the GPU. Returns one dict per file: format, ok, status, traceACGT (int32[4][ns]), basecallpos,
+        qual, basecalls1, basecalls2 (None for files the library does not unpack)."""
+        n = len(files)
+        flen = np.array([len(f) for f in files], np.int64)
+        foff = np.concatenate([[0], np.cumsum(flen)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        blob = np.frombuffer(b"".join(bytes(f) for f in files) or b"\0", np.uint8)
+        info = (capi.TraceInfo * max(n, 1))()
+        rc = self._lib.tb_trace_scan(_ptr(blob), _ptr(foff), _ptr(flen), n, C.cast(info, C.c_void_p))
+        if rc != capi.TB_OK:
+            raise TracyError(rc, self._lib.tb_strerror(rc).decode())
+        live = [i for i in range(n) if info[i].format >= 0 and info[i].status == 0]
+        ns = np.array([info[i].nsamples if i in set(live) else 0 for i in range(n)], np.int64)
+        nb = np.array([info[i].nbasecalls if i in set(live) else 0 for i in range(n)], np.int64)
+        soff = np.concatenate([[0], np.cumsum(4 * ns)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        boff = np.concatenate([[0], np.cumsum(nb)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+        samples = np.zeros(max(int(4 * ns.sum()), 1), np.int32)
+        tot = max(int(nb.sum()), 1)
+        ploc, qual, b1, b2 = np.zeros(tot, np.int32), np.zeros(tot, np.uint8), np.zeros(tot, np.uint8), np.zeros(tot, np.uint8)
+        self._check(self._lib.tb_trace_unpack(self._h, _ptr(blob), _ptr(foff), _ptr(flen), n, capi.TB_MEM_HOST, _ptr(samples), _ptr(soff),
+                                              _ptr(ploc), _ptr(qual), _ptr(b1), _ptr(b2), _ptr(boff)))
+        out = []
+        for i in range(n):
+            d = dict(format=info[i].format, ok=bool(info[i].ok), status=info[i].status, traceACGT=None, basecallpos=None, qual=None, basecalls1=None, basecalls2=None)
+            if info[i].format >= 0 and info[i].status == 0:
+                s, b = int(soff[i]), slice(int(boff[i]), int(boff[i] + nb[i]))
+                d.update(traceACGT=samples[s: s + 4 * int(ns[i])].reshape(4, int(ns[i])).copy(), basecallpos=ploc[b].copy(), qual=qual[b].copy(),
+                         basecalls1=b1[b].tobytes() if info[i].format == 0 else b"",      # readscf leaves both strings empty
+                         basecalls2=b2[b].tobytes() if info[i].format == 0 else b"")
+            out.append(d)
+        return out
+
     def allelic_fraction(self, traces, bcpos, primary, secdecompose, trim_left=50, trim_right=50):
         """allelicFraction(c, tr, bc) for a batch (reference src/decompose.h:412-617) -> float64[N][2] = (bestI, bestJ)."""
         n = len(traces)
@@ -382,6 +415,21 @@ def reference_slice(bestpos, seqlen, conslen, maxindel=1000):
     if rc != capi.TB_OK:
         raise TracyError(rc, lib.tb_strerror(rc).decode())
     return ri.value, cp.value, s0.value, s1.value
+
+
+def scan_traces(files):
+    """traceFormat + the directory walk of readab / readscf (host only, no GPU): one dict per file with format, ok, status,
+    nsamples, nbasecalls (reference src/scf.h:19-35, src/abif.h:300-388, src/scf.h:56-93)."""
+    lib = capi.lib()
+    n = len(files)
+    flen = np.array([len(f) for f in files], np.int64)
+    foff = np.concatenate([[0], np.cumsum(flen)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
+    blob = np.frombuffer(b"".join(bytes(f) for f in files) or b"\0", np.uint8)
+    info = (capi.TraceInfo * max(n, 1))()
+    rc = lib.tb_trace_scan(_ptr(blob), _ptr(foff), _ptr(flen), n, C.cast(info, C.c_void_p))
+    if rc != capi.TB_OK:
+        raise TracyError(rc, lib.tb_strerror(rc).decode())
+    return [dict(format=info[i].format, ok=bool(info[i].ok), status=info[i].status, nsamples=info[i].nsamples, nbasecalls=info[i].nbasecalls) for i in range(n)]
 
 
 def trim_reference_slice(row0, row1, refslice, forward=True, pos=0, trim_left=0, trim_right=0):

@@ -15,7 +15,7 @@ SYMBOLS = [
     "tb_ctx_set_scratch_limit", "tb_ctx_stats", "tb_ctx_last_kernel_ms", "tb_ctx_last_call_ms", "tb_ctx_last_packed_pairs", "tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss",
     "tb_rows_from_ops", "tb_decompose_sweep", "tb_version", "tb_create_profile", "tb_revcomp_profile", "tb_trim_reference_slice",
     "tb_find_breakpoint", "tb_basecall", "tb_index_build", "tb_index_destroy", "tb_index_info", "tb_anchor", "tb_ctx_last_anchor_ms",
-    "tb_reference_slice", "tb_allelic_fraction", "tb_ctx_last_fraction_ms",
+    "tb_reference_slice", "tb_allelic_fraction", "tb_ctx_last_fraction_ms", "tb_trace_scan", "tb_trace_unpack",
 ]
 
 
@@ -71,6 +71,10 @@ class FractionBatch(C.Structure):
                 ("trim_left", C.c_int32), ("trim_right", C.c_int32), ("ntraces", C.c_size_t), ("mem", C.c_int32)]
 
 
+class TraceInfo(C.Structure):
+    _fields_ = [("format", C.c_int32), ("ok", C.c_int32), ("status", C.c_int32), ("nsamples", C.c_int32), ("nbasecalls", C.c_int32)]
+
+
 class LibraryMissing(RuntimeError):
     pass
 
@@ -122,5 +126,7 @@ def lib():
                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.tb_allelic_fraction.argtypes = [vp, C.POINTER(FractionBatch), vp, vp]
     L.tb_ctx_last_fraction_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.tb_trace_scan.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    L.tb_trace_unpack.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_int32, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L

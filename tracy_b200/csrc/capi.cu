@@ -25,6 +25,8 @@ unsigned long long gotoh_packed_ptr_words(int m, int n);
 
 
 cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
+void scan_trace_file(const uint8_t* buf, int64_t n, TraceDesc* d);
+cudaError_t launch_trace_unpack(const TraceUnpack& U, int nfiles, cudaStream_t st);
 cudaError_t launch_allelic_fraction(const FractionBatch& F, int ntraces, int maxD, cudaStream_t st);
 cudaError_t index_sort_temp_bytes(long long n, size_t* bytes);
 cudaError_t index_build(const unsigned char* text, long long n, unsigned long long* keys_a, unsigned* pos_a, unsigned long long* keys_b,
@@ -1253,5 +1255,81 @@ int tb_allelic_fraction(tb_ctx* ctx, const tb_fraction_batch* b, double* a1, dou
 int tb_ctx_last_fraction_ms(const tb_ctx* ctx, float* ms) {
   if (!ctx || !ms) return TB_ERR_INVALID;
   *ms = ctx->last_fraction_ms;
+  return TB_OK;
+}
+
+// ---- trace-file ingest (scan + kernel in trace_io.cu) -------------------------------------
+int tb_trace_scan(const uint8_t* files, const int64_t* off, const int64_t* len, size_t nfiles, tb_trace_info* info) {
+  if (!files || !off || !len || !info) return TB_ERR_INVALID;
+  for (size_t i = 0; i < nfiles; ++i) {
+    if (off[i] < 0 || len[i] < 0) return TB_ERR_INVALID;
+    tb::TraceDesc d;
+    tb::scan_trace_file(files + off[i], len[i], &d);
+    info[i].format = d.format; info[i].ok = d.ok; info[i].status = d.status; info[i].nsamples = d.ns; info[i].nbasecalls = d.nb;
+  }
+  return TB_OK;
+}
+
+int tb_trace_unpack(tb_ctx* ctx, const uint8_t* files, const int64_t* off, const int64_t* len, size_t nfiles, int32_t out_mem,
+                    int32_t* samples, const int64_t* samples_off, int32_t* ploc, uint8_t* qual, char* basecalls1, char* basecalls2,
+                    const int64_t* bc_off) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (!files || !off || !len || !samples || !samples_off || !ploc || !qual || !basecalls1 || !basecalls2 || !bc_off)
+    return fail(ctx, TB_ERR_INVALID, "null pointer in trace unpack");
+  if (nfiles == 0) return TB_OK;
+  if (nfiles > 65535u * 1024u) return fail(ctx, TB_ERR_INVALID, "too many files in one call");
+  if (out_mem != TB_MEM_HOST && out_mem != TB_MEM_DEVICE) return fail(ctx, TB_ERR_INVALID, "out_mem must be TB_MEM_HOST or TB_MEM_DEVICE");
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->lanes[0].stream;
+  std::vector<tb::TraceDesc> desc(nfiles);
+  long long fmin = LLONG_MAX, fmax = 0, smax = 0, bmax = 0;
+  for (size_t i = 0; i < nfiles; ++i) {
+    if (off[i] < 0 || len[i] < 0 || samples_off[i] < 0 || bc_off[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative offset/length");
+    tb::scan_trace_file(files + off[i], len[i], &desc[i]);
+    fmin = std::min<long long>(fmin, off[i]); fmax = std::max<long long>(fmax, off[i] + len[i]);
+    if (desc[i].format >= 0 && desc[i].status == 0) {
+      smax = std::max<long long>(smax, samples_off[i] + 4ll * desc[i].ns);
+      bmax = std::max<long long>(bmax, bc_off[i] + desc[i].nb);
+    }
+  }
+  std::vector<int64_t> rel(nfiles);
+  for (size_t i = 0; i < nfiles; ++i) rel[i] = off[i] - fmin;
+  Staged S(st);
+  void *d_files, *d_off, *d_desc, *d_soff, *d_boff;
+  TB_CUDA(ctx, S.up(&d_files, files + fmin, (size_t)std::max(fmax - fmin, 1ll)));
+  TB_CUDA(ctx, S.up(&d_off, rel.data(), nfiles * 8)); TB_CUDA(ctx, S.up(&d_desc, desc.data(), nfiles * sizeof(tb::TraceDesc)));
+  TB_CUDA(ctx, S.up(&d_soff, samples_off, nfiles * 8)); TB_CUDA(ctx, S.up(&d_boff, bc_off, nfiles * 8));
+  ctx->h2d += (size_t)(fmax - fmin) + nfiles * (24 + sizeof(tb::TraceDesc));
+  tb::TraceUnpack U{};
+  U.files = (const uint8_t*)d_files; U.file_off = (const int64_t*)d_off; U.desc = (const tb::TraceDesc*)d_desc;
+  U.samples_off = (const int64_t*)d_soff; U.bc_off = (const int64_t*)d_boff;
+  void *o_s = samples, *o_p = ploc, *o_q = qual, *o_1 = basecalls1, *o_2 = basecalls2;
+  if (out_mem == TB_MEM_HOST) {
+    TB_CUDA(ctx, S.alloc(&o_s, (size_t)std::max(smax, 1ll) * 4)); TB_CUDA(ctx, S.alloc(&o_p, (size_t)std::max(bmax, 1ll) * 4));
+    TB_CUDA(ctx, S.alloc(&o_q, (size_t)std::max(bmax, 1ll))); TB_CUDA(ctx, S.alloc(&o_1, (size_t)std::max(bmax, 1ll))); TB_CUDA(ctx, S.alloc(&o_2, (size_t)std::max(bmax, 1ll)));
+  }
+  U.samples = (int32_t*)o_s; U.ploc = (int32_t*)o_p; U.qual = (uint8_t*)o_q; U.basecalls1 = (char*)o_1; U.basecalls2 = (char*)o_2;
+  for (size_t f0 = 0; f0 < nfiles; f0 += 65535) {           // gridDim.x limit is far above this; keep launches moderate
+    tb::TraceUnpack V = U;
+    const size_t fn = std::min<size_t>(65535, nfiles - f0);
+    V.file_off += f0; V.desc += f0; V.samples_off += f0; V.bc_off += f0;
+    TB_CUDA(ctx, tb::launch_trace_unpack(V, (int)fn, st));
+    ctx->launches++;
+  }
+  if (out_mem == TB_MEM_HOST) {
+    for (size_t i = 0; i < nfiles; ++i) {                   // items may be sparse in the caller's arenas
+      const tb::TraceDesc& d = desc[i];
+      if (d.format < 0 || d.status != 0) continue;
+      if (d.ns) TB_CUDA(ctx, cudaMemcpyAsync(samples + samples_off[i], (const int32_t*)o_s + samples_off[i], (size_t)16 * d.ns, cudaMemcpyDeviceToHost, st));
+      if (d.nb) {
+        TB_CUDA(ctx, cudaMemcpyAsync(ploc + bc_off[i], (const int32_t*)o_p + bc_off[i], (size_t)4 * d.nb, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(ctx, cudaMemcpyAsync(qual + bc_off[i], (const uint8_t*)o_q + bc_off[i], (size_t)d.nb, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(ctx, cudaMemcpyAsync(basecalls1 + bc_off[i], (const char*)o_1 + bc_off[i], (size_t)d.nb, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(ctx, cudaMemcpyAsync(basecalls2 + bc_off[i], (const char*)o_2 + bc_off[i], (size_t)d.nb, cudaMemcpyDeviceToHost, st));
+      }
+      ctx->d2h += (size_t)16 * d.ns + (size_t)7 * d.nb;
+    }
+  }
+  TB_CUDA(ctx, cudaStreamSynchronize(st));
   return TB_OK;
 }

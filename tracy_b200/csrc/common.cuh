@@ -62,6 +62,25 @@ struct BasecallBatch {
   float sigratio;
 };
 
+// One trace file's directory, as the host scan leaves it (trace_io.cu). Offsets are bytes from the start of the file.
+struct TraceDesc {
+  int32_t format;            // 0 ABIF, 1 SCF, -1 unknown
+  int32_t ok;                // what readab() / readscf() return
+  int32_t status;            // 0, or a TB_TRACE_* reason the file cannot be unpacked
+  int32_t scf_v3;
+  int32_t ns;                // samples per channel
+  int32_t nb;                // basecall positions (after the reference's resize to the shortest vector)
+  int32_t ch_off[4], ch_n[4];
+  int64_t ploc_off; int32_t ploc_n;
+  int64_t q_off; int32_t q_n;
+  int64_t b1_off, b2_off; int32_t b1_n, b2_n;
+};
+struct TraceUnpack {
+  const uint8_t* files; const int64_t* file_off; const TraceDesc* desc;
+  int32_t* samples; const int64_t* samples_off;                  // int32 [4][ns] per file
+  int32_t* ploc; uint8_t* qual; char* basecalls1; char* basecalls2; const int64_t* bc_off;
+};
+
 // Device view of an allelicFraction batch (fraction.cu).
 struct FractionBatch {
   const int32_t* trace_base; const int64_t* trace_off; const int32_t* trace_len;   // item = int32[4][nsamples]

@@ -103,3 +103,59 @@ def profile_from_seq(rng, s, noise=0.3):
         p[k] = (np.float32(1.0) - w) / np.float32(3.0)
     p[code, np.arange(m)] = w
     return p
+
+
+# ---- synthetic trace FILES (tests / benches of the ingest path) ---------------------------------------------------------
+def abif_bytes(channels, order, ploc, basecalls, qual, basecalls2=None, extra=()):
+    """A minimal valid ABIF file (big-endian directory of 28-byte entries, reference src/abif.h:300-378): DATA.9-12 =
+    `channels` in file order, FWO_.1 = `order` (e.g. b"GATC"), PLOC.2, PBAS.2, PCON.2, optionally P2BA.1.
+    extra: further (name, number, etype, esize, payload bytes) records."""
+    import struct
+    recs = []
+    for i, ch in enumerate(channels):
+        recs.append((b"DATA", 9 + i, 4, 2, np.asarray(ch, ">i2").tobytes(), len(ch)))
+    recs.append((b"FWO_", 1, 2, 1, bytes(order), len(order)))
+    recs.append((b"PLOC", 2, 4, 2, np.asarray(ploc, ">i2").tobytes(), len(ploc)))
+    recs.append((b"PBAS", 2, 2, 1, bytes(basecalls), len(basecalls)))
+    recs.append((b"PCON", 2, 2, 1, np.asarray(qual, np.uint8).tobytes(), len(qual)))      # stored as char; readab forces etype 1
+    if basecalls2 is not None:
+        recs.append((b"P2BA", 1, 2, 1, bytes(basecalls2), len(basecalls2)))
+    for name, number, etype, esize, payload in extra:
+        recs.append((name, number, etype, esize, bytes(payload), len(payload) // max(esize, 1)))
+    body = bytearray()
+    dirent = []
+    data_start = 128
+    for name, number, etype, esize, payload, ne in recs:
+        dsize = len(payload)
+        if dsize > 4:
+            doff = data_start + len(body)
+            body += payload
+            field = struct.pack(">i", doff)
+        else:
+            field = payload.ljust(4, b"\0")
+        dirent.append(name + struct.pack(">ihhii", number, etype, esize, ne, dsize) + field + struct.pack(">i", 0))
+    dir_off = data_start + len(body)
+    head = b"ABIF" + struct.pack(">h", 101) + b"tdir" + struct.pack(">ihhiiii", 1, 1023, 28, len(dirent), 28 * len(dirent), dir_off, 0)
+    return head.ljust(data_start, b"\0") + bytes(body) + b"".join(dirent) + b"\0" * 2
+
+
+def scf_bytes(channels, ploc, version=b"3.00"):
+    """A minimal SCF file (reference src/scf.h:56-93): 128-byte header, then for 3.x the four channels one after the other
+    as twice-differenced big-endian int16, else interleaved plain samples; then int32 basecall positions."""
+    import struct
+    ch = [np.asarray(c, np.int64) for c in channels]
+    ns = len(ch[0])
+    if float(version) > 2.9:
+        enc = []
+        for c in ch:
+            d = c.copy()
+            for _ in range(2):
+                d[1:] = d[1:] - d[:-1]
+            enc.append(((d + 32768) % 65536 - 32768).astype(">i2").tobytes())
+        samples = b"".join(enc)
+    else:
+        samples = np.stack(ch, 1).astype(">i2").tobytes()
+    off = 128
+    bases_off = off + len(samples)
+    head = b".scf" + struct.pack(">iii", ns, off, len(ploc)) + struct.pack(">ii", 0, 0) + struct.pack(">i", bases_off) + struct.pack(">ii", 0, 0) + version
+    return head.ljust(128, b"\0") + samples + np.asarray(ploc, ">i4").tobytes()

@@ -200,6 +200,28 @@ class _Ref:
                                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.c_char_p, C.c_int]
         L.ref_get_reference_slice.restype = C.c_int
 
+    def plot_alignment(self, row0, row1, chr_name, pos, refslice_len, forward, score, key=0, a1a2=(0.0, 0.0), linelimit=60):
+        """plotAlignment(...) -> the text it writes (src/fmindex.h:329-420)."""
+        import tempfile
+        p = tempfile.mktemp()
+        self.lib.ref_plot_alignment.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_double, C.c_double, C.c_uint]
+        self.lib.ref_plot_alignment(os.fsencode(p), bytes(row0), bytes(row1), len(row0), bytes(chr_name), pos, refslice_len, int(forward), key, score,
+                                    float(a1a2[0]), float(a1a2[1]), linelimit)
+        out = open(p, "rb").read()
+        os.remove(p)
+        return out
+
+    def write_decomposition(self, pairs):
+        import tempfile
+        p = tempfile.mktemp()
+        a = np.ascontiguousarray(pairs, np.int32).reshape(-1)
+        self.lib.ref_write_decomposition.argtypes = [C.c_char_p, _i32p, C.c_int]
+        self.lib.ref_write_decomposition(os.fsencode(p), a, len(a) // 2)
+        out = open(p, "rb").read()
+        os.remove(p)
+        return out
+
     def read_trace(self, path):
         """traceFormat + readab / readscf on a file -> dict(format, ok, samples [list of 4 int32 arrays], basecallpos, qual, basecalls1, basecalls2)."""
         L = self.lib

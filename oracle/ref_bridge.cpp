@@ -356,6 +356,20 @@ void ref_trace_get(int32_t* samples, int32_t* ploc, uint8_t* qual, char* b1, cha
   memcpy(b2, g_trace.basecalls2.data(), g_trace.basecalls2.size());
 }
 
+// plotAlignment (src/fmindex.h:329-420) and writeDecomposition (src/decompose.h:621-627) into the given path
+void ref_plot_alignment(const char* path, const char* row0, const char* row1, int L, const char* chr, unsigned pos, int refslice_len, int forward,
+                        int key, int score, double a1, double a2, unsigned linelimit) {
+  TAlign al(boost::extents[2][L]);
+  for (int j = 0; j < L; ++j) { al[0][j] = row0[j]; al[1][j] = row1[j]; }
+  tracy::ReferenceSlice rs; rs.forward = forward != 0; rs.pos = pos; rs.chr = chr; rs.refslice = std::string((size_t)refslice_len, 'A');
+  tracy::plotAlignment(path, al, rs, key, score, std::make_pair(a1, a2), linelimit);
+}
+void ref_write_decomposition(const char* path, const int32_t* pairs, int n) {
+  std::vector<std::pair<int32_t, int32_t> > dcp;
+  for (int i = 0; i < n; ++i) dcp.push_back(std::make_pair(pairs[2 * i], pairs[2 * i + 1]));
+  tracy::writeDecomposition(path, dcp);
+}
+
 // allelicFraction(c, tr, bc), src/decompose.h:412-617
 void ref_allelic_fraction(const int32_t* acgt, int nsamples, const int32_t* bcpos, const char* primary, const char* secdecompose, int nbc,
                           int trimLeft, int trimRight, double* a1, double* a2) {

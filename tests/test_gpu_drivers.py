@@ -41,3 +41,20 @@ def test_decompose_batch_golden(ctx, capsys):
                 a = r[name]
                 assert [a["score"], a["pos"]] == [int(x) for x in G[f"{name}_s{i}"]], (i, name)
                 assert (a["row0"], a["row1"], a["refslice"]) == (bytes(G[f"{name}_r0{i}"]), bytes(G[f"{name}_r1{i}"]), bytes(G[f"{name}_sl{i}"])), (i, name)
+
+
+def test_consensus_batch_golden(ctx):
+    """drivers.consensus_batch against the DP sequence of consensus() composed from the reference's functions."""
+    Gc = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "consensus_golden.npz"))
+    n = int(Gc["n"])
+    res = drivers.consensus_batch(ctx, [Gc[f"p1_{i}"] for i in range(n)], [Gc[f"p2_{i}"] for i in range(n)], DnaScore(3, -5, -10, -4),
+                                  min_overlap=100, match_fraction=0.5)
+    for i, r in enumerate(res):
+        assert [int(r["forward"]), r["score"]] == [int(x) for x in Gc[f"meta{i}"]], i
+        assert (r["row0"], r["row1"]) == (bytes(Gc[f"r0_{i}"]), bytes(Gc[f"r1_{i}"])), i
+        a0, a1 = np.frombuffer(r["row0"], np.uint8), np.frombuffer(r["row1"], np.uint8)
+        both = (a0 != 45) & (a1 != 45)
+        na, nm = int(both.sum()), int((both & (a0 == a1)).sum())
+        assert r["num_aligned"] == na and r["num_match"] == nm
+        assert r["ok"] == (not (na < 100 or (nm / na if na else 0.0) < 0.5)), i          # src/consensus.h:546-549
+    assert not res[-1]["ok"] and any(r["ok"] for r in res)

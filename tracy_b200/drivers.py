@@ -4,6 +4,7 @@
   align_genome_batch  sage()  for an indexed genome         reference src/sage.h:216-222, :258-260, :311; src/fmindex.h:236-326
   decompose_batch  indigo()   for single-FASTA references   reference src/indigo.h:190-388
   assemble_denovo  assemble() de novo branch                reference src/assemble.h:418-471
+  consensus_batch  consensus() up to the overlap check      reference src/consensus.h:499-556
 
 Everything between the file readers and the file writers of those drivers: orientation pick, semi-global alignment of the
 trimmed trace, reference-slice trimming, final alignment (align); orientation optimisation, exclusion of unmatched traces,
@@ -13,7 +14,7 @@ host logic of tracy_b200.api / tracy_b200.msa. File formats, basecalling and the
 import numpy as np
 
 from . import decompose, msa
-from .api import PS, SS, AlignConfig, DnaScore, find_breakpoint, reference_slice, rows_from_ops, trim_reference_slice
+from .api import PP, PS, SS, AlignConfig, DnaScore, find_breakpoint, reference_slice, rows_from_ops, trim_reference_slice
 
 _SEMIGLOBAL = AlignConfig(True, False)          # AlignConfig<true, false>, src/sage.h:165
 _COMP = {ord("A"): ord("T"), ord("C"): ord("G"), ord("G"): ord("C"), ord("T"): ord("A"), ord("N"): ord("N")}
@@ -102,6 +103,32 @@ def align_genome_batch(ctx, index, seqs, consensus, trimmed_profiles, full_profi
         row0, row1 = rows_from_ops(PS, full_profiles[i], slices[j], bytes(ops2[j, : ol2[j]]))
         out[i] = dict(forward=meta[j][2], chr=meta[j][0], kmersupport=int(a["kmersupport"][i]), refslice=slices[j], pos=pos[j],
                       score=int(score[j]), row0=row0, row1=row1)
+    return out
+
+
+def consensus_batch(ctx, profiles1, profiles2, sc=DnaScore(3, -5, -10, -4), min_overlap=0, match_fraction=0.0):
+    """The DP sequence of `tracy consensus` for a batch of trace PAIRS (reference src/consensus.h:499-556).
+
+    profiles1 / profiles2: createProfile() of the two trimmed traces of every pair (float32[6][len]).
+    Orientation of the second trace by two global score fills (strict '>', :517-527), the global alignment (:535), the overlap
+    statistics and the minOverlap / matchFraction gate (:538-549). Returns per pair dict(forward, score, row0, row1, num_aligned,
+    num_match, ok); pairwiseConsensus and the writers stay with the caller."""
+    glob = AlignConfig(True, True)                                         # AlignConfig<true, true>, src/consensus.h:464
+    n = len(profiles1)
+    rev2 = ctx.revcomp_profile(profiles2)                                  # reverseComplementProfile, :514
+    s = ctx.gotoh(PP, list(profiles1) + list(profiles1), list(profiles2) + list(rev2), sc, glob, traceback=False)[0]
+    forward = [bool(s[i] > s[n + i]) for i in range(n)]
+    second = [profiles2[i] if forward[i] else rev2[i] for i in range(n)]
+    score, ops, ol = ctx.gotoh(PP, profiles1, second, sc, glob)
+    out = []
+    for i in range(n):
+        row0, row1 = rows_from_ops(PP, profiles1[i], second[i], bytes(ops[i, : ol[i]]))
+        a0, a1 = np.frombuffer(row0, np.uint8), np.frombuffer(row1, np.uint8)
+        both = (a0 != 0x2D) & (a1 != 0x2D)
+        na, nm = int(both.sum()), int((both & (a0 == a1)).sum())
+        frac = nm / na if na else 0.0
+        out.append(dict(forward=forward[i], score=int(score[i]), row0=row0, row1=row1, num_aligned=na, num_match=nm,
+                        ok=not (na < min_overlap or frac < match_fraction)))
     return out
 
 

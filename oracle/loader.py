@@ -27,6 +27,12 @@ def build(force=False):
     bridge = os.path.join(_HERE, "ref_bridge.cpp")
     if os.path.isdir("/root/reference/src") and (force or not os.path.exists(ref_so) or os.path.getmtime(ref_so) < os.path.getmtime(bridge)):
         need = True
+    if os.path.isdir("/root/reference/src"):   # the drop-in check binary (tests/cpp/dropin.cpp against the reference headers + include/tracy_b200.hpp)
+        exe = os.path.join(_HERE, "_ref", "dropin_test")
+        deps = [os.path.join(_HERE, "..", "tests", "cpp", "dropin.cpp"), os.path.join(_HERE, "..", "include", "tracy_b200.hpp"),
+                os.path.join(_HERE, "..", "include", "tracy_b200.h")]
+        if force or not os.path.exists(exe) or any(os.path.getmtime(exe) < os.path.getmtime(d) for d in deps):
+            need = True
     if need:
         subprocess.run(["make", "-s", "-C", _HERE, "all"], check=True)
 

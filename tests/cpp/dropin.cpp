@@ -1,0 +1,179 @@
+// Drop-in check (TEST INFRASTRUCTURE): ONE translation unit holds the UNMODIFIED reference headers from
+// /root/reference/src (behind the container-only Boost stand-ins of oracle/shim) AND include/tracy_b200.hpp, calls
+// tracy::gotohScore / tracy::gotoh / tracy::decomposeAlleles on the CPU and tracy_b200::gotohScore / gotoh /
+// decomposeAlleles (same argument objects, plus a Context) on the B200, and compares every result.
+// Built by oracle/Makefile into oracle/_ref/dropin_test where /root/reference exists; run by tests/test_gpu_dropin.py.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <sdsl/suffix_arrays.hpp>
+
+#include "tracy_boost_stubs.hpp"
+#include "abif.h"
+#include "scf.h"
+#include "align.h"
+#include "gotoh.h"
+#include "fmindex.h"
+#include "profile.h"
+#include "decompose.h"
+
+#define TRACY_B200_WITH_BOOST
+#include "tracy_b200.hpp"
+
+typedef boost::multi_array<float, 2> TProfile;
+typedef boost::multi_array<char, 2> TAlign;
+static std::mt19937_64 rng(20261017);
+static int checks = 0, failures = 0;
+
+static void expect(bool ok, const char* what, int id) {
+  ++checks;
+  if (!ok) { ++failures; std::printf("MISMATCH %s #%d\n", what, id); }
+}
+static std::string random_seq(int n, const char* alphabet = "ACGT") {
+  std::string s((size_t)n, 'A');
+  const size_t k = std::strlen(alphabet);
+  for (auto& c : s) c = alphabet[rng() % k];
+  return s;
+}
+// a createProfile-like profile of `s`: rows A,C,G,T sum to 1, rows N and - are zero; `msa` also fills the N / gap rows
+static void random_profile(std::string const& s, TProfile& p, bool msa) {
+  p.resize(boost::extents[6][s.size()]);
+  std::uniform_real_distribution<float> U(0.f, 1.f);
+  for (size_t j = 0; j < s.size(); ++j) {
+    const int b = s[j] == 'C' ? 1 : s[j] == 'G' ? 2 : s[j] == 'T' ? 3 : 0;
+    const float w = 0.55f + 0.45f * U(rng);
+    for (int k = 0; k < 6; ++k) p[k][j] = 0.f;
+    for (int k = 0; k < 4; ++k) p[k][j] = k == b ? w : (1.f - w) / 3.f;
+    if (msa && U(rng) < 0.2f) { p[4][j] = 0.1f * U(rng); p[5][j] = 0.3f * U(rng); }
+  }
+}
+static bool same_align(TAlign const& x, TAlign const& y) {
+  if (x.shape()[1] != y.shape()[1]) return false;
+  for (size_t i = 0; i < 2; ++i)
+    for (size_t j = 0; j < x.shape()[1]; ++j)
+      if (x[i][j] != y[i][j]) return false;
+  return true;
+}
+static std::string mutate(std::string const& s, double sub, double indel) {
+  std::string out;
+  std::uniform_real_distribution<double> U(0, 1);
+  for (char c : s) {
+    const double u = U(rng);
+    if (u < indel) continue;
+    if (u < 2 * indel) out.push_back("ACGT"[rng() % 4]);
+    out.push_back(U(rng) < sub ? "ACGT"[rng() % 4] : c);
+  }
+  return out;
+}
+
+template <bool H, bool V>
+static void dp_checks(tracy_b200::Context& g, int id) {
+  tracy::AlignConfig<H, V> ac;
+  tracy::DnaScore<int32_t> sc(3, -5, -10, -4);
+  const std::string ref = random_seq(150 + (int)(rng() % 400));
+  const int off = (int)(rng() % 60), len = 60 + (int)(rng() % (ref.size() - 120));
+  const std::string tr = mutate(ref.substr(off, len), 0.03, 0.01);
+  TProfile p1, p2, onehot;
+  random_profile(tr, p1, false);
+  random_profile(mutate(ref, 0.02, 0.005), p2, id % 2 == 0);
+  tracy::_createProfile(ref, onehot);
+  TAlign a, b;
+  // profile x profile
+  expect(tracy::gotohScore(p1, p2, ac, sc) == tracy_b200::gotohScore(g, p1, p2, ac, sc), "gotohScore(profile,profile)", id);
+  int s1 = tracy::gotoh(p1, p2, a, ac, sc), s2 = tracy_b200::gotoh(g, p1, p2, b, ac, sc);
+  expect(s1 == s2 && same_align(a, b), "gotoh(profile,profile)", id);
+  // profile x reference: the reference goes through the one-hot profile, the B200 call takes the string itself
+  expect(tracy::gotohScore(p1, onehot, ac, sc) == tracy_b200::gotohScore(g, p1, ref, ac, sc), "gotohScore(profile,refstring)", id);
+  s1 = tracy::gotoh(p1, onehot, a, ac, sc); s2 = tracy_b200::gotoh(g, p1, ref, b, ac, sc);
+  expect(s1 == s2 && same_align(a, b), "gotoh(profile,refstring)", id);
+  // string x string
+  expect(tracy::gotohScore(tr, ref, ac, sc) == tracy_b200::gotohScore(g, tr, ref, ac, sc), "gotohScore(string,string)", id);
+  s1 = tracy::gotoh(tr, ref, a, ac, sc); s2 = tracy_b200::gotoh(g, tr, ref, b, ac, sc);
+  expect(s1 == s2 && same_align(a, b), "gotoh(string,string)", id);
+}
+
+struct DecompCfg { uint16_t trimLeft, trimRight, maxindel, madc; };
+
+static void decompose_check(tracy_b200::Context& g, int id, int ins, int del, int snvs, bool unrelated) {
+  // two alleles of one locus, the second with an indel behind position bp; basecalls carry both (primary / secondary)
+  const std::string ref = random_seq(700 + (int)(rng() % 200));
+  const int start = 30 + (int)(rng() % 60), L = 380 + (int)(rng() % 120), bpos = 120 + (int)(rng() % 100);
+  std::string a1 = ref.substr(start, L);
+  std::string a2 = (ref.substr(start, bpos) + random_seq(ins) + ref.substr(start + bpos + del)).substr(0, L);
+  for (int k = 0; k < snvs; ++k) a2[rng() % a2.size()] = "ACGT"[rng() % 4];
+  tracy::BaseCalls bc;
+  bc.primary = a1; bc.secondary = a2; bc.consensus = a1;
+  for (size_t i = 0; i < bc.secondary.size(); ++i) {
+    if (rng() % 40 == 0) bc.secondary[i] = 'N';
+    else if (a1[i] != a2[i] && rng() % 6 == 0) bc.secondary[i] = tracy::iupac(a1[i], a2[i]);
+  }
+  DecompCfg c; c.trimLeft = 20; c.trimRight = 25; c.maxindel = id % 2 ? 30 : 1000; c.madc = 5;
+  tracy::ReferenceSlice rs; rs.refslice = unrelated ? random_seq((int)ref.size()) : ref; rs.forward = true;
+  TAlign align;
+  tracy::AlignConfig<true, false> semiglobal;
+  tracy::DnaScore<int32_t> sc(3, -5, -10, -4);
+  tracy::gotoh(tracy::trimmedSeq(bc.primary, c.trimLeft, c.trimRight), rs.refslice, align, semiglobal, sc);
+  tracy::TraceBreakpoint bp; bp.indelshift = true; bp.traceleft = true; bp.breakpoint = (uint32_t)(bpos - c.trimLeft); bp.bestDiff = 0.5f;
+  tracy::BaseCalls bc2 = bc;
+  std::vector<std::pair<int32_t, int32_t> > d1, d2;
+  std::stringstream out1, out2;
+  std::streambuf* old = std::cout.rdbuf(out1.rdbuf());
+  tracy::decomposeAlleles(c, align, bc, bp, rs, d1);
+  std::cout.rdbuf(old);
+  tracy_b200::decomposeAlleles(g, c, align, bc2, bp, rs, d2, &out2);
+  expect(bc.primary == bc2.primary && bc.secondary == bc2.secondary, "decomposeAlleles primary/secondary", id);
+  expect(d1 == d2, "decomposeAlleles decomposition table", id);
+  expect(out1.str() == out2.str(), "decomposeAlleles diagnostics", id);
+}
+
+int main() {
+  try {
+    tracy_b200::Context g(0);
+    for (int i = 0; i < 6; ++i) {
+      dp_checks<true, false>(g, 10 + i);
+      dp_checks<true, true>(g, 20 + i);
+      dp_checks<false, false>(g, 30 + i);
+      dp_checks<false, true>(g, 40 + i);
+    }
+    const int shapes[][3] = {{0, 12, 1}, {9, 0, 1}, {0, 0, 4}, {5, 3, 1}, {0, 27, 2}, {14, 0, 1}, {0, 1, 0}, {1, 0, 0}};
+    for (int i = 0; i < 16; ++i) decompose_check(g, 100 + i, shapes[i % 8][0], shapes[i % 8][1], shapes[i % 8][2], i == 15);
+    // batch form: the same pairs in one call
+    {
+      std::vector<TProfile> ps(8);
+      std::vector<std::string> refs(8);
+      std::vector<const TProfile*> pa;
+      std::vector<const std::string*> pb;
+      tracy::AlignConfig<true, false> ac;
+      tracy::DnaScore<int32_t> sc(3, -5, -10, -4);
+      for (int i = 0; i < 8; ++i) {
+        refs[i] = random_seq(300 + 40 * i);
+        random_profile(mutate(refs[i].substr(20, 200), 0.02, 0.01), ps[i], false);
+        pa.push_back(&ps[i]); pb.push_back(&refs[i]);
+      }
+      std::vector<std::string> ops;
+      const std::vector<int32_t> s = tracy_b200::gotohBatch(g, pa, pb, ac, sc, &ops);
+      for (int i = 0; i < 8; ++i) {
+        TProfile oh; tracy::_createProfile(refs[i], oh);
+        TAlign a;
+        const int want = tracy::gotoh(ps[i], oh, a, ac, sc);
+        std::string r0(ops[i].size(), 0), r1(ops[i].size(), 0);
+        tb_rows_from_ops(2, ps[i].data(), (int32_t)ps[i].shape()[1], refs[i].data(), (int32_t)refs[i].size(), (const uint8_t*)ops[i].data(), (int32_t)ops[i].size(), &r0[0], &r1[0]);
+        bool ok = want == s[i] && a.shape()[1] == ops[i].size();
+        for (size_t j = 0; ok && j < ops[i].size(); ++j) ok = a[0][j] == r0[j] && a[1][j] == r1[j];
+        expect(ok, "gotohBatch(profile,refstring)", i);
+      }
+    }
+  } catch (std::exception const& e) {
+    std::printf("dropin: exception: %s\n", e.what());
+    return 2;
+  }
+  std::printf("dropin: %d checks, %d mismatches\n", checks, failures);
+  return failures ? 1 : 0;
+}

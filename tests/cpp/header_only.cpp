@@ -1,0 +1,27 @@
+// Compile check of include/tracy_b200.hpp WITHOUT Boost or the reference headers: its own Matrix / AlignConfig / DnaScore
+// stand-ins and plain structs shaped like tracy's BaseCalls / ReferenceSlice / TraceBreakpoint / config.
+#include "tracy_b200.hpp"
+
+struct Calls { std::string primary, secondary, consensus; };
+struct Slice { std::string refslice; };
+struct Breakpoint { bool indelshift, traceleft; uint32_t breakpoint; float bestDiff; };
+struct Cfg { uint16_t trimLeft, trimRight, maxindel, madc; };
+
+int main() {
+  using namespace tracy_b200;
+  Context g(0);                                   // throws without a B200: this file is only compiled by the CPU tests
+  Matrix<float> p1(6, 10), p2(6, 20);
+  Matrix<char> align;
+  AlignConfig<true, false> ac;
+  DnaScore<int32_t> sc(3, -5, -10, -4);
+  std::string s1 = "ACGT", s2 = "ACGGT";
+  int s = gotohScore(g, p1, p2, ac, sc) + gotoh(g, p1, p2, align, ac, sc) + gotoh(g, p1, s2, align, ac, sc) + gotoh(g, s1, s2, align, ac, sc);
+  std::vector<const Matrix<float>*> a{&p1};
+  std::vector<const std::string*> b{&s2};
+  std::vector<std::string> ops;
+  s += gotohBatch(g, a, b, ac, sc, &ops)[0];
+  Calls bc; Slice rs; Breakpoint bp{true, true, 3, 0.f}; Cfg c{0, 0, 30, 5};
+  std::vector<std::pair<int32_t, int32_t> > dcp;
+  decomposeAlleles(g, c, align, bc, bp, rs, dcp, nullptr);
+  return s == 12345;
+}

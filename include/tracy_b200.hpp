@@ -370,5 +370,186 @@ inline bool decomposeAlleles(Context& g, TConfig const& c, TAlign const& align, 
   return decomposeAllelesBatch(g, c, one, log);
 }
 
+// ---- the rows either side of the DP: same call shapes, many traces per GPU call --------------------------------------
+namespace detail {
+// Trace::traceACGT (four equally long channels) of many traces as one int32 [4][ns] arena
+template <typename TTrace>
+inline void pack_traces(std::vector<const TTrace*> const& tr, std::vector<int32_t>& base, std::vector<int64_t>& off, std::vector<int32_t>& len) {
+  off.resize(tr.size()); len.resize(tr.size());
+  for (std::size_t t = 0; t < tr.size(); ++t) {
+    auto const& ch = tr[t]->traceACGT;
+    const std::size_t ns = ch.size() ? ch[0].size() : 0;
+    off[t] = (int64_t)base.size(); len[t] = (int32_t)ns;
+    for (std::size_t k = 0; k < 4; ++k) {
+      if (k >= ch.size() || ch[k].size() != ns) throw Error(TB_ERR_INVALID, "trace channels differ in length");
+      base.insert(base.end(), ch[k].begin(), ch[k].end());
+    }
+  }
+  if (base.empty()) base.push_back(0);
+}
+}  // namespace detail
+
+// basecall(tr, bc, sigratio) for many traces -- reference src/abif.h:408-511 without its last line: estimateQualities(bc)
+// is host code of the reference and stays with the caller (tracy::estimateQualities(bc) after this call).
+template <typename TTrace, typename TBaseCalls>
+inline void basecallBatch(Context& g, std::vector<const TTrace*> const& tr, std::vector<TBaseCalls*> const& bc, float sigratio) {
+  const std::size_t n = tr.size();
+  if (n == 0) return;
+  std::vector<int32_t> base, ploc; std::vector<int64_t> toff, poff(n); std::vector<int32_t> tlen, plen(n);
+  detail::pack_traces(tr, base, toff, tlen);
+  for (std::size_t t = 0; t < n; ++t) {
+    poff[t] = (int64_t)ploc.size(); plen[t] = (int32_t)tr[t]->basecallpos.size();
+    ploc.insert(ploc.end(), tr[t]->basecallpos.begin(), tr[t]->basecallpos.end());
+  }
+  const std::size_t tot = std::max<std::size_t>(ploc.size(), 1);
+  if (ploc.empty()) ploc.push_back(0);
+  std::vector<int32_t> opos(tot), olen(n);
+  std::string pri(tot, 'N'), sec(tot, 'N'), con(tot, 'N');
+  tb_basecall_batch b{{base.data(), toff.data(), tlen.data()}, {ploc.data(), poff.data(), plen.data()}, n, TB_MEM_HOST};
+  g.check(tb_basecall(g.get(), &b, sigratio, opos.data(), &pri[0], &sec[0], &con[0], poff.data(), olen.data()));
+  for (std::size_t t = 0; t < n; ++t) {
+    const std::size_t o = (std::size_t)poff[t], k = (std::size_t)olen[t];
+    bc[t]->bcPos.assign(opos.begin() + o, opos.begin() + o + k);
+    bc[t]->primary = pri.substr(o, k); bc[t]->secondary = sec.substr(o, k); bc[t]->consensus = con.substr(o, k);
+  }
+}
+template <typename TTrace, typename TBaseCalls>
+inline void basecall(Context& g, TTrace const& tr, TBaseCalls& bc, float sigratio) {
+  basecallBatch(g, std::vector<const TTrace*>{&tr}, std::vector<TBaseCalls*>{&bc}, sigratio);
+}
+
+// createProfile(tr, bc, p, trimleft, trimright) for many traces -- reference src/profile.h:21-52.
+template <typename TTrace, typename TBaseCalls, typename TProfile>
+inline void createProfileBatch(Context& g, std::vector<const TTrace*> const& tr, std::vector<const TBaseCalls*> const& bc, std::vector<TProfile*> const& p,
+                               int32_t trimleft = 0, int32_t trimright = 0) {
+  const std::size_t n = tr.size();
+  if (n == 0) return;
+  std::vector<int32_t> base, bpos; std::vector<int64_t> toff, boff(n), ooff(n); std::vector<int32_t> tlen, blen(n), tl(n, trimleft), trr(n, trimright), olen(n);
+  std::string pri, sec;
+  detail::pack_traces(tr, base, toff, tlen);
+  int64_t ototal = 0;
+  for (std::size_t t = 0; t < n; ++t) {
+    boff[t] = (int64_t)bpos.size(); blen[t] = (int32_t)bc[t]->bcPos.size();
+    bpos.insert(bpos.end(), bc[t]->bcPos.begin(), bc[t]->bcPos.end());
+    pri += bc[t]->primary; sec += bc[t]->secondary;
+    ooff[t] = ototal; ototal += 6ll * blen[t];
+  }
+  if (bpos.empty()) { bpos.push_back(0); pri.push_back('N'); sec.push_back('N'); }
+  std::vector<float> out((std::size_t)std::max<int64_t>(ototal, 1));
+  tb_profile_batch b{{base.data(), toff.data(), tlen.data()}, {bpos.data(), boff.data(), blen.data()}, pri.data(), sec.data(), tl.data(), trr.data(), n, TB_MEM_HOST};
+  g.check(tb_create_profile(g.get(), &b, out.data(), ooff.data(), olen.data()));
+  for (std::size_t t = 0; t < n; ++t) {
+    const std::size_t sz = (std::size_t)olen[t];
+    detail::resize_align(*p[t], 6, sz);
+    for (std::size_t k = 0; k < 6; ++k)
+      for (std::size_t j = 0; j < sz; ++j) (*p[t])[k][j] = out[(std::size_t)ooff[t] + k * sz + j];
+  }
+}
+template <typename TTrace, typename TBaseCalls, typename TProfile>
+inline void createProfile(Context& g, TTrace const& tr, TBaseCalls const& bc, TProfile& p, int32_t trimleft = 0, int32_t trimright = 0) {
+  createProfileBatch(g, std::vector<const TTrace*>{&tr}, std::vector<const TBaseCalls*>{&bc}, std::vector<TProfile*>{&p}, trimleft, trimright);
+}
+
+// reverseComplementProfile(p, out) -- reference src/profile.h:74-90.
+template <typename TProfile>
+inline void reverseComplementProfile(Context& g, TProfile const& p, TProfile& out) {
+  int64_t off = 0;
+  int32_t len = (int32_t)p.shape()[1];
+  detail::resize_align(out, 6, (std::size_t)len);
+  if (len == 0) return;
+  tb_arena in{p.data(), &off, &len};
+  g.check(tb_revcomp_profile(g.get(), &in, 1, TB_MEM_HOST, out.data(), &off));
+}
+
+// findBreakpoint(ptrace, bp) -- reference src/decompose.h:7-56 (host arithmetic inside the library).
+template <typename TProfile, typename TBreakpoint>
+inline void findBreakpoint(TProfile const& ptrace, TBreakpoint& bp) {
+  int32_t shift = 0, left = 0; uint32_t pos = 0; float diff = 0;
+  const int rc = tb_find_breakpoint(ptrace.data(), (int32_t)ptrace.shape()[1], &shift, &left, &pos, &diff);
+  if (rc != TB_OK) throw Error(rc, tb_strerror(rc));
+  bp.indelshift = shift != 0; bp.traceleft = left != 0; bp.breakpoint = pos; bp.bestDiff = diff;
+}
+
+// trimReferenceSlice(c, align, rs) -- reference src/fmindex.h:429-463.
+template <typename TConfig, typename TAlign, typename TRefSlice>
+inline void trimReferenceSlice(TConfig const& c, TAlign const& align, TRefSlice& rs) {
+  const std::size_t L = align.shape()[1];
+  std::string r0(L, '-'), r1(L, '-');
+  for (std::size_t j = 0; j < L; ++j) { r0[j] = align[0][j]; r1[j] = align[1][j]; }
+  int32_t ri = 0, risize = 0; uint32_t npos = 0;
+  const int rc = tb_trim_reference_slice(r0.data(), r1.data(), (int32_t)L, (int32_t)rs.refslice.size(), rs.forward ? 1 : 0, rs.pos, (int32_t)c.trimLeft,
+                                         (int32_t)c.trimRight, &ri, &risize, &npos);
+  if (rc != TB_OK) throw Error(rc, tb_strerror(rc));
+  rs.refslice = rs.refslice.substr((std::size_t)ri, (std::size_t)risize);
+  rs.pos = npos;
+}
+
+// allelicFraction(c, tr, bc) -- reference src/decompose.h:412-617 (GPU, FP64, bit-exact), for many traces.
+template <typename TConfig, typename TTrace, typename TBaseCalls>
+inline std::vector<std::pair<double, double> > allelicFractionBatch(Context& g, TConfig const& c, std::vector<const TTrace*> const& tr,
+                                                                    std::vector<const TBaseCalls*> const& bc) {
+  const std::size_t n = tr.size();
+  std::vector<std::pair<double, double> > out(n, std::make_pair(0.5, 0.5));
+  if (n == 0) return out;
+  std::vector<int32_t> base, bpos; std::vector<int64_t> toff, boff(n); std::vector<int32_t> tlen, blen(n);
+  std::string pri, sec;
+  detail::pack_traces(tr, base, toff, tlen);
+  for (std::size_t t = 0; t < n; ++t) {
+    if (bc[t]->primary.size() != bc[t]->bcPos.size() || bc[t]->secDecompose.size() != bc[t]->bcPos.size())
+      throw Error(TB_ERR_INVALID, "allelicFraction: primary / secDecompose / bcPos differ in length");
+    boff[t] = (int64_t)bpos.size(); blen[t] = (int32_t)bc[t]->bcPos.size();
+    bpos.insert(bpos.end(), bc[t]->bcPos.begin(), bc[t]->bcPos.end());
+    pri += bc[t]->primary; sec += bc[t]->secDecompose;
+  }
+  if (bpos.empty()) { bpos.push_back(0); pri.push_back('N'); sec.push_back('N'); }
+  std::vector<double> a1(n), a2(n);
+  tb_fraction_batch b{{base.data(), toff.data(), tlen.data()}, {bpos.data(), boff.data(), blen.data()}, pri.data(), sec.data(), (int32_t)c.trimLeft,
+                      (int32_t)c.trimRight, n, TB_MEM_HOST};
+  g.check(tb_allelic_fraction(g.get(), &b, a1.data(), a2.data()));
+  for (std::size_t t = 0; t < n; ++t) out[t] = std::make_pair(a1[t], a2[t]);
+  return out;
+}
+template <typename TConfig, typename TTrace, typename TBaseCalls>
+inline std::pair<double, double> allelicFraction(Context& g, TConfig const& c, TTrace const& tr, TBaseCalls const& bc) {
+  return allelicFractionBatch(g, c, std::vector<const TTrace*>{&tr}, std::vector<const TBaseCalls*>{&bc})[0];
+}
+
+// The reference text on the device, indexed for anchoring (stands where tracy holds its csa_wt<> FM-index).
+class Index {
+ public:
+  Index(Context& g, std::string const& text) : g_(g) { g.check(tb_index_build(g.get(), text.data(), (int64_t)text.size(), TB_MEM_HOST, &idx_)); }
+  ~Index() { tb_index_destroy(g_.get(), idx_); }
+  Index(const Index&) = delete;
+  Index& operator=(const Index&) = delete;
+  const tb_index* get() const { return idx_; }
+ private:
+  Context& g_;
+  tb_index* idx_ = nullptr;
+};
+
+// The anchoring part of getReferenceSlice(c, fm_index, bc, rs) -- reference src/fmindex.h:236-284 -- for many traces:
+// sets rs.forward and rs.kmersupport, returns per trace whether the reference function would return true, and (optionally)
+// bestPos, from which tb_reference_slice gives the slice the reference then fetches (:286-305).
+template <typename TConfig, typename TBaseCalls, typename TRefSlice>
+inline std::vector<char> anchorBatch(Context& g, Index const& index, TConfig const& c, std::vector<const TBaseCalls*> const& bc,
+                                     std::vector<TRefSlice*> const& rs, std::vector<int64_t>* bestpos = nullptr) {
+  const std::size_t n = bc.size();
+  std::vector<char> ok(n, 0);
+  if (n == 0) return ok;
+  std::string cons; std::vector<int64_t> off(n); std::vector<int32_t> len(n);
+  for (std::size_t t = 0; t < n; ++t) { off[t] = (int64_t)cons.size(); len[t] = (int32_t)bc[t]->consensus.size(); cons += bc[t]->consensus; }
+  if (cons.empty()) cons.push_back('N');
+  std::vector<uint8_t> anchored(n), forward(n); std::vector<uint32_t> support(n); std::vector<int64_t> pos(n);
+  tb_arena a{cons.data(), off.data(), len.data()};
+  tb_anchor_result r{anchored.data(), forward.data(), support.data(), pos.data(), nullptr};
+  g.check(tb_anchor(g.get(), index.get(), &a, n, TB_MEM_HOST, tb_anchor_config{(int32_t)c.trimLeft, (int32_t)c.trimRight, (int32_t)c.kmer, (int32_t)c.minKmerSupport}, &r));
+  for (std::size_t t = 0; t < n; ++t) {
+    ok[t] = (char)anchored[t];
+    if (anchored[t]) { rs[t]->forward = forward[t] != 0; rs[t]->kmersupport = support[t]; }
+  }
+  if (bestpos) *bestpos = pos;
+  return ok;
+}
+
 }  // namespace tracy_b200
 #endif  // TRACY_B200_HPP

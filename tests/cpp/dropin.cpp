@@ -133,6 +133,113 @@ static void decompose_check(tracy_b200::Context& g, int id, int ins, int del, in
   expect(out1.str() == out2.str(), "decomposeAlleles diagnostics", id);
 }
 
+// a synthetic chromatogram of `seq` (optionally a second allele mixed in): Gaussian-ish peaks every 12 samples
+static void make_trace(std::string const& seq, std::string const& seq2, double frac, tracy::Trace& tr) {
+  const size_t nbc = seq.size(), ns = 12 * nbc + 40;
+  tr = tracy::Trace();
+  tr.traceACGT.assign(4, tracy::Trace::TMountains(ns, 0));
+  for (int k = 0; k < 4; ++k) for (size_t p = 0; p < ns; ++p) tr.traceACGT[k][p] = (int32_t)(rng() % 20);
+  auto slot = [](char c) { return c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0; };
+  for (size_t j = 0; j < nbc; ++j) {
+    const int pos = (int)(12 * j + 10 + rng() % 3);
+    tr.basecallpos.push_back(pos);
+    const int h = 700 + (int)(rng() % 500);
+    const int shape[5] = {15, 55, 100, 55, 15};
+    for (int d = -2; d <= 2; ++d) {
+      tr.traceACGT[slot(seq[j])][pos + d] += (int32_t)(h * frac * shape[d + 2] / 100);
+      if (!seq2.empty() && j < seq2.size()) tr.traceACGT[slot(seq2[j])][pos + d] += (int32_t)(h * (1 - frac) * shape[d + 2] / 100);
+    }
+  }
+}
+static bool same_profile(TProfile const& x, TProfile const& y) {
+  if (x.shape()[1] != y.shape()[1]) return false;
+  for (size_t k = 0; k < 6; ++k)
+    for (size_t j = 0; j < x.shape()[1]; ++j)
+      if (std::memcmp(&x[k][j], &y[k][j], sizeof(float)) != 0) return false;
+  return true;
+}
+// getReferenceSlice names htslib's faidx for indexed genomes (filetype 0); this check anchors in a single-sequence reference
+// (filetype 1), which never reaches them -- link-only stand-ins (htslib cannot be built in this container).
+struct faidx_t {};
+extern "C" {
+faidx_t* fai_load(const char*) { std::abort(); }
+void fai_destroy(faidx_t*) {}
+int faidx_nseq(const faidx_t*) { std::abort(); }
+const char* faidx_iseq(const faidx_t*, int) { std::abort(); }
+int faidx_seq_len(const faidx_t*, const char*) { std::abort(); }
+char* faidx_fetch_seq(const faidx_t*, const char*, int, int, int*) { std::abort(); }
+}
+struct AnchorCfg { boost::filesystem::path genome; uint16_t trimLeft, trimRight, kmer, maxindel, minKmerSupport; };
+
+// samples -> basecall -> createProfile -> findBreakpoint / reverseComplementProfile -> allelicFraction -> trimReferenceSlice
+static void pipeline_check(tracy_b200::Context& g, int id) {
+  const std::string ref = random_seq(900);
+  const int start = 50 + (int)(rng() % 100), L = 300 + (int)(rng() % 200), bpos = 100 + (int)(rng() % 100);
+  const std::string a1 = ref.substr(start, L);
+  const std::string a2 = id % 3 == 0 ? std::string() : (ref.substr(start, bpos) + ref.substr(start + bpos + 9)).substr(0, L);
+  tracy::Trace tr;
+  make_trace(a1, a2, 0.62, tr);
+  tracy::BaseCalls b1, b2;
+  tracy::basecall(tr, b1, 0.33f);
+  tracy_b200::basecall(g, tr, b2, 0.33f);
+  expect(b1.bcPos == b2.bcPos && b1.primary == b2.primary && b1.secondary == b2.secondary && b1.consensus == b2.consensus, "basecall", id);
+  TProfile p1, p2, q1, q2;
+  tracy::createProfile(tr, b1, p1, 20, 30);
+  tracy_b200::createProfile(g, tr, b1, p2, 20, 30);
+  expect(same_profile(p1, p2), "createProfile", id);
+  tracy::reverseComplementProfile(p1, q1);
+  tracy_b200::reverseComplementProfile(g, p1, q2);
+  expect(same_profile(q1, q2), "reverseComplementProfile", id);
+  tracy::TraceBreakpoint t1, t2;
+  tracy::findBreakpoint(p1, t1);
+  tracy_b200::findBreakpoint(p1, t2);
+  expect(t1.indelshift == t2.indelshift && t1.traceleft == t2.traceleft && t1.breakpoint == t2.breakpoint && t1.bestDiff == t2.bestDiff, "findBreakpoint", id);
+  DecompCfg c; c.trimLeft = 20; c.trimRight = 30; c.maxindel = 30; c.madc = 5;
+  b1.secDecompose = b1.secondary;
+  for (auto& ch : b1.secDecompose) if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') ch = 'N';
+  const std::pair<double, double> f1 = tracy::allelicFraction(c, tr, b1), f2 = tracy_b200::allelicFraction(g, c, tr, b1);
+  expect(std::memcmp(&f1, &f2, sizeof(f1)) == 0, "allelicFraction", id);
+  tracy::AlignConfig<true, false> semiglobal;
+  tracy::DnaScore<int32_t> sc(3, -5, -10, -4);
+  TAlign al;
+  tracy::ReferenceSlice r1, r2;
+  r1.refslice = id % 2 ? ref : random_seq(40) + ref; r1.forward = id % 2 == 0; r1.pos = 1000 + id; r2 = r1;
+  tracy_b200::gotoh(g, p1, r1.refslice, al, semiglobal, sc);
+  tracy::trimReferenceSlice(c, al, r1);
+  tracy_b200::trimReferenceSlice(c, al, r2);
+  expect(r1.refslice == r2.refslice && r1.pos == r2.pos, "trimReferenceSlice", id);
+}
+
+// getReferenceSlice over sdsl's FM-index against tracy_b200::anchorBatch over the sorted k-mer index (single-sequence reference)
+static void anchor_check(tracy_b200::Context& g) {
+  std::string text = random_seq(40000);
+  text.replace(20000, 1500, text.substr(5000, 1500));                    // a repeat: forces the non-unique pass for reads inside it
+  sdsl::csa_wt<> fm;
+  sdsl::construct_im(fm, text.c_str(), 1);
+  tracy_b200::Index index(g, text);
+  AnchorCfg c; c.genome = boost::filesystem::path("mem"); c.trimLeft = 50; c.trimRight = 50; c.kmer = 15; c.maxindel = 1000; c.minKmerSupport = 3;
+  std::vector<tracy::BaseCalls> bcs(24);
+  std::vector<const tracy::BaseCalls*> pb;
+  std::vector<tracy::ReferenceSlice> mine(24);
+  std::vector<tracy::ReferenceSlice*> pr;
+  for (int i = 0; i < 24; ++i) {
+    const int L = 200 + (int)(rng() % 800), p = i == 5 ? 20100 : i == 6 ? 5100 : (int)(rng() % (text.size() - L));
+    std::string s = mutate(text.substr(p, i == 5 || i == 6 ? 1200 : L), 0.01, 0.003);
+    if (i % 2) tracy::reverseComplement(s);
+    if (i == 23) s = random_seq(500);
+    bcs[i].consensus = s;
+    pb.push_back(&bcs[i]); pr.push_back(&mine[i]);
+  }
+  const std::vector<char> ok = tracy_b200::anchorBatch(g, index, c, pb, pr);
+  std::streambuf* old = std::cerr.rdbuf(nullptr);
+  for (int i = 0; i < 24; ++i) {
+    tracy::ReferenceSlice rs; rs.filetype = 1; rs.refslice = text;
+    const bool want = tracy::getReferenceSlice(c, fm, bcs[i], rs);
+    expect(want == (ok[i] != 0) && (!want || (rs.forward == mine[i].forward && rs.kmersupport == mine[i].kmersupport)), "getReferenceSlice anchoring", i);
+  }
+  std::cerr.rdbuf(old);
+}
+
 int main() {
   try {
     tracy_b200::Context g(0);
@@ -144,6 +251,8 @@ int main() {
     }
     const int shapes[][3] = {{0, 12, 1}, {9, 0, 1}, {0, 0, 4}, {5, 3, 1}, {0, 27, 2}, {14, 0, 1}, {0, 1, 0}, {1, 0, 0}};
     for (int i = 0; i < 16; ++i) decompose_check(g, 100 + i, shapes[i % 8][0], shapes[i % 8][1], shapes[i % 8][2], i == 15);
+    for (int i = 0; i < 12; ++i) pipeline_check(g, 200 + i);
+    anchor_check(g);
     // batch form: the same pairs in one call
     {
       std::vector<TProfile> ps(8);

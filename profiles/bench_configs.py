@@ -60,4 +60,38 @@ R = [ref[i % 64] for i in range(NTd)]; P = [pri[i % 64] for i in range(NTd)]; S 
 t = timed(lambda: ctx.decompose_sweep(R, P, S, [950] * NTd, [300] * NTd, [310] * NTd, [30] * NTd, [30] * NTd), reps=2)
 out["decompose_sweep_10k_traces_pm30"] = {"traces": NTd, "kernel_ms": ctx.last_kernel_ms()["sweep_ms"], "host_call_s": t,
                                           "compared_columns_per_s": NTd * 59 * 650 / (ctx.last_kernel_ms()["sweep_ms"] * 1e-3)}
+
+# config 3 tail: allelicFraction (FP64 grid fit) for 2 000 heterozygous traces of 600 basecalls, ~150 differing positions each
+NF = 2000
+tr_l, pos_l, pri_l, sec_l = [], [], [], []
+for i in range(64):
+    nbc = 600
+    ns = 12 * nbc + 30
+    tr = rng.integers(0, 40, size=(4, ns)).astype(np.int32)
+    pos = (12 * np.arange(nbc) + 8).astype(np.int32)
+    pri = bytearray(rng.choice(list(b"ACGT"), nbc).astype(np.uint8).tobytes()); sec = bytearray(pri)
+    for j in range(nbc):
+        a = b"ACGT".index(pri[j]); h = int(rng.integers(500, 1500))
+        if rng.random() < 0.3:
+            b = (a + int(rng.integers(1, 4))) % 4
+            sec[j] = b"ACGT"[b]; tr[a, pos[j]] += int(h * 0.6); tr[b, pos[j]] += int(h * 0.4)
+        else:
+            tr[a, pos[j]] += h
+    tr_l.append(tr); pos_l.append(pos); pri_l.append(bytes(pri)); sec_l.append(bytes(sec))
+sel = [i % 64 for i in range(NF)]
+t = timed(lambda: ctx.allelic_fraction([tr_l[i] for i in sel], [pos_l[i] for i in sel], [pri_l[i] for i in sel], [sec_l[i] for i in sel], 50, 50), reps=2)
+fm = C = None
+import ctypes
+v = ctypes.c_float()
+ctx._lib.tb_ctx_last_fraction_ms(ctx._h, ctypes.byref(v))
+out["allelic_fraction_2k_traces"] = {"traces": NF, "kernel_ms": v.value, "host_call_s": t, "traces_per_s_kernel": NF / (v.value * 1e-3),
+                                     "grid_points_per_trace": 176851}
+
+# ingest: 4 000 ABIF files of 12 k samples x 4 channels (host directory walk + GPU unpack), host clock around the call
+chs = [rng.integers(0, 2000, 12000) for _ in range(4)]
+f = synth.abif_bytes(chs, b"GATC", np.arange(990) * 12 + 20, synth.random_seq(rng, 990), rng.integers(0, 60, 990))
+files = [f] * 4000
+t = timed(lambda: ctx.read_traces(files), reps=2)
+out["ingest_4k_abif_files"] = {"files": len(files), "file_bytes": len(f), "host_call_s": t, "files_per_s": len(files) / t,
+                               "note": "Python list/array assembly included; the GPU unpack itself is copy-bound"}
 print(json.dumps(out, indent=1))

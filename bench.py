@@ -167,12 +167,34 @@ def workload_config(args, world):
 
 
 # ---- the B200 arm ----------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank to the CPUs NVML names as local to its GPU BEFORE the pinned staging buffers are allocated, so that
+    they land on the GPU's NUMA node (one process per GPU; 8 ranks copying 2.4 GB per step each otherwise share one node's
+    memory controller). Returns the number of CPUs bound to, 0 when NVML has no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import tracy_b200
     from tracy_b200 import AlignConfig, DnaScore
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; tracy_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else 0
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -311,7 +333,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": world * (se1["h2d_bytes"] - se0["h2d_bytes"]) // args.steps,      # every rank moves the same amount
                 "d2h_bytes_per_step": world * (se1["d2h_bytes"] - se0["d2h_bytes"]) // args.steps},
-        "gpu_launches": launches, "roofline": roof, "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps,
+        "gpu_launches": launches, "roofline": roof, "clocks": clocks, "host_cpus_bound_per_rank": numa_cpus, "wall_ms_per_step": wall_ms / args.steps,
         "kernel_ms": {k: v / args.steps for k, v in kern.items()}, "parity": dict(chk, score_checksum=checksum), "gen_seconds": gen_s,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -12,7 +12,8 @@
 // results behind. tests/cpp/dropin.cpp compiles them in ONE translation unit with the unmodified reference headers and
 // compares the two implementations call by call.
 //
-// Batch forms (gotohBatch, decomposeAllelesBatch) are what the GPU is for: one call for many independent traces.
+// Batch forms (gotohBatch, decomposeAllelesBatch, basecallBatch, ... and the drivers alignBatch / alignGenomeBatch) are what
+// the GPU is for: one call for many independent traces.
 #ifndef TRACY_B200_HPP
 #define TRACY_B200_HPP
 
@@ -549,6 +550,131 @@ inline std::vector<char> anchorBatch(Context& g, Index const& index, TConfig con
   }
   if (bestpos) *bestpos = pos;
   return ok;
+}
+
+// ---- batch drivers: the DP sequence of sage() for many traces ---------------------------------------------------------
+// reverseComplement(std::string&), reference src/fmindex.h:11-26: reversed and upper-cased, A<->T, C<->G, N kept; any other
+// character leaves the ORIGINAL character of that slot in place (the reference's `default: break`).
+inline void reverseComplement(std::string& sequence) {
+  const std::string fwd(sequence);
+  const std::size_t n = fwd.size();
+  for (std::size_t i = 0; i < n; ++i) {
+    char c = fwd[n - 1 - i];
+    if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+    switch (c) {
+      case 'A': sequence[i] = 'T'; break;
+      case 'C': sequence[i] = 'G'; break;
+      case 'G': sequence[i] = 'C'; break;
+      case 'T': sequence[i] = 'A'; break;
+      case 'N': sequence[i] = 'N'; break;
+      default: break;
+    }
+  }
+}
+
+namespace detail {
+// gapped rows of gotoh(profile, refstring) from an s/h/v string, into any [2][L] array
+template <typename TProfile, typename TAlign>
+inline void rows_into(TProfile const& p, std::string const& ref, std::string const& ops, TAlign& align) {
+  const std::size_t L = ops.size();
+  resize_align(align, 2, L);
+  std::string r0(L, '\0'), r1(L, '\0');
+  const int rc = tb_rows_from_ops(2, p.data(), (int32_t)p.shape()[1], ref.data(), (int32_t)ref.size(), reinterpret_cast<const uint8_t*>(ops.data()), (int32_t)L, &r0[0], &r1[0]);
+  if (rc != TB_OK) throw Error(rc, tb_strerror(rc));
+  for (std::size_t j = 0; j < L; ++j) { align[0][j] = r0[j]; align[1][j] = r1[j]; }
+}
+// trimReferenceSlice + final alignment, shared by the two drivers below (src/sage.h:258-260, :311)
+template <typename TConfig, typename TProfile, typename TRefSlice, typename TAlign, typename TAlignConfig, typename TScore>
+inline void trim_and_align(Context& g, TConfig const& c, std::vector<std::size_t> const& live, std::vector<const TProfile*> const& trimmed,
+                           std::vector<const TProfile*> const& full, std::vector<TRefSlice*> const& rs, std::vector<TAlign*> const& final_align,
+                           std::vector<int32_t>& scores, TAlignConfig const& ac, TScore const& sc) {
+  if (live.empty()) return;
+  std::vector<const TProfile*> pa, pf;
+  std::vector<const std::string*> pb;
+  for (std::size_t i : live) { pa.push_back(trimmed[i]); pf.push_back(full[i]); pb.push_back(&rs[i]->refslice); }
+  std::vector<std::string> ops;
+  gotohBatch(g, pa, pb, ac, sc, &ops);                                   // gotoh(trimmedtrace, prefslice, align, ...)
+  for (std::size_t k = 0; k < live.size(); ++k) {
+    Matrix<char> al;
+    const std::size_t L = ops[k].size();
+    al.resize(2, L);                                                     // only the gap pattern matters to trimReferenceSlice
+    for (std::size_t j = 0; j < L; ++j) { al[0][j] = ops[k][j] == 'h' ? '-' : 'X'; al[1][j] = ops[k][j] == 'v' ? '-' : 'X'; }
+    trimReferenceSlice(c, al, *rs[live[k]]);
+  }
+  const std::vector<int32_t> s = gotohBatch(g, pf, pb, ac, sc, &ops);    // gotoh(fulltraceprofile, referenceprofile, final, ...)
+  for (std::size_t k = 0; k < live.size(); ++k) {
+    scores[live[k]] = s[k];
+    rows_into(*pf[k], rs[live[k]]->refslice, ops[k], *final_align[live[k]]);
+  }
+}
+}  // namespace detail
+
+// `tracy align` against single-FASTA references for many traces -- the DP sequence of sage(), reference src/sage.h:233-260,
+// :311: both orientation scores of every trace in one score-only call (strict '>' picks forward), the semi-global alignment
+// of the trimmed trace, trimReferenceSlice, the final alignment of the full trace. On entry rs[i]->refslice holds the
+// reference sequence (upper-case ACGTN); on return rs[i] is what sage() leaves (forward, refslice, pos; kmersupport = 0),
+// final_align[i] the reported alignment. Returns the scores of the final alignments.
+template <typename TConfig, typename TProfile, typename TRefSlice, typename TAlign, typename TAlignConfig, typename TScore>
+inline std::vector<int32_t> alignBatch(Context& g, TConfig const& c, std::vector<const TProfile*> const& trimmed, std::vector<const TProfile*> const& full,
+                                       std::vector<TRefSlice*> const& rs, std::vector<TAlign*> const& final_align, TAlignConfig const& semiglobal,
+                                       TScore const& sc) {
+  const std::size_t n = trimmed.size();
+  std::vector<int32_t> scores(n, 0);
+  if (n == 0) return scores;
+  std::vector<std::string> rev(n);
+  std::vector<const TProfile*> pa(2 * n);
+  std::vector<const std::string*> pb(2 * n);
+  for (std::size_t i = 0; i < n; ++i) {
+    rev[i] = rs[i]->refslice; reverseComplement(rev[i]);
+    pa[i] = pa[n + i] = trimmed[i]; pb[i] = &rs[i]->refslice; pb[n + i] = &rev[i];
+  }
+  const std::vector<int32_t> gs = gotohBatch(g, pa, pb, semiglobal, sc);  // gsFwd / gsRev, src/sage.h:239-240
+  std::vector<std::size_t> live(n);
+  for (std::size_t i = 0; i < n; ++i) {
+    live[i] = i;
+    rs[i]->kmersupport = 0; rs[i]->pos = 0;
+    rs[i]->forward = gs[i] > gs[n + i];                                   // src/sage.h:247
+    if (!rs[i]->forward) rs[i]->refslice.swap(rev[i]);
+  }
+  detail::trim_and_align(g, c, live, trimmed, full, rs, final_align, scores, semiglobal, sc);
+  return scores;
+}
+
+// `tracy align` against an INDEXED genome for many traces -- reference src/sage.h:216-222, :258-260, :311 with
+// getReferenceSlice (src/fmindex.h:236-326) anchored on the GPU. seqs: the genome's sequences (what `index` was built from,
+// joined and ended by '\n'); names: their names (rs.chr). anchored[i] == 0 where the reference prints "Couldn't anchor the
+// Sanger trace" and gives up (rs[i], final_align[i] untouched apart from the defaults).
+template <typename TConfig, typename TBaseCalls, typename TProfile, typename TRefSlice, typename TAlign, typename TAlignConfig, typename TScore>
+inline std::vector<int32_t> alignGenomeBatch(Context& g, Index const& index, std::vector<std::string> const& names, std::vector<std::string> const& seqs,
+                                             TConfig const& c, std::vector<const TBaseCalls*> const& bc, std::vector<const TProfile*> const& trimmed,
+                                             std::vector<const TProfile*> const& full, std::vector<TRefSlice*> const& rs, std::vector<TAlign*> const& final_align,
+                                             TAlignConfig const& semiglobal, TScore const& sc, std::vector<char>* anchored = nullptr) {
+  const std::size_t n = bc.size();
+  std::vector<int32_t> scores(n, 0);
+  if (n == 0) return scores;
+  std::vector<int64_t> bestpos;
+  const std::vector<char> ok = anchorBatch(g, index, c, bc, rs, &bestpos);
+  std::vector<uint32_t> seqlen(seqs.size());
+  for (std::size_t k = 0; k < seqs.size(); ++k) seqlen[k] = (uint32_t)seqs[k].size() + 1;      // src/fmindex.h:247
+  std::vector<std::size_t> live;
+  for (std::size_t i = 0; i < n; ++i) {
+    if (!ok[i]) continue;
+    int32_t ri = 0; uint32_t chrpos = 0, s0 = 0, s1 = 0;
+    const int rc = tb_reference_slice(bestpos[i], seqlen.data(), (int32_t)seqlen.size(), (int32_t)bc[i]->consensus.size(), (int32_t)c.maxindel, &ri, &chrpos, &s0, &s1);
+    if (rc != TB_OK) throw Error(rc, tb_strerror(rc));
+    std::string const& chr = seqs[(std::size_t)ri];
+    // faidx_fetch_seq(fai, chr, slicestart, sliceend) is end-INCLUSIVE and clips to the sequence (htslib faidx.c:914-991)
+    const std::size_t e = std::min<std::size_t>(s1, chr.empty() ? 0 : chr.size() - 1);
+    rs[i]->chr = names[(std::size_t)ri];
+    rs[i]->pos = s0;
+    rs[i]->refslice = s0 <= e && !chr.empty() ? chr.substr(s0, e - s0 + 1) : std::string();
+    for (auto& ch : rs[i]->refslice) if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);        // to_upper_copy, src/fmindex.h:302
+    if (!rs[i]->forward) reverseComplement(rs[i]->refslice);
+    live.push_back(i);
+  }
+  detail::trim_and_align(g, c, live, trimmed, full, rs, final_align, scores, semiglobal, sc);
+  if (anchored) *anchored = ok;
+  return scores;
 }
 
 }  // namespace tracy_b200

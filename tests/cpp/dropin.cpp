@@ -158,16 +158,35 @@ static bool same_profile(TProfile const& x, TProfile const& y) {
       if (std::memcmp(&x[k][j], &y[k][j], sizeof(float)) != 0) return false;
   return true;
 }
-// getReferenceSlice names htslib's faidx for indexed genomes (filetype 0); this check anchors in a single-sequence reference
-// (filetype 1), which never reaches them -- link-only stand-ins (htslib cannot be built in this container).
-struct faidx_t {};
+// getReferenceSlice fetches the slice of an indexed genome through htslib's faidx, which cannot be built in this container:
+// in-memory stand-in with faidx.c's documented behaviour (faidx_fetch_seq is end-INCLUSIVE and clips, htslib faidx.c:914-991).
+struct faidx_t { std::vector<std::string> names, seqs; };
+static faidx_t g_genome;
 extern "C" {
-faidx_t* fai_load(const char*) { std::abort(); }
-void fai_destroy(faidx_t*) {}
-int faidx_nseq(const faidx_t*) { std::abort(); }
-const char* faidx_iseq(const faidx_t*, int) { std::abort(); }
-int faidx_seq_len(const faidx_t*, const char*) { std::abort(); }
-char* faidx_fetch_seq(const faidx_t*, const char*, int, int, int*) { std::abort(); }
+faidx_t* fai_load(const char*) { return new faidx_t(g_genome); }
+void fai_destroy(faidx_t* f) { delete f; }
+int faidx_nseq(const faidx_t* f) { return (int)f->names.size(); }
+const char* faidx_iseq(const faidx_t* f, int i) { return f->names[i].c_str(); }
+int faidx_seq_len(const faidx_t* f, const char* seq) {
+  for (size_t i = 0; i < f->names.size(); ++i) if (f->names[i] == seq) return (int)f->seqs[i].size();
+  return -1;
+}
+char* faidx_fetch_seq(const faidx_t* f, const char* name, int beg, int end, int* len) {
+  for (size_t i = 0; i < f->names.size(); ++i) {
+    if (f->names[i] != name) continue;
+    long long L = (long long)f->seqs[i].size(), b = beg, e = end;
+    if (e < b) b = e;
+    if (b < 0) b = 0; else if (L <= b) b = L;
+    if (e < 0) e = 0; else if (L <= e) e = L - 1;
+    long long n = e + 1 - b; if (n < 0) n = 0;
+    char* out = (char*)malloc((size_t)n + 1);
+    memcpy(out, f->seqs[i].data() + b, (size_t)n); out[n] = 0;
+    *len = (int)n;
+    return out;
+  }
+  *len = -2;
+  return NULL;
+}
 }
 struct AnchorCfg { boost::filesystem::path genome; uint16_t trimLeft, trimRight, kmer, maxindel, minKmerSupport; };
 
@@ -240,6 +259,91 @@ static void anchor_check(tracy_b200::Context& g) {
   std::cerr.rdbuf(old);
 }
 
+// sage()'s DP sequence per trace from the reference's own functions against tracy_b200::alignBatch (single FASTA) and
+// tracy_b200::alignGenomeBatch (indexed genome: getReferenceSlice over csa_wt<> + the faidx stand-in)
+static void driver_check(tracy_b200::Context& g) {
+  const int N = 10;
+  tracy::AlignConfig<true, false> semiglobal;
+  tracy::DnaScore<int32_t> sc(3, -5, -10, -4);
+  std::vector<std::string> names = {"chrA", "chrB"}, seqs = {random_seq(9000), random_seq(6000)};
+  const std::string text = seqs[0] + "\n" + seqs[1] + "\n";
+  g_genome.names = names; g_genome.seqs = seqs;
+  sdsl::csa_wt<> fm;
+  sdsl::construct_im(fm, text.c_str(), 1);
+  tracy_b200::Index index(g, text);
+  AnchorCfg c; c.genome = boost::filesystem::path("mem"); c.trimLeft = 40; c.trimRight = 30; c.kmer = 15; c.maxindel = 250; c.minKmerSupport = 3;
+  std::vector<tracy::Trace> tr(N);
+  std::vector<tracy::BaseCalls> bc(N);
+  std::vector<TProfile> trimmed(N), full(N);
+  for (int i = 0; i < N; ++i) {
+    const int ch = i % 2, L = 300 + (int)(rng() % 300);
+    const int p = i == 3 ? 0 : i == 4 ? (int)seqs[ch].size() - L : (int)(rng() % (seqs[ch].size() - L));
+    std::string s = mutate(seqs[ch].substr(p, L), 0.01, 0.004);
+    if (i % 3 == 0) tracy::reverseComplement(s);
+    if (i == N - 1) s = random_seq(L);                                   // cannot be anchored
+    make_trace(s, std::string(), 1.0, tr[i]);
+    tracy::basecall(tr[i], bc[i], 0.33f);
+    tracy::createProfile(tr[i], bc[i], full[i]);
+    tracy::createProfile(tr[i], bc[i], trimmed[i], c.trimLeft, c.trimRight);
+  }
+  std::vector<const TProfile*> pt, pf;
+  std::vector<const tracy::BaseCalls*> pb;
+  for (int i = 0; i < N; ++i) { pt.push_back(&trimmed[i]); pf.push_back(&full[i]); pb.push_back(&bc[i]); }
+  // (a) single FASTA reference: a 1.5 kb window around the read
+  {
+    std::vector<tracy::ReferenceSlice> mine(N);
+    std::vector<tracy::ReferenceSlice*> pr;
+    std::vector<TAlign> fin(N);
+    std::vector<TAlign*> pa;
+    for (int i = 0; i < N; ++i) { mine[i].refslice = seqs[i % 2].substr(i * 300 % 3000, 2500); mine[i].chr = "fa"; pr.push_back(&mine[i]); pa.push_back(&fin[i]); }
+    std::vector<tracy::ReferenceSlice> want = mine;
+    const std::vector<int32_t> s = tracy_b200::alignBatch(g, c, pt, pf, pr, pa, semiglobal, sc);
+    for (int i = 0; i < N; ++i) {
+      tracy::ReferenceSlice& rs = want[i];
+      TProfile fwd, rev, prefslice, refprofile;
+      tracy::_createProfile(rs.refslice, fwd);
+      tracy::reverseComplementProfile(fwd, rev);
+      const int gf = tracy::gotohScore(trimmed[i], fwd, semiglobal, sc), gr = tracy::gotohScore(trimmed[i], rev, semiglobal, sc);
+      rs.kmersupport = 0; rs.pos = 0;
+      if (gf > gr) { rs.forward = true; tracy::copyProfile(fwd, prefslice); }
+      else { rs.forward = false; tracy::reverseComplement(rs.refslice); tracy::copyProfile(rev, prefslice); }
+      TAlign al, final;
+      tracy::gotoh(trimmed[i], prefslice, al, semiglobal, sc);
+      tracy::trimReferenceSlice(c, al, rs);
+      tracy::_createProfile(rs.refslice, refprofile);
+      const int score = tracy::gotoh(full[i], refprofile, final, semiglobal, sc);
+      expect(score == s[i] && same_align(final, fin[i]) && rs.forward == mine[i].forward && rs.refslice == mine[i].refslice && rs.pos == mine[i].pos,
+             "alignBatch (sage, single FASTA)", i);
+    }
+  }
+  // (b) indexed genome
+  {
+    std::vector<tracy::ReferenceSlice> mine(N);
+    std::vector<tracy::ReferenceSlice*> pr;
+    std::vector<TAlign> fin(N);
+    std::vector<TAlign*> pa;
+    for (int i = 0; i < N; ++i) { pr.push_back(&mine[i]); pa.push_back(&fin[i]); }
+    std::vector<char> anchored;
+    const std::vector<int32_t> s = tracy_b200::alignGenomeBatch(g, index, names, seqs, c, pb, pt, pf, pr, pa, semiglobal, sc, &anchored);
+    std::streambuf* old = std::cerr.rdbuf(nullptr);
+    for (int i = 0; i < N; ++i) {
+      tracy::ReferenceSlice rs; rs.filetype = 0;
+      const bool ok = tracy::getReferenceSlice(c, fm, bc[i], rs);
+      if (!ok) { expect(!anchored[i], "alignGenomeBatch (unanchored)", i); continue; }
+      TProfile prefslice, refprofile;
+      tracy::_createProfile(rs.refslice, prefslice);
+      TAlign al, final;
+      tracy::gotoh(trimmed[i], prefslice, al, semiglobal, sc);
+      tracy::trimReferenceSlice(c, al, rs);
+      tracy::_createProfile(rs.refslice, refprofile);
+      const int score = tracy::gotoh(full[i], refprofile, final, semiglobal, sc);
+      expect(anchored[i] && score == s[i] && same_align(final, fin[i]) && rs.forward == mine[i].forward && rs.refslice == mine[i].refslice &&
+             rs.pos == mine[i].pos && rs.chr == mine[i].chr && rs.kmersupport == mine[i].kmersupport, "alignGenomeBatch (sage, indexed genome)", i);
+    }
+    std::cerr.rdbuf(old);
+  }
+}
+
 int main() {
   try {
     tracy_b200::Context g(0);
@@ -253,6 +357,7 @@ int main() {
     for (int i = 0; i < 16; ++i) decompose_check(g, 100 + i, shapes[i % 8][0], shapes[i % 8][1], shapes[i % 8][2], i == 15);
     for (int i = 0; i < 12; ++i) pipeline_check(g, 200 + i);
     anchor_check(g);
+    driver_check(g);
     // batch form: the same pairs in one call
     {
       std::vector<TProfile> ps(8);

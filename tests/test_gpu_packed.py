@@ -167,3 +167,33 @@ def test_packed_config2_full_shape(ctx, oracle_port):
     finally:
         os.environ.pop("TRACY_B200_NO_PACKED", None)
     assert np.array_equal(s, s2) and np.array_equal(ol, ol2) and np.array_equal(ops, ops2)
+
+
+def test_host_pipeline_chunks_lanes_and_stage2(ctx, oracle_port, monkeypatch):
+    """The TB_MEM_HOST pipeline (chunks over three lanes, one kernel per chunk, stage 2 only for chunks whose windows hold N or
+    foreign characters, 5-of-6 profile rows copied): many small chunks give the same results as one chunk and as the oracle."""
+    rng = np.random.default_rng(2024)
+    N, m, n = 5000, 96, 260
+    prof, win = synth.align_batch(N, m, n, seed=9)
+    prof = prof.copy(); win = win.copy()
+    prof[:, 5, :] = rng.random((N, m), dtype=np.float32)          # the '-' row never enters _score (src/align.h:112-116)
+    for i in rng.choice(N, 400, replace=False):
+        win[i, rng.integers(0, n, 3)] = ord("N")                   # 5-class packed kernel
+    for i in rng.choice(N, 60, replace=False):
+        win[i, rng.integers(0, n)] = ord("R")                      # general kernel (scores 0 against everything)
+    a1, a2 = tracy_b200.uniform_profiles(prof), tracy_b200.uniform_seqs(win)
+    sc, ac = DnaScore(3, -5, -10, -4), AlignConfig(True, False)
+    monkeypatch.delenv("TRACY_B200_CHUNK", raising=False)
+    s0, o0, l0 = ctx.gotoh("ps", a1, a2, sc, ac)
+    for chunk, lanes in (("333", "3"), ("1000", "2"), ("128", "4")):
+        monkeypatch.setenv("TRACY_B200_CHUNK", chunk)
+        monkeypatch.setenv("TRACY_B200_LANES", lanes)
+        s1, o1, l1 = ctx.gotoh("ps", a1, a2, sc, ac)
+        assert np.array_equal(s0, s1) and np.array_equal(l0, l1)
+        assert all(bytes(o0[i, : l0[i]]) == bytes(o1[i, : l1[i]]) for i in range(0, N, 7))
+        s2 = ctx.gotoh("ps", a1, a2, sc, ac, traceback=False)[0]
+        assert np.array_equal(s0, s2)
+    monkeypatch.delenv("TRACY_B200_CHUNK"); monkeypatch.delenv("TRACY_B200_LANES")
+    for i in list(range(0, N, 97)) + [int(x) for x in np.nonzero((win == ord("R")).any(1))[0][:8]]:
+        ws, wops = oracle_port.gotoh_ps(prof[i], bytes(win[i]), 1, 0, (3, -5, -10, -4))
+        assert int(s0[i]) == ws and bytes(o0[i, : l0[i]]) == wops, i

@@ -552,6 +552,22 @@ inline std::vector<char> anchorBatch(Context& g, Index const& index, TConfig con
   return ok;
 }
 
+// distanceMatrix(c, sps, d) -- reference src/msa.h:33-42: d[i][j] = gotohScore(sps[i], sps[j], AlignConfig<true,true>) for
+// all i < j, as ONE batched GPU call (the N(N-1)/2 fills of assemble's all-pairs stage). sps: any indexable container of
+// profiles; d: any [n][n] array (only the upper triangle is written, like the reference).
+template <typename TConfig, typename TSeqProfiles, typename TDistArray>
+inline void distanceMatrix(Context& g, TConfig const& c, TSeqProfiles const& sps, TDistArray& d) {
+  typedef typename std::decay<decltype(sps[0])>::type TProfile;
+  const std::size_t n = sps.size();
+  std::vector<const TProfile*> a, b;
+  for (std::size_t i = 0; i < n; ++i)
+    for (std::size_t j = i + 1; j < n; ++j) { a.push_back(&sps[i]); b.push_back(&sps[j]); }
+  const std::vector<int32_t> s = gotohBatch(g, a, b, AlignConfig<true, true>(), c.aliscore);
+  std::size_t k = 0;
+  for (std::size_t i = 0; i < n; ++i)
+    for (std::size_t j = i + 1; j < n; ++j) d[i][j] = s[k++];
+}
+
 // ---- batch drivers: the DP sequence of sage() for many traces ---------------------------------------------------------
 // reverseComplement(std::string&), reference src/fmindex.h:11-26: reversed and upper-cased, A<->T, C<->G, N kept; any other
 // character leaves the ORIGINAL character of that slot in place (the reference's `default: break`).

@@ -23,6 +23,7 @@
 #include "fmindex.h"
 #include "profile.h"
 #include "decompose.h"
+#include "msa.h"
 
 #define TRACY_B200_WITH_BOOST
 #include "tracy_b200.hpp"
@@ -344,6 +345,23 @@ static void driver_check(tracy_b200::Context& g) {
   }
 }
 
+// distanceMatrix of assemble's all-pairs stage (src/msa.h:33-42)
+struct MsaCfg { tracy::DnaScore<int32_t> aliscore; MsaCfg() : aliscore(3, -5, -10, -4) {} };
+static void distance_check(tracy_b200::Context& g) {
+  const int N = 12;
+  const std::string contig = random_seq(115 * N + 400);
+  std::vector<TProfile> sps(N);
+  for (int i = 0; i < N; ++i) random_profile(mutate(contig.substr(115 * i, 400), 0.02, 0.005), sps[i], i % 4 == 0);
+  boost::multi_array<int, 2> d1(boost::extents[N][N]), d2(boost::extents[N][N]);
+  for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) d1[i][j] = d2[i][j] = -7;
+  MsaCfg c;
+  tracy::distanceMatrix(c, sps, d1);
+  tracy_b200::distanceMatrix(g, c, sps, d2);
+  bool ok = true;
+  for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) ok = ok && d1[i][j] == d2[i][j];
+  expect(ok, "distanceMatrix", 0);
+}
+
 int main() {
   try {
     tracy_b200::Context g(0);
@@ -358,6 +376,7 @@ int main() {
     for (int i = 0; i < 12; ++i) pipeline_check(g, 200 + i);
     anchor_check(g);
     driver_check(g);
+    distance_check(g);
     // batch form: the same pairs in one call
     {
       std::vector<TProfile> ps(8);

@@ -288,9 +288,9 @@ class Context:
         rc = self._lib.tb_trace_scan(_ptr(blob), _ptr(foff), _ptr(flen), n, C.cast(info, C.c_void_p))
         if rc != capi.TB_OK:
             raise TracyError(rc, self._lib.tb_strerror(rc).decode())
-        live = [i for i in range(n) if info[i].format >= 0 and info[i].status == 0]
-        ns = np.array([info[i].nsamples if i in set(live) else 0 for i in range(n)], np.int64)
-        nb = np.array([info[i].nbasecalls if i in set(live) else 0 for i in range(n)], np.int64)
+        live = [info[i].format >= 0 and info[i].status == 0 for i in range(n)]
+        ns = np.array([info[i].nsamples if live[i] else 0 for i in range(n)], np.int64)
+        nb = np.array([info[i].nbasecalls if live[i] else 0 for i in range(n)], np.int64)
         soff = np.concatenate([[0], np.cumsum(4 * ns)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
         boff = np.concatenate([[0], np.cumsum(nb)[:-1]]).astype(np.int64) if n else np.zeros(0, np.int64)
         samples = np.zeros(max(int(4 * ns.sum()), 1), np.int32)

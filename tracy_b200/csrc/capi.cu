@@ -1316,7 +1316,28 @@ int tb_trace_unpack(tb_ctx* ctx, const uint8_t* files, const int64_t* off, const
     TB_CUDA(ctx, tb::launch_trace_unpack(V, (int)fn, st));
     ctx->launches++;
   }
-  if (out_mem == TB_MEM_HOST) {
+  bool all_live = true;
+  for (size_t i = 0; i < nfiles; ++i) all_live = all_live && desc[i].format >= 0 && desc[i].status == 0;
+  if (out_mem == TB_MEM_HOST && all_live) {                 // every item was written: five bulk copies of the arenas' used extents
+    long long smin = LLONG_MAX, bmin = LLONG_MAX;
+    for (size_t i = 0; i < nfiles; ++i) { smin = std::min<long long>(smin, samples_off[i]); bmin = std::min<long long>(bmin, bc_off[i]); }
+    // holes between items (if the caller left any) would be overwritten with scratch contents: fall back to per-item copies then
+    long long sused = 0, bused = 0;
+    for (size_t i = 0; i < nfiles; ++i) { sused += 4ll * desc[i].ns; bused += desc[i].nb; }
+    if (sused == smax - smin && bused == bmax - bmin) {
+      if (sused) TB_CUDA(ctx, cudaMemcpyAsync(samples + smin, (const int32_t*)o_s + smin, (size_t)sused * 4, cudaMemcpyDeviceToHost, st));
+      if (bused) {
+        TB_CUDA(ctx, cudaMemcpyAsync(ploc + bmin, (const int32_t*)o_p + bmin, (size_t)bused * 4, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(ctx, cudaMemcpyAsync(qual + bmin, (const uint8_t*)o_q + bmin, (size_t)bused, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(ctx, cudaMemcpyAsync(basecalls1 + bmin, (const char*)o_1 + bmin, (size_t)bused, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(ctx, cudaMemcpyAsync(basecalls2 + bmin, (const char*)o_2 + bmin, (size_t)bused, cudaMemcpyDeviceToHost, st));
+      }
+      ctx->d2h += (size_t)sused * 4 + (size_t)bused * 7;
+    } else {
+      all_live = false;
+    }
+  }
+  if (out_mem == TB_MEM_HOST && !all_live) {
     for (size_t i = 0; i < nfiles; ++i) {                   // items may be sparse in the caller's arenas
       const tb::TraceDesc& d = desc[i];
       if (d.format < 0 || d.status != 0) continue;

@@ -104,7 +104,8 @@ int tb_ctx_last_packed_pairs(const tb_ctx* ctx, uint64_t* pairs);
  *       aligns against _createProfile(std::string) (src/align.h:121-136), as src/sage.h:233-258,
  *       src/indigo.h:228-236,302 and src/assemble.h:221-257 do: identical to _pp on the one-hot profile.
  * _pp : both profiles (wild-type trace reference, assemble all-pairs, MSA merges; src/msa.h:39,116,258,293).
- * _ss : both sequences, byte-equality scoring (src/align.h:96-101; src/indigo.h:359-387).
+ * _ss : both sequences, byte-equality scoring (src/align.h:96-101; src/indigo.h:359-387). Upper-case ACGTN pairs run on the
+ *       packed kernel, everything else on the general string kernel; identical results.
  * Pass res->ops == NULL for the gotohScore() shape. Profile values must be finite. */
 int tb_gotoh_ps(tb_ctx* ctx, const tb_batch* batch, tb_score sc, tb_align_config ac, tb_result* res);
 int tb_gotoh_pp(tb_ctx* ctx, const tb_batch* batch, tb_score sc, tb_align_config ac, tb_result* res);

@@ -197,3 +197,30 @@ def test_host_pipeline_chunks_lanes_and_stage2(ctx, oracle_port, monkeypatch):
     for i in list(range(0, N, 97)) + [int(x) for x in np.nonzero((win == ord("R")).any(1))[0][:8]]:
         ws, wops = oracle_port.gotoh_ps(prof[i], bytes(win[i]), 1, 0, (3, -5, -10, -4))
         assert int(s0[i]) == ws and bytes(o0[i, : l0[i]]) == wops, i
+
+
+def test_string_pairs_through_packed_kernel(ctx, oracle_port):
+    """tb_gotoh_ss: upper-case ACGTN pairs run on the packed kernel (a1's characters as one-hot profile columns); lower case,
+    IUPAC codes and gaps on either side are byte-compared by the general string kernel. Same results as the reference's
+    string overload (src/align.h:96-101) either way."""
+    rng = np.random.default_rng(321)
+    a1, a2 = [], []
+    for i in range(160):
+        m, n = int(rng.integers(1, 700)), int(rng.integers(1, 1400))
+        alpha1 = [b"ACGT", b"ACGTN", b"ACGTacgt", b"ACGTRY-", b"ACGT"][i % 5]
+        alpha2 = [b"ACGT", b"ACGTN", b"ACGT", b"ACGT", b"ACGTNn-K"][i % 5]
+        t = synth.random_seq(rng, n, alpha2)
+        s = bytearray(t[: min(m, n)]) + bytearray(synth.random_seq(rng, max(0, m - n), alpha1))
+        for q in rng.integers(0, len(s), max(1, len(s) // 12)):
+            s[q] = alpha1[int(rng.integers(0, len(alpha1)))]
+        a1.append(bytes(s)); a2.append(t)
+    total_packed = 0
+    for hf, vf, sc in ((1, 0, (3, -5, -10, -4)), (0, 0, (3, -5, -10, -4)), (1, 1, (5, -4, -10, -1)), (0, 1, (2, -3, -6, -2))):
+        s, ops, ol = ctx.gotoh("ss", a1, a2, DnaScore(*sc), AlignConfig(bool(hf), bool(vf)))
+        total_packed += ctx.last_packed_pairs()
+        s2 = ctx.gotoh("ss", a1, a2, DnaScore(*sc), AlignConfig(bool(hf), bool(vf)), traceback=False)[0]
+        assert np.array_equal(s, s2)
+        for i in range(len(a1)):
+            ws, wops = oracle_port.gotoh_ss(a1[i], a2[i], hf, vf, sc)
+            assert int(s[i]) == ws and bytes(ops[i, : ol[i]]) == wops, (hf, vf, i)
+    assert total_packed >= 4 * 60          # the ACGT / ACGTN pairs (2 of 5 alphabets) took the packed kernel

@@ -155,7 +155,7 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
   TB_CUDA(ctx, tb::gotoh_general_blocks_per_sm(mode, traceback, &bps_g));
   if (bps_g < 1) return fail(ctx, TB_ERR_CUDA, "general kernel does not fit on an SM");
   const int wpb_g = tb::gotoh_general_warps_per_block();
-  p.use_packed = mode == tb::kModePS &&
+  p.use_packed = (mode == tb::kModePS || mode == tb::kModeSS) &&   // string x string: a1's characters act as one-hot profile columns
                  tb::gotoh_packed_eligible(sh.maxm, sh.maxn, sc.match, sc.mismatch, sc.gap_open, sc.gap_extend) &&
                  getenv("TRACY_B200_NO_PACKED") == nullptr;
   int bps_p = 0, bps_p5 = 0, wpb_p = 1;
@@ -321,13 +321,14 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   for (size_t i = 0; i < np; ++i)
     if (l1[i] < 0 || l2[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative length");
   Shape all;
-  accumulate(all, l1, l2, np, mode == tb::kModePS);
+  accumulate(all, l1, l2, np, mode != tb::kModePP);
   if (traceback && res->ops_stride < all.maxsum) return fail(ctx, TB_ERR_INVALID, "ops_stride smaller than max(len1+len2)");
   if (int rc = check_range(ctx, all, sc)) return rc;
 
   tb::GotohBatch B{};
   B.match = sc.match; B.mismatch = sc.mismatch; B.go = sc.gap_open; B.ge = sc.gap_extend;
   B.hfree = ac.h_free != 0; B.vfree = ac.v_free != 0;
+  B.a_is_seq = mode == tb::kModeSS;
   B.order = nullptr;
 
   if (batch->mem == TB_MEM_DEVICE) {

@@ -35,6 +35,7 @@ struct GotohBatch {
   int2* rowbuf; unsigned long long rowbuf_slot;                        // 2 x (maxn+1) band-boundary rows (S,V)
   uint8_t* ops_scratch; unsigned long long ops_slot;                   // reversed traceback string
   unsigned int* counter;                                               // work-queue head
+  int a_is_seq;                                                        // packed kernel: a1 items are strings (string x string pairs), not profiles
 };
 
 // Device view of a decompose-sweep batch (sweep.cu).

@@ -135,19 +135,37 @@ __device__ __forceinline__ int walk_traceback_packed(const uint4* __restrict__ p
 
 // Substitution tables of one pass (rows base+1 .. base+1024), entries in per-half form: A = half-band A in the low half,
 // B = half-band B in the high half, so that A | B is the packed addend of one word. Layout [class][q][lane][4].
+// The five channel weights of a1's row r0. a1 is a profile float[6][m], or -- string x string pairs (reference src/align.h:96-101,
+// `s1[row] == s2[col] ? match : mismatch`) routed through this kernel -- a string whose character is its one-hot column:
+// sub_onehot then yields exactly match / mismatch. Byte equality is case-sensitive and knows no wildcard, so only upper-case
+// A,C,G,T,N are taken here; anything else sets *foreign and the pair is left to the general string kernel.
+__device__ __forceinline__ int strict_class(unsigned char ch) {
+  return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : ch == 'N' ? 4 : 5;
+}
+__device__ __forceinline__ void pk_row_weights(const void* a, bool aseq, int m, int r0, float p[5], int* foreign) {
+  if (aseq) {
+    const int c = strict_class(static_cast<const unsigned char*>(a)[r0]);
+    if (c == 5) *foreign = 1;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) p[k] = k == c ? 1.0f : 0.0f;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) p[k] = static_cast<const float*>(a)[(size_t)k * m + r0];
+  }
+}
+
 template <int CLASSES>
-__device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const float* a, int m, int base, float fmatch, float fmismatch, int lane,
-                                                int* smin_io = nullptr, int* smax_io = nullptr) {
-  int smin = 0, smax = 0;
+__device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const void* a, bool aseq, int m, int base, float fmatch, float fmismatch, int lane,
+                                                int* smin_io = nullptr, int* smax_io = nullptr, int* foreign_io = nullptr) {
+  int smin = 0, smax = 0, foreign = 0;
   __syncwarp();
 #pragma unroll 4
   for (int rr = lane; rr < kPkRows; rr += 32) {
     const int r0 = base + rr;                              // 0-based row of a1
     const int half = rr >> 9, rb = rr & 511, l = rb >> 4, i = rb & 15;
     const int at = (i >> 2) * 128 + l * 4 + (i & 3);
-    float p[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) p[k] = r0 < m ? a[(size_t)k * m + r0] : 0.0f;
+    float p[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (r0 < m) pk_row_weights(a, aseq, m, r0, p, &foreign);
     int* const tab = half ? tabB : tabA;
 #pragma unroll
     for (int cls = 0; cls < 5; ++cls) {                    // the range check always covers all five classes
@@ -159,6 +177,7 @@ __device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const floa
   }
   __syncwarp();
   if (smin_io) { *smin_io = min(*smin_io, smin); *smax_io = max(*smax_io, smax); }
+  if (foreign_io) *foreign_io |= foreign;
 }
 
 // ---- checkpointed traceback (TBMODE == kTbCkpt) -------------------------------------------------------------------
@@ -177,7 +196,7 @@ __device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const floa
 // change of pass) the next round is planned from the cell reached, so every round consumes at least one cell.
 // Cost at 1000 x 4000: ~5 rounds x ~20 k instructions against 1.44 M for flag extraction in every cell.
 struct PkPair {
-  const float* a; const unsigned char* b;
+  const void* a; bool aseq; const unsigned char* b;
   int m, n, T, NQ, go, ge, goe, bias;
   bool hfree, vfree;
   float fmatch, fmismatch;
@@ -217,7 +236,7 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
     // ================= plan one round from (r, c, state) =================
     const int pass = (r - 1) >> 10, rr0 = (r - 1) & 1023;
     const int v0 = ((rr0 >> 9) << 5) + ((rr0 & 511) >> 4), i0 = rr0 & 15;       // current block (0..63) and row inside it
-    if (pass != tab_pass) { pk_build_tables<CLASSES>(tabA, tabB, P.a, m, pass * kPkRows, P.fmatch, P.fmismatch, lane); tab_pass = pass; }
+    if (pass != tab_pass) { pk_build_tables<CLASSES>(tabA, tabB, P.a, P.aseq, m, pass * kPkRows, P.fmatch, P.fmismatch, lane); tab_pass = pass; }
     // the free end-gap row almost always starts with a long horizontal run: look left first there
     const bool horizontal = state == 1 || (first_round && hfree && r == m && state == 0);
     first_round = false;
@@ -437,16 +456,16 @@ gotoh_packed_kernel(const GotohBatch B) {
     if (B.status[pi]) continue;                          // finished by an earlier kernel of this call
     const int m = B.a_len[pi], n = B.b_len[pi];
     if (m == 0 || n == 0) continue;                      // degenerate shapes: general kernel
-    const float* const a = (const float*)B.a_base + B.a_off[pi];
+    const bool aseq = B.a_is_seq != 0;
+    const void* const a = aseq ? (const void*)((const char*)B.a_base + B.a_off[pi]) : (const void*)((const float*)B.a_base + B.a_off[pi]);
     const unsigned char* const b = (const unsigned char*)B.b_base + B.b_off[pi];
 
     // ---- per-pair range check (decides whether 16-bit biased fields are exact for this pair) ----
     int smin = 0, smax = 0, foreign = 0;
-    pk_build_tables<CLASSES>(tabA, tabB, a, m, 0, fmatch, fmismatch, lane, &smin, &smax);   // pass 0's tables double as the range scan
+    pk_build_tables<CLASSES>(tabA, tabB, a, aseq, m, 0, fmatch, fmismatch, lane, &smin, &smax, &foreign);   // pass 0's tables double as the range scan
     for (int r0 = kPkRows + lane; r0 < m; r0 += 32) {                                       // rows of later passes
       float p[5];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) p[k] = a[(size_t)k * m + r0];
+      pk_row_weights(a, aseq, m, r0, p, &foreign);
 #pragma unroll
       for (int cls = 0; cls < 5; ++cls) {
         const int s = sub_onehot(p, cls, fmatch, fmismatch);
@@ -458,7 +477,7 @@ gotoh_packed_kernel(const GotohBatch B) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) { const int j = j0 + 32 * u + lane; ch[u] = j < n ? b[j] : (unsigned char)'A'; }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) foreign |= base_class(ch[u]) >= CLASSES;
+      for (int u = 0; u < 8; ++u) foreign |= (aseq ? strict_class(ch[u]) : base_class(ch[u])) >= CLASSES;
     }
     smin = __reduce_min_sync(kFull, smin); smax = __reduce_max_sync(kFull, smax);
     if (__any_sync(kFull, foreign)) continue;
@@ -488,7 +507,7 @@ gotoh_packed_kernel(const GotohBatch B) {
       unsigned* const bot = rowbuf0 + (unsigned long long)((pass + 1) & 1) * (unsigned)(n + 1);
       const bool more = pass + 1 < npass;
 
-      if (pass > 0) pk_build_tables<CLASSES>(tabA, tabB, a, m, base, fmatch, fmismatch, lane);
+      if (pass > 0) pk_build_tables<CLASSES>(tabA, tabB, a, aseq, m, base, fmatch, fmismatch, lane);
 
       // ---- per-lane state ----
       const int rtop_lo = base + lane * kRowsPerLane, rtop_hi = rtop_lo + 512;   // DP row just above the lane's rows
@@ -645,7 +664,7 @@ gotoh_packed_kernel(const GotohBatch B) {
       int L;
       if (CKPT) {
         PkPair pp;
-        pp.a = a; pp.b = b; pp.m = m; pp.n = n; pp.T = T; pp.NQ = NQ; pp.go = go; pp.ge = ge; pp.goe = goe; pp.bias = bias;
+        pp.a = a; pp.aseq = aseq; pp.b = b; pp.m = m; pp.n = n; pp.T = T; pp.NQ = NQ; pp.go = go; pp.ge = ge; pp.goe = goe; pp.bias = bias;
         pp.hfree = hfree; pp.vfree = vfree; pp.fmatch = fmatch; pp.fmismatch = fmismatch;
         L = walk_traceback_ckpt<CLASSES>(pp, rowck, colck, span, tabA, tabB, npass - 1, ops_rev, lane);
       } else {

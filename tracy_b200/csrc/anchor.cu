@@ -348,20 +348,23 @@ int index_dir_chars(long long n) {
   while (d < 14 && (1ll << (2 * d)) * kBucketScan < n) ++d;
   return d;
 }
-// keys_a/pos_a are filled from the text and sorted into keys_b/pos_b (scratch, freed by the caller), from which the
-// records and then the directory are built.
-cudaError_t index_build(const unsigned char* text, long long n, unsigned long long* keys_a, unsigned* pos_a,
-                        unsigned long long* keys_b, unsigned* pos_b, void* temp, size_t temp_bytes,
-                        uint4* rec, uint2* dir, int dir_chars, int* invalid, cudaStream_t st) {
+// The build in three steps, so that the caller can release the sort's input columns before the records are allocated
+// (peak device memory 28 B per text character instead of 40):
+//   index_sort_text : keys/positions from the text into keys_a/pos_a, radix-sorted into keys_b/pos_b
+//   index_make_records / index_make_dir : records from the sorted columns, then the directory over the records
+cudaError_t index_sort_text(const unsigned char* text, long long n, unsigned long long* keys_a, unsigned* pos_a,
+                            unsigned long long* keys_b, unsigned* pos_b, void* temp, size_t temp_bytes, int* invalid, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(invalid, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  const long long blocks = (n + 255) / 256;
-  index_keys_kernel<<<(unsigned)blocks, 256, 0, st>>>(text, n, keys_a, pos_a, invalid);
+  index_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(text, n, keys_a, pos_a, invalid);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_a, keys_b, pos_a, pos_b, n, 0, 64, st);
-  if (e != cudaSuccess) return e;
-  index_records_kernel<<<(unsigned)blocks, 256, 0, st>>>(keys_b, pos_b, n, rec);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_a, keys_b, pos_a, pos_b, n, 0, 64, st);
+}
+cudaError_t index_make_records(const unsigned long long* keys_b, const unsigned* pos_b, long long n, uint4* rec, cudaStream_t st) {
+  index_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys_b, pos_b, n, rec);
+  return cudaGetLastError();
+}
+cudaError_t index_make_dir(const uint4* rec, long long n, uint2* dir, int dir_chars, cudaStream_t st) {
   index_dir_kernel<<<(1u << (2 * dir_chars)) / 256, 256, 0, st>>>(rec, n, dir_chars, dir);
   return cudaGetLastError();
 }

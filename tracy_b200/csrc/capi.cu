@@ -29,8 +29,10 @@ void scan_trace_file(const uint8_t* buf, int64_t n, TraceDesc* d);
 cudaError_t launch_trace_unpack(const TraceUnpack& U, int nfiles, cudaStream_t st);
 cudaError_t launch_allelic_fraction(const FractionBatch& F, int ntraces, int maxD, cudaStream_t st);
 cudaError_t index_sort_temp_bytes(long long n, size_t* bytes);
-cudaError_t index_build(const unsigned char* text, long long n, unsigned long long* keys_a, unsigned* pos_a, unsigned long long* keys_b,
-                        unsigned* pos_b, void* temp, size_t temp_bytes, uint4* rec, uint2* dir, int dir_chars, int* invalid, cudaStream_t st);
+cudaError_t index_sort_text(const unsigned char* text, long long n, unsigned long long* keys_a, unsigned* pos_a, unsigned long long* keys_b,
+                            unsigned* pos_b, void* temp, size_t temp_bytes, int* invalid, cudaStream_t st);
+cudaError_t index_make_records(const unsigned long long* keys_b, const unsigned* pos_b, long long n, uint4* rec, cudaStream_t st);
+cudaError_t index_make_dir(const uint4* rec, long long n, uint2* dir, int dir_chars, cudaStream_t st);
 int index_dir_chars(long long n);
 cudaError_t launch_anchor_unique(const KmerIndexView& X, const AnchorBatch& A, int ntraces, unsigned tsize, cudaStream_t st);
 cudaError_t launch_anchor_count(const KmerIndexView& X, const AnchorBatch& A, int ntodo, cudaStream_t st);
@@ -994,17 +996,24 @@ int tb_index_build(tb_ctx* ctx, const char* text, int64_t text_len, int32_t mem,
 #define TB_IDX(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cleanup(cuda_fail(ctx, e__, #call)); } while (0)
   TB_IDX(tb::index_sort_temp_bytes(n, &temp_bytes));
   TB_IDX(cudaMalloc(&X->text, (size_t)n + 64));
-  TB_IDX(cudaMalloc(&X->rec, (size_t)n * 16)); TB_IDX(cudaMalloc(&X->dir, nd * 8));
   TB_IDX(cudaMalloc(&keys_a, (size_t)n * 8)); TB_IDX(cudaMalloc(&pos_a, (size_t)n * 4));
   TB_IDX(cudaMalloc(&keys_b, (size_t)n * 8)); TB_IDX(cudaMalloc(&pos_b, (size_t)n * 4));
   TB_IDX(cudaMalloc(&temp, temp_bytes ? temp_bytes : 1)); TB_IDX(cudaMalloc(&d_invalid, 4));
   TB_IDX(cudaMemcpyAsync(X->text, text, (size_t)n, mem == TB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
   if (mem == TB_MEM_HOST) ctx->h2d += (size_t)n;
-  TB_IDX(tb::index_build(X->text, n, keys_a, pos_a, keys_b, pos_b, temp, temp_bytes, X->rec, X->dir, X->dir_chars, d_invalid, st));
-  ctx->launches += 4;
+  TB_IDX(tb::index_sort_text(X->text, n, keys_a, pos_a, keys_b, pos_b, temp, temp_bytes, d_invalid, st));
   int invalid = 0;
   TB_IDX(cudaMemcpyAsync(&invalid, d_invalid, 4, cudaMemcpyDeviceToHost, st));
   TB_IDX(cudaStreamSynchronize(st));
+  // the sort's input columns and scratch go before the records come: 28 B per character at the peak instead of 40
+  cudaFree(keys_a); keys_a = nullptr; cudaFree(pos_a); pos_a = nullptr; cudaFree(temp); temp = nullptr;
+  if (!invalid) {
+    TB_IDX(cudaMalloc(&X->rec, (size_t)n * 16)); TB_IDX(cudaMalloc(&X->dir, nd * 8));
+    TB_IDX(tb::index_make_records(keys_b, pos_b, n, X->rec, st));
+    TB_IDX(tb::index_make_dir(X->rec, n, X->dir, X->dir_chars, st));
+    TB_IDX(cudaStreamSynchronize(st));
+  }
+  ctx->launches += 4;
 #undef TB_IDX
   if (invalid) return cleanup(fail(ctx, TB_ERR_UNSUPPORTED, "text holds a byte outside ACGTN, the IUPAC codes RYSWKMBDHV and '\\n'"));
   X->bytes = (size_t)n * 17 + nd * 8;

@@ -227,9 +227,24 @@ def run_b200(args, rank, world, local_rank):
     d_len = torch.zeros(P, dtype=torch.int32, device=dev)
     counts = [P] * world
     g_scores = torch.empty(P * world, dtype=torch.int32, device=dev) if world > 1 else None
-    if world > 1:   # the one broadcast the north star names: shared reference bytes, once, outside the steps
-        ref_blob = d_win[: min(P, 1024)].clone()
-        dist.broadcast(ref_blob, src=0)
+    bcast = None
+    if world > 1:   # the one broadcast the north star names: the reference text, once, outside the steps; every rank indexes its copy
+        try:
+            from tracy_b200 import shard
+            nref = 8_000_000
+            text = torch.zeros(nref, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                text.copy_(torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)[torch.randint(0, 4, (nref,), device=dev)])
+                text[-1] = 10
+            idx = shard.broadcast_genome_and_index(ctx, text, src=0)
+            probe = text[123456 + 1000 * rank: 123456 + 1000 * rank + 900].cpu().numpy().tobytes()
+            hit = ctx.anchor(idx, [probe])
+            bcast = {"text_bytes": nref, "index_device_bytes": int(idx.device_bytes),
+                     "anchor_check": bool(hit["anchored"][0]) and int(hit["bestpos"][0]) == 123456 + 1000 * rank}
+            idx.close()
+            del text
+        except Exception as e:   # the broadcast + index check must never take the bench down
+            bcast = {"error": str(e)[:200]}
 
     def device_step():
         ctx.gotoh_device("ps", d_prof.data_ptr(), d_aoff.data_ptr(), d_alen.data_ptr(), d_win.data_ptr(), d_boff.data_ptr(), d_blen.data_ptr(), P,
@@ -333,7 +348,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": world * (se1["h2d_bytes"] - se0["h2d_bytes"]) // args.steps,      # every rank moves the same amount
                 "d2h_bytes_per_step": world * (se1["d2h_bytes"] - se0["d2h_bytes"]) // args.steps},
-        "gpu_launches": launches, "roofline": roof, "clocks": clocks, "host_cpus_bound_per_rank": numa_cpus, "wall_ms_per_step": wall_ms / args.steps,
+        "gpu_launches": launches, "roofline": roof, "clocks": clocks, "host_cpus_bound_per_rank": numa_cpus, "reference_broadcast": bcast, "wall_ms_per_step": wall_ms / args.steps,
         "kernel_ms": {k: v / args.steps for k, v in kern.items()}, "parity": dict(chk, score_checksum=checksum), "gen_seconds": gen_s,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -163,6 +163,12 @@ class Context:
         self._check(self._lib.tb_index_build(self._h, _ptr(text), text.size, capi.TB_MEM_HOST, C.byref(h)))
         return KmerIndex(self, h)
 
+    def build_index_device(self, text_ptr, n):
+        """build_index for a text that already sits in HBM (e.g. after a broadcast over NCCL): raw device pointer + length."""
+        h = C.c_void_p()
+        self._check(self._lib.tb_index_build(self._h, C.c_void_p(int(text_ptr)), int(n), capi.TB_MEM_DEVICE, C.byref(h)))
+        return KmerIndex(self, h)
+
     def anchor(self, index, consensus, trim_left=50, trim_right=50, kmer=15, min_kmer_support=3):
         """scanSequence + findMaxFreq + the orientation rule of getReferenceSlice for a batch of consensus strings.
         Returns dict of arrays: anchored (bool), forward (bool), kmersupport (uint32), bestpos (int64), pass_ (uint8)."""

@@ -47,3 +47,12 @@ def gather_scores(local_scores, counts, group=None):
     out = torch.empty(world * mx, dtype=local_scores.dtype, device=local_scores.device)
     dist.all_gather_into_tensor(out, buf, group=group)
     return torch.cat([out[r * mx: r * mx + counts[r]] for r in range(world)])
+
+
+def broadcast_genome_and_index(ctx, text_tensor, src=0, group=None):
+    """The broadcast the north star names, with its consumer: rank `src` holds the reference text (uint8 tensor on the rank's
+    GPU; the other ranks pass a tensor of the same size), one NCCL broadcast over NVLink ships it, and every rank builds its
+    own anchoring index from the device copy (17 ms per 64 Mbp -- cheaper than shipping the 17 B/char index itself).
+    Returns the rank's KmerIndex."""
+    broadcast_reference(text_tensor, src=src, group=group)
+    return ctx.build_index_device(text_tensor.data_ptr(), text_tensor.numel())

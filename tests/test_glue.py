@@ -23,6 +23,12 @@ class OracleContext:
     def gotoh(self, kind, a1, a2, sc=DnaScore(3, -5, -10, -4), ac=AlignConfig(True, False), traceback=True, out=None):
         assert kind == "pp"
         s4 = (sc.match, sc.mismatch, sc.go, sc.ge)
+
+        def items(a):                                              # an Arena of offsets into one packed array, or a plain list
+            if isinstance(a, tracy_b200.Arena):
+                return [a.base[o: o + 6 * n_].reshape(6, n_) for o, n_ in zip(a.off, a.len)]
+            return a
+        a1, a2 = items(a1), items(a2)
         n = len(a1)
         scores = np.zeros(n, np.int32)
         stride = max(max((np.asarray(x).shape[1] + np.asarray(y).shape[1] for x, y in zip(a1, a2)), default=1), 1)

@@ -15,9 +15,40 @@ Tree building, row merging and consensus are integer/byte logic kept literal (ti
 """
 import numpy as np
 
-from .api import PP, AlignConfig, DnaScore
+from .api import PP, AlignConfig, Arena, DnaScore
 
 _END_FREE = AlignConfig(True, True)
+
+
+class _Pool:
+    """The profiles of one stage packed ONCE into a flat float32 array (reference layout per item) with spare slots; batches
+    of pairs are then arenas of offsets into it -- a pair list of N(N-1)/2 entries costs two index arrays, not a copy of
+    every profile per pair. The C ABI copies only the extent an arena touches."""
+
+    def __init__(self, profiles, spare=0):
+        ps = [np.ascontiguousarray(p, np.float32) for p in profiles]
+        self.cap = 6 * max([p.shape[1] for p in ps] + [1])
+        n = len(ps)
+        self.base = np.zeros((n + spare) * self.cap, np.float32)
+        self.off = np.arange(n + spare, dtype=np.int64) * self.cap
+        self.lens = np.zeros(n + spare, np.int32)
+        for i, p in enumerate(ps):
+            self.put(i, p)
+
+    def put(self, slot, p):
+        p = np.ascontiguousarray(p, np.float32)
+        self.lens[slot] = p.shape[1]
+        self.base[self.off[slot]: self.off[slot] + p.size] = p.reshape(-1)
+
+    def arena(self, idx):
+        idx = np.asarray(idx, np.int64)
+        return Arena(self.base, np.ascontiguousarray(self.off[idx]), np.ascontiguousarray(self.lens[idx]))
+
+
+def _revcomp(p):
+    """reverseComplementProfile (src/profile.h:74-90) on the host: columns reversed, rows A<->T and C<->G swapped, N and '-'
+    kept -- a pure permutation, no arithmetic (Context.revcomp_profile is the batched device version)."""
+    return np.ascontiguousarray(np.asarray(p, np.float32)[[3, 2, 1, 0, 4, 5], ::-1])
 
 
 # ---- small literal helpers -------------------------------------------------------------------------------------------
@@ -65,7 +96,8 @@ def distance_matrix(ctx, profiles, sc):
     ii, jj = np.triu_indices(n, 1)
     d = np.zeros((n, n), np.int64)
     if len(ii):
-        s, _, _ = ctx.gotoh(PP, [profiles[i] for i in ii], [profiles[j] for j in jj], sc, _END_FREE, traceback=False)
+        pool = _Pool(profiles)
+        s, _, _ = ctx.gotoh(PP, pool.arena(ii), pool.arena(jj), sc, _END_FREE, traceback=False)
         d[ii, jj] = s
     return d
 
@@ -197,8 +229,9 @@ def rev_seq_based_on_dist(ctx, profiles, fwd, sc):
     num = len(seq)
     d = np.zeros((num, num), np.int64)
     ii, jj = np.triu_indices(num, 1)
+    pool = _Pool(seq, spare=1)                                             # slot `num` holds the flip under trial
     if len(ii):
-        s, _, _ = ctx.gotoh(PP, [seq[i] for i in ii], [seq[j] for j in jj], sc, _END_FREE, traceback=False)
+        s, _, _ = ctx.gotoh(PP, pool.arena(ii), pool.arena(jj), sc, _END_FREE, traceback=False)
         d[ii, jj] = s
         d[jj, ii] = s
     total = int(d[ii, jj].sum()) if len(ii) else 0
@@ -206,14 +239,16 @@ def rev_seq_based_on_dist(ctx, profiles, fwd, sc):
     while iterate:
         quality = sorted((int(d[i].sum()), i) for i in range(num))      # worst row sum first, src/msa.h:270-282
         for _, k in quality:
-            s_rc = ctx.revcomp_profile([seq[k]])[0]
+            s_rc = _revcomp(seq[k])
             others = [i for i in range(num) if i != k]
             new_d = np.zeros(num, np.int64)
             if others:
-                sc_new, _, _ = ctx.gotoh(PP, [seq[i] for i in others], [s_rc] * len(others), sc, _END_FREE, traceback=False)
+                pool.put(num, s_rc)
+                sc_new, _, _ = ctx.gotoh(PP, pool.arena(others), pool.arena([num] * len(others)), sc, _END_FREE, traceback=False)
                 new_d[others] = sc_new
             if int(new_d.sum()) >= int(d[others, k].sum()):              # scoreSum >= oldScoreSum, src/msa.h:298
                 seq[k] = s_rc
+                pool.put(k, s_rc)
                 fwd[k] = not fwd[k]
                 d[:, k] = new_d
                 d[k, :] = new_d
@@ -233,9 +268,10 @@ def exclude_unmatched(ctx, profiles, sc, match_fraction):
     keep = [False] * n
     cand = {i: [j for j in range(n) if j != i] for i in range(n)}
     pending = [i for i in range(n) if cand[i]]
+    pool = _Pool(profiles)
     while pending:
         js = [cand[i].pop(0) for i in pending]
-        s, ops, ol = ctx.gotoh(PP, [profiles[i] for i in pending], [profiles[j] for j in js], sc, _END_FREE, traceback=True)
+        s, ops, ol = ctx.gotoh(PP, pool.arena(pending), pool.arena(js), sc, _END_FREE, traceback=True)
         nxt = []
         for k, i in enumerate(pending):
             num_aligned = int((ops[k, : ol[k]] == ord("s")).sum())

@@ -110,6 +110,9 @@ struct tb_ctx {
   float last_fast_ms = 0, last_general_ms = 0, last_sweep_ms = 0, last_call_ms = 0, last_anchor_ms = 0, last_fraction_ms = 0;
   uint64_t last_packed_pairs = 0;
   std::vector<int32_t> tmp_len1, tmp_len2;
+  int occ_general[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};   // blocks per SM, general kernel [mode][traceback]
+  int occ_packed[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};    // packed kernel [tbmode][4 / 5 classes]
+  size_t free_at_first_plan = 0;
 };
 
 namespace {
@@ -153,8 +156,10 @@ void accumulate(Shape& s, const int32_t* l1, const int32_t* l2, size_t n, bool p
 // Size the persistent grids and the per-slot scratch for a launch over `npairs` pairs with maxima `sh`.
 int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npairs, tb_score sc, Plan* out) {
   Plan p;
-  int bps_g = 0;
-  TB_CUDA(ctx, tb::gotoh_general_blocks_per_sm(mode, traceback, &bps_g));
+  // occupancy answers never change for a context: ask the runtime once per instantiation (a small call should not pay
+  // five occupancy queries and a cudaMemGetInfo every time)
+  int& bps_g = ctx->occ_general[mode][traceback ? 1 : 0];
+  if (bps_g < 0) TB_CUDA(ctx, tb::gotoh_general_blocks_per_sm(mode, traceback, &bps_g));
   if (bps_g < 1) return fail(ctx, TB_ERR_CUDA, "general kernel does not fit on an SM");
   const int wpb_g = tb::gotoh_general_warps_per_block();
   p.use_packed = (mode == tb::kModePS || mode == tb::kModeSS) &&   // string x string: a1's characters act as one-hot profile columns
@@ -164,8 +169,11 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
   if (p.use_packed) {
     const char* mode_env = getenv("TRACY_B200_TB_MODE");   // "flags" selects the pointer-flag fill (kept for comparison / profiling)
     p.tbmode = !traceback ? 0 : (mode_env && std::strcmp(mode_env, "flags") == 0) ? 1 : 2;
-    TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(p.tbmode, 4, &bps_p));
-    TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(p.tbmode, 5, &bps_p5));
+    int& c4 = ctx->occ_packed[p.tbmode][0];
+    int& c5 = ctx->occ_packed[p.tbmode][1];
+    if (c4 < 0) TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(p.tbmode, 4, &c4));
+    if (c5 < 0) TB_CUDA(ctx, tb::gotoh_packed_blocks_per_sm(p.tbmode, 5, &c5));
+    bps_p = c4; bps_p5 = c5;
     wpb_p = tb::gotoh_packed_warps_per_block();
     if (bps_p < 1 || bps_p5 < 1) p.use_packed = false;
   }
@@ -182,9 +190,12 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
   const unsigned long long per_slot = p.ptr_words * 8 + p.rowbuf_elems * 8 + p.ops_bytes;
   size_t limit = ctx->scratch_limit;
   if (limit == 0) {
-    size_t fr = 0, tot = 0;
-    TB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
-    limit = fr / 3;
+    if (ctx->free_at_first_plan == 0) {                     // free HBM when the context first planned (its own scratch not yet taken)
+      size_t fr = 0, tot = 0;
+      TB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+      ctx->free_at_first_plan = fr;
+    }
+    limit = ctx->free_at_first_plan / 3;
   }
   limit /= 3;   // up to three lanes hold scratch at a time by default
   unsigned long long max_slots = per_slot ? std::max<unsigned long long>(limit / per_slot, 1) : (1ull << 30);

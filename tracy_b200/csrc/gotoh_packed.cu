@@ -154,9 +154,10 @@ __device__ __forceinline__ void pk_row_weights(const void* a, bool aseq, int m, 
   }
 }
 
-template <int CLASSES>
-__device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const void* a, bool aseq, int m, int base, float fmatch, float fmismatch, int lane,
+template <int CLASSES, bool ASEQ>
+__device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const void* av, int m, int base, float fmatch, float fmismatch, int lane,
                                                 int* smin_io = nullptr, int* smax_io = nullptr, int* foreign_io = nullptr) {
+  const float* const a = static_cast<const float*>(av);
   int smin = 0, smax = 0, foreign = 0;
   __syncwarp();
 #pragma unroll 4
@@ -164,8 +165,15 @@ __device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const void
     const int r0 = base + rr;                              // 0-based row of a1
     const int half = rr >> 9, rb = rr & 511, l = rb >> 4, i = rb & 15;
     const int at = (i >> 2) * 128 + l * 4 + (i & 3);
-    float p[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    if (r0 < m) pk_row_weights(a, aseq, m, r0, p, &foreign);
+    float p[5];
+    if constexpr (ASEQ) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) p[k] = 0.0f;
+      if (r0 < m) pk_row_weights(av, true, m, r0, p, &foreign);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) p[k] = r0 < m ? a[(size_t)k * m + r0] : 0.0f;
+    }
     int* const tab = half ? tabB : tabA;
 #pragma unroll
     for (int cls = 0; cls < 5; ++cls) {                    // the range check always covers all five classes
@@ -196,7 +204,7 @@ __device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const void
 // change of pass) the next round is planned from the cell reached, so every round consumes at least one cell.
 // Cost at 1000 x 4000: ~5 rounds x ~20 k instructions against 1.44 M for flag extraction in every cell.
 struct PkPair {
-  const void* a; bool aseq; const unsigned char* b;
+  const void* a; const unsigned char* b;
   int m, n, T, NQ, go, ge, goe, bias;
   bool hfree, vfree;
   float fmatch, fmismatch;
@@ -212,7 +220,7 @@ __device__ __forceinline__ unsigned pk_span_nibble(unsigned long long w, int row
   return (row & 1) ? (byte & 15u) : (byte >> 4);
 }
 
-template <int CLASSES>
+template <int CLASSES, bool ASEQ>
 __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __restrict__ rowck, const uint4* __restrict__ colck,
                                                 unsigned long long* __restrict__ span, int* tabA, int* tabB, int tab_pass,
                                                 uint8_t* __restrict__ ops_rev, int lane) {
@@ -236,7 +244,7 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
     // ================= plan one round from (r, c, state) =================
     const int pass = (r - 1) >> 10, rr0 = (r - 1) & 1023;
     const int v0 = ((rr0 >> 9) << 5) + ((rr0 & 511) >> 4), i0 = rr0 & 15;       // current block (0..63) and row inside it
-    if (pass != tab_pass) { pk_build_tables<CLASSES>(tabA, tabB, P.a, P.aseq, m, pass * kPkRows, P.fmatch, P.fmismatch, lane); tab_pass = pass; }
+    if (pass != tab_pass) { pk_build_tables<CLASSES, ASEQ>(tabA, tabB, P.a, m, pass * kPkRows, P.fmatch, P.fmismatch, lane); tab_pass = pass; }
     // the free end-gap row almost always starts with a long horizontal run: look left first there
     const bool horizontal = state == 1 || (first_round && hfree && r == m && state == 0);
     first_round = false;
@@ -423,7 +431,7 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
   return k;
 }
 
-template <int TBMODE, bool VFREE, int CLASSES>
+template <int TBMODE, bool VFREE, int CLASSES, bool ASEQ>
 __global__ void __launch_bounds__(kPkWarps * 32, CLASSES == 4 ? 6 : 5)   // 12 / 10 warps per SM: what the tables allow
 gotoh_packed_kernel(const GotohBatch B) {
   constexpr bool TRACEBACK = TBMODE != kTbNone, FLAGS = TBMODE == kTbFlags, CKPT = TBMODE == kTbCkpt;
@@ -456,16 +464,21 @@ gotoh_packed_kernel(const GotohBatch B) {
     if (B.status[pi]) continue;                          // finished by an earlier kernel of this call
     const int m = B.a_len[pi], n = B.b_len[pi];
     if (m == 0 || n == 0) continue;                      // degenerate shapes: general kernel
-    const bool aseq = B.a_is_seq != 0;
-    const void* const a = aseq ? (const void*)((const char*)B.a_base + B.a_off[pi]) : (const void*)((const float*)B.a_base + B.a_off[pi]);
+    constexpr bool aseq = ASEQ;                          // string x string pairs (GotohBatch::a_is_seq) have their own instantiation
+    const float* const a = ASEQ ? reinterpret_cast<const float*>((const char*)B.a_base + B.a_off[pi]) : (const float*)B.a_base + B.a_off[pi];   // ASEQ: bytes, only touched through pk_row_weights
     const unsigned char* const b = (const unsigned char*)B.b_base + B.b_off[pi];
 
     // ---- per-pair range check (decides whether 16-bit biased fields are exact for this pair) ----
     int smin = 0, smax = 0, foreign = 0;
-    pk_build_tables<CLASSES>(tabA, tabB, a, aseq, m, 0, fmatch, fmismatch, lane, &smin, &smax, &foreign);   // pass 0's tables double as the range scan
+    pk_build_tables<CLASSES, ASEQ>(tabA, tabB, a, m, 0, fmatch, fmismatch, lane, &smin, &smax, &foreign);   // pass 0's tables double as the range scan
     for (int r0 = kPkRows + lane; r0 < m; r0 += 32) {                                       // rows of later passes
       float p[5];
-      pk_row_weights(a, aseq, m, r0, p, &foreign);
+      if constexpr (ASEQ) {
+        pk_row_weights(a, true, m, r0, p, &foreign);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) p[k] = a[(size_t)k * m + r0];
+      }
 #pragma unroll
       for (int cls = 0; cls < 5; ++cls) {
         const int s = sub_onehot(p, cls, fmatch, fmismatch);
@@ -507,7 +520,7 @@ gotoh_packed_kernel(const GotohBatch B) {
       unsigned* const bot = rowbuf0 + (unsigned long long)((pass + 1) & 1) * (unsigned)(n + 1);
       const bool more = pass + 1 < npass;
 
-      if (pass > 0) pk_build_tables<CLASSES>(tabA, tabB, a, aseq, m, base, fmatch, fmismatch, lane);
+      if (pass > 0) pk_build_tables<CLASSES, ASEQ>(tabA, tabB, a, m, base, fmatch, fmismatch, lane);
 
       // ---- per-lane state ----
       const int rtop_lo = base + lane * kRowsPerLane, rtop_hi = rtop_lo + 512;   // DP row just above the lane's rows
@@ -664,9 +677,9 @@ gotoh_packed_kernel(const GotohBatch B) {
       int L;
       if (CKPT) {
         PkPair pp;
-        pp.a = a; pp.aseq = aseq; pp.b = b; pp.m = m; pp.n = n; pp.T = T; pp.NQ = NQ; pp.go = go; pp.ge = ge; pp.goe = goe; pp.bias = bias;
+        pp.a = a; pp.b = b; pp.m = m; pp.n = n; pp.T = T; pp.NQ = NQ; pp.go = go; pp.ge = ge; pp.goe = goe; pp.bias = bias;
         pp.hfree = hfree; pp.vfree = vfree; pp.fmatch = fmatch; pp.fmismatch = fmismatch;
-        L = walk_traceback_ckpt<CLASSES>(pp, rowck, colck, span, tabA, tabB, npass - 1, ops_rev, lane);
+        L = walk_traceback_ckpt<CLASSES, ASEQ>(pp, rowck, colck, span, tabA, tabB, npass - 1, ops_rev, lane);
       } else {
         L = walk_traceback_packed(ptr, T, m, n, ops_rev, lane);
       }
@@ -701,17 +714,25 @@ bool gotoh_packed_eligible(int maxm, int maxn, int match, int mismatch, int go, 
 template <int TB_, bool VF_, int CL_>
 static cudaError_t packed_launch_one(const GotohBatch& B, int blocks, cudaStream_t stream) {
   const size_t smem = packed_smem_bytes(CL_);
-  cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_, CL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_, CL_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_, CL_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gotoh_packed_kernel<TB_, VF_, CL_><<<blocks, kPkWarps * 32, smem, stream>>>(B);
+  if (B.a_is_seq) gotoh_packed_kernel<TB_, VF_, CL_, true><<<blocks, kPkWarps * 32, smem, stream>>>(B);
+  else gotoh_packed_kernel<TB_, VF_, CL_, false><<<blocks, kPkWarps * 32, smem, stream>>>(B);
   return cudaGetLastError();
 }
 template <int TB_, bool VF_, int CL_>
 static cudaError_t packed_occ_one(int* out) {
+  // the profile and the string instantiations differ by a few registers; size the grid by the tighter one
   const size_t smem = packed_smem_bytes(CL_);
-  cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_, CL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_, CL_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gotoh_packed_kernel<TB_, VF_, CL_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, gotoh_packed_kernel<TB_, VF_, CL_>, kPkWarps * 32, smem);
+  int a = 0, b = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, gotoh_packed_kernel<TB_, VF_, CL_, false>, kPkWarps * 32, smem);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, gotoh_packed_kernel<TB_, VF_, CL_, true>, kPkWarps * 32, smem);
+  *out = a < b ? a : b;
+  return e;
 }
 
 #define TB_PK_DISPATCH(FN, ...)                                                                       \

@@ -652,7 +652,10 @@ gotoh_packed_kernel(const GotohBatch B) {
         } else if (st0 < 64 || st1 >= n) {
           for (int st = st0; st < st1; ++st) do_step(st, std::true_type(), std::false_type());
         } else {
-#pragma unroll 2
+          // Not unrolled when a traceback follows: the x2 body (ping-pong row registers, 4.7 KB) plus the walk's code thrash the
+          // instruction cache (98.2 ms against 101.7 ms per 100 k pairs; x4: 110 ms). gotohScore has no walk: x4 there (69.0 ms
+          // against 72.2 ms with x2).
+#pragma unroll(TRACEBACK ? 1 : 4)
           for (int st = st0; st < st1; ++st) do_step(st, std::false_type(), std::false_type());
         }
         // roll the feed chunks over; checkpoint the lane's 16 rows (S, H) every 32 columns

@@ -309,15 +309,17 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
     const int* const tab = half ? tabB : tabA;
     unsigned long long* const myspan = span + (size_t)lane * kPkSpan;
     // prefetch ring: the top-edge entries and window characters of the next four columns
-    uint2 tq[4]; unsigned cq[4];
+    constexpr int kRing = 2;
+    uint2 tq[kRing]; unsigned cq[kRing];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { tq[u] = top_load(cA + 1 + u); cq[u] = cls_load(cA + 1 + u); }
-    for (int jc = 0; jc < kPkSpan; jc += 4) {
-      uint2 tn[4]; unsigned cn[4];
+    for (int u = 0; u < kRing; ++u) { tq[u] = top_load(cA + 1 + u); cq[u] = cls_load(cA + 1 + u); }
+#pragma unroll 1
+    for (int jc = 0; jc < kPkSpan; jc += kRing) {
+      uint2 tn[kRing]; unsigned cn[kRing];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { tn[u] = top_load(cA + 5 + jc + u); cn[u] = cls_load(cA + 5 + jc + u); }
+      for (int u = 0; u < kRing; ++u) { tn[u] = top_load(cA + 1 + kRing + jc + u); cn[u] = cls_load(cA + 1 + kRing + jc + u); }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kRing; ++u) {
         const int col = cA + 1 + jc + u;
         unsigned us, uv;
         top_fix(tq[u], col, us, uv);
@@ -360,7 +362,7 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
         myspan[jc + u] = (unsigned long long)lo | ((unsigned long long)hi << 32);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { tq[u] = tn[u]; cq[u] = cn[u]; }
+      for (int u = 0; u < kRing; ++u) { tq[u] = tn[u]; cq[u] = cn[u]; }
     }
     __syncwarp();
 
@@ -652,10 +654,10 @@ gotoh_packed_kernel(const GotohBatch B) {
         } else if (st0 < 64 || st1 >= n) {
           for (int st = st0; st < st1; ++st) do_step(st, std::true_type(), std::false_type());
         } else {
-          // Not unrolled when a traceback follows: the x2 body (ping-pong row registers, 4.7 KB) plus the walk's code thrash the
-          // instruction cache (98.2 ms against 101.7 ms per 100 k pairs; x4: 110 ms). gotohScore has no walk: x4 there (69.0 ms
-          // against 72.2 ms with x2).
-#pragma unroll(TRACEBACK ? 1 : 4)
+          // x4 (ping-pong row registers). Instruction-cache bound together with the walk's code: with the walk's span loop
+          // unrolled x4 this cost 110 ms per 100 k pairs against 98.2 ms not unrolled; with the span loop kept rolled (ring of 2)
+          // x4 gives 95.8 ms. gotohScore has no walk: 69.0 ms (72.2 ms with x2).
+#pragma unroll 4
           for (int st = st0; st < st1; ++st) do_step(st, std::false_type(), std::false_type());
         }
         // roll the feed chunks over; checkpoint the lane's 16 rows (S, H) every 32 columns

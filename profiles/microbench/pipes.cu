@@ -22,9 +22,11 @@ template <int OP> __device__ __forceinline__ unsigned op(unsigned a, unsigned b,
   if constexpr (OP == 11) return __viaddmax_s32((int)a, (int)b, (int)c);
   if constexpr (OP == 12) return __funnelshift_l(a, b, 16);          // SHF
   if constexpr (OP == 13) return a * 3u + b;                         // IMAD
+  if constexpr (OP == 14) { __half2 x = *reinterpret_cast<__half2*>(&a), y = *reinterpret_cast<__half2*>(&b);
+                            __half2 r = __hmax2(x, y); return *reinterpret_cast<unsigned*>(&r) ^ 0u; }   // HMNMX2
+  if constexpr (OP == 15) return __vmaxu2(a, b);                     // VIMNMX.U16x2
   return 0;
 }
-
 template <int OP> __global__ void k(unsigned* out, unsigned seed, long long* clk) {
   unsigned v[ILP], w = seed ^ threadIdx.x, z = seed * 3 + 1;
 #pragma unroll
@@ -90,5 +92,7 @@ int main() {
   run2<0, 4>("VIMNMX3.U16x2 + HSET2"); run2<0, 13>("VIMNMX3.U16x2 + IMAD"); run2<0, 8>("VIMNMX3.U16x2 + HFMA2"); run2<0, 5>("VIMNMX3.U16x2 + PRMT");
   run2<0, 12>("VIMNMX3.U16x2 + SHF"); run2<4, 13>("HSET2 + IMAD"); run2<4, 8>("HSET2 + HFMA2"); run2<5, 13>("PRMT + IMAD"); run2<1, 13>("VIADDMNMX.U16x2 + IMAD");
   run2<12, 13>("SHF + IMAD"); run2<5, 4>("PRMT + HSET2"); run2<8, 13>("HFMA2 + IMAD");
+  run<14>("hmax2 (HMNMX2)", 1); run<15>("vmaxu2 (VIMNMX.U16x2)", 1);
+  run2<14, 1>("HMNMX2 + VIADDMNMX.U16x2"); run2<14, 13>("HMNMX2 + IMAD"); run2<14, 8>("HMNMX2 + HFMA2"); run2<14, 4>("HMNMX2 + HSET2");
   return 0;
 }

@@ -300,7 +300,7 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
     auto top_fix = [&](uint2 e, int col, unsigned& ts, unsigned& tv) {
       if (R0 == 0) { ts = (unsigned)((col == 0 ? 0 : (hfree ? 0 : go + col * ge)) + bias); tv = (unsigned)kPkNeg; }   // src/gotoh.h:109-118
       else if (col == 0) { ts = (unsigned)((vfree ? 0 : go + R0 * ge) + bias); tv = (unsigned)kPkNeg; }
-      else { ts = vbh ? e.x >> 16 : e.x & 0xffffu; tv = vbh ? e.y >> 16 : e.y & 0xffffu; }
+      else { ts = vbh ? e.x >> 16 : e.x & 0xffffu; tv = (vbh ? e.y >> 16 : e.y & 0xffffu) + (unsigned)(vfree && col == n ? 0 : goe); }   // the fill stores W = V - goe
       ts = pk_dup(ts); tv = pk_dup(tv);
     };
     auto cls_load = [&](int col) -> unsigned { return (unsigned)P.b[min(max(col, 1), n) - 1]; };   // raw character; classified at use
@@ -594,6 +594,7 @@ gotoh_packed_kernel(const GotohBatch B) {
           const int vge_lo = vfree && c_lo == n ? 0 : ge, vge_hi = vfree && c_hi == n ? 0 : ge;
           const int vgoe_lo = vfree && c_lo == n ? 0 : goe, vgoe_hi = vfree && c_hi == n ? 0 : goe;
           const unsigned vge_p = pk_plain(vge_hi, vge_lo), vge_d = pk_dpx(vge_hi, vge_lo), vgoe_p = pk_plain(vgoe_hi, vgoe_lo);
+          const unsigned vgoe_d = pk_dpx(vgoe_hi, vgoe_lo);
 
           unsigned subw[kRowsPerLane];
 #pragma unroll
@@ -604,17 +605,21 @@ gotoh_packed_kernel(const GotohBatch B) {
 
           // V[r][c] = max(S[r-1][c] + goe, V[r-1][c] + ge) with S[r-1][c] = max(g, V[r-1][c]) and goe <= ge collapses to
           // V[r][c] = max(g[r-1] + goe, V[r-1][c] + ge): one DPX op per row on the serial chain (g = max(diag + sub, H)).
+          // Without per-cell flags the vertical vector is carried as W = V - goe(column): W[r][c] = max(W[r-1][c] + ge, g[r-1])
+          // and S = max(W + goe, g) are one VIADDMNMX each with no separate add (16 instructions less per step); the same
+          // form goes through the shuffles, the pass hand-over row and the row checkpoints (the walk adds goe back).
           const unsigned next_diag = us;
           unsigned d = diag;
           unsigned vext = uv + vge_p;
-          unsigned vn = __viaddmax_u16x2(uv, vge_d, us + vgoe_p);            // src/gotoh.h:130 for the lane's first row
+          unsigned vn = FLAGS ? __viaddmax_u16x2(uv, vge_d, us + vgoe_p)     // src/gotoh.h:130 for the lane's first row
+                              : __viaddmax_u16x2(uv, vge_d, us);
           unsigned acc[8];
 #pragma unroll
           for (int i = 0; i < kRowsPerLane; ++i) {
             const unsigned hext = hh[i] + hge[i];
             const unsigned hn = __viaddmax_u16x2(sl[i], hgoe[i], hext);      // src/gotoh.h:129
             const unsigned g = __viaddmax_u16x2(d, subw[i], hn);             // max(diag + sub, H)
-            const unsigned s = __vmaxu2(g, vn);                              // src/gotoh.h:131
+            const unsigned s = FLAGS ? __vmaxu2(g, vn) : __viaddmax_u16x2(vn, vgoe_d, g);   // src/gotoh.h:131
             if (FLAGS) {
               unsigned ac = (i & 1) ? acc[i >> 1] : 0x44004400u;             // 4.0 | 4.0
               ac = pk_push(ac, pk_flag_gt(hn, hext));                        // HOPEN, src/gotoh.h:137
@@ -627,7 +632,7 @@ gotoh_packed_kernel(const GotohBatch B) {
             sl[i] = s; hh[i] = hn;
             us = s; uv = vn;
             if (FLAGS) vext = vn + vge_p;
-            vn = __viaddmax_u16x2(vn, vge_d, g + vgoe_p);                    // next row's V
+            vn = FLAGS ? __viaddmax_u16x2(vn, vge_d, g + vgoe_p) : __viaddmax_u16x2(vn, vge_d, g);   // next row's V (W)
           }
           diag = next_diag;
           bs = us; bv = uv;

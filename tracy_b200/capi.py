@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtracy_b200.so")
+LIB_PATH = os.environ.get("TRACY_B200_LIB") or os.path.join(HERE, "libtracy_b200.so")   # override: kernel variant experiments
 
 TB_OK, TB_ERR_INVALID, TB_ERR_CUDA, TB_ERR_NOMEM, TB_ERR_UNSUPPORTED = range(5)
 TB_MEM_HOST, TB_MEM_DEVICE = 0, 1

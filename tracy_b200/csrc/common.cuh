@@ -112,15 +112,12 @@ struct AnchorBatch {
 
 // reference src/align.h:121-136: A,C,G,T,N (case-insensitive) -> 0..4; '-' and everything else contribute
 // nothing to _score (row 5 is never read, src/align.h:113-114) -> class 5.
+// Branch-free (a switch compiles to a ladder of divergent branches, and every lane holds a different character): 3-bit
+// entries for the folded letters 'A'..'T'; everything else, and 'U'..'Z', is class 5.
 __device__ __forceinline__ int base_class(unsigned char ch) {
-  switch (ch) {
-    case 'A': case 'a': return 0;
-    case 'C': case 'c': return 1;
-    case 'G': case 'g': return 2;
-    case 'T': case 't': return 3;
-    case 'N': case 'n': return 4;
-    default: return 5;
-  }
+  const unsigned t = ((unsigned)ch & 0xDFu) - 0x41u;                 // 'A'/'a' -> 0 ... 'Z'/'z' -> 25, any other byte >= 26
+  const unsigned e = (unsigned)(0x076db65b6daada68ull >> (3u * min(t, 19u))) & 7u;
+  return t < 20u ? (int)e : 5;
 }
 
 // Substitution score of a trace-profile row against a one-hot reference column of class b

@@ -23,6 +23,13 @@
 
 #include "common.cuh"
 
+#ifndef TB_WALK_RING
+#define TB_WALK_RING 1        // iterations of the tile recompute kept in flight (top-edge / window prefetch): 1 = 2 < 4 measured
+#endif
+#ifndef TB_FILL_UNROLL_TB
+#define TB_FILL_UNROLL_TB 4   // unrolling of the common fill step when a traceback follows (instruction-cache trade-off)
+#endif
+
 namespace tb {
 
 constexpr int kPkWarps = 2;                       // warps per block (40 KB of tables per block: five blocks per SM)
@@ -211,7 +218,22 @@ struct PkPair {
 };
 
 constexpr int kPkSpan = 64;                      // columns per lane per round
+#ifdef TB_WALK_STATS
+// profiling build only (profiles/walk_stats.py): [0] pairs [1] rounds [2] horizontal rounds [3] 64-iteration rounds
+// [4] clk plan + edges [5] clk tile recompute [6] clk path walk [7] clk total [8] walk-loop iterations [9] window loads
+__device__ unsigned long long tb_walk_stats[16];
+#define TB_STAT_ADD(i, v) do { if (lane == 0) atomicAdd(&tb_walk_stats[i], (unsigned long long)(v)); } while (0)
+#define TB_CLK() clock64()
+#else
+#define TB_STAT_ADD(i, v) do { } while (0)
+#define TB_CLK() 0ll
+#endif
 
+__device__ __forceinline__ unsigned pk_ldg_u32(unsigned long long gaddr) {   // aligned word of global memory, read-only path
+  unsigned v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(gaddr));
+  return v;
+}
 __device__ __forceinline__ unsigned pk_dup(unsigned field) { return field * 0x10001u; }   // the same value in both halves
 
 // 4-bit pointer of row `row` (0..15) from a span word: byte row>>1, even rows in the high nibble
@@ -220,20 +242,24 @@ __device__ __forceinline__ unsigned pk_span_nibble(unsigned long long w, int row
   return (row & 1) ? (byte & 15u) : (byte >> 4);
 }
 
-template <int CLASSES, bool ASEQ>
+template <int CLASSES, bool ASEQ, bool VF>
 __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __restrict__ rowck, const uint4* __restrict__ colck,
                                                 unsigned long long* __restrict__ span, int* tabA, int* tabB, int tab_pass,
                                                 uint8_t* __restrict__ ops_rev, int lane) {
   const int m = P.m, n = P.n, T = P.T, go = P.go, ge = P.ge, goe = P.goe, bias = P.bias;
-  const bool vfree = P.vfree, hfree = P.hfree;
+  constexpr bool vfree = VF;
+  const bool hfree = P.hfree;
   int r = m, c = n, state = 0, k = 0;
   auto put = [&](unsigned char ch, int run) {                       // run <= 32 equal characters, one coalesced store
     if (lane < run) ops_rev[k + lane] = ch;
     k += run;
   };
   bool first_round = true;
+  const long long t_begin = TB_CLK(); (void)t_begin;
+  TB_STAT_ADD(0, 1);
 
   while (r > 0 || c > 0) {
+    const long long t_plan = TB_CLK(); (void)t_plan;
     if (r == 0 || c == 0) {                                         // row 0 is all 'h', column 0 all 'v'
       const int cnt = r == 0 ? c : r;
       const unsigned char ch = r == 0 ? 'h' : 'v';
@@ -248,6 +274,7 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
     // the free end-gap row almost always starts with a long horizontal run: look left first there
     const bool horizontal = state == 1 || (first_round && hfree && r == m && state == 0);
     first_round = false;
+    TB_STAT_ADD(1, 1); TB_STAT_ADD(2, horizontal ? 1 : 0);
     int vk, cA;                                                     // this lane's block and the checkpoint column its span starts after
     bool act;
     if (horizontal) {
@@ -263,33 +290,43 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
       const int base_c = 32 - (vk & 31) - 32 * (vk >> 5);
       const int e = c + 15 - i0 - 16 * lane;                        // column where a pure diagonal crosses this block's bottom row
       cA = base_c + 32 * ((e - 24 - base_c) >> 5);                  // last checkpoint column <= e - 24
+      act = act && cA + kPkSpan >= 1;                               // a span left of column 1 holds nothing (column 0 is a closed form)
     }
     const int half = vk >> 5, l = vk & 31;
     const int base_c = 32 - l - 32 * half;
     int qa = (cA - base_c) >> 5;                                    // checkpoint index of column cA (cA is on the grid)
-    if (cA < 1) { cA = 0; qa = -1; }                                // before the block's first checkpoint: start from column 0
+    // The 64 columns of a span are recomputed as TWO 32-column halves side by side: the low field of every word runs
+    // columns cA+1 .. cA+32 from checkpoint qa, the high field columns cA+33 .. cA+64 from checkpoint qa+1. A span that
+    // starts before the block's first checkpoint has no checkpoint on its left: it starts from column 0 and runs all its
+    // 64 columns in the low field (`whole`; the warp then takes 64 iterations instead of 32 -- rare, near the window start).
+    const bool whole = cA < 1;
+    if (whole) { cA = 0; qa = -1; }
     const int R0 = pass * kPkRows + 512 * half + 16 * l;            // DP row just above the block
-    // ---- left edge (both halves of every word carry the same value; the half that is not this block's runs with sub = 0) ----
+    // ---- left edges ----
     unsigned sl[kRowsPerLane], hh[kRowsPerLane], hge[kRowsPerLane], hgoe[kRowsPerLane];
     {
       const unsigned* cw = reinterpret_cast<const unsigned*>(colck);
-      const unsigned long long qb = ((unsigned long long)pass * (unsigned)P.NQ + (unsigned)max(qa, 0)) * 8ull;
+      const unsigned long long qb0 = ((unsigned long long)pass * (unsigned)P.NQ + (unsigned)max(qa, 0)) * 8ull;
+      const unsigned long long qb1 = ((unsigned long long)pass * (unsigned)P.NQ + (unsigned)min(qa + 1, P.NQ - 1)) * 8ull;
 #pragma unroll
       for (int i = 0; i < kRowsPerLane; ++i) {
         const int ri = R0 + i + 1;
-        unsigned sv = (unsigned)((vfree ? 0 : go + ri * ge) + bias), hv = (unsigned)kPkNeg;      // src/gotoh.h:120-121
+        unsigned sv0 = (unsigned)((vfree ? 0 : go + ri * ge) + bias), hv0 = (unsigned)kPkNeg;    // src/gotoh.h:120-121
         if (qa >= 0) {
-          const unsigned ws = cw[((qb + (unsigned)(i >> 2)) * 32ull + (unsigned)l) * 4ull + (unsigned)(i & 3)];
-          const unsigned wh = cw[((qb + (unsigned)(4 + (i >> 2))) * 32ull + (unsigned)l) * 4ull + (unsigned)(i & 3)];
-          sv = half ? ws >> 16 : ws & 0xffffu; hv = half ? wh >> 16 : wh & 0xffffu;
+          const unsigned ws = cw[((qb0 + (unsigned)(i >> 2)) * 32ull + (unsigned)l) * 4ull + (unsigned)(i & 3)];
+          const unsigned wh = cw[((qb0 + (unsigned)(4 + (i >> 2))) * 32ull + (unsigned)l) * 4ull + (unsigned)(i & 3)];
+          sv0 = half ? ws >> 16 : ws & 0xffffu; hv0 = half ? wh >> 16 : wh & 0xffffu;
         }
-        sl[i] = pk_dup(sv); hh[i] = pk_dup(hv);
+        const unsigned ws1 = cw[((qb1 + (unsigned)(i >> 2)) * 32ull + (unsigned)l) * 4ull + (unsigned)(i & 3)];
+        const unsigned wh1 = cw[((qb1 + (unsigned)(4 + (i >> 2))) * 32ull + (unsigned)l) * 4ull + (unsigned)(i & 3)];
+        const unsigned sv1 = half ? ws1 >> 16 : ws1 & 0xffffu, hv1 = half ? wh1 >> 16 : wh1 & 0xffffu;
+        sl[i] = pk_dpx((int)sv1, (int)sv0); hh[i] = pk_dpx((int)hv1, (int)hv0);
         const bool fr = hfree && ri == m;                           // src/align.h:67-80
         hge[i] = pk_plain(fr ? 0 : ge, fr ? 0 : ge);
         hgoe[i] = pk_dpx(fr ? 0 : goe, fr ? 0 : goe);
       }
     }
-    // ---- top edge reader: (S, V) of the row above the block at column col, duplicated into both halves ----
+    // ---- top edge reader: (S, V) fields of the row above the block at column col ----
     const int vb = vk > 0 ? vk - 1 : 63, pb = vk > 0 ? pass : pass - 1;
     const uint2* const top_base = rowck + ((unsigned long long)max(pb, 0) * (unsigned)T + (unsigned)vb) * 32ull + (unsigned)(vb & 31);
     const int vbh = vb >> 5;
@@ -301,36 +338,65 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
       if (R0 == 0) { ts = (unsigned)((col == 0 ? 0 : (hfree ? 0 : go + col * ge)) + bias); tv = (unsigned)kPkNeg; }   // src/gotoh.h:109-118
       else if (col == 0) { ts = (unsigned)((vfree ? 0 : go + R0 * ge) + bias); tv = (unsigned)kPkNeg; }
       else { ts = vbh ? e.x >> 16 : e.x & 0xffffu; tv = (vbh ? e.y >> 16 : e.y & 0xffffu) + (unsigned)(vfree && col == n ? 0 : goe); }   // the fill stores W = V - goe
-      ts = pk_dup(ts); tv = pk_dup(tv);
     };
-    auto cls_load = [&](int col) -> unsigned { return (unsigned)P.b[min(max(col, 1), n) - 1]; };   // raw character; classified at use
-    unsigned diag, dv_unused;
-    top_fix(top_load(cA), cA, diag, dv_unused);
+    // window characters (raw; classified at use) come as aligned 32-bit words, one load per four columns and half
+    const unsigned long long bbase = (unsigned long long)P.b;
+    auto caddr = [&](int col) -> unsigned long long { return bbase + (unsigned)(min(col, n) - 1); };   // col >= 1
+    unsigned diag;
+    {
+      unsigned d0, d1, unused;
+      top_fix(top_load(cA), cA, d0, unused);
+      top_fix(top_load(cA + 32), cA + 32, d1, unused);
+      diag = pk_dpx((int)d1, (int)d0);
+    }
     const int* const tab = half ? tabB : tabA;
-    unsigned long long* const myspan = span + (size_t)lane * kPkSpan;
-    // prefetch ring: the top-edge entries and window characters of the next four columns
-    constexpr int kRing = 2;
-    uint2 tq[kRing]; unsigned cq[kRing];
+    const unsigned selsub = half ? 0x7632u : 0x5410u;               // this block's field of the two table words -> (low column, high column)
+    const unsigned seltop = vbh ? 0x7632u : 0x5410u;                // the same for the block above
+    unsigned long long* const myspan = span + lane;                // span scratch is [column][lane]: one 256 B line per store
+    const int lim_lo = whole ? kPkSpan : 32, lim_hi = whole ? 0 : 32;
+    const int iters = __any_sync(kFull, act && whole) ? kPkSpan : 32;
+    TB_STAT_ADD(3, iters == kPkSpan ? 1 : 0);
+    const long long t_tile = TB_CLK(); (void)t_tile;
+    TB_STAT_ADD(4, t_tile - t_plan);
+    // prefetch ring: the top-edge entries (DRAM: every lane its own 32-byte sector) and window characters of the next
+    // kRing iterations; the loop itself stays rolled (instruction cache), the ring shifts through registers
+    constexpr int kRing = TB_WALK_RING;
+    uint2 tq[kRing], tr[kRing];
 #pragma unroll
-    for (int u = 0; u < kRing; ++u) { tq[u] = top_load(cA + 1 + u); cq[u] = cls_load(cA + 1 + u); }
+    for (int u = 0; u < kRing; ++u) { tq[u] = top_load(cA + 1 + u); tr[u] = top_load(cA + 33 + u); }
+    unsigned long long pa = caddr(cA + 1), ph = caddr(cA + 33);
+    unsigned wa = pk_ldg_u32(pa & ~3ull), wh = pk_ldg_u32(ph & ~3ull);
 #pragma unroll 1
-    for (int jc = 0; jc < kPkSpan; jc += kRing) {
-      uint2 tn[kRing]; unsigned cn[kRing];
-#pragma unroll
-      for (int u = 0; u < kRing; ++u) { tn[u] = top_load(cA + 1 + kRing + jc + u); cn[u] = cls_load(cA + 1 + kRing + jc + u); }
-#pragma unroll
-      for (int u = 0; u < kRing; ++u) {
-        const int col = cA + 1 + jc + u;
-        unsigned us, uv;
-        top_fix(tq[u], col, us, uv);
-        const unsigned cl = min((unsigned)base_class((unsigned char)cq[u]), (unsigned)(CLASSES - 1));
-        const uint4* const pt = reinterpret_cast<const uint4*>(tab + cl * 512) + l;
+    for (int jc = 0; jc < iters; ++jc) {
+      const uint2 tn = top_load(cA + 1 + kRing + jc), sn = top_load(cA + 33 + kRing + jc);
+      const unsigned long long pa1 = caddr(cA + 2 + jc), ph1 = caddr(cA + 34 + jc);
+      unsigned wa1 = wa, wh1 = wh;
+      if ((pa1 & 3ull) == 0 && pa1 != pa) wa1 = pk_ldg_u32(pa1);
+      if ((ph1 & 3ull) == 0 && ph1 != ph) wh1 = pk_ldg_u32(ph1);
+      const unsigned ch0 = __byte_perm(wa, 0u, 0x4440u | (unsigned)(pa & 3ull)), ch1 = __byte_perm(wh, 0u, 0x4440u | (unsigned)(ph & 3ull));
+      {
+        constexpr int u = 0;
+        const int col = cA + 1 + jc + u, colh = col + 32;
+        const bool vf0 = vfree && col == n, vf1 = vfree && colh == n;   // src/align.h:52-65
+        const int vge0 = vf0 ? 0 : ge, vgoe0 = vf0 ? 0 : goe, vge1 = vf1 ? 0 : ge, vgoe1 = vf1 ? 0 : goe;
+        const unsigned vge_p = pk_plain(vge1, vge0), vge_d = pk_dpx(vge1, vge0), vgoe_p = pk_plain(vgoe1, vgoe0);
+        unsigned us = __byte_perm(tq[u].x, tr[u].x, seltop);          // (S, W) of the row above at the two columns
+        unsigned uv = __byte_perm(tq[u].y, tr[u].y, seltop) + vgoe_p; // the fill stores W = V - goe
+        if (R0 == 0) {                                                // DP row 0, src/gotoh.h:109-118 (col >= 1 here)
+          us = pk_dpx((hfree ? 0 : go + colh * ge) + bias, (hfree ? 0 : go + col * ge) + bias);
+          uv = pk_dpx(kPkNeg, kPkNeg);
+        }
+        const unsigned cl0 = min((unsigned)base_class((unsigned char)ch0), (unsigned)(CLASSES - 1));
+        const unsigned cl1 = min((unsigned)base_class((unsigned char)ch1), (unsigned)(CLASSES - 1));
+        const uint4* const pt0 = reinterpret_cast<const uint4*>(tab + cl0 * 512) + l;
+        const uint4* const pt1 = reinterpret_cast<const uint4*>(tab + cl1 * 512) + l;
         unsigned subw[kRowsPerLane];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const uint4 x = pt[j * 32]; subw[4 * j] = x.x; subw[4 * j + 1] = x.y; subw[4 * j + 2] = x.z; subw[4 * j + 3] = x.w; }
-        const bool vf = vfree && col == n;                          // src/align.h:52-65
-        const int vge_i = vf ? 0 : ge, vgoe_i = vf ? 0 : goe;
-        const unsigned vge_p = pk_plain(vge_i, vge_i), vge_d = pk_dpx(vge_i, vge_i), vgoe_p = pk_plain(vgoe_i, vgoe_i);
+        for (int j = 0; j < 4; ++j) {
+          const uint4 x = pt0[j * 32], y = pt1[j * 32];
+          subw[4 * j] = __byte_perm(x.x, y.x, selsub); subw[4 * j + 1] = __byte_perm(x.y, y.y, selsub);
+          subw[4 * j + 2] = __byte_perm(x.z, y.z, selsub); subw[4 * j + 3] = __byte_perm(x.w, y.w, selsub);
+        }
         const unsigned next_diag = us;
         unsigned d = diag;
         unsigned vext = uv + vge_p;
@@ -354,22 +420,27 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
           vn = __viaddmax_u16x2(vn, vge_d, g + vgoe_p);
         }
         diag = next_diag;
-        // low mantissa byte of this block's half of each accumulator = rows (2a, 2a+1)
-        const unsigned sel = half ? 0x6262u : 0x4040u;
-        const unsigned w01 = __byte_perm(acc[0], acc[1], sel), w23 = __byte_perm(acc[2], acc[3], sel);
-        const unsigned w45 = __byte_perm(acc[4], acc[5], sel), w67 = __byte_perm(acc[6], acc[7], sel);
-        const unsigned lo = __byte_perm(w01, w23, 0x5410), hi = __byte_perm(w45, w67, 0x5410);
-        myspan[jc + u] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+        // low mantissa byte of each half of an accumulator = rows (2a, 2a+1) of the low / high column
+        const unsigned w01 = __byte_perm(acc[0], acc[1], 0x6240), w23 = __byte_perm(acc[2], acc[3], 0x6240);
+        const unsigned w45 = __byte_perm(acc[4], acc[5], 0x6240), w67 = __byte_perm(acc[6], acc[7], 0x6240);
+        const int j = jc;
+        if (j < lim_lo) myspan[j * 32] = (unsigned long long)__byte_perm(w01, w23, 0x5410) | ((unsigned long long)__byte_perm(w45, w67, 0x5410) << 32);
+        if (j < lim_hi) myspan[(32 + j) * 32] = (unsigned long long)__byte_perm(w01, w23, 0x7632) | ((unsigned long long)__byte_perm(w45, w67, 0x7632) << 32);
       }
 #pragma unroll
-      for (int u = 0; u < kRing; ++u) { tq[u] = tn[u]; cq[u] = cn[u]; }
+      for (int u = 0; u + 1 < kRing; ++u) { tq[u] = tq[u + 1]; tr[u] = tr[u + 1]; }
+      tq[kRing - 1] = tn; tr[kRing - 1] = sn;
+      wa = wa1; wh = wh1; pa = pa1; ph = ph1;
     }
     __syncwarp();
+    const long long t_walk = TB_CLK(); (void)t_walk;
+    TB_STAT_ADD(5, t_walk - t_tile);
 
     // ================= walk through the spans of this round =================
     int wk = -1, wc0 = 0, wcA = 0;                                  // window: lane t holds the word of column wc0 - t of span wk
     unsigned long long ww = 0;
     for (;;) {
+      TB_STAT_ADD(8, 1);
       if (r == 0 || c == 0) break;
       if (((r - 1) >> 10) != pass) break;                           // next pass: other tables, new round
       const int rr = (r - 1) & 1023;
@@ -396,8 +467,9 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
       if (!sact || c <= scA || c > scA + kPkSpan) break;            // the path left what was speculated: plan again from here
       if (sk != wk || c > wc0 || c < wc0 - 31) {                    // load a window: 32 columns ending at c
         wk = sk; wc0 = c; wcA = scA;
+        TB_STAT_ADD(9, 1);
         const int cc = c - lane;
-        ww = cc > scA ? span[(size_t)sk * kPkSpan + (cc - scA - 1)] : 0ull;
+        ww = cc > scA ? span[(size_t)(cc - scA - 1) * 32 + sk] : 0ull;
       }
       const int off = wc0 - c, j = lane - off;                      // this lane looks at the j-th cell of the run (j >= 0)
       const int avail = min(32 - off, c - wcA);                     // columns left in the window and in the span
@@ -429,7 +501,9 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
       }
     }
     __syncwarp();
+    TB_STAT_ADD(6, TB_CLK() - t_walk);
   }
+  TB_STAT_ADD(7, TB_CLK() - t_begin);
   return k;
 }
 
@@ -437,6 +511,7 @@ template <int TBMODE, bool VFREE, int CLASSES, bool ASEQ>
 __global__ void __launch_bounds__(kPkWarps * 32, CLASSES == 4 ? 6 : 5)   // 12 / 10 warps per SM: what the tables allow
 gotoh_packed_kernel(const GotohBatch B) {
   constexpr bool TRACEBACK = TBMODE != kTbNone, FLAGS = TBMODE == kTbFlags, CKPT = TBMODE == kTbCkpt;
+  constexpr int kFillUnroll = TRACEBACK ? TB_FILL_UNROLL_TB : 4;
   constexpr int kPkTabWords = CLASSES * 512, kPkSmemWordsPerWarp = 2 * kPkTabWords + kPkTileWords;
   extern __shared__ int smem_pk[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -662,7 +737,7 @@ gotoh_packed_kernel(const GotohBatch B) {
           // x4 (ping-pong row registers). Instruction-cache bound together with the walk's code: with the walk's span loop
           // unrolled x4 this cost 110 ms per 100 k pairs against 98.2 ms not unrolled; with the span loop kept rolled (ring of 2)
           // x4 gives 95.8 ms. gotohScore has no walk: 69.0 ms (72.2 ms with x2).
-#pragma unroll 4
+#pragma unroll(kFillUnroll)
           for (int st = st0; st < st1; ++st) do_step(st, std::false_type(), std::false_type());
         }
         // roll the feed chunks over; checkpoint the lane's 16 rows (S, H) every 32 columns
@@ -689,7 +764,7 @@ gotoh_packed_kernel(const GotohBatch B) {
         PkPair pp;
         pp.a = a; pp.b = b; pp.m = m; pp.n = n; pp.T = T; pp.NQ = NQ; pp.go = go; pp.ge = ge; pp.goe = goe; pp.bias = bias;
         pp.hfree = hfree; pp.vfree = vfree; pp.fmatch = fmatch; pp.fmismatch = fmismatch;
-        L = walk_traceback_ckpt<CLASSES, ASEQ>(pp, rowck, colck, span, tabA, tabB, npass - 1, ops_rev, lane);
+        L = walk_traceback_ckpt<CLASSES, ASEQ, VFREE>(pp, rowck, colck, span, tabA, tabB, npass - 1, ops_rev, lane);
       } else {
         L = walk_traceback_packed(ptr, T, m, n, ops_rev, lane);
       }
@@ -777,3 +852,12 @@ cudaError_t gotoh_packed_blocks_per_sm(int tbmode, int classes, int* out) {
 }
 
 }  // namespace tb
+
+#ifdef TB_WALK_STATS
+extern "C" int tb_debug_walk_stats(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, tb::tb_walk_stats, sizeof(tb::tb_walk_stats)) != cudaSuccess) return 1;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tb::tb_walk_stats, z, sizeof(z)); }
+  return 0;
+}
+#endif

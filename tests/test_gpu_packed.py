@@ -224,3 +224,23 @@ def test_string_pairs_through_packed_kernel(ctx, oracle_port):
             ws, wops = oracle_port.gotoh_ss(a1[i], a2[i], hf, vf, sc)
             assert int(s[i]) == ws and bytes(ops[i, : ol[i]]) == wops, (hf, vf, i)
     assert total_packed >= 4 * 60          # the ACGT / ACGTN pairs (2 of 5 alphabets) took the packed kernel
+
+
+def test_spans_at_the_window_start(ctx, oracle_port):
+    """The tile recompute runs a span's two 32-column halves side by side from two column checkpoints; spans that begin left
+    of a block's first checkpoint start from column 0 and run all 64 columns in one field. Every start offset 0..71 of the
+    trace inside the window (so that the diagonal crosses column 0..71 in the top blocks), windows that end right after the
+    trace and windows with a long right flank (horizontal rounds that reach column 0), against the oracle."""
+    rng = np.random.default_rng(2025)
+    A, Bs = [], []
+    for off in range(72):
+        m = int(rng.integers(40, 700))
+        core = synth.random_seq(rng, m)
+        A.append(synth.profile_from_seq(rng, core, 0.3))
+        right = int(rng.integers(0, 50)) if off % 3 else int(rng.integers(200, 2200))
+        Bs.append(synth.random_seq(rng, off) + synth.mutate_seq(rng, core, 0.02, 0.02) + synth.random_seq(rng, right))
+    for hf, vf in ((1, 0), (1, 1), (0, 0)):
+        s, ops, ol = ctx.gotoh("ps", A, Bs, DnaScore(3, -5, -10, -4), AlignConfig(bool(hf), bool(vf)))
+        assert ctx.last_packed_pairs() == len(A)
+        for i in range(len(A)):
+            assert (int(s[i]), bytes(ops[i, : ol[i]])) == oracle_port.gotoh_ps(A[i], Bs[i], hf, vf, (3, -5, -10, -4)), (hf, vf, i)

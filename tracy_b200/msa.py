@@ -222,6 +222,38 @@ def consensus(rows, fraction_called=0.5, ignore_last=False):
 
 
 # ---- orientation ------------------------------------------------------------------------------------------------------
+class _DeviceTrials:
+    """One orientation trial of revSeqBasedOnDist = every profile against the flipped one. With a device context the pool stays
+    in HBM for the whole stage: the arenas of a trial (all `num` slots against the spare slot) never change, so a trial is one
+    21 KB upload of the flipped profile, one tb_gotoh_pp on device pointers and one read of `num` scores -- no per-trial copy
+    of the pool through pinned staging (that was 8 ms per trial at 512 traces, against ~1 ms of kernel)."""
+
+    def __init__(self, ctx, pool, num):
+        import torch
+        self.torch, self.ctx, self.num, self.cap = torch, ctx, num, pool.cap
+        dev = torch.device("cuda", ctx.device)
+        self.base = torch.from_numpy(pool.base).to(dev)
+        self.off1 = torch.from_numpy(np.ascontiguousarray(pool.off[:num])).to(dev)
+        self.len1 = torch.from_numpy(np.ascontiguousarray(pool.lens[:num])).to(dev)
+        self.off2 = torch.full((num,), int(pool.off[num]), dtype=torch.int64, device=dev)
+        self.len2 = torch.zeros(num, dtype=torch.int32, device=dev)
+        self.scores = torch.zeros(num, dtype=torch.int32, device=dev)
+        self.stage = torch.zeros(pool.cap, dtype=torch.float32).pin_memory()
+
+    def put(self, slot, p):
+        p = np.ascontiguousarray(p, np.float32)
+        self.stage[: p.size] = self.torch.from_numpy(p.reshape(-1))
+        self.base[slot * self.cap: slot * self.cap + p.size].copy_(self.stage[: p.size], non_blocking=False)
+        return p.shape[1]
+
+    def trial(self, s_rc, sc):
+        self.len2.fill_(self.put(self.num, s_rc))
+        self.torch.cuda.synchronize(self.base.device)               # torch's stream -> the context's stream
+        self.ctx.gotoh_device(PP, self.base.data_ptr(), self.off1.data_ptr(), self.len1.data_ptr(), self.base.data_ptr(), self.off2.data_ptr(),
+                              self.len2.data_ptr(), self.num, self.scores.data_ptr(), sc=sc, ac=_END_FREE)
+        return self.scores.cpu().numpy().astype(np.int64)
+
+
 def rev_seq_based_on_dist(ctx, profiles, fwd, sc):
     """revSeqBasedOnDist (src/msa.h:243-328). profiles: list of float32[6][len] (replaced in place when a flip is kept),
     fwd: list of bool (toggled in place). Returns the final symmetric score matrix."""
@@ -235,6 +267,7 @@ def rev_seq_based_on_dist(ctx, profiles, fwd, sc):
         d[ii, jj] = s
         d[jj, ii] = s
     total = int(d[ii, jj].sum()) if len(ii) else 0
+    dev = _DeviceTrials(ctx, pool, num) if num > 1 and hasattr(ctx, "gotoh_device") else None   # test doubles serve ctx.gotoh only
     iterate = True
     while iterate:
         quality = sorted((int(d[i].sum()), i) for i in range(num))      # worst row sum first, src/msa.h:270-282
@@ -242,13 +275,18 @@ def rev_seq_based_on_dist(ctx, profiles, fwd, sc):
             s_rc = _revcomp(seq[k])
             others = [i for i in range(num) if i != k]
             new_d = np.zeros(num, np.int64)
-            if others:
+            if others and dev is not None:
+                new_d = dev.trial(s_rc, sc)
+                new_d[k] = 0                                             # the pair (k, flipped k) rides along and is dropped
+            elif others:
                 pool.put(num, s_rc)
                 sc_new, _, _ = ctx.gotoh(PP, pool.arena(others), pool.arena([num] * len(others)), sc, _END_FREE, traceback=False)
                 new_d[others] = sc_new
             if int(new_d.sum()) >= int(d[others, k].sum()):              # scoreSum >= oldScoreSum, src/msa.h:298
                 seq[k] = s_rc
                 pool.put(k, s_rc)
+                if dev is not None:
+                    dev.put(k, s_rc)
                 fwd[k] = not fwd[k]
                 d[:, k] = new_d
                 d[k, :] = new_d

@@ -6,10 +6,13 @@
 // with B running 32 columns behind A, so that lane 31's bottom row of A is exactly what lane 0 needs as the top of B one
 // step later: the hand-over is the same rotating shuffle. One pass therefore covers 1024 DP rows in n+63 steps.
 //
-// Why this shape (measured on B200, profiles/microbench): the DP is bound by the ALU pipe (0.5 warp-instr/clk/SMSP:
-// VIMNMX*, VIADDMNMX, HSET2, PRMT, LOP3 all live there) while the FMA pipe (IMAD, HFMA2) idles. Per packed word (2 cells):
-//   ALU: 2x VIADDMNMX.U16x2 (H, V), 1x VIMNMX3.U16x2 (S), 4x HSET2.BF (the four pointer flags as 1.0/0.0)
-//   FMA: 4x IMAD.IADD (gap extensions, diagonal + substitution), 4x HFMA2 (acc = 2*acc + flag: bit packing on the idle pipe)
+// Why this shape (measured on B200, profiles/microbench): the DP is bound by the ALU pipe (3-input DPX forms VIMNMX3 /
+// VIADDMNMX, HSET2, PRMT at 0.5 warp-instr/clk/SMSP; the 2-input VIMNMX.U16x2 at 1.0) and by the shared-memory data pipe
+// (the substitution-table reads), while the FMA pipe (IMAD, HFMA2) idles. Per packed word (2 cells):
+//   fill without flags (gotohScore, checkpoint traceback): 4x VIADDMNMX.U16x2 (H, g, S, W) + 2x IMAD.IADD (H + ge, table words)
+//   fill with flags (TRACY_B200_TB_MODE=flags) and the traceback's tile recompute: 3x VIADDMNMX.U16x2 + VIMNMX.U16x2,
+//     4x HSET2.BF (the four pointer flags as 1.0/0.0) on the ALU pipe; 3x IMAD.IADD and 4x HFMA2 (acc = 2*acc + flag: bit
+//     packing on the idle pipe) on the FMA pipe
 // Values are kept below 0x7c00 so that the fp16 compare of the raw bit patterns is the integer compare (positive halves
 // order like their bits); accumulating from 4.0 leaves the 8 flag bits of two rows in the low mantissa byte of each half.
 //
@@ -38,7 +41,6 @@ constexpr int kPkRows = 1024;                     // DP rows per pass (two 512-r
 // 16 KB per warp, 12 warps per SM) for windows without N, CLASSES = 5 (A,C,G,T,N: 20 KB per warp, 10 warps per SM).
 constexpr int kPkNeg = 2048;                      // field value standing in for the reference's -inf
 constexpr int kPkMaxField = 0x7bff - 16;          // largest field value for which fp16 compare == integer compare
-constexpr int kPkTileWords = 0;                   // (no per-warp shared memory besides the tables)
 // Traceback modes of the packed kernel: none (gotohScore), pointer flags for every cell, or checkpoints + tile recompute.
 enum : int { kTbNone = 0, kTbFlags = 1, kTbCkpt = 2 };
 
@@ -201,15 +203,17 @@ __device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const void
 // tile recomputable on its own: left edge from (b) (or the column-0 initialisation), top edge from (a) of the block above.
 //
 // The walk proceeds in ROUNDS. A round gives each of the 32 lanes one block and a 64-column span that starts on one of the
-// block's checkpoint columns, and every lane recomputes its span serially with the fill's own per-row instruction sequence
-// (flags included), all lanes in lock-step -- the recompute runs at full SIMT efficiency. Spans are chosen by speculation:
+// block's checkpoint columns, and every lane recomputes its span with the fill's own per-row instruction sequence (flags
+// included) -- columns cA+1..cA+32 in the low field from checkpoint qa, columns cA+33..cA+64 in the high field from checkpoint
+// qa+1, all lanes in lock-step: the recompute runs at full SIMT efficiency. Spans are chosen by speculation:
 //   * diagonal round (state 's' / 'v'): lane k takes the k-th block above the current one, around the column where a
 //     pure diagonal from the current cell would cross it (>= 8 columns of slack either side);
 //   * horizontal round (state 'h'): all lanes take the current block, consecutive spans to the left (2048 columns).
-// The 4-bit pointers of every span go to a 16 KB scratch (64-bit word per column: 16 rows x 4 bits); the walk then consumes
+// The 4-bit pointers of every span go to a 16 KB scratch ([column][lane] 64-bit words: 16 rows x 4 bits); the walk then consumes
 // them run by run with ballots, exactly like the flag walkers. When the path leaves the speculated spans (a long indel, a
 // change of pass) the next round is planned from the cell reached, so every round consumes at least one cell.
-// Cost at 1000 x 4000: ~5 rounds x ~20 k instructions against 1.44 M for flag extraction in every cell.
+// Cost at 1000 x 4000 (profiles/r01_tb_cost.txt): 4.2 rounds, ~80 k instructions per pair against 1.44 M for flag extraction in
+// every cell.
 struct PkPair {
   const void* a; const unsigned char* b;
   int m, n, T, NQ, go, ge, goe, bias;
@@ -234,7 +238,6 @@ __device__ __forceinline__ unsigned pk_ldg_u32(unsigned long long gaddr) {   // 
   asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(gaddr));
   return v;
 }
-__device__ __forceinline__ unsigned pk_dup(unsigned field) { return field * 0x10001u; }   // the same value in both halves
 
 // 4-bit pointer of row `row` (0..15) from a span word: byte row>>1, even rows in the high nibble
 __device__ __forceinline__ unsigned pk_span_nibble(unsigned long long w, int row) {
@@ -448,19 +451,13 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
       int sk;                                                       // lane (span) that should hold column c of block v
       if (horizontal) {
         if (v != v0) break;
-        const int bc = 32 - (v0 & 31) - 32 * (v0 >> 5);
-        const int cB0 = bc + 32 * (((__shfl_sync(kFull, c, 0) - bc) + 31) >> 5);   // (uniform; c is warp-uniform)
-        sk = -1;                                                    // located below from the spans' cA values
-        (void)cB0;
-      } else {
-        sk = v0 - v;
-        if (sk < 0 || sk > 31) break;
-      }
-      if (horizontal) {
         // spans are consecutive: span t covers (cA_t, cA_t + 64]; find the one that holds c
         const unsigned hit = __ballot_sync(kFull, act && c > cA && c <= cA + kPkSpan);
         if (!hit) break;
         sk = __ffs(hit) - 1;
+      } else {
+        sk = v0 - v;
+        if (sk < 0 || sk > 31) break;
       }
       const int scA = __shfl_sync(kFull, cA, sk);
       const bool sact = __shfl_sync(kFull, (int)act, sk) != 0;
@@ -512,7 +509,7 @@ __global__ void __launch_bounds__(kPkWarps * 32, CLASSES == 4 ? 6 : 5)   // 12 /
 gotoh_packed_kernel(const GotohBatch B) {
   constexpr bool TRACEBACK = TBMODE != kTbNone, FLAGS = TBMODE == kTbFlags, CKPT = TBMODE == kTbCkpt;
   constexpr int kFillUnroll = TRACEBACK ? TB_FILL_UNROLL_TB : 4;
-  constexpr int kPkTabWords = CLASSES * 512, kPkSmemWordsPerWarp = 2 * kPkTabWords + kPkTileWords;
+  constexpr int kPkTabWords = CLASSES * 512, kPkSmemWordsPerWarp = 2 * kPkTabWords;   // no per-warp shared memory besides the tables
   extern __shared__ int smem_pk[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned slot = blockIdx.x * kPkWarps + wib;
@@ -783,7 +780,7 @@ gotoh_packed_kernel(const GotohBatch B) {
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
-static size_t packed_smem_bytes(int classes) { return (size_t)kPkWarps * (2 * classes * 512 + kPkTileWords) * sizeof(int); }
+static size_t packed_smem_bytes(int classes) { return (size_t)kPkWarps * (2 * classes * 512) * sizeof(int); }
 int gotoh_packed_warps_per_block() { return kPkWarps; }
 unsigned long long gotoh_packed_ptr_words(int m, int n) { return packed_ptr_words_impl(m, n); }
 

@@ -223,21 +223,34 @@ def consensus(rows, fraction_called=0.5, ignore_last=False):
 
 # ---- orientation ------------------------------------------------------------------------------------------------------
 class _DeviceTrials:
-    """One orientation trial of revSeqBasedOnDist = every profile against the flipped one. With a device context the pool stays
-    in HBM for the whole stage: the arenas of a trial (all `num` slots against the spare slot) never change, so a trial is one
-    21 KB upload of the flipped profile, one tb_gotoh_pp on device pointers and one read of `num` scores -- no per-trial copy
-    of the pool through pinned staging (that was 8 ms per trial at 512 traces, against ~1 ms of kernel)."""
+    """Orientation trials of revSeqBasedOnDist (every profile against one flipped profile) on a pool that stays in HBM for the
+    whole stage, several trials per call. A trial fills only `num` of the GPU's ~1 800 warp slots and lasts as long as one pair
+    on one warp, so up to T consecutive trials (in the reference's order) go out together, each against the state at the start
+    of the group. The reference runs them one after the other and a kept flip of k_s changes ONE input of a later trial t of
+    the group: the pair (k_s, flip of k_t). Those T(T-1)/2 pairs (flip of k_s against flip of k_t) ride along in the same call,
+    and the host replays the reference's sequential accept rule on exact numbers -- same pairs, same kernel, same integers.
+    Arena order: trial t = `num` pairs (slot i, spare t) followed by its t fix-up pairs (spare s, spare t), s < t, so a shorter
+    last group is a prefix."""
 
-    def __init__(self, ctx, pool, num):
+    def __init__(self, ctx, pool, num, T):
         import torch
-        self.torch, self.ctx, self.num, self.cap = torch, ctx, num, pool.cap
+        self.torch, self.ctx, self.num, self.cap, self.T = torch, ctx, num, pool.cap, T
         dev = torch.device("cuda", ctx.device)
         self.base = torch.from_numpy(pool.base).to(dev)
-        self.off1 = torch.from_numpy(np.ascontiguousarray(pool.off[:num])).to(dev)
-        self.len1 = torch.from_numpy(np.ascontiguousarray(pool.lens[:num])).to(dev)
-        self.off2 = torch.full((num,), int(pool.off[num]), dtype=torch.int64, device=dev)
-        self.len2 = torch.zeros(num, dtype=torch.int32, device=dev)
-        self.scores = torch.zeros(num, dtype=torch.int32, device=dev)
+        self.start = [t * num + t * (t - 1) // 2 for t in range(T + 1)]
+        npairs = self.start[T]
+        a1_off, a2_off = np.zeros(npairs, np.int64), np.zeros(npairs, np.int64)
+        self.a1_len, self.a2_len = np.zeros(npairs, np.int32), np.zeros(npairs, np.int32)
+        for t in range(T):
+            b = self.start[t]
+            a1_off[b: b + num] = pool.off[:num]
+            self.a1_len[b: b + num] = pool.lens[:num]                     # a flip keeps the length
+            a1_off[b + num: b + num + t] = pool.off[num: num + t]
+            a2_off[b: b + num + t] = pool.off[num + t]
+        self.a1_off, self.a2_off = torch.from_numpy(a1_off).to(dev), torch.from_numpy(a2_off).to(dev)
+        self.d_a1_len = torch.zeros(npairs, dtype=torch.int32, device=dev)
+        self.d_a2_len = torch.zeros(npairs, dtype=torch.int32, device=dev)
+        self.scores = torch.zeros(npairs, dtype=torch.int32, device=dev)
         self.stage = torch.zeros(pool.cap, dtype=torch.float32).pin_memory()
 
     def put(self, slot, p):
@@ -246,12 +259,25 @@ class _DeviceTrials:
         self.base[slot * self.cap: slot * self.cap + p.size].copy_(self.stage[: p.size], non_blocking=False)
         return p.shape[1]
 
-    def trial(self, s_rc, sc):
-        self.len2.fill_(self.put(self.num, s_rc))
+    def group(self, flips, sc):
+        """flips: the flipped profiles of up to T consecutive trials. Returns (base int64[len(flips)][num], fix) with
+        base[t][i] = score(slot i, flip t) and fix[t][s] = score(flip s, flip t) for s < t."""
+        num, g = self.num, len(flips)
+        lens = [self.put(num + t, p) for t, p in enumerate(flips)]
+        for t in range(g):
+            b = self.start[t]
+            self.a1_len[b + num: b + num + t] = lens[:t]
+            self.a2_len[b: b + num + t] = lens[t]
+        n = self.start[g]
+        self.d_a1_len[:n].copy_(self.torch.from_numpy(self.a1_len[:n]))
+        self.d_a2_len[:n].copy_(self.torch.from_numpy(self.a2_len[:n]))
         self.torch.cuda.synchronize(self.base.device)               # torch's stream -> the context's stream
-        self.ctx.gotoh_device(PP, self.base.data_ptr(), self.off1.data_ptr(), self.len1.data_ptr(), self.base.data_ptr(), self.off2.data_ptr(),
-                              self.len2.data_ptr(), self.num, self.scores.data_ptr(), sc=sc, ac=_END_FREE)
-        return self.scores.cpu().numpy().astype(np.int64)
+        self.ctx.gotoh_device(PP, self.base.data_ptr(), self.a1_off.data_ptr(), self.d_a1_len.data_ptr(), self.base.data_ptr(),
+                              self.a2_off.data_ptr(), self.d_a2_len.data_ptr(), n, self.scores.data_ptr(), sc=sc, ac=_END_FREE)
+        sco = self.scores[:n].cpu().numpy().astype(np.int64)
+        base = [sco[self.start[t]: self.start[t] + num] for t in range(g)]
+        fix = [sco[self.start[t] + num: self.start[t] + num + t] for t in range(g)]
+        return base, fix
 
 
 def rev_seq_based_on_dist(ctx, profiles, fwd, sc):
@@ -261,35 +287,46 @@ def rev_seq_based_on_dist(ctx, profiles, fwd, sc):
     num = len(seq)
     d = np.zeros((num, num), np.int64)
     ii, jj = np.triu_indices(num, 1)
-    pool = _Pool(seq, spare=1)                                             # slot `num` holds the flip under trial
+    on_device = num > 1 and hasattr(ctx, "gotoh_device")                   # test doubles serve ctx.gotoh only: one trial per call
+    T = min(8, max(1, 1700 // num)) if on_device else 1
+    pool = _Pool(seq, spare=T)                                             # slots num.. hold the flips under trial
     if len(ii):
         s, _, _ = ctx.gotoh(PP, pool.arena(ii), pool.arena(jj), sc, _END_FREE, traceback=False)
         d[ii, jj] = s
         d[jj, ii] = s
     total = int(d[ii, jj].sum()) if len(ii) else 0
-    dev = _DeviceTrials(ctx, pool, num) if num > 1 and hasattr(ctx, "gotoh_device") else None   # test doubles serve ctx.gotoh only
+    dev = _DeviceTrials(ctx, pool, num, T) if on_device else None
     iterate = True
     while iterate:
-        quality = sorted((int(d[i].sum()), i) for i in range(num))      # worst row sum first, src/msa.h:270-282
-        for _, k in quality:
-            s_rc = _revcomp(seq[k])
-            others = [i for i in range(num) if i != k]
-            new_d = np.zeros(num, np.int64)
-            if others and dev is not None:
-                new_d = dev.trial(s_rc, sc)
-                new_d[k] = 0                                             # the pair (k, flipped k) rides along and is dropped
-            elif others:
-                pool.put(num, s_rc)
-                sc_new, _, _ = ctx.gotoh(PP, pool.arena(others), pool.arena([num] * len(others)), sc, _END_FREE, traceback=False)
-                new_d[others] = sc_new
-            if int(new_d.sum()) >= int(d[others, k].sum()):              # scoreSum >= oldScoreSum, src/msa.h:298
-                seq[k] = s_rc
-                pool.put(k, s_rc)
-                if dev is not None:
-                    dev.put(k, s_rc)
-                fwd[k] = not fwd[k]
-                d[:, k] = new_d
-                d[k, :] = new_d
+        quality = [k for _, k in sorted((int(d[i].sum()), i) for i in range(num))]   # worst row sum first, src/msa.h:270-282
+        for g0 in range(0, num, T):
+            ks = quality[g0: g0 + T]
+            flips = [_revcomp(seq[k]) for k in ks]
+            if dev is not None:
+                base, fix = dev.group(flips, sc)
+            kept = []                                                    # trials of this group whose flip was kept
+            for t, k in enumerate(ks):
+                s_rc = flips[t]
+                others = [i for i in range(num) if i != k]
+                new_d = np.zeros(num, np.int64)
+                if others and dev is not None:
+                    new_d = base[t].copy()
+                    for s_ in kept:                                      # k_s was flipped after the group went out
+                        new_d[ks[s_]] = fix[t][s_]
+                    new_d[k] = 0                                         # the pair (k, flipped k) rides along and is dropped
+                elif others:
+                    pool.put(num, s_rc)
+                    sc_new, _, _ = ctx.gotoh(PP, pool.arena(others), pool.arena([num] * len(others)), sc, _END_FREE, traceback=False)
+                    new_d[others] = sc_new
+                if int(new_d.sum()) >= int(d[others, k].sum()):          # scoreSum >= oldScoreSum, src/msa.h:298
+                    seq[k] = s_rc
+                    pool.put(k, s_rc)
+                    if dev is not None:
+                        dev.put(k, s_rc)
+                    kept.append(t)
+                    fwd[k] = not fwd[k]
+                    d[:, k] = new_d
+                    d[k, :] = new_d
         updated = int(d.sum())
         if total < updated:
             total = updated

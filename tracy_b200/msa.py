@@ -280,6 +280,30 @@ class _DeviceTrials:
         return base, fix
 
 
+class _HostTrials:
+    """The same grouping with the pool in host memory, for contexts without device entry points (the CPU test double of
+    tests/test_glue.py): one ctx.gotoh call per group, arenas in the order _DeviceTrials uses."""
+
+    def __init__(self, ctx, pool, num, T):
+        self.ctx, self.pool, self.num, self.T = ctx, pool, num, T
+
+    def put(self, slot, p):                                            # the caller keeps the host pool current itself
+        pass
+
+    def group(self, flips, sc):
+        num = self.num
+        i1, i2, start = [], [], [0]
+        for t, p in enumerate(flips):
+            self.pool.put(num + t, p)
+            i1 += list(range(num)) + [num + s for s in range(t)]
+            i2 += [num + t] * (num + t)
+            start.append(len(i1))
+        sco, _, _ = self.ctx.gotoh(PP, self.pool.arena(i1), self.pool.arena(i2), sc, _END_FREE, traceback=False)
+        sco = np.asarray(sco, np.int64)
+        return ([sco[start[t]: start[t] + num] for t in range(len(flips))],
+                [sco[start[t] + num: start[t + 1]] for t in range(len(flips))])
+
+
 def rev_seq_based_on_dist(ctx, profiles, fwd, sc):
     """revSeqBasedOnDist (src/msa.h:243-328). profiles: list of float32[6][len] (replaced in place when a flip is kept),
     fwd: list of bool (toggled in place). Returns the final symmetric score matrix."""
@@ -287,42 +311,38 @@ def rev_seq_based_on_dist(ctx, profiles, fwd, sc):
     num = len(seq)
     d = np.zeros((num, num), np.int64)
     ii, jj = np.triu_indices(num, 1)
-    on_device = num > 1 and hasattr(ctx, "gotoh_device")                   # test doubles serve ctx.gotoh only: one trial per call
-    T = min(8, max(1, 1700 // num)) if on_device else 1
+    on_device = hasattr(ctx, "gotoh_device")                               # test doubles serve ctx.gotoh only
+    T = min(8, max(1, 1700 // max(num, 1)))
     pool = _Pool(seq, spare=T)                                             # slots num.. hold the flips under trial
     if len(ii):
         s, _, _ = ctx.gotoh(PP, pool.arena(ii), pool.arena(jj), sc, _END_FREE, traceback=False)
         d[ii, jj] = s
         d[jj, ii] = s
     total = int(d[ii, jj].sum()) if len(ii) else 0
-    dev = _DeviceTrials(ctx, pool, num, T) if on_device else None
+    trials = (_DeviceTrials if on_device else _HostTrials)(ctx, pool, num, T) if num > 1 else None
     iterate = True
     while iterate:
         quality = [k for _, k in sorted((int(d[i].sum()), i) for i in range(num))]   # worst row sum first, src/msa.h:270-282
         for g0 in range(0, num, T):
             ks = quality[g0: g0 + T]
             flips = [_revcomp(seq[k]) for k in ks]
-            if dev is not None:
-                base, fix = dev.group(flips, sc)
+            if trials is not None:
+                base, fix = trials.group(flips, sc)
             kept = []                                                    # trials of this group whose flip was kept
             for t, k in enumerate(ks):
                 s_rc = flips[t]
                 others = [i for i in range(num) if i != k]
                 new_d = np.zeros(num, np.int64)
-                if others and dev is not None:
+                if others:
                     new_d = base[t].copy()
                     for s_ in kept:                                      # k_s was flipped after the group went out
                         new_d[ks[s_]] = fix[t][s_]
                     new_d[k] = 0                                         # the pair (k, flipped k) rides along and is dropped
-                elif others:
-                    pool.put(num, s_rc)
-                    sc_new, _, _ = ctx.gotoh(PP, pool.arena(others), pool.arena([num] * len(others)), sc, _END_FREE, traceback=False)
-                    new_d[others] = sc_new
                 if int(new_d.sum()) >= int(d[others, k].sum()):          # scoreSum >= oldScoreSum, src/msa.h:298
                     seq[k] = s_rc
                     pool.put(k, s_rc)
-                    if dev is not None:
-                        dev.put(k, s_rc)
+                    if trials is not None:
+                        trials.put(k, s_rc)
                     kept.append(t)
                     fwd[k] = not fwd[k]
                     d[:, k] = new_d

@@ -555,8 +555,8 @@ inline std::vector<char> anchorBatch(Context& g, Index const& index, TConfig con
 // distanceMatrix(c, sps, d) -- reference src/msa.h:33-42: d[i][j] = gotohScore(sps[i], sps[j], AlignConfig<true,true>) for
 // all i < j, as ONE batched GPU call (the N(N-1)/2 fills of assemble's all-pairs stage). sps: any indexable container of
 // profiles; d: any [n][n] array (only the upper triangle is written, like the reference).
-template <typename TConfig, typename TSeqProfiles, typename TDistArray>
-inline void distanceMatrix(Context& g, TConfig const& c, TSeqProfiles const& sps, TDistArray& d) {
+template <typename TCtx, typename TConfig, typename TSeqProfiles, typename TDistArray>
+inline void distanceMatrix(TCtx& g, TConfig const& c, TSeqProfiles const& sps, TDistArray& d) {
   typedef typename std::decay<decltype(sps[0])>::type TProfile;
   const std::size_t n = sps.size();
   std::vector<const TProfile*> a, b;
@@ -566,6 +566,249 @@ inline void distanceMatrix(Context& g, TConfig const& c, TSeqProfiles const& sps
   std::size_t k = 0;
   for (std::size_t i = 0; i < n; ++i)
     for (std::size_t j = i + 1; j < n; ++j) d[i][j] = s[k++];
+}
+
+// ---- assemble: orientation of the traces by their all-pairs scores ----------------------------------------------------------
+namespace detail {
+// reverseComplementProfile on the host (reference src/profile.h:74-90 is a pure permutation: columns reversed, rows A<->T and
+// C<->G swapped, N and '-' kept), for glue that must not pay a device round trip per profile.
+template <typename TProfile> inline void revcomp_profile_host(TProfile const& p, TProfile& out) {
+  const std::size_t len = p.shape()[1];
+  resize_align(out, 6, len);
+  static const int from[6] = {3, 2, 1, 0, 4, 5};
+  for (int r = 0; r < 6; ++r)
+    for (std::size_t j = 0; j < len; ++j) out[r][j] = p[from[r]][len - 1 - j];
+}
+}  // namespace detail
+
+// revSeqBasedOnDist(c, seq, fwd) -- reference src/msa.h:243-328: all-pairs gotohScore matrix (AlignConfig<true,true>), then
+// sweeps over the traces, worst row sum first; a trace is flipped when the sum of its scores against all others does not get
+// worse (`scoreSum >= oldScoreSum`); sweeps repeat while the matrix total grows. int32 sums as in the reference.
+// The reference runs one trial (num - 1 fills) after the other. Here the initial matrix is ONE batched call and the trials
+// go out in groups of T consecutive ones, each against the state at the start of the group; a flip kept inside the group
+// changes one input of a later trial t of that group -- the pair (k_s, flip of k_t) -- so those T(T-1)/2 pairs (flip of k_s
+// against flip of k_t) ride along in the same call and the host replays the sequential accept rule on exact numbers.
+// TCtx: Context, or any type for which gotohBatch(ctx, a1, a2, ac, sc) is callable (the CPU double of tests/cpp/hostlogic.cpp
+// serves it with the reference's own gotohScore). `log` receives the reference's progress dots (it prints them to std::cout).
+template <typename TCtx, typename TConfig, typename TSeqProfiles>
+inline void revSeqBasedOnDist(TCtx& g, TConfig const& c, TSeqProfiles& seq, std::vector<bool>& fwd, std::ostream* log = &std::cout) {
+  typedef typename TSeqProfiles::value_type TProfile;
+  const std::size_t num = seq.size();
+  std::vector<std::vector<int32_t> > d(num, std::vector<int32_t>(num, 0));
+  int32_t totalScore = 0;
+  {
+    std::vector<const TProfile*> a, b;
+    for (std::size_t i = 0; i < num; ++i)
+      for (std::size_t j = i + 1; j < num; ++j) { a.push_back(&seq[i]); b.push_back(&seq[j]); }
+    const std::vector<int32_t> s = gotohBatch(g, a, b, AlignConfig<true, true>(), c.aliscore);
+    std::size_t k = 0;
+    for (std::size_t i = 0; i < num; ++i)
+      for (std::size_t j = i + 1; j < num; ++j) { d[i][j] = d[j][i] = s[k++]; totalScore += d[i][j]; }
+  }
+  const std::size_t T = std::min<std::size_t>(8, std::max<std::size_t>(1, 1700 / std::max<std::size_t>(num, 1)));
+  bool iterateScore = true;
+  while (iterateScore) {
+    std::vector<std::pair<int32_t, int32_t> > quality;                 // (row sum, index), worst first, src/msa.h:270-282
+    for (std::size_t i = 0; i < num; ++i) {
+      int32_t rowSum = 0;
+      for (std::size_t j = 0; j < num; ++j) rowSum += d[i][j];
+      quality.push_back(std::make_pair(rowSum, (int32_t)i));
+    }
+    std::sort(quality.begin(), quality.end());
+    for (std::size_t g0 = 0; g0 < num; g0 += T) {
+      const std::size_t gsz = std::min(T, num - g0);
+      std::vector<TProfile> flips(gsz);
+      for (std::size_t t = 0; t < gsz; ++t) detail::revcomp_profile_host(seq[(std::size_t)quality[g0 + t].second], flips[t]);
+      std::vector<const TProfile*> a, b;
+      std::vector<std::size_t> start(gsz + 1, 0);
+      for (std::size_t t = 0; t < gsz; ++t) {                          // trial t: num pairs (i, flip t), then its fix-up pairs (flip s, flip t)
+        start[t] = a.size();
+        for (std::size_t i = 0; i < num; ++i) { a.push_back(&seq[i]); b.push_back(&flips[t]); }
+        for (std::size_t s = 0; s < t; ++s) { a.push_back(&flips[s]); b.push_back(&flips[t]); }
+      }
+      start[gsz] = a.size();
+      const std::vector<int32_t> sco = gotohBatch(g, a, b, AlignConfig<true, true>(), c.aliscore);
+      std::vector<std::size_t> kept;                                   // trials of this group whose flip was kept
+      for (std::size_t t = 0; t < gsz; ++t) {
+        const std::size_t k = (std::size_t)quality[g0 + t].second;
+        std::vector<int32_t> newD(num, 0);
+        for (std::size_t i = 0; i < num; ++i) if (i != k) newD[i] = sco[start[t] + i];
+        for (std::size_t s : kept) newD[(std::size_t)quality[g0 + s].second] = sco[start[t] + num + s];   // k_s was flipped after the group went out
+        int32_t scoreSum = 0, oldScoreSum = 0;
+        for (std::size_t i = 0; i < num; ++i) if (i != k) { oldScoreSum += d[i][k]; scoreSum += newD[i]; }
+        if (scoreSum >= oldScoreSum) {                                  // src/msa.h:298
+          seq[k] = flips[t];
+          fwd[k] = !fwd[k];
+          for (std::size_t i = 0; i < num; ++i) { d[i][k] = newD[i]; d[k][i] = d[i][k]; }
+          kept.push_back(t);
+        }
+        if (log) *log << "." << std::flush;
+      }
+    }
+    int32_t updatedScore = 0;
+    for (std::size_t i = 0; i < num; ++i)
+      for (std::size_t j = 0; j < num; ++j) updatedScore += d[i][j];
+    if (totalScore < updatedScore) totalScore = updatedScore;
+    else iterateScore = false;
+  }
+  if (log) *log << std::endl;
+}
+
+// ---- assemble: guide tree and progressive alignment -------------------------------------------------------------------------
+namespace detail {
+// Consensus character of one profile column (reference src/align.h:254-270): the first strict maximum over the six rows,
+// compared as double; the N row and the gap row both read 'N' (never '-': that would allow gap-to-gap columns).
+template <typename TProfile> inline char profile_cons_char(TProfile const& p, std::size_t pos) {
+  int best = 0;
+  double top = p[0][pos];
+  for (int k = 1; k < 6; ++k) if ((double)p[k][pos] > top) { top = p[k][pos]; best = k; }
+  return best < 4 ? "ACGT"[best] : 'N';
+}
+// Column-frequency profile of a character alignment (reference src/align.h:138-180). A row takes part in the columns between
+// its first and last non-gap character; A, C, G, T, N (either case) and '-' are counted there, any other character takes the
+// row out of that column's denominator; each count is divided by the denominator in float.
+template <typename TProfile> inline void profile_of_alignment(std::vector<std::string> const& rows, TProfile& p) {
+  const std::size_t ncol = rows.empty() ? 0 : rows[0].size();
+  resize_align(p, 6, ncol);
+  std::vector<long> first(rows.size(), -1), last(rows.size(), (long)ncol);
+  for (std::size_t i = 0; i < rows.size(); ++i)
+    for (std::size_t j = 0; j < ncol; ++j)
+      if (rows[i][j] != '-') { if (first[i] < 0) first[i] = (long)j; last[i] = (long)j; }
+  for (std::size_t j = 0; j < ncol; ++j) {
+    float cnt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int sum = 0;
+    for (std::size_t i = 0; i < rows.size(); ++i) {
+      if ((long)j < first[i] || (long)j > last[i]) continue;          // a row of gaps only keeps first = -1, last = ncol: like the reference it then covers every column
+      const char ch = rows[i][j];
+      const int k = (ch == 'A' || ch == 'a') ? 0 : (ch == 'C' || ch == 'c') ? 1 : (ch == 'G' || ch == 'g') ? 2 : (ch == 'T' || ch == 't') ? 3
+                    : (ch == 'N' || ch == 'n') ? 4 : ch == '-' ? 5 : -1;
+      if (k >= 0) { cnt[k] += 1; ++sum; }
+    }
+    for (int k = 0; k < 6; ++k) p[k][j] = sum > 0 ? cnt[k] / sum : cnt[k];
+  }
+}
+// UPGMA guide tree over a SCORE matrix (reference src/msa.h:44-87: the largest score joins first, first maximum in row-major
+// order wins; the score of a new node against an open node is the mean of its children's, C++ integer division; joined nodes
+// leave the matrix). d: (2 num + 1)^2 ints, upper triangle, -1 = closed. p[v] = {parent, left, right}, -1 = none. Returns the root.
+inline long upgma_tree(std::vector<std::vector<int> >& d, std::vector<std::vector<int> >& p, long num) {
+  long nn = num;
+  for (; nn < 2 * num + 1; ++nn) {
+    long bi = 0, bj = 0;
+    int top = -1;
+    for (long i = 0; i < nn; ++i)
+      for (long j = i + 1; j < nn; ++j) if (d[i][j] > top) { top = d[i][j]; bi = i; bj = j; }
+    if (top == -1) break;
+    p[bi][0] = p[bj][0] = (int)nn;
+    p[nn][1] = (int)bi; p[nn][2] = (int)bj;
+    for (long i = 0; i < nn; ++i)
+      if (p[i][0] == -1) d[i][nn] = ((bi < i ? d[bi][i] : d[i][bi]) + (bj < i ? d[bj][i] : d[i][bj])) / 2;
+    for (long i = 0; i < bi; ++i) d[i][bi] = -1;
+    for (long i = bi + 1; i < nn + 1; ++i) d[bi][i] = -1;
+    for (long i = 0; i < bj; ++i) d[i][bj] = -1;
+    for (long i = bj + 1; i < nn + 1; ++i) d[bj][i] = -1;
+  }
+  return nn > 0 ? nn - 1 : 0;
+}
+}  // namespace detail
+
+// msa(c, sps, align, seqidx) -- reference src/msa.h:330-368 with palign :89-160: all-pairs score matrix, UPGMA guide tree,
+// progressive profile x profile alignment (AlignConfig<true,true>) bottom-up, rows merged by the gap pattern of each node's
+// alignment, node profile = column frequencies of its rows. The reference recurses node by node (one gotoh per node); nodes
+// of equal height are independent, so each height level is ONE batched call. seqidx: the input index of every output row.
+// TCtx as for revSeqBasedOnDist (gotohBatch with and without the ops strings).
+template <typename TCtx, typename TConfig, typename TSeqProfiles, typename TAlign>
+inline void msa(TCtx& g, TConfig const& c, TSeqProfiles const& sps, TAlign& align, std::vector<uint32_t>& seqidx) {
+  typedef typename TSeqProfiles::value_type TProfile;
+  const long num = (long)sps.size();
+  std::vector<std::vector<int> > d((std::size_t)(2 * num + 1), std::vector<int>((std::size_t)(2 * num + 1), 0));
+  for (long i = 0; i < 2 * num + 1; ++i)
+    for (long j = i + 1; j < 2 * num + 1; ++j) d[i][j] = -1;
+  distanceMatrix(g, c, sps, d);
+  std::vector<std::vector<int> > p((std::size_t)(2 * num + 1), std::vector<int>(3, -1));
+  const long root = detail::upgma_tree(d, p, num);
+
+  struct Node { std::vector<std::string> rows; TProfile prof; std::vector<uint32_t> idx; int height = 0; };
+  std::vector<Node> node((std::size_t)(2 * num + 1));
+  int top = 0;
+  for (long v = 0; v <= root; ++v) {                                    // children have smaller indices than their parent
+    Node& nd = node[(std::size_t)v];
+    if (p[v][1] == -1 && p[v][2] == -1) {
+      if (v >= num) continue;
+      const std::size_t len = sps[(std::size_t)v].shape()[1];           // leaf: consensus characters of the trace profile
+      nd.rows.assign(1, std::string(len, 'N'));
+      for (std::size_t j = 0; j < len; ++j) nd.rows[0][j] = detail::profile_cons_char(sps[(std::size_t)v], j);
+      detail::resize_align(nd.prof, 6, len);
+      for (int k = 0; k < 6; ++k) for (std::size_t j = 0; j < len; ++j) nd.prof[k][j] = sps[(std::size_t)v][k][j];
+      nd.idx.assign(1, (uint32_t)v);
+    } else {
+      nd.height = 1 + std::max(node[(std::size_t)p[v][1]].height, node[(std::size_t)p[v][2]].height);
+      top = std::max(top, nd.height);
+    }
+  }
+  for (int h = 1; h <= top; ++h) {
+    std::vector<long> level;
+    std::vector<const TProfile*> a, b;
+    for (long v = num; v <= root; ++v)
+      if (node[(std::size_t)v].height == h) { level.push_back(v); a.push_back(&node[(std::size_t)p[v][1]].prof); b.push_back(&node[(std::size_t)p[v][2]].prof); }
+    std::vector<std::string> ops;
+    gotohBatch(g, a, b, AlignConfig<true, true>(), c.aliscore, &ops);
+    for (std::size_t q = 0; q < level.size(); ++q) {
+      Node& nd = node[(std::size_t)level[q]];
+      Node& l = node[(std::size_t)p[level[q]][1]];
+      Node& r = node[(std::size_t)p[level[q]][2]];
+      const std::string& o = ops[q];                                    // 's' both advance, 'h' gap in the left rows, 'v' gap in the right rows
+      nd.rows.assign(l.rows.size() + r.rows.size(), std::string(o.size(), '-'));
+      std::size_t a1p = 0, a2p = 0;
+      for (std::size_t j = 0; j < o.size(); ++j) {
+        if (o[j] != 'h') { for (std::size_t k = 0; k < l.rows.size(); ++k) nd.rows[k][j] = l.rows[k][a1p]; ++a1p; }
+        if (o[j] != 'v') { for (std::size_t k = 0; k < r.rows.size(); ++k) nd.rows[l.rows.size() + k][j] = r.rows[k][a2p]; ++a2p; }
+      }
+      detail::profile_of_alignment(nd.rows, nd.prof);
+      nd.idx = l.idx;
+      nd.idx.insert(nd.idx.end(), r.idx.begin(), r.idx.end());
+      l.rows.clear(); r.rows.clear();                                   // children are not needed again
+    }
+  }
+  const Node& rt = node[(std::size_t)root];
+  const std::size_t ncol = rt.rows.empty() ? 0 : rt.rows[0].size();
+  detail::resize_align(align, rt.rows.size(), ncol);
+  for (std::size_t i = 0; i < rt.rows.size(); ++i)
+    for (std::size_t j = 0; j < ncol; ++j) align[i][j] = rt.rows[i][j];
+  seqidx = rt.idx;
+}
+
+// matchingTraces(c, profiles) -- the exclusion loop of assemble(), reference src/assemble.h:428-458: trace i stays in the
+// assembly iff its end-gap-free alignment with SOME other trace j has more than 10 % of i aligned, more than 25 aligned columns
+// and a score above numAligned * (matchFraction * match + (1 - matchFraction) * mismatch), the threshold evaluated in the
+// reference's own mixed int / float arithmetic. The reference tries j = 0, 1, ... one gotoh() at a time and stops at the first
+// hit; traces are independent of each other, so round r aligns every still-unmatched trace with its r-th candidate in one call.
+template <typename TCtx, typename TConfig, typename TSeqProfiles>
+inline std::vector<bool> matchingTraces(TCtx& g, TConfig const& c, TSeqProfiles const& profiles) {
+  typedef typename TSeqProfiles::value_type TProfile;
+  const std::size_t n = profiles.size();
+  std::vector<bool> keep(n, false);
+  std::vector<std::size_t> pending, next(n, 0);                        // next[i]: the candidate j trace i tries in this round
+  for (std::size_t i = 0; i < n; ++i) { next[i] = i == 0 ? 1 : 0; if (next[i] < n) pending.push_back(i); }
+  while (!pending.empty()) {
+    std::vector<const TProfile*> a, b;
+    for (std::size_t i : pending) { a.push_back(&profiles[i]); b.push_back(&profiles[next[i]]); }
+    std::vector<std::string> ops;
+    const std::vector<int32_t> gs = gotohBatch(g, a, b, AlignConfig<true, true>(), c.aliscore, &ops);
+    std::vector<std::size_t> still;
+    for (std::size_t q = 0; q < pending.size(); ++q) {
+      const std::size_t i = pending[q];
+      const int32_t seqSize = (int32_t)profiles[i].shape()[1];
+      const int32_t numAligned = (int32_t)std::count(ops[q].begin(), ops[q].end(), 's');
+      const double frac = (double)numAligned / (double)seqSize;
+      const double scoreThreshold = numAligned * c.matchFraction * c.aliscore.match + numAligned * (1 - c.matchFraction) * c.aliscore.mismatch;
+      if (frac > 0.1 && numAligned > 25 && gs[q] > scoreThreshold) { keep[i] = true; continue; }
+      ++next[i];
+      if (next[i] == i) ++next[i];
+      if (next[i] < n) still.push_back(i);
+    }
+    pending.swap(still);
+  }
+  return keep;
 }
 
 // ---- batch drivers: the DP sequence of sage() for many traces ---------------------------------------------------------

@@ -6,6 +6,7 @@ struct Calls { std::string primary, secondary, consensus; };
 struct Slice { std::string refslice; };
 struct Breakpoint { bool indelshift, traceleft; uint32_t breakpoint; float bestDiff; };
 struct Cfg { uint16_t trimLeft, trimRight, maxindel, madc; };
+struct AssembleCfg { tracy_b200::DnaScore<int32_t> aliscore; float matchFraction; };
 
 int main() {
   using namespace tracy_b200;
@@ -23,5 +24,13 @@ int main() {
   Calls bc; Slice rs; Breakpoint bp{true, true, 3, 0.f}; Cfg c{0, 0, 30, 5};
   std::vector<std::pair<int32_t, int32_t> > dcp;
   decomposeAlleles(g, c, align, bc, bp, rs, dcp, nullptr);
+  // the assemble glue: orientation, exclusion, guide tree + progressive alignment
+  AssembleCfg ac2{sc, 0.5f};
+  std::vector<Matrix<float> > traces(3, Matrix<float>(6, 30));
+  std::vector<bool> fwd(3, true);
+  revSeqBasedOnDist(g, ac2, traces, fwd, nullptr);
+  s += (int)matchingTraces(g, ac2, traces).size();
+  std::vector<uint32_t> seqidx;
+  msa(g, ac2, traces, align, seqidx);
   return s == 12345;
 }

@@ -1,0 +1,175 @@
+// Host-logic check (TEST INFRASTRUCTURE, CPU only): the glue of include/tracy_b200.hpp that sits ABOVE the batched DP calls,
+// run with a CPU double of the context whose gotohBatch() is served by the UNMODIFIED reference's own gotohScore, against the
+// reference's function of the same name from /root/reference/src. What is compared is therefore the host logic alone
+// (grouping of the orientation trials, fix-up pairs, the sequential accept rule, int32 sums; UPGMA, level-wise progressive
+// alignment, row merging, column-frequency profiles); the device side of gotohBatch
+// is what tests/cpp/dropin.cpp checks on the B200.
+// Built and run by tests/test_cpp_binding.py where /root/reference exists.
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <sdsl/suffix_arrays.hpp>
+
+#include "tracy_boost_stubs.hpp"
+#include "abif.h"
+#include "scf.h"
+#include "align.h"
+#include "gotoh.h"
+#include "fmindex.h"
+#include "profile.h"
+#include "decompose.h"
+#include "msa.h"
+
+#define TRACY_B200_WITH_BOOST
+#include "tracy_b200.hpp"
+
+typedef boost::multi_array<float, 2> TProfile;
+
+namespace cpu_double {
+struct Ctx { long calls = 0, pairs = 0; };
+// the call shape revSeqBasedOnDist needs, found by argument-dependent lookup on Ctx
+template <typename TA, typename TB, bool H, bool V, typename TScore>
+inline std::vector<int32_t> gotohBatch(Ctx& g, std::vector<const TA*> const& a1, std::vector<const TB*> const& a2, tracy_b200::AlignConfig<H, V> const&,
+                                       TScore const& sc, std::vector<std::string>* ops = nullptr) {
+  std::vector<int32_t> s(a1.size());
+  tracy::AlignConfig<H, V> ac;
+  if (ops) ops->assign(a1.size(), std::string());
+  for (std::size_t i = 0; i < a1.size(); ++i) {
+    if (!ops) { s[i] = tracy::gotohScore(*a1[i], *a2[i], ac, sc); continue; }
+    boost::multi_array<char, 2> al;
+    s[i] = tracy::gotoh(*a1[i], *a2[i], al, ac, sc);
+    for (std::size_t j = 0; j < al.shape()[1]; ++j) (*ops)[i] += al[0][j] == '-' ? 'h' : al[1][j] == '-' ? 'v' : 's';   // start -> end, as tb_gotoh_* returns them
+  }
+  ++g.calls; g.pairs += (long)a1.size();
+  return s;
+}
+}  // namespace cpu_double
+
+struct Cfg { tracy::DnaScore<int32_t> aliscore; float matchFraction; Cfg() : aliscore(3, -5, -10, -4), matchFraction(0.5f) {} };
+
+static std::mt19937_64 rng(4242);
+static void profile_of(std::string const& s, TProfile& p, float wmin = 0.55f) {
+  p.resize(boost::extents[6][s.size()]);
+  std::uniform_real_distribution<float> U(0.f, 1.f);
+  for (std::size_t j = 0; j < s.size(); ++j) {
+    const int b = s[j] == 'C' ? 1 : s[j] == 'G' ? 2 : s[j] == 'T' ? 3 : 0;
+    const float w = wmin + (1.f - wmin) * U(rng);
+    for (int k = 0; k < 6; ++k) p[k][j] = 0.f;
+    for (int k = 0; k < 4; ++k) p[k][j] = k == b ? w : (1.f - w) / 3.f;
+  }
+}
+static bool same(TProfile const& x, TProfile const& y) {
+  if (x.shape()[1] != y.shape()[1]) return false;
+  for (int k = 0; k < 6; ++k)
+    for (std::size_t j = 0; j < x.shape()[1]; ++j) if (x[k][j] != y[k][j]) return false;
+  return true;
+}
+
+int main() {
+  int checks = 0, failures = 0;
+  const char comp[] = "TGCA";
+  for (int rep = 0; rep < 12; ++rep) {
+    // overlapping reads of a random contig, a random subset reverse-complemented, a few unrelated reads mixed in
+    const int num = 1 + (int)(rng() % 11), len = 60 + (int)(rng() % 80), step = 15 + (int)(rng() % 30);
+    std::string contig((std::size_t)(step * num + len), 'A');
+    for (auto& ch : contig) ch = "ACGT"[rng() % 4];
+    std::vector<TProfile> seq((std::size_t)num);
+    for (int i = 0; i < num; ++i) {
+      std::string s = contig.substr((std::size_t)(step * i), (std::size_t)len);
+      if (rng() % 7 == 0) for (auto& ch : s) ch = "ACGT"[rng() % 4];
+      for (int e = 0; e < 3; ++e) s[rng() % s.size()] = "ACGT"[rng() % 4];
+      if (rng() % 2) {
+        std::string r(s.rbegin(), s.rend());
+        for (auto& ch : r) ch = comp[ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3];
+        s = r;
+      }
+      profile_of(s, seq[(std::size_t)i]);
+    }
+    std::vector<TProfile> seq_ref(seq), seq_new(seq);
+    std::vector<bool> fwd_ref((std::size_t)num, true), fwd_new((std::size_t)num, true);
+    Cfg c;
+    std::stringstream sink;
+    std::streambuf* old = std::cout.rdbuf(sink.rdbuf());           // the reference prints its progress dots to std::cout
+    tracy::revSeqBasedOnDist(c, seq_ref, fwd_ref);
+    std::cout.rdbuf(old);
+    cpu_double::Ctx g;
+    std::stringstream dots;
+    tracy_b200::revSeqBasedOnDist(g, c, seq_new, fwd_new, &dots);
+    ++checks;
+    bool ok = fwd_ref == fwd_new && dots.str() == sink.str();
+    for (int i = 0; ok && i < num; ++i) ok = same(seq_ref[(std::size_t)i], seq_new[(std::size_t)i]);
+    if (!ok) { ++failures; std::printf("MISMATCH revSeqBasedOnDist #%d (num=%d)\n", rep, num); }
+    else std::printf("revSeqBasedOnDist #%d: num=%d, %d flipped, %ld batched calls for %ld pairs\n", rep, num,
+                     (int)std::count(fwd_new.begin(), fwd_new.end(), false), g.calls, g.pairs);
+  }
+  // msa: distance matrix -> UPGMA -> progressive alignment, level by level here, node by node in the reference
+  for (int rep = 0; rep < 10; ++rep) {
+    const int num = 1 + (int)(rng() % 12), len = 50 + (int)(rng() % 70), step = 12 + (int)(rng() % 25);
+    std::string contig((std::size_t)(step * num + len), 'A');
+    for (auto& ch : contig) ch = "ACGT"[rng() % 4];
+    std::vector<TProfile> sps((std::size_t)num);
+    for (int i = 0; i < num; ++i) {
+      std::string s = contig.substr((std::size_t)(step * i), (std::size_t)(len - (int)(rng() % 10)));
+      for (int e = 0; e < 4; ++e) s[rng() % s.size()] = "ACGT"[rng() % 4];
+      if (rng() % 3 == 0) s.erase(rng() % (s.size() - 5), 1 + rng() % 3);
+      profile_of(s, sps[(std::size_t)i]);
+    }
+    Cfg c;
+    boost::multi_array<char, 2> al_ref, al_new;
+    std::vector<uint32_t> idx_ref, idx_new;
+    tracy::msa(c, sps, al_ref, idx_ref);
+    cpu_double::Ctx g;
+    tracy_b200::msa(g, c, sps, al_new, idx_new);
+    ++checks;
+    bool ok = idx_ref == idx_new && al_ref.shape()[0] == al_new.shape()[0] && al_ref.shape()[1] == al_new.shape()[1];
+    for (std::size_t i = 0; ok && i < al_ref.shape()[0]; ++i)
+      for (std::size_t j = 0; ok && j < al_ref.shape()[1]; ++j) ok = al_ref[i][j] == al_new[i][j];
+    if (!ok) { ++failures; std::printf("MISMATCH msa #%d (num=%d)\n", rep, num); }
+    else std::printf("msa #%d: num=%d, %zu x %zu alignment, %ld batched calls for %ld pairs\n", rep, num, (std::size_t)al_new.shape()[0],
+                     (std::size_t)al_new.shape()[1], g.calls, g.pairs);
+  }
+  // the exclusion loop of assemble(): the reference has it inline in assemble() (src/assemble.h:428-458), so the comparison side is
+  // that loop written out here around the reference's own gotoh(): first hit in index order, one pair at a time
+  for (int rep = 0; rep < 8; ++rep) {
+    const int num = 2 + (int)(rng() % 9), len = 120 + (int)(rng() % 80), step = 30 + (int)(rng() % 40);
+    std::string contig((std::size_t)(step * num + len), 'A');
+    for (auto& ch : contig) ch = "ACGT"[rng() % 4];
+    std::vector<TProfile> ps((std::size_t)num);
+    for (int i = 0; i < num; ++i) {
+      std::string s = contig.substr((std::size_t)(step * i), (std::size_t)len);
+      if (rng() % 3 == 0) for (auto& ch : s) ch = "ACGT"[rng() % 4];          // an unrelated trace: must be excluded
+      for (int e = 0; e < 5; ++e) s[rng() % s.size()] = "ACGT"[rng() % 4];
+      profile_of(s, ps[(std::size_t)i], 0.93f);
+    }
+    Cfg c;
+    c.matchFraction = rep % 2 ? 0.5f : 0.8f;
+    std::vector<bool> want((std::size_t)num, false);
+    for (int i = 0; i < num; ++i)
+      for (int j = 0; j < num && !want[(std::size_t)i]; ++j) {
+        if (i == j) continue;
+        tracy::AlignConfig<true, true> ac;
+        boost::multi_array<char, 2> al;
+        const int32_t gs = tracy::gotoh(ps[(std::size_t)i], ps[(std::size_t)j], al, ac, c.aliscore);
+        int32_t numAligned = 0;
+        for (std::size_t k = 0; k < al.shape()[1]; ++k) if (al[0][k] != '-' && al[1][k] != '-') ++numAligned;
+        const double frac = (double)numAligned / (double)(int32_t)ps[(std::size_t)i].shape()[1];
+        const double thr = numAligned * c.matchFraction * c.aliscore.match + numAligned * (1 - c.matchFraction) * c.aliscore.mismatch;
+        if (frac > 0.1 && numAligned > 25 && gs > thr) want[(std::size_t)i] = true;
+      }
+    cpu_double::Ctx g;
+    const std::vector<bool> got = tracy_b200::matchingTraces(g, c, ps);
+    ++checks;
+    if (got != want) { ++failures; std::printf("MISMATCH matchingTraces #%d (num=%d)\n", rep, num); }
+    else std::printf("matchingTraces #%d: num=%d, %d kept, %ld batched calls for %ld pairs\n", rep, num, (int)std::count(got.begin(), got.end(), true), g.calls, g.pairs);
+  }
+  std::printf("%d checks, %d mismatches\n", checks, failures);
+  return failures ? 1 : 0;
+}

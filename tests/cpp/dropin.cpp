@@ -362,6 +362,43 @@ static void distance_check(tracy_b200::Context& g) {
   expect(ok, "distanceMatrix", 0);
 }
 
+// The assemble glue on the B200 (revSeqBasedOnDist with grouped trials, msa = UPGMA + level-wise palign) against the reference's
+// functions (the host logic alone is also checked on the CPU: tests/cpp/hostlogic.cpp).
+struct AssembleCfg { tracy::DnaScore<int32_t> aliscore; float matchFraction; AssembleCfg() : aliscore(3, -5, -10, -4), matchFraction(0.5f) {} };
+static void assemble_check(tracy_b200::Context& g) {
+  for (int rep = 0; rep < 4; ++rep) {
+    const int N = 5 + 3 * rep;
+    const std::string contig = random_seq(60 * N + 300);
+    std::vector<TProfile> a(N);
+    for (int i = 0; i < N; ++i) {
+      std::string s = mutate(contig.substr(60 * i, 300), 0.02, 0.005);
+      if (i % 2) tracy::reverseComplement(s);
+      random_profile(s, a[i], false);
+    }
+    std::vector<TProfile> b(a);
+    std::vector<bool> f1(N, true), f2(N, true);
+    AssembleCfg c;
+    std::stringstream sink, dots;
+    std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+    tracy::revSeqBasedOnDist(c, a, f1);
+    std::cout.rdbuf(old);
+    tracy_b200::revSeqBasedOnDist(g, c, b, f2, &dots);
+    bool ok = f1 == f2 && sink.str() == dots.str();
+    for (int i = 0; ok && i < N; ++i)
+      for (int k = 0; ok && k < 6; ++k)
+        for (size_t j = 0; ok && j < a[i].shape()[1]; ++j) ok = a[i][k][j] == b[i][k][j];
+    expect(ok, "revSeqBasedOnDist", rep);
+    TAlign al1, al2;
+    std::vector<uint32_t> i1, i2;
+    tracy::msa(c, a, al1, i1);
+    tracy_b200::msa(g, c, a, al2, i2);
+    ok = i1 == i2 && al1.shape()[0] == al2.shape()[0] && al1.shape()[1] == al2.shape()[1];
+    for (size_t i = 0; ok && i < al1.shape()[0]; ++i)
+      for (size_t j = 0; ok && j < al1.shape()[1]; ++j) ok = al1[i][j] == al2[i][j];
+    expect(ok, "msa", rep);
+  }
+}
+
 int main() {
   try {
     tracy_b200::Context g(0);
@@ -377,6 +414,7 @@ int main() {
     anchor_check(g);
     driver_check(g);
     distance_check(g);
+    assemble_check(g);
     // batch form: the same pairs in one call
     {
       std::vector<TProfile> ps(8);

@@ -811,6 +811,28 @@ inline std::vector<bool> matchingTraces(TCtx& g, TConfig const& c, TSeqProfiles 
   return keep;
 }
 
+// assembleDenovo -- the DP sequence of the de novo branch of assemble(), reference src/assemble.h:419-468, from the trace
+// profiles on: orientation (revSeqBasedOnDist; inputProfiles and fwdProfiles are updated in place like there), exclusion of the
+// traces that match nothing (idxMap: the input index of every trace kept), msa of the rest. Returns -1 when fewer than two
+// traces remain (the reference's "At least 2 traces are required" exit), else 0; consensus calling on `align` is the
+// reference's own host function (src/msa.h:162-239). `excluded` (optional) receives the indices the reference warns about.
+template <typename TCtx, typename TConfig, typename TSeqProfiles, typename TAlign>
+inline int assembleDenovo(TCtx& g, TConfig const& c, TSeqProfiles& inputProfiles, std::vector<bool>& fwdProfiles, TAlign& align,
+                          std::vector<uint32_t>& seqidx, std::vector<uint32_t>& idxMap, std::vector<uint32_t>* excluded = nullptr,
+                          std::ostream* log = &std::cout) {
+  revSeqBasedOnDist(g, c, inputProfiles, fwdProfiles, log);
+  const std::vector<bool> keep = matchingTraces(g, c, inputProfiles);
+  TSeqProfiles seqProfiles;
+  idxMap.clear();
+  for (std::size_t i = 0; i < inputProfiles.size(); ++i) {
+    if (keep[i]) { seqProfiles.push_back(inputProfiles[i]); idxMap.push_back((uint32_t)i); }
+    else if (excluded) excluded->push_back((uint32_t)i);
+  }
+  if (idxMap.size() < 2) return -1;
+  msa(g, c, seqProfiles, align, seqidx);
+  return 0;
+}
+
 // ---- batch drivers: the DP sequence of sage() for many traces ---------------------------------------------------------
 // reverseComplement(std::string&), reference src/fmindex.h:11-26: reversed and upper-cased, A<->T, C<->G, N kept; any other
 // character leaves the ORIGINAL character of that slot in place (the reference's `default: break`).

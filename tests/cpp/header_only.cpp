@@ -32,5 +32,7 @@ int main() {
   s += (int)matchingTraces(g, ac2, traces).size();
   std::vector<uint32_t> seqidx;
   msa(g, ac2, traces, align, seqidx);
+  std::vector<uint32_t> idxmap;
+  s += assembleDenovo(g, ac2, traces, fwd, align, seqidx, idxmap);
   return s == 12345;
 }

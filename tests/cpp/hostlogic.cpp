@@ -170,6 +170,54 @@ int main() {
     if (got != want) { ++failures; std::printf("MISMATCH matchingTraces #%d (num=%d)\n", rep, num); }
     else std::printf("matchingTraces #%d: num=%d, %d kept, %ld batched calls for %ld pairs\n", rep, num, (int)std::count(got.begin(), got.end(), true), g.calls, g.pairs);
   }
+  // the whole de novo DP sequence: orientation -> exclusion -> msa, against the same sequence made of the reference's functions
+  for (int rep = 0; rep < 4; ++rep) {
+    const int num = 4 + (int)(rng() % 7), len = 140 + (int)(rng() % 60), step = 35 + (int)(rng() % 30);
+    std::string contig((std::size_t)(step * num + len), 'A');
+    for (auto& ch : contig) ch = "ACGT"[rng() % 4];
+    std::vector<TProfile> in((std::size_t)num);
+    for (int i = 0; i < num; ++i) {
+      std::string s = contig.substr((std::size_t)(step * i), (std::size_t)len);
+      if (rng() % 5 == 0) for (auto& ch : s) ch = "ACGT"[rng() % 4];
+      if (rng() % 2) { std::string r(s.rbegin(), s.rend()); for (auto& ch : r) ch = comp[ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3]; s = r; }
+      profile_of(s, in[(std::size_t)i], 0.93f);
+    }
+    Cfg c;
+    std::vector<TProfile> p_ref(in), p_new(in);
+    std::vector<bool> f_ref((std::size_t)num, true), f_new((std::size_t)num, true);
+    std::stringstream sink;
+    std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+    tracy::revSeqBasedOnDist(c, p_ref, f_ref);
+    std::cout.rdbuf(old);
+    std::vector<TProfile> kept;
+    std::vector<uint32_t> map_ref;
+    for (int i = 0; i < num; ++i) {
+      bool hit = false;
+      for (int j = 0; j < num && !hit; ++j) {
+        if (i == j) continue;
+        tracy::AlignConfig<true, true> ac;
+        boost::multi_array<char, 2> al;
+        const int32_t gs = tracy::gotoh(p_ref[(std::size_t)i], p_ref[(std::size_t)j], al, ac, c.aliscore);
+        int32_t na = 0;
+        for (std::size_t k = 0; k < al.shape()[1]; ++k) if (al[0][k] != '-' && al[1][k] != '-') ++na;
+        const double thr = na * c.matchFraction * c.aliscore.match + na * (1 - c.matchFraction) * c.aliscore.mismatch;
+        hit = (double)na / (double)(int32_t)p_ref[(std::size_t)i].shape()[1] > 0.1 && na > 25 && gs > thr;
+      }
+      if (hit) { kept.push_back(p_ref[(std::size_t)i]); map_ref.push_back((uint32_t)i); }
+    }
+    boost::multi_array<char, 2> al_ref, al_new;
+    std::vector<uint32_t> idx_ref, idx_new, map_new;
+    const int rc_ref = map_ref.size() < 2 ? -1 : 0;
+    if (rc_ref == 0) tracy::msa(c, kept, al_ref, idx_ref);
+    cpu_double::Ctx g;
+    const int rc_new = tracy_b200::assembleDenovo(g, c, p_new, f_new, al_new, idx_new, map_new, nullptr, nullptr);
+    ++checks;
+    bool ok = rc_ref == rc_new && f_ref == f_new && map_ref == map_new && idx_ref == idx_new && al_ref.shape()[0] == al_new.shape()[0] && al_ref.shape()[1] == al_new.shape()[1];
+    for (std::size_t i = 0; ok && i < al_ref.shape()[0]; ++i)
+      for (std::size_t j = 0; ok && j < al_ref.shape()[1]; ++j) ok = al_ref[i][j] == al_new[i][j];
+    if (!ok) { ++failures; std::printf("MISMATCH assembleDenovo #%d (num=%d)\n", rep, num); }
+    else std::printf("assembleDenovo #%d: num=%d, %zu kept, %zu x %zu alignment\n", rep, num, map_new.size(), (std::size_t)al_new.shape()[0], (std::size_t)al_new.shape()[1]);
+  }
   std::printf("%d checks, %d mismatches\n", checks, failures);
   return failures ? 1 : 0;
 }

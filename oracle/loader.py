@@ -218,6 +218,24 @@ class _Ref:
         os.remove(p)
         return out
 
+    def trace_outputs(self, what, acgt, bcpos, qual, primary, secondary, consensus, trim_left=0, trim_right=0, row0=b"", row1=b"", chr_name=b"", pos=0, forward=True):
+        """what = "txt": traceTxtOut (src/abif.h:512-534); "json": traceJsonOut (src/json.h:108-117); "align_json":
+        alignmentTracePadding + traceAlignJsonOut (src/json.h:383-479, 197-217). Returns the bytes the reference writes."""
+        import tempfile
+        p = tempfile.mktemp()
+        acgt = np.ascontiguousarray(acgt, np.int32)
+        bcpos = np.ascontiguousarray(bcpos, np.int32)
+        qual = np.ascontiguousarray(qual, np.uint8)
+        self.lib.ref_trace_outputs.argtypes = [C.c_char_p, C.c_int, _i32p, C.c_int, _i32p, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_char_p, C.c_char_p,
+                                               C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_uint, C.c_int]
+        self.lib.ref_trace_outputs.restype = None
+        self.lib.ref_trace_outputs(os.fsencode(p), {"txt": 0, "json": 1, "align_json": 2}[what], acgt.reshape(-1), acgt.shape[1], bcpos, qual, bytes(primary),
+                                   bytes(secondary), bytes(consensus), len(bcpos), trim_left, trim_right, bytes(row0), bytes(row1), len(row0), bytes(chr_name),
+                                   pos, int(forward))
+        out = open(p, "rb").read()
+        os.remove(p)
+        return out
+
     def write_decomposition(self, pairs):
         import tempfile
         p = tempfile.mktemp()

@@ -31,6 +31,7 @@
 #include "profile.h"   // createProfile, reverseComplementProfile         (reference, unmodified)
 #include "decompose.h" // findBreakpoint, decomposeAlleles, ...           (reference, unmodified)
 #include "msa.h"       // distanceMatrix, upgma, palign, consensus, revSeqBasedOnDist, msa (reference, unmodified)
+#include "json.h"      // traceJsonOut, alignmentTracePadding, traceAlignJsonOut (reference, unmodified; variants.h / htslib only declared)
 
 namespace {
 typedef boost::multi_array<float, 2> TProfile;
@@ -368,6 +369,32 @@ void ref_write_decomposition(const char* path, const int32_t* pairs, int n) {
   std::vector<std::pair<int32_t, int32_t> > dcp;
   for (int i = 0; i < n; ++i) dcp.push_back(std::make_pair(pairs[2 * i], pairs[2 * i + 1]));
   tracy::writeDecomposition(path, dcp);
+}
+
+// The per-trace text outputs into the given path: what = 0 traceTxtOut (src/abif.h:512-534, P.abif of align / decompose),
+// 1 traceJsonOut (src/json.h:108-117, the basecall subcommand's JSON), 2 alignmentTracePadding + traceAlignJsonOut
+// (src/json.h:383-479, 197-217: P.json of `tracy align`, src/sage.h:319-343).
+void ref_trace_outputs(const char* path, int what, const int32_t* acgt, int nsamples, const int32_t* bcpos, const uint8_t* qual, const char* pri,
+                       const char* sec, const char* cons, int nbc, int trimLeft, int trimRight, const char* row0, const char* row1, int L,
+                       const char* chr, unsigned pos, int forward) {
+  tracy::Trace tr;
+  tr.traceACGT.resize(4);
+  for (int k = 0; k < 4; ++k) tr.traceACGT[k].assign(acgt + (size_t)k * nsamples, acgt + (size_t)(k + 1) * nsamples);
+  tracy::BaseCalls bc;
+  bc.bcPos.assign(bcpos, bcpos + nbc);
+  bc.estQual.assign(qual, qual + nbc);
+  bc.primary = std::string(pri, pri + nbc);
+  bc.secondary = std::string(sec, sec + nbc);
+  bc.consensus = std::string(cons, cons + nbc);
+  if (what == 0) { tracy::traceTxtOut(path, bc, tr, (uint32_t)trimLeft, (uint32_t)trimRight); return; }
+  if (what == 1) { tracy::traceJsonOut(path, bc, tr); return; }
+  TAlign al(boost::extents[2][L]);
+  for (int j = 0; j < L; ++j) { al[0][j] = row0[j]; al[1][j] = row1[j]; }
+  tracy::ReferenceSlice rs; rs.forward = forward != 0; rs.pos = pos; rs.chr = chr;
+  tracy::BaseCalls nbc_;
+  tracy::Trace ntr;
+  tracy::alignmentTracePadding(al, tr, bc, ntr, nbc_);
+  tracy::traceAlignJsonOut(path, nbc_, ntr, rs, al);
 }
 
 // allelicFraction(c, tr, bc), src/decompose.h:412-617

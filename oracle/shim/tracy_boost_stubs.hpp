@@ -31,8 +31,12 @@ inline bool is_regular_file(const path& p) { return exists(p); }
 inline std::size_t file_size(const path&) { return 0; }
 inline bool remove(const path& p) { return ::remove(p.string().c_str()) == 0; }
 }  // namespace filesystem
+namespace gregorian {
+struct date {};
+inline std::string to_iso_string(const date&) { return "00000000"; }
+}  // namespace gregorian
 namespace posix_time {
-struct ptime {};
+struct ptime { gregorian::date date() const { return gregorian::date(); } };
 struct second_clock { static ptime local_time() { return ptime(); } };
 inline std::string to_simple_string(const ptime&) { return "0000-00-00 00:00:00"; }
 }  // namespace posix_time

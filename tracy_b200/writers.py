@@ -4,8 +4,16 @@ the batch drivers return, byte-identical to the reference's writers.
   align_fasta          P.align.fa   reference src/sage.h:326-339
   plot_alignment       P.txt, P.align1/.align2/.align3   reference src/fmindex.h:329-427 (plotAlignment)
   write_decomposition  P.decomp     reference src/decompose.h:621-627
-The JSON / BCF writers (src/json.h, src/variants.h) are not covered.
+  trace_txt            P.abif       reference src/abif.h:512-534 (traceTxtOut: the tab-separated trace table of align / decompose)
+  trace_json           basecall JSON   reference src/json.h:32-117 (traceJsonOut)
+  alignment_trace_padding, trace_align_json   P.json of `tracy align`   reference src/json.h:383-479, 120-217, src/sage.h:319-343
+The decompose JSON (traceAlleleAlignJsonOut, needs the variant records) and the BCF writer (src/variants.h) are not covered.
 """
+import numpy as np
+
+EMPTY_TRACE_SIGNAL = -99          # reference src/json.h:12-14
+
+_IUPAC_EXPANDED = {"A": "A", "C": "C", "G": "G", "T": "T", "N": "N", "R": "A|G", "Y": "C|T", "S": "C|G", "W": "A|T", "K": "G|T", "M": "A|C"}
 
 
 def _g(x):
@@ -74,3 +82,140 @@ def plot_alignment(row0, row1, chr_name, pos, refslice_len, forward, score, key=
 def write_decomposition(decomp):
     """writeDecomposition(path, dcp), reference src/decompose.h:621-627: `indel<TAB>decomp` rows."""
     return "indel\tdecomp\n" + "".join("%d\t%d\n" % (int(a), int(b)) for a, b in decomp)
+
+
+# ---- per-trace outputs ---------------------------------------------------------------------------------------------------
+def _called(nsamples, bcpos):
+    """The walk all of the reference's per-sample writers share: sample i carries basecall k when it equals the NEXT expected
+    basecall position; the expectation only moves forward (a position that is not larger than its predecessor is never met)."""
+    if len(bcpos) == 0:
+        raise ValueError("the reference reads bcPos[0] unconditionally: at least one basecall is required")
+    k, idx = 0, int(bcpos[0])
+    for i in range(nsamples):
+        if idx == i:
+            yield i, k
+            if k < len(bcpos) - 1:
+                k += 1
+                idx = int(bcpos[k])
+
+
+def _s(x):
+    return bytes(x).decode("latin-1") if not isinstance(x, str) else x
+
+
+def _peaks(acgt):
+    return "".join('"peak%s": [%s],\n' % ("ACGT"[k], ", ".join(str(int(v)) for v in acgt[k])) for k in range(4))
+
+
+def trace_txt(acgt, bcpos, qual, primary, secondary, consensus, trim_left, trim_right):
+    """traceTxtOut (reference src/abif.h:512-534): one row per trace sample; samples that carry a basecall show its number,
+    the three calls, the quality and whether the call lies in the trimmed ends."""
+    acgt = np.asarray(acgt)
+    pri, sec, con = _s(primary), _s(secondary), _s(consensus)
+    rtr = len(pri) - trim_right if trim_right < len(pri) else 0
+    hit = dict(_called(acgt.shape[1], bcpos))
+    out = ["pos\tpeakA\tpeakC\tpeakG\tpeakT\tbasenum\tprimary\tsecondary\tconsensus\tqual\ttrim\n"]
+    for i in range(acgt.shape[1]):
+        row = "%d\t%d\t%d\t%d\t%d\t" % (i + 1, acgt[0][i], acgt[1][i], acgt[2][i], acgt[3][i])
+        if i in hit:
+            k = hit[i]
+            row += "%d\t%s\t%s\t%s\t%d\t%s\n" % (k + 1, pri[k], sec[k], con[k], int(qual[k]), "Y" if (k < trim_left or k >= rtr) else "N")
+        else:
+            row += "NA\tNA\tNA\tNA\tNA\tNA\n"
+        out.append(row)
+    return "".join(out)
+
+
+def trace_json(acgt, bcpos, qual, primary, secondary):
+    """traceJsonOut (reference src/json.h:32-117)."""
+    acgt = np.asarray(acgt)
+    pri, sec = _s(primary), _s(secondary)
+    calls = list(_called(acgt.shape[1], bcpos))
+    out = ["{\n", '"pos": [%s],\n' % ", ".join(str(i + 1) for i in range(acgt.shape[1])), _peaks(acgt)]
+    out.append('"basecallPos": [%s],\n' % ", ".join(str(i + 1) for i, _ in calls))
+    out.append('"basecallQual": [%s],\n' % ", ".join(str(int(qual[k])) for _, k in calls))
+    items = []
+    for i, k in calls:
+        v = "%d:%s" % (k + 1, pri[k])
+        if pri[k] != sec[k]:
+            v += "|" + _IUPAC_EXPANDED.get(sec[k], "N")
+        items.append('"%d":"%s"' % (i + 1, v))
+    out.append('"basecalls": {%s},\n' % ", ".join(items))
+    out.append('"primarySeq": "%s",\n"secondarySeq": "%s"\n\n}\n' % (pri, sec))
+    return "".join(out)
+
+
+def alignment_trace_padding(row, acgt, bcpos, qual, primary, secondary, consensus):
+    """alignmentTracePadding (reference src/json.h:383-479): every gap run of the trace's alignment row becomes `step` empty
+    samples per gap column, inserted half-way between the two basecalls around it, with a '-' basecall in their middle
+    (step = the truncated mean basecall distance, 6 for a single basecall); runs before the first / after the last base only
+    count as leading / trailing gaps. Returns dict(acgt, bcpos, qual, primary, secondary, consensus, leading, trailing)."""
+    acgt = np.asarray(acgt)
+    bcpos = [int(x) for x in bcpos]
+    pri, sec, con = _s(primary), _s(secondary), _s(consensus)
+    step = 6
+    if len(bcpos) > 1:
+        step = int(float(sum(bcpos[i] - bcpos[i - 1] for i in range(1, len(bcpos)))) / (len(bcpos) - 1))
+    ins_pos, ins_size, pos, gapsize, ingap, leading = [], [], 0, 0, False, 0
+    for ch in _s(row):
+        if ch == "-":
+            gapsize = gapsize + 1 if ingap else 1
+            ingap = True
+        else:
+            if ingap:
+                ingap = False
+                if pos:
+                    ins_pos.append(int((bcpos[pos - 1] + bcpos[pos]) / 2.0))
+                    ins_size.append(gapsize)
+                else:
+                    leading = gapsize
+            pos += 1
+    trailing = gapsize if ingap else 0
+    cols, nbp, nq, npri, nsec, ncon = [], [], [], [], [], []
+    k, idx = 0, bcpos[0]
+    offset, q, ins_idx = 0, 0, (ins_pos[0] if ins_pos else -1)
+    empty = (EMPTY_TRACE_SIGNAL,) * 4
+    for t in range(acgt.shape[1]):
+        cols.append((int(acgt[0][t]), int(acgt[1][t]), int(acgt[2][t]), int(acgt[3][t])))
+        if ins_idx == t:
+            for _ in range(ins_size[q]):
+                nbp.append(t + offset + int(step / 2.0)); nq.append(0); npri.append("-"); nsec.append("-"); ncon.append("-")
+                cols.extend([empty] * step)
+                offset += step
+            if q < len(ins_pos) - 1:
+                q += 1
+                ins_idx = ins_pos[q]
+        if idx == t:
+            nbp.append(idx + offset); nq.append(int(qual[k])); npri.append(pri[k]); nsec.append(sec[k]); ncon.append(con[k])
+            if k < len(bcpos) - 1:
+                k += 1
+                idx = bcpos[k]
+    return dict(acgt=np.array(cols, np.int32).T.reshape(4, -1), bcpos=np.array(nbp, np.int32), qual=np.array(nq, np.uint8), primary="".join(npri),
+                secondary="".join(nsec), consensus="".join(ncon), leading=leading, trailing=trailing)
+
+
+def assembly_trace(padded, trace_file_name="trace"):
+    """assemblyTrace (reference src/json.h:120-195): the JSON object of one gapped trace."""
+    acgt, pri, sec = padded["acgt"], padded["primary"], padded["secondary"]
+    calls = list(_called(acgt.shape[1], padded["bcpos"]))
+    out = ['{\n"traceFileName": "%s",\n"leadingGaps": %d,\n"trailingGaps": %d,\n' % (trace_file_name, padded["leading"], padded["trailing"]), _peaks(acgt)]
+    out.append('"basecallPos": [%s],\n' % ", ".join(str(i + 1) for i, _ in calls))
+    out.append('"basecallQual": [%s],\n' % ", ".join(str(int(padded["qual"][k])) for _, k in calls))
+    items, gapless = [], 0
+    for i, k in calls:
+        if pri[k] != "-":
+            gapless += 1
+            v = "%d:%s" % (gapless, pri[k]) + ("|" + sec[k] if pri[k] != sec[k] else "")
+        else:
+            v = "-"
+        items.append('"%d":"%s"' % (i + 1, v))
+    out.append('"basecalls": {%s}\n}\n' % ", ".join(items))
+    return "".join(out)
+
+
+def trace_align_json(acgt, bcpos, qual, primary, secondary, consensus, row0, row1, chr_name, pos, forward):
+    """P.json of `tracy align` (reference src/sage.h:319-343): the trace padded along alignment row 0, then traceAlignJsonOut
+    (src/json.h:197-217)."""
+    padded = alignment_trace_padding(row0, acgt, bcpos, qual, primary, secondary, consensus)
+    return ('{\n"gappedTrace":\n' + assembly_trace(padded) + ',\n"refchr": "%s",\n"refpos": %d,\n"altalign": "%s",\n"refalign": "%s",\n"forward": %d\n}\n'
+            % (_s(chr_name), pos + 1, _s(row0), _s(row1), 1 if forward else 0))

@@ -236,6 +236,25 @@ class _Ref:
         os.remove(p)
         return out
 
+    def call_variants(self, alignments):
+        """callVariants (src/variants.h:56-126) over a sequence of (row0, row1, chr, pos) into ONE variant vector, as indigo() calls
+        it for both alleles. Returns the list of (pos, basenum, gt, chr, ref, alt, type) the reference ends up with."""
+        L = self.lib
+        L.ref_call_variants.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_uint]
+        L.ref_variants_dump.argtypes = [C.c_char_p, C.c_int]
+        L.ref_variants_dump.restype = C.c_int
+        L.ref_variants_reset()
+        for row0, row1, chr_name, pos in alignments:
+            L.ref_call_variants(bytes(row0), bytes(row1), len(row0), bytes(chr_name), pos)
+        buf = C.create_string_buffer(1 << 20)
+        n = L.ref_variants_dump(buf, len(buf))
+        assert n >= 0
+        out = []
+        for line in buf.raw[:n].decode("latin-1").splitlines():
+            p, b, g, c, r, a, t = line.split("\t")
+            out.append((int(p), int(b), int(g), c, r, a, t))
+        return out
+
     def write_decomposition(self, pairs):
         import tempfile
         p = tempfile.mktemp()

@@ -397,6 +397,26 @@ void ref_trace_outputs(const char* path, int what, const int32_t* acgt, int nsam
   tracy::traceAlignJsonOut(path, nbc_, ntr, rs, al);
 }
 
+// callVariants(align, rs, var), src/variants.h:56-126 (with insertVariant :34-53): the calls accumulate in one vector across
+// calls, as indigo() does for the two alleles (src/indigo.h:405-422); dump = one "pos basenum gt chr ref alt type" line per variant.
+static std::vector<tracy::Variant> g_variants;
+void ref_variants_reset() { g_variants.clear(); }
+void ref_call_variants(const char* row0, const char* row1, int L, const char* chr, unsigned pos) {
+  TAlign al(boost::extents[2][L]);
+  for (int j = 0; j < L; ++j) { al[0][j] = row0[j]; al[1][j] = row1[j]; }
+  tracy::ReferenceSlice rs; rs.pos = pos; rs.chr = chr;
+  tracy::callVariants(al, rs, g_variants);
+}
+int ref_variants_dump(char* out, int cap) {
+  std::ostringstream o;
+  for (auto const& v : g_variants)
+    o << v.pos << '\t' << v.basenum << '\t' << v.gt << '\t' << v.chr << '\t' << v.ref << '\t' << v.alt << '\t' << tracy::variantType(v.ref, v.alt) << '\n';
+  const std::string t = o.str();
+  if ((int)t.size() + 1 > cap) return -(int)t.size();
+  std::memcpy(out, t.c_str(), t.size() + 1);
+  return (int)t.size();
+}
+
 // allelicFraction(c, tr, bc), src/decompose.h:412-617
 void ref_allelic_fraction(const int32_t* acgt, int nsamples, const int32_t* bcpos, const char* primary, const char* secdecompose, int nbc,
                           int trimLeft, int trimRight, double* a1, double* a2) {

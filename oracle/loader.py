@@ -255,6 +255,34 @@ class _Ref:
             out.append((int(p), int(b), int(g), c, r, a, t))
         return out
 
+    def decompose_json(self, cfg, acgt, bcpos, qual, primary, secondary, alignments, allele1, allele2, align3, decomp, indelshift, breakpoint, a1a2, sort=True):
+        """traceAlleleAlignJsonOut (src/json.h:260-381) -> the bytes of P.json. alignments: the (row0, row1, chr, pos) sequence whose
+        callVariants calls make the variant vector; allele1/allele2: (row0, row1, chr, pos, forward, score); align3: (row0, row1, score)."""
+        import tempfile
+        L = self.lib
+        L.ref_call_variants.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_uint]
+        L.ref_variants_reset()
+        for row0, row1, chr_name, pos in alignments:
+            L.ref_call_variants(bytes(row0), bytes(row1), len(row0), bytes(chr_name), pos)
+        prefix = tempfile.mktemp()
+        acgt = np.ascontiguousarray(acgt, np.int32)
+        bcpos = np.ascontiguousarray(bcpos, np.int32)
+        qual = np.ascontiguousarray(qual, np.uint8)
+        d = np.ascontiguousarray(decomp, np.int32).reshape(-1)
+        u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        al = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_uint, C.c_int, C.c_int]
+        L.ref_decompose_json.argtypes = ([C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_char_p, _i32p, C.c_int, _i32p, u8, C.c_char_p, C.c_char_p, C.c_int]
+                                         + al + al + [C.c_char_p, C.c_char_p, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, C.c_uint, C.c_double, C.c_double, C.c_int])
+        L.ref_decompose_json.restype = None
+        a1 = [bytes(allele1[0]), bytes(allele1[1]), len(allele1[0]), bytes(allele1[2]), allele1[3], int(allele1[4]), allele1[5]]
+        a2 = [bytes(allele2[0]), bytes(allele2[1]), len(allele2[0]), bytes(allele2[2]), allele2[3], int(allele2[4]), allele2[5]]
+        L.ref_decompose_json(os.fsencode(prefix), cfg["trim_left"], cfg["trim_right"], cfg["qual_cut"], cfg["pratio"], os.fsencode(cfg["input"]), os.fsencode(cfg["genome"]),
+                             acgt.reshape(-1), acgt.shape[1], bcpos, qual, bytes(primary), bytes(secondary), len(bcpos), *a1, *a2,
+                             bytes(align3[0]), bytes(align3[1]), len(align3[0]), align3[2], d, len(d) // 2, int(indelshift), breakpoint, float(a1a2[0]), float(a1a2[1]), int(sort))
+        out = open(prefix + ".json", "rb").read()
+        os.remove(prefix + ".json")
+        return out
+
     def write_decomposition(self, pairs):
         import tempfile
         p = tempfile.mktemp()

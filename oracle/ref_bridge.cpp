@@ -417,6 +417,45 @@ int ref_variants_dump(char* out, int cap) {
   return (int)t.size();
 }
 
+// traceAlleleAlignJsonOut (src/json.h:260-381): P.json of `tracy decompose`, over the variant vector the ref_call_variants calls left
+// behind (sorted first when `sorted` is set, as indigo() does before the output, src/indigo.h:443). The config is the slice of
+// IndigoConfig (src/indigo.h:18-40) the writer reads, with its field types.
+struct JsonCfg {
+  uint16_t trimLeft, trimRight, qualCut;
+  float pratio;
+  std::string outprefix;
+  boost::filesystem::path ab, genome;
+};
+void ref_decompose_json(const char* outprefix, int trimLeft, int trimRight, int qualCut, float pratio, const char* ab, const char* genome,
+                        const int32_t* acgt, int nsamples, const int32_t* bcpos, const uint8_t* qual, const char* pri, const char* sec, int nbc,
+                        const char* a1r0, const char* a1r1, int L1, const char* chr1, unsigned pos1, int fwd1, int score1,
+                        const char* a2r0, const char* a2r1, int L2, const char* chr2, unsigned pos2, int fwd2, int score2,
+                        const char* a3r0, const char* a3r1, int L3, int score3, const int32_t* dcp, int ndcp, int indelshift, unsigned breakpoint,
+                        double f1, double f2, int sorted) {
+  JsonCfg c;
+  c.trimLeft = (uint16_t)trimLeft; c.trimRight = (uint16_t)trimRight; c.qualCut = (uint16_t)qualCut; c.pratio = pratio;
+  c.outprefix = outprefix; c.ab = boost::filesystem::path(ab); c.genome = boost::filesystem::path(genome);
+  tracy::Trace tr;
+  tr.traceACGT.resize(4);
+  for (int k = 0; k < 4; ++k) tr.traceACGT[k].assign(acgt + (size_t)k * nsamples, acgt + (size_t)(k + 1) * nsamples);
+  tracy::BaseCalls bc;
+  bc.bcPos.assign(bcpos, bcpos + nbc);
+  bc.estQual.assign(qual, qual + nbc);
+  bc.primary = std::string(pri, pri + nbc);
+  bc.secondary = std::string(sec, sec + nbc);
+  auto mk = [](const char* r0, const char* r1, int L) { TAlign al(boost::extents[2][L]); for (int j = 0; j < L; ++j) { al[0][j] = r0[j]; al[1][j] = r1[j]; } return al; };
+  TAlign al1 = mk(a1r0, a1r1, L1), al2 = mk(a2r0, a2r1, L2), al3 = mk(a3r0, a3r1, L3);
+  tracy::ReferenceSlice rs1, rs2, rs3;
+  rs1.chr = chr1; rs1.pos = pos1; rs1.forward = fwd1 != 0;
+  rs2.chr = chr2; rs2.pos = pos2; rs2.forward = fwd2 != 0;
+  std::vector<std::pair<int32_t, int32_t> > d;
+  for (int i = 0; i < ndcp; ++i) d.push_back(std::make_pair(dcp[2 * i], dcp[2 * i + 1]));
+  tracy::TraceBreakpoint bp; bp.indelshift = indelshift != 0; bp.traceleft = true; bp.breakpoint = breakpoint; bp.bestDiff = 0;
+  std::vector<tracy::Variant> var(g_variants);
+  if (sorted) std::sort(var.begin(), var.end());
+  tracy::traceAlleleAlignJsonOut(c, bc, tr, var, rs1, rs2, rs3, al1, al2, al3, d, score1, score2, score3, bp, std::make_pair(f1, f2));
+}
+
 // allelicFraction(c, tr, bc), src/decompose.h:412-617
 void ref_allelic_fraction(const int32_t* acgt, int nsamples, const int32_t* bcpos, const char* primary, const char* secdecompose, int nbc,
                           int trimLeft, int trimRight, double* a1, double* a2) {

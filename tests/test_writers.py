@@ -60,3 +60,52 @@ def test_trace_writers_differential(oracle_ref):
     mod, cs = _trace_writer_cases(5, 150, 500)
     for i, c in enumerate(cs):
         assert _mine(c) == mod.reference_outputs(oracle_ref, c), i
+
+
+def _decompose_json_cases(seed, n):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_decompose_json", os.path.join(ROOT, "tests", "golden", "make_golden_decompose_json.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, mod.cases(seed, n)
+
+
+def _my_decompose_json(c):
+    from tracy_b200 import variants
+    var = []
+    for r0, r1, ch, p in c["als"]:
+        variants.call_variants(r0, r1, ch, p, var)
+    var = writers.sort_variants(var)
+    keys = [(v["chr"], v["pos"], v["basenum"]) for v in var]
+    unique = len(set(keys)) == len(keys)          # std::sort leaves the order of records with equal keys open
+    doc = writers.decompose_json(c["cfg"], c["acgt"], c["bcpos"], c["qual"], c["pri"], c["sec"], var, c["allele1"], c["allele2"], c["align3"], c["decomp"],
+                                 c["indelshift"], c["breakpoint"], c["a1a2"]).encode("latin-1")
+    return doc, unique
+
+
+def test_decompose_json_matches_reference_goldens():
+    """P.json of `tracy decompose` (traceAlleleAlignJsonOut over callVariants + sort) byte for byte against documents written by
+    the reference (tests/golden/make_golden_decompose_json.py); every document also parses as JSON."""
+    import json
+    G = np.load(os.path.join(ROOT, "tests", "golden", "decompose_json_golden.npz"))
+    _, cs = _decompose_json_cases(21, int(G["n"]))
+    for i, c in enumerate(cs):
+        doc, unique = _my_decompose_json(c)
+        if unique:
+            assert doc == bytes(G[f"json{i}"]), i
+        parsed = json.loads(doc)
+        assert parsed["meta"]["program"] == "tracy" and len(parsed["variants"]["rows"]) == len(parsed["variants"]["xranges"])
+
+
+def test_decompose_json_differential(oracle_ref):
+    import pytest
+    if oracle_ref is None:
+        pytest.skip("reference build not present")
+    mod, cs = _decompose_json_cases(8, 80)
+    compared = 0
+    for i, c in enumerate(cs):
+        doc, unique = _my_decompose_json(c)
+        if unique:
+            assert doc == mod.reference_json(oracle_ref, c), i
+            compared += 1
+    assert compared > 40

@@ -7,7 +7,8 @@ the batch drivers return, byte-identical to the reference's writers.
   trace_txt            P.abif       reference src/abif.h:512-534 (traceTxtOut: the tab-separated trace table of align / decompose)
   trace_json           basecall JSON   reference src/json.h:32-117 (traceJsonOut)
   alignment_trace_padding, trace_align_json   P.json of `tracy align`   reference src/json.h:383-479, 120-217, src/sage.h:319-343
-The decompose JSON (traceAlleleAlignJsonOut, needs the variant records) and the BCF writer (src/variants.h) are not covered.
+  decompose_json       P.json of `tracy decompose`   reference src/json.h:16-30, 249-381 (traceAlleleAlignJsonOut)
+The BCF writer (src/variants.h:141-266, htslib) is not covered.
 """
 import numpy as np
 
@@ -219,3 +220,56 @@ def trace_align_json(acgt, bcpos, qual, primary, secondary, consensus, row0, row
     padded = alignment_trace_padding(row0, acgt, bcpos, qual, primary, secondary, consensus)
     return ('{\n"gappedTrace":\n' + assembly_trace(padded) + ',\n"refchr": "%s",\n"refpos": %d,\n"altalign": "%s",\n"refalign": "%s",\n"forward": %d\n}\n'
             % (_s(chr_name), pos + 1, _s(row0), _s(row1), 1 if forward else 0))
+
+
+# ---- P.json of `tracy decompose` ------------------------------------------------------------------------------------------
+TRACY_VERSION = "0.9.1"           # reference src/version.h:8 (the writer prints it into the meta block)
+
+
+def x_window_viewport(bcpos, k):
+    """xWindowViewport (reference src/json.h:249-258): the sample range shown around basecall k, 150 samples either side,
+    clipped to the first sample and the last basecall."""
+    lb = int(bcpos[k]) + 1
+    lb = 1 if lb <= 150 else lb - 150
+    ub = int(bcpos[k]) + 1
+    ub = ub + 150 if ub + 150 < int(bcpos[-1]) else int(bcpos[-1])
+    return lb, ub
+
+
+def sort_variants(var):
+    """std::sort over Variant::operator< (reference src/variants.h:20-22): by chromosome, position, base number."""
+    return sorted(var, key=lambda v: (v["chr"], v["pos"], v["basenum"]))
+
+
+def decompose_json(cfg, acgt, bcpos, qual, primary, secondary, var, allele1, allele2, align3, decomp, indelshift, breakpoint, a1a2):
+    """traceAlleleAlignJsonOut (reference src/json.h:260-381). cfg: dict(trim_left, trim_right, qual_cut, pratio, input, genome);
+    var: variant records (tracy_b200.variants) in output order; allele1 / allele2: (row0, row1, chr, pos, forward, score);
+    align3: (allele1 row, allele2 row, score); decomp: (indel, count) pairs; a1a2: the allelic fractions."""
+    from .variants import variant_type
+    pri = _s(primary)
+    tl, tr = int(cfg["trim_left"]), int(cfg["trim_right"])
+    out = ['{\n"meta": {"program": "tracy", "version": "%s", "arguments": {"trimLeft": %d, "trimRight": %d, "pratio": %s, "genome": "%s", "input": "%s"}},\n'
+           % (TRACY_VERSION, tl, tr, _g(float(np.float32(cfg["pratio"]))), str(cfg["genome"]).rsplit("/", 1)[-1], str(cfg["input"]).rsplit("/", 1)[-1])]
+    out.append(trace_json(acgt, bcpos, qual, primary, secondary)[2:-3])       # the body between "{\n" and "\n}\n"
+    out.append(",\n")
+    out.append('"chartConfig": { "x": { "axis": { "range": [%d, %d] }}},\n' % x_window_viewport(bcpos, tl + int(breakpoint)))
+    for n, (r0, r1, chr_name, pos, fwd, score) in ((1, allele1), (2, allele2)):
+        out.append('"ref%dchr": "%s",\n"ref%dpos": %d,\n"alt%dalign": "%s",\n"ref%dalign": "%s",\n"ref%dforward": %d,\n"align%dscore": %d,\n'
+                   % (n, _s(chr_name), n, pos + 1, n, _s(r0), n, _s(r1), n, 1 if fwd else 0, n, score))
+    out.append('"allele1fraction": %s,\n"allele1align": "%s",\n"allele2fraction": %s,\n"allele2align": "%s",\n"align3score": %d,\n'
+               % (_g(a1a2[0]), _s(align3[0]), _g(a1a2[1]), _s(align3[1]), align3[2]))
+    out.append('"hetindel": %d,\n' % (1 if indelshift else 0))
+    out.append('"decomposition": {\n"x": [%s],\n"y": [%s]\n},\n' % (", ".join(str(int(a)) for a, _ in decomp), ", ".join(str(int(b)) for _, b in decomp)))
+    out.append('"variants": {\n"columns": ["chr", "pos", "id", "ref", "alt", "qual", "filter", "type", "genotype", "basepos", "signalpos"],\n"rows": [\n')
+    fwd1 = bool(allele1[4])
+    rows, ranges = [], []
+    for v in var:
+        k = tl + v["basenum"] - 1 if fwd1 else len(pri) - (tr + v["basenum"])          # the basecall the variant sits on
+        q = int(qual[k])
+        gt = {0: "hom. REF", 1: "het.", 2: "hom. ALT"}.get(v["gt"], "missing")
+        rows.append('["%s", %d, "%s", "%s", "%s", %d, "%s", "%s", "%s", %d, %d]'
+                    % (v["chr"], v["pos"], v["id"], v["ref"], v["alt"], q, "LowQual" if q < int(cfg["qual_cut"]) else "PASS", variant_type(v["ref"], v["alt"]), gt,
+                       k + 1, int(bcpos[k]) + 1))
+        ranges.append("[%d, %d]" % x_window_viewport(bcpos, k))
+    out.append(",\n".join(rows) + '],\n"xranges": [\n' + ",\n".join(ranges) + "]\n}\n}\n")
+    return "".join(out)

@@ -283,6 +283,35 @@ class _Ref:
         os.remove(prefix + ".json")
         return out
 
+    def estimate_qualities(self, bcpos, primary, secondary):
+        """estimateQualities + findBestTraceSection(bc) (src/abif.h:164-253) -> (estQual uint8[n], best section index)."""
+        n = len(bcpos)
+        u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        self.lib.ref_estimate_qualities.argtypes = [_i32p, C.c_char_p, C.c_char_p, C.c_int, u8, C.POINTER(C.c_uint32)]
+        q = np.zeros(max(n, 1), np.uint8)
+        best = C.c_uint32(0)
+        self.lib.ref_estimate_qualities(np.ascontiguousarray(bcpos, np.int32), bytes(primary), bytes(secondary), n, q, C.byref(best))
+        return q[:n], int(best.value)
+
+    def trim_trace(self, bcpos, secondary, stringency):
+        """trimTrace(c, bc, leftTrim, rightTrim) (src/trim.h:35-73) -> (left, right)."""
+        self.lib.ref_trim_trace.argtypes = [_i32p, C.c_char_p, C.c_int, C.c_float, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        le, ri = C.c_uint32(0), C.c_uint32(0)
+        self.lib.ref_trim_trace(np.ascontiguousarray(bcpos, np.int32), bytes(secondary), len(bcpos), float(stringency), C.byref(le), C.byref(ri))
+        return int(le.value), int(ri.value)
+
+    def trim_basecalls(self, nsamples, bcpos, qual, primary, secondary, consensus, trim_left, trim_right):
+        """trimTrace(tr, bc, trimLeft, trimRight, nbc) (src/trim.h:76-99) -> (bcpos, qual, primary, secondary, consensus)."""
+        n = len(bcpos)
+        u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        self.lib.ref_trim_basecalls.argtypes = [C.c_int, _i32p, u8, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint, C.c_uint, _i32p, u8, C.c_char_p, C.c_char_p, C.c_char_p]
+        self.lib.ref_trim_basecalls.restype = C.c_int
+        ob, oq = np.zeros(n, np.int32), np.zeros(n, np.uint8)
+        op, os_, oc = C.create_string_buffer(n + 1), C.create_string_buffer(n + 1), C.create_string_buffer(n + 1)
+        m = self.lib.ref_trim_basecalls(nsamples, np.ascontiguousarray(bcpos, np.int32), np.ascontiguousarray(qual, np.uint8), bytes(primary), bytes(secondary),
+                                        bytes(consensus), n, trim_left, trim_right, ob, oq, op, os_, oc)
+        return ob[:m], oq[:m], op.raw[:m], os_.raw[:m], oc.raw[:m]
+
     def write_decomposition(self, pairs):
         import tempfile
         p = tempfile.mktemp()

@@ -32,6 +32,7 @@
 #include "decompose.h" // findBreakpoint, decomposeAlleles, ...           (reference, unmodified)
 #include "msa.h"       // distanceMatrix, upgma, palign, consensus, revSeqBasedOnDist, msa (reference, unmodified)
 #include "json.h"      // traceJsonOut, alignmentTracePadding, traceAlignJsonOut (reference, unmodified; variants.h / htslib only declared)
+#include "trim.h"      // trimTrace, nearestSNP (reference, unmodified)
 
 namespace {
 typedef boost::multi_array<float, 2> TProfile;
@@ -454,6 +455,40 @@ void ref_decompose_json(const char* outprefix, int trimLeft, int trimRight, int 
   std::vector<tracy::Variant> var(g_variants);
   if (sorted) std::sort(var.begin(), var.end());
   tracy::traceAlleleAlignJsonOut(c, bc, tr, var, rs1, rs2, rs3, al1, al2, al3, d, score1, score2, score3, bp, std::make_pair(f1, f2));
+}
+
+// estimateQualities (src/abif.h:232-253) with findBestTraceSection (:164-229), and the two trimTrace overloads (src/trim.h:35-99):
+// what every subcommand runs between basecall() and createProfile().
+struct TrimCfg { float trimStringency; };
+void ref_estimate_qualities(const int32_t* bcpos, const char* pri, const char* sec, int n, uint8_t* qual, uint32_t* best_section) {
+  tracy::BaseCalls bc;
+  bc.bcPos.assign(bcpos, bcpos + n);
+  bc.primary = std::string(pri, pri + n);
+  bc.secondary = std::string(sec, sec + n);
+  tracy::estimateQualities(bc);
+  for (int i = 0; i < n; ++i) qual[i] = bc.estQual[i];
+  *best_section = tracy::findBestTraceSection(bc);
+}
+void ref_trim_trace(const int32_t* bcpos, const char* sec, int n, float stringency, uint32_t* left, uint32_t* right) {
+  tracy::BaseCalls bc;
+  bc.bcPos.assign(bcpos, bcpos + n);
+  bc.secondary = std::string(sec, sec + n);
+  TrimCfg c; c.trimStringency = stringency;
+  tracy::trimTrace(c, bc, *left, *right);
+}
+int ref_trim_basecalls(int nsamples, const int32_t* bcpos, const uint8_t* qual, const char* pri, const char* sec, const char* cons, int n, unsigned trimLeft,
+                       unsigned trimRight, int32_t* obcpos, uint8_t* oqual, char* opri, char* osec, char* ocons) {
+  tracy::Trace tr;
+  tr.traceACGT.resize(4);
+  for (int k = 0; k < 4; ++k) tr.traceACGT[k].assign((size_t)nsamples, 0);
+  tracy::BaseCalls bc, nbc;
+  bc.bcPos.assign(bcpos, bcpos + n);
+  bc.estQual.assign(qual, qual + n);
+  bc.primary = std::string(pri, pri + n); bc.secondary = std::string(sec, sec + n); bc.consensus = std::string(cons, cons + n);
+  tracy::trimTrace(tr, bc, trimLeft, trimRight, nbc);
+  const int m = (int)nbc.bcPos.size();
+  for (int i = 0; i < m; ++i) { obcpos[i] = nbc.bcPos[i]; oqual[i] = nbc.estQual[i]; opri[i] = nbc.primary[i]; osec[i] = nbc.secondary[i]; ocons[i] = nbc.consensus[i]; }
+  return m;
 }
 
 // allelicFraction(c, tr, bc), src/decompose.h:412-617

@@ -312,6 +312,30 @@ class _Ref:
                                         bytes(consensus), n, trim_left, trim_right, ob, oq, op, os_, oc)
         return ob[:m], oq[:m], op.raw[:m], os_.raw[:m], oc.raw[:m]
 
+    def aligned_trace_by_row(self, rows, row, name, forward, isref):
+        """alignedTraceByRow (src/json.h:220-246) -> the bytes it writes. rows: uint8[nrow][ncol] character alignment."""
+        import tempfile
+        p = tempfile.mktemp()
+        rows = np.ascontiguousarray(rows, np.uint8)
+        self.lib.ref_aligned_trace_by_row.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_uint, C.c_char_p, C.c_int, C.c_int]
+        self.lib.ref_aligned_trace_by_row(os.fsencode(p), rows.tobytes(), rows.shape[0], rows.shape[1], row, name.encode(), int(forward), int(isref))
+        out = open(p, "rb").read()
+        os.remove(p)
+        return out
+
+    def reverse_complement_trace(self, acgt, bcpos, qual, primary, secondary, consensus):
+        """reverseComplementTrace (src/trim.h:124-151) -> (acgt, bcpos, qual, primary, secondary, consensus)."""
+        acgt = np.ascontiguousarray(acgt, np.int32)
+        n, ns = len(bcpos), acgt.shape[1]
+        u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        self.lib.ref_reverse_complement_trace.argtypes = [_i32p, C.c_int, _i32p, u8, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, _i32p, _i32p, u8, C.c_char_p, C.c_char_p, C.c_char_p]
+        self.lib.ref_reverse_complement_trace.restype = C.c_int
+        oa, ob, oq = np.zeros(4 * ns, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+        op, os_, oc = C.create_string_buffer(n + 1), C.create_string_buffer(n + 1), C.create_string_buffer(n + 1)
+        m = self.lib.ref_reverse_complement_trace(acgt.reshape(-1), ns, np.ascontiguousarray(bcpos, np.int32), np.ascontiguousarray(qual, np.uint8), bytes(primary),
+                                                  bytes(secondary), bytes(consensus), n, oa, ob, oq, op, os_, oc)
+        return oa.reshape(4, ns), ob[:m], oq[:m], op.raw[:m], os_.raw[:m], oc.raw[:m]
+
     def write_decomposition(self, pairs):
         import tempfile
         p = tempfile.mktemp()

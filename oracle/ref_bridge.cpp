@@ -491,6 +491,31 @@ int ref_trim_basecalls(int nsamples, const int32_t* bcpos, const uint8_t* qual, 
   return m;
 }
 
+// The two reference functions inside the output section of assemble() (src/assemble.h:496-545): alignedTraceByRow (src/json.h:220-246)
+// and reverseComplementTrace (src/trim.h:124-151, with reverseComplement(char) :102-123).
+void ref_aligned_trace_by_row(const char* path, const char* rows, int nrow, int ncol, unsigned row, const char* name, int forward, int isref) {
+  TAlign al(boost::extents[nrow][ncol]);
+  for (int i = 0; i < nrow; ++i) for (int j = 0; j < ncol; ++j) al[i][j] = rows[(size_t)i * ncol + j];
+  std::ofstream f(path);
+  tracy::alignedTraceByRow(f, al, row, name, forward != 0, isref != 0);
+}
+int ref_reverse_complement_trace(const int32_t* acgt, int nsamples, const int32_t* bcpos, const uint8_t* qual, const char* pri, const char* sec, const char* cons,
+                                 int n, int32_t* oacgt, int32_t* obcpos, uint8_t* oqual, char* opri, char* osec, char* ocons) {
+  tracy::Trace tr, ntr;
+  tr.traceACGT.resize(4);
+  for (int k = 0; k < 4; ++k) tr.traceACGT[k].assign(acgt + (size_t)k * nsamples, acgt + (size_t)(k + 1) * nsamples);
+  tr.qual.assign((size_t)n, 0);
+  tracy::BaseCalls bc, nbc;
+  bc.bcPos.assign(bcpos, bcpos + n);
+  bc.estQual.assign(qual, qual + n);
+  bc.primary = std::string(pri, pri + n); bc.secondary = std::string(sec, sec + n); bc.consensus = std::string(cons, cons + n);
+  tracy::reverseComplementTrace(tr, bc, ntr, nbc);
+  for (int k = 0; k < 4; ++k) for (int i = 0; i < nsamples; ++i) oacgt[(size_t)k * nsamples + i] = ntr.traceACGT[k][i];
+  const int m = (int)nbc.bcPos.size();
+  for (int i = 0; i < m; ++i) { obcpos[i] = nbc.bcPos[i]; oqual[i] = nbc.estQual[i]; opri[i] = nbc.primary[i]; osec[i] = nbc.secondary[i]; ocons[i] = nbc.consensus[i]; }
+  return m;
+}
+
 // allelicFraction(c, tr, bc), src/decompose.h:412-617
 void ref_allelic_fraction(const int32_t* acgt, int nsamples, const int32_t* bcpos, const char* primary, const char* secdecompose, int nbc,
                           int trimLeft, int trimRight, double* a1, double* a2) {

@@ -109,3 +109,67 @@ def test_decompose_json_differential(oracle_ref):
             assert doc == mod.reference_json(oracle_ref, c), i
             compared += 1
     assert compared > 40
+
+
+def _assemble_writer_cases(seed, n):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_assemble_writers", os.path.join(ROOT, "tests", "golden", "make_golden_assemble_writers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, mod.cases(seed, n)
+
+
+def _my_assemble_parts(c):
+    from tracy_b200 import trim
+    g = trim.reverse_complement_trace(c["acgt"], c["bcpos"], c["qual"], c["pri"], c["sec"], c["sec"])
+    return dict(acgt_sum=[int(x) for x in (g["acgt"].astype(np.int64) * np.arange(1, g["acgt"].shape[1] + 1)).sum(axis=1)], bcpos=[int(x) for x in g["bcpos"]],
+                qual=[int(x) for x in g["qual"]], primary=g["primary"], secondary=g["secondary"],
+                byrow=writers.aligned_trace_by_row(c["rows"], c["row"], c["name"], c["fwd"], c["isref"]))
+
+
+def test_assemble_output_functions_match_reference_goldens():
+    """alignedTraceByRow and reverseComplementTrace -- the two reference functions inside assemble()'s output section."""
+    import json
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "assemble_writers_golden.json")))
+    _, cs = _assemble_writer_cases(41, len(want))
+    for i, c in enumerate(cs):
+        assert _my_assemble_parts(c) == want[i], i
+
+
+def test_assemble_output_functions_differential(oracle_ref):
+    import pytest
+    if oracle_ref is None:
+        pytest.skip("reference build not present")
+    mod, cs = _assemble_writer_cases(3, 200)
+    for i, c in enumerate(cs):
+        assert _my_assemble_parts(c) == mod.reference_outputs(oracle_ref, c), i
+
+
+def test_assemble_files_layout():
+    """The files of `tracy assemble` (reference src/assemble.h:473-579) put together from the pinned parts: FASTA records per row with
+    the orientation, a JSON document that parses and holds one msa entry and one gapped trace per row, one `.vertical` line per column,
+    the consensus as FASTA or FASTQ."""
+    import json
+    from tracy_b200 import trim
+    rng = np.random.default_rng(12)
+    rows = np.frombuffer(b"--ACGT-AC" b"TTAC-TGAC" b"-TACGT---", np.uint8).reshape(3, 9)
+    names, fwd = ["t1", "t2", "t3"], [True, False, True]
+    padded = []
+    for i in range(3):
+        seq = bytes(rows[i]).replace(b"-", b"")
+        n = len(seq)
+        acgt = rng.integers(0, 900, (4, n * 10 + 8)).astype(np.int32)
+        bcpos = (np.arange(n) * 10 + 4).astype(np.int32)
+        tr = dict(acgt=acgt, bcpos=bcpos, qual=np.full(n, 30, np.uint8), primary=seq.decode(), secondary=seq.decode(), consensus=seq.decode())
+        if not fwd[i]:
+            tr = trim.reverse_complement_trace(acgt, bcpos, tr["qual"], seq, seq, seq)
+            tr["primary"] = tr["secondary"] = tr["consensus"] = seq.decode()           # keep the row's characters for the padding walk
+        padded.append(writers.alignment_trace_padding(bytes(rows[i]), tr["acgt"], tr["bcpos"], tr["qual"], tr["primary"], tr["secondary"], tr["consensus"]))
+    out = writers.assemble_files(names, fwd, rows, b"TTACGTGAC", b"TTACGTGAC", b"IIIIIIIII", padded, include_consensus=True, fmt="fastq")
+    assert out[".align.fa"] == ">t1 (forward)\n--ACGT-AC\n>t2 (reverse)\nTTAC-TGAC\n>t3 (forward)\n-TACGT---\n>Consensus\nTTACGTGAC\n"
+    assert out[".vertical"].splitlines()[2] == "AAA|A" and len(out[".vertical"].splitlines()) == 9
+    assert out[".cons.fq"] == "@Consensus\nTTACGTGAC\n+\nIIIIIIIII\n"
+    doc = json.loads(out[".json"])
+    assert [m["traceFileName"] for m in doc["msa"]] == names and doc["msa"][0]["leadingGaps"] == "2" and doc["msa"][2]["align"] == "TACGT"
+    assert len(doc["gappedTraces"]) == 3 and doc["gappedTraces"][0]["leadingGaps"] == 2 and doc["gappedTraces"][1]["basecalls"]
+    assert ".cons.fa" in writers.assemble_files(names, fwd, rows, b"TTACGTGAC", b"TTACGTGAC", b"IIIIIIIII", padded)

@@ -121,3 +121,29 @@ def trim_basecalls(nsamples, bcpos, qual, primary, secondary, consensus, trim_le
                 idx = int(bcpos[k])
     return dict(bcpos=np.array([int(bcpos[k]) for k in keep], np.int32), qual=np.array([int(qual[k]) for k in keep], np.uint8),
                 primary="".join(pri[k] for k in keep), secondary="".join(sec[k] for k in keep), consensus="".join(con[k] for k in keep))
+
+
+_COMPLEMENT = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N", "H": "D", "V": "B", "M": "K", "Y": "R", "D": "H", "B": "V", "K": "M", "R": "Y", "U": "A",
+               "S": "S", "W": "W"}
+
+
+def reverse_complement_trace(acgt, bcpos, qual, primary, secondary, consensus):
+    """reverseComplementTrace (reference src/trim.h:124-151): the samples reversed with channels A<->T, C<->G swapped; the
+    basecalls walked from the last one down (positions that do not come up in decreasing order are dropped, like the writers'
+    forward walk), complemented over the IUPAC alphabet (:102-123; other characters stay). Returns dict(acgt, bcpos, qual, primary,
+    secondary, consensus)."""
+    acgt = np.asarray(acgt)
+    pri, sec, con = _s(primary), _s(secondary), _s(consensus)
+    ns = acgt.shape[1]
+    out = np.ascontiguousarray(acgt[::-1, ::-1]).astype(np.int32)
+    k = len(bcpos) - 1
+    idx = int(bcpos[k])
+    nb, nq, np_, ns_, nc = [], [], [], [], []
+    for new_pos, t in enumerate(range(ns, 0, -1)):
+        if idx == t - 1:
+            nb.append(new_pos); nq.append(int(qual[k]))
+            np_.append(_COMPLEMENT.get(pri[k], pri[k])); ns_.append(_COMPLEMENT.get(sec[k], sec[k])); nc.append(_COMPLEMENT.get(con[k], con[k]))
+            if k > 0:
+                k -= 1
+                idx = int(bcpos[k])
+    return dict(acgt=out, bcpos=np.array(nb, np.int32), qual=np.array(nq, np.uint8), primary="".join(np_), secondary="".join(ns_), consensus="".join(nc))

@@ -8,6 +8,7 @@ the batch drivers return, byte-identical to the reference's writers.
   trace_json           basecall JSON   reference src/json.h:32-117 (traceJsonOut)
   alignment_trace_padding, trace_align_json   P.json of `tracy align`   reference src/json.h:383-479, 120-217, src/sage.h:319-343
   decompose_json       P.json of `tracy decompose`   reference src/json.h:16-30, 249-381 (traceAlleleAlignJsonOut)
+  aligned_trace_by_row, assemble_files   P.align.fa / P.json / P.vertical / P.cons.fa|fq of `tracy assemble`   reference src/json.h:220-246, src/assemble.h:473-579
 The BCF writer (src/variants.h:141-266, htslib) is not covered.
 """
 import numpy as np
@@ -273,3 +274,39 @@ def decompose_json(cfg, acgt, bcpos, qual, primary, secondary, var, allele1, all
         ranges.append("[%d, %d]" % x_window_viewport(bcpos, k))
     out.append(",\n".join(rows) + '],\n"xranges": [\n' + ",\n".join(ranges) + "]\n}\n}\n")
     return "".join(out)
+
+
+# ---- the files of `tracy assemble` (de novo) ------------------------------------------------------------------------------
+def aligned_trace_by_row(rows, row, trace_file_name, forward, ref):
+    """alignedTraceByRow (reference src/json.h:220-246): one row of the multiple alignment without its end gaps, as a JSON object."""
+    r = bytes(np.asarray(rows, np.uint8)[row]).decode("latin-1")
+    lead = len(r) - len(r.lstrip("-"))
+    trail = 0
+    for ch in r:                                                       # the reference's count: a row of gaps only has lead = trail = len
+        trail = 0 if ch != "-" else trail + 1
+    return ('{\n"reference": %s,\n"forward": %s,\n"traceFileName": "%s",\n"leadingGaps": "%d",\n"trailingGaps": "%d",\n"align": "%s"\n}\n'
+            % ("true" if ref else "false", "true" if forward else "false", trace_file_name, lead, trail, r[lead: max(len(r) - trail, lead)] if lead < len(r) - trail else ""))
+
+
+def assemble_files(names, forward, rows, gapped, consensus, quality, padded_traces, include_consensus=False, fmt="fasta"):
+    """The output section of the de novo branch of assemble() (reference src/assemble.h:473-579). names / forward: per alignment row
+    (the reference's c.ab[idxMap[seqidx[i]]].stem() and fwd[seqidx[i]]); rows: uint8[nrow][ncol]; gapped / consensus / quality: what
+    msa.consensus returns; padded_traces: per row the dict alignment_trace_padding returns for that trace (reverse-complemented first
+    when the row is not forward). Returns {suffix: text} for .align.fa, .json, .vertical and .cons.fa | .cons.fq."""
+    a = np.asarray(rows, np.uint8)
+    gapped, cs, qs = _s(gapped), _s(consensus), _s(quality)
+    fa = "".join(">%s (%s)\n%s\n" % (names[i], "forward" if forward[i] else "reverse", bytes(a[i]).decode("latin-1")) for i in range(a.shape[0]))
+    if include_consensus:
+        fa += ">Consensus\n" + gapped + "\n"
+    js = ['{\n"gapFreeConsensus": "%s",\n"gappedConsensus": "%s",\n"msa": \n[\n' % (cs, gapped)]
+    js.append(",\n".join(aligned_trace_by_row(a, i, names[i], forward[i], False) for i in range(a.shape[0])))
+    js.append('],\n"gappedTraces": \n[\n')
+    js.append(", ".join(assembly_trace(padded_traces[i], names[i]) for i in range(a.shape[0])))
+    js.append("]\n}\n")
+    vertical = "".join(bytes(a[:, j]).decode("latin-1") + "|" + gapped[j] + "\n" for j in range(a.shape[1]))
+    out = {".align.fa": fa, ".json": "".join(js), ".vertical": vertical}
+    if fmt == "fasta":
+        out[".cons.fa"] = ">Consensus\n" + cs + "\n"
+    elif fmt == "fastq":
+        out[".cons.fq"] = "@Consensus\n" + cs + "\n+\n" + qs + "\n"
+    return out

@@ -336,6 +336,12 @@ class _Ref:
                                                   bytes(secondary), bytes(consensus), n, oa, ob, oq, op, os_, oc)
         return oa.reshape(4, ns), ob[:m], oq[:m], op.raw[:m], os_.raw[:m], oc.raw[:m]
 
+    def nearest_snp(self, primary, secondary, trim_left, trim_right, rtp):
+        """nearestSNP(c, bc, rtp) (src/trim.h:11-33)."""
+        self.lib.ref_nearest_snp.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint]
+        self.lib.ref_nearest_snp.restype = C.c_uint
+        return int(self.lib.ref_nearest_snp(bytes(primary), bytes(secondary), len(primary), trim_left, trim_right, rtp))
+
     def write_decomposition(self, pairs):
         import tempfile
         p = tempfile.mktemp()

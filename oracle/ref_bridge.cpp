@@ -516,6 +516,17 @@ int ref_reverse_complement_trace(const int32_t* acgt, int nsamples, const int32_
   return m;
 }
 
+// nearestSNP(c, bc, rtp), src/trim.h:11-33: the heterozygous position closest to the reliable trace section (the JSON viewport of a
+// decompose run without a heterozygous indel, src/indigo.h:391-395).
+struct SnpCfg { uint16_t trimLeft, trimRight; };
+unsigned ref_nearest_snp(const char* pri, const char* sec, int n, int trimLeft, int trimRight, unsigned rtp) {
+  tracy::BaseCalls bc;
+  bc.primary = std::string(pri, pri + n);
+  bc.secondary = std::string(sec, sec + n);
+  SnpCfg c; c.trimLeft = (uint16_t)trimLeft; c.trimRight = (uint16_t)trimRight;
+  return tracy::nearestSNP(c, bc, rtp);
+}
+
 // allelicFraction(c, tr, bc), src/decompose.h:412-617
 void ref_allelic_fraction(const int32_t* acgt, int nsamples, const int32_t* bcpos, const char* primary, const char* secdecompose, int nbc,
                           int trimLeft, int trimRight, double* a1, double* a2) {

@@ -37,10 +37,24 @@ def reference_outputs(ref, c):
     return dict(qual=[int(x) for x in q], best=best, left=left, right=right, kept_bcpos=[int(x) for x in kept[0]], kept_primary=kept[2].decode("latin-1"))
 
 
+def snp_cases(seed, n_cases):
+    """Seeded inputs of nearestSNP (src/trim.h:11-33): calls with no, few or many heterozygous positions, any trims, any start."""
+    rng = np.random.default_rng(seed)
+    for it in range(n_cases):
+        n = int(rng.integers(1, 120))
+        pri = bytes(rng.choice(list(b"ACGT"), n).astype(np.uint8))
+        p = [0, 0.02, 0.2][it % 3]
+        sec = bytes(np.where(rng.random(n) < p, rng.choice(list(b"ACGTRY"), n), np.frombuffer(pri, np.uint8)).astype(np.uint8))
+        yield pri, sec, int(rng.integers(0, n // 2 + 2)), int(rng.integers(0, n // 2 + 2)), int(rng.integers(0, n))
+
+
 if __name__ == "__main__":
     ref = loader.ref()
     assert ref is not None, "needs the reference build (oracle/_ref/libtracy_ref.so)"
     out = [reference_outputs(ref, c) for c in cases(31, 40)]
     with open(os.path.join(ROOT, "tests", "golden", "trim_golden.json"), "w") as f:
         json.dump(out, f)
-    print("wrote trim_golden.json:", len(out), "cases")
+    snp = [ref.nearest_snp(*c) for c in snp_cases(32, 300)]
+    with open(os.path.join(ROOT, "tests", "golden", "nearest_snp_golden.json"), "w") as f:
+        json.dump(snp, f)
+    print("wrote trim_golden.json:", len(out), "cases; nearest_snp_golden.json:", len(snp), "cases")

@@ -48,3 +48,12 @@ def test_trim_differential(oracle_ref):
         pytest.skip("reference build not present")
     for i, c in enumerate(_gen.cases(7, 300)):
         assert _mine(c) == _gen.reference_outputs(oracle_ref, c), i
+
+
+def test_nearest_snp_goldens(oracle_ref):
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "nearest_snp_golden.json")))
+    for i, c in enumerate(_gen.snp_cases(32, len(want))):
+        assert trim.nearest_snp(*c) == want[i], i
+    if oracle_ref is not None:
+        for i, c in enumerate(_gen.snp_cases(33, 1500)):
+            assert trim.nearest_snp(*c) == oracle_ref.nearest_snp(*c), i

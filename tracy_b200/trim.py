@@ -147,3 +147,26 @@ def reverse_complement_trace(acgt, bcpos, qual, primary, secondary, consensus):
                 k -= 1
                 idx = int(bcpos[k])
     return dict(acgt=out, bcpos=np.array(nb, np.int32), qual=np.array(nq, np.uint8), primary="".join(np_), secondary="".join(ns_), consensus="".join(nc))
+
+
+def nearest_snp(primary, secondary, trim_left, trim_right, rtp):
+    """nearestSNP(c, bc, rtp) (reference src/trim.h:11-33): walking outwards from basecall rtp (the reliable trace section), the first
+    position inside the trimmed range whose primary and secondary calls differ, as an index into the TRIMMED trace; the right side is
+    looked at first at every distance. Without any such position: rtp - trimLeft (or trimLeft when rtp lies in the left trim)."""
+    pri, sec = _s(primary), _s(secondary)
+    n = min(len(pri), len(sec))
+    offset = 0
+    while True:
+        dead_end = True
+        if rtp + offset + trim_right < n:
+            if trim_left < rtp + offset and pri[rtp + offset] != sec[rtp + offset]:
+                return rtp + offset - trim_left
+            dead_end = False
+        if offset + trim_left < rtp:
+            if pri[rtp - offset] != sec[rtp - offset]:
+                return rtp - offset - trim_left
+            dead_end = False
+        if dead_end:
+            break
+        offset += 1
+    return rtp - trim_left if rtp > trim_left else trim_left

@@ -173,3 +173,28 @@ def test_assemble_files_layout():
     assert [m["traceFileName"] for m in doc["msa"]] == names and doc["msa"][0]["leadingGaps"] == "2" and doc["msa"][2]["align"] == "TACGT"
     assert len(doc["gappedTraces"]) == 3 and doc["gappedTraces"][0]["leadingGaps"] == 2 and doc["gappedTraces"][1]["basecalls"]
     assert ".cons.fa" in writers.assemble_files(names, fwd, rows, b"TTACGTGAC", b"TTACGTGAC", b"IIIIIIIII", padded)
+
+
+def test_per_subcommand_file_sets():
+    """`align -o P` writes P.abif, P.align.fa, P.txt, P.json; `decompose -o P` writes P.abif, P.decomp, P.align1-3,
+    P.json (P.bcf needs htslib). The composed sets hold exactly the texts of the single writers."""
+    import json
+    from tracy_b200 import variants
+    rng = np.random.default_rng(3)
+    n = 30
+    acgt = rng.integers(0, 2000, (4, n * 12 + 30)).astype(np.int32)
+    bcpos = (np.arange(n) * 12 + 9).astype(np.int32)
+    qual = rng.integers(0, 61, n).astype(np.uint8)
+    pri = bytes(rng.choice(list(b"ACGT"), n).astype(np.uint8))
+    row0, row1 = pri[:10] + b"--" + pri[10:], b"AC" + pri[2:10] + b"GT" + pri[10:]
+    files = writers.align_files("t1", acgt, bcpos, qual, pri, pri, pri, 2, 3, row0, row1, b"chr5", 1000, 40, True, 77)
+    assert sorted(files) == [".abif", ".align.fa", ".json", ".txt"]
+    assert files[".json"] == writers.trace_align_json(acgt, bcpos, qual, pri, pri, pri, row0, row1, b"chr5", 1000, True)
+    assert files[".abif"].count("\n") == acgt.shape[1] + 1 and json.loads(files[".json"])["refpos"] == 1001
+    var = variants.call_variants(row0[2:], row1[2:], b"chr5", 1000, [])
+    a1 = (row0[2:], row1[2:], b"chr5", 1000, True, 50)
+    cfg = dict(trim_left=2, trim_right=3, qual_cut=45, pratio=0.33, input="x/t1.ab1", genome="g.fa")
+    dfiles = writers.decompose_files(cfg, acgt, bcpos, qual, pri, pri, pri, [(-1, 5), (0, 9), (1, 4)], var, a1, a1, (row0[2:], row1[2:], 12), (40, 40), False, 4, (0.6, 0.4))
+    assert sorted(dfiles) == [".abif", ".align1", ".align2", ".align3", ".decomp", ".json"]
+    assert dfiles[".align3"].startswith(">Alt1 (Estimated allelic Fraction: 0.6)") and ">Alt2 (Estimated allelic Fraction: 0.4)" in dfiles[".align3"]
+    assert json.loads(dfiles[".json"])["decomposition"]["x"] == [-1, 0, 1]

@@ -310,3 +310,28 @@ def assemble_files(names, forward, rows, gapped, consensus, quality, padded_trac
     elif fmt == "fastq":
         out[".cons.fq"] = "@Consensus\n" + cs + "\n+\n" + qs + "\n"
     return out
+
+
+# ---- all files of one trace, as SURVEY appendix B lists them ---------------------------------------------------------------
+def align_files(trace_name, acgt, bcpos, qual, primary, secondary, consensus, trim_left, trim_right, row0, row1, chr_name, pos, refslice_len, forward, score,
+                linelimit=60):
+    """`tracy align -o P`: {suffix: text} for P.abif (reference src/sage.h:188), P.align.fa (:326-339), P.txt (:342), P.json (:319-345).
+    The trace arguments are the UNTRIMMED trace and basecalls (the trims only mark rows of P.abif); row0 / row1: the final alignment of
+    the full trace against the trimmed reference slice; pos / refslice_len / forward: that slice."""
+    return {".abif": trace_txt(acgt, bcpos, qual, primary, secondary, consensus, trim_left, trim_right),
+            ".align.fa": align_fasta(trace_name, row0, row1, chr_name, forward),
+            ".txt": plot_alignment(row0, row1, chr_name, pos, refslice_len, forward, score, 0, (0, 0), linelimit),
+            ".json": trace_align_json(acgt, bcpos, qual, primary, secondary, consensus, row0, row1, chr_name, pos, forward)}
+
+
+def decompose_files(cfg, acgt, bcpos, qual, primary, secondary, consensus, decomp, var, allele1, allele2, align3, refslice_lens, indelshift, breakpoint, a1a2, linelimit=60):
+    """`tracy decompose -o P`: {suffix: text} for P.abif (reference src/indigo.h:187), P.decomp (:341), P.align1 / .align2 / .align3
+    (:366, 377, 388) and P.json (:450); P.bcf needs htslib and is not written. allele1 / allele2: (row0, row1, chr, pos, forward, score),
+    align3: (allele 1 row, allele 2 row, score), refslice_lens: the lengths of the two reference slices."""
+    out = {".abif": trace_txt(acgt, bcpos, qual, primary, secondary, consensus, cfg["trim_left"], cfg["trim_right"]), ".decomp": write_decomposition(decomp)}
+    for key, (al, rl) in enumerate(((allele1, refslice_lens[0]), (allele2, refslice_lens[1])), start=1):
+        out[".align%d" % key] = plot_alignment(al[0], al[1], al[2], al[3], rl, al[4], al[5], key, a1a2, linelimit)
+    # allele 1 against allele 2 (global): the "reference" is the second allele itself, src/indigo.h:380-388
+    out[".align3"] = plot_alignment(align3[0], align3[1], b"Alt2", 0, len(bytes(align3[1]).replace(b"-", b"")), True, align3[2], 3, a1a2, linelimit)
+    out[".json"] = decompose_json(cfg, acgt, bcpos, qual, primary, secondary, var, allele1, allele2, align3, decomp, indelshift, breakpoint, a1a2)
+    return out

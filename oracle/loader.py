@@ -342,6 +342,19 @@ class _Ref:
         self.lib.ref_nearest_snp.restype = C.c_uint
         return int(self.lib.ref_nearest_snp(bytes(primary), bytes(secondary), len(primary), trim_left, trim_right, rtp))
 
+    def trace_fastx(self, fastq, otype, trim_left, trim_right, nsamples, bcpos, qual, primary, secondary, consensus):
+        """traceFastaOut / traceFastqOut (src/fasta.h:98-158) -> the bytes they write."""
+        import tempfile
+        p = tempfile.mktemp()
+        u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        self.lib.ref_trace_fastx.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, _i32p, u8, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        self.lib.ref_trace_fastx.restype = None
+        self.lib.ref_trace_fastx(os.fsencode(p), int(fastq), otype.encode(), trim_left, trim_right, nsamples, np.ascontiguousarray(bcpos, np.int32),
+                                 np.ascontiguousarray(qual, np.uint8), bytes(primary), bytes(secondary), bytes(consensus), len(bcpos))
+        out = open(p, "rb").read()
+        os.remove(p)
+        return out
+
     def write_decomposition(self, pairs):
         import tempfile
         p = tempfile.mktemp()

@@ -527,6 +527,21 @@ unsigned ref_nearest_snp(const char* pri, const char* sec, int n, int trimLeft, 
   return tracy::nearestSNP(c, bc, rtp);
 }
 
+// traceFastaOut / traceFastqOut (src/fasta.h:98-158): the fasta / fastq formats of the basecall subcommand (src/teal.h:105-109).
+struct TealCfg { uint16_t trimLeft, trimRight; std::string otype; boost::filesystem::path outfile; };
+void ref_trace_fastx(const char* path, int fastq, const char* otype, int trimLeft, int trimRight, int nsamples, const int32_t* bcpos, const uint8_t* qual,
+                     const char* pri, const char* sec, const char* cons, int n) {
+  tracy::Trace tr;
+  tr.traceACGT.resize(4);
+  for (int k = 0; k < 4; ++k) tr.traceACGT[k].assign((size_t)nsamples, 0);
+  tracy::BaseCalls bc;
+  bc.bcPos.assign(bcpos, bcpos + n);
+  bc.estQual.assign(qual, qual + n);
+  bc.primary = std::string(pri, pri + n); bc.secondary = std::string(sec, sec + n); bc.consensus = std::string(cons, cons + n);
+  TealCfg c; c.trimLeft = (uint16_t)trimLeft; c.trimRight = (uint16_t)trimRight; c.otype = otype; c.outfile = boost::filesystem::path(path);
+  if (fastq) tracy::traceFastqOut(c, bc, tr); else tracy::traceFastaOut(c, bc, tr);
+}
+
 // allelicFraction(c, tr, bc), src/decompose.h:412-617
 void ref_allelic_fraction(const int32_t* acgt, int nsamples, const int32_t* bcpos, const char* primary, const char* secdecompose, int nbc,
                           int trimLeft, int trimRight, double* a1, double* a2) {

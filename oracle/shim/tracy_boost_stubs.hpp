@@ -20,6 +20,7 @@ class path {
   path(const std::string& s) : p_(s) {}
   path(const char* s) : p_(s) {}
   const std::string& string() const { return p_; }
+  const char* c_str() const { return p_.c_str(); }
   path parent_path() const { auto k = p_.find_last_of('/'); return k == std::string::npos ? path("") : path(p_.substr(0, k)); }
   path filename() const { auto k = p_.find_last_of('/'); return k == std::string::npos ? *this : path(p_.substr(k + 1)); }
   path stem() const { std::string f = filename().string(); auto k = f.find_last_of('.'); return (k == std::string::npos || k == 0) ? path(f) : path(f.substr(0, k)); }

@@ -198,3 +198,36 @@ def test_per_subcommand_file_sets():
     assert sorted(dfiles) == [".abif", ".align1", ".align2", ".align3", ".decomp", ".json"]
     assert dfiles[".align3"].startswith(">Alt1 (Estimated allelic Fraction: 0.6)") and ">Alt2 (Estimated allelic Fraction: 0.4)" in dfiles[".align3"]
     assert json.loads(dfiles[".json"])["decomposition"]["x"] == [-1, 0, 1]
+
+
+def _fastx_cases(seed, n_cases):
+    rng = np.random.default_rng(seed)
+    for it in range(n_cases):
+        n = int(rng.integers(1, 80))
+        ns = n * 10 + int(rng.integers(2, 30))
+        bcpos = np.sort(rng.choice(ns, n, replace=False)).astype(np.int32)
+        if it % 9 == 0 and n > 2:
+            bcpos[n // 2] = bcpos[n // 2 - 1]
+        qual = rng.integers(0, 61, n).astype(np.uint8)
+        pri, sec, con = (bytes(rng.choice(list(a), n).astype(np.uint8)) for a in (b"ACGT", b"ACGTRY", b"ACGTN"))
+        tl = int(rng.integers(0, n // 2 + 1))
+        tr = int(rng.integers(0, n - tl)) if n - tl > 0 else 0
+        yield ["primary", "secondary", "consensus", "other"][it % 4], tl, tr, ns, bcpos, qual, pri, sec, con
+
+
+def test_trace_fasta_fastq(oracle_ref):
+    """The fasta / fastq formats of the basecall subcommand (traceFastaOut / traceFastqOut, src/fasta.h:98-158): fixed cases written by
+    the reference, and a differential run where its build exists."""
+    q = np.array([0, 10, 40, 60, 20], np.uint8)
+    pos = np.array([3, 9, 15, 21, 27], np.int32)
+    assert writers.trace_fasta("primary", 1, 1, b"ACGTA", b"ACRTA", b"ACNTA") == ">primary\nCGT\n"
+    assert writers.trace_fasta("consensus", 0, 0, b"ACGTA", b"ACRTA", b"ACNTA") == ">consensus\nACNTA\n"
+    assert writers.trace_fasta("nothing", 0, 0, b"ACGTA", b"ACRTA", b"ACNTA") == ""
+    assert writers.trace_fastq("secondary", 1, 1, 30, pos, q, b"ACGTA", b"ACRTA", b"ACNTA") == "@secondary\nCRT\n+\n+I]\n"
+    assert writers.trace_fastq("nothing", 0, 2, 30, pos, q, b"ACGTA", b"ACRTA", b"ACNTA") == "+\n!+I\n"
+    if oracle_ref is not None:
+        assert oracle_ref.trace_fastx(1, "secondary", 1, 1, 30, pos, q, b"ACGTA", b"ACRTA", b"ACNTA") == b"@secondary\nCRT\n+\n+I]\n"
+        assert oracle_ref.trace_fastx(1, "nothing", 0, 2, 30, pos, q, b"ACGTA", b"ACRTA", b"ACNTA") == b"+\n!+I\n"
+        for i, (ot, tl, tr, ns, bcpos, qual, pri, sec, con) in enumerate(_fastx_cases(8, 300)):
+            assert writers.trace_fasta(ot, tl, tr, pri, sec, con).encode("latin-1") == oracle_ref.trace_fastx(0, ot, tl, tr, ns, bcpos, qual, pri, sec, con), i
+            assert writers.trace_fastq(ot, tl, tr, ns, bcpos, qual, pri, sec, con).encode("latin-1") == oracle_ref.trace_fastx(1, ot, tl, tr, ns, bcpos, qual, pri, sec, con), i

@@ -5,6 +5,7 @@ the batch drivers return, byte-identical to the reference's writers.
   plot_alignment       P.txt, P.align1/.align2/.align3   reference src/fmindex.h:329-427 (plotAlignment)
   write_decomposition  P.decomp     reference src/decompose.h:621-627
   trace_txt            P.abif       reference src/abif.h:512-534 (traceTxtOut: the tab-separated trace table of align / decompose)
+  trace_fasta, trace_fastq   basecall subcommand   reference src/fasta.h:98-158
   trace_json           basecall JSON   reference src/json.h:32-117 (traceJsonOut)
   alignment_trace_padding, trace_align_json   P.json of `tracy align`   reference src/json.h:383-479, 120-217, src/sage.h:319-343
   decompose_json       P.json of `tracy decompose`   reference src/json.h:16-30, 249-381 (traceAlleleAlignJsonOut)
@@ -335,3 +336,28 @@ def decompose_files(cfg, acgt, bcpos, qual, primary, secondary, consensus, decom
     out[".align3"] = plot_alignment(align3[0], align3[1], b"Alt2", 0, len(bytes(align3[1]).replace(b"-", b"")), True, align3[2], 3, a1a2, linelimit)
     out[".json"] = decompose_json(cfg, acgt, bcpos, qual, primary, secondary, var, allele1, allele2, align3, decomp, indelshift, breakpoint, a1a2)
     return out
+
+
+# ---- the fasta / fastq formats of the basecall subcommand -------------------------------------------------------------------
+def trace_fasta(otype, trim_left, trim_right, primary, secondary, consensus):
+    """traceFastaOut (reference src/fasta.h:98-119): the primary, secondary or consensus calls between the trims; any other `otype`
+    writes an empty file."""
+    seq = {"primary": primary, "secondary": secondary, "consensus": consensus}.get(otype)
+    if seq is None:
+        return ""
+    seq = _s(seq)
+    return ">%s\n%s\n" % (otype, seq[trim_left: max(len(seq) - trim_right, trim_left)])
+
+
+def trace_fastq(otype, trim_left, trim_right, nsamples, bcpos, qual, primary, secondary, consensus):
+    """traceFastqOut (reference src/fasta.h:121-158): the record of trace_fasta with '@', then '+' and the estimated qualities
+    (Phred + 33) of the basecalls that come up in the writers' walk and lie between the trims (measured on the PRIMARY calls, whichever
+    sequence is written)."""
+    seq = {"primary": primary, "secondary": secondary, "consensus": consensus}.get(otype)
+    head = ""
+    if seq is not None:
+        seq = _s(seq)
+        head = "@%s\n%s\n" % (otype, seq[trim_left: max(len(seq) - trim_right, trim_left)])
+    last = len(_s(primary)) - trim_right
+    quals = "".join(chr((int(qual[k]) + 33) & 0xFF) for _, k in _called(nsamples, bcpos) if trim_left <= k < last)
+    return head + "+\n" + quals + "\n"

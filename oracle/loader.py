@@ -493,6 +493,30 @@ class _Ref:
         align = np.frombuffer(rows.raw[: nrow * ncol], np.uint8).reshape(nrow, ncol).copy()
         return dict(rows=align, seqidx=seqidx[:nrow].copy(), dist=dist.reshape(n, n), gapped=g.raw[:ncol], cons=cs.raw[: cl.value], qual=q.raw[: cl.value])
 
+    def assemble_reference(self, profiles, reference, sc, match_fraction=0.5, fraction_called=0.5, inc_ref=False):
+        """The DP sequence of the reference-guided branch of assemble() (src/assemble.h:163-292), composed in ref_bridge.cpp from the
+        reference's functions. Returns dict(rows, idx, forward, gapped, cons, qual) -- idx / forward per ranked trace."""
+        base, off, lens = self._pack(profiles)
+        n = len(profiles)
+        width = int(lens.astype(np.int64).sum()) + len(reference) + 16
+        cap = (n + 1) * width
+        rows = C.create_string_buffer(cap)
+        idx, fwd = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.uint8)
+        g, cs, q = C.create_string_buffer(width), C.create_string_buffer(width), C.create_string_buffer(width)
+        nk, cl = C.c_int(0), C.c_int(0)
+        u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+        self.lib.ref_assemble_reference.argtypes = [_f32p, _i64p, _i32p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                                    C.c_char_p, C.c_int, _i32p, u8, C.POINTER(C.c_int), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+        self.lib.ref_assemble_reference.restype = C.c_int
+        ncol = self.lib.ref_assemble_reference(base, off, lens, n, bytes(reference), len(reference), *sc, match_fraction, fraction_called, int(inc_ref), rows, cap,
+                                               idx, fwd, C.byref(nk), g, cs, q, C.byref(cl))
+        assert ncol >= 0
+        k = nk.value
+        nrow = k + 1 if k else 0
+        return dict(rows=np.frombuffer(rows.raw[: nrow * ncol], np.uint8).reshape(nrow, ncol).copy() if k else np.zeros((0, 0), np.uint8), idx=[int(x) for x in idx[:k]],
+                    forward=[bool(x) for x in fwd[:k]], gapped=g.raw[:ncol], cons=cs.raw[: cl.value], qual=q.raw[: cl.value])
+
     @staticmethod
     def _conv(x):
         if isinstance(x, (bytes, bytearray)):

@@ -317,6 +317,68 @@ int ref_msa(const float* base, const int64_t* off, const int32_t* len, int n, in
   return ncol;
 }
 
+// The DP sequence of the reference-guided branch of assemble() (src/assemble.h:163-292) composed from the reference's own functions
+// (_createProfile(string), gotohScore, reverseComplementProfile, gotoh, _createProfile(align), consensus). assemble() itself cannot be
+// compiled here (Boost.Program_options), so the glue between those calls -- the score threshold :226-231, the TraceScore order :34-45
+// (best score first, then input index), the row merge :262-281 -- is restated below; everything numeric is the reference's code.
+// Outputs: rows (nrow x ncol; traces in reverse order of their rank, the reference last), idx / fwd per ranked trace, the consensus strings.
+int ref_assemble_reference(const float* base, const int64_t* off, const int32_t* len, int n, const char* refseq, int reflen, int match, int mismatch, int go,
+                           int ge, float matchFraction, float fractionCalled, int incRef, char* rows, int cap, int32_t* idx, uint8_t* fwd, int* nkept,
+                           char* gapped, char* cons, char* qual, int* conslen) {
+  TProfiles in; load_profiles(base, off, len, n, in);
+  MsaCfg c(match, mismatch, go, ge, fractionCalled);
+  TProfile pref;
+  tracy::_createProfile(std::string(refseq, refseq + reflen), pref);
+  tracy::AlignConfig<true, false> semiglobal;
+  struct Ranked { int32_t score, idx, newidx; bool forward; };
+  std::vector<Ranked> rank;
+  std::vector<TProfile> prof;
+  for (int i = 0; i < n; ++i) {
+    const int32_t gsFwd = tracy::gotohScore(in[i], pref, semiglobal, c.aliscore);
+    TProfile rev;
+    tracy::reverseComplementProfile(in[i], rev);
+    const int32_t gsRev = tracy::gotohScore(rev, pref, semiglobal, c.aliscore);
+    const double seqsize = in[i].shape()[1];
+    const double scoreThreshold = seqsize * matchFraction * c.aliscore.match + seqsize * (1 - matchFraction) * c.aliscore.mismatch;
+    if ((gsFwd > scoreThreshold) || (gsRev > scoreThreshold)) {
+      rank.push_back(Ranked{std::max(gsFwd, gsRev), i, (int32_t)rank.size(), gsFwd >= gsRev});
+      prof.push_back(gsFwd >= gsRev ? in[i] : rev);
+    }
+  }
+  std::sort(rank.begin(), rank.end(), [](Ranked const& a, Ranked const& b) { return a.score > b.score || (a.score == b.score && a.idx < b.idx); });
+  *nkept = (int)rank.size();
+  *conslen = 0;
+  if (rank.empty()) return 0;
+  TAlign align;
+  tracy::gotoh(prof[rank[0].newidx], pref, align, semiglobal, c.aliscore);
+  for (size_t i = 1; i < rank.size(); ++i) {
+    TAlign alignNew, combined;
+    TProfile ap;
+    tracy::_createProfile(align, ap);
+    tracy::gotoh(prof[rank[i].newidx], ap, alignNew, semiglobal, c.aliscore);
+    const size_t nSeq = align.shape()[0] + 1, nCol = alignNew.shape()[1];
+    combined.resize(boost::extents[nSeq][nCol]);
+    size_t p = 0;
+    for (size_t j = 0; j < nCol; ++j) {
+      combined[0][j] = alignNew[0][j];
+      const bool has = alignNew[1][j] != '-';
+      for (size_t k = 1; k < nSeq; ++k) combined[k][j] = has ? align[k - 1][p] : '-';
+      if (has) ++p;
+    }
+    align.resize(boost::extents[nSeq][nCol]);
+    align = combined;
+  }
+  const int nrow = (int)align.shape()[0], ncol = (int)align.shape()[1];
+  if ((long long)nrow * ncol > cap) return -(nrow * ncol);
+  for (int i = 0; i < nrow; ++i) for (int j = 0; j < ncol; ++j) rows[(size_t)i * ncol + j] = align[i][j];
+  for (size_t i = 0; i < rank.size(); ++i) { idx[i] = rank[i].idx; fwd[i] = rank[i].forward ? 1 : 0; }
+  std::string g, cs, q;
+  tracy::consensus(c, align, g, cs, q, incRef == 0);
+  std::memcpy(gapped, g.data(), g.size()); std::memcpy(cons, cs.data(), cs.size()); std::memcpy(qual, q.data(), q.size());
+  *conslen = (int)cs.size();
+  return ncol;
+}
+
 // Timed CPU baseline helper: runs `npairs` profile-x-sequence gotoh() calls back to back (the reference's
 // own single-threaded path) and returns the number of DP cells (sum m*n). Used by bench.py only.
 long long ref_bench_gotoh_ps(const float* profs, const char* seqs, int npairs, int m, int n, int hfree, int vfree,

@@ -116,3 +116,34 @@ def test_reverse_complement_seq(oracle_ref):
     for _ in range(100):
         s = bytes(alphabet[rng.integers(0, len(alphabet), int(rng.integers(0, 60)))])
         assert drivers.reverse_complement_seq(s) == oracle_ref.reverse_complement(s), s
+
+
+ASM_REF = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "assemble_reference_golden.npz"))
+
+
+def run_assemble_reference_case(ctx, it):
+    from tracy_b200 import drivers
+    G = ASM_REF
+    profs = [G[f"p{it}_{i}"] for i in range(int(G[f"n{it}"]))]
+    got = drivers.assemble_reference(ctx, profs, bytes(G[f"ref{it}"]), DnaScore(*SC), 0.5, 0.5, bool(G[f"inc{it}"]))
+    assert got["idx"] == [int(x) for x in G[f"idx{it}"]] and got["forward"] == [bool(x) for x in G[f"fwd{it}"]]
+    assert np.array_equal(got["rows"], G[f"rows{it}"])
+    assert got["gapped"] == bytes(G[f"gapped{it}"]) and got["consensus"] == bytes(G[f"cons{it}"]) and got["quality"] == bytes(G[f"qual{it}"])
+    assert sorted(got["idx"] + got["excluded"]) == list(range(len(profs)))
+
+
+@pytest.mark.parametrize("it", range(8))
+def test_assemble_reference_host_logic(oracle_port, it):
+    """The reference-guided branch of assemble() (orientation scores in one batch, threshold, ranking, iterative alignment against the
+    growing alignment profile, consensus) with the DP served by the CPU oracle, against the sequence composed from the reference's
+    functions (tests/golden/make_golden_assemble_reference.py)."""
+    run_assemble_reference_case(OracleContext(oracle_port), it)
+
+
+def test_onehot_profile_all_bytes(oracle_ref):
+    """_createProfile(std::string) (src/align.h:119-136) for every byte value: A, C, G, T, N in either case and '-' have a row."""
+    from tracy_b200 import msa as _msa
+    p = _msa.onehot_profile(bytes(range(1, 256)))
+    assert p.sum() == 11 and p[5, 0x2D - 1] == 1 and p[4, ord("n") - 1] == 1 and p[:, ord("x") - 1].sum() == 0
+    if oracle_ref is not None:
+        assert np.array_equal(oracle_ref.onehot(bytes(range(1, 256))), p)

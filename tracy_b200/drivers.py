@@ -287,3 +287,47 @@ def assemble_denovo(ctx, profiles, sc=DnaScore(3, -5, -10, -4), match_fraction=0
     rows, seqidx, _ = msa.msa(ctx, [profs[i] for i in kept], sc)            # src/assemble.h:468
     gapped, cs, qs = msa.consensus(rows, fraction_called, False)            # src/assemble.h:471
     return dict(forward=fwd, kept=kept, rows=rows, seqidx=seqidx, gapped=gapped, consensus=cs, quality=qs)
+
+
+def assemble_reference(ctx, profiles, reference, sc=DnaScore(3, -5, -10, -4), match_fraction=0.5, fraction_called=0.5, inc_ref=False):
+    """The DP sequence of the reference-guided branch of `tracy assemble` (reference src/assemble.h:163-292) from the trace profiles
+    on: both orientations of every trace scored against the one-hot reference profile (ONE batched call instead of 2N), traces below
+    the match threshold dropped, the rest ranked by score (then input order) and aligned one after the other against the profile of
+    the alignment so far (inherently sequential: each alignment changes the next one's input), consensus over the rows.
+    Returns dict(rows, idx, forward, excluded, gapped, consensus, quality): rows = the traces in reverse rank order, the reference last."""
+    semiglobal = AlignConfig(True, False)
+    profs = [np.ascontiguousarray(p, np.float32) for p in profiles]
+    n = len(profs)
+    pref = msa.onehot_profile(reference)
+    revs = [msa._revcomp(p) for p in profs]
+    ranked, excluded = [], []
+    if n:
+        s, _, _ = ctx.gotoh(PP, profs + revs, [pref] * (2 * n), sc, semiglobal, traceback=False)
+        f32 = np.float32
+        for i in range(n):
+            gs_fwd, gs_rev = int(s[i]), int(s[n + i])
+            size = float(profs[i].shape[1])                      # double seqsize; matchFraction is a float, (1 - matchFraction) a float too
+            thr = size * float(f32(match_fraction)) * sc.match + size * float(f32(1) - f32(match_fraction)) * sc.mismatch
+            if gs_fwd > thr or gs_rev > thr:
+                ranked.append((max(gs_fwd, gs_rev), i, gs_fwd >= gs_rev))
+            else:
+                excluded.append(i)
+    ranked.sort(key=lambda t: (-t[0], t[1]))                     # TraceScore::operator<, src/assemble.h:42-44
+    if not ranked:
+        return dict(rows=np.zeros((0, 0), np.uint8), idx=[], forward=[], excluded=excluded, gapped=b"", consensus=b"", quality=b"")
+    rows = None
+    for _, i, fwd in ranked:
+        p = profs[i] if fwd else revs[i]
+        target = pref if rows is None else msa.profile_from_alignment(rows)
+        _, ops, ol = ctx.gotoh(PP, [p], [target], sc, semiglobal, traceback=True)
+        o = ops[0, : ol[0]]
+        cons_p = np.frombuffer(msa.profile_cons_chars(p), np.uint8)
+        new0 = np.full(len(o), 0x2D, np.uint8)
+        new0[o != ord("h")] = cons_p[: int((o != ord("h")).sum())]
+        has = o != ord("v")
+        old = np.frombuffer(msa.profile_cons_chars(pref), np.uint8).reshape(1, -1) if rows is None else rows
+        below = np.full((old.shape[0], len(o)), 0x2D, np.uint8)
+        below[:, has] = old[:, : int(has.sum())]
+        rows = np.vstack([new0.reshape(1, -1), below])
+    gapped, cs, qs = msa.consensus(rows, fraction_called, not inc_ref)
+    return dict(rows=rows, idx=[i for _, i, _ in ranked], forward=[f for _, _, f in ranked], excluded=excluded, gapped=gapped, consensus=cs, quality=qs)

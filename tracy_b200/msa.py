@@ -85,6 +85,19 @@ def profile_from_alignment(rows):
     return p
 
 
+def onehot_profile(seq):
+    """_createProfile(std::string, p) (reference src/align.h:119-136): one column per character, 1 in the row of A, C, G, T, N (either
+    case) or '-', all zero for anything else. (The '-' row never enters _score, but it decides the column's consensus character.)"""
+    raw = np.frombuffer(bytes(seq), np.uint8)
+    up = raw & 0xDF
+    p = np.zeros((6, len(raw)), np.float32)
+    letter = ((raw | 0x20) >= 0x61) & ((raw | 0x20) <= 0x7A)            # a byte that is a letter: folding is only meaningful there
+    for k, ch in enumerate(b"ACGTN"):
+        p[k, letter & (up == ch)] = 1
+    p[5, raw == 0x2D] = 1
+    return p
+
+
 def _trunc_div2(x):
     return x // 2 if x >= 0 else -((-x) // 2)              # C++ integer division truncates toward zero
 

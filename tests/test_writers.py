@@ -173,6 +173,11 @@ def test_assemble_files_layout():
     assert [m["traceFileName"] for m in doc["msa"]] == names and doc["msa"][0]["leadingGaps"] == "2" and doc["msa"][2]["align"] == "TACGT"
     assert len(doc["gappedTraces"]) == 3 and doc["gappedTraces"][0]["leadingGaps"] == 2 and doc["gappedTraces"][1]["basecalls"]
     assert ".cons.fa" in writers.assemble_files(names, fwd, rows, b"TTACGTGAC", b"TTACGTGAC", b"IIIIIIIII", padded)
+    # reference-guided layout (src/assemble.h:284-376): traces in rank order = rows bottom-up, the reference in the last row
+    rg = writers.assemble_files(names[:2], fwd[:2], rows, b"TTACGTGAC", b"TTACGTGAC", b"IIIIIIIII", [padded[1], padded[0]], reference_last=True)
+    assert rg[".align.fa"] == ">t1 (forward)\nTTAC-TGAC\n>t2 (reverse)\n--ACGT-AC\n>Reference\n-TACGT---\n"
+    doc = json.loads(rg[".json"])
+    assert [m["reference"] for m in doc["msa"]] == [False, False, True] and doc["msa"][2]["traceFileName"] == "" and len(doc["gappedTraces"]) == 2
 
 
 def test_per_subcommand_file_sets():

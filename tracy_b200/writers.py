@@ -289,20 +289,28 @@ def aligned_trace_by_row(rows, row, trace_file_name, forward, ref):
             % ("true" if ref else "false", "true" if forward else "false", trace_file_name, lead, trail, r[lead: max(len(r) - trail, lead)] if lead < len(r) - trail else ""))
 
 
-def assemble_files(names, forward, rows, gapped, consensus, quality, padded_traces, include_consensus=False, fmt="fasta"):
-    """The output section of the de novo branch of assemble() (reference src/assemble.h:473-579). names / forward: per alignment row
-    (the reference's c.ab[idxMap[seqidx[i]]].stem() and fwd[seqidx[i]]); rows: uint8[nrow][ncol]; gapped / consensus / quality: what
-    msa.consensus returns; padded_traces: per row the dict alignment_trace_padding returns for that trace (reverse-complemented first
-    when the row is not forward). Returns {suffix: text} for .align.fa, .json, .vertical and .cons.fa | .cons.fq."""
+def assemble_files(names, forward, rows, gapped, consensus, quality, padded_traces, include_consensus=False, fmt="fasta", reference_last=False):
+    """The output section of assemble() (reference src/assemble.h:284-376 reference-guided, :473-579 de novo). names / forward: per TRACE
+    in output order (de novo: row i of the alignment, i.e. c.ab[idxMap[seqidx[i]]].stem() and fwd[seqidx[i]]; reference-guided: rank
+    order, trace i sitting in row ntraces-1-i with the reference in the last row -- pass reference_last=True); rows: uint8[nrow][ncol];
+    gapped / consensus / quality: what msa.consensus returns; padded_traces: per trace the dict alignment_trace_padding returns for its
+    row (reverse-complemented first when the trace is not forward). Returns {suffix: text} for .align.fa, .json, .vertical and
+    .cons.fa | .cons.fq."""
     a = np.asarray(rows, np.uint8)
     gapped, cs, qs = _s(gapped), _s(consensus), _s(quality)
-    fa = "".join(">%s (%s)\n%s\n" % (names[i], "forward" if forward[i] else "reverse", bytes(a[i]).decode("latin-1")) for i in range(a.shape[0]))
+    nt = len(names)
+    row_of = [nt - 1 - i for i in range(nt)] if reference_last else list(range(nt))
+    fa = "".join(">%s (%s)\n%s\n" % (names[i], "forward" if forward[i] else "reverse", bytes(a[row_of[i]]).decode("latin-1")) for i in range(nt))
+    if reference_last:
+        fa += ">Reference\n" + bytes(a[nt]).decode("latin-1") + "\n"
     if include_consensus:
         fa += ">Consensus\n" + gapped + "\n"
     js = ['{\n"gapFreeConsensus": "%s",\n"gappedConsensus": "%s",\n"msa": \n[\n' % (cs, gapped)]
-    js.append(",\n".join(aligned_trace_by_row(a, i, names[i], forward[i], False) for i in range(a.shape[0])))
+    js.append(",\n".join(aligned_trace_by_row(a, row_of[i], names[i], forward[i], False) for i in range(nt)))
+    if reference_last:
+        js.append(",\n" + aligned_trace_by_row(a, nt, "", True, True))
     js.append('],\n"gappedTraces": \n[\n')
-    js.append(", ".join(assembly_trace(padded_traces[i], names[i]) for i in range(a.shape[0])))
+    js.append(", ".join(assembly_trace(padded_traces[i], names[i]) for i in range(nt)))
     js.append("]\n}\n")
     vertical = "".join(bytes(a[:, j]).decode("latin-1") + "|" + gapped[j] + "\n" for j in range(a.shape[1]))
     out = {".align.fa": fa, ".json": "".join(js), ".vertical": vertical}

@@ -833,6 +833,80 @@ inline int assembleDenovo(TCtx& g, TConfig const& c, TSeqProfiles& inputProfiles
   return 0;
 }
 
+// assembleReference -- the DP sequence of the reference-guided branch of assemble(), reference src/assemble.h:163-282, from the
+// trace profiles on: both orientations of every trace scored against the one-hot profile of the reference (ONE batched call for
+// the 2N fills of :221-226), traces whose better score does not exceed seqsize * (matchFraction * match + (1 - matchFraction) *
+// mismatch) dropped, the rest ranked (best score first, then input index: TraceScore, :34-45) and aligned one after the other
+// against the column profile of the alignment so far (:250-281; sequential by construction). align: the traces in reverse rank
+// order, the reference in the last row. idx / fwd: input index and orientation per ranked trace. Returns the number of traces kept;
+// consensus calling on `align` is the reference's own host function (src/msa.h:162-239).
+namespace detail {
+// _createProfile(std::string, p), reference src/align.h:119-136: A, C, G, T, N (either case) and '-' have a row, anything else none.
+template <typename TProfile> inline void onehot_profile(std::string const& s, TProfile& p) {
+  resize_align(p, 6, s.size());
+  for (std::size_t j = 0; j < s.size(); ++j) {
+    for (int k = 0; k < 6; ++k) p[k][j] = 0;
+    const char ch = s[j];
+    const int k = (ch == 'A' || ch == 'a') ? 0 : (ch == 'C' || ch == 'c') ? 1 : (ch == 'G' || ch == 'g') ? 2 : (ch == 'T' || ch == 't') ? 3
+                  : (ch == 'N' || ch == 'n') ? 4 : ch == '-' ? 5 : -1;
+    if (k >= 0) p[k][j] = 1;
+  }
+}
+}  // namespace detail
+
+template <typename TCtx, typename TConfig, typename TSeqProfiles, typename TAlign>
+inline std::size_t assembleReference(TCtx& g, TConfig const& c, TSeqProfiles const& traces, std::string const& reference, TAlign& align,
+                                     std::vector<uint32_t>& idx, std::vector<bool>& fwd) {
+  typedef typename TSeqProfiles::value_type TProfile;
+  const std::size_t n = traces.size();
+  TProfile pref;
+  detail::onehot_profile(reference, pref);
+  std::vector<TProfile> rev(n);
+  std::vector<const TProfile*> a, b;
+  for (std::size_t i = 0; i < n; ++i) { a.push_back(&traces[i]); b.push_back(&pref); }
+  for (std::size_t i = 0; i < n; ++i) { detail::revcomp_profile_host(traces[i], rev[i]); a.push_back(&rev[i]); b.push_back(&pref); }
+  const std::vector<int32_t> s = gotohBatch(g, a, b, AlignConfig<true, false>(), c.aliscore);
+  struct Ranked { int32_t score; uint32_t idx; bool forward; };
+  std::vector<Ranked> rank;
+  for (std::size_t i = 0; i < n; ++i) {
+    const int32_t gsFwd = s[i], gsRev = s[n + i];
+    const double seqsize = (double)traces[i].shape()[1];
+    const double scoreThreshold = seqsize * c.matchFraction * c.aliscore.match + seqsize * (1 - c.matchFraction) * c.aliscore.mismatch;
+    if (gsFwd > scoreThreshold || gsRev > scoreThreshold) rank.push_back(Ranked{std::max(gsFwd, gsRev), (uint32_t)i, gsFwd >= gsRev});
+  }
+  std::sort(rank.begin(), rank.end(), [](Ranked const& x, Ranked const& y) { return x.score > y.score || (x.score == y.score && x.idx < y.idx); });
+  idx.clear(); fwd.clear();
+  std::vector<std::string> rows;                                        // the alignment so far; the reference row is the last one
+  for (std::size_t r = 0; r < rank.size(); ++r) {
+    const TProfile& p = rank[r].forward ? traces[rank[r].idx] : rev[rank[r].idx];
+    TProfile ap;
+    if (r) detail::profile_of_alignment(rows, ap);
+    const TProfile& target = r ? ap : pref;
+    std::vector<const TProfile*> one(1, &p), other(1, &target);
+    std::vector<std::string> ops;
+    gotohBatch(g, one, other, AlignConfig<true, false>(), c.aliscore, &ops);
+    const std::string& o = ops[0];
+    if (!r) {                                                           // row of the reference: its profile's consensus characters
+      rows.assign(1, std::string(pref.shape()[1], 'N'));
+      for (std::size_t j = 0; j < rows[0].size(); ++j) rows[0][j] = detail::profile_cons_char(pref, j);
+    }
+    std::vector<std::string> merged(rows.size() + 1, std::string(o.size(), '-'));
+    std::size_t tp = 0, ap_ = 0;
+    for (std::size_t j = 0; j < o.size(); ++j) {
+      if (o[j] != 'h') merged[0][j] = detail::profile_cons_char(p, tp++);
+      if (o[j] != 'v') { for (std::size_t k = 0; k < rows.size(); ++k) merged[k + 1][j] = rows[k][ap_]; ++ap_; }
+    }
+    rows.swap(merged);
+    idx.push_back(rank[r].idx);
+    fwd.push_back(rank[r].forward);
+  }
+  const std::size_t ncol = rows.empty() ? 0 : rows[0].size();
+  detail::resize_align(align, rows.size(), ncol);
+  for (std::size_t i = 0; i < rows.size(); ++i)
+    for (std::size_t j = 0; j < ncol; ++j) align[i][j] = rows[i][j];
+  return rank.size();
+}
+
 // ---- batch drivers: the DP sequence of sage() for many traces ---------------------------------------------------------
 // reverseComplement(std::string&), reference src/fmindex.h:11-26: reversed and upper-cased, A<->T, C<->G, N kept; any other
 // character leaves the ORIGINAL character of that slot in place (the reference's `default: break`).

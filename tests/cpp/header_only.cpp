@@ -34,5 +34,6 @@ int main() {
   msa(g, ac2, traces, align, seqidx);
   std::vector<uint32_t> idxmap;
   s += assembleDenovo(g, ac2, traces, fwd, align, seqidx, idxmap);
+  s += (int)assembleReference(g, ac2, traces, s2, align, seqidx, fwd);
   return s == 12345;
 }

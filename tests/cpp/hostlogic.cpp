@@ -218,6 +218,74 @@ int main() {
     if (!ok) { ++failures; std::printf("MISMATCH assembleDenovo #%d (num=%d)\n", rep, num); }
     else std::printf("assembleDenovo #%d: num=%d, %zu kept, %zu x %zu alignment\n", rep, num, map_new.size(), (std::size_t)al_new.shape()[0], (std::size_t)al_new.shape()[1]);
   }
+  // the reference-guided branch of assemble(): assemble() cannot be compiled here (Boost.Program_options), so the comparison side is
+  // its DP sequence (src/assemble.h:213-282) written out around the reference's own functions
+  for (int rep = 0; rep < 6; ++rep) {
+    const int L = 160 + (int)(rng() % 120), num = 1 + (int)(rng() % 5);
+    std::string reference((std::size_t)L, 'A');
+    for (auto& ch : reference) ch = "ACGT"[rng() % 4];
+    if (rep % 2 == 0) { reference[40] = 'n'; reference[41] = 'N'; reference[42] = '-'; reference[43] = 'x'; }
+    std::vector<TProfile> tr((std::size_t)num);
+    for (int i = 0; i < num; ++i) {
+      std::string s = reference.substr(rng() % (std::size_t)(L - 90), 60 + rng() % 50);
+      for (auto& ch : s) if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') ch = 'A';
+      for (int e = 0; e < 3; ++e) s[rng() % s.size()] = "ACGT"[rng() % 4];
+      if (rng() % 4 == 0) for (auto& ch : s) ch = "ACGT"[rng() % 4];
+      if (rng() % 2) { std::string r(s.rbegin(), s.rend()); for (auto& ch : r) ch = comp[ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3]; s = r; }
+      profile_of(s, tr[(std::size_t)i], 0.9f);
+    }
+    Cfg c;
+    // the reference's functions in the reference's order
+    TProfile pref;
+    tracy::_createProfile(reference, pref);
+    tracy::AlignConfig<true, false> semiglobal;
+    struct R { int32_t score, idx; bool forward; };
+    std::vector<R> rank;
+    std::vector<TProfile> prof;
+    for (int i = 0; i < num; ++i) {
+      const int32_t f = tracy::gotohScore(tr[(std::size_t)i], pref, semiglobal, c.aliscore);
+      TProfile rv;
+      tracy::reverseComplementProfile(tr[(std::size_t)i], rv);
+      const int32_t r = tracy::gotohScore(rv, pref, semiglobal, c.aliscore);
+      const double seqsize = tr[(std::size_t)i].shape()[1];
+      const double thr = seqsize * c.matchFraction * c.aliscore.match + seqsize * (1 - c.matchFraction) * c.aliscore.mismatch;
+      if (f > thr || r > thr) { rank.push_back(R{std::max(f, r), i, f >= r}); prof.push_back(f >= r ? tr[(std::size_t)i] : rv); }
+    }
+    std::vector<std::size_t> order(rank.size());
+    for (std::size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](std::size_t x, std::size_t y) { return rank[x].score > rank[y].score || (rank[x].score == rank[y].score && rank[x].idx < rank[y].idx); });
+    boost::multi_array<char, 2> al_ref;
+    for (std::size_t r = 0; r < order.size(); ++r) {
+      if (!r) { tracy::gotoh(prof[order[0]], pref, al_ref, semiglobal, c.aliscore); continue; }
+      boost::multi_array<char, 2> alNew, comb;
+      TProfile ap;
+      tracy::_createProfile(al_ref, ap);
+      tracy::gotoh(prof[order[r]], ap, alNew, semiglobal, c.aliscore);
+      const std::size_t nSeq = al_ref.shape()[0] + 1, nCol = alNew.shape()[1];
+      comb.resize(boost::extents[nSeq][nCol]);
+      std::size_t p = 0;
+      for (std::size_t j = 0; j < nCol; ++j) {
+        comb[0][j] = alNew[0][j];
+        const bool has = alNew[1][j] != '-';
+        for (std::size_t k = 1; k < nSeq; ++k) comb[k][j] = has ? al_ref[k - 1][p] : '-';
+        if (has) ++p;
+      }
+      al_ref.resize(boost::extents[nSeq][nCol]);
+      al_ref = comb;
+    }
+    cpu_double::Ctx g;
+    boost::multi_array<char, 2> al_new;
+    std::vector<uint32_t> idx_new;
+    std::vector<bool> fwd_new;
+    const std::size_t kept = tracy_b200::assembleReference(g, c, tr, reference, al_new, idx_new, fwd_new);
+    ++checks;
+    bool ok = kept == order.size() && al_ref.shape()[0] == al_new.shape()[0] && al_ref.shape()[1] == al_new.shape()[1];
+    for (std::size_t r = 0; ok && r < order.size(); ++r) ok = (int32_t)idx_new[r] == rank[order[r]].idx && fwd_new[r] == rank[order[r]].forward;
+    for (std::size_t i = 0; ok && kept && i < al_ref.shape()[0]; ++i)
+      for (std::size_t j = 0; ok && j < al_ref.shape()[1]; ++j) ok = al_ref[i][j] == al_new[i][j];
+    if (!ok) { ++failures; std::printf("MISMATCH assembleReference #%d (num=%d)\n", rep, num); }
+    else std::printf("assembleReference #%d: num=%d, %zu kept, %zu x %zu alignment\n", rep, num, kept, (std::size_t)al_new.shape()[0], (std::size_t)al_new.shape()[1]);
+  }
   std::printf("%d checks, %d mismatches\n", checks, failures);
   return failures ? 1 : 0;
 }

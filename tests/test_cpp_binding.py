@@ -22,7 +22,7 @@ def test_header_compiles_and_links_standalone(tmp_path):
 
 def test_host_logic_against_reference(tmp_path):
     """The C++ glue above the batched DP calls (revSeqBasedOnDist with grouped trials, matchingTraces, msa = UPGMA + level-wise
-    progressive alignment) with a CPU double of the context served by the reference's own gotohScore / gotoh, against the
+    progressive alignment, assembleDenovo, assembleReference) with a CPU double of the context served by the reference's own gotohScore / gotoh, against the
     reference's functions: tests/cpp/hostlogic.cpp, compiled with the unmodified reference headers where they exist."""
     ref = "/root/reference/src"
     if not os.path.isdir(ref):
@@ -36,7 +36,7 @@ def test_host_logic_against_reference(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "34 checks, 0 mismatches" in r.stdout, r.stdout[-3000:]
+    assert r.returncode == 0 and "40 checks, 0 mismatches" in r.stdout, r.stdout[-3000:]
 
 
 @pytest.mark.gpu

@@ -99,6 +99,11 @@ int tb_ctx_last_call_ms(const tb_ctx* ctx, float* device_ms);
  * ranges outside its exact range) went through the general int32 kernel. Results are identical either way. */
 int tb_ctx_last_packed_pairs(const tb_ctx* ctx, uint64_t* pairs);
 
+/* For the most recent tb_gotoh_pp call: how many pairs were "big", i.e. spread over many warps as (pair, band) work units with
+ * the bands pipelined through a per-pair row buffer (progressive MSA merges of tens of thousands of columns, reference
+ * src/msa.h:116), instead of one warp per pair. tb_ctx_last_packed_pairs counts the pairs the fp32x2 profile kernel completed. */
+int tb_ctx_last_big_pairs(const tb_ctx* ctx, uint64_t* pairs);
+
 /* ---- gotohScore / gotoh ---------------------------------------------------------------------------------
  * _ps : a1 = trace profile float[6][m], a2 = reference SEQUENCE. Semantics are those of the reference when it
  *       aligns against _createProfile(std::string) (src/align.h:121-136), as src/sage.h:233-258,

@@ -154,6 +154,12 @@ class Context:
         self._check(self._lib.tb_ctx_last_packed_pairs(self._h, C.byref(v)))
         return v.value
 
+    def last_big_pairs(self):
+        """Pairs of the last "pp" call that were spread over many warps (band-pipelined big pairs)."""
+        v = C.c_uint64()
+        self._check(self._lib.tb_ctx_last_big_pairs(self._h, C.byref(v)))
+        return v.value
+
     # ---- reference anchoring (reference src/fmindex.h:173-326) -------------------------------------------------
     def build_index(self, text):
         """Index of the reference text for anchor(): `text` is what tracy indexes (upper-cased; a multi-sequence genome joined and

@@ -12,7 +12,7 @@ TB_MEM_HOST, TB_MEM_DEVICE = 0, 1
 # every symbol include/tracy_b200.h declares (tests/test_boundary.py checks the header against this list)
 SYMBOLS = [
     "tb_ctx_create", "tb_ctx_destroy", "tb_strerror", "tb_last_error", "tb_host_alloc", "tb_host_free",
-    "tb_ctx_set_scratch_limit", "tb_ctx_stats", "tb_ctx_last_kernel_ms", "tb_ctx_last_call_ms", "tb_ctx_last_packed_pairs", "tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss",
+    "tb_ctx_set_scratch_limit", "tb_ctx_stats", "tb_ctx_last_kernel_ms", "tb_ctx_last_call_ms", "tb_ctx_last_packed_pairs", "tb_ctx_last_big_pairs", "tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss",
     "tb_rows_from_ops", "tb_decompose_sweep", "tb_version", "tb_create_profile", "tb_revcomp_profile", "tb_trim_reference_slice",
     "tb_find_breakpoint", "tb_basecall", "tb_index_build", "tb_index_destroy", "tb_index_info", "tb_anchor", "tb_ctx_last_anchor_ms",
     "tb_reference_slice", "tb_allelic_fraction", "tb_ctx_last_fraction_ms", "tb_trace_scan", "tb_trace_unpack",
@@ -106,6 +106,7 @@ def lib():
     L.tb_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.tb_ctx_last_call_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.tb_ctx_last_packed_pairs.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.tb_ctx_last_big_pairs.argtypes = [vp, C.POINTER(C.c_uint64)]
     for name in ("tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss"):
         getattr(L, name).argtypes = [vp, C.POINTER(Batch), Score, AlignConfig, C.POINTER(Result)]
     L.tb_rows_from_ops.argtypes = [C.c_int, vp, C.c_int32, vp, C.c_int32, vp, C.c_int32, vp, vp]

@@ -22,6 +22,9 @@ cudaError_t gotoh_packed_blocks_per_sm(int tbmode, int classes, int* out);
 int gotoh_packed_warps_per_block();
 bool gotoh_packed_eligible(int maxm, int maxn, int match, int mismatch, int go, int ge);
 unsigned long long gotoh_packed_ptr_words(int m, int n);
+cudaError_t launch_gotoh_pp(int nch, bool traceback, bool harr, const GotohBatch& B, const PPWork& W, int blocks, cudaStream_t stream);
+cudaError_t gotoh_pp_blocks_per_sm(int nch, bool traceback, bool harr, int* out);
+int gotoh_pp_warps_per_block();
 
 
 cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
@@ -74,6 +77,8 @@ struct PinBuf {
 };
 
 struct Plan {
+  bool use_pp = false, pp_harr = false;    // profile x profile: the fp32x2 kernel (gotoh_pp.cu) ahead of the general one
+  int blocks_pp = 0, blocks_pp5 = 0;
   bool use_packed = false;
   int tbmode = 0;                          // packed kernel traceback mode: 0 none, 1 flags, 2 checkpoints (default)
   int blocks_packed = 0, blocks_packed5 = 0, blocks_general = 0;   // packed: 4-class (ACGT) and 5-class (ACGTN) instantiations
@@ -87,6 +92,9 @@ struct Lane {   // one in-flight chunk of a TB_MEM_HOST batch
   cudaEvent_t h0 = nullptr, d1 = nullptr;                               // host-mode chunk: before its H2D, after its D2H (TRACY_B200_TRACE)
   DevBuf a, b, meta_d, scores, ops, ops_len, status, counter;
   DevBuf ptr, rowbuf, opsrev;
+  DevBuf pp_units, pp_small, pp_big, pp_rowbuf, pp_ptr, pp_flags;   // big-pair work list and scratch of the profile x profile kernel
+  PinBuf pp_stage;
+  tb::PPWork ppw{};
   PinBuf meta, cnt;
   bool timed = false, timed2 = false;
   cudaEvent_t kend = nullptr;        // the event after the last kernel enqueued for the lane's current call/chunk
@@ -112,6 +120,8 @@ struct tb_ctx {
   std::vector<int32_t> tmp_len1, tmp_len2;
   int occ_general[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};   // blocks per SM, general kernel [mode][traceback]
   int occ_packed[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};    // packed kernel [tbmode][4 / 5 classes]
+  int occ_pp[2][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};   // profile x profile kernel [4 / 5 channels][traceback][register-array variant]
+  uint64_t last_pp_pairs = 0, last_big_pairs = 0;
   size_t free_at_first_plan = 0;
 };
 
@@ -141,20 +151,23 @@ inline unsigned long long general_ptr_words(int m, int n) {
   unsigned long long nb = (unsigned long long)(m + 511) / 512;
   return nb * (unsigned long long)(n + 31) * 32ull;
 }
-void accumulate(Shape& s, const int32_t* l1, const int32_t* l2, size_t n, bool packed) {
+// big (optional): pairs that the profile x profile kernel spreads over many warps with per-pair scratch; they do not size
+// the per-warp-slot pointer scratch
+void accumulate(Shape& s, const int32_t* l1, const int32_t* l2, size_t n, bool packed, const uint8_t* big = nullptr) {
   for (size_t i = 0; i < n; ++i) {
     const int m = l1[i], k = l2[i];
     s.maxm = std::max(s.maxm, m);
     s.maxn = std::max(s.maxn, k);
     s.maxsum = std::max(s.maxsum, m + k);
-    s.gen_words = std::max(s.gen_words, general_ptr_words(m, k));
+    if (!big || !big[i]) s.gen_words = std::max(s.gen_words, general_ptr_words(m, k));
     if (packed) s.packed_words = std::max(s.packed_words, tb::gotoh_packed_ptr_words(m, k));
   }
 }
 
 
 // Size the persistent grids and the per-slot scratch for a launch over `npairs` pairs with maxima `sh`.
-int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npairs, tb_score sc, Plan* out) {
+// pp_tickets: work units of the profile x profile kernel (whole small pairs + bands of big pairs); 0 = npairs.
+int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npairs, tb_score sc, Plan* out, size_t pp_tickets = 0) {
   Plan p;
   // occupancy answers never change for a context: ask the runtime once per instantiation (a small call should not pay
   // five occupancy queries and a cudaMemGetInfo every time)
@@ -165,6 +178,21 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
   p.use_packed = (mode == tb::kModePS || mode == tb::kModeSS) &&   // string x string: a1's characters act as one-hot profile columns
                  tb::gotoh_packed_eligible(sh.maxm, sh.maxn, sc.match, sc.mismatch, sc.gap_open, sc.gap_extend) &&
                  getenv("TRACY_B200_NO_PACKED") == nullptr;
+  unsigned long long warps_pp = 0;
+  const int wpb_pp = tb::gotoh_pp_warps_per_block();
+  if (mode == tb::kModePP && getenv("TRACY_B200_NO_PPFAST") == nullptr) {
+    const char* v = getenv("TRACY_B200_PP_VARIANT");          // "arr": free-row costs in register arrays (2 blocks / SM) instead of selects (3 blocks / SM)
+    p.pp_harr = v && std::strcmp(v, "arr") == 0;
+    int& o4 = ctx->occ_pp[0][traceback ? 1 : 0][p.pp_harr ? 1 : 0];
+    int& o5 = ctx->occ_pp[1][traceback ? 1 : 0][p.pp_harr ? 1 : 0];
+    if (o4 < 0) TB_CUDA(ctx, tb::gotoh_pp_blocks_per_sm(4, traceback, p.pp_harr, &o4));
+    if (o5 < 0) TB_CUDA(ctx, tb::gotoh_pp_blocks_per_sm(5, traceback, p.pp_harr, &o5));
+    if (o4 >= 1 && o5 >= 1) {
+      p.use_pp = true;
+      p.blocks_pp = ctx->sms * o4; p.blocks_pp5 = ctx->sms * o5;
+      warps_pp = (unsigned long long)std::max(p.blocks_pp, p.blocks_pp5) * wpb_pp;
+    }
+  }
   int bps_p = 0, bps_p5 = 0, wpb_p = 1;
   if (p.use_packed) {
     const char* mode_env = getenv("TRACY_B200_TB_MODE");   // "flags" selects the pointer-flag fill (kept for comparison / profiling)
@@ -202,11 +230,18 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
   warps_g = std::min(warps_g, max_slots);
   warps_p = std::min(warps_p, max_slots);
   warps_p5 = std::min(warps_p5, max_slots);
+  if (p.use_pp) {   // cut to the number of work units, not pairs: a big pair is many units (bands), each taken by a warp
+    warps_pp = std::min<unsigned long long>(warps_pp, std::max<size_t>(pp_tickets ? pp_tickets : npairs, 1));
+    warps_pp = std::min(warps_pp, max_slots);
+    const int cap = (int)((warps_pp + wpb_pp - 1) / wpb_pp);
+    p.blocks_pp = std::min(p.blocks_pp, cap); p.blocks_pp5 = std::min(p.blocks_pp5, cap);
+  }
   p.blocks_general = (int)((warps_g + wpb_g - 1) / wpb_g);
   p.blocks_packed = p.use_packed ? (int)((warps_p + wpb_p - 1) / wpb_p) : 0;
   p.blocks_packed5 = p.use_packed ? (int)((warps_p5 + wpb_p - 1) / wpb_p) : 0;
   p.slots = (unsigned)std::max<unsigned long long>((unsigned long long)p.blocks_general * wpb_g,
                                                    (unsigned long long)std::max(p.blocks_packed, p.blocks_packed5) * wpb_p);
+  if (p.use_pp) p.slots = std::max<unsigned>(p.slots, (unsigned)std::max(p.blocks_pp, p.blocks_pp5) * wpb_pp);
   *out = p;
   return TB_OK;
 }
@@ -216,6 +251,84 @@ int reserve_scratch(tb_ctx* ctx, Lane& L, const Plan& p) {
   TB_CUDA(ctx, L.rowbuf.reserve((size_t)(p.rowbuf_elems * 8ull * p.slots)));
   TB_CUDA(ctx, L.opsrev.reserve((size_t)(p.ops_bytes * p.slots)));
   TB_CUDA(ctx, L.counter.reserve(64));
+  return TB_OK;
+}
+
+// ---- profile x profile: big pairs (one pair over many warps, gotoh_pp.cu) ---------------------------------------------
+constexpr int kPPBandRows = 512;
+inline int pp_bands(int m) { return (m + kPPBandRows - 1) / kPPBandRows; }
+
+// big[i] = 1: pair i is cut into (pair, band) units. A pair on one warp takes bands x columns steps whatever else the GPU
+// does, so when the call cannot fill the machine with whole pairs, every pair of three bands or more is spread out; in a
+// large batch only outliers are (sixteen bands or more). The per-pair scratch (bottom row per band, pointer words) of the
+// pairs chosen stays within `budget` bytes, largest pairs first. Returns the number of work units (tickets).
+size_t classify_pp(const tb_ctx* ctx, const int32_t* l1, const int32_t* l2, size_t np, bool traceback, size_t budget, std::vector<uint8_t>& big) {
+  big.assign(np, 0);
+  const size_t machine = (size_t)ctx->sms * 12;
+  const int min_bands = np >= 2 * machine ? 16 : 3;
+  std::vector<size_t> cand;
+  for (size_t i = 0; i < np; ++i)
+    if (l1[i] > 0 && l2[i] >= 256 && pp_bands(l1[i]) >= min_bands) cand.push_back(i);
+  std::sort(cand.begin(), cand.end(), [&](size_t x, size_t y) {
+    const long long cx = (long long)l1[x] * l2[x], cy = (long long)l1[y] * l2[y];
+    return cx != cy ? cx > cy : x < y;
+  });
+  size_t used = 0, units = np;
+  for (size_t i : cand) {
+    const size_t nb = (size_t)pp_bands(l1[i]);
+    const size_t need = nb * ((size_t)l2[i] + 1) * 8 + (traceback ? nb * ((size_t)l2[i] + 31) * 256 : 0) + nb * 4;
+    if (used + need > budget) continue;
+    used += need; big[i] = 1; units += nb - 1;
+  }
+  return units;
+}
+
+// Work list and per-pair scratch of the big pairs of one launch (pairs p0 .. p0+cn-1 of the call, indices relative to p0).
+int build_pp_work(tb_ctx* ctx, Lane& L, const int32_t* l1, const int32_t* l2, const uint8_t* big, size_t cn, bool traceback) {
+  tb::PPWork W{};
+  W.one = 1.0f; W.nsmall = (int)cn;
+  size_t nbig = 0, nunits = 0;
+  if (big) for (size_t i = 0; i < cn; ++i) if (big[i]) { ++nbig; nunits += (size_t)pp_bands(l1[i]); }
+  if (nbig == 0) { L.ppw = W; return TB_OK; }
+  const size_t nsmall = cn - nbig;
+  const size_t o_units = 0, o_small = o_units + nunits * sizeof(tb::PPUnit), o_big = (o_small + nsmall * 4 + 15) & ~(size_t)15, total = o_big + nbig * sizeof(tb::PPBig);
+  TB_CUDA(ctx, L.pp_stage.reserve(total));
+  char* h = static_cast<char*>(L.pp_stage.p);
+  tb::PPUnit* hu = reinterpret_cast<tb::PPUnit*>(h + o_units);
+  int32_t* hs = reinterpret_cast<int32_t*>(h + o_small);
+  tb::PPBig* hb = reinterpret_cast<tb::PPBig*>(h + o_big);
+  std::vector<size_t> order;
+  for (size_t i = 0; i < cn; ++i) if (big[i]) order.push_back(i);
+  std::sort(order.begin(), order.end(), [&](size_t x, size_t y) {            // largest first: its pipeline is the longest
+    const long long cx = (long long)l1[x] * l2[x], cy = (long long)l1[y] * l2[y];
+    return cx != cy ? cx > cy : x < y;
+  });
+  long long rows = 0, words = 0; int flags = 0; size_t u = 0;
+  for (size_t k = 0; k < order.size(); ++k) {
+    const size_t i = order[k];
+    const int nb = pp_bands(l1[i]);
+    hb[k].rowbuf_off = rows; hb[k].ptr_off = words; hb[k].flag_off = flags; hb[k].nb = nb;
+    rows += (long long)nb * (l2[i] + 1);
+    if (traceback) words += (long long)nb * (l2[i] + 31) * 32;
+    flags += nb;
+    for (int b = 0; b < nb; ++b) hu[u++] = tb::PPUnit{(int32_t)i, b, (int32_t)k, 0};
+  }
+  size_t ns = 0;
+  for (size_t i = 0; i < cn; ++i) if (!big[i]) hs[ns++] = (int32_t)i;
+  TB_CUDA(ctx, L.pp_units.reserve(total));
+  TB_CUDA(ctx, L.pp_rowbuf.reserve((size_t)rows * 8 + 64));
+  TB_CUDA(ctx, L.pp_ptr.reserve((size_t)words * 8 + 64));
+  TB_CUDA(ctx, L.pp_flags.reserve((size_t)flags * 4 + 64));
+  TB_CUDA(ctx, cudaMemcpyAsync(L.pp_units.p, h, total, cudaMemcpyHostToDevice, L.stream));
+  TB_CUDA(ctx, cudaMemsetAsync(L.pp_flags.p, 0, (size_t)flags * 4, L.stream));
+  ctx->h2d += total;
+  char* d = L.pp_units.as<char>();
+  W.units = reinterpret_cast<const tb::PPUnit*>(d + o_units); W.nunits = (int)nunits;
+  W.small_ids = reinterpret_cast<const int32_t*>(d + o_small); W.nsmall = (int)nsmall;
+  W.big = reinterpret_cast<const tb::PPBig*>(d + o_big);
+  W.big_rowbuf = L.pp_rowbuf.as<int2>(); W.big_ptr = L.pp_ptr.as<unsigned long long>(); W.big_flags = L.pp_flags.as<int>();
+  L.ppw = W;
+  ctx->last_big_pairs += nbig;
   return TB_OK;
 }
 
@@ -241,6 +354,13 @@ int enqueue_gotoh(tb_ctx* ctx, Lane& L, int mode, bool traceback, tb::GotohBatch
     TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
     L.timed = true;
     L.kend = L.k1;
+  } else if (p.use_pp) {
+    TB_CUDA(ctx, cudaEventRecord(L.k0, L.stream));
+    B.counter = counters;           // [0] ticket counter, [1] pairs completed by the 4-channel kernel
+    TB_CUDA(ctx, tb::launch_gotoh_pp(4, traceback, p.pp_harr, B, L.ppw, p.blocks_pp, L.stream));
+    TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
+    L.timed = true;
+    L.kend = L.k1;
   } else {
     TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
     B.counter = counters + 8;
@@ -262,7 +382,7 @@ int collect_timing(tb_ctx* ctx, Lane& L);
 // (the caller then repeats its D2H of the results).
 int finish_gotoh(tb_ctx* ctx, Lane& L, bool* ran) {
   *ran = false;
-  if (!L.plan.use_packed || !L.timed) return TB_OK;
+  if ((!L.plan.use_packed && !L.plan.use_pp) || !L.timed) return TB_OK;
   const unsigned int* cnt = static_cast<const unsigned int*>(L.cnt.p);
   if (cnt[1] >= (unsigned)L.view.npairs) return TB_OK;
   if (int rc = collect_timing(ctx, L)) return rc;          // stage 1's events are about to be re-recorded
@@ -270,7 +390,8 @@ int finish_gotoh(tb_ctx* ctx, Lane& L, bool* ran) {
   tb::GotohBatch B = L.view;
   TB_CUDA(ctx, cudaEventRecord(L.k0, L.stream));
   B.counter = counters + 2;       // second queue head; its completion count lands in counters[3]
-  TB_CUDA(ctx, tb::launch_gotoh_packed(L.plan.tbmode, 5, B, L.plan.blocks_packed5, L.stream));
+  if (L.plan.use_pp) TB_CUDA(ctx, tb::launch_gotoh_pp(5, L.traceback, L.plan.pp_harr, B, L.ppw, L.plan.blocks_pp5, L.stream));
+  else TB_CUDA(ctx, tb::launch_gotoh_packed(L.plan.tbmode, 5, B, L.plan.blocks_packed5, L.stream));
   TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
   B.counter = counters + 8;
   TB_CUDA(ctx, tb::launch_gotoh_general(L.mode, L.traceback, B, L.plan.blocks_general, L.stream));
@@ -333,8 +454,22 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   }
   for (size_t i = 0; i < np; ++i)
     if (l1[i] < 0 || l2[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative length");
+  // profile x profile: which pairs are spread over many warps (per-pair scratch instead of per-slot scratch)
+  std::vector<uint8_t> big;
+  size_t pp_tickets = 0;
+  ctx->last_big_pairs = 0;
+  if (mode == tb::kModePP && getenv("TRACY_B200_NO_PPFAST") == nullptr && getenv("TRACY_B200_NO_BIG") == nullptr) {
+    if (ctx->free_at_first_plan == 0) {
+      size_t fr = 0, tot = 0;
+      TB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+      ctx->free_at_first_plan = fr;
+    }
+    const size_t budget = (ctx->scratch_limit ? ctx->scratch_limit : ctx->free_at_first_plan / 3) / 2;
+    pp_tickets = classify_pp(ctx, l1, l2, np, traceback, budget, big);
+  }
+  const uint8_t* bigp = big.empty() ? nullptr : big.data();
   Shape all;
-  accumulate(all, l1, l2, np, mode != tb::kModePP);
+  accumulate(all, l1, l2, np, mode != tb::kModePP, bigp);
   if (traceback && res->ops_stride < all.maxsum) return fail(ctx, TB_ERR_INVALID, "ops_stride smaller than max(len1+len2)");
   if (int rc = check_range(ctx, all, sc)) return rc;
 
@@ -347,8 +482,9 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   if (batch->mem == TB_MEM_DEVICE) {
     Lane& L = ctx->lanes[0];
     Plan plan;
-    if (int rc = make_plan(ctx, mode, traceback, all, np, sc, &plan)) return rc;
+    if (int rc = make_plan(ctx, mode, traceback, all, np, sc, &plan, pp_tickets)) return rc;
     if (int rc = reserve_scratch(ctx, L, plan)) return rc;
+    if (plan.use_pp) if (int rc = build_pp_work(ctx, L, l1, l2, bigp, np, traceback)) return rc;
     TB_CUDA(ctx, L.status.reserve(np));
     B.a_base = batch->a1.base; B.a_off = batch->a1.off; B.a_len = batch->a1.len;
     B.b_base = batch->a2.base; B.b_off = batch->a2.off; B.b_len = batch->a2.len;
@@ -365,7 +501,7 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
 
   // ---- TB_MEM_HOST: chunks pipelined over kLanes streams, each H2D -> kernels -> D2H ----
   Plan plan;
-  if (int rc = make_plan(ctx, mode, traceback, all, np, sc, &plan)) return rc;
+  if (int rc = make_plan(ctx, mode, traceback, all, np, sc, &plan, pp_tickets)) return rc;
   // A chunk is a whole number of waves of the persistent grid (pairs of one batch cost about the same, so a
   // chunk then ends without a tail of idle warp slots), about an eighth of the batch, inputs <= 768 MiB.
   const size_t wave = std::max<size_t>(plan.slots, 1);
@@ -422,6 +558,9 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     L.chunk = -1;
     return collect_timing(ctx, L);
   };
+  // The chunk pipeline as one unit: on ANY error the lanes still hold kernels and D2H copies into the caller's buffers, so they
+  // are drained before the error is returned (the caller may free those buffers right away).
+  auto pipeline = [&]() -> int {
   size_t nchunks = 0;
   for (size_t ci = 0, p0 = 0; p0 < np; ++ci, ++nchunks) {
     Lane& L = ctx->lanes[ci % nlanes];
@@ -437,9 +576,13 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     }
     const size_t abytes = (size_t)(amax - amin) * esa, bbytes = (size_t)(bmax - bmin) * esb;
     Plan cp = plan;                                       // scratch per slot sized for the batch maxima, once
-    if (cn < (size_t)plan.slots)
-      if (int rc = make_plan(ctx, mode, traceback, all, cn, sc, &cp)) return rc;
+    if (cn < (size_t)plan.slots) {
+      size_t tickets = cn;
+      if (bigp) for (size_t i = p0; i < p0 + cn; ++i) if (bigp[i]) tickets += (size_t)pp_bands(l1[i]) - 1;
+      if (int rc = make_plan(ctx, mode, traceback, all, cn, sc, &cp, tickets)) return rc;
+    }
     if (int rc = reserve_scratch(ctx, L, cp)) return rc;
+    if (cp.use_pp) if (int rc = build_pp_work(ctx, L, l1 + p0, l2 + p0, bigp ? bigp + p0 : nullptr, cn, traceback)) return rc;
     TB_CUDA(ctx, L.a.reserve(abytes + 16)); TB_CUDA(ctx, L.b.reserve(bbytes + 16));
     TB_CUDA(ctx, L.scores.reserve(cn * 4)); TB_CUDA(ctx, L.status.reserve(cn));
     if (traceback) { TB_CUDA(ctx, L.ops.reserve(cn * (size_t)res->ops_stride)); TB_CUDA(ctx, L.ops_len.reserve(cn * 4)); }
@@ -481,6 +624,15 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   for (size_t k = 0; k < (size_t)nlanes; ++k)            // retire in issue order
     if (int rc = retire(ctx->lanes[(nchunks + k) % nlanes])) return rc;
   return TB_OK;
+  };
+  const int prc = pipeline();
+  if (prc != TB_OK) {
+    const std::string keep = ctx->err;
+    for (int i = 0; i < kLanes; ++i) { cudaStreamSynchronize(ctx->lanes[i].stream); ctx->lanes[i].chunk = -1; ctx->lanes[i].timed = ctx->lanes[i].timed2 = false; }
+    cudaGetLastError();
+    ctx->err = keep;
+  }
+  return prc;
 }
 
 char cons_char(const float* p, int len, int pos) {
@@ -548,9 +700,10 @@ void tb_ctx_destroy(tb_ctx* c) {
   for (int i = 0; i < kLanes; ++i) {
     Lane& L = c->lanes[i];
     if (L.stream) cudaStreamSynchronize(L.stream);
-    DevBuf* bufs[] = {&L.a, &L.b, &L.meta_d, &L.scores, &L.ops, &L.ops_len, &L.status, &L.counter, &L.ptr, &L.rowbuf, &L.opsrev};
+    DevBuf* bufs[] = {&L.a, &L.b, &L.meta_d, &L.scores, &L.ops, &L.ops_len, &L.status, &L.counter, &L.ptr, &L.rowbuf, &L.opsrev,
+                      &L.pp_units, &L.pp_small, &L.pp_big, &L.pp_rowbuf, &L.pp_ptr, &L.pp_flags};
     for (DevBuf* b : bufs) b->release();
-    L.meta.release(); L.cnt.release();
+    L.meta.release(); L.cnt.release(); L.pp_stage.release();
     if (L.c0) cudaEventDestroy(L.c0);
     if (L.k0) cudaEventDestroy(L.k0);
     if (L.k1) cudaEventDestroy(L.k1);
@@ -603,6 +756,12 @@ int tb_ctx_last_call_ms(const tb_ctx* ctx, float* device_ms) {
 int tb_ctx_last_packed_pairs(const tb_ctx* ctx, uint64_t* pairs) {
   if (!ctx || !pairs) return TB_ERR_INVALID;
   *pairs = ctx->last_packed_pairs;
+  return TB_OK;
+}
+
+int tb_ctx_last_big_pairs(const tb_ctx* ctx, uint64_t* pairs) {
+  if (!ctx || !pairs) return TB_ERR_INVALID;
+  *pairs = ctx->last_big_pairs;
   return TB_OK;
 }
 

@@ -38,6 +38,20 @@ struct GotohBatch {
   int a_is_seq;                                                        // packed kernel: a1 items are strings (string x string pairs), not profiles
 };
 
+// Work list of the profile x profile kernel (gotoh_pp.cu). Tickets 0 .. nunits-1 are (pair, band) units of "big" pairs
+// (one pair spread over many warps, bands in increasing order per pair); tickets nunits .. nunits+nsmall-1 are whole pairs.
+struct PPUnit { int32_t pair, band, big, pad; };
+struct PPBig { long long rowbuf_off, ptr_off; int32_t flag_off, nb; };   // offsets into PPWork::big_rowbuf / big_ptr / big_flags
+struct PPWork {
+  const PPUnit* units; int nunits;
+  const int32_t* small_ids; int nsmall;        // small_ids == nullptr: pairs 0 .. nsmall-1
+  const PPBig* big;
+  int2* big_rowbuf;                            // per big pair: nb x (n + 1) bottom rows (S, V)
+  unsigned long long* big_ptr;                 // per big pair: nb x (n + 31) x 32 pointer words (traceback only)
+  int* big_flags;                              // per big pair: nb progress words (columns of the bottom row published), zeroed per call
+  float one;                                   // 1.0f, as a run-time value (see gotoh_pp.cu)
+};
+
 // Device view of a decompose-sweep batch (sweep.cu).
 struct SweepBatch {
   const char* ref_base; const int64_t* ref_off; const int32_t* ref_len;

@@ -54,5 +54,10 @@ def broadcast_genome_and_index(ctx, text_tensor, src=0, group=None):
     GPU; the other ranks pass a tensor of the same size), one NCCL broadcast over NVLink ships it, and every rank builds its
     own anchoring index from the device copy (17 ms per 64 Mbp -- cheaper than shipping the 17 B/char index itself).
     Returns the rank's KmerIndex."""
+    import torch
     broadcast_reference(text_tensor, src=src, group=group)
+    # dist.broadcast only enqueues (NCCL's stream on the GPU box); the index build copies the text on the context's own
+    # non-blocking stream, which is ordered against neither NCCL's nor torch's: wait for the text to have landed first.
+    if text_tensor.is_cuda:
+        torch.cuda.synchronize(text_tensor.device)
     return ctx.build_index_device(text_tensor.data_ptr(), text_tensor.numel())

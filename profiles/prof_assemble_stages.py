@@ -33,12 +33,21 @@ def stage(name, fn):
 
 
 fwd = [True] * N
-stage("revSeqBasedOnDist", lambda: msa.rev_seq_based_on_dist(ctx, profs, fwd, sc))
-keep = stage("exclude_unmatched", lambda: msa.exclude_unmatched(ctx, profs, sc, 0.5))
-kept = [profs[i] for i, k in enumerate(keep) if k]
-d = stage("distance_matrix", lambda: msa.distance_matrix(ctx, kept, sc))
-phylo, root = stage("upgma", lambda: msa.upgma(d, len(kept)))
+t_all = time.perf_counter()
+T = stage("orientation_table", lambda: msa.orientation_table(ctx, profs, sc))
+out["orientation_table"]["pairs"] = 4 * N * (N - 1)
+out["orientation_table"]["kernel_ms"] = sum(ctx.last_kernel_ms()[k] for k in ("packed_ms", "general_ms"))
+d, T, o = stage("revSeqBasedOnDist_replay", lambda: msa.rev_seq_based_on_dist(ctx, profs, fwd, sc, table=T, with_state=True))
+keep = stage("exclude_unmatched", lambda: msa.exclude_unmatched(ctx, profs, sc, 0.5, dist=d))
+idx = [i for i, k in enumerate(keep) if k]
+kept = [profs[i] for i in idx]
+dm = stage("distance_matrix_from_table", lambda: msa.oriented_distance(T, o, idx))
+phylo, root = stage("upgma", lambda: msa.upgma(dm, len(kept)))
 rows, _, seqidx = stage("palign", lambda: msa.palign(ctx, kept, phylo, root, sc))
 stage("consensus", lambda: msa.consensus(rows, 0.01, False))
+out["total_seconds"] = round(time.perf_counter() - t_all, 3)
+out["total_kernel_launches"] = sum(v["kernel_launches"] for v in out.values() if isinstance(v, dict))
 out["msa_columns"] = int(rows.shape[1])
+out["traces_kept"] = len(kept)
+out["flipped"] = int(sum(1 for f in fwd if not f))
 print(json.dumps(out))

@@ -102,6 +102,31 @@ def run_msa_case(ctx, idx):
     assert gapped == bytes(GOLD[f"ms_gapped{idx}"]) and cs == bytes(GOLD[f"ms_cons{idx}"]) and qs == bytes(GOLD[f"ms_qual{idx}"])
 
 
+def run_assemble64(ctx):
+    """N = 64 overlapping traces, 24 of them planted reverse-complemented (tests/golden/make_golden_assemble64.py: the reference's
+    revSeqBasedOnDist -> msa -> consensus): orientation vector, distance matrix, leaf order (the guide tree's post-order), every
+    alignment row and the consensus through drivers.assemble_denovo -- orientation table, score-ordered exclusion, table-fed msa."""
+    from tracy_b200 import drivers
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "assemble64_golden.npz"))
+    n = int(g["n"])
+    profs = [g[f"p{k}"].copy() for k in range(n)]
+    T = msa.orientation_table(ctx, profs, DnaScore(*SC))
+    r = drivers.assemble_denovo(ctx, profs, DnaScore(*SC), 0.5, 0.05, table=T)
+    assert r["forward"] == [bool(x) for x in g["fwd"]]
+    assert r["kept"] == list(range(n))
+    assert list(r["seqidx"]) == list(g["seqidx"])
+    assert np.array_equal(r["rows"], g["rows"])
+    assert (r["gapped"], r["consensus"], r["quality"]) == (bytes(g["gapped"]), bytes(g["cons"]), bytes(g["qual"]))
+    # the table-fed distance matrix is the one distanceMatrix() computes on the oriented traces
+    fwd = [True] * n
+    d, T, o = msa.rev_seq_based_on_dist(ctx, [p.copy() for p in profs], fwd, DnaScore(*SC), table=T, with_state=True)
+    assert np.array_equal(np.triu(msa.oriented_distance(T, o), 1), np.triu(g["dist"], 1))
+
+
+def test_assemble64_host_logic(oracle_port):
+    run_assemble64(OracleContext(oracle_port))
+
+
 def test_reverse_complement_seq(oracle_ref):
     """drivers.reverse_complement_seq against reverseComplement(std::string&) (src/fmindex.h:11-26), incl. its quirk for
     characters outside ACGTN; the three fixed cases were produced by the reference."""

@@ -54,6 +54,13 @@ def test_msa_pipeline_gpu(ctx, idx):
     run_msa_case(ctx, idx)
 
 
+def test_assemble64_gpu(ctx):
+    """SURVEY section 8d-4 at N = 64: orientation vector, distance matrix, leaf order, MSA rows and consensus equal the reference's."""
+    from test_glue import run_assemble64
+    run_assemble64(ctx)
+    assert ctx.stats()["kernel_launches"] > 0
+
+
 def test_exclude_unmatched(ctx, oracle_port):
     """The exclusion loop of assemble() (src/assemble.h:428-448): a stray trace is dropped, overlapping ones are kept;
     the batched rounds give the same booleans as the reference's first-hit scan done with the CPU oracle."""

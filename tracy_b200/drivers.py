@@ -273,18 +273,20 @@ def decompose_batch(ctx, traces, bcpos, primaries, secondaries, references, sc=D
     return out
 
 
-def assemble_denovo(ctx, profiles, sc=DnaScore(3, -5, -10, -4), match_fraction=0.5, fraction_called=0.1):
+def assemble_denovo(ctx, profiles, sc=DnaScore(3, -5, -10, -4), match_fraction=0.5, fraction_called=0.1, table=None):
     """The de novo branch of `tracy assemble` from the trace profiles on (reference src/assemble.h:418-471):
     revSeqBasedOnDist -> exclusion of traces that match nothing -> msa -> consensus.
-    Returns dict(forward, kept (indices into `profiles`), rows, seqidx (into kept), gapped, consensus, quality)."""
+    Returns dict(forward, kept (indices into `profiles`), rows, seqidx (into kept), gapped, consensus, quality).
+    table: msa.orientation_table(ctx, profiles, sc) when the caller already holds it."""
     profs = [np.ascontiguousarray(p, np.float32).copy() for p in profiles]
     fwd = [True] * len(profs)
-    msa.rev_seq_based_on_dist(ctx, profs, fwd, sc)                          # src/assemble.h:422
-    keep = msa.exclude_unmatched(ctx, profs, sc, match_fraction)            # src/assemble.h:428-458
+    d, table, orient = msa.rev_seq_based_on_dist(ctx, profs, fwd, sc, table=table, with_state=True)   # src/assemble.h:422
+    keep = msa.exclude_unmatched(ctx, profs, sc, match_fraction, dist=d)    # src/assemble.h:428-458
     kept = [i for i, k in enumerate(keep) if k]
     if len(kept) < 2:
         return dict(forward=fwd, kept=kept, rows=None, seqidx=[], gapped=b"", consensus=b"", quality=b"")
-    rows, seqidx, _ = msa.msa(ctx, [profs[i] for i in kept], sc)            # src/assemble.h:468
+    # msa()'s distanceMatrix (src/msa.h:33-42) asks for scores the orientation table already holds
+    rows, seqidx, _ = msa.msa(ctx, [profs[i] for i in kept], sc, dist=msa.oriented_distance(table, orient, kept))   # src/assemble.h:468
     gapped, cs, qs = msa.consensus(rows, fraction_called, False)            # src/assemble.h:471
     return dict(forward=fwd, kept=kept, rows=rows, seqidx=seqidx, gapped=gapped, consensus=cs, quality=qs)
 

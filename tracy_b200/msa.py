@@ -7,10 +7,11 @@ consensus :162-239, revSeqBasedOnDist :243-328, msa :330-368), `_createProfile(c
 Every gotohScore()/gotoh() call of those functions goes to the GPU through a `Context` (profile x profile,
 AlignConfig<true,true>), batched wherever the reference's loop order leaves the calls independent:
   * distanceMatrix / the initial matrix of revSeqBasedOnDist: all N(N-1)/2 pairs in one call;
-  * one orientation trial of revSeqBasedOnDist: the N-1 scores against the flipped profile in one call (the trials
-    themselves stay sequential: a flip changes the inputs of the next trial);
+  * revSeqBasedOnDist: the 4 N (N-1) scores of all ordered pairs in all orientation combinations in one call (the
+    orientation table); the sequential accept rule is replayed on the host over those exact numbers;
   * palign: all guide-tree nodes of equal height in one call;
-  * the exclusion loop: round r pairs every still-unmatched trace with its r-th candidate.
+  * the exclusion loop: the best-scoring partner of every trace first (existence of a hit is all that decides), then the
+    remaining candidates in a few geometric rounds.
 Tree building, row merging and consensus are integer/byte logic kept literal (tie-breaks, C++ integer division).
 """
 import numpy as np
@@ -130,11 +131,12 @@ def upgma(dist, num):
         if nn < 2 or sub[di, dj] <= -1:
             break
         p[di, 0] = nn; p[dj, 0] = nn; p[nn, 1] = di; p[nn, 2] = dj
-        for i in range(nn):                                 # updateDistanceMatrix, src/msa.h:60-70
-            if p[i, 0] == -1:
-                a = d[di, i] if di < i else d[i, di]
-                b = d[dj, i] if dj < i else d[i, dj]
-                d[i, nn] = _trunc_div2(int(a) + int(b))
+        io = np.nonzero(p[:nn, 0] == -1)[0]                 # updateDistanceMatrix, src/msa.h:60-70: the open nodes
+        if len(io):
+            a = np.where(di < io, d[di, io], d[io, di])
+            b = np.where(dj < io, d[dj, io], d[io, dj])
+            t = a + b
+            d[io, nn] = np.where(t >= 0, t // 2, -((-t) // 2))   # C++ integer division truncates toward zero
         d[:di, di] = -1; d[di, di + 1: nn + 1] = -1
         d[:dj, dj] = -1; d[dj, dj + 1: nn + 1] = -1
         nn += 1
@@ -192,10 +194,11 @@ def palign(ctx, sps, phylo, root, sc):
     return res[root]
 
 
-def msa(ctx, profiles, sc):
-    """msa (src/msa.h:330-368): distance matrix -> UPGMA -> progressive alignment. Returns (align rows, seqidx, dist)."""
+def msa(ctx, profiles, sc, dist=None):
+    """msa (src/msa.h:330-368): distance matrix -> UPGMA -> progressive alignment. Returns (align rows, seqidx, dist).
+    dist: the matrix distanceMatrix() would compute, when the caller already holds it (oriented_distance)."""
     n = len(profiles)
-    d = distance_matrix(ctx, profiles, sc)
+    d = distance_matrix(ctx, profiles, sc) if dist is None else np.asarray(dist, np.int64)
     phylo, root = upgma(d, n)
     rows, _, seqidx = palign(ctx, profiles, phylo, root, sc)
     return rows, seqidx, d
@@ -235,160 +238,118 @@ def consensus(rows, fraction_called=0.5, ignore_last=False):
 
 
 # ---- orientation ------------------------------------------------------------------------------------------------------
-class _DeviceTrials:
-    """Orientation trials of revSeqBasedOnDist (every profile against one flipped profile) on a pool that stays in HBM for the
-    whole stage, several trials per call. A trial fills only `num` of the GPU's ~1 800 warp slots and lasts as long as one pair
-    on one warp, so up to T consecutive trials (in the reference's order) go out together, each against the state at the start
-    of the group. The reference runs them one after the other and a kept flip of k_s changes ONE input of a later trial t of
-    the group: the pair (k_s, flip of k_t). Those T(T-1)/2 pairs (flip of k_s against flip of k_t) ride along in the same call,
-    and the host replays the reference's sequential accept rule on exact numbers -- same pairs, same kernel, same integers.
-    Arena order: trial t = `num` pairs (slot i, spare t) followed by its t fix-up pairs (spare s, spare t), s < t, so a shorter
-    last group is a prefix."""
-
-    def __init__(self, ctx, pool, num, T):
-        import torch
-        self.torch, self.ctx, self.num, self.cap, self.T = torch, ctx, num, pool.cap, T
-        dev = torch.device("cuda", ctx.device)
-        self.base = torch.from_numpy(pool.base).to(dev)
-        self.start = [t * num + t * (t - 1) // 2 for t in range(T + 1)]
-        npairs = self.start[T]
-        a1_off, a2_off = np.zeros(npairs, np.int64), np.zeros(npairs, np.int64)
-        self.a1_len, self.a2_len = np.zeros(npairs, np.int32), np.zeros(npairs, np.int32)
-        for t in range(T):
-            b = self.start[t]
-            a1_off[b: b + num] = pool.off[:num]
-            self.a1_len[b: b + num] = pool.lens[:num]                     # a flip keeps the length
-            a1_off[b + num: b + num + t] = pool.off[num: num + t]
-            a2_off[b: b + num + t] = pool.off[num + t]
-        self.a1_off, self.a2_off = torch.from_numpy(a1_off).to(dev), torch.from_numpy(a2_off).to(dev)
-        self.d_a1_len = torch.zeros(npairs, dtype=torch.int32, device=dev)
-        self.d_a2_len = torch.zeros(npairs, dtype=torch.int32, device=dev)
-        self.scores = torch.zeros(npairs, dtype=torch.int32, device=dev)
-        self.stage = torch.zeros(pool.cap, dtype=torch.float32).pin_memory()
-
-    def put(self, slot, p):
-        p = np.ascontiguousarray(p, np.float32)
-        self.stage[: p.size] = self.torch.from_numpy(p.reshape(-1))
-        self.base[slot * self.cap: slot * self.cap + p.size].copy_(self.stage[: p.size], non_blocking=False)
-        return p.shape[1]
-
-    def group(self, flips, sc):
-        """flips: the flipped profiles of up to T consecutive trials. Returns (base int64[len(flips)][num], fix) with
-        base[t][i] = score(slot i, flip t) and fix[t][s] = score(flip s, flip t) for s < t."""
-        num, g = self.num, len(flips)
-        lens = [self.put(num + t, p) for t, p in enumerate(flips)]
-        for t in range(g):
-            b = self.start[t]
-            self.a1_len[b + num: b + num + t] = lens[:t]
-            self.a2_len[b: b + num + t] = lens[t]
-        n = self.start[g]
-        self.d_a1_len[:n].copy_(self.torch.from_numpy(self.a1_len[:n]))
-        self.d_a2_len[:n].copy_(self.torch.from_numpy(self.a2_len[:n]))
-        self.torch.cuda.synchronize(self.base.device)               # torch's stream -> the context's stream
-        self.ctx.gotoh_device(PP, self.base.data_ptr(), self.a1_off.data_ptr(), self.d_a1_len.data_ptr(), self.base.data_ptr(),
-                              self.a2_off.data_ptr(), self.d_a2_len.data_ptr(), n, self.scores.data_ptr(), sc=sc, ac=_END_FREE)
-        sco = self.scores[:n].cpu().numpy().astype(np.int64)
-        base = [sco[self.start[t]: self.start[t] + num] for t in range(g)]
-        fix = [sco[self.start[t] + num: self.start[t] + num + t] for t in range(g)]
-        return base, fix
+def orientation_table(ctx, profiles, sc):
+    """T[i][k][oi][ok] = gotohScore(P_i in orientation oi, P_k in orientation ok, AlignConfig<true,true>) for every ORDERED pair
+    i != k (a1 = i, a2 = k; orientation 1 = reverseComplementProfile of the input) in ONE batched call: 4 N (N-1) fills.
+    Everything revSeqBasedOnDist (src/msa.h:243-328) and the distance matrix of msa() (src/msa.h:33-42) ever ask the DP is an
+    entry of this table, so the sequential accept rule becomes a host walk over exact numbers. Neither a1/a2 symmetry nor
+    reverse-complement symmetry is assumed: the float substitution sum (src/align.h:112-116) changes its order under both."""
+    num = len(profiles)
+    T = np.zeros((num, num, 2, 2), np.int64)
+    if num < 2:
+        return T
+    pool = _Pool(list(profiles) + [_revcomp(p) for p in profiles])       # slot i: as given, slot num + i: flipped
+    ii, kk = np.nonzero(~np.eye(num, dtype=bool))
+    a_idx = np.concatenate([ii + oi * num for oi in (0, 1) for _ in (0, 1)])
+    b_idx = np.concatenate([kk + ok * num for _ in (0, 1) for ok in (0, 1)])
+    s, _, _ = ctx.gotoh(PP, pool.arena(a_idx), pool.arena(b_idx), sc, _END_FREE, traceback=False)
+    s = np.asarray(s, np.int64).reshape(2, 2, len(ii))
+    for oi in (0, 1):
+        for ok in (0, 1):
+            T[ii, kk, oi, ok] = s[oi, ok]
+    return T
 
 
-class _HostTrials:
-    """The same grouping with the pool in host memory, for contexts without device entry points (the CPU test double of
-    tests/test_glue.py): one ctx.gotoh call per group, arenas in the order _DeviceTrials uses."""
-
-    def __init__(self, ctx, pool, num, T):
-        self.ctx, self.pool, self.num, self.T = ctx, pool, num, T
-
-    def put(self, slot, p):                                            # the caller keeps the host pool current itself
-        pass
-
-    def group(self, flips, sc):
-        num = self.num
-        i1, i2, start = [], [], [0]
-        for t, p in enumerate(flips):
-            self.pool.put(num + t, p)
-            i1 += list(range(num)) + [num + s for s in range(t)]
-            i2 += [num + t] * (num + t)
-            start.append(len(i1))
-        sco, _, _ = self.ctx.gotoh(PP, self.pool.arena(i1), self.pool.arena(i2), sc, _END_FREE, traceback=False)
-        sco = np.asarray(sco, np.int64)
-        return ([sco[start[t]: start[t] + num] for t in range(len(flips))],
-                [sco[start[t] + num: start[t + 1]] for t in range(len(flips))])
-
-
-def rev_seq_based_on_dist(ctx, profiles, fwd, sc):
+def rev_seq_based_on_dist(ctx, profiles, fwd, sc, table=None, with_state=False):
     """revSeqBasedOnDist (src/msa.h:243-328). profiles: list of float32[6][len] (replaced in place when a flip is kept),
-    fwd: list of bool (toggled in place). Returns the final symmetric score matrix."""
+    fwd: list of bool (toggled in place). Returns the final symmetric score matrix (with_state: also the orientation table and
+    the per-trace orientation bits, from which msa()'s distance matrix is read without another DP call).
+    The reference runs one trial (num - 1 fills against the flipped profile) after the other; here all fills any trial can
+    ask for are in the orientation table and the loop below is the reference's accept rule replayed on it."""
     seq = profiles
     num = len(seq)
+    T = orientation_table(ctx, seq, sc) if table is None else table
+    o = np.zeros(num, np.int64)                                        # orientation relative to the input
+    idx = np.arange(num)
     d = np.zeros((num, num), np.int64)
-    ii, jj = np.triu_indices(num, 1)
-    on_device = hasattr(ctx, "gotoh_device")                               # test doubles serve ctx.gotoh only
-    T = min(8, max(1, 1700 // max(num, 1)))
-    pool = _Pool(seq, spare=T)                                             # slots num.. hold the flips under trial
-    if len(ii):
-        s, _, _ = ctx.gotoh(PP, pool.arena(ii), pool.arena(jj), sc, _END_FREE, traceback=False)
-        d[ii, jj] = s
-        d[jj, ii] = s
-    total = int(d[ii, jj].sum()) if len(ii) else 0
-    trials = (_DeviceTrials if on_device else _HostTrials)(ctx, pool, num, T) if num > 1 else None
-    iterate = True
+    iu, ju = np.triu_indices(num, 1)
+    d[iu, ju] = T[iu, ju, 0, 0]                                        # d[i][j] = gotohScore(seq[i], seq[j]), i < j (src/msa.h:251-260)
+    d[ju, iu] = d[iu, ju]
+    total = int(d[iu, ju].sum()) if num > 1 else 0
+    iterate = num > 0
     while iterate:
         quality = [k for _, k in sorted((int(d[i].sum()), i) for i in range(num))]   # worst row sum first, src/msa.h:270-282
-        for g0 in range(0, num, T):
-            ks = quality[g0: g0 + T]
-            flips = [_revcomp(seq[k]) for k in ks]
-            if trials is not None:
-                base, fix = trials.group(flips, sc)
-            kept = []                                                    # trials of this group whose flip was kept
-            for t, k in enumerate(ks):
-                s_rc = flips[t]
-                others = [i for i in range(num) if i != k]
-                new_d = np.zeros(num, np.int64)
-                if others:
-                    new_d = base[t].copy()
-                    for s_ in kept:                                      # k_s was flipped after the group went out
-                        new_d[ks[s_]] = fix[t][s_]
-                    new_d[k] = 0                                         # the pair (k, flipped k) rides along and is dropped
-                if int(new_d.sum()) >= int(d[others, k].sum()):          # scoreSum >= oldScoreSum, src/msa.h:298
-                    seq[k] = s_rc
-                    pool.put(k, s_rc)
-                    if trials is not None:
-                        trials.put(k, s_rc)
-                    kept.append(t)
-                    fwd[k] = not fwd[k]
-                    d[:, k] = new_d
-                    d[k, :] = new_d
+        for k in quality:
+            new_d = T[idx, k, o, 1 - o[k]].copy()                     # gotohScore(seq[i], flipped seq[k]) for all i, src/msa.h:293
+            new_d[k] = 0
+            old = int(d[:, k].sum()) - int(d[k, k])
+            if int(new_d.sum()) >= old:                               # scoreSum >= oldScoreSum, src/msa.h:298
+                o[k] ^= 1
+                fwd[k] = not fwd[k]
+                d[:, k] = new_d
+                d[k, :] = new_d
         updated = int(d.sum())
         if total < updated:
             total = updated
         else:
             iterate = False
+    for k in range(num):
+        if o[k]:
+            seq[k] = _revcomp(seq[k])
+    return (d, T, o) if with_state else d
+
+
+def oriented_distance(T, o, keep=None):
+    """distanceMatrix (src/msa.h:33-42) of the oriented traces read from the orientation table: d[i][j] = gotohScore(sps[i], sps[j])
+    for i < j over the traces kept (index order)."""
+    idx = np.arange(len(o)) if keep is None else np.asarray(keep, np.int64)
+    n = len(idx)
+    d = np.zeros((n, n), np.int64)
+    iu, ju = np.triu_indices(n, 1)
+    d[iu, ju] = T[idx[iu], idx[ju], o[idx[iu]], o[idx[ju]]]
     return d
 
 
-def exclude_unmatched(ctx, profiles, sc, match_fraction):
-    """The exclusion loop of assemble() (src/assemble.h:428-448): trace i is kept iff some j != i (first hit in index order
-    is enough, so only existence matters) aligns with > 10 % of i aligned, > 25 aligned columns and a score above the
-    match-fraction threshold. Returns a list of bool (True = keep)."""
+def exclude_unmatched(ctx, profiles, sc, match_fraction, dist=None):
+    """The exclusion loop of assemble() (src/assemble.h:428-448): trace i is kept iff some j != i aligns with > 10 % of i aligned,
+    > 25 aligned columns and a score above the match-fraction threshold. The reference tries j = 0, 1, ... and stops at the first
+    hit; only EXISTENCE of a hit decides, so the candidates may be tried in any order: with `dist` (the symmetric score matrix
+    revSeqBasedOnDist leaves) the best-scoring partner goes first and an overlapping trace is settled by one alignment. Rounds of
+    1, 3, 12 and then all remaining candidates per still-unmatched trace: a handful of batched calls instead of one per
+    candidate rank. Returns a list of bool (True = keep)."""
     n = len(profiles)
     keep = [False] * n
-    cand = {i: [j for j in range(n) if j != i] for i in range(n)}
+    if dist is not None:
+        dm = np.array(dist, np.int64)
+        np.fill_diagonal(dm, np.iinfo(np.int64).min)
+        cand = {i: [int(j) for j in np.argsort(-dm[i], kind="stable") if j != i] for i in range(n)}
+    else:
+        cand = {i: [j for j in range(n) if j != i] for i in range(n)}
     pending = [i for i in range(n) if cand[i]]
     pool = _Pool(profiles)
-    while pending:
-        js = [cand[i].pop(0) for i in pending]
-        s, ops, ol = ctx.gotoh(PP, pool.arena(pending), pool.arena(js), sc, _END_FREE, traceback=True)
-        nxt = []
-        for k, i in enumerate(pending):
-            num_aligned = int((ops[k, : ol[k]] == ord("s")).sum())
+    f32, mf = np.float32, np.float32(match_fraction)
+    for block in (1, 3, 12, n):
+        if not pending:
+            break
+        ia, ja = [], []
+        for i in pending:
+            js = cand[i][:block]
+            cand[i] = cand[i][block:]
+            ia += [i] * len(js)
+            ja += js
+        s, ops, ol = ctx.gotoh(PP, pool.arena(ia), pool.arena(ja), sc, _END_FREE, traceback=True)
+        ops = np.asarray(ops)
+        col = np.arange(ops.shape[1])[None, :]
+        aligned = ((ops == ord("s")) & (col < np.asarray(ol)[:, None])).sum(axis=1)
+        hit = set()
+        for q, i in enumerate(ia):
+            num_aligned = int(aligned[q])
             frac = num_aligned / float(np.asarray(profiles[i]).shape[1])
-            f32, mf, na = np.float32, np.float32(match_fraction), np.float32(num_aligned)   # float arithmetic, as in C++
+            na = f32(num_aligned)                                      # float arithmetic, as in C++
             thr = float(f32(f32(na * mf) * f32(sc.match)) + f32(f32(na * f32(f32(1) - mf)) * f32(sc.mismatch)))
-            if frac > 0.1 and num_aligned > 25 and int(s[k]) > thr:
-                keep[i] = True
-            elif cand[i]:
-                nxt.append(i)
-        pending = nxt
+            if frac > 0.1 and num_aligned > 25 and int(s[q]) > thr:
+                hit.add(i)
+        for i in hit:
+            keep[i] = True
+        pending = [i for i in pending if i not in hit and cand[i]]
     return keep

@@ -105,6 +105,17 @@ def gen_batch_into(prof_out, win_out, m, n, seed, chunk=5000):
         win_out[lo:hi] = w
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 # ---- the CPU reference arm ------------------------------------------------------------------------------------
 def cpu_reference_gcups(m, n, pairs_per_thread, threads, repeats=1, seed=4242):
     """tracy's gotoh() (fill + bitsets + traceback + _createAlignment) on `threads` host threads, each running the
@@ -151,17 +162,19 @@ def run_reference(args, rank):
     sample = f"{total} pairs of {args.m}x{args.n} per step ({ppt} per thread x {threads} threads), gotoh() with traceback + _createAlignment"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": float(np.mean(secs) * 1e3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-        "data": "synthetic", "config": workload_config(args, 1),
-        "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": threads, "kind": kind, "sample": sample},
+        "ms_per_step": float(np.mean(secs) * 1e3), "higher_is_better": True, "scaling": "strong" if args.total_pairs else "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": workload_config(args, max(args.gpus, 1)),
+        "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": threads, "kind": kind, "sample": sample, "cpu_model": cpu_model()},
         "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
 def workload_config(args, world):
+    """The same dict for both arms at every N (the driver compares them): `world` is --gpus, not the rank count of the arm."""
     return {"workload": f"batched Gotoh fill+traceback (tb_gotoh_ps): {args.pairs} pairs/GPU of {args.m} bp trace profile x {args.n} bp reference window "
                         f"(BASELINE.json configs[1]), scores 3/-5/-10/-4, AlignConfig<true,false>",
-            "pairs_per_gpu": args.pairs, "m": args.m, "n": args.n, "traceback": True, "sharding": f"{world} x independent pair ranges, no data-path collective"
+            "pairs_per_gpu": args.pairs, "m": args.m, "n": args.n, "traceback": True, "outputs": "score + s/h/v string + both gapped alignment rows per pair",
+            "sharding": f"{world} x independent pair ranges, no data-path collective"
             + ("; one all-gather of scores per step" if world > 1 else ""),
             "l2": "inputs (2.8 GB/GPU) and the pointer scratch (GBs) exceed the 126 MB L2; no explicit flush"}
 
@@ -209,8 +222,11 @@ def run_b200(args, rank, world, local_rank):
     h_prof = torch.empty((P, 6, m), dtype=torch.float32, pin_memory=True)
     h_win = torch.empty((P, n), dtype=torch.uint8, pin_memory=True)
     h_scores = torch.empty(P, dtype=torch.int32, pin_memory=True)
-    h_ops = torch.empty((P, stride), dtype=torch.uint8, pin_memory=True)
     h_len = torch.empty(P, dtype=torch.int32, pin_memory=True)
+    pstride = ((m + n + 3) // 4 + 15) // 16 * 16                      # 2-bit packed ops: the form that travels in the e2e leg
+    h_pk = torch.empty((P, pstride), dtype=torch.uint8, pin_memory=True)
+    h_row0 = torch.empty((P, stride), dtype=torch.uint8, pin_memory=True)
+    h_row1 = torch.empty((P, stride), dtype=torch.uint8, pin_memory=True)
     t0 = time.perf_counter()
     gen_batch_into(h_prof.numpy(), h_win.numpy(), m, n, seed=44 + 1000003 * rank)
     gen_s = time.perf_counter() - t0
@@ -225,6 +241,8 @@ def run_b200(args, rank, world, local_rank):
     d_scores = torch.zeros(P, dtype=torch.int32, device=dev)
     d_ops = torch.zeros((P, stride), dtype=torch.uint8, device=dev)
     d_len = torch.zeros(P, dtype=torch.int32, device=dev)
+    d_row0 = torch.zeros((P, stride), dtype=torch.uint8, device=dev)
+    d_row1 = torch.zeros((P, stride), dtype=torch.uint8, device=dev)
     counts = [P] * world
     g_scores = torch.empty(P * world, dtype=torch.int32, device=dev) if world > 1 else None
     bcast = None
@@ -248,7 +266,8 @@ def run_b200(args, rank, world, local_rank):
 
     def device_step():
         ctx.gotoh_device("ps", d_prof.data_ptr(), d_aoff.data_ptr(), d_alen.data_ptr(), d_win.data_ptr(), d_boff.data_ptr(), d_blen.data_ptr(), P,
-                         d_scores.data_ptr(), d_ops.data_ptr(), stride, d_len.data_ptr(), sc, ac)
+                         d_scores.data_ptr(), d_ops.data_ptr(), stride, d_len.data_ptr(), sc, ac,
+                         row0=d_row0.data_ptr(), row1=d_row1.data_ptr(), rows_stride=stride)
         ms = ctx.last_call_ms()
         k = ctx.last_kernel_ms()
         if world > 1:
@@ -260,8 +279,11 @@ def run_b200(args, rank, world, local_rank):
             ms += e0.elapsed_time(e1)
         return ms, k
 
-    def host_step():
-        ctx.gotoh("ps", a1, a2, sc, ac, traceback=True, out=(h_scores.numpy(), h_ops.numpy(), h_len.numpy()))
+    def host_step():     # what a drop-in gotoh() caller gets back: score, traceback (2 bits per op on the wire), both gapped rows
+        ctx.gotoh("ps", a1, a2, sc, ac, traceback=True, out=(h_scores.numpy(), h_pk.numpy(), h_len.numpy()), rows=(h_row0.numpy(), h_row1.numpy()), packed=True)
+
+    def host_step_ops_only():   # the compact form: score + packed traceback, no rows
+        ctx.gotoh("ps", a1, a2, sc, ac, traceback=True, out=(h_scores.numpy(), h_pk.numpy(), h_len.numpy()), packed=True)
 
     def sync():
         torch.cuda.synchronize()
@@ -300,6 +322,18 @@ def run_b200(args, rank, world, local_rank):
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
     se1 = ctx.stats()
+    # the same call without the rows (score + packed ops only), one warm-up + min(steps, 2) steps
+    host_step_ops_only()
+    so0 = ctx.stats()
+    sync()
+    t0 = time.perf_counter()
+    nops = min(args.steps, 2)
+    for _ in range(nops):
+        host_step_ops_only()
+    sync()
+    e2e_ops_ms = (time.perf_counter() - t0) * 1e3 / nops
+    so1 = ctx.stats()
+    host_step()                                                        # leave the rows of the full call in the buffers for the parity check
 
     # spot parity inside the bench: device leg and host leg agree, and a few pairs match the CPU oracle
     assert torch.equal(d_scores.cpu(), h_scores), "device-resident and host-buffer legs disagree"
@@ -307,17 +341,19 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         from oracle import loader
         port = loader.port()
-        ops_h, len_h = h_ops.numpy(), h_len.numpy()
+        pk_h, len_h, r0_h, r1_h = h_pk.numpy(), h_len.numpy(), h_row0.numpy(), h_row1.numpy()
         for i in range(0, P, max(1, P // 4))[:4]:
             ws, wops = port.gotoh_ps(h_prof.numpy()[i], bytes(h_win.numpy()[i]), HFREE, VFREE, SC)
-            assert int(h_scores[i]) == ws and bytes(ops_h[i, : len_h[i]]) == wops, f"bench parity: pair {i} differs from the oracle"
+            assert int(h_scores[i]) == ws and tracy_b200.unpack_ops(pk_h[i], len_h[i]) == wops, f"bench parity: pair {i} differs from the oracle"
+            want_rows = tracy_b200.rows_from_ops("ps", h_prof.numpy()[i], bytes(h_win.numpy()[i]), wops)
+            assert (bytes(r0_h[i, : len_h[i]]), bytes(r1_h[i, : len_h[i]])) == want_rows, f"bench parity: rows of pair {i} differ"
             chk["pairs_checked_vs_oracle"] += 1
     checksum = int(h_scores.numpy().astype(np.int64).sum())
 
     if world > 1:
-        t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms, wall_ms, e2e_ms, e2e_ops_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms, e2e_ms = t.tolist()
+        dev_ms, wall_ms, e2e_ms, e2e_ops_ms = t.tolist()
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt.item())
@@ -340,27 +376,53 @@ def run_b200(args, rank, world, local_rank):
             "peak_source": peak_src, "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": bytes_launch,
             "note": "integer DP: the binding limit is the ALU/FMA pipe issue rate (DESIGN.md section 4), HBM fraction is reported as the contract asks",
             "packed_pairs_last_step": ctx.last_packed_pairs()}
+    prof_info = load_profile_info()
+    if prof_info.get("warp_instructions_per_pair") and k_ms > 0:
+        # the bound that actually binds: warp-instruction issue slots, 1 per clock per scheduler, 4 schedulers per SM
+        ipp = float(prof_info["warp_instructions_per_pair"])
+        ach = ipp * P / (k_ms * 1e-3)
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        roof["issue"] = {"bound": "alu+lsu issue (warp instructions / s over 148 SMs x 4 schedulers)", "achieved": ach, "peak": 148 * 4 * sm_mhz * 1e6,
+                         "frac": ach / (148 * 4 * sm_mhz * 1e6), "peak_at_1965_mhz": 148 * 4 * 1965e6, "peak_at_1342_mhz": 148 * 4 * 1342e6,
+                         "frac_at_1965_mhz": ach / (148 * 4 * 1965e6), "warp_instructions_per_pair": ipp,
+                         "pipes_from_capture": prof_info.get("pipes"), "source": prof_info.get("capture")}
     out = {
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.total_pairs else "weak", "vs_baseline": None,
         "dtype": "u16x2",            # biased unsigned 16-bit DP cells, two per 32-bit register (int32 in the general kernel)
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_val, "unit": "GCUPS", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": world * (se1["h2d_bytes"] - se0["h2d_bytes"]) // args.steps,      # every rank moves the same amount
                 "d2h_bytes_per_step": world * (se1["d2h_bytes"] - se0["d2h_bytes"]) // args.steps},
+        "e2e_ops_only": {"value": float(P) * m * n * world / (e2e_ops_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ops_ms,
+                         "h2d_bytes_per_step": world * (so1["h2d_bytes"] - so0["h2d_bytes"]) // nops, "d2h_bytes_per_step": world * (so1["d2h_bytes"] - so0["d2h_bytes"]) // nops,
+                         "note": "same host-buffer call returning score + 2-bit packed traceback only (no gapped rows)"},
         "gpu_launches": launches, "roofline": roof, "clocks": clocks, "host_cpus_bound_per_rank": numa_cpus, "reference_broadcast": bcast, "wall_ms_per_step": wall_ms / args.steps,
         "kernel_ms": {k: v / args.steps for k, v in kern.items()}, "parity": dict(chk, score_checksum=checksum), "gen_seconds": gen_s,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         threads = max(1, min(cores, args.cpu_threads or cores))
-        g, s, kind, total = cpu_reference_gcups(m, n, args.cpu_pairs_per_thread, threads)
-        out["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind, "seconds": s,
-                               "sample": f"{total} pairs of {m}x{n} ({args.cpu_pairs_per_thread} per thread x {threads} threads), tracy gotoh() with traceback"}
+        ppt = max(1, (args.cpu_sample_pairs + threads - 1) // threads)
+        g, s, kind, total = cpu_reference_gcups(m, n, ppt, threads)
+        g1, s1, _, total1 = cpu_reference_gcups(m, n, args.cpu_single_pairs, 1, seed=777)
+        out["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind, "seconds": s, "cpu_model": cpu_model(),
+                               "sample": f"{total} pairs of {m}x{n} ({ppt} per thread x {threads} threads), tracy gotoh() with traceback + _createAlignment",
+                               "single_thread": {"value": g1, "unit": "GCUPS", "cores": 1, "seconds": s1,
+                                                 "sample": f"{total1} pairs of {m}x{n} on one thread: the faithful single-threaded tracy path"}}
     print(json.dumps(out), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def load_profile_info():
+    """Per-pair instruction count and pipe utilisations of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
 
 
 def load_traffic(cells_per_launch):
@@ -384,12 +446,17 @@ def main():
     ap.add_argument("--m", type=int, default=1000)
     ap.add_argument("--n", type=int, default=4000)
     ap.add_argument("--cpu-threads", type=int, default=0)
-    ap.add_argument("--cpu-pairs-per-thread", type=int, default=8)
+    ap.add_argument("--cpu-pairs-per-thread", type=int, default=8, help="--impl reference: pairs per thread per step")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=2048, help="cpu_baseline of the b200 arm: pairs timed over all host threads (BASELINE.md section 3)")
+    ap.add_argument("--cpu-single-pairs", type=int, default=32, help="cpu_baseline.single_thread: pairs timed on one thread")
+    ap.add_argument("--total-pairs", type=int, default=0, help="strong split: this many pairs over all GPUs (BASELINE.json configs[4]: 1 000 000 over 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.total_pairs:
+        args.pairs = (args.total_pairs + max(args.gpus, 1) - 1) // max(args.gpus, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return

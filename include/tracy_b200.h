@@ -72,7 +72,18 @@ typedef struct {
   int32_t* scores;     /* [npairs]  S[m][n], the value gotoh()/gotohScore() return */
   uint8_t* ops;        /* may be NULL for score-only calls */
   int64_t ops_stride;
-  int32_t* ops_len;    /* [npairs]; may be NULL iff ops is NULL */
+  int32_t* ops_len;    /* [npairs]; may be NULL iff ops, row0 and row1 are all NULL */
+  /* Optional outputs, made on the device from the traceback (zero-initialise the struct when they are not wanted):
+   * row0 / row1: the two gapped alignment rows gotoh() leaves in `align` (_createAlignment, reference src/align.h:196-223,
+   *   :254-293): npairs * rows_stride bytes each, pair i's rows hold ops_len[i] characters; rows_stride >= max_i(len1[i]+len2[i]).
+   *   Both or neither. With rows and ops == NULL the call is still a traceback call (ops_len is required).
+   * ops_packed != 0: `ops` receives 2 bits per op instead of one byte -- 4 ops per byte, the first op in the two low bits,
+   *   0 = 's', 1 = 'h', 2 = 'v' (tb_unpack_ops turns a string back into bytes); ops_stride is then in BYTES of the packed form,
+   *   >= ceil(max_i(len1[i]+len2[i]) / 4). A quarter of the device-to-host traffic of the one-byte form. */
+  uint8_t* row0;
+  uint8_t* row1;
+  int64_t rows_stride;
+  int32_t ops_packed;
 } tb_result;
 
 /* ---- context --------------------------------------------------------------------------------------------- */
@@ -115,6 +126,9 @@ int tb_ctx_last_big_pairs(const tb_ctx* ctx, uint64_t* pairs);
 int tb_gotoh_ps(tb_ctx* ctx, const tb_batch* batch, tb_score sc, tb_align_config ac, tb_result* res);
 int tb_gotoh_pp(tb_ctx* ctx, const tb_batch* batch, tb_score sc, tb_align_config ac, tb_result* res);
 int tb_gotoh_ss(tb_ctx* ctx, const tb_batch* batch, tb_score sc, tb_align_config ac, tb_result* res);
+
+/* 2-bit packed ops (tb_result::ops_packed) back to one byte per op ('s','h','v'); out needs ops_len bytes. Host helper. */
+int tb_unpack_ops(const uint8_t* packed, int32_t ops_len, uint8_t* out);
 
 /* Gapped alignment rows from a traceback string: what gotoh() leaves in `align` (src/align.h:196-223 for
  * sequences, :254-293 for profiles: argmax channel, strict >, indices >= 4 print as 'N', never '-').

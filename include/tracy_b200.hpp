@@ -581,31 +581,66 @@ template <typename TProfile> inline void revcomp_profile_host(TProfile const& p,
 }
 }  // namespace detail
 
+// The orientation table of a set of traces: t(i, k, oi, ok) = gotohScore(P_i in orientation oi, P_k in orientation ok,
+// AlignConfig<true,true>) for every ORDERED pair i != k (a1 = i, a2 = k; orientation 1 = reverseComplementProfile of the input), in
+// ONE batched call of 4 N (N-1) fills. Every score revSeqBasedOnDist (reference src/msa.h:243-328) and the distance matrix of msa()
+// (src/msa.h:33-42) can ask for is an entry, so the reference's sequential accept rule becomes a host walk over exact numbers.
+// Neither a1/a2 symmetry nor reverse-complement symmetry is assumed: the float substitution sum (src/align.h:112-116) changes its
+// order under both.
+struct OrientationTable {
+  std::size_t num = 0;
+  std::vector<int32_t> t;                                              // [i][k][oi][ok]
+  std::vector<uint8_t> o;                                              // orientation per trace after revSeqBasedOnDist (0 = as given)
+  int32_t at(std::size_t i, std::size_t k, int oi, int ok) const { return t[((i * num + k) * 2 + (std::size_t)oi) * 2 + (std::size_t)ok]; }
+};
+
+template <typename TCtx, typename TConfig, typename TSeqProfiles>
+inline OrientationTable orientationTable(TCtx& g, TConfig const& c, TSeqProfiles const& seq) {
+  typedef typename TSeqProfiles::value_type TProfile;
+  OrientationTable T;
+  T.num = seq.size();
+  T.t.assign(T.num * T.num * 4, 0);
+  T.o.assign(T.num, 0);
+  if (T.num < 2) return T;
+  std::vector<TProfile> flip(T.num);
+  for (std::size_t i = 0; i < T.num; ++i) detail::revcomp_profile_host(seq[i], flip[i]);
+  std::vector<const TProfile*> a, b;
+  a.reserve(T.num * (T.num - 1) * 4); b.reserve(T.num * (T.num - 1) * 4);
+  for (std::size_t i = 0; i < T.num; ++i)
+    for (std::size_t k = 0; k < T.num; ++k) {
+      if (i == k) continue;
+      for (int oi = 0; oi < 2; ++oi)
+        for (int ok = 0; ok < 2; ++ok) { a.push_back(oi ? &flip[i] : &seq[i]); b.push_back(ok ? &flip[k] : &seq[k]); }
+    }
+  const std::vector<int32_t> s = gotohBatch(g, a, b, AlignConfig<true, true>(), c.aliscore);
+  std::size_t q = 0;
+  for (std::size_t i = 0; i < T.num; ++i)
+    for (std::size_t k = 0; k < T.num; ++k) {
+      if (i == k) continue;
+      for (int x = 0; x < 4; ++x) T.t[(i * T.num + k) * 4 + (std::size_t)x] = s[q++];
+    }
+  return T;
+}
+
 // revSeqBasedOnDist(c, seq, fwd) -- reference src/msa.h:243-328: all-pairs gotohScore matrix (AlignConfig<true,true>), then
 // sweeps over the traces, worst row sum first; a trace is flipped when the sum of its scores against all others does not get
 // worse (`scoreSum >= oldScoreSum`); sweeps repeat while the matrix total grows. int32 sums as in the reference.
-// The reference runs one trial (num - 1 fills) after the other. Here the initial matrix is ONE batched call and the trials
-// go out in groups of T consecutive ones, each against the state at the start of the group; a flip kept inside the group
-// changes one input of a later trial t of that group -- the pair (k_s, flip of k_t) -- so those T(T-1)/2 pairs (flip of k_s
-// against flip of k_t) ride along in the same call and the host replays the sequential accept rule on exact numbers.
+// The reference runs one trial (num - 1 fills against the flipped profile) after the other, each depending on the flips kept
+// before it. Here ALL fills any trial can ask for are computed up front (orientationTable: one GPU call) and the loop below is the
+// reference's accept rule replayed on that table. `table` (optional) returns it with the final orientation bits, from which
+// msa()'s distance matrix is read without another DP call (orientedDistance).
 // TCtx: Context, or any type for which gotohBatch(ctx, a1, a2, ac, sc) is callable (the CPU double of tests/cpp/hostlogic.cpp
 // serves it with the reference's own gotohScore). `log` receives the reference's progress dots (it prints them to std::cout).
 template <typename TCtx, typename TConfig, typename TSeqProfiles>
-inline void revSeqBasedOnDist(TCtx& g, TConfig const& c, TSeqProfiles& seq, std::vector<bool>& fwd, std::ostream* log = &std::cout) {
+inline void revSeqBasedOnDist(TCtx& g, TConfig const& c, TSeqProfiles& seq, std::vector<bool>& fwd, std::ostream* log = &std::cout,
+                              OrientationTable* table = nullptr, std::vector<std::vector<int32_t> >* dist = nullptr) {
   typedef typename TSeqProfiles::value_type TProfile;
   const std::size_t num = seq.size();
+  OrientationTable T = orientationTable(g, c, seq);
   std::vector<std::vector<int32_t> > d(num, std::vector<int32_t>(num, 0));
   int32_t totalScore = 0;
-  {
-    std::vector<const TProfile*> a, b;
-    for (std::size_t i = 0; i < num; ++i)
-      for (std::size_t j = i + 1; j < num; ++j) { a.push_back(&seq[i]); b.push_back(&seq[j]); }
-    const std::vector<int32_t> s = gotohBatch(g, a, b, AlignConfig<true, true>(), c.aliscore);
-    std::size_t k = 0;
-    for (std::size_t i = 0; i < num; ++i)
-      for (std::size_t j = i + 1; j < num; ++j) { d[i][j] = d[j][i] = s[k++]; totalScore += d[i][j]; }
-  }
-  const std::size_t T = std::min<std::size_t>(8, std::max<std::size_t>(1, 1700 / std::max<std::size_t>(num, 1)));
+  for (std::size_t i = 0; i < num; ++i)
+    for (std::size_t j = i + 1; j < num; ++j) { d[i][j] = d[j][i] = T.at(i, j, 0, 0); totalScore += d[i][j]; }   // src/msa.h:251-260
   bool iterateScore = true;
   while (iterateScore) {
     std::vector<std::pair<int32_t, int32_t> > quality;                 // (row sum, index), worst first, src/msa.h:270-282
@@ -615,35 +650,18 @@ inline void revSeqBasedOnDist(TCtx& g, TConfig const& c, TSeqProfiles& seq, std:
       quality.push_back(std::make_pair(rowSum, (int32_t)i));
     }
     std::sort(quality.begin(), quality.end());
-    for (std::size_t g0 = 0; g0 < num; g0 += T) {
-      const std::size_t gsz = std::min(T, num - g0);
-      std::vector<TProfile> flips(gsz);
-      for (std::size_t t = 0; t < gsz; ++t) detail::revcomp_profile_host(seq[(std::size_t)quality[g0 + t].second], flips[t]);
-      std::vector<const TProfile*> a, b;
-      std::vector<std::size_t> start(gsz + 1, 0);
-      for (std::size_t t = 0; t < gsz; ++t) {                          // trial t: num pairs (i, flip t), then its fix-up pairs (flip s, flip t)
-        start[t] = a.size();
-        for (std::size_t i = 0; i < num; ++i) { a.push_back(&seq[i]); b.push_back(&flips[t]); }
-        for (std::size_t s = 0; s < t; ++s) { a.push_back(&flips[s]); b.push_back(&flips[t]); }
+    for (std::size_t q = 0; q < num; ++q) {
+      const std::size_t k = (std::size_t)quality[q].second;
+      std::vector<int32_t> newD(num, 0);
+      int32_t scoreSum = 0, oldScoreSum = 0;
+      for (std::size_t i = 0; i < num; ++i)
+        if (i != k) { newD[i] = T.at(i, k, T.o[i], 1 - T.o[k]); oldScoreSum += d[i][k]; scoreSum += newD[i]; }   // src/msa.h:290-297
+      if (scoreSum >= oldScoreSum) {                                    // src/msa.h:298
+        T.o[k] ^= 1;
+        fwd[k] = !fwd[k];
+        for (std::size_t i = 0; i < num; ++i) { d[i][k] = newD[i]; d[k][i] = d[i][k]; }
       }
-      start[gsz] = a.size();
-      const std::vector<int32_t> sco = gotohBatch(g, a, b, AlignConfig<true, true>(), c.aliscore);
-      std::vector<std::size_t> kept;                                   // trials of this group whose flip was kept
-      for (std::size_t t = 0; t < gsz; ++t) {
-        const std::size_t k = (std::size_t)quality[g0 + t].second;
-        std::vector<int32_t> newD(num, 0);
-        for (std::size_t i = 0; i < num; ++i) if (i != k) newD[i] = sco[start[t] + i];
-        for (std::size_t s : kept) newD[(std::size_t)quality[g0 + s].second] = sco[start[t] + num + s];   // k_s was flipped after the group went out
-        int32_t scoreSum = 0, oldScoreSum = 0;
-        for (std::size_t i = 0; i < num; ++i) if (i != k) { oldScoreSum += d[i][k]; scoreSum += newD[i]; }
-        if (scoreSum >= oldScoreSum) {                                  // src/msa.h:298
-          seq[k] = flips[t];
-          fwd[k] = !fwd[k];
-          for (std::size_t i = 0; i < num; ++i) { d[i][k] = newD[i]; d[k][i] = d[i][k]; }
-          kept.push_back(t);
-        }
-        if (log) *log << "." << std::flush;
-      }
+      if (log) *log << "." << std::flush;
     }
     int32_t updatedScore = 0;
     for (std::size_t i = 0; i < num; ++i)
@@ -651,7 +669,19 @@ inline void revSeqBasedOnDist(TCtx& g, TConfig const& c, TSeqProfiles& seq, std:
     if (totalScore < updatedScore) totalScore = updatedScore;
     else iterateScore = false;
   }
+  for (std::size_t k = 0; k < num; ++k)
+    if (T.o[k]) { TProfile s; detail::revcomp_profile_host(seq[k], s); seq[k] = s; }
   if (log) *log << std::endl;
+  if (dist) *dist = d;
+  if (table) *table = std::move(T);
+}
+
+// distanceMatrix (reference src/msa.h:33-42) of the oriented traces `keep` (input indices, increasing) read from the table:
+// d[i][j] = gotohScore(sps[i], sps[j]) for i < j.
+template <typename TDistArray>
+inline void orientedDistance(OrientationTable const& T, std::vector<uint32_t> const& keep, TDistArray& d) {
+  for (std::size_t i = 0; i < keep.size(); ++i)
+    for (std::size_t j = i + 1; j < keep.size(); ++j) d[i][j] = T.at(keep[i], keep[j], T.o[keep[i]], T.o[keep[j]]);
 }
 
 // ---- assemble: guide tree and progressive alignment -------------------------------------------------------------------------
@@ -716,14 +746,18 @@ inline long upgma_tree(std::vector<std::vector<int> >& d, std::vector<std::vecto
 // alignment, node profile = column frequencies of its rows. The reference recurses node by node (one gotoh per node); nodes
 // of equal height are independent, so each height level is ONE batched call. seqidx: the input index of every output row.
 // TCtx as for revSeqBasedOnDist (gotohBatch with and without the ops strings).
+// table / keep (optional): the orientation table and the input indices of sps, when revSeqBasedOnDist left them -- the distance
+// matrix is then read from the table instead of being computed again.
 template <typename TCtx, typename TConfig, typename TSeqProfiles, typename TAlign>
-inline void msa(TCtx& g, TConfig const& c, TSeqProfiles const& sps, TAlign& align, std::vector<uint32_t>& seqidx) {
+inline void msa(TCtx& g, TConfig const& c, TSeqProfiles const& sps, TAlign& align, std::vector<uint32_t>& seqidx,
+                OrientationTable const* table = nullptr, std::vector<uint32_t> const* keep = nullptr) {
   typedef typename TSeqProfiles::value_type TProfile;
   const long num = (long)sps.size();
   std::vector<std::vector<int> > d((std::size_t)(2 * num + 1), std::vector<int>((std::size_t)(2 * num + 1), 0));
   for (long i = 0; i < 2 * num + 1; ++i)
     for (long j = i + 1; j < 2 * num + 1; ++j) d[i][j] = -1;
-  distanceMatrix(g, c, sps, d);
+  if (table && keep && keep->size() == (std::size_t)num) orientedDistance(*table, *keep, d);
+  else distanceMatrix(g, c, sps, d);
   std::vector<std::vector<int> > p((std::size_t)(2 * num + 1), std::vector<int>(3, -1));
   const long root = detail::upgma_tree(d, p, num);
 
@@ -781,31 +815,39 @@ inline void msa(TCtx& g, TConfig const& c, TSeqProfiles const& sps, TAlign& alig
 // assembly iff its end-gap-free alignment with SOME other trace j has more than 10 % of i aligned, more than 25 aligned columns
 // and a score above numAligned * (matchFraction * match + (1 - matchFraction) * mismatch), the threshold evaluated in the
 // reference's own mixed int / float arithmetic. The reference tries j = 0, 1, ... one gotoh() at a time and stops at the first
-// hit; traces are independent of each other, so round r aligns every still-unmatched trace with its r-th candidate in one call.
+// hit; only the EXISTENCE of a hit decides, so the candidates may be tried in any order: with `dist` (the symmetric score matrix
+// revSeqBasedOnDist leaves) the best-scoring partner goes first and an overlapping trace is settled by one alignment. Rounds of
+// 1, 3, 12 and then all remaining candidates per still-unmatched trace: a handful of batched calls.
 template <typename TCtx, typename TConfig, typename TSeqProfiles>
-inline std::vector<bool> matchingTraces(TCtx& g, TConfig const& c, TSeqProfiles const& profiles) {
+inline std::vector<bool> matchingTraces(TCtx& g, TConfig const& c, TSeqProfiles const& profiles, std::vector<std::vector<int32_t> > const* dist = nullptr) {
   typedef typename TSeqProfiles::value_type TProfile;
   const std::size_t n = profiles.size();
   std::vector<bool> keep(n, false);
-  std::vector<std::size_t> pending, next(n, 0);                        // next[i]: the candidate j trace i tries in this round
-  for (std::size_t i = 0; i < n; ++i) { next[i] = i == 0 ? 1 : 0; if (next[i] < n) pending.push_back(i); }
-  while (!pending.empty()) {
+  std::vector<std::vector<std::size_t> > cand(n);
+  std::vector<std::size_t> pending, pos(n, 0);
+  for (std::size_t i = 0; i < n; ++i) {
+    for (std::size_t j = 0; j < n; ++j) if (j != i) cand[i].push_back(j);
+    if (dist) std::stable_sort(cand[i].begin(), cand[i].end(), [&](std::size_t x, std::size_t y) { return (*dist)[i][x] > (*dist)[i][y]; });
+    if (!cand[i].empty()) pending.push_back(i);
+  }
+  const std::size_t blocks[4] = {1, 3, 12, n};
+  for (int r = 0; r < 4 && !pending.empty(); ++r) {
     std::vector<const TProfile*> a, b;
-    for (std::size_t i : pending) { a.push_back(&profiles[i]); b.push_back(&profiles[next[i]]); }
+    std::vector<std::size_t> who;
+    for (std::size_t i : pending)
+      for (std::size_t q = 0; q < blocks[r] && pos[i] < cand[i].size(); ++q, ++pos[i]) { a.push_back(&profiles[i]); b.push_back(&profiles[cand[i][pos[i]]]); who.push_back(i); }
     std::vector<std::string> ops;
     const std::vector<int32_t> gs = gotohBatch(g, a, b, AlignConfig<true, true>(), c.aliscore, &ops);
-    std::vector<std::size_t> still;
-    for (std::size_t q = 0; q < pending.size(); ++q) {
-      const std::size_t i = pending[q];
+    for (std::size_t q = 0; q < who.size(); ++q) {
+      const std::size_t i = who[q];
       const int32_t seqSize = (int32_t)profiles[i].shape()[1];
       const int32_t numAligned = (int32_t)std::count(ops[q].begin(), ops[q].end(), 's');
       const double frac = (double)numAligned / (double)seqSize;
       const double scoreThreshold = numAligned * c.matchFraction * c.aliscore.match + numAligned * (1 - c.matchFraction) * c.aliscore.mismatch;
-      if (frac > 0.1 && numAligned > 25 && gs[q] > scoreThreshold) { keep[i] = true; continue; }
-      ++next[i];
-      if (next[i] == i) ++next[i];
-      if (next[i] < n) still.push_back(i);
+      if (frac > 0.1 && numAligned > 25 && gs[q] > scoreThreshold) keep[i] = true;
     }
+    std::vector<std::size_t> still;
+    for (std::size_t i : pending) if (!keep[i] && pos[i] < cand[i].size()) still.push_back(i);
     pending.swap(still);
   }
   return keep;
@@ -820,8 +862,10 @@ template <typename TCtx, typename TConfig, typename TSeqProfiles, typename TAlig
 inline int assembleDenovo(TCtx& g, TConfig const& c, TSeqProfiles& inputProfiles, std::vector<bool>& fwdProfiles, TAlign& align,
                           std::vector<uint32_t>& seqidx, std::vector<uint32_t>& idxMap, std::vector<uint32_t>* excluded = nullptr,
                           std::ostream* log = &std::cout) {
-  revSeqBasedOnDist(g, c, inputProfiles, fwdProfiles, log);
-  const std::vector<bool> keep = matchingTraces(g, c, inputProfiles);
+  OrientationTable table;
+  std::vector<std::vector<int32_t> > dist;
+  revSeqBasedOnDist(g, c, inputProfiles, fwdProfiles, log, &table, &dist);
+  const std::vector<bool> keep = matchingTraces(g, c, inputProfiles, &dist);
   TSeqProfiles seqProfiles;
   idxMap.clear();
   for (std::size_t i = 0; i < inputProfiles.size(); ++i) {
@@ -829,7 +873,7 @@ inline int assembleDenovo(TCtx& g, TConfig const& c, TSeqProfiles& inputProfiles
     else if (excluded) excluded->push_back((uint32_t)i);
   }
   if (idxMap.size() < 2) return -1;
-  msa(g, c, seqProfiles, align, seqidx);
+  msa(g, c, seqProfiles, align, seqidx, &table, &idxMap);               // the distance matrix comes from the orientation table
   return 0;
 }
 

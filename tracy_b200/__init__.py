@@ -5,7 +5,7 @@ include/tracy_b200.h). Importing it never touches the GPU; creating a Context do
 built library is present -- there is no CPU implementation in this package.
 """
 from .api import (PS, PP, SS, AlignConfig, Arena, Context, DnaScore, TracyError, default_context, gotoh, gotohScore,
-                  find_breakpoint, pack_profiles, pack_seqs, rows_from_ops, trim_reference_slice, uniform_profiles, uniform_seqs)
+                  find_breakpoint, pack_profiles, pack_seqs, rows_from_ops, trim_reference_slice, unpack_ops, uniform_profiles, uniform_seqs)
 
 __all__ = ["PS", "PP", "SS", "AlignConfig", "Arena", "Context", "DnaScore", "TracyError", "default_context", "gotoh",
-           "gotohScore", "find_breakpoint", "trim_reference_slice", "pack_profiles", "pack_seqs", "rows_from_ops", "uniform_profiles", "uniform_seqs"]
+           "gotohScore", "find_breakpoint", "trim_reference_slice", "pack_profiles", "pack_seqs", "rows_from_ops", "unpack_ops", "uniform_profiles", "uniform_seqs"]

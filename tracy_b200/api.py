@@ -199,10 +199,13 @@ class Context:
     def _fn(self, kind):
         return {PS: self._lib.tb_gotoh_ps, PP: self._lib.tb_gotoh_pp, SS: self._lib.tb_gotoh_ss}[kind]
 
-    def gotoh(self, kind, a1, a2, sc=DnaScore(3, -5, -10, -4), ac=AlignConfig(True, False), traceback=True, out=None):
+    def gotoh(self, kind, a1, a2, sc=DnaScore(3, -5, -10, -4), ac=AlignConfig(True, False), traceback=True, out=None, rows=None, packed=False):
         """Batch of pairs in HOST memory. a1/a2: Arena (or lists of profiles / byte strings).
         Returns (scores int32[N], ops uint8[N][stride] or None, ops_len int32[N] or None).
-        `out` may carry preallocated (scores, ops, ops_len) arrays (e.g. pinned)."""
+        `out` may carry preallocated (scores, ops, ops_len) arrays (e.g. pinned).
+        rows: True, or a preallocated (row0, row1) pair of uint8[N][stride] arrays -- the gapped alignment rows gotoh() leaves in
+        `align` (reference src/align.h:196-293), made on the device; they are then returned as a 4th and 5th value.
+        packed: ops come back at 2 bits per op (4 per byte; unpack_ops) in an array of stride ceil(max(len1+len2)/4)."""
         if not isinstance(a1, Arena):
             a1 = pack_seqs(a1) if kind == SS else pack_profiles(a1)
         if not isinstance(a2, Arena):
@@ -210,28 +213,42 @@ class Context:
         n = a1.n
         if a2.n != n:
             raise ValueError("a1 and a2 must hold the same number of items")
+        maxsum = int((a1.len.astype(np.int64) + a2.len).max()) if n else 1
         if out is not None:
             scores, ops, ops_len = out
         else:
             scores = np.zeros(n, np.int32)
             ops = ops_len = None
             if traceback:
-                stride = int((a1.len.astype(np.int64) + a2.len).max()) if n else 1
-                stride = max((stride + 15) // 16 * 16, 16)
+                stride = max((((maxsum + 3) // 4 if packed else maxsum) + 15) // 16 * 16, 16)
                 ops = np.zeros((n, stride), np.uint8)
+                ops_len = np.zeros(n, np.int32)
+        r0 = r1 = None
+        if rows is not None and rows is not False:
+            if rows is True:
+                rs = max((maxsum + 15) // 16 * 16, 16)
+                r0, r1 = np.zeros((n, rs), np.uint8), np.zeros((n, rs), np.uint8)
+            else:
+                r0, r1 = rows
+            if ops_len is None:
                 ops_len = np.zeros(n, np.int32)
         b = capi.Batch(capi.Arena(_ptr(a1.base), _ptr(a1.off), _ptr(a1.len)),
                        capi.Arena(_ptr(a2.base), _ptr(a2.off), _ptr(a2.len)), n, capi.TB_MEM_HOST)
-        r = capi.Result(_ptr(scores), _ptr(ops) if traceback else None, ops.shape[1] if traceback else 0,
-                        _ptr(ops_len) if traceback else None)
+        want_ops = traceback and ops is not None
+        r = capi.Result(_ptr(scores), _ptr(ops) if want_ops else None, ops.shape[1] if want_ops else 0,
+                        _ptr(ops_len) if ops_len is not None else None,
+                        _ptr(r0) if r0 is not None else None, _ptr(r1) if r1 is not None else None, r0.shape[1] if r0 is not None else 0,
+                        1 if (packed and want_ops) else 0)
         self._check(self._fn(kind)(self._h, C.byref(b), sc.c(), ac.c(), C.byref(r)))
+        if r0 is not None:
+            return scores, ops, ops_len, r0, r1
         return scores, ops, ops_len
 
     def gotoh_device(self, kind, a1_base, a1_off, a1_len, a2_base, a2_off, a2_len, n, scores, ops=None, ops_stride=0, ops_len=None,
-                     sc=DnaScore(3, -5, -10, -4), ac=AlignConfig(True, False)):
+                     sc=DnaScore(3, -5, -10, -4), ac=AlignConfig(True, False), row0=None, row1=None, rows_stride=0, packed=False):
         """Everything already resident in HBM: arguments are raw device pointers (ints), e.g. torch tensor .data_ptr()."""
         b = capi.Batch(capi.Arena(a1_base, a1_off, a1_len), capi.Arena(a2_base, a2_off, a2_len), n, capi.TB_MEM_DEVICE)
-        r = capi.Result(scores, ops, ops_stride, ops_len)
+        r = capi.Result(scores, ops, ops_stride, ops_len, row0, row1, rows_stride, 1 if packed else 0)
         self._check(self._fn(kind)(self._h, C.byref(b), sc.c(), ac.c(), C.byref(r)))
 
     # ---- decompose sweeps ---------------------------------------------------------------------------------
@@ -378,6 +395,16 @@ class Context:
     def rows_from_ops(self, kind, a1, a2, ops):
         """Gapped rows as gotoh() leaves them in `align` (reference src/align.h:196-293)."""
         return rows_from_ops(kind, a1, a2, ops)
+
+
+def unpack_ops(packed, ops_len):
+    """2-bit packed ops (Context.gotoh(..., packed=True)) of ONE pair -> bytes of 's' / 'h' / 'v'."""
+    buf = np.ascontiguousarray(packed, np.uint8)
+    out = np.zeros(max(int(ops_len), 1), np.uint8)
+    rc = capi.lib().tb_unpack_ops(_ptr(buf), int(ops_len), _ptr(out))
+    if rc != capi.TB_OK:
+        raise TracyError(rc, "tb_unpack_ops")
+    return out[: int(ops_len)].tobytes()
 
 
 def rows_from_ops(kind, a1, a2, ops):

@@ -13,7 +13,7 @@ TB_MEM_HOST, TB_MEM_DEVICE = 0, 1
 SYMBOLS = [
     "tb_ctx_create", "tb_ctx_destroy", "tb_strerror", "tb_last_error", "tb_host_alloc", "tb_host_free",
     "tb_ctx_set_scratch_limit", "tb_ctx_stats", "tb_ctx_last_kernel_ms", "tb_ctx_last_call_ms", "tb_ctx_last_packed_pairs", "tb_ctx_last_big_pairs", "tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss",
-    "tb_rows_from_ops", "tb_decompose_sweep", "tb_version", "tb_create_profile", "tb_revcomp_profile", "tb_trim_reference_slice",
+    "tb_rows_from_ops", "tb_unpack_ops", "tb_decompose_sweep", "tb_version", "tb_create_profile", "tb_revcomp_profile", "tb_trim_reference_slice",
     "tb_find_breakpoint", "tb_basecall", "tb_index_build", "tb_index_destroy", "tb_index_info", "tb_anchor", "tb_ctx_last_anchor_ms",
     "tb_reference_slice", "tb_allelic_fraction", "tb_ctx_last_fraction_ms", "tb_trace_scan", "tb_trace_unpack",
 ]
@@ -36,7 +36,8 @@ class Batch(C.Structure):
 
 
 class Result(C.Structure):
-    _fields_ = [("scores", C.c_void_p), ("ops", C.c_void_p), ("ops_stride", C.c_int64), ("ops_len", C.c_void_p)]
+    _fields_ = [("scores", C.c_void_p), ("ops", C.c_void_p), ("ops_stride", C.c_int64), ("ops_len", C.c_void_p),
+                ("row0", C.c_void_p), ("row1", C.c_void_p), ("rows_stride", C.c_int64), ("ops_packed", C.c_int32)]
 
 
 class SweepBatch(C.Structure):
@@ -110,6 +111,7 @@ def lib():
     for name in ("tb_gotoh_ps", "tb_gotoh_pp", "tb_gotoh_ss"):
         getattr(L, name).argtypes = [vp, C.POINTER(Batch), Score, AlignConfig, C.POINTER(Result)]
     L.tb_rows_from_ops.argtypes = [C.c_int, vp, C.c_int32, vp, C.c_int32, vp, C.c_int32, vp, vp]
+    L.tb_unpack_ops.argtypes = [vp, C.c_int32, vp]
     L.tb_decompose_sweep.argtypes = [vp, C.POINTER(SweepBatch), C.POINTER(SweepResult)]
     L.tb_version.restype = C.c_char_p
     L.tb_create_profile.argtypes = [vp, C.POINTER(ProfileBatch), vp, vp, vp]

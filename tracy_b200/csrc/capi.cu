@@ -25,6 +25,7 @@ unsigned long long gotoh_packed_ptr_words(int m, int n);
 cudaError_t launch_gotoh_pp(int nch, bool traceback, bool harr, const GotohBatch& B, const PPWork& W, int blocks, cudaStream_t stream);
 cudaError_t gotoh_pp_blocks_per_sm(int nch, bool traceback, bool harr, int* out);
 int gotoh_pp_warps_per_block();
+cudaError_t launch_post_ops(const PostBatch& P, int sms, cudaStream_t stream);
 
 
 cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
@@ -92,6 +93,9 @@ struct Lane {   // one in-flight chunk of a TB_MEM_HOST batch
   cudaEvent_t h0 = nullptr, d1 = nullptr;                               // host-mode chunk: before its H2D, after its D2H (TRACY_B200_TRACE)
   DevBuf a, b, meta_d, scores, ops, ops_len, status, counter;
   DevBuf ptr, rowbuf, opsrev;
+  DevBuf row0, row1, opk;                  // host-mode outputs made by post_ops.cu: gapped rows, 2-bit packed ops
+  tb::PostBatch post{}; bool want_post = false;
+  cudaEvent_t kp = nullptr;                // after the post-processing kernel
   DevBuf pp_units, pp_small, pp_big, pp_rowbuf, pp_ptr, pp_flags;   // big-pair work list and scratch of the profile x profile kernel
   PinBuf pp_stage;
   tb::PPWork ppw{};
@@ -332,6 +336,16 @@ int build_pp_work(tb_ctx* ctx, Lane& L, const int32_t* l1, const int32_t* l2, co
   return TB_OK;
 }
 
+// Gapped rows / packed ops of the lane's current batch (L.post, filled by run_gotoh), after the DP kernels on the same stream.
+int enqueue_post(tb_ctx* ctx, Lane& L) {
+  if (!L.want_post) return TB_OK;
+  TB_CUDA(ctx, tb::launch_post_ops(L.post, ctx->sms, L.stream));
+  TB_CUDA(ctx, cudaEventRecord(L.kp, L.stream));
+  L.kend = L.kp;
+  ctx->launches++;
+  return TB_OK;
+}
+
 // Enqueue the DP kernels for one device-resident batch view on lane L's stream.
 // Stage 1 is ONE kernel: the 4-class packed kernel when the batch is eligible for it (it completes every pair whose
 // window is pure ACGT and whose score range fits 16 bits), the general kernel otherwise. Whether stage 2 is needed --
@@ -370,6 +384,7 @@ int enqueue_gotoh(tb_ctx* ctx, Lane& L, int mode, bool traceback, tb::GotohBatch
     L.kend = L.k2;
   }
   ctx->launches++;
+  if (int rc = enqueue_post(ctx, L)) return rc;
   TB_CUDA(ctx, L.cnt.reserve(64));
   TB_CUDA(ctx, cudaMemcpyAsync(L.cnt.p, counters, 64, cudaMemcpyDeviceToHost, L.stream));
   L.view = B; L.plan = p; L.mode = mode; L.traceback = traceback;
@@ -399,6 +414,7 @@ int finish_gotoh(tb_ctx* ctx, Lane& L, bool* ran) {
   ctx->launches += 2;
   L.timed = L.timed2 = true;
   L.kend = L.k2;
+  if (int rc = enqueue_post(ctx, L)) return rc;                  // again, over the pairs stage 2 finished
   TB_CUDA(ctx, cudaMemsetAsync(counters + 1, 0, 4, L.stream));   // stage 1's count is already in last_packed_pairs
   TB_CUDA(ctx, cudaMemcpyAsync(L.cnt.p, counters, 64, cudaMemcpyDeviceToHost, L.stream));
   *ran = true;
@@ -412,6 +428,18 @@ int collect_timing(tb_ctx* ctx, Lane& L) {
   if (L.timed && L.cnt.p) ctx->last_packed_pairs += static_cast<const unsigned int*>(L.cnt.p)[1] + static_cast<const unsigned int*>(L.cnt.p)[3];
   L.timed = L.timed2 = false;
   return TB_OK;
+}
+
+// True when rows 4 (N) and 5 ('-') of `items` back-to-back float[6][len] profiles are all +0.0f (bit pattern 0).
+bool rows45_zero(const float* base, size_t items, size_t len) {
+  uint32_t acc = 0;
+  for (size_t i = 0; i < items && acc == 0; ++i) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(base + i * 6 * len + 4 * len);
+    uint32_t a = 0;
+    for (size_t j = 0; j < 2 * len; ++j) a |= p[j];
+    acc |= a;
+  }
+  return acc == 0;
 }
 
 size_t elem_size_a(int mode) { return mode == tb::kModeSS ? 1 : sizeof(float); }
@@ -438,8 +466,11 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   if (np > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "npairs too large");
   if (!batch->a1.base || !batch->a1.off || !batch->a1.len || !batch->a2.base || !batch->a2.off || !batch->a2.len || !res->scores)
     return fail(ctx, TB_ERR_INVALID, "null arena/score pointer");
-  const bool traceback = res->ops != nullptr;
-  if (traceback && !res->ops_len) return fail(ctx, TB_ERR_INVALID, "ops given without ops_len");
+  const bool want_rows = res->row0 != nullptr || res->row1 != nullptr;
+  if (want_rows && (!res->row0 || !res->row1)) return fail(ctx, TB_ERR_INVALID, "row0 and row1 go together");
+  const bool traceback = res->ops != nullptr || want_rows;
+  const bool packed_ops = res->ops != nullptr && res->ops_packed != 0;
+  if (traceback && !res->ops_len) return fail(ctx, TB_ERR_INVALID, "ops / rows given without ops_len");
   TB_CUDA(ctx, cudaSetDevice(ctx->device));
 
   // Lengths on the host (needed for validation and scratch sizing in both memory modes).
@@ -470,8 +501,13 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   const uint8_t* bigp = big.empty() ? nullptr : big.data();
   Shape all;
   accumulate(all, l1, l2, np, mode != tb::kModePP, bigp);
-  if (traceback && res->ops_stride < all.maxsum) return fail(ctx, TB_ERR_INVALID, "ops_stride smaller than max(len1+len2)");
+  if (res->ops && !packed_ops && res->ops_stride < all.maxsum) return fail(ctx, TB_ERR_INVALID, "ops_stride smaller than max(len1+len2)");
+  if (packed_ops && res->ops_stride < (all.maxsum + 3) / 4) return fail(ctx, TB_ERR_INVALID, "ops_stride smaller than ceil(max(len1+len2) / 4) bytes of packed ops");
+  if (want_rows && res->rows_stride < all.maxsum) return fail(ctx, TB_ERR_INVALID, "rows_stride smaller than max(len1+len2)");
   if (int rc = check_range(ctx, all, sc)) return rc;
+  // the DP kernels write one byte per op: into the caller's buffer when that is the form asked for, else into a lane buffer
+  const bool plain_ops = res->ops != nullptr && !packed_ops;
+  const int64_t ustride = plain_ops ? res->ops_stride : (((int64_t)all.maxsum + 15) & ~(int64_t)15);
 
   tb::GotohBatch B{};
   B.match = sc.match; B.mismatch = sc.mismatch; B.go = sc.gap_open; B.ge = sc.gap_extend;
@@ -488,8 +524,17 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     TB_CUDA(ctx, L.status.reserve(np));
     B.a_base = batch->a1.base; B.a_off = batch->a1.off; B.a_len = batch->a1.len;
     B.b_base = batch->a2.base; B.b_off = batch->a2.off; B.b_len = batch->a2.len;
-    B.scores = res->scores; B.ops = res->ops; B.ops_stride = res->ops_stride; B.ops_len = res->ops_len;
+    if (traceback && !plain_ops) TB_CUDA(ctx, L.ops.reserve(np * (size_t)ustride));
+    B.scores = res->scores; B.ops = !traceback ? nullptr : plain_ops ? res->ops : L.ops.as<uint8_t>(); B.ops_stride = ustride; B.ops_len = res->ops_len;
     B.status = L.status.as<uint8_t>(); B.npairs = (int)np;
+    L.want_post = want_rows || packed_ops;
+    if (L.want_post) {
+      tb::PostBatch& P = L.post;
+      P.a_base = B.a_base; P.a_off = B.a_off; P.a_len = B.a_len; P.b_base = B.b_base; P.b_off = B.b_off; P.b_len = B.b_len;
+      P.ops = B.ops; P.ops_stride = ustride; P.ops_len = B.ops_len; P.npairs = (int)np; P.mode = mode;
+      P.row0 = res->row0; P.row1 = res->row1; P.rows_stride = res->rows_stride;
+      P.packed = packed_ops ? res->ops : nullptr; P.packed_stride = packed_ops ? res->ops_stride : 0;
+    }
     if (int rc = enqueue_gotoh(ctx, L, mode, traceback, B, plan)) return rc;
     TB_CUDA(ctx, cudaStreamSynchronize(L.stream));
     bool again = false;
@@ -509,12 +554,25 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   chunk = std::max<size_t>(1, chunk / wave) * wave;
   {
     const double per_pair = (double)item_elems_a(mode, all.maxm) * elem_size_a(mode) + (double)item_elems_b(mode, all.maxn) * elem_size_b(mode) +
-                            (traceback ? (double)res->ops_stride : 0.0);
+                            (traceback ? (double)ustride : 0.0);
     const size_t cap = (size_t)std::max(1.0, (768.0 * 1024 * 1024) / std::max(per_pair, 1.0));
     if (chunk > cap) chunk = cap >= wave ? cap / wave * wave : cap;
   }
   chunk = std::min(chunk, np);
   bool ramp = chunk >= 4 * wave;   // the first chunks are 1, 2 and 4 waves so that the kernels start after a short first copy
+  {
+    // Pooled arenas (an all-pairs list is two index arrays into ONE set of profiles): when everything the call touches and
+    // returns is small, there is nothing to pipeline -- one chunk, one launch, instead of re-sending the pool with every chunk.
+    long long amin = LLONG_MAX, amax = 0, bmin = LLONG_MAX, bmax = 0;
+    for (size_t i = 0; i < np; ++i) {
+      const long long ao = batch->a1.off[i], bo = batch->a2.off[i];
+      amin = std::min(amin, ao); amax = std::max(amax, ao + item_elems_a(mode, l1[i]));
+      bmin = std::min(bmin, bo); bmax = std::max(bmax, bo + item_elems_b(mode, l2[i]));
+    }
+    const double touched = (double)(amax - amin) * elem_size_a(mode) + (double)(bmax - bmin) * elem_size_b(mode) +
+                           (double)np * (28.0 + (traceback ? (double)ustride : 0.0) + (want_rows ? 2.0 * (double)res->rows_stride : 0.0));
+    if (amin >= 0 && bmin >= 0 && touched <= 512.0 * 1024 * 1024) { chunk = np; ramp = false; }
+  }
   if (const char* ce = getenv("TRACY_B200_CHUNK")) { const long v = atol(ce); if (v > 0) { chunk = std::min<size_t>((size_t)v, np); ramp = false; } }   // tuning knob
   const bool trace = getenv("TRACY_B200_TRACE") != nullptr;   // per-chunk timeline on stderr (profiles/)
   const size_t esa = elem_size_a(mode), esb = elem_size_b(mode);
@@ -524,6 +582,7 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   for (size_t i = 1; a_rows5 && i < np; ++i)
     a_rows5 = l1[i] == l1[0] && batch->a1.off[i] == batch->a1.off[0] + (int64_t)i * 6 * l1[0];
   if (a_rows5 && l1[0] == 0) a_rows5 = false;
+  const bool no_rows4 = getenv("TRACY_B200_NO_ROWS4") != nullptr;
   int nlanes = 3;
   if (const char* le = getenv("TRACY_B200_LANES")) nlanes = std::max(1, std::min(kLanes, atoi(le)));   // tuning knob
   TB_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->lanes[0].stream));
@@ -532,9 +591,14 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     TB_CUDA(ctx, cudaMemcpyAsync(res->scores + p0, L.scores.p, cn * 4, cudaMemcpyDeviceToHost, L.stream));
     ctx->d2h += cn * 4;
     if (traceback) {
-      TB_CUDA(ctx, cudaMemcpyAsync(res->ops + p0 * (size_t)res->ops_stride, L.ops.p, cn * (size_t)res->ops_stride, cudaMemcpyDeviceToHost, L.stream));
+      if (plain_ops) TB_CUDA(ctx, cudaMemcpyAsync(res->ops + p0 * (size_t)ustride, L.ops.p, cn * (size_t)ustride, cudaMemcpyDeviceToHost, L.stream));
+      if (packed_ops) TB_CUDA(ctx, cudaMemcpyAsync(res->ops + p0 * (size_t)res->ops_stride, L.opk.p, cn * (size_t)res->ops_stride, cudaMemcpyDeviceToHost, L.stream));
+      if (want_rows) {
+        TB_CUDA(ctx, cudaMemcpyAsync(res->row0 + p0 * (size_t)res->rows_stride, L.row0.p, cn * (size_t)res->rows_stride, cudaMemcpyDeviceToHost, L.stream));
+        TB_CUDA(ctx, cudaMemcpyAsync(res->row1 + p0 * (size_t)res->rows_stride, L.row1.p, cn * (size_t)res->rows_stride, cudaMemcpyDeviceToHost, L.stream));
+      }
       TB_CUDA(ctx, cudaMemcpyAsync(res->ops_len + p0, L.ops_len.p, cn * 4, cudaMemcpyDeviceToHost, L.stream));
-      ctx->d2h += cn * (size_t)res->ops_stride + cn * 4;
+      ctx->d2h += (plain_ops ? cn * (size_t)ustride : 0) + (packed_ops ? cn * (size_t)res->ops_stride : 0) + (want_rows ? 2 * cn * (size_t)res->rows_stride : 0) + cn * 4;
     }
     return TB_OK;
   };
@@ -585,7 +649,9 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     if (cp.use_pp) if (int rc = build_pp_work(ctx, L, l1 + p0, l2 + p0, bigp ? bigp + p0 : nullptr, cn, traceback)) return rc;
     TB_CUDA(ctx, L.a.reserve(abytes + 16)); TB_CUDA(ctx, L.b.reserve(bbytes + 16));
     TB_CUDA(ctx, L.scores.reserve(cn * 4)); TB_CUDA(ctx, L.status.reserve(cn));
-    if (traceback) { TB_CUDA(ctx, L.ops.reserve(cn * (size_t)res->ops_stride)); TB_CUDA(ctx, L.ops_len.reserve(cn * 4)); }
+    if (traceback) { TB_CUDA(ctx, L.ops.reserve(cn * (size_t)ustride)); TB_CUDA(ctx, L.ops_len.reserve(cn * 4)); }
+    if (want_rows) { TB_CUDA(ctx, L.row0.reserve(cn * (size_t)res->rows_stride)); TB_CUDA(ctx, L.row1.reserve(cn * (size_t)res->rows_stride)); }
+    if (packed_ops) TB_CUDA(ctx, L.opk.reserve(cn * (size_t)res->ops_stride));
     // offsets and lengths of the chunk go through ONE pinned block and one copy: [a_off | b_off | a_len | b_len]
     TB_CUDA(ctx, L.meta.reserve(cn * 24)); TB_CUDA(ctx, L.meta_d.reserve(cn * 24));
     int64_t* hoff = static_cast<int64_t*>(L.meta.p);
@@ -595,9 +661,16 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
 
     if (trace) TB_CUDA(ctx, cudaEventRecord(L.h0, L.stream));
     if (a_rows5) {
-      const size_t pitch = (size_t)6 * l1[0] * 4, width = (size_t)5 * l1[0] * 4;
-      TB_CUDA(ctx, cudaMemcpy2DAsync(L.a.p, pitch, (const char*)batch->a1.base + (size_t)amin * esa, pitch, width, cn, cudaMemcpyHostToDevice, L.stream));
-      ctx->h2d += width * cn;
+      // rows 0..4 enter _score; row 5 ('-') only decides consensus characters (wanted with the gapped rows). Trace profiles made
+      // by createProfile carry exact zeros in rows 4 and 5 (src/profile.h:37): when this chunk's do, 4 rows travel and the
+      // device copy's rows 4, 5 are zeroed in place -- 16 KB instead of 24 KB per 1 000-column profile.
+      const size_t len = (size_t)l1[0], pitch = 6 * len * 4;
+      const float* src = (const float*)batch->a1.base + amin;
+      int rows = want_rows ? 6 : 5;
+      if (!no_rows4 && rows45_zero(src, cn, len)) rows = 4;
+      TB_CUDA(ctx, cudaMemcpy2DAsync(L.a.p, pitch, src, pitch, (size_t)rows * len * 4, cn, cudaMemcpyHostToDevice, L.stream));
+      if (rows == 4) TB_CUDA(ctx, cudaMemset2DAsync((char*)L.a.p + 4 * len * 4, pitch, 0, 2 * len * 4, cn, L.stream));
+      ctx->h2d += (size_t)rows * len * 4 * cn;
     } else {
       TB_CUDA(ctx, cudaMemcpyAsync(L.a.p, (const char*)batch->a1.base + (size_t)amin * esa, abytes, cudaMemcpyHostToDevice, L.stream));
       ctx->h2d += abytes;
@@ -612,8 +685,16 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     C.a_base = L.a.p; C.a_off = doff; C.a_len = dlen;
     C.b_base = L.b.p; C.b_off = doff + cn; C.b_len = dlen + cn;
     C.scores = L.scores.as<int32_t>(); C.ops = traceback ? L.ops.as<uint8_t>() : nullptr;
-    C.ops_stride = res->ops_stride; C.ops_len = traceback ? L.ops_len.as<int32_t>() : nullptr;
+    C.ops_stride = ustride; C.ops_len = traceback ? L.ops_len.as<int32_t>() : nullptr;
     C.status = L.status.as<uint8_t>(); C.npairs = (int)cn;
+    L.want_post = want_rows || packed_ops;
+    if (L.want_post) {
+      tb::PostBatch& P = L.post;
+      P.a_base = C.a_base; P.a_off = C.a_off; P.a_len = C.a_len; P.b_base = C.b_base; P.b_off = C.b_off; P.b_len = C.b_len;
+      P.ops = C.ops; P.ops_stride = ustride; P.ops_len = C.ops_len; P.npairs = (int)cn; P.mode = mode;
+      P.row0 = want_rows ? L.row0.as<uint8_t>() : nullptr; P.row1 = want_rows ? L.row1.as<uint8_t>() : nullptr; P.rows_stride = res->rows_stride;
+      P.packed = packed_ops ? L.opk.as<uint8_t>() : nullptr; P.packed_stride = packed_ops ? res->ops_stride : 0;
+    }
     if (int rc = enqueue_gotoh(ctx, L, mode, traceback, C, cp)) return rc;
     L.chunk = (long)ci; L.p0 = p0;
 
@@ -683,7 +764,7 @@ int tb_ctx_create(tb_ctx** out, int device) {
     Lane& L = c->lanes[i];
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&L.c0) != cudaSuccess ||
         cudaEventCreate(&L.k0) != cudaSuccess || cudaEventCreate(&L.h0) != cudaSuccess || cudaEventCreate(&L.d1) != cudaSuccess ||
-        cudaEventCreate(&L.k1) != cudaSuccess || cudaEventCreate(&L.k2) != cudaSuccess) {
+        cudaEventCreate(&L.k1) != cudaSuccess || cudaEventCreate(&L.k2) != cudaSuccess || cudaEventCreate(&L.kp) != cudaSuccess) {
       cudaGetLastError();
       tb_ctx_destroy(c);
       return TB_ERR_CUDA;
@@ -701,7 +782,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     Lane& L = c->lanes[i];
     if (L.stream) cudaStreamSynchronize(L.stream);
     DevBuf* bufs[] = {&L.a, &L.b, &L.meta_d, &L.scores, &L.ops, &L.ops_len, &L.status, &L.counter, &L.ptr, &L.rowbuf, &L.opsrev,
-                      &L.pp_units, &L.pp_small, &L.pp_big, &L.pp_rowbuf, &L.pp_ptr, &L.pp_flags};
+                      &L.pp_units, &L.pp_small, &L.pp_big, &L.pp_rowbuf, &L.pp_ptr, &L.pp_flags, &L.row0, &L.row1, &L.opk};
     for (DevBuf* b : bufs) b->release();
     L.meta.release(); L.cnt.release(); L.pp_stage.release();
     if (L.c0) cudaEventDestroy(L.c0);
@@ -710,6 +791,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     if (L.k2) cudaEventDestroy(L.k2);
     if (L.h0) cudaEventDestroy(L.h0);
     if (L.d1) cudaEventDestroy(L.d1);
+    if (L.kp) cudaEventDestroy(L.kp);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   delete c;
@@ -797,6 +879,13 @@ int tb_rows_from_ops(int kind, const void* a1, int32_t len1, const void* a2, int
     }
     row0[j] = x; row1[j] = y;
   }
+  return TB_OK;
+}
+
+int tb_unpack_ops(const uint8_t* packed, int32_t L, uint8_t* out) {
+  if (!packed || !out || L < 0) return TB_ERR_INVALID;
+  static const uint8_t sym[4] = {'s', 'h', 'v', '?'};
+  for (int32_t j = 0; j < L; ++j) out[j] = sym[(packed[j >> 2] >> (2 * (j & 3))) & 3];
   return TB_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 
 namespace tb {
 
@@ -50,6 +51,16 @@ struct PPWork {
   unsigned long long* big_ptr;                 // per big pair: nb x (n + 31) x 32 pointer words (traceback only)
   int* big_flags;                              // per big pair: nb progress words (columns of the bottom row published), zeroed per call
   float one;                                   // 1.0f, as a run-time value (see gotoh_pp.cu)
+};
+
+// Device view of the output post-processing (post_ops.cu): gapped rows and 2-bit packed ops from the one-byte-per-op strings.
+struct PostBatch {
+  const void* a_base; const int64_t* a_off; const int32_t* a_len;
+  const void* b_base; const int64_t* b_off; const int32_t* b_len;
+  const uint8_t* ops; int64_t ops_stride; const int32_t* ops_len;
+  uint8_t* row0; uint8_t* row1; int64_t rows_stride;      // nullptr: not wanted
+  uint8_t* packed; int64_t packed_stride;                  // nullptr: not wanted
+  int npairs, mode;
 };
 
 // Device view of a decompose-sweep batch (sweep.cu).

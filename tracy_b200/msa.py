@@ -61,26 +61,33 @@ def profile_cons_chars(p):
 
 
 def profile_from_alignment(rows):
-    """_createProfile(boost::multi_array<char,2>, p), src/align.h:138-180. rows: uint8[nrow][ncol] -> float32[6][ncol]."""
+    """_createProfile(boost::multi_array<char,2>, p), src/align.h:138-180. rows: uint8[nrow][ncol] -> float32[6][ncol].
+    A row takes part between its first and last non-gap character; the counts are accumulated over those spans only (a trace
+    covers ~1 000 of the tens of thousands of columns of a large assembly)."""
     a = np.asarray(rows, np.uint8)
     nrow, ncol = a.shape
     notgap = a != 0x2D
-    first = np.where(notgap.any(axis=1), notgap.argmax(axis=1), -1)
-    last = np.where(notgap.any(axis=1), ncol - 1 - notgap[:, ::-1].argmax(axis=1), ncol)
-    # a row without any nucleotide keeps first = -1, last = ncol: covered everywhere (src/align.h:147-158)
-    cols = np.arange(ncol)[None, :]
-    cover = (first[:, None] <= cols) & (cols <= last[:, None])
-    up = a & 0xDF                                           # upper-case letters; '-' (0x2d) becomes 0x0d, never a letter
-    p = np.zeros((6, ncol), np.float32)
-    known = np.zeros((nrow, ncol), bool)
-    for k, ch in enumerate(b"ACGTN"):
-        hit = cover & (up == ch) & notgap
-        p[k] = hit.sum(axis=0)
-        known |= hit
-    gap = cover & ~notgap
-    p[5] = gap.sum(axis=0)
-    known |= gap
-    total = (cover & known).sum(axis=0)                     # `else --sum`: unknown characters do not count
+    has = notgap.any(axis=1)
+    first = notgap.argmax(axis=1)
+    last = ncol - 1 - notgap[:, ::-1].argmax(axis=1)
+    cnt = np.zeros((6, ncol), np.int64)
+    total = np.zeros(ncol, np.int64)
+    nfull = int((~has).sum())           # a row without any nucleotide keeps first = -1, last = ncol: covered everywhere (src/align.h:147-158)
+    if nfull:
+        cnt[5] += nfull
+        total += nfull
+    for i in np.nonzero(has)[0]:
+        f, l = int(first[i]), int(last[i]) + 1
+        seg = a[i, f:l]
+        up = seg & 0xDF                                     # upper-case letters; '-' (0x2d) becomes 0x0d, never a letter
+        known = seg == 0x2D
+        cnt[5, f:l] += known
+        for k, ch in enumerate(b"ACGTN"):
+            hit = up == ch
+            cnt[k, f:l] += hit
+            known = known | hit
+        total[f:l] += known                                 # `else --sum`: unknown characters do not count
+    p = cnt.astype(np.float32)
     nz = total > 0
     p[:, nz] = p[:, nz] / total[nz].astype(np.float32)
     return p
@@ -118,27 +125,53 @@ def distance_matrix(ctx, profiles, sc):
 
 def upgma(dist, num):
     """upgma (src/msa.h:72-87) on the (2*num+1)^2 matrix the reference uses: returns (phylogeny int[2num+1][3], root).
-    closestPair starts at dMax = -1 with a strict '>', so pairs with a negative score are never joined (src/msa.h:47-50)."""
+    closestPair starts at dMax = -1 with a strict '>', so pairs with a negative score are never joined (src/msa.h:47-50).
+    The reference rescans the whole matrix for every join (O(n^3)); here every open row keeps its maximum and the first column
+    that holds it, which a join changes in O(n): the global scan is then a scan over row maxima, and taking the lowest row among
+    equal maxima (and the lowest column inside it) is the reference's first-maximum-in-(i, j)-order tie-break."""
     size = 2 * num + 1
     d = np.full((size, size), -1, np.int64)
     d[:num, :num] = np.where(np.triu(np.ones((num, num), bool), 1), dist[:num, :num], -1)
     p = np.full((size, 3), -1, np.int64)
+    rowmax = np.full(size, -1, np.int64)
+    rowarg = np.zeros(size, np.int64)
+
+    def rescan(i, hi):                                       # row i over columns i+1 .. hi-1
+        seg = d[i, i + 1: hi]
+        if len(seg):
+            k = int(np.argmax(seg))
+            rowmax[i], rowarg[i] = seg[k], i + 1 + k
+        else:
+            rowmax[i] = -1
+    for i in range(num):
+        rescan(i, num)
     nn = num
-    while nn < 2 * num + 1:
-        sub = np.where(np.triu(np.ones((nn, nn), bool), 1), d[:nn, :nn], -1)
-        flat = int(np.argmax(sub))                          # first maximum in (i, j) row-major order = the reference's scan
-        di, dj = divmod(flat, nn)
-        if nn < 2 or sub[di, dj] <= -1:
+    live = np.arange(num)                                    # nodes without a parent, ascending
+    while nn < 2 * num + 1 and len(live) >= 2:
+        a = int(np.argmax(rowmax[live]))
+        di = int(live[a])
+        if rowmax[di] <= -1:
             break
+        dj = int(rowarg[di])
         p[di, 0] = nn; p[dj, 0] = nn; p[nn, 1] = di; p[nn, 2] = dj
-        io = np.nonzero(p[:nn, 0] == -1)[0]                 # updateDistanceMatrix, src/msa.h:60-70: the open nodes
+        io = live[(live != di) & (live != dj)]              # updateDistanceMatrix, src/msa.h:60-70: the open nodes
         if len(io):
-            a = np.where(di < io, d[di, io], d[io, di])
-            b = np.where(dj < io, d[dj, io], d[io, dj])
-            t = a + b
+            x = np.where(di < io, d[di, io], d[io, di])
+            y = np.where(dj < io, d[dj, io], d[io, dj])
+            t = x + y
             d[io, nn] = np.where(t >= 0, t // 2, -((-t) // 2))   # C++ integer division truncates toward zero
         d[:di, di] = -1; d[di, di + 1: nn + 1] = -1
         d[:dj, dj] = -1; d[dj, dj + 1: nn + 1] = -1
+        rowmax[di] = rowmax[dj] = -1
+        if len(io):
+            stale = (rowarg[io] == di) | (rowarg[io] == dj)
+            for i in io[stale]:
+                rescan(int(i), nn + 1)
+            fresh = io[~stale]
+            better = d[fresh, nn] > rowmax[fresh]           # the new column is the last one: it wins only when strictly larger
+            rowmax[fresh[better]] = d[fresh[better], nn]
+            rowarg[fresh[better]] = nn
+        live = np.append(io, nn)
         nn += 1
     return p, (nn - 1 if nn > 0 else 0)
 
@@ -205,36 +238,35 @@ def msa(ctx, profiles, sc, dist=None):
 
 
 def consensus(rows, fraction_called=0.5, ignore_last=False):
-    """consensus (src/msa.h:162-239): returns (gapped, cs, qstr) byte strings."""
+    """consensus (src/msa.h:162-239): returns (gapped, cs, qstr) byte strings. Counts are accumulated over each row's span."""
     a = np.asarray(rows, np.uint8)
     nrow = a.shape[0] - (1 if ignore_last else 0)
     ncol = a.shape[1]
     a = a[:nrow]
     notgap = a != 0x2D
-    has = notgap.any(axis=1)
-    start = np.where(has, notgap.argmax(axis=1), ncol)       # a row of gaps only: start = ncol, end = -1 -> covers nothing
-    end = np.where(has, ncol - 1 - notgap[:, ::-1].argmax(axis=1), -1)
-    cols = np.arange(ncol)[None, :]
-    fl = (start[:, None] <= cols) & (cols <= end[:, None])
-    cov = fl.sum(axis=0)
-    thr = int(np.float32(fraction_called) * np.float32(nrow))   # (int32_t)(float * size_t): float arithmetic
-    up = a & 0xDF
-    counts = np.stack([(fl & (up == ch) & notgap).sum(axis=0) for ch in b"ACGT"] + [np.zeros(ncol, np.int64)])
+    has = notgap.any(axis=1)                                 # a row of gaps only: start = ncol, end = -1 -> covers nothing
+    start = notgap.argmax(axis=1)
+    end = ncol - 1 - notgap[:, ::-1].argmax(axis=1)
+    cov = np.zeros(ncol, np.int64)
+    counts = np.zeros((5, ncol), np.int64)
+    for i in np.nonzero(has)[0]:
+        f, l = int(start[i]), int(end[i]) + 1
+        up = a[i, f:l] & 0xDF
+        cov[f:l] += 1
+        for k, ch in enumerate(b"ACGT"):
+            counts[k, f:l] += up == ch
     counts[4] = cov - counts[:4].sum(axis=0)
-    cons = bytearray(b"-" * ncol)
-    qual = bytearray(b"#" * ncol)
-    qualval = 33
-    for j in range(ncol):
-        max_idx = 4
-        if cov[j] >= 1 and cov[j] >= thr:
-            max_idx = int(np.argmax(counts[:, j]))           # first maximum, strict '>' scan
-            qualval = 47 + int(counts[max_idx, j]) * 10 // nrow
-        if max_idx < 4:
-            cons[j] = b"ACGT"[max_idx]
-            qual[j] = qualval & 0xFF
-    cs = bytes(c for c in cons if c != 0x2D)
-    qs = bytes(q for c, q in zip(cons, qual) if c != 0x2D)
-    return bytes(cons), cs, qs
+    thr = int(np.float32(fraction_called) * np.float32(nrow))   # (int32_t)(float * size_t): float arithmetic
+    called = (cov >= 1) & (cov >= thr)
+    max_idx = np.where(called, np.argmax(counts, axis=0), 4)  # first maximum, strict '>' scan
+    top = counts[np.minimum(max_idx, 4), np.arange(ncol)]
+    # qualval is only assigned in called columns and carried over otherwise, but it is only WRITTEN where max_idx < 4, i.e. in a
+    # called column with a nucleotide majority, where it was just assigned: no carry-over is ever visible
+    qv = (47 + top * 10 // max(nrow, 1)) & 0xFF
+    cons = np.where(max_idx < 4, np.frombuffer(b"ACGT-", np.uint8)[np.minimum(max_idx, 4)], 0x2D).astype(np.uint8)
+    qual = np.where(max_idx < 4, qv, ord("#")).astype(np.uint8)
+    sel = cons != 0x2D
+    return cons.tobytes(), cons[sel].tobytes(), qual[sel].tobytes()
 
 
 # ---- orientation ------------------------------------------------------------------------------------------------------
@@ -319,13 +351,16 @@ def exclude_unmatched(ctx, profiles, sc, match_fraction, dist=None):
     candidate rank. Returns a list of bool (True = keep)."""
     n = len(profiles)
     keep = [False] * n
+    if n < 2:
+        return keep
     if dist is not None:
-        dm = np.array(dist, np.int64)
-        np.fill_diagonal(dm, np.iinfo(np.int64).min)
-        cand = {i: [int(j) for j in np.argsort(-dm[i], kind="stable") if j != i] for i in range(n)}
+        dm = -np.array(dist, np.int64)
+        np.fill_diagonal(dm, np.iinfo(np.int64).max)            # the trace itself sorts last and is cut off
+        order = np.argsort(dm, axis=1, kind="stable")[:, : n - 1]
     else:
-        cand = {i: [j for j in range(n) if j != i] for i in range(n)}
-    pending = [i for i in range(n) if cand[i]]
+        order = np.array([[j for j in range(n) if j != i] for i in range(n)], np.int64)
+    pos = np.zeros(n, np.int64)
+    pending = list(range(n))
     pool = _Pool(profiles)
     f32, mf = np.float32, np.float32(match_fraction)
     for block in (1, 3, 12, n):
@@ -333,10 +368,10 @@ def exclude_unmatched(ctx, profiles, sc, match_fraction, dist=None):
             break
         ia, ja = [], []
         for i in pending:
-            js = cand[i][:block]
-            cand[i] = cand[i][block:]
+            js = order[i, pos[i]: pos[i] + block]
+            pos[i] += len(js)
             ia += [i] * len(js)
-            ja += js
+            ja += [int(j) for j in js]
         s, ops, ol = ctx.gotoh(PP, pool.arena(ia), pool.arena(ja), sc, _END_FREE, traceback=True)
         ops = np.asarray(ops)
         col = np.arange(ops.shape[1])[None, :]
@@ -351,5 +386,5 @@ def exclude_unmatched(ctx, profiles, sc, match_fraction, dist=None):
                 hit.add(i)
         for i in hit:
             keep[i] = True
-        pending = [i for i in pending if i not in hit and cand[i]]
+        pending = [i for i in pending if i not in hit and pos[i] < n - 1]
     return keep

@@ -230,7 +230,7 @@ def run_b200(args, rank, world, local_rank):
     t0 = time.perf_counter()
     gen_batch_into(h_prof.numpy(), h_win.numpy(), m, n, seed=44 + 1000003 * rank)
     gen_s = time.perf_counter() - t0
-    a1 = tracy_b200.uniform_profiles(h_prof.numpy())
+    a1 = tracy_b200.uniform_profiles(h_prof.numpy(), trace_profiles=True)   # the generator keeps createProfile's invariant: rows 4, 5 exactly zero
     a2 = tracy_b200.uniform_seqs(h_win.numpy())
 
     # device-resident copies for the `value` leg

@@ -44,6 +44,11 @@ typedef struct { int32_t match, mismatch, gap_open, gap_extend; } tb_score;
 typedef struct { int32_t h_free, v_free; } tb_align_config;
 
 enum { TB_MEM_HOST = 0, TB_MEM_DEVICE = 1 };
+/* Optional promise, OR-ed into tb_batch::mem of a tb_gotoh_ps / tb_gotoh_pp call: rows 4 (N) and 5 ('-') of every a1 profile are
+ * exact zeros -- what createProfile(Trace, BaseCalls, ...) always produces (reference src/profile.h:37). A TB_MEM_HOST batch of equally
+ * long, back-to-back a1 profiles then travels as 4 rows of 6 (16 instead of 24 bytes per column); the device copy's rows 4 and 5 are
+ * cleared. If the promise is false the results are those of the profiles with rows 4 and 5 cleared. */
+enum { TB_A1_TRACE_PROFILES = 0x100 };
 
 /* One side of a batch. base: const float* (profiles) or const char* (sequences). off[i] is in ELEMENTS
  * (floats / chars) from base; len[i] is the number of columns (profile) or characters (sequence). */

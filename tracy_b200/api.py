@@ -50,6 +50,7 @@ class Arena:
     base: np.ndarray      # float32 (profiles) or uint8 (sequences), 1-D contiguous
     off: np.ndarray       # int64[N]
     len: np.ndarray       # int32[N]
+    trace_profiles: bool = False   # a1 only: every profile has exact zeros in rows 4 (N) and 5 ('-'), as createProfile makes them (TB_A1_TRACE_PROFILES)
 
     @property
     def n(self):
@@ -79,12 +80,13 @@ def pack_seqs(items):
     return Arena(base, off, lens)
 
 
-def uniform_profiles(arr):
-    """float32[N][6][m] -> Arena without copying."""
+def uniform_profiles(arr, trace_profiles=False):
+    """float32[N][6][m] -> Arena without copying. trace_profiles=True: the caller vouches that rows 4 and 5 of every profile are
+    exact zeros (createProfile outputs, reference src/profile.h:37); host batches then upload 4 rows of 6."""
     arr = np.ascontiguousarray(arr, np.float32)
     n, six, m = arr.shape
     assert six == 6
-    return Arena(arr.reshape(-1), np.arange(n, dtype=np.int64) * (6 * m), np.full(n, m, np.int32))
+    return Arena(arr.reshape(-1), np.arange(n, dtype=np.int64) * (6 * m), np.full(n, m, np.int32), trace_profiles)
 
 
 def uniform_seqs(arr):
@@ -233,7 +235,8 @@ class Context:
             if ops_len is None:
                 ops_len = np.zeros(n, np.int32)
         b = capi.Batch(capi.Arena(_ptr(a1.base), _ptr(a1.off), _ptr(a1.len)),
-                       capi.Arena(_ptr(a2.base), _ptr(a2.off), _ptr(a2.len)), n, capi.TB_MEM_HOST)
+                       capi.Arena(_ptr(a2.base), _ptr(a2.off), _ptr(a2.len)), n,
+                       capi.TB_MEM_HOST | (capi.TB_A1_TRACE_PROFILES if (a1.trace_profiles and kind != SS) else 0))
         want_ops = traceback and ops is not None
         r = capi.Result(_ptr(scores), _ptr(ops) if want_ops else None, ops.shape[1] if want_ops else 0,
                         _ptr(ops_len) if ops_len is not None else None,

@@ -8,6 +8,7 @@ LIB_PATH = os.environ.get("TRACY_B200_LIB") or os.path.join(HERE, "libtracy_b200
 
 TB_OK, TB_ERR_INVALID, TB_ERR_CUDA, TB_ERR_NOMEM, TB_ERR_UNSUPPORTED = range(5)
 TB_MEM_HOST, TB_MEM_DEVICE = 0, 1
+TB_A1_TRACE_PROFILES = 0x100
 
 # every symbol include/tracy_b200.h declares (tests/test_boundary.py checks the header against this list)
 SYMBOLS = [

@@ -25,7 +25,6 @@ unsigned long long gotoh_packed_ptr_words(int m, int n);
 cudaError_t launch_gotoh_pp(int nch, bool traceback, bool harr, const GotohBatch& B, const PPWork& W, int blocks, cudaStream_t stream);
 cudaError_t gotoh_pp_blocks_per_sm(int nch, bool traceback, bool harr, int* out);
 int gotoh_pp_warps_per_block();
-cudaError_t launch_post_ops(const PostBatch& P, int sms, cudaStream_t stream);
 
 
 cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
@@ -94,8 +93,6 @@ struct Lane {   // one in-flight chunk of a TB_MEM_HOST batch
   DevBuf a, b, meta_d, scores, ops, ops_len, status, counter;
   DevBuf ptr, rowbuf, opsrev;
   DevBuf row0, row1, opk;                  // host-mode outputs made by post_ops.cu: gapped rows, 2-bit packed ops
-  tb::PostBatch post{}; bool want_post = false;
-  cudaEvent_t kp = nullptr;                // after the post-processing kernel
   DevBuf pp_units, pp_small, pp_big, pp_rowbuf, pp_ptr, pp_flags;   // big-pair work list and scratch of the profile x profile kernel
   PinBuf pp_stage;
   tb::PPWork ppw{};
@@ -336,16 +333,6 @@ int build_pp_work(tb_ctx* ctx, Lane& L, const int32_t* l1, const int32_t* l2, co
   return TB_OK;
 }
 
-// Gapped rows / packed ops of the lane's current batch (L.post, filled by run_gotoh), after the DP kernels on the same stream.
-int enqueue_post(tb_ctx* ctx, Lane& L) {
-  if (!L.want_post) return TB_OK;
-  TB_CUDA(ctx, tb::launch_post_ops(L.post, ctx->sms, L.stream));
-  TB_CUDA(ctx, cudaEventRecord(L.kp, L.stream));
-  L.kend = L.kp;
-  ctx->launches++;
-  return TB_OK;
-}
-
 // Enqueue the DP kernels for one device-resident batch view on lane L's stream.
 // Stage 1 is ONE kernel: the 4-class packed kernel when the batch is eligible for it (it completes every pair whose
 // window is pure ACGT and whose score range fits 16 bits), the general kernel otherwise. Whether stage 2 is needed --
@@ -384,7 +371,6 @@ int enqueue_gotoh(tb_ctx* ctx, Lane& L, int mode, bool traceback, tb::GotohBatch
     L.kend = L.k2;
   }
   ctx->launches++;
-  if (int rc = enqueue_post(ctx, L)) return rc;
   TB_CUDA(ctx, L.cnt.reserve(64));
   TB_CUDA(ctx, cudaMemcpyAsync(L.cnt.p, counters, 64, cudaMemcpyDeviceToHost, L.stream));
   L.view = B; L.plan = p; L.mode = mode; L.traceback = traceback;
@@ -414,7 +400,6 @@ int finish_gotoh(tb_ctx* ctx, Lane& L, bool* ran) {
   ctx->launches += 2;
   L.timed = L.timed2 = true;
   L.kend = L.k2;
-  if (int rc = enqueue_post(ctx, L)) return rc;                  // again, over the pairs stage 2 finished
   TB_CUDA(ctx, cudaMemsetAsync(counters + 1, 0, 4, L.stream));   // stage 1's count is already in last_packed_pairs
   TB_CUDA(ctx, cudaMemcpyAsync(L.cnt.p, counters, 64, cudaMemcpyDeviceToHost, L.stream));
   *ran = true;
@@ -428,18 +413,6 @@ int collect_timing(tb_ctx* ctx, Lane& L) {
   if (L.timed && L.cnt.p) ctx->last_packed_pairs += static_cast<const unsigned int*>(L.cnt.p)[1] + static_cast<const unsigned int*>(L.cnt.p)[3];
   L.timed = L.timed2 = false;
   return TB_OK;
-}
-
-// True when rows 4 (N) and 5 ('-') of `items` back-to-back float[6][len] profiles are all +0.0f (bit pattern 0).
-bool rows45_zero(const float* base, size_t items, size_t len) {
-  uint32_t acc = 0;
-  for (size_t i = 0; i < items && acc == 0; ++i) {
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(base + i * 6 * len + 4 * len);
-    uint32_t a = 0;
-    for (size_t j = 0; j < 2 * len; ++j) a |= p[j];
-    acc |= a;
-  }
-  return acc == 0;
 }
 
 size_t elem_size_a(int mode) { return mode == tb::kModeSS ? 1 : sizeof(float); }
@@ -475,12 +448,14 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
 
   // Lengths on the host (needed for validation and scratch sizing in both memory modes).
   const int32_t *l1 = batch->a1.len, *l2 = batch->a2.len;
-  if (batch->mem == TB_MEM_DEVICE) {
+  const int32_t mem = batch->mem & 0xff;
+  const bool a1_trace_profiles = (batch->mem & TB_A1_TRACE_PROFILES) != 0;   // the caller vouches: rows 4 (N) and 5 ('-') of every a1 profile are zero
+  if (mem == TB_MEM_DEVICE) {
     ctx->tmp_len1.resize(np); ctx->tmp_len2.resize(np);
     TB_CUDA(ctx, cudaMemcpy(ctx->tmp_len1.data(), batch->a1.len, np * 4, cudaMemcpyDeviceToHost));
     TB_CUDA(ctx, cudaMemcpy(ctx->tmp_len2.data(), batch->a2.len, np * 4, cudaMemcpyDeviceToHost));
     l1 = ctx->tmp_len1.data(); l2 = ctx->tmp_len2.data();
-  } else if (batch->mem != TB_MEM_HOST) {
+  } else if (mem != TB_MEM_HOST) {
     return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST or TB_MEM_DEVICE");
   }
   for (size_t i = 0; i < np; ++i)
@@ -513,9 +488,10 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   B.match = sc.match; B.mismatch = sc.mismatch; B.go = sc.gap_open; B.ge = sc.gap_extend;
   B.hfree = ac.h_free != 0; B.vfree = ac.v_free != 0;
   B.a_is_seq = mode == tb::kModeSS;
+  B.mode = mode;
   B.order = nullptr;
 
-  if (batch->mem == TB_MEM_DEVICE) {
+  if (mem == TB_MEM_DEVICE) {
     Lane& L = ctx->lanes[0];
     Plan plan;
     if (int rc = make_plan(ctx, mode, traceback, all, np, sc, &plan, pp_tickets)) return rc;
@@ -527,14 +503,8 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     if (traceback && !plain_ops) TB_CUDA(ctx, L.ops.reserve(np * (size_t)ustride));
     B.scores = res->scores; B.ops = !traceback ? nullptr : plain_ops ? res->ops : L.ops.as<uint8_t>(); B.ops_stride = ustride; B.ops_len = res->ops_len;
     B.status = L.status.as<uint8_t>(); B.npairs = (int)np;
-    L.want_post = want_rows || packed_ops;
-    if (L.want_post) {
-      tb::PostBatch& P = L.post;
-      P.a_base = B.a_base; P.a_off = B.a_off; P.a_len = B.a_len; P.b_base = B.b_base; P.b_off = B.b_off; P.b_len = B.b_len;
-      P.ops = B.ops; P.ops_stride = ustride; P.ops_len = B.ops_len; P.npairs = (int)np; P.mode = mode;
-      P.row0 = res->row0; P.row1 = res->row1; P.rows_stride = res->rows_stride;
-      P.packed = packed_ops ? res->ops : nullptr; P.packed_stride = packed_ops ? res->ops_stride : 0;
-    }
+    B.row0 = res->row0; B.row1 = res->row1; B.rows_stride = res->rows_stride;
+    B.opk = packed_ops ? res->ops : nullptr; B.opk_stride = packed_ops ? res->ops_stride : 0;
     if (int rc = enqueue_gotoh(ctx, L, mode, traceback, B, plan)) return rc;
     TB_CUDA(ctx, cudaStreamSynchronize(L.stream));
     bool again = false;
@@ -662,12 +632,13 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     if (trace) TB_CUDA(ctx, cudaEventRecord(L.h0, L.stream));
     if (a_rows5) {
       // rows 0..4 enter _score; row 5 ('-') only decides consensus characters (wanted with the gapped rows). Trace profiles made
-      // by createProfile carry exact zeros in rows 4 and 5 (src/profile.h:37): when this chunk's do, 4 rows travel and the
-      // device copy's rows 4, 5 are zeroed in place -- 16 KB instead of 24 KB per 1 000-column profile.
+      // by createProfile carry exact zeros in rows 4 and 5 (src/profile.h:37): when the caller says so (TB_A1_TRACE_PROFILES; a
+      // host-side scan of 8 KB per pair would cost more than the copy it saves), 4 rows travel and the device copy's rows 4, 5
+      // are zeroed in place -- 16 KB instead of 24 KB per 1 000-column profile.
       const size_t len = (size_t)l1[0], pitch = 6 * len * 4;
       const float* src = (const float*)batch->a1.base + amin;
       int rows = want_rows ? 6 : 5;
-      if (!no_rows4 && rows45_zero(src, cn, len)) rows = 4;
+      if (!no_rows4 && a1_trace_profiles) rows = 4;
       TB_CUDA(ctx, cudaMemcpy2DAsync(L.a.p, pitch, src, pitch, (size_t)rows * len * 4, cn, cudaMemcpyHostToDevice, L.stream));
       if (rows == 4) TB_CUDA(ctx, cudaMemset2DAsync((char*)L.a.p + 4 * len * 4, pitch, 0, 2 * len * 4, cn, L.stream));
       ctx->h2d += (size_t)rows * len * 4 * cn;
@@ -687,14 +658,8 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     C.scores = L.scores.as<int32_t>(); C.ops = traceback ? L.ops.as<uint8_t>() : nullptr;
     C.ops_stride = ustride; C.ops_len = traceback ? L.ops_len.as<int32_t>() : nullptr;
     C.status = L.status.as<uint8_t>(); C.npairs = (int)cn;
-    L.want_post = want_rows || packed_ops;
-    if (L.want_post) {
-      tb::PostBatch& P = L.post;
-      P.a_base = C.a_base; P.a_off = C.a_off; P.a_len = C.a_len; P.b_base = C.b_base; P.b_off = C.b_off; P.b_len = C.b_len;
-      P.ops = C.ops; P.ops_stride = ustride; P.ops_len = C.ops_len; P.npairs = (int)cn; P.mode = mode;
-      P.row0 = want_rows ? L.row0.as<uint8_t>() : nullptr; P.row1 = want_rows ? L.row1.as<uint8_t>() : nullptr; P.rows_stride = res->rows_stride;
-      P.packed = packed_ops ? L.opk.as<uint8_t>() : nullptr; P.packed_stride = packed_ops ? res->ops_stride : 0;
-    }
+    C.row0 = want_rows ? L.row0.as<uint8_t>() : nullptr; C.row1 = want_rows ? L.row1.as<uint8_t>() : nullptr; C.rows_stride = res->rows_stride;
+    C.opk = packed_ops ? L.opk.as<uint8_t>() : nullptr; C.opk_stride = packed_ops ? res->ops_stride : 0;
     if (int rc = enqueue_gotoh(ctx, L, mode, traceback, C, cp)) return rc;
     L.chunk = (long)ci; L.p0 = p0;
 
@@ -764,7 +729,7 @@ int tb_ctx_create(tb_ctx** out, int device) {
     Lane& L = c->lanes[i];
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&L.c0) != cudaSuccess ||
         cudaEventCreate(&L.k0) != cudaSuccess || cudaEventCreate(&L.h0) != cudaSuccess || cudaEventCreate(&L.d1) != cudaSuccess ||
-        cudaEventCreate(&L.k1) != cudaSuccess || cudaEventCreate(&L.k2) != cudaSuccess || cudaEventCreate(&L.kp) != cudaSuccess) {
+        cudaEventCreate(&L.k1) != cudaSuccess || cudaEventCreate(&L.k2) != cudaSuccess) {
       cudaGetLastError();
       tb_ctx_destroy(c);
       return TB_ERR_CUDA;
@@ -791,7 +756,6 @@ void tb_ctx_destroy(tb_ctx* c) {
     if (L.k2) cudaEventDestroy(L.k2);
     if (L.h0) cudaEventDestroy(L.h0);
     if (L.d1) cudaEventDestroy(L.d1);
-    if (L.kp) cudaEventDestroy(L.kp);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   delete c;

@@ -37,6 +37,10 @@ struct GotohBatch {
   uint8_t* ops_scratch; unsigned long long ops_slot;                   // reversed traceback string
   unsigned int* counter;                                               // work-queue head
   int a_is_seq;                                                        // packed kernel: a1 items are strings (string x string pairs), not profiles
+  // optional output forms, written by the warp that finished the pair right after its traceback (emit_pair_outputs)
+  uint8_t* row0; uint8_t* row1; int64_t rows_stride;                   // gapped alignment rows; nullptr: not wanted
+  uint8_t* opk; int64_t opk_stride;                                    // ops at 2 bits each; nullptr: not wanted
+  int mode;                                                            // kModePS / kModePP / kModeSS: how a1 / a2 read
 };
 
 // Work list of the profile x profile kernel (gotoh_pp.cu). Tickets 0 .. nunits-1 are (pair, band) units of "big" pairs
@@ -51,16 +55,6 @@ struct PPWork {
   unsigned long long* big_ptr;                 // per big pair: nb x (n + 31) x 32 pointer words (traceback only)
   int* big_flags;                              // per big pair: nb progress words (columns of the bottom row published), zeroed per call
   float one;                                   // 1.0f, as a run-time value (see gotoh_pp.cu)
-};
-
-// Device view of the output post-processing (post_ops.cu): gapped rows and 2-bit packed ops from the one-byte-per-op strings.
-struct PostBatch {
-  const void* a_base; const int64_t* a_off; const int32_t* a_len;
-  const void* b_base; const int64_t* b_off; const int32_t* b_len;
-  const uint8_t* ops; int64_t ops_stride; const int32_t* ops_len;
-  uint8_t* row0; uint8_t* row1; int64_t rows_stride;      // nullptr: not wanted
-  uint8_t* packed; int64_t packed_stride;                  // nullptr: not wanted
-  int npairs, mode;
 };
 
 // Device view of a decompose-sweep batch (sweep.cu).
@@ -178,6 +172,93 @@ __device__ __forceinline__ int sub_profile4(const float p1[5], const float p2[5]
     for (int k2 = 0; k2 < 4; ++k2)
       acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(p1[k1], p2[k2]), k1 == k2 ? fmatch : fmismatch));
   return __float2int_rz(acc);
+}
+
+// ---- output forms made from the traceback string (one warp, one pair) -------------------------------------------------
+// What gotoh() leaves behind besides the score:
+//   * the two gapped alignment rows, reference src/align.h:196-223 (strings) and :254-293 (profiles: per column the first strict
+//     maximum over the six rows, indices >= 4 print 'N', never '-') -- _createAlignment;
+//   * the s/h/v string at 2 bits per op (4 ops per byte, first op in the low bits: 0 = 's', 1 = 'h', 2 = 'v').
+// Called by the warp that has just written the pair's one-byte-per-op string (still in L1/L2), so the host neither walks 10^5
+// strings per batch nor receives 1 B per op when 2 bits do -- and no second kernel has to find room next to persistent grids.
+__device__ __forceinline__ char out_cons_char(const float* p, int len, int pos) {   // src/align.h:254-270
+  int best = 0;
+  float bv = p[pos];
+#pragma unroll
+  for (int k = 1; k < 6; ++k) {
+    const float v = p[(size_t)k * len + pos];
+    if (v > bv) { bv = v; best = k; }                     // float compare == the reference's double compare of the same floats
+  }
+  return best < 4 ? "ACGT"[best] : 'N';
+}
+__device__ __forceinline__ char out_onehot_char(unsigned char ch) {                 // src/align.h:121-136 seen through _profileConsChar
+  const unsigned char u = ch & 0xDFu;
+  return u == 'C' ? 'C' : u == 'G' ? 'G' : u == 'T' ? 'T' : (u == 'N' || ch == '-') ? 'N' : 'A';   // 'A', and the all-zero column: index 0 wins
+}
+static __device__ __noinline__ void emit_pair_outputs_impl(const void* a, int m, const void* b, int n, int mode, uint8_t* r0, uint8_t* r1, uint8_t* pk,
+                                                          const uint8_t* __restrict__ ops, int L, int lane) {
+  // 128 ops per iteration, four consecutive ones per lane (the strings start 16-byte aligned: strides are multiples of 16)
+  // (word accesses only when the caller's strides and pointers keep every string 4-byte aligned)
+  const bool al = ((reinterpret_cast<unsigned long long>(ops) | (r0 ? reinterpret_cast<unsigned long long>(r0) | reinterpret_cast<unsigned long long>(r1) : 0ull)) & 3ull) == 0ull;
+  int rbase = 0, cbase = 0;
+  for (int j0 = 0; j0 < L; j0 += 128) {
+    const int j = j0 + 4 * lane;
+    unsigned w = 0u;
+    if (j < L) {
+      if (al) w = *reinterpret_cast<const unsigned*>(ops + j);
+      else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (j + q < L) w |= (unsigned)ops[j + q] << (8 * q);
+      }
+    }
+    unsigned char op[4];
+    bool in[4];
+    int nr = 0, nc = 0;
+    unsigned byte = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      op[q] = (unsigned char)(w >> (8 * q));
+      in[q] = j + q < L;
+      nr += in[q] && op[q] != 'h';
+      nc += in[q] && op[q] != 'v';
+      byte |= (in[q] ? (op[q] == 'h' ? 1u : op[q] == 'v' ? 2u : 0u) : 0u) << (2 * q);
+    }
+    if (pk && in[0]) pk[(j0 >> 2) + lane] = (uint8_t)byte;
+    // exclusive prefix sums of (nr, nc) over the lanes: both counts are <= 4, packed into one word
+    unsigned both = (unsigned)nr | ((unsigned)nc << 16), scan = both;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(kFull, scan, d);
+      if (lane >= d) scan += t;
+    }
+    const unsigned tot = __shfl_sync(kFull, scan, 31);
+    if (r0) {
+      int r = rbase + (int)((scan - both) & 0xffffu), c = cbase + (int)((scan - both) >> 16);
+      unsigned x4 = 0, y4 = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        char x = '-', y = '-';
+        const bool ar = in[q] && op[q] != 'h', ac = in[q] && op[q] != 'v';
+        if (ar && r < m) x = mode == kModeSS ? ((const char*)a)[r] : out_cons_char((const float*)a, m, r);
+        if (ac && c < n) y = mode == kModePP ? out_cons_char((const float*)b, n, c) : mode == kModeSS ? ((const char*)b)[c] : out_onehot_char(((const unsigned char*)b)[c]);
+        r += ar; c += ac;
+        x4 |= (unsigned)(unsigned char)x << (8 * q); y4 |= (unsigned)(unsigned char)y << (8 * q);
+      }
+      if (in[3] && al) {
+        *reinterpret_cast<unsigned*>(r0 + j) = x4; *reinterpret_cast<unsigned*>(r1 + j) = y4;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (in[q]) { r0[j + q] = (uint8_t)(x4 >> (8 * q)); r1[j + q] = (uint8_t)(y4 >> (8 * q)); }
+      }
+    }
+    rbase += (int)(tot & 0xffffu); cbase += (int)(tot >> 16);
+  }
+}
+__device__ __forceinline__ void emit_pair_outputs(const GotohBatch& B, int pi, const uint8_t* ops, int L, int lane) {
+  const void* const a = B.mode == kModeSS ? (const void*)((const char*)B.a_base + B.a_off[pi]) : (const void*)((const float*)B.a_base + B.a_off[pi]);
+  const void* const b = B.mode == kModePP ? (const void*)((const float*)B.b_base + B.b_off[pi]) : (const void*)((const char*)B.b_base + B.b_off[pi]);
+  emit_pair_outputs_impl(a, B.a_len[pi], b, B.b_len[pi], B.mode, B.row0 ? B.row0 + (long long)pi * B.rows_stride : nullptr,
+                         B.row0 ? B.row1 + (long long)pi * B.rows_stride : nullptr, B.opk ? B.opk + (long long)pi * B.opk_stride : nullptr, ops, L, lane);
 }
 
 // ---- pointer scratch layout -------------------------------------------------------------------------------

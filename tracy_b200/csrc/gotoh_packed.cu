@@ -217,6 +217,7 @@ __device__ __forceinline__ void pk_build_tables(int* tabA, int* tabB, const void
 struct PkPair {
   const void* a; const unsigned char* b;
   int m, n, T, NQ, go, ge, goe, bias;
+  unsigned smn, hmn;               // the fields of S[m][n] and H[m][n] (the free end-gap run starts at (m, n) iff they are equal)
   bool hfree, vfree;
   float fmatch, fmismatch;
 };
@@ -261,6 +262,37 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
   const long long t_begin = TB_CLK(); (void)t_begin;
   TB_STAT_ADD(0, 1);
 
+  // ---- the free end-gap run along row m, without recomputing it ----
+  // With free horizontal end gaps H[m][c] is the running maximum of S[m][0 .. c-1]. The walk enters state 'h' at (m, n) iff
+  // S[m][n] == H[m][n] (src/gotoh.h:134, 149) and leaves it at the column c*+1 whose H was opened from S (src/gotoh.h:137, 157),
+  // i.e. where c* is the LAST strict new maximum of row m = the leftmost column that attains the maximum M = H[m][n]. Columns
+  // right of c*+1 cannot end the run. The column checkpoints hold H[m][c_q] for one column in every 32: the first c_q with
+  // H[m][c_q] == M bounds c* from above (c* <= c_q - 1), so the run is emitted up to c_q in one go and the first round starts
+  // there in state 'h' -- no horizontal rounds over thousands of columns, no 32-columns-per-iteration walk through them.
+  bool jump_round = false;
+  if (hfree && n > 0 && P.smn == P.hmn) {
+    const int pass = (m - 1) >> 10, rr0 = (m - 1) & 1023;
+    const int mh = rr0 >> 9, ml = (rr0 & 511) >> 4, mi = rr0 & 15;
+    const unsigned* cw = reinterpret_cast<const unsigned*>(colck);
+    const int nq = T >> 5;                                            // checkpoints written: one per full chunk of 32 steps
+    int cstart = n;
+    for (int q0 = 0; q0 < nq; q0 += 32) {
+      const int q = q0 + lane;
+      const int cq = 32 * (q + 1) - ml - 32 * mh;                     // the column lane `ml` was on when checkpoint q was taken
+      bool hit = false;
+      if (q < nq && cq >= 1 && cq <= n) {
+        const unsigned w = cw[((((unsigned long long)pass * (unsigned)P.NQ + (unsigned)q) * 8ull + 4ull + (unsigned)(mi >> 2)) * 32ull + (unsigned)ml) * 4ull + (unsigned)(mi & 3)];
+        hit = (mh ? w >> 16 : w & 0xffffu) == P.hmn;
+      }
+      const unsigned any = __ballot_sync(kFull, hit);
+      if (any) { cstart = 32 * (q0 + __ffs(any)) - ml - 32 * mh; break; }
+    }
+    const int cnt = n - cstart;
+    for (int j = lane; j < cnt; j += 32) ops_rev[k + j] = 'h';
+    k += cnt;
+    c = cstart; state = 1; jump_round = true;
+  }
+
   while (r > 0 || c > 0) {
     const long long t_plan = TB_CLK(); (void)t_plan;
     if (r == 0 || c == 0) {                                         // row 0 is all 'h', column 0 all 'v'
@@ -274,8 +306,10 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
     const int pass = (r - 1) >> 10, rr0 = (r - 1) & 1023;
     const int v0 = ((rr0 >> 9) << 5) + ((rr0 & 511) >> 4), i0 = rr0 & 15;       // current block (0..63) and row inside it
     if (pass != tab_pass) { pk_build_tables<CLASSES, ASEQ>(tabA, tabB, P.a, m, pass * kPkRows, P.fmatch, P.fmismatch, lane); tab_pass = pass; }
-    // the free end-gap row almost always starts with a long horizontal run: look left first there
-    const bool horizontal = state == 1 || (first_round && hfree && r == m && state == 0);
+    // state 'h' lays all lanes on the current block, to the left -- except right after the jump along the free end-gap row, where
+    // the run is known to end within 32 columns: that round is a diagonal round whose first span holds the end of the run
+    const bool jumped = jump_round && first_round;
+    const bool horizontal = state == 1 && !jumped;
     first_round = false;
     TB_STAT_ADD(1, 1); TB_STAT_ADD(2, horizontal ? 1 : 0);
     int vk, cA;                                                     // this lane's block and the checkpoint column its span starts after
@@ -291,8 +325,10 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
       act = vk >= 0;
       if (!act) vk = 0;
       const int base_c = 32 - (vk & 31) - 32 * (vk >> 5);
-      const int e = c + 15 - i0 - 16 * lane;                        // column where a pure diagonal crosses this block's bottom row
+      // after the jump the diagonal starts somewhere in (c - 32, c]: aim the blocks above at the middle of that range
+      const int e = (jumped ? c - 16 : c) + 15 - i0 - 16 * lane;    // column where a pure diagonal crosses this block's bottom row
       cA = base_c + 32 * ((e - 24 - base_c) >> 5);                  // last checkpoint column <= e - 24
+      if (jumped && lane == 0) cA = base_c + 32 * ((c - kPkSpan - base_c + 31) >> 5);   // first checkpoint column >= c - 64: the span ends at or after c
       act = act && cA + kPkSpan >= 1;                               // a span left of column 1 holds nothing (column 0 is a closed form)
     }
     const int half = vk >> 5, l = vk & 31;
@@ -586,7 +622,7 @@ gotoh_packed_kernel(const GotohBatch B) {
     uint8_t* const ops_out = TRACEBACK ? B.ops + (long long)pi * B.ops_stride : nullptr;
     const int rr_m = (m - 1) & (kPkRows - 1);                // where row m lives in the last pass
     const int m_half = rr_m >> 9, m_lane = (rr_m & 511) >> 4, m_i = rr_m & 15;
-    unsigned score_word = 0;
+    unsigned score_word = 0, hmn_word = 0;
 
     for (int pass = 0; pass < npass; ++pass) {
       const int base = pass * kPkRows;
@@ -718,7 +754,7 @@ gotoh_packed_kernel(const GotohBatch B) {
           if (MORE) { if (lane == 31 && c_hi >= 1 && c_hi <= n) bot[c_hi] = __byte_perm(bs, bv, 0x7632); }   // S | V << 16 of row base+1024
           else if (EDGE && st == cap_st) {                                    // S[m][n] passes through this lane now
 #pragma unroll
-            for (int i = 0; i < kRowsPerLane; ++i) if (i == m_i) score_word = sl[i];
+            for (int i = 0; i < kRowsPerLane; ++i) if (i == m_i) { score_word = sl[i]; hmn_word = hh[i]; }
           }
         }
         pw += 32; prow += 32;
@@ -753,6 +789,7 @@ gotoh_packed_kernel(const GotohBatch B) {
 
     const unsigned sw = __shfl_sync(kFull, score_word, m_lane);
     const int score = (int)(m_half ? sw >> 16 : sw & 0xffffu) - bias;
+    [[maybe_unused]] const unsigned hw = __shfl_sync(kFull, hmn_word, m_lane);
 
     if (TRACEBACK) {
       __syncwarp();
@@ -761,6 +798,7 @@ gotoh_packed_kernel(const GotohBatch B) {
         PkPair pp;
         pp.a = a; pp.b = b; pp.m = m; pp.n = n; pp.T = T; pp.NQ = NQ; pp.go = go; pp.ge = ge; pp.goe = goe; pp.bias = bias;
         pp.hfree = hfree; pp.vfree = vfree; pp.fmatch = fmatch; pp.fmismatch = fmismatch;
+        pp.smn = m_half ? sw >> 16 : sw & 0xffffu; pp.hmn = m_half ? hw >> 16 : hw & 0xffffu;
         L = walk_traceback_ckpt<CLASSES, ASEQ, VFREE>(pp, rowck, colck, span, tabA, tabB, npass - 1, ops_rev, lane);
       } else {
         L = walk_traceback_packed(ptr, T, m, n, ops_rev, lane);
@@ -774,6 +812,7 @@ gotoh_packed_kernel(const GotohBatch B) {
         for (int u = 0; u < 8; ++u) { const int j = j0 + 32 * u + lane; if (j < L) ops_out[j] = ch[u]; }
       }
       if (lane == 0) B.ops_len[pi] = L;
+      if (B.row0 || B.opk) { __syncwarp(); emit_pair_outputs(B, pi, ops_out, L, lane); }
     }
     if (lane == 0) { B.scores[pi] = score; B.status[pi] = 1; atomicAdd(B.counter + 1, 1u); }
   }

@@ -241,8 +241,6 @@ def run_b200(args, rank, world, local_rank):
     d_scores = torch.zeros(P, dtype=torch.int32, device=dev)
     d_ops = torch.zeros((P, stride), dtype=torch.uint8, device=dev)
     d_len = torch.zeros(P, dtype=torch.int32, device=dev)
-    d_row0 = torch.zeros((P, stride), dtype=torch.uint8, device=dev)
-    d_row1 = torch.zeros((P, stride), dtype=torch.uint8, device=dev)
     counts = [P] * world
     g_scores = torch.empty(P * world, dtype=torch.int32, device=dev) if world > 1 else None
     bcast = None
@@ -266,8 +264,7 @@ def run_b200(args, rank, world, local_rank):
 
     def device_step():
         ctx.gotoh_device("ps", d_prof.data_ptr(), d_aoff.data_ptr(), d_alen.data_ptr(), d_win.data_ptr(), d_boff.data_ptr(), d_blen.data_ptr(), P,
-                         d_scores.data_ptr(), d_ops.data_ptr(), stride, d_len.data_ptr(), sc, ac,
-                         row0=d_row0.data_ptr(), row1=d_row1.data_ptr(), rows_stride=stride)
+                         d_scores.data_ptr(), d_ops.data_ptr(), stride, d_len.data_ptr(), sc, ac)
         ms = ctx.last_call_ms()
         k = ctx.last_kernel_ms()
         if world > 1:

@@ -77,6 +77,7 @@ class Context {
 };
 
 namespace detail {
+template <typename T> inline void resize_align(Matrix<T>& a, std::size_t r, std::size_t c) { a.resize(r, c); }   // the header's own stand-in, with or without Boost around
 #if defined(TRACY_B200_WITH_BOOST) || defined(BOOST_MULTI_ARRAY_HPP) || defined(BOOST_MULTI_ARRAY_RG071801_HPP)
 template <typename TAlign> inline void resize_align(TAlign& a, std::size_t r, std::size_t c) { a.resize(boost::extents[r][c]); }   // src/align.h:200,277
 #else
@@ -100,7 +101,7 @@ inline int run_pair(Context& g, TA const& a1, TB const& a2, tb_align_config ac, 
   int32_t m = item_len(a1), n = item_len(a2), score = 0, L = 0;
   std::vector<uint8_t> buf(ops ? (std::size_t)m + n + 16 : 0);
   tb_batch b{{item_ptr(a1), &off, &m}, {item_ptr(a2), &off, &n}, 1, TB_MEM_HOST};
-  tb_result r{&score, ops ? buf.data() : nullptr, (int64_t)buf.size(), ops ? &L : nullptr};
+  tb_result r{&score, ops ? buf.data() : nullptr, (int64_t)buf.size(), ops ? &L : nullptr, nullptr, nullptr, 0, 0};
   constexpr int kind = kind_of<TA, TB>();
   g.check(kind == 0 ? tb_gotoh_pp(g.get(), &b, sc, ac, &r) : kind == 1 ? tb_gotoh_ss(g.get(), &b, sc, ac, &r) : tb_gotoh_ps(g.get(), &b, sc, ac, &r));
   if (ops) ops->assign(buf.begin(), buf.begin() + L);
@@ -135,9 +136,11 @@ inline int gotoh(Context& g, TA const& a1, TB const& a2, TAlign& align, TAlignCo
 // Many independent pairs in one GPU call. a1[i] / a2[i] are pointers to the caller's objects (no copies are made of
 // profiles that already sit back to back; otherwise they are packed once). ops (optional) receives the s/h/v strings in
 // start->end order (see tracy_b200.h); rows can be made from them with tb_rows_from_ops.
+// rows (optional): the two gapped rows of every pair (what gotoh() leaves in `align`), made on the device.
 template <typename TA, typename TB, typename TAlignConfig, typename TScore>
 inline std::vector<int32_t> gotohBatch(Context& g, std::vector<const TA*> const& a1, std::vector<const TB*> const& a2, TAlignConfig const& ac,
-                                       TScore const& sc, std::vector<std::string>* ops = nullptr) {
+                                       TScore const& sc, std::vector<std::string>* ops = nullptr,
+                                       std::vector<std::pair<std::string, std::string> >* rows = nullptr) {
   const std::size_t n = a1.size();
   if (a2.size() != n) throw Error(TB_ERR_INVALID, "gotohBatch: a1 and a2 differ in length");
   std::vector<int32_t> scores(n, 0);
@@ -160,10 +163,11 @@ inline std::vector<int32_t> gotohBatch(Context& g, std::vector<const TA*> const&
   }
   if (pa.empty()) pa.resize(1);
   if (pb.empty()) pb.resize(1);
-  std::vector<uint8_t> obuf(ops ? n * (std::size_t)stride : 0);
-  std::vector<int32_t> olen(ops ? n : 0);
+  std::vector<uint8_t> obuf(ops ? n * (std::size_t)stride : 0), r0buf(rows ? n * (std::size_t)stride : 0), r1buf(rows ? n * (std::size_t)stride : 0);
+  std::vector<int32_t> olen(ops || rows ? n : 0);
   tb_batch b{{pa.data(), oa.data(), la.data()}, {pb.data(), ob.data(), lb.data()}, n, TB_MEM_HOST};
-  tb_result r{scores.data(), ops ? obuf.data() : nullptr, stride, ops ? olen.data() : nullptr};
+  tb_result r{scores.data(), ops ? obuf.data() : nullptr, stride, (ops || rows) ? olen.data() : nullptr,
+              rows ? r0buf.data() : nullptr, rows ? r1buf.data() : nullptr, rows ? stride : 0, 0};
   constexpr int kind = detail::kind_of<TA, TB>();
   const tb_align_config acc = detail::ac_of(ac);
   const tb_score scc = detail::sc_of(sc);
@@ -171,6 +175,13 @@ inline std::vector<int32_t> gotohBatch(Context& g, std::vector<const TA*> const&
   if (ops) {
     ops->resize(n);
     for (std::size_t i = 0; i < n; ++i) (*ops)[i].assign(obuf.begin() + i * stride, obuf.begin() + i * stride + olen[i]);
+  }
+  if (rows) {
+    rows->resize(n);
+    for (std::size_t i = 0; i < n; ++i) {
+      (*rows)[i].first.assign(r0buf.begin() + i * stride, r0buf.begin() + i * stride + olen[i]);
+      (*rows)[i].second.assign(r1buf.begin() + i * stride, r1buf.begin() + i * stride + olen[i]);
+    }
   }
   return scores;
 }
@@ -1074,6 +1085,184 @@ inline std::vector<int32_t> alignGenomeBatch(Context& g, Index const& index, std
   detail::trim_and_align(g, c, live, trimmed, full, rs, final_align, scores, semiglobal, sc);
   if (anchored) *anchored = ok;
   return scores;
+}
+
+// ---- `tracy decompose`: the DP sequence of indigo() for many traces -----------------------------------------------------------
+// trimmedSeq(str, ltrim, rtrim) -- reference src/abif.h:68-75.
+inline std::string trimmedSeq(std::string const& str, uint32_t ltrim, uint32_t rtrim) {
+  if ((std::size_t)ltrim + rtrim + 1 >= str.size()) return str;
+  return str.substr(ltrim, str.size() - ltrim - rtrim);
+}
+
+// bool findHomozygousBreakpoint(align, bp) -- reference src/decompose.h:59-128: the breakpoint of a homozygous indel from the
+// mismatch density in the 25 columns either side of every alignment column. The window counts come from one prefix sum (the
+// reference recounts both windows per column); counts / 25 in double and the float bestDiff field compare as there.
+template <typename TAlign, typename TBreakpoint>
+inline bool findHomozygousBreakpoint(TAlign const& align, TBreakpoint& bp, std::ostream* err = &std::cerr) {
+  const long L = (long)align.shape()[1];
+  long first = 0, last = 0, varIndex = 0;
+  for (long j = 0; j < L; ++j) {
+    if (align[0][j] != '-' && align[1][j] != '-') { first = j; break; }
+    if (align[0][j] != '-') ++varIndex;
+  }
+  for (long j = L - 1; j >= 0; --j)
+    if (align[0][j] != '-' && align[1][j] != '-') { last = j; break; }
+  if (first >= last) { if (err) *err << "No valid alignment found between consensus and reference!" << std::endl; return false; }
+  bp.bestDiff = 0; bp.traceleft = true; bp.breakpoint = 0;
+  const long w = 25;
+  if (last < first + 2 * w) { if (err) *err << "Alignment too short between consensus and reference!" << std::endl; return false; }
+  std::vector<int32_t> pre((std::size_t)L + 1, 0);
+  for (long j = 0; j < L; ++j) pre[(std::size_t)j + 1] = pre[(std::size_t)j] + (align[0][j] != align[1][j] ? 1 : 0);
+  for (long i = first; i < first + w; ++i) if (align[0][i] != '-') ++varIndex;
+  for (long i = first + w; i < last - w; ++i) {
+    if (align[0][i] != '-') ++varIndex;
+    const double left = (double)(pre[(std::size_t)i] - pre[(std::size_t)(i - w)]) / (double)w;
+    const double right = (double)(pre[(std::size_t)(i + w)] - pre[(std::size_t)i]) / (double)w;
+    const double diff = right > left ? right - left : left - right;
+    if (diff > bp.bestDiff) { bp.breakpoint = (uint32_t)varIndex; bp.bestDiff = diff; bp.traceleft = left < right; }
+  }
+  bp.indelshift = true;
+  if (bp.bestDiff < 0.25) { bp.indelshift = false; bp.breakpoint = (uint32_t)varIndex; bp.traceleft = true; bp.bestDiff = 0; }
+  return true;
+}
+
+// generateSecondaryDecomposed(tr, bc) -- reference src/decompose.h:378-410: the second allele as plain nucleotides; an IUPAC pair
+// resolves to its higher peak at the basecall position (the pair's first base needs a strictly higher peak).
+template <typename TTrace, typename TBaseCalls>
+inline void generateSecondaryDecomposed(TTrace const& tr, TBaseCalls& bc) {
+  bc.secDecompose.resize(bc.secondary.size());
+  const std::size_t n = std::min(bc.primary.size(), bc.secondary.size());
+  for (std::size_t i = 0; i < n; ++i) {
+    const char s = bc.secondary[i];
+    if (bc.primary[i] == s || s == 'A' || s == 'C' || s == 'G' || s == 'T') { bc.secDecompose[i] = s; continue; }
+    const char* two = s == 'R' ? "AG" : s == 'Y' ? "CT" : s == 'S' ? "CG" : s == 'W' ? "AT" : s == 'K' ? "GT" : s == 'M' ? "AC" : nullptr;
+    if (!two) { bc.secDecompose[i] = 'N'; continue; }
+    const std::size_t at = bc.bcPos[i];
+    bc.secDecompose[i] = tr.traceACGT[detail::base_slot(two[0])][at] > tr.traceACGT[detail::base_slot(two[1])][at] ? two[0] : two[1];
+  }
+}
+
+// What indigo() holds for one trace after its DP sequence (reference src/indigo.h:190-388); ok = false where indigo() returns -1
+// ("Alignment of trace to reference failed!", no usable homozygous breakpoint).
+template <typename TAlign, typename TRefSlice, typename TBreakpoint>
+struct DecomposeOut {
+  bool ok = false;
+  TBreakpoint bp;                                                       // findBreakpoint / findHomozygousBreakpoint
+  TAlign align; int32_t aliTrimScore = 0;                               // trimmed trace profile against the oriented reference
+  std::vector<std::pair<int32_t, int32_t> > dcp;                        // the .decomp table
+  std::pair<double, double> a1a2 = std::make_pair(0.5, 0.5);            // allelicFraction
+  TAlign final1, final2, final3; TRefSlice allele1, allele2, secrs;     // P.align1 / .align2 / .align3
+  int32_t a1Score = 0, a2Score = 0, a3Score = 0;
+};
+
+// decomposeBatch -- `tracy decompose` against single-FASTA references for many basecalled traces: createProfile, findBreakpoint,
+// the two orientation scores (strict '>' keeps forward), the semi-global alignment with its score gate, findHomozygousBreakpoint
+// where no heterozygous shift shows, decomposeAlleles, generateSecondaryDecomposed, allelicFraction and the three allele
+// alignments -- every DP / sweep / fit stage ONE batched GPU call over all traces, the glue in between on the host.
+// tr / bc / rs: tracy's Trace, BaseCalls (primary, secondary, secDecompose are updated in place) and ReferenceSlice (refslice = the
+// reference sequence on entry; forward, refslice, pos, kmersupport as indigo() leaves them). c: trimLeft, trimRight, maxindel, madc.
+template <typename TConfig, typename TTrace, typename TBaseCalls, typename TRefSlice, typename TOut, typename TScore>
+inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrace*> const& tr, std::vector<TBaseCalls*> const& bc,
+                           std::vector<TRefSlice*> const& rs, std::vector<TOut>& out, TScore const& sc, std::ostream* log = nullptr) {
+  typedef Matrix<float> TProfile;
+  typedef decltype(out[0].align) TAlign;
+  typedef decltype(out[0].bp) TBreakpoint;
+  const std::size_t n = tr.size();
+  out.assign(n, TOut());
+  if (n == 0) return;
+  const AlignConfig<true, false> semiglobal;
+  std::vector<TProfile> prof(n);
+  {
+    std::vector<const TBaseCalls*> cbc(bc.begin(), bc.end());
+    std::vector<TProfile*> pp(n);
+    for (std::size_t i = 0; i < n; ++i) pp[i] = &prof[i];
+    createProfileBatch(g, tr, cbc, pp, (int32_t)c.trimLeft, (int32_t)c.trimRight);             // src/indigo.h:190-192
+  }
+  std::vector<std::string> rev(n);
+  std::vector<const TProfile*> pa(2 * n);
+  std::vector<const std::string*> pb(2 * n);
+  for (std::size_t i = 0; i < n; ++i) {
+    findBreakpoint(prof[i], out[i].bp);                                                          // src/indigo.h:195-196
+    rev[i] = rs[i]->refslice; reverseComplement(rev[i]);
+    pa[i] = pa[n + i] = &prof[i]; pb[i] = &rs[i]->refslice; pb[n + i] = &rev[i];
+  }
+  const std::vector<int32_t> gs = gotohBatch(g, pa, pb, semiglobal, sc);                         // gsFwd / gsRev, src/indigo.h:235-236
+  for (std::size_t i = 0; i < n; ++i) {
+    rs[i]->kmersupport = 0; rs[i]->pos = 0;
+    rs[i]->forward = gs[i] > gs[n + i];                                                          // src/indigo.h:243
+    if (!rs[i]->forward) rs[i]->refslice.swap(rev[i]);
+  }
+  pa.resize(n); pb.resize(n);
+  std::vector<std::pair<std::string, std::string> > rows;
+  const std::vector<int32_t> ali = gotohBatch(g, pa, pb, semiglobal, sc, nullptr, &rows);        // src/indigo.h:302
+  typedef DecomposeItem<TAlign, TBaseCalls, TBreakpoint, TRefSlice, std::vector<std::pair<int32_t, int32_t> > > TItem;
+  std::vector<TItem> items;
+  std::vector<std::size_t> live;
+  for (std::size_t i = 0; i < n; ++i) {
+    const double seqsize = (double)prof[i].shape()[1], matchFraction = 0.35;
+    const double scoreThreshold = seqsize * matchFraction * sc.match + seqsize * (1 - matchFraction) * sc.mismatch;   // src/indigo.h:303-305
+    out[i].aliTrimScore = ali[i];
+    if (ali[i] <= scoreThreshold) continue;
+    const std::size_t L = rows[i].first.size();
+    detail::resize_align(out[i].align, 2, L);
+    for (std::size_t j = 0; j < L; ++j) { out[i].align[0][j] = rows[i].first[j]; out[i].align[1][j] = rows[i].second[j]; }
+    if (!out[i].bp.indelshift && !findHomozygousBreakpoint(out[i].align, out[i].bp, nullptr)) continue;   // src/indigo.h:314-317
+    out[i].ok = true;
+    live.push_back(i);
+  }
+  items.resize(live.size());
+  for (std::size_t k = 0; k < live.size(); ++k) {
+    const std::size_t i = live[k];
+    items[k].align = &out[i].align; items[k].bc = bc[i]; items[k].bp = out[i].bp; items[k].rs = rs[i]; items[k].dcp = &out[i].dcp;
+  }
+  decomposeAllelesBatch(g, c, items, log);                                                       // src/indigo.h:340
+  if (live.empty()) return;
+  // allelicFraction (src/indigo.h:350) reads bcPos[i + trimLeft] even where trimmedSeq() left a short read untrimmed (out of
+  // bounds there): such reads keep the start value
+  std::vector<const TTrace*> ftr; std::vector<const TBaseCalls*> fbc; std::vector<std::size_t> fit;
+  for (std::size_t i : live) {
+    generateSecondaryDecomposed(*tr[i], *bc[i]);                                                 // src/indigo.h:344
+    if ((std::size_t)c.trimLeft + c.trimRight + 1 < bc[i]->primary.size()) { ftr.push_back(tr[i]); fbc.push_back(bc[i]); fit.push_back(i); }
+  }
+  const std::vector<std::pair<double, double> > fr = allelicFractionBatch(g, c, ftr, fbc);
+  for (std::size_t k = 0; k < fit.size(); ++k) out[fit[k]].a1a2 = fr[k];
+  // allele-specific alignments (src/indigo.h:355-388): string x string
+  const std::size_t m = live.size();
+  std::vector<std::string> pri(m), sec(m);
+  std::vector<const std::string*> qa(2 * m), qb(2 * m);
+  for (std::size_t k = 0; k < m; ++k) {
+    const std::size_t i = live[k];
+    pri[k] = trimmedSeq(bc[i]->primary, c.trimLeft, c.trimRight);
+    sec[k] = trimmedSeq(bc[i]->secDecompose, c.trimLeft, c.trimRight);
+    out[i].allele1 = *rs[i]; out[i].allele2 = *rs[i];
+    qa[k] = &pri[k]; qa[m + k] = &sec[k]; qb[k] = qb[m + k] = &rs[i]->refslice;
+  }
+  std::vector<std::string> ops;
+  gotohBatch(g, qa, qb, semiglobal, sc, &ops);                                                   // gotoh(pri / sec, rs.refslice, ...)
+  for (std::size_t k = 0; k < 2 * m; ++k) {
+    Matrix<char> al;
+    const std::size_t L = ops[k].size();
+    al.resize(2, L);                                                                             // only the gap pattern matters to trimReferenceSlice
+    for (std::size_t j = 0; j < L; ++j) { al[0][j] = ops[k][j] == 'h' ? '-' : 'X'; al[1][j] = ops[k][j] == 'v' ? '-' : 'X'; }
+    TRefSlice& dst = k < m ? out[live[k]].allele1 : out[live[k - m]].allele2;
+    trimReferenceSlice(c, al, dst);
+    qb[k] = &dst.refslice;
+  }
+  const std::vector<int32_t> s2 = gotohBatch(g, qa, qb, semiglobal, sc, nullptr, &rows);         // final1 / final2
+  auto fill = [](TAlign& dst, std::pair<std::string, std::string> const& r) {
+    detail::resize_align(dst, 2, r.first.size());
+    for (std::size_t j = 0; j < r.first.size(); ++j) { dst[0][j] = r.first[j]; dst[1][j] = r.second[j]; }
+  };
+  for (std::size_t k = 0; k < m; ++k) {
+    TOut& o = out[live[k]];
+    o.a1Score = s2[k]; o.a2Score = s2[m + k];
+    fill(o.final1, rows[k]); fill(o.final2, rows[m + k]);
+    o.secrs.refslice = sec[k]; o.secrs.forward = true; o.secrs.pos = 0; o.secrs.chr = "Alt2";    // src/indigo.h:381-386
+    qa[k] = &pri[k]; qb[k] = &sec[k];
+  }
+  qa.resize(m); qb.resize(m);
+  const std::vector<int32_t> s3 = gotohBatch(g, qa, qb, AlignConfig<false, false>(), sc, nullptr, &rows);   // allele 1 vs allele 2, global
+  for (std::size_t k = 0; k < m; ++k) { out[live[k]].a3Score = s3[k]; fill(out[live[k]].final3, rows[k]); }
 }
 
 }  // namespace tracy_b200

@@ -49,8 +49,8 @@ def load_gotoh_golden():
     return cases
 
 
-def load_decompose_golden():
-    z = np.load(os.path.join(ROOT, "tests", "golden", "decompose_golden.npz"))
+def load_decompose_golden(name="decompose_golden.npz"):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name))
     cases = []
     for i in range(int(z["n"])):
         trimL, trimR, maxindel, madc, bp, nref = (int(x) for x in z[f"cfg{i}"])

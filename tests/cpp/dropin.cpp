@@ -399,6 +399,95 @@ static void assemble_check(tracy_b200::Context& g) {
   }
 }
 
+// indigo()'s DP sequence per trace from the reference's own functions (src/indigo.h:190-388) against tracy_b200::decomposeBatch:
+// heterozygous indels, homozygous indels (findHomozygousBreakpoint), clean traces and one unrelated trace (score gate).
+struct IndigoCfg { uint16_t trimLeft, trimRight, maxindel, madc; };
+static void decompose_driver_check(tracy_b200::Context& g) {
+  const int N = 14;
+  IndigoCfg c; c.trimLeft = 30; c.trimRight = 40; c.maxindel = 1000; c.madc = 5;
+  tracy::DnaScore<int32_t> sc(3, -5, -10, -4);
+  tracy::AlignConfig<true, false> semiglobal;
+  std::vector<tracy::Trace> tr(N);
+  std::vector<tracy::BaseCalls> bc1(N), bc2(N);
+  std::vector<tracy::ReferenceSlice> rs1(N), rs2(N);
+  for (int i = 0; i < N; ++i) {
+    const std::string ref = random_seq(1500 + 100 * (i % 4));
+    const int start = 200 + (int)(rng() % 200), L = 420 + (int)(rng() % 120), bpos = 140 + (int)(rng() % 100);
+    std::string a1 = ref.substr(start, L), a2;
+    const int kind = i % 5;                                              // 0 het deletion, 1 het insertion, 2 homozygous deletion, 3 clean, 4 SNVs only
+    if (kind == 0) a2 = (ref.substr(start, bpos) + ref.substr(start + bpos + 3 + (int)(rng() % 20))).substr(0, L);
+    else if (kind == 1) a2 = (ref.substr(start, bpos) + random_seq(2 + (int)(rng() % 15)) + ref.substr(start + bpos)).substr(0, L);
+    else if (kind == 2) a1 = (ref.substr(start, bpos) + ref.substr(start + bpos + 12)).substr(0, L);
+    else if (kind == 4) { a2 = a1; for (int q = 0; q < 5; ++q) a2[rng() % a2.size()] = "ACGT"[rng() % 4]; }
+    if (i == N - 1) a1 = random_seq(L);                                  // matches nothing: "Alignment of trace to reference failed!"
+    make_trace(a1, a2, 0.6, tr[i]);
+    tracy::basecall(tr[i], bc1[i], 0.33f);
+    bc2[i] = bc1[i];
+    rs1[i].refslice = i % 2 ? ref : [&] { std::string r = ref; tracy::reverseComplement(r); return r; }();
+    rs1[i].chr = "ref"; rs1[i].filetype = 1;
+    rs2[i] = rs1[i];
+  }
+  // reference, one trace at a time
+  struct Want { bool ok = false; tracy::TraceBreakpoint bp; TAlign align, f1, f2, f3; std::vector<std::pair<int32_t, int32_t> > dcp; std::pair<double, double> fr;
+                tracy::ReferenceSlice al1, al2; int s1 = 0, s2 = 0, s3 = 0; };
+  std::vector<Want> want(N);
+  std::ostringstream sink;
+  std::streambuf* old_out = std::cout.rdbuf(sink.rdbuf());
+  std::streambuf* old_err = std::cerr.rdbuf(sink.rdbuf());
+  for (int i = 0; i < N; ++i) {
+    Want& w = want[i];
+    TProfile trimmed, fwdp, revp, pref;
+    tracy::createProfile(tr[i], bc1[i], trimmed, c.trimLeft, c.trimRight);
+    tracy::findBreakpoint(trimmed, w.bp);
+    tracy::_createProfile(rs1[i].refslice, fwdp);
+    tracy::reverseComplementProfile(fwdp, revp);
+    const int gsFwd = tracy::gotohScore(trimmed, fwdp, semiglobal, sc), gsRev = tracy::gotohScore(trimmed, revp, semiglobal, sc);
+    rs1[i].kmersupport = 0; rs1[i].pos = 0;
+    if (gsFwd > gsRev) { rs1[i].forward = true; tracy::copyProfile(fwdp, pref); }
+    else { rs1[i].forward = false; tracy::reverseComplement(rs1[i].refslice); tracy::copyProfile(revp, pref); }
+    const int ali = tracy::gotoh(trimmed, pref, w.align, semiglobal, sc);
+    const double seqsize = trimmed.shape()[1];
+    if (ali <= seqsize * 0.35 * sc.match + seqsize * (1 - 0.35) * sc.mismatch) continue;
+    if (!w.bp.indelshift && !tracy::findHomozygousBreakpoint(w.align, w.bp)) continue;
+    if (!tracy::decomposeAlleles(c, w.align, bc1[i], w.bp, rs1[i], w.dcp)) continue;
+    tracy::generateSecondaryDecomposed(tr[i], bc1[i]);
+    w.fr = tracy::allelicFraction(c, tr[i], bc1[i]);
+    const std::string pri = tracy::trimmedSeq(bc1[i].primary, c.trimLeft, c.trimRight), sec = tracy::trimmedSeq(bc1[i].secDecompose, c.trimLeft, c.trimRight);
+    TAlign tmp;
+    tracy::gotoh(pri, rs1[i].refslice, tmp, semiglobal, sc);
+    w.al1 = rs1[i]; tracy::trimReferenceSlice(c, tmp, w.al1);
+    w.s1 = tracy::gotoh(pri, w.al1.refslice, w.f1, semiglobal, sc);
+    tracy::gotoh(sec, rs1[i].refslice, tmp, semiglobal, sc);
+    w.al2 = rs1[i]; tracy::trimReferenceSlice(c, tmp, w.al2);
+    w.s2 = tracy::gotoh(sec, w.al2.refslice, w.f2, semiglobal, sc);
+    tracy::AlignConfig<false, false> global;
+    w.s3 = tracy::gotoh(pri, sec, w.f3, global, sc);
+    w.ok = true;
+  }
+  std::cout.rdbuf(old_out); std::cerr.rdbuf(old_err);
+  // tracy_b200, all traces at once
+  std::vector<const tracy::Trace*> ptr(N); std::vector<tracy::BaseCalls*> pbc(N); std::vector<tracy::ReferenceSlice*> prs(N);
+  for (int i = 0; i < N; ++i) { ptr[i] = &tr[i]; pbc[i] = &bc2[i]; prs[i] = &rs2[i]; }
+  std::vector<tracy_b200::DecomposeOut<TAlign, tracy::ReferenceSlice, tracy::TraceBreakpoint> > got;
+  tracy_b200::decomposeBatch(g, c, ptr, pbc, prs, got, sc, nullptr);
+  int nok = 0;
+  for (int i = 0; i < N; ++i) {
+    const Want& w = want[i];
+    bool same = w.ok == got[i].ok;
+    if (same && w.ok) {
+      ++nok;
+      same = rs1[i].forward == rs2[i].forward && rs1[i].refslice == rs2[i].refslice && same_align(w.align, got[i].align) &&
+             w.bp.indelshift == got[i].bp.indelshift && w.bp.traceleft == got[i].bp.traceleft && w.bp.breakpoint == got[i].bp.breakpoint && w.bp.bestDiff == got[i].bp.bestDiff &&
+             bc1[i].primary == bc2[i].primary && bc1[i].secondary == bc2[i].secondary && bc1[i].secDecompose == bc2[i].secDecompose && w.dcp == got[i].dcp &&
+             std::memcmp(&w.fr, &got[i].a1a2, sizeof(w.fr)) == 0 && w.s1 == got[i].a1Score && w.s2 == got[i].a2Score && w.s3 == got[i].a3Score &&
+             same_align(w.f1, got[i].final1) && same_align(w.f2, got[i].final2) && same_align(w.f3, got[i].final3) &&
+             w.al1.refslice == got[i].allele1.refslice && w.al1.pos == got[i].allele1.pos && w.al2.refslice == got[i].allele2.refslice && w.al2.pos == got[i].allele2.pos;
+    }
+    expect(same, "decomposeBatch (indigo DP sequence)", i);
+  }
+  expect(nok >= N - 3, "decomposeBatch: accepted traces", nok);
+}
+
 int main() {
   try {
     tracy_b200::Context g(0);
@@ -415,6 +504,7 @@ int main() {
     driver_check(g);
     distance_check(g);
     assemble_check(g);
+    decompose_driver_check(g);
     // batch form: the same pairs in one call
     {
       std::vector<TProfile> ps(8);

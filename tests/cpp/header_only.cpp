@@ -7,6 +7,9 @@ struct Slice { std::string refslice; };
 struct Breakpoint { bool indelshift, traceleft; uint32_t breakpoint; float bestDiff; };
 struct Cfg { uint16_t trimLeft, trimRight, maxindel, madc; };
 struct AssembleCfg { tracy_b200::DnaScore<int32_t> aliscore; float matchFraction; };
+struct Chromatogram { std::vector<std::vector<int32_t> > traceACGT; };
+struct FullCalls { std::vector<uint32_t> bcPos; std::string primary, secondary, consensus, secDecompose; };
+struct FullSlice { std::string chr, refslice; bool forward; uint32_t pos, kmersupport; };
 
 int main() {
   using namespace tracy_b200;
@@ -35,5 +38,11 @@ int main() {
   std::vector<uint32_t> idxmap;
   s += assembleDenovo(g, ac2, traces, fwd, align, seqidx, idxmap);
   s += (int)assembleReference(g, ac2, traces, s2, align, seqidx, fwd);
+  // the `tracy decompose` driver over plain structs shaped like tracy's
+  Chromatogram tr; FullCalls fc; FullSlice fs;
+  std::vector<const Chromatogram*> trs{&tr}; std::vector<FullCalls*> bcs{&fc}; std::vector<FullSlice*> rss{&fs};
+  std::vector<DecomposeOut<Matrix<char>, FullSlice, Breakpoint> > dout;
+  decomposeBatch(g, c, trs, bcs, rss, dout, sc);
+  s += (int)dout.size() + (int)trimmedSeq(s1, 1, 1).size();
   return s == 12345;
 }

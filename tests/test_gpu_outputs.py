@@ -102,3 +102,19 @@ def test_four_row_upload(ctx, oracle_port, monkeypatch):
     ctx.gotoh("ps", tracy_b200.uniform_profiles(prof2), a2, DnaScore(*SC), AlignConfig(True, False), rows=True)
     s8, ops8, ol8, t0, t1 = ctx.gotoh("ps", a1, a2, DnaScore(*SC), AlignConfig(True, False), rows=True)
     assert np.array_equal(s8, s) and np.array_equal(t0, r0) and np.array_equal(t1, r1)
+
+
+def test_odd_strides(ctx):
+    """Caller-chosen strides that leave the strings unaligned (the C++ single-pair wrapper passes len1 + len2 + 16)."""
+    rng = np.random.default_rng(77)
+    A, B = _batch(rng, "ps", 20)
+    s, ops, ol, r0, r1 = ctx.gotoh("ps", A, B, DnaScore(*SC), AlignConfig(True, False), rows=True)
+    mx = int(max(a.shape[1] + len(b) for a, b in zip(A, B)))
+    for stride in (mx, mx + 1, mx + 3):
+        o2, l2 = np.zeros((len(A), stride), np.uint8), np.zeros(len(A), np.int32)
+        q0, q1 = np.zeros((len(A), stride + 2), np.uint8), np.zeros((len(A), stride + 2), np.uint8)
+        s2, _, _, _, _ = ctx.gotoh("ps", A, B, DnaScore(*SC), AlignConfig(True, False), out=(np.zeros(len(A), np.int32), o2, l2), rows=(q0, q1))
+        assert np.array_equal(s2, s) and np.array_equal(l2, ol)
+        for i in range(len(A)):
+            assert bytes(o2[i, : ol[i]]) == bytes(ops[i, : ol[i]])
+            assert bytes(q0[i, : ol[i]]) == bytes(r0[i, : ol[i]]) and bytes(q1[i, : ol[i]]) == bytes(r1[i, : ol[i]])

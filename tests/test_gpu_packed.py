@@ -244,3 +244,28 @@ def test_spans_at_the_window_start(ctx, oracle_port):
         assert ctx.last_packed_pairs() == len(A)
         for i in range(len(A)):
             assert (int(s[i]), bytes(ops[i, : ol[i]])) == oracle_port.gotoh_ps(A[i], Bs[i], hf, vf, (3, -5, -10, -4)), (hf, vf, i)
+
+
+def test_config2_1024_pairs_vs_reference_headers(ctx, oracle_ref, oracle_port):
+    """a fixed subset of BASELINE configs[1] (1 kb x 4 kb, scores 3/-5/-10/-4, AlignConfig<true,false>) pair by pair
+    against tracy's own gotoh() -- the unmodified reference headers (oracle/_ref) where they travelled with the snapshot, else the C
+    restatement -- on all host threads: score and both gapped rows (made on the device) of each of 1 024 pairs."""
+    from concurrent.futures import ThreadPoolExecutor
+    m, n, N = 1000, 4000, 1024
+    prof, win = synth.align_batch(N, m, n, seed=4096)
+    a1, a2 = tracy_b200.uniform_profiles(prof, trace_profiles=True), tracy_b200.uniform_seqs(win)
+    sc = (3, -5, -10, -4)
+    s, ops, ol, r0, r1 = ctx.gotoh("ps", a1, a2, DnaScore(*sc), AlignConfig(True, False), rows=True)
+    assert ctx.last_packed_pairs() == N
+
+    def one(i):
+        if oracle_ref is not None:
+            return oracle_ref.gotoh(prof[i], oracle_ref.onehot(bytes(win[i])), 1, 0, sc)
+        ws, wops = oracle_port.gotoh_ps(prof[i], bytes(win[i]), 1, 0, sc)
+        return (ws,) + tracy_b200.rows_from_ops("ps", prof[i], bytes(win[i]), wops)
+    with ThreadPoolExecutor(os.cpu_count() or 8) as ex:
+        want = list(ex.map(one, range(N)))
+    bad = [i for i in range(N) if (int(s[i]), bytes(r0[i, : ol[i]]), bytes(r1[i, : ol[i]])) != want[i]]
+    assert not bad, bad[:10]
+    for i in range(0, N, 64):      # the s/h/v strings say the same as the rows
+        assert tracy_b200.rows_from_ops("ps", prof[i], bytes(win[i]), bytes(ops[i, : ol[i]])) == (want[i][1], want[i][2])

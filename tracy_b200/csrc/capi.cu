@@ -27,7 +27,7 @@ cudaError_t gotoh_pp_blocks_per_sm(int nch, bool traceback, bool harr, int* out)
 int gotoh_pp_warps_per_block();
 
 
-cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream);
+cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, long long max_tasks, cudaStream_t stream);
 void scan_trace_file(const uint8_t* buf, int64_t n, TraceDesc* d);
 cudaError_t launch_trace_unpack(const TraceUnpack& U, int nfiles, cudaStream_t st);
 cudaError_t launch_allelic_fraction(const FractionBatch& F, int ntraces, int maxD, cudaStream_t st);
@@ -876,7 +876,7 @@ int tb_decompose_sweep(tb_ctx* ctx, const tb_sweep_batch* batch, tb_sweep_result
     S.ndel = batch->ndel; S.nins = batch->nins;
     S.fref = res->fref; S.fins = res->fins; S.grid = res->grid;
     TB_CUDA(ctx, cudaEventRecord(L.k0, L.stream));
-    TB_CUDA(ctx, tb::launch_sweep(S, (int)nt, res->grid != nullptr, L.stream));
+    TB_CUDA(ctx, tb::launch_sweep(S, (int)nt, res->grid != nullptr, 2ll * os + (res->grid ? (long long)os * os : 0ll), L.stream));
     ctx->launches++;
     TB_CUDA(ctx, cudaEventRecord(L.k1, L.stream));
     TB_CUDA(ctx, cudaStreamSynchronize(L.stream));
@@ -922,7 +922,10 @@ int tb_decompose_sweep(tb_ctx* ctx, const tb_sweep_batch* batch, tb_sweep_result
   S.ref_len = i32; S.vi_end = i32 + nt; S.align_index = i32 + 2 * nt; S.var_index = i32 + 3 * nt; S.ndel = i32 + 4 * nt; S.nins = i32 + 5 * nt;
   S.fref = L.scores.as<int32_t>(); S.fins = S.fref + out_elems; S.grid = res->grid ? L.ops.as<int32_t>() : nullptr;
   TB_CUDA(ctx, cudaEventRecord(L.k0, st));
-  TB_CUDA(ctx, tb::launch_sweep(S, (int)nt, res->grid != nullptr, st));
+  long long max_tasks = 1;
+  for (size_t i = 0; i < nt; ++i)
+    max_tasks = std::max(max_tasks, (long long)batch->ndel[i] + batch->nins[i] + (res->grid ? (long long)batch->ndel[i] * batch->nins[i] : 0ll));
+  TB_CUDA(ctx, tb::launch_sweep(S, (int)nt, res->grid != nullptr, max_tasks, st));
   ctx->launches++;
   TB_CUDA(ctx, cudaEventRecord(L.k1, st));
   TB_CUDA(ctx, cudaMemcpyAsync(res->fref, S.fref, out_elems * 4, cudaMemcpyDeviceToHost, st));

@@ -184,7 +184,7 @@ __device__ __forceinline__ int sub_profile4(const float p1[5], const float p2[5]
 __device__ __forceinline__ char out_cons_char(const float* p, int len, int pos) {   // src/align.h:254-270
   int best = 0;
   float bv = p[pos];
-#pragma unroll
+#pragma unroll 1
   for (int k = 1; k < 6; ++k) {
     const float v = p[(size_t)k * len + pos];
     if (v > bv) { bv = v; best = k; }                     // float compare == the reference's double compare of the same floats
@@ -197,61 +197,38 @@ __device__ __forceinline__ char out_onehot_char(unsigned char ch) {             
 }
 static __device__ __noinline__ void emit_pair_outputs_impl(const void* a, int m, const void* b, int n, int mode, uint8_t* r0, uint8_t* r1, uint8_t* pk,
                                                           const uint8_t* __restrict__ ops, int L, int lane) {
-  // 128 ops per iteration, four consecutive ones per lane (the strings start 16-byte aligned: strides are multiples of 16)
-  // (word accesses only when the caller's strides and pointers keep every string 4-byte aligned)
-  const bool al = ((reinterpret_cast<unsigned long long>(ops) | (r0 ? reinterpret_cast<unsigned long long>(r0) | reinterpret_cast<unsigned long long>(r1) : 0ull)) & 3ull) == 0ull;
+  // 32 ops per iteration, one per lane; deliberately small and rolled: the warps of an SM are in different phases (fill, walk,
+  // this), and every KB of code here pushes the fill's unrolled step loop out of the 32 KB instruction cache they share --
+  // wider variants (4 and 16 ops per lane, loads batched) ran the whole kernel 2 and 6 ms slower per 100 k pairs.
+  // (the op of the NEXT iteration is loaded one iteration ahead: the string was just written and comes back from L2)
   int rbase = 0, cbase = 0;
-  for (int j0 = 0; j0 < L; j0 += 128) {
-    const int j = j0 + 4 * lane;
-    unsigned w = 0u;
-    if (j < L) {
-      if (al) w = *reinterpret_cast<const unsigned*>(ops + j);
-      else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (j + q < L) w |= (unsigned)ops[j + q] << (8 * q);
-      }
-    }
-    unsigned char op[4];
-    bool in[4];
-    int nr = 0, nc = 0;
-    unsigned byte = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      op[q] = (unsigned char)(w >> (8 * q));
-      in[q] = j + q < L;
-      nr += in[q] && op[q] != 'h';
-      nc += in[q] && op[q] != 'v';
-      byte |= (in[q] ? (op[q] == 'h' ? 1u : op[q] == 'v' ? 2u : 0u) : 0u) << (2 * q);
-    }
-    if (pk && in[0]) pk[(j0 >> 2) + lane] = (uint8_t)byte;
-    // exclusive prefix sums of (nr, nc) over the lanes: both counts are <= 4, packed into one word
-    unsigned both = (unsigned)nr | ((unsigned)nc << 16), scan = both;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned t = __shfl_up_sync(kFull, scan, d);
-      if (lane >= d) scan += t;
-    }
-    const unsigned tot = __shfl_sync(kFull, scan, 31);
+  unsigned char next = lane < L ? ops[lane] : (unsigned char)'s';
+#pragma unroll 1
+  for (int j0 = 0; j0 < L; j0 += 32) {
+    const int j = j0 + lane;
+    const unsigned char op = next;
+    next = j + 32 < L ? ops[j + 32] : (unsigned char)'s';
+    const bool in = j < L, adv_r = in && op != 'h', adv_c = in && op != 'v';
+    const unsigned mr = __ballot_sync(kFull, adv_r), mc = __ballot_sync(kFull, adv_c);
     if (r0) {
-      int r = rbase + (int)((scan - both) & 0xffffu), c = cbase + (int)((scan - both) >> 16);
-      unsigned x4 = 0, y4 = 0;
+      const unsigned lt = (1u << lane) - 1u;
+      const int r = rbase + __popc(mr & lt), c = cbase + __popc(mc & lt);
+      char x = '-', y = '-';
+      if (adv_r && r < m) x = mode == kModeSS ? ((const char*)a)[r] : out_cons_char((const float*)a, m, r);
+      if (adv_c && c < n) y = mode == kModePP ? out_cons_char((const float*)b, n, c) : mode == kModeSS ? ((const char*)b)[c] : out_onehot_char(((const unsigned char*)b)[c]);
+      if (in) { r0[j] = (uint8_t)x; r1[j] = (uint8_t)y; }
+    }
+    rbase += __popc(mr); cbase += __popc(mc);
+    if (pk) {
+      const unsigned lo = __ballot_sync(kFull, in && op == 'h'), hi = __ballot_sync(kFull, in && op == 'v');
+      if (lane < 8 && j0 + 4 * lane < L) {
+        const unsigned l4 = (lo >> (4 * lane)) & 15u, h4 = (hi >> (4 * lane)) & 15u;   // four ops -> one byte: bit pairs (h, v) interleaved
+        unsigned byte = 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        char x = '-', y = '-';
-        const bool ar = in[q] && op[q] != 'h', ac = in[q] && op[q] != 'v';
-        if (ar && r < m) x = mode == kModeSS ? ((const char*)a)[r] : out_cons_char((const float*)a, m, r);
-        if (ac && c < n) y = mode == kModePP ? out_cons_char((const float*)b, n, c) : mode == kModeSS ? ((const char*)b)[c] : out_onehot_char(((const unsigned char*)b)[c]);
-        r += ar; c += ac;
-        x4 |= (unsigned)(unsigned char)x << (8 * q); y4 |= (unsigned)(unsigned char)y << (8 * q);
-      }
-      if (in[3] && al) {
-        *reinterpret_cast<unsigned*>(r0 + j) = x4; *reinterpret_cast<unsigned*>(r1 + j) = y4;
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (in[q]) { r0[j + q] = (uint8_t)(x4 >> (8 * q)); r1[j + q] = (uint8_t)(y4 >> (8 * q)); }
+        for (int q = 0; q < 4; ++q) byte |= (((l4 >> q) & 1u) | (((h4 >> q) & 1u) << 1)) << (2 * q);
+        pk[(j0 >> 2) + lane] = (uint8_t)byte;
       }
     }
-    rbase += (int)(tot & 0xffffu); cbase += (int)(tot >> 16);
   }
 }
 __device__ __forceinline__ void emit_pair_outputs(const GotohBatch& B, int pi, const uint8_t* ops, int L, int lane) {

@@ -608,7 +608,12 @@ gotoh_packed_kernel(const GotohBatch B) {
     // lowest value any field can take: all-gap path to the far corner, one more open+extend, and up to 63 run-in /
     // run-out steps in which a half-band computes unread cells from in-range inputs (each step moves a value by at
     // most |goe| down or smax up), plus slack
-    const long long lb = 2ll * go + 2ll * goe + (long long)(npass * kPkRows + n + 100) * ge - 16 + 72ll * goe + 72ll * min(smin, 0);
+    // With free horizontal end gaps (every align / decompose / assemble call of tracy) no value depends on the column count: row 0 is
+    // all zeros, so S[r][c] >= go + r * ge (down column c from row 0), H and V sit at most one gap open below an S of their row / the
+    // row above, and the padding rows of the last pass start from go + r * ge as well -- the window may be as long as it likes
+    // (a 50 kb FASTA reference, src/sage.h:227-230) without leaving the 16-bit range.
+    const long long far = hfree ? (long long)(npass * kPkRows + 100) : (long long)(npass * kPkRows + n + 100);
+    const long long lb = 2ll * go + 2ll * goe + far * ge - 16 + 72ll * goe + 72ll * min(smin, 0);
     const long long bias_ll = (long long)kPkNeg + 64 - lb;
     const long long ub = (long long)max(smax, 0) * min(m, n) + 72ll * max(smax, 0);
     if (bias_ll + ub > kPkMaxField || smin < -16384 || smax > 16384) continue;   // leave status 0: the general kernel takes it

@@ -3,8 +3,10 @@
 // The reference slides the reference row of an existing alignment against the primary/secondary basecalls for
 // every candidate deletion length, insertion length and (fallback) ins x del pair, counting positions that
 // disagree with the primary call and cannot be phased (phaseRefAllele(...) == 'N', src/decompose.h:147-175).
-// The strings are read-only during the sweeps, so every (trace, shift) is independent: one block per trace,
-// one warp per shift, lanes striding the alignment columns (coalesced byte loads), warp-reduced count.
+// The strings are read-only during the sweeps, so every (trace, shift) is independent: one warp per shift, lanes striding the
+// alignment columns (coalesced byte loads), warp-reduced count. blockIdx.x is the trace; blockIdx.y splits a trace's shifts over
+// several blocks -- with the CLI default maxindel = 1000 the ins x del fallback grid is up to ~4 * 10^5 shifts of ~800 columns for
+// ONE trace, which one block of 8 warps would hold for tens of milliseconds while the other SMs idle.
 #include "common.cuh"
 
 namespace tb {
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(kSweepWarps * 32) sweep_kernel(const SweepBatc
   const int L = S.ref_len[t], vend = S.vi_end[t], ai = S.align_index[t], vi = S.var_index[t];
   const int nd = S.ndel[t], ni = S.nins[t];
   const int ntask = nd + ni + (GRID ? nd * ni : 0);
-  for (int task = warp; task < ntask; task += kSweepWarps) {
+  for (int task = warp + kSweepWarps * blockIdx.y; task < ntask; task += kSweepWarps * gridDim.y) {
     int del, ins;
     int32_t* out;
     if (task < nd) { del = task; ins = 0; out = S.fref + (size_t)t * S.out_stride + del; }
@@ -62,9 +64,15 @@ __global__ void __launch_bounds__(kSweepWarps * 32) sweep_kernel(const SweepBatc
   }
 }
 
-cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, cudaStream_t stream) {
-  if (grid) sweep_kernel<true><<<ntraces, kSweepWarps * 32, 0, stream>>>(S);
-  else sweep_kernel<false><<<ntraces, kSweepWarps * 32, 0, stream>>>(S);
+// max_tasks: the largest number of shifts of any trace in the batch (ndel + nins, plus ndel * nins with the grid).
+cudaError_t launch_sweep(const SweepBatch& S, int ntraces, bool grid, long long max_tasks, cudaStream_t stream) {
+  // enough blocks to fill 148 SMs a few times over, no more splits than a trace has groups of 8 shifts
+  long long split = (4 * 148 + ntraces - 1) / ntraces;
+  split = std::min(split, (max_tasks + kSweepWarps - 1) / kSweepWarps);
+  split = std::max(1ll, std::min(split, 1024ll));
+  const dim3 g((unsigned)ntraces, (unsigned)split);
+  if (grid) sweep_kernel<true><<<g, kSweepWarps * 32, 0, stream>>>(S);
+  else sweep_kernel<false><<<g, kSweepWarps * 32, 0, stream>>>(S);
   return cudaGetLastError();
 }
 

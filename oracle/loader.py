@@ -583,6 +583,35 @@ class _Ref:
                                            breakpoint, refslice_len, dcp, 4096)
         return pri.raw[:nbc], sec.raw[:nbc], dcp[: 2 * n].reshape(n, 2).copy()
 
+    def subcommand(self, name, args):
+        """Run the reference's own subcommand entry point files-in -> files-out: name in consensus / align / assemble
+        (src/consensus.h:332, src/sage.h:58, src/assemble.h:57); args = the command line after the subcommand name. Returns its exit code."""
+        what = {"consensus": 0, "align": 1, "assemble": 2}[name]
+        self.lib.ref_subcommand.argtypes = [C.c_int, C.c_char_p]
+        self.lib.ref_subcommand.restype = C.c_int
+        return self.lib.ref_subcommand(what, "\n".join([name] + [str(a) for a in args]).encode())
+
+    def gt_letter(self, cl6, use_iupac=False):
+        """gtLetter (src/consensus.h:94-171): six weights -> (consensus letter, quality)."""
+        self.lib.ref_gt_letter.argtypes = [np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_int, C.c_char_p]
+        self.lib.ref_gt_letter.restype = C.c_uint
+        out = C.create_string_buffer(2)
+        q = self.lib.ref_gt_letter(np.ascontiguousarray(cl6, np.float64), int(use_iupac), out)
+        return out.raw[:1], int(q)
+
+    def pairwise_consensus(self, row0, row1, p1, p2, compute_union=True, use_iupac=False):
+        """pairwiseConsensus (src/consensus.h:189-238) -> (consensus bytes, uint32 qualities)."""
+        self.lib.ref_pairwise_consensus.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _f32p, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                                    np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), C.c_int]
+        self.lib.ref_pairwise_consensus.restype = C.c_int
+        p1 = np.ascontiguousarray(p1, np.float32); p2 = np.ascontiguousarray(p2, np.float32)
+        cap = 2 * len(row0) + 8
+        out = C.create_string_buffer(cap); q = np.zeros(cap, np.uint32)
+        k = self.lib.ref_pairwise_consensus(bytes(row0), bytes(row1), len(row0), p1.reshape(-1), p1.shape[1], p2.reshape(-1), p2.shape[1],
+                                            int(compute_union), int(use_iupac), out, q, cap)
+        assert k >= 0
+        return out.raw[:k], q[:k].copy()
+
     def bench_gotoh_ps(self, profs, seqs, m, n, hfree, vfree, sc, with_traceback=True):
         profs = np.ascontiguousarray(profs, np.float32)
         npairs = profs.shape[0]

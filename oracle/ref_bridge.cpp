@@ -33,6 +33,9 @@
 #include "msa.h"       // distanceMatrix, upgma, palign, consensus, revSeqBasedOnDist, msa (reference, unmodified)
 #include "json.h"      // traceJsonOut, alignmentTracePadding, traceAlignJsonOut (reference, unmodified; variants.h / htslib only declared)
 #include "trim.h"      // trimTrace, nearestSNP (reference, unmodified)
+#include "consensus.h" // gtLetter, pairwiseConsensus, plotClustalPairwise, int consensus(argc, argv) (reference, unmodified)
+#include "sage.h"      // int sage(argc, argv) = `tracy align` (reference, unmodified)
+#include "assemble.h"  // int assemble(argc, argv) = `tracy assemble` (reference, unmodified)
 
 namespace {
 typedef boost::multi_array<float, 2> TProfile;
@@ -668,6 +671,46 @@ int ref_get_reference_slice(void* h, int filetype, const char* cons, int len, in
   memcpy(refslice_io, rs.refslice.data(), (size_t)L); *refslice_len = (int)rs.refslice.size();
   snprintf(chr_out, (size_t)chr_cap, "%s", rs.chr.c_str());
   return ok ? 1 : 0;
+}
+
+// The reference's own subcommand entry points, files in -> files out (src/tracy.cpp:66-81 hands them argc-1, argv+1):
+// what 0 = `tracy consensus` (src/consensus.h:332), 1 = `tracy align` (src/sage.h:58), 2 = `tracy assemble` (src/assemble.h:57).
+// args is a '\n'-joined argument list whose first entry is the subcommand name. The progress lines on stdout/stderr are dropped.
+int ref_subcommand(int what, const char* args) {
+  std::vector<std::string> a; { std::stringstream ss(args); std::string x; while (std::getline(ss, x)) a.push_back(x); }
+  std::vector<char*> argv; for (auto& x : a) argv.push_back(&x[0]);
+  std::streambuf* o1 = std::cout.rdbuf(nullptr); std::streambuf* o2 = std::cerr.rdbuf(nullptr);
+  int rc = -99;
+  try {
+    if (what == 0) rc = tracy::consensus((int)argv.size(), argv.data());
+    else if (what == 1) rc = tracy::sage((int)argv.size(), argv.data());
+    else if (what == 2) rc = tracy::assemble((int)argv.size(), argv.data());
+  } catch (std::exception const&) { rc = -98; }
+  std::cout.clear(); std::cerr.clear();
+  std::cout.rdbuf(o1); std::cerr.rdbuf(o2);
+  return rc;
+}
+// gtLetter (src/consensus.h:94-171) on one column's six weights; returns the quality, *letter the consensus character
+unsigned ref_gt_letter(const double* cl6, int useIUPAC, char* letter) {
+  tracy::ConsensusConfig c; c.useIUPAC = useIUPAC != 0;
+  std::vector<double> cl(cl6, cl6 + 6); std::string cons; std::vector<uint32_t> qual;
+  tracy::gtLetter(c, cl, cons, qual);
+  *letter = cons[0];
+  return qual[0];
+}
+// pairwiseConsensus (src/consensus.h:189-238): rows of the pairwise alignment + the two trimmed profiles -> consensus + qualities
+int ref_pairwise_consensus(const char* row0, const char* row1, int L, const float* p1, int m, const float* p2, int n, int computeUnion, int useIUPAC,
+                           char* cons_out, uint32_t* qual_out, int cap) {
+  tracy::ConsensusConfig c; c.useIUPAC = useIUPAC != 0; c.computeUnion = computeUnion != 0;
+  TAlign al(boost::extents[2][L]);
+  for (int j = 0; j < L; ++j) { al[0][j] = row0[j]; al[1][j] = row1[j]; }
+  TProfile a, b; load_profile(p1, m, a); load_profile(p2, n, b);
+  std::string cons; std::vector<uint32_t> qual;
+  tracy::pairwiseConsensus(c, al, a, b, cons, qual);
+  int k = (int)cons.size(); if (k > cap) return -k;
+  memcpy(cons_out, cons.data(), (size_t)k);
+  for (int i = 0; i < k; ++i) qual_out[i] = qual[i];
+  return k;
 }
 
 }  // extern "C"

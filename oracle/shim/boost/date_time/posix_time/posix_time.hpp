@@ -1,0 +1,1 @@
+#include "tracy_boost_stubs.hpp"

@@ -1,0 +1,1 @@
+#include "options_description.hpp"

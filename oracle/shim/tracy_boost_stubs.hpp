@@ -3,6 +3,7 @@
 #pragma once
 #include <algorithm>
 #include <cctype>
+#include <cstdio>
 #include <sstream>
 #include <string>
 namespace boost {
@@ -29,7 +30,7 @@ class path {
 };
 inline bool exists(const path& p) { FILE* f = fopen(p.string().c_str(), "rb"); if (f) fclose(f); return f != nullptr; }
 inline bool is_regular_file(const path& p) { return exists(p); }
-inline std::size_t file_size(const path&) { return 0; }
+inline std::size_t file_size(const path& p) { FILE* f = fopen(p.string().c_str(), "rb"); if (!f) return 0; fseek(f, 0, SEEK_END); long n = ftell(f); fclose(f); return n > 0 ? (std::size_t)n : 0; }
 inline bool remove(const path& p) { return ::remove(p.string().c_str()) == 0; }
 }  // namespace filesystem
 namespace gregorian {

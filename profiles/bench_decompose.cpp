@@ -1,0 +1,88 @@
+// BASELINE.json configs[2] through the C++ host layer (include/tracy_b200.hpp, no Boost, no reference headers):
+// N synthetic heterozygous traces (two alleles differing by one indel of 1..25 bp, mixed 60/40 in signal space) against 4 kb
+// single-FASTA references, `-i 30`: basecallBatch -> decomposeBatch (createProfile, findBreakpoint, orientation scores,
+// alignment, decomposeAlleles sweeps, generateSecondaryDecomposed, allelicFraction, three allele alignments).
+// Prints one JSON line: traces/s end to end (host clock around the two calls, host glue included) and the GPU launches.
+//   g++ -std=c++17 -O2 -I include profiles/bench_decompose.cpp -o gpurun_out/bench_decompose -Ltracy_b200 -ltracy_b200 -Wl,-rpath,$PWD/tracy_b200
+#include <chrono>
+#include <cstdio>
+#include <random>
+
+#include "tracy_b200.hpp"
+
+struct Trace { std::vector<std::vector<int32_t> > traceACGT; std::vector<uint32_t> basecallpos; };
+struct BaseCalls { std::vector<uint32_t> bcPos; std::string primary, secondary, consensus, secDecompose; };
+struct RefSlice { std::string chr, refslice; bool forward = true; uint32_t pos = 0, kmersupport = 0; };
+struct Breakpoint { bool indelshift = false, traceleft = true; uint32_t breakpoint = 0; float bestDiff = 0; };
+struct Cfg { uint16_t trimLeft, trimRight, maxindel, madc; };
+
+static std::mt19937_64 rng(45);
+static std::string random_seq(int n) { std::string s((size_t)n, 'A'); for (auto& c : s) c = "ACGT"[rng() % 4]; return s; }
+static void make_trace(std::string const& a1, std::string const& a2, double frac, Trace& tr) {
+  const size_t nbc = a1.size(), ns = 12 * nbc + 40;
+  tr.traceACGT.assign(4, std::vector<int32_t>(ns, 0));
+  for (int k = 0; k < 4; ++k) for (size_t p = 0; p < ns; ++p) tr.traceACGT[k][p] = (int32_t)(rng() % 20);
+  auto slot = [](char c) { return c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0; };
+  const int shape[5] = {15, 55, 100, 55, 15};
+  for (size_t j = 0; j < nbc; ++j) {
+    const int pos = (int)(12 * j + 10 + rng() % 3), h = 700 + (int)(rng() % 500);
+    tr.basecallpos.push_back((uint32_t)pos);
+    for (int d = -2; d <= 2; ++d) {
+      tr.traceACGT[slot(a1[j])][pos + d] += (int32_t)(h * frac * shape[d + 2] / 100);
+      if (j < a2.size()) tr.traceACGT[slot(a2[j])][pos + d] += (int32_t)(h * (1 - frac) * shape[d + 2] / 100);
+    }
+  }
+}
+
+int main(int argc, char** argv) {
+  const int N = argc > 1 ? std::atoi(argv[1]) : 10000, B = 256;
+  std::vector<Trace> base(B);
+  std::vector<std::string> refs(B);
+  for (int i = 0; i < B; ++i) {
+    refs[i] = random_seq(4000);
+    const int start = 1000 + (int)(rng() % 1500), L = 850 + (int)(rng() % 150), bp = 200 + (int)(rng() % 500), len = 1 + (int)(rng() % 25);
+    std::string a1 = refs[i].substr(start, L), a2;
+    if (i % 2) a2 = (refs[i].substr(start, bp) + refs[i].substr(start + bp + len)).substr(0, L);
+    else a2 = (refs[i].substr(start, bp) + random_seq(len) + refs[i].substr(start + bp)).substr(0, L);
+    for (int q = 0; q < 2; ++q) a2[rng() % a2.size()] = "ACGT"[rng() % 4];     // 0.2 % SNVs
+    make_trace(a1, a2, 0.6, base[i]);
+  }
+  std::vector<Trace> tr(N);
+  std::vector<BaseCalls> bc(N);
+  std::vector<RefSlice> rs(N);
+  for (int i = 0; i < N; ++i) { tr[i] = base[i % B]; rs[i].refslice = refs[i % B]; rs[i].chr = "ref"; }
+  std::vector<const Trace*> ptr(N); std::vector<BaseCalls*> pbc(N); std::vector<RefSlice*> prs(N);
+  for (int i = 0; i < N; ++i) { ptr[i] = &tr[i]; pbc[i] = &bc[i]; prs[i] = &rs[i]; }
+  try {
+    tracy_b200::Context g(0);
+    tracy_b200::DnaScore<int32_t> sc(3, -5, -10, -4);
+    Cfg c{50, 50, 30, 5};
+    typedef tracy_b200::DecomposeOut<tracy_b200::Matrix<char>, RefSlice, Breakpoint> TOut;
+    std::vector<TOut> out;
+    {   // warm-up on a slice (allocations, first launches)
+      std::vector<const Trace*> a(ptr.begin(), ptr.begin() + 64); std::vector<BaseCalls*> b(pbc.begin(), pbc.begin() + 64); std::vector<RefSlice*> r(prs.begin(), prs.begin() + 64);
+      tracy_b200::basecallBatch(g, a, b, 0.33f);
+      tracy_b200::decomposeBatch(g, c, a, b, r, out, sc);
+      for (int i = 0; i < 64; ++i) { rs[i] = RefSlice(); rs[i].refslice = refs[i % B]; rs[i].chr = "ref"; }
+    }
+    uint64_t k0 = 0, k1 = 0, h0 = 0, h1 = 0, d0 = 0, d1 = 0;
+    tb_ctx_stats(g.get(), &k0, &h0, &d0);
+    const auto t0 = std::chrono::steady_clock::now();
+    tracy_b200::basecallBatch(g, ptr, pbc, 0.33f);
+    const auto t1 = std::chrono::steady_clock::now();
+    tracy_b200::decomposeBatch(g, c, ptr, pbc, prs, out, sc);
+    const auto t2 = std::chrono::steady_clock::now();
+    tb_ctx_stats(g.get(), &k1, &h1, &d1);
+    const double s_bc = std::chrono::duration<double>(t1 - t0).count(), s_dc = std::chrono::duration<double>(t2 - t1).count();
+    int ok = 0, shift = 0; long dcp = 0;
+    for (int i = 0; i < N; ++i) { ok += out[i].ok; shift += out[i].ok && out[i].bp.indelshift; dcp += (long)out[i].dcp.size(); }
+    std::printf("{\"workload\": \"tracy decompose, %d synthetic heterozygous traces (~900 bp, indel 1-25 bp) vs 4 kb references, maxindel 30 (BASELINE.json configs[2])\", "
+                "\"traces\": %d, \"seconds\": %.4f, \"traces_per_s\": %.1f, \"basecall_seconds\": %.4f, \"decompose_seconds\": %.4f, \"decomposed\": %d, "
+                "\"heterozygous_shift_found\": %d, \"decomp_rows\": %ld, \"kernel_launches\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"host\": \"C++ (tracy_b200.hpp decomposeBatch)\"}\n",
+                N, N, s_bc + s_dc, N / (s_bc + s_dc), s_bc, s_dc, ok, shift, dcp, (unsigned long long)(k1 - k0), (unsigned long long)(h1 - h0), (unsigned long long)(d1 - d0));
+  } catch (std::exception const& e) {
+    std::printf("{\"error\": \"%s\"}\n", e.what());
+    return 1;
+  }
+  return 0;
+}

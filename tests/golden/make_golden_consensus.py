@@ -1,5 +1,6 @@
 """Generates tests/golden/consensus_golden.npz: the DP sequence of consensus() (reference src/consensus.h:499-556) composed
-from the REFERENCE's own functions (oracle/_ref): createProfile, reverseComplementProfile, gotohScore, gotoh.
+from the REFERENCE's own functions (oracle/_ref): createProfile, reverseComplementProfile, gotohScore, gotoh, and
+pairwiseConsensus (:189-238) over each alignment.
 
     python tests/golden/make_golden_consensus.py        (build container only: needs /root/reference)
 """
@@ -48,6 +49,11 @@ def main():
         d[f"p1_{i}"], d[f"p2_{i}"] = t1, f2
         d[f"meta{i}"] = np.array([fw, score], np.int64)
         d[f"r0_{i}"], d[f"r1_{i}"] = np.frombuffer(r0, np.uint8), np.frombuffer(r1, np.uint8)
+        # pairwiseConsensus (src/consensus.h:189-238) over that alignment, union / intersection x plain / IUPAC letters
+        for un in (0, 1):
+            for iu in (0, 1):
+                cons, qual = ref.pairwise_consensus(r0, r1, t1, f2 if fw else r2, un, iu)
+                d[f"cons{un}{iu}_{i}"], d[f"qual{un}{iu}_{i}"] = np.frombuffer(cons, np.uint8), qual
     np.savez_compressed(os.path.join(OUT, "consensus_golden.npz"), **d)
 
 

@@ -49,6 +49,7 @@ def align_batch(ctx, trimmed_profiles, full_profiles, references, sc=DnaScore(3,
     n = len(references)
     refs = [bytes(r) for r in references]
     rc = [reverse_complement_seq(r) for r in refs]
+    tls, trs = np.broadcast_to(trim_left, (n,)), np.broadcast_to(trim_right, (n,))         # one trim pair for all, or one per trace (-t)
     # gsFwd / gsRev (src/sage.h:239-240): one score-only batch of 2N pairs
     s = ctx.gotoh(PS, list(trimmed_profiles) + list(trimmed_profiles), refs + rc, sc, _SEMIGLOBAL, traceback=False)[0]
     forward = [bool(s[i] > s[n + i]) for i in range(n)]                    # strict '>', src/sage.h:247
@@ -58,7 +59,7 @@ def align_batch(ctx, trimmed_profiles, full_profiles, references, sc=DnaScore(3,
     slices, pos = [], []
     for i in range(n):
         r0, r1 = _gap_rows(ops[i, : ol[i]])
-        sl, p = trim_reference_slice(r0, r1, pref[i], forward[i], 0, trim_left, trim_right)
+        sl, p = trim_reference_slice(r0, r1, pref[i], forward[i], 0, int(tls[i]), int(trs[i]))
         slices.append(sl); pos.append(p)
     # gotoh(fulltraceprofile, referenceprofile) (src/sage.h:311): the reported alignment
     score, ops2, ol2 = ctx.gotoh(PS, full_profiles, slices, sc, _SEMIGLOBAL)

@@ -172,6 +172,21 @@ typedef struct {
 
 int tb_decompose_sweep(tb_ctx* ctx, const tb_sweep_batch* batch, tb_sweep_result* res);
 
+/* ---- device-resident trace samples ---------------------------------------------------------------------------------
+ * tracy holds a trace as four std::vector<int32_t> (Trace::traceACGT, reference src/abif.h:35-47) and reads it in basecall(),
+ * createProfile(), generateSecondaryDecomposed() and allelicFraction(). tb_trace_set_create gathers the channels of n traces
+ * (channels[4*t + k] = channel k of trace t, nsamples[t] samples each) through pinned staging buffers (host threads fill one
+ * while the other is in flight) into ONE device arena, so that the samples cross PCIe once for all of those calls.
+ * Use: OR TB_TRACE_SET into tb_basecall_batch / tb_profile_batch / tb_fraction_batch ::mem (with TB_MEM_HOST), put the handle in
+ * trace.base, and in trace.off either NULL (item t = trace t of the set; ntraces must equal the set's size) or ntraces int64 indices
+ * into the set (host memory); trace.len is ignored. */
+typedef struct tb_trace_set tb_trace_set;
+enum { TB_TRACE_SET = 0x200 };
+int tb_trace_set_create(tb_ctx* ctx, const int32_t* const* channels, const int32_t* nsamples, size_t ntraces, tb_trace_set** out);
+int tb_trace_set_destroy(tb_ctx* ctx, tb_trace_set* set);
+/* ntraces / device bytes / the device arena (base: int32 samples [4][ns] per trace; off, len: device arrays) of a set */
+int tb_trace_set_info(const tb_trace_set* set, size_t* ntraces, uint64_t* device_bytes, tb_arena* device_arena);
+
 /* ---- profile construction either side of the DP -----------------------------------------------------------------
  * createProfile(Trace, BaseCalls, p, trimleft, trimright), reference src/profile.h:21-52, for a batch of traces (GPU).
  * trace item t: int32 samples [4][nsamples] row-major (channels A,C,G,T = Trace::traceACGT), trace.len[t] = nsamples.
@@ -295,6 +310,29 @@ int tb_trace_scan(const uint8_t* files, const int64_t* off, const int64_t* len, 
 int tb_trace_unpack(tb_ctx* ctx, const uint8_t* files, const int64_t* off, const int64_t* len, size_t nfiles, int32_t out_mem,
                     int32_t* samples, const int64_t* samples_off, int32_t* ploc, uint8_t* qual, char* basecalls1, char* basecalls2,
                     const int64_t* bc_off);
+
+/* ---- several GPUs of one node behind one handle (BASELINE.json configs[4]; csrc/multi.cu) ----------------------------------------
+ * One context per device, owned by the handle; each call cuts its batch into contiguous ranges of equal DP cost, runs every range
+ * through its device's own pipeline on its own host thread and lets each device write its slice of the caller's result arrays (the
+ * gather of the scores). No data-path collective: pairs and traces are independent. devices == NULL: devices 0 .. ndev-1; ndev <= 0:
+ * every visible device. The same device may be named more than once (each entry gets its own context). */
+typedef struct tb_multi tb_multi;
+int tb_multi_create(tb_multi** out, const int* devices, int ndev);
+void tb_multi_destroy(tb_multi* m);
+int tb_multi_size(const tb_multi* m);
+tb_ctx* tb_multi_ctx(tb_multi* m, int i);               /* the i-th device's context (stats, timings, single-device calls) */
+const char* tb_multi_last_error(const tb_multi* m);
+/* first[0..parts]: pair ranges of equal sum((len1+1)*(len2+1)) -- the split tb_multi_gotoh uses */
+int tb_multi_partition(const int32_t* len1, const int32_t* len2, size_t n, int parts, size_t* first);
+/* tb_gotoh_pp (kind 0) / tb_gotoh_ss (1) / tb_gotoh_ps (2) over all devices; the batch lives in host memory (TB_MEM_HOST, optionally
+ * with TB_A1_TRACE_PROFILES). first_out (optional, [size+1]): the ranges the devices took. */
+int tb_multi_gotoh(tb_multi* m, int kind, const tb_batch* batch, tb_score sc, tb_align_config ac, tb_result* res, size_t* first_out);
+/* The reference text to every device -- PCIe once, then GPU to GPU (cudaMemcpyPeerAsync along a doubling tree: NVLink where the
+ * devices are peers) -- and one anchoring index per device built from its copy. out: [size] indexes, out[i] belongs to tb_multi_ctx(i). */
+int tb_multi_index_build(tb_multi* m, const char* text, int64_t text_len, tb_index** out);
+/* tb_anchor over all devices: traces split by consensus length, every device queries its own index, results land in the caller's
+ * (host) arrays in trace order. */
+int tb_multi_anchor(tb_multi* m, tb_index* const* idx, const tb_arena* consensus, size_t ntraces, tb_anchor_config cfg, tb_anchor_result* res);
 
 const char* tb_version(void);
 

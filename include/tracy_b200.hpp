@@ -18,6 +18,9 @@
 #define TRACY_B200_HPP
 
 #include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <iostream>
@@ -72,8 +75,33 @@ class Context {
   Context& operator=(const Context&) = delete;
   tb_ctx* get() const { return ctx_; }
   void check(int rc) const { if (rc != TB_OK) throw Error(rc, std::string(tb_strerror(rc)) + ": " + tb_last_error(ctx_)); }
+  // kind: 0 profile x profile, 1 string x string, 2 profile x string
+  void gotoh(int kind, tb_batch const& b, tb_score sc, tb_align_config ac, tb_result& r) {
+    check(kind == 0 ? tb_gotoh_pp(ctx_, &b, sc, ac, &r) : kind == 1 ? tb_gotoh_ss(ctx_, &b, sc, ac, &r) : tb_gotoh_ps(ctx_, &b, sc, ac, &r));
+  }
  private:
   tb_ctx* ctx_ = nullptr;
+};
+
+// Several GPUs of one node behind one object (tb_multi, csrc/multi.cu): gotohBatch(g, ...) takes a MultiContext in place of a Context
+// and spreads the pairs over the devices in cost-balanced ranges, each device writing its slice of the results; broadcastIndex ships
+// a reference text to every device (PCIe once, then GPU to GPU) and builds one anchoring index per device; anchorBatch shards traces.
+class MultiContext {
+ public:
+  explicit MultiContext(std::vector<int> const& devices = std::vector<int>()) {
+    const int rc = tb_multi_create(&m_, devices.empty() ? nullptr : devices.data(), (int)devices.size());
+    if (rc != TB_OK) throw Error(rc, std::string("tracy_b200: ") + tb_strerror(rc) + " (are the B200s visible? there is no CPU fallback)");
+  }
+  ~MultiContext() { tb_multi_destroy(m_); }
+  MultiContext(const MultiContext&) = delete;
+  MultiContext& operator=(const MultiContext&) = delete;
+  tb_multi* get() const { return m_; }
+  int size() const { return tb_multi_size(m_); }
+  tb_ctx* device_context(int i) const { return tb_multi_ctx(m_, i); }
+  void check(int rc) const { if (rc != TB_OK) throw Error(rc, std::string(tb_strerror(rc)) + ": " + tb_multi_last_error(m_)); }
+  void gotoh(int kind, tb_batch const& b, tb_score sc, tb_align_config ac, tb_result& r) { check(tb_multi_gotoh(m_, kind, &b, sc, ac, &r, nullptr)); }
+ private:
+  tb_multi* m_ = nullptr;
 };
 
 namespace detail {
@@ -137,8 +165,9 @@ inline int gotoh(Context& g, TA const& a1, TB const& a2, TAlign& align, TAlignCo
 // profiles that already sit back to back; otherwise they are packed once). ops (optional) receives the s/h/v strings in
 // start->end order (see tracy_b200.h); rows can be made from them with tb_rows_from_ops.
 // rows (optional): the two gapped rows of every pair (what gotoh() leaves in `align`), made on the device.
-template <typename TA, typename TB, typename TAlignConfig, typename TScore>
-inline std::vector<int32_t> gotohBatch(Context& g, std::vector<const TA*> const& a1, std::vector<const TB*> const& a2, TAlignConfig const& ac,
+template <typename TCtx, typename TA, typename TB, typename TAlignConfig, typename TScore,
+          typename = typename std::enable_if<std::is_same<TCtx, Context>::value || std::is_same<TCtx, MultiContext>::value>::type>
+inline std::vector<int32_t> gotohBatch(TCtx& g, std::vector<const TA*> const& a1, std::vector<const TB*> const& a2, TAlignConfig const& ac,
                                        TScore const& sc, std::vector<std::string>* ops = nullptr,
                                        std::vector<std::pair<std::string, std::string> >* rows = nullptr) {
   const std::size_t n = a1.size();
@@ -171,7 +200,7 @@ inline std::vector<int32_t> gotohBatch(Context& g, std::vector<const TA*> const&
   constexpr int kind = detail::kind_of<TA, TB>();
   const tb_align_config acc = detail::ac_of(ac);
   const tb_score scc = detail::sc_of(sc);
-  g.check(kind == 0 ? tb_gotoh_pp(g.get(), &b, scc, acc, &r) : kind == 1 ? tb_gotoh_ss(g.get(), &b, scc, acc, &r) : tb_gotoh_ps(g.get(), &b, scc, acc, &r));
+  g.gotoh(kind, b, scc, acc, r);
   if (ops) {
     ops->resize(n);
     for (std::size_t i = 0; i < n; ++i) (*ops)[i].assign(obuf.begin() + i * stride, obuf.begin() + i * stride + olen[i]);
@@ -401,14 +430,80 @@ inline void pack_traces(std::vector<const TTrace*> const& tr, std::vector<int32_
 }
 }  // namespace detail
 
+namespace detail {
+// Stage times of the batch drivers on stderr when TRACY_B200_TIMING is set (profiles/bench_decompose.cpp reads them).
+struct StageClock {
+  bool on; std::chrono::steady_clock::time_point t;
+  StageClock() : on(std::getenv("TRACY_B200_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[tracy_b200] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+}  // namespace detail
+
+// The samples of many traces resident on the device (tb_trace_set): gathered from the traces' own channel vectors through pinned
+// staging and uploaded ONCE; basecallBatch / createProfileBatch / allelicFractionBatch / decomposeBatch take it in place of packing
+// and shipping Trace::traceACGT again per call (a 10 000-trace batch is 1.8 GB of int32 samples).
+class TraceSet {
+ public:
+  template <typename TTrace>
+  TraceSet(Context& g, std::vector<const TTrace*> const& tr) : g_(&g) {
+    std::vector<const int32_t*> ch(4 * tr.size(), nullptr);
+    std::vector<int32_t> ns(tr.size(), 0);
+    for (std::size_t t = 0; t < tr.size(); ++t) {
+      auto const& c = tr[t]->traceACGT;
+      ns[t] = (int32_t)(c.size() ? c[0].size() : 0);
+      for (std::size_t k = 0; k < 4; ++k) {
+        if (k >= c.size() || c[k].size() != (std::size_t)ns[t]) throw Error(TB_ERR_INVALID, "trace channels differ in length");
+        static_assert(sizeof(typename std::decay<decltype(c[k][0])>::type) == 4, "Trace::TValue is a 32-bit integer");
+        ch[4 * t + k] = reinterpret_cast<const int32_t*>(c[k].data());
+      }
+    }
+    g.check(tb_trace_set_create(g.get(), ch.data(), ns.data(), tr.size(), &h_));
+    n_ = tr.size();
+  }
+  ~TraceSet() { if (h_) tb_trace_set_destroy(g_->get(), h_); }
+  TraceSet(const TraceSet&) = delete;
+  TraceSet& operator=(const TraceSet&) = delete;
+  tb_trace_set* get() const { return h_; }
+  std::size_t size() const { return n_; }
+ private:
+  Context* g_;
+  tb_trace_set* h_ = nullptr;
+  std::size_t n_ = 0;
+};
+
+namespace detail {
+// the trace side of a basecall / profile / fraction batch: a resident set (optionally a subset by index) or the traces packed here
+template <typename TTrace>
+struct TraceArena {
+  std::vector<int32_t> base; std::vector<int64_t> off; std::vector<int32_t> len;
+  tb_arena arena{nullptr, nullptr, nullptr};
+  int32_t mem = TB_MEM_HOST;
+  TraceArena(std::vector<const TTrace*> const& tr, TraceSet const* set, std::vector<int64_t> const* idx) {
+    if (set) {
+      if (idx ? idx->size() != tr.size() : set->size() != tr.size()) throw Error(TB_ERR_INVALID, "trace set and trace list differ in length");
+      arena.base = set->get(); arena.off = idx ? idx->data() : nullptr; mem = TB_MEM_HOST | TB_TRACE_SET;
+    } else {
+      pack_traces(tr, base, off, len);
+      arena.base = base.data(); arena.off = off.data(); arena.len = len.data();
+    }
+  }
+};
+}  // namespace detail
+
 // basecall(tr, bc, sigratio) for many traces -- reference src/abif.h:408-511 without its last line: estimateQualities(bc)
 // is host code of the reference and stays with the caller (tracy::estimateQualities(bc) after this call).
 template <typename TTrace, typename TBaseCalls>
-inline void basecallBatch(Context& g, std::vector<const TTrace*> const& tr, std::vector<TBaseCalls*> const& bc, float sigratio) {
+inline void basecallBatch(Context& g, std::vector<const TTrace*> const& tr, std::vector<TBaseCalls*> const& bc, float sigratio,
+                          TraceSet const* set = nullptr, std::vector<int64_t> const* idx = nullptr) {
   const std::size_t n = tr.size();
   if (n == 0) return;
-  std::vector<int32_t> base, ploc; std::vector<int64_t> toff, poff(n); std::vector<int32_t> tlen, plen(n);
-  detail::pack_traces(tr, base, toff, tlen);
+  std::vector<int32_t> ploc; std::vector<int64_t> poff(n); std::vector<int32_t> plen(n);
+  detail::TraceArena<TTrace> ta(tr, set, idx);
   for (std::size_t t = 0; t < n; ++t) {
     poff[t] = (int64_t)ploc.size(); plen[t] = (int32_t)tr[t]->basecallpos.size();
     ploc.insert(ploc.end(), tr[t]->basecallpos.begin(), tr[t]->basecallpos.end());
@@ -417,7 +512,7 @@ inline void basecallBatch(Context& g, std::vector<const TTrace*> const& tr, std:
   if (ploc.empty()) ploc.push_back(0);
   std::vector<int32_t> opos(tot), olen(n);
   std::string pri(tot, 'N'), sec(tot, 'N'), con(tot, 'N');
-  tb_basecall_batch b{{base.data(), toff.data(), tlen.data()}, {ploc.data(), poff.data(), plen.data()}, n, TB_MEM_HOST};
+  tb_basecall_batch b{ta.arena, {ploc.data(), poff.data(), plen.data()}, n, ta.mem};
   g.check(tb_basecall(g.get(), &b, sigratio, opos.data(), &pri[0], &sec[0], &con[0], poff.data(), olen.data()));
   for (std::size_t t = 0; t < n; ++t) {
     const std::size_t o = (std::size_t)poff[t], k = (std::size_t)olen[t];
@@ -433,12 +528,12 @@ inline void basecall(Context& g, TTrace const& tr, TBaseCalls& bc, float sigrati
 // createProfile(tr, bc, p, trimleft, trimright) for many traces -- reference src/profile.h:21-52.
 template <typename TTrace, typename TBaseCalls, typename TProfile>
 inline void createProfileBatch(Context& g, std::vector<const TTrace*> const& tr, std::vector<const TBaseCalls*> const& bc, std::vector<TProfile*> const& p,
-                               int32_t trimleft = 0, int32_t trimright = 0) {
+                               int32_t trimleft = 0, int32_t trimright = 0, TraceSet const* set = nullptr, std::vector<int64_t> const* idx = nullptr) {
   const std::size_t n = tr.size();
   if (n == 0) return;
-  std::vector<int32_t> base, bpos; std::vector<int64_t> toff, boff(n), ooff(n); std::vector<int32_t> tlen, blen(n), tl(n, trimleft), trr(n, trimright), olen(n);
+  std::vector<int32_t> bpos; std::vector<int64_t> boff(n), ooff(n); std::vector<int32_t> blen(n), tl(n, trimleft), trr(n, trimright), olen(n);
   std::string pri, sec;
-  detail::pack_traces(tr, base, toff, tlen);
+  detail::TraceArena<TTrace> ta(tr, set, idx);
   int64_t ototal = 0;
   for (std::size_t t = 0; t < n; ++t) {
     boff[t] = (int64_t)bpos.size(); blen[t] = (int32_t)bc[t]->bcPos.size();
@@ -448,13 +543,12 @@ inline void createProfileBatch(Context& g, std::vector<const TTrace*> const& tr,
   }
   if (bpos.empty()) { bpos.push_back(0); pri.push_back('N'); sec.push_back('N'); }
   std::vector<float> out((std::size_t)std::max<int64_t>(ototal, 1));
-  tb_profile_batch b{{base.data(), toff.data(), tlen.data()}, {bpos.data(), boff.data(), blen.data()}, pri.data(), sec.data(), tl.data(), trr.data(), n, TB_MEM_HOST};
+  tb_profile_batch b{ta.arena, {bpos.data(), boff.data(), blen.data()}, pri.data(), sec.data(), tl.data(), trr.data(), n, ta.mem};
   g.check(tb_create_profile(g.get(), &b, out.data(), ooff.data(), olen.data()));
   for (std::size_t t = 0; t < n; ++t) {
     const std::size_t sz = (std::size_t)olen[t];
     detail::resize_align(*p[t], 6, sz);
-    for (std::size_t k = 0; k < 6; ++k)
-      for (std::size_t j = 0; j < sz; ++j) (*p[t])[k][j] = out[(std::size_t)ooff[t] + k * sz + j];
+    if (sz) std::copy(out.begin() + ooff[t], out.begin() + ooff[t] + 6 * (int64_t)sz, p[t]->data());     // both sides are row-major [6][sz]
   }
 }
 template <typename TTrace, typename TBaseCalls, typename TProfile>
@@ -499,13 +593,14 @@ inline void trimReferenceSlice(TConfig const& c, TAlign const& align, TRefSlice&
 // allelicFraction(c, tr, bc) -- reference src/decompose.h:412-617 (GPU, FP64, bit-exact), for many traces.
 template <typename TConfig, typename TTrace, typename TBaseCalls>
 inline std::vector<std::pair<double, double> > allelicFractionBatch(Context& g, TConfig const& c, std::vector<const TTrace*> const& tr,
-                                                                    std::vector<const TBaseCalls*> const& bc) {
+                                                                    std::vector<const TBaseCalls*> const& bc, TraceSet const* set = nullptr,
+                                                                    std::vector<int64_t> const* idx = nullptr) {
   const std::size_t n = tr.size();
   std::vector<std::pair<double, double> > out(n, std::make_pair(0.5, 0.5));
   if (n == 0) return out;
-  std::vector<int32_t> base, bpos; std::vector<int64_t> toff, boff(n); std::vector<int32_t> tlen, blen(n);
+  std::vector<int32_t> bpos; std::vector<int64_t> boff(n); std::vector<int32_t> blen(n);
   std::string pri, sec;
-  detail::pack_traces(tr, base, toff, tlen);
+  detail::TraceArena<TTrace> ta(tr, set, idx);
   for (std::size_t t = 0; t < n; ++t) {
     if (bc[t]->primary.size() != bc[t]->bcPos.size() || bc[t]->secDecompose.size() != bc[t]->bcPos.size())
       throw Error(TB_ERR_INVALID, "allelicFraction: primary / secDecompose / bcPos differ in length");
@@ -515,8 +610,7 @@ inline std::vector<std::pair<double, double> > allelicFractionBatch(Context& g, 
   }
   if (bpos.empty()) { bpos.push_back(0); pri.push_back('N'); sec.push_back('N'); }
   std::vector<double> a1(n), a2(n);
-  tb_fraction_batch b{{base.data(), toff.data(), tlen.data()}, {bpos.data(), boff.data(), blen.data()}, pri.data(), sec.data(), (int32_t)c.trimLeft,
-                      (int32_t)c.trimRight, n, TB_MEM_HOST};
+  tb_fraction_batch b{ta.arena, {bpos.data(), boff.data(), blen.data()}, pri.data(), sec.data(), (int32_t)c.trimLeft, (int32_t)c.trimRight, n, ta.mem};
   g.check(tb_allelic_fraction(g.get(), &b, a1.data(), a2.data()));
   for (std::size_t t = 0; t < n; ++t) out[t] = std::make_pair(a1[t], a2[t]);
   return out;
@@ -539,11 +633,37 @@ class Index {
   tb_index* idx_ = nullptr;
 };
 
+// The reference text on every device of a MultiContext: shipped over PCIe once, passed on GPU to GPU, indexed per device.
+class MultiIndex {
+ public:
+  MultiIndex(MultiContext& g, std::string const& text) : g_(g), idx_((std::size_t)g.size(), nullptr) {
+    g.check(tb_multi_index_build(g.get(), text.data(), (int64_t)text.size(), idx_.data()));
+  }
+  ~MultiIndex() { for (std::size_t i = 0; i < idx_.size(); ++i) if (idx_[i]) tb_index_destroy(g_.device_context((int)i), idx_[i]); }
+  MultiIndex(const MultiIndex&) = delete;
+  MultiIndex& operator=(const MultiIndex&) = delete;
+  tb_index* const* get() const { return idx_.data(); }
+ private:
+  MultiContext& g_;
+  std::vector<tb_index*> idx_;
+};
+
+namespace detail {
+inline void run_anchor(Context& g, Index const& index, tb_arena const& a, std::size_t n, tb_anchor_config cfg, tb_anchor_result& r) {
+  g.check(tb_anchor(g.get(), index.get(), &a, n, TB_MEM_HOST, cfg, &r));
+}
+inline void run_anchor(MultiContext& g, MultiIndex const& index, tb_arena const& a, std::size_t n, tb_anchor_config cfg, tb_anchor_result& r) {
+  g.check(tb_multi_anchor(g.get(), index.get(), &a, n, cfg, &r));
+}
+}  // namespace detail
+
 // The anchoring part of getReferenceSlice(c, fm_index, bc, rs) -- reference src/fmindex.h:236-284 -- for many traces:
 // sets rs.forward and rs.kmersupport, returns per trace whether the reference function would return true, and (optionally)
 // bestPos, from which tb_reference_slice gives the slice the reference then fetches (:286-305).
-template <typename TConfig, typename TBaseCalls, typename TRefSlice>
-inline std::vector<char> anchorBatch(Context& g, Index const& index, TConfig const& c, std::vector<const TBaseCalls*> const& bc,
+// (g, index): a Context with its Index, or a MultiContext with its MultiIndex (traces sharded over the devices).
+template <typename TCtx, typename TIndex, typename TConfig, typename TBaseCalls, typename TRefSlice,
+          typename = typename std::enable_if<std::is_same<TCtx, Context>::value || std::is_same<TCtx, MultiContext>::value>::type>
+inline std::vector<char> anchorBatch(TCtx& g, TIndex const& index, TConfig const& c, std::vector<const TBaseCalls*> const& bc,
                                      std::vector<TRefSlice*> const& rs, std::vector<int64_t>* bestpos = nullptr) {
   const std::size_t n = bc.size();
   std::vector<char> ok(n, 0);
@@ -554,7 +674,7 @@ inline std::vector<char> anchorBatch(Context& g, Index const& index, TConfig con
   std::vector<uint8_t> anchored(n), forward(n); std::vector<uint32_t> support(n); std::vector<int64_t> pos(n);
   tb_arena a{cons.data(), off.data(), len.data()};
   tb_anchor_result r{anchored.data(), forward.data(), support.data(), pos.data(), nullptr};
-  g.check(tb_anchor(g.get(), index.get(), &a, n, TB_MEM_HOST, tb_anchor_config{(int32_t)c.trimLeft, (int32_t)c.trimRight, (int32_t)c.kmer, (int32_t)c.minKmerSupport}, &r));
+  detail::run_anchor(g, index, a, n, tb_anchor_config{(int32_t)c.trimLeft, (int32_t)c.trimRight, (int32_t)c.kmer, (int32_t)c.minKmerSupport}, r);
   for (std::size_t t = 0; t < n; ++t) {
     ok[t] = (char)anchored[t];
     if (anchored[t]) { rs[t]->forward = forward[t] != 0; rs[t]->kmersupport = support[t]; }
@@ -1087,6 +1207,114 @@ inline std::vector<int32_t> alignGenomeBatch(Context& g, Index const& index, std
   return scores;
 }
 
+// ---- `tracy consensus`: consensus letters and the DP sequence of consensus() for many trace pairs --------------------------------
+// gtLetter(c, cl, cons, qual) -- reference src/consensus.h:94-171: one consensus letter and its quality from the six weights of a
+// column (A, C, G, T, N, '-'). Host arithmetic in double with libm's log10 / pow, operation for operation as there: the results are
+// rounded to integers, so they have to come from the same sequence. After the rescaling the best letter's value is 0, so the quality
+// is a function of the second best's phred-scaled value alone. c: useIUPAC.
+template <typename TConfig>
+inline void gtLetter(TConfig const& c, std::vector<double>& cl, std::string& cons, std::vector<uint32_t>& qual) {
+  const double smallest = -1000;
+  double gl[6], total = 0;
+  for (std::size_t k = 0; k < cl.size(); ++k) total += cl[k];
+  for (std::size_t k = 0; k < 6; ++k) {
+    cl[k] = total > 0 ? cl[k] / total : 0;
+    gl[k] = cl[k] > 0 ? std::max(std::log10(cl[k]), smallest) : smallest;
+  }
+  uint32_t first = gl[0] < gl[1] ? 1 : 0, second = 1 - first;
+  for (uint32_t k = 2; k < 6; ++k) {
+    if (gl[k] > gl[first]) { second = first; first = k; }
+    else if (gl[k] > gl[second]) second = k;
+  }
+  const bool two = c.useIUPAC && gl[second] > -1 && first <= 3 && second <= 3;
+  const double top = gl[first];
+  for (std::size_t k = 0; k < 6; ++k) gl[k] -= top;
+  const uint32_t pl1 = (uint32_t)std::round(-10 * gl[first]), pl2 = (uint32_t)std::round(-10 * gl[second]);
+  double like = std::log10(1 - 1 / (std::pow((double)10, -((double)pl1 / (double)10)) + std::pow((double)10, -((double)pl2 / (double)10))));
+  if (!(like > smallest)) like = smallest;
+  int32_t gq = (int32_t)std::round(-10 * like);
+  if (gq < 0) gq = 0;
+  if (two) {
+    const uint32_t lo = std::min(first, second), hi = std::max(first, second);
+    cons += detail::iupac_of("ACGT"[lo], "ACGT"[hi]);
+  } else cons += first <= 3 ? "ACGT"[first] : first == 4 ? 'N' : '-';
+  qual.push_back((uint32_t)gq);
+}
+
+// pairwiseConsensus(c, align, trimmedtrace1, trimmedtrace2, cons, qual) -- reference src/consensus.h:189-238: one letter per column
+// of the pairwise alignment from the summed profile columns (float + float, then double); columns with a gap take the one trace's
+// column when c.computeUnion, none otherwise.
+template <typename TConfig, typename TAlign, typename TProfile>
+inline void pairwiseConsensus(TConfig const& c, TAlign const& align, TProfile const& t1, TProfile const& t2, std::string& cons, std::vector<uint32_t>& qual) {
+  std::size_t s1 = 0, s2 = 0;
+  std::vector<double> cl(6);
+  const std::size_t L = align.shape()[1];
+  for (std::size_t j = 0; j < L; ++j) {
+    const bool g1 = align[0][j] == '-', g2 = align[1][j] == '-';
+    if (!g1 && !g2) {
+      for (int k = 0; k < 6; ++k) cl[k] = t1[k][s1] + t2[k][s2];
+      gtLetter(c, cl, cons, qual);
+    } else if (c.computeUnion) {
+      if (!g1) { for (int k = 0; k < 6; ++k) cl[k] = t1[k][s1]; gtLetter(c, cl, cons, qual); }
+      if (!g2) { for (int k = 0; k < 6; ++k) cl[k] = t2[k][s2]; gtLetter(c, cl, cons, qual); }
+    }
+    s1 += g1 ? 0 : 1; s2 += g2 ? 0 : 1;
+  }
+}
+
+// What consensus() holds for one trace pair after its DP sequence; ok = false where it prints "No sufficient trace overlap!".
+template <typename TAlign>
+struct ConsensusOut {
+  bool forward = true, ok = false;
+  int32_t score = 0;
+  uint32_t numAligned = 0, numMatch = 0;
+  TAlign align;
+  std::string cons;
+  std::vector<uint32_t> qual;
+};
+
+// consensusBatch -- `tracy consensus` for many trace PAIRS, reference src/consensus.h:499-577: orientation of every second trace by
+// two global score fills (strict '>' keeps forward), the global alignment, the overlap gate (c.minOverlap, c.matchFraction) and
+// pairwiseConsensus -- two batched GPU calls for all pairs, the letters on the host. p1 / p2: createProfile() of the trimmed traces
+// (p2 as read; on return p2[i] is the oriented profile the alignment was made with, like consensus()'s trimmedtrace2).
+template <typename TCtx, typename TConfig, typename TProfile, typename TOut, typename TScore>
+inline void consensusBatch(TCtx& g, TConfig const& c, std::vector<const TProfile*> const& p1, std::vector<TProfile*> const& p2, std::vector<TOut>& out,
+                           TScore const& sc) {
+  const std::size_t n = p1.size();
+  out.assign(n, TOut());
+  if (n == 0) return;
+  const AlignConfig<true, true> global;
+  std::vector<TProfile> rev(n);
+  std::vector<const TProfile*> a(2 * n), b(2 * n);
+  for (std::size_t i = 0; i < n; ++i) {
+    detail::revcomp_profile_host(*p2[i], rev[i]);                               // reverseComplementProfile, src/consensus.h:514
+    a[i] = a[n + i] = p1[i]; b[i] = p2[i]; b[n + i] = &rev[i];
+  }
+  const std::vector<int32_t> gs = gotohBatch(g, a, b, global, sc);            // gsFwd / gsRev, :517-518
+  for (std::size_t i = 0; i < n; ++i) {
+    out[i].forward = gs[i] > gs[n + i];                                         // :523
+    if (!out[i].forward) std::swap(*p2[i], rev[i]);
+    b[i] = p2[i];
+  }
+  a.resize(n); b.resize(n);
+  std::vector<std::pair<std::string, std::string> > rows;
+  const std::vector<int32_t> s = gotohBatch(g, a, b, global, sc, nullptr, &rows);   // :535
+  for (std::size_t i = 0; i < n; ++i) {
+    TOut& o = out[i];
+    o.score = s[i];
+    const std::size_t L = rows[i].first.size();
+    detail::resize_align(o.align, 2, L);
+    for (std::size_t j = 0; j < L; ++j) {
+      const char x = rows[i].first[j], y = rows[i].second[j];
+      o.align[0][j] = x; o.align[1][j] = y;
+      if (x != '-' && y != '-') { ++o.numAligned; if (x == y) ++o.numMatch; }
+    }
+    const double frac = o.numAligned ? (double)o.numMatch / (double)o.numAligned : 0.0;
+    o.ok = !(o.numAligned < c.minOverlap || frac < c.matchFraction);            // :546-549
+    if (o.ok) pairwiseConsensus(c, o.align, *p1[i], *p2[i], o.cons, o.qual);
+  }
+}
+
 // ---- `tracy decompose`: the DP sequence of indigo() for many traces -----------------------------------------------------------
 // trimmedSeq(str, ltrim, rtrim) -- reference src/abif.h:68-75.
 inline std::string trimmedSeq(std::string const& str, uint32_t ltrim, uint32_t rtrim) {
@@ -1161,9 +1389,11 @@ struct DecomposeOut {
 // alignments -- every DP / sweep / fit stage ONE batched GPU call over all traces, the glue in between on the host.
 // tr / bc / rs: tracy's Trace, BaseCalls (primary, secondary, secDecompose are updated in place) and ReferenceSlice (refslice = the
 // reference sequence on entry; forward, refslice, pos, kmersupport as indigo() leaves them). c: trimLeft, trimRight, maxindel, madc.
+// traces (optional): the samples of `tr` already resident on the device (TraceSet over the same list), e.g. shared with basecallBatch.
 template <typename TConfig, typename TTrace, typename TBaseCalls, typename TRefSlice, typename TOut, typename TScore>
 inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrace*> const& tr, std::vector<TBaseCalls*> const& bc,
-                           std::vector<TRefSlice*> const& rs, std::vector<TOut>& out, TScore const& sc, std::ostream* log = nullptr) {
+                           std::vector<TRefSlice*> const& rs, std::vector<TOut>& out, TScore const& sc, std::ostream* log = nullptr,
+                           TraceSet const* traces = nullptr) {
   typedef Matrix<float> TProfile;
   typedef decltype(out[0].align) TAlign;
   typedef decltype(out[0].bp) TBreakpoint;
@@ -1171,13 +1401,15 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
   out.assign(n, TOut());
   if (n == 0) return;
   const AlignConfig<true, false> semiglobal;
+  detail::StageClock clk;
   std::vector<TProfile> prof(n);
   {
     std::vector<const TBaseCalls*> cbc(bc.begin(), bc.end());
     std::vector<TProfile*> pp(n);
     for (std::size_t i = 0; i < n; ++i) pp[i] = &prof[i];
-    createProfileBatch(g, tr, cbc, pp, (int32_t)c.trimLeft, (int32_t)c.trimRight);             // src/indigo.h:190-192
+    createProfileBatch(g, tr, cbc, pp, (int32_t)c.trimLeft, (int32_t)c.trimRight, traces);     // src/indigo.h:190-192
   }
+  clk.lap("createProfile");
   std::vector<std::string> rev(n);
   std::vector<const TProfile*> pa(2 * n);
   std::vector<const std::string*> pb(2 * n);
@@ -1186,7 +1418,9 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
     rev[i] = rs[i]->refslice; reverseComplement(rev[i]);
     pa[i] = pa[n + i] = &prof[i]; pb[i] = &rs[i]->refslice; pb[n + i] = &rev[i];
   }
+  clk.lap("findBreakpoint + revcomp");
   const std::vector<int32_t> gs = gotohBatch(g, pa, pb, semiglobal, sc);                         // gsFwd / gsRev, src/indigo.h:235-236
+  clk.lap("orientation scores");
   for (std::size_t i = 0; i < n; ++i) {
     rs[i]->kmersupport = 0; rs[i]->pos = 0;
     rs[i]->forward = gs[i] > gs[n + i];                                                          // src/indigo.h:243
@@ -1195,6 +1429,7 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
   pa.resize(n); pb.resize(n);
   std::vector<std::pair<std::string, std::string> > rows;
   const std::vector<int32_t> ali = gotohBatch(g, pa, pb, semiglobal, sc, nullptr, &rows);        // src/indigo.h:302
+  clk.lap("alignment");
   typedef DecomposeItem<TAlign, TBaseCalls, TBreakpoint, TRefSlice, std::vector<std::pair<int32_t, int32_t> > > TItem;
   std::vector<TItem> items;
   std::vector<std::size_t> live;
@@ -1215,17 +1450,20 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
     const std::size_t i = live[k];
     items[k].align = &out[i].align; items[k].bc = bc[i]; items[k].bp = out[i].bp; items[k].rs = rs[i]; items[k].dcp = &out[i].dcp;
   }
+  clk.lap("breakpoints + items");
   decomposeAllelesBatch(g, c, items, log);                                                       // src/indigo.h:340
+  clk.lap("decomposeAlleles");
   if (live.empty()) return;
   // allelicFraction (src/indigo.h:350) reads bcPos[i + trimLeft] even where trimmedSeq() left a short read untrimmed (out of
   // bounds there): such reads keep the start value
-  std::vector<const TTrace*> ftr; std::vector<const TBaseCalls*> fbc; std::vector<std::size_t> fit;
+  std::vector<const TTrace*> ftr; std::vector<const TBaseCalls*> fbc; std::vector<std::size_t> fit; std::vector<int64_t> fidx;
   for (std::size_t i : live) {
     generateSecondaryDecomposed(*tr[i], *bc[i]);                                                 // src/indigo.h:344
-    if ((std::size_t)c.trimLeft + c.trimRight + 1 < bc[i]->primary.size()) { ftr.push_back(tr[i]); fbc.push_back(bc[i]); fit.push_back(i); }
+    if ((std::size_t)c.trimLeft + c.trimRight + 1 < bc[i]->primary.size()) { ftr.push_back(tr[i]); fbc.push_back(bc[i]); fit.push_back(i); fidx.push_back((int64_t)i); }
   }
-  const std::vector<std::pair<double, double> > fr = allelicFractionBatch(g, c, ftr, fbc);
+  const std::vector<std::pair<double, double> > fr = allelicFractionBatch(g, c, ftr, fbc, traces, traces ? &fidx : nullptr);
   for (std::size_t k = 0; k < fit.size(); ++k) out[fit[k]].a1a2 = fr[k];
+  clk.lap("allelicFraction");
   // allele-specific alignments (src/indigo.h:355-388): string x string
   const std::size_t m = live.size();
   std::vector<std::string> pri(m), sec(m);
@@ -1248,7 +1486,9 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
     trimReferenceSlice(c, al, dst);
     qb[k] = &dst.refslice;
   }
+  clk.lap("allele alignments 1");
   const std::vector<int32_t> s2 = gotohBatch(g, qa, qb, semiglobal, sc, nullptr, &rows);         // final1 / final2
+  clk.lap("allele alignments 2");
   auto fill = [](TAlign& dst, std::pair<std::string, std::string> const& r) {
     detail::resize_align(dst, 2, r.first.size());
     for (std::size_t j = 0; j < r.first.size(); ++j) { dst[0][j] = r.first[j]; dst[1][j] = r.second[j]; }
@@ -1263,6 +1503,7 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
   qa.resize(m); qb.resize(m);
   const std::vector<int32_t> s3 = gotohBatch(g, qa, qb, AlignConfig<false, false>(), sc, nullptr, &rows);   // allele 1 vs allele 2, global
   for (std::size_t k = 0; k < m; ++k) { out[live[k]].a3Score = s3[k]; fill(out[live[k]].final3, rows[k]); }
+  clk.lap("allele 1 vs allele 2");
 }
 
 }  // namespace tracy_b200

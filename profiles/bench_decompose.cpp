@@ -68,18 +68,21 @@ int main(int argc, char** argv) {
     uint64_t k0 = 0, k1 = 0, h0 = 0, h1 = 0, d0 = 0, d1 = 0;
     tb_ctx_stats(g.get(), &k0, &h0, &d0);
     const auto t0 = std::chrono::steady_clock::now();
-    tracy_b200::basecallBatch(g, ptr, pbc, 0.33f);
+    tracy_b200::TraceSet resident(g, ptr);                          // the samples cross PCIe once for basecall, createProfile, allelicFraction
+    const auto tu = std::chrono::steady_clock::now();
+    tracy_b200::basecallBatch(g, ptr, pbc, 0.33f, &resident);
     const auto t1 = std::chrono::steady_clock::now();
-    tracy_b200::decomposeBatch(g, c, ptr, pbc, prs, out, sc);
+    tracy_b200::decomposeBatch(g, c, ptr, pbc, prs, out, sc, nullptr, &resident);
     const auto t2 = std::chrono::steady_clock::now();
+    const double s_up = std::chrono::duration<double>(tu - t0).count();
     tb_ctx_stats(g.get(), &k1, &h1, &d1);
     const double s_bc = std::chrono::duration<double>(t1 - t0).count(), s_dc = std::chrono::duration<double>(t2 - t1).count();
     int ok = 0, shift = 0; long dcp = 0;
     for (int i = 0; i < N; ++i) { ok += out[i].ok; shift += out[i].ok && out[i].bp.indelshift; dcp += (long)out[i].dcp.size(); }
     std::printf("{\"workload\": \"tracy decompose, %d synthetic heterozygous traces (~900 bp, indel 1-25 bp) vs 4 kb references, maxindel 30 (BASELINE.json configs[2])\", "
-                "\"traces\": %d, \"seconds\": %.4f, \"traces_per_s\": %.1f, \"basecall_seconds\": %.4f, \"decompose_seconds\": %.4f, \"decomposed\": %d, "
+                "\"traces\": %d, \"seconds\": %.4f, \"traces_per_s\": %.1f, \"upload_seconds\": %.4f, \"basecall_seconds\": %.4f, \"decompose_seconds\": %.4f, \"decomposed\": %d, "
                 "\"heterozygous_shift_found\": %d, \"decomp_rows\": %ld, \"kernel_launches\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"host\": \"C++ (tracy_b200.hpp decomposeBatch)\"}\n",
-                N, N, s_bc + s_dc, N / (s_bc + s_dc), s_bc, s_dc, ok, shift, dcp, (unsigned long long)(k1 - k0), (unsigned long long)(h1 - h0), (unsigned long long)(d1 - d0));
+                N, N, s_bc + s_dc, N / (s_bc + s_dc), s_up, s_bc - s_up, s_dc, ok, shift, dcp, (unsigned long long)(k1 - k0), (unsigned long long)(h1 - h0), (unsigned long long)(d1 - d0));
   } catch (std::exception const& e) {
     std::printf("{\"error\": \"%s\"}\n", e.what());
     return 1;

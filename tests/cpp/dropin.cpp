@@ -24,6 +24,9 @@
 #include "profile.h"
 #include "decompose.h"
 #include "msa.h"
+#include "json.h"
+#include "trim.h"
+#include "consensus.h"
 
 #define TRACY_B200_WITH_BOOST
 #include "tracy_b200.hpp"
@@ -469,7 +472,8 @@ static void decompose_driver_check(tracy_b200::Context& g) {
   std::vector<const tracy::Trace*> ptr(N); std::vector<tracy::BaseCalls*> pbc(N); std::vector<tracy::ReferenceSlice*> prs(N);
   for (int i = 0; i < N; ++i) { ptr[i] = &tr[i]; pbc[i] = &bc2[i]; prs[i] = &rs2[i]; }
   std::vector<tracy_b200::DecomposeOut<TAlign, tracy::ReferenceSlice, tracy::TraceBreakpoint> > got;
-  tracy_b200::decomposeBatch(g, c, ptr, pbc, prs, got, sc, nullptr);
+  tracy_b200::TraceSet resident(g, ptr);                  // the samples uploaded once; createProfile takes all of it, allelicFraction a subset by index
+  tracy_b200::decomposeBatch(g, c, ptr, pbc, prs, got, sc, nullptr, &resident);
   int nok = 0;
   for (int i = 0; i < N; ++i) {
     const Want& w = want[i];
@@ -486,6 +490,114 @@ static void decompose_driver_check(tracy_b200::Context& g) {
     expect(same, "decomposeBatch (indigo DP sequence)", i);
   }
   expect(nok >= N - 3, "decomposeBatch: accepted traces", nok);
+}
+
+// consensus()'s DP sequence per trace pair from the reference's own functions (src/consensus.h:499-577) against
+// tracy_b200::consensusBatch on the B200: orientation, global alignment, overlap gate, pairwiseConsensus
+static void consensus_driver_check(tracy_b200::Context& g) {
+  const int N = 24;
+  struct CC { bool useIUPAC, computeUnion; uint32_t minOverlap; float matchFraction; };
+  const char comp[] = "TGCA";
+  for (int variant = 0; variant < 2; ++variant) {
+    std::vector<TProfile> p1((size_t)N), p2((size_t)N);
+    for (int i = 0; i < N; ++i) {
+      const std::string gseq = random_seq(1400);
+      std::string a = gseq.substr(50, 500 + rng() % 200), b = mutate(gseq.substr(250 + rng() % 200, 500 + rng() % 300), 0.01, 0.004);
+      if (i == N - 1) b = random_seq(600);
+      if (rng() % 2) { std::string r(b.rbegin(), b.rend()); for (auto& ch : r) ch = comp[ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3]; b = r; }
+      random_profile(a, p1[(size_t)i], false); random_profile(b, p2[(size_t)i], false);
+    }
+    CC nc{variant == 1, variant == 0, 25u, 0.5f};
+    tracy::ConsensusConfig rc; rc.useIUPAC = nc.useIUPAC; rc.computeUnion = nc.computeUnion;
+    tracy::DnaScore<int32_t> sc(3, -5, -10, -4);
+    std::vector<TProfile> q2(p2);
+    std::vector<const TProfile*> a((size_t)N); std::vector<TProfile*> b((size_t)N);
+    for (int i = 0; i < N; ++i) { a[(size_t)i] = &p1[(size_t)i]; b[(size_t)i] = &q2[(size_t)i]; }
+    std::vector<tracy_b200::ConsensusOut<TAlign> > out;
+    tracy_b200::consensusBatch(g, nc, a, b, out, sc);
+    int passed = 0;
+    for (int i = 0; i < N; ++i) {
+      tracy::AlignConfig<true, true> global;
+      TProfile rev, second;
+      tracy::reverseComplementProfile(p2[(size_t)i], rev);
+      const int32_t gf = tracy::gotohScore(p1[(size_t)i], p2[(size_t)i], global, sc), gr = tracy::gotohScore(p1[(size_t)i], rev, global, sc);
+      const bool forward = gf > gr;
+      tracy::copyProfile(forward ? p2[(size_t)i] : rev, second);
+      TAlign fali;
+      const int32_t score = tracy::gotoh(p1[(size_t)i], second, fali, global, sc);
+      uint32_t na = 0, nm = 0;
+      for (size_t j = 0; j < fali.shape()[1]; ++j) if (fali[0][j] != '-' && fali[1][j] != '-') { ++na; if (fali[0][j] == fali[1][j]) ++nm; }
+      const double mf = na ? (double)nm / (double)na : 0.0;
+      const bool pass = !(na < nc.minOverlap || mf < nc.matchFraction);
+      bool ok = out[(size_t)i].forward == forward && out[(size_t)i].score == score && out[(size_t)i].ok == pass && same_align(fali, out[(size_t)i].align);
+      if (ok && pass) {
+        std::string cons; std::vector<uint32_t> qual;
+        tracy::pairwiseConsensus(rc, fali, p1[(size_t)i], second, cons, qual);
+        ok = cons == out[(size_t)i].cons && qual == out[(size_t)i].qual;
+        ++passed;
+      }
+      expect(ok, "consensusBatch (consensus DP sequence + pairwiseConsensus)", 100 * variant + i);
+    }
+    expect(passed >= N - 3 && !out[(size_t)N - 1].ok, "consensusBatch: overlap gate", passed);
+  }
+}
+
+// Several devices behind one handle: the same batch through a MultiContext (every visible device, and device 0 named twice so that the
+// range split and the per-device result slices are exercised on a one-GPU box too) and through the single Context must agree pair by
+// pair; the text broadcast + per-device index + sharded anchoring must agree with the single-device index.
+static void multi_check(tracy_b200::Context& g) {
+  int visible = 1;
+  { tb_multi* probe = nullptr; if (tb_multi_create(&probe, nullptr, 0) == TB_OK) { visible = tb_multi_size(probe); tb_multi_destroy(probe); } }
+  std::vector<std::vector<int> > layouts;
+  layouts.push_back(std::vector<int>{0, 0});
+  layouts.push_back(std::vector<int>{0, 0, 0});
+  if (visible > 1) { std::vector<int> all; for (int d = 0; d < visible; ++d) all.push_back(d); layouts.push_back(all); }
+  const int N = 61;
+  std::vector<TProfile> ps((size_t)N);
+  std::vector<std::string> refs((size_t)N);
+  std::vector<const TProfile*> pa;
+  std::vector<const std::string*> pb;
+  tracy_b200::AlignConfig<true, false> ac;
+  tracy_b200::DnaScore<int32_t> sc(3, -5, -10, -4);
+  for (int i = 0; i < N; ++i) {
+    refs[(size_t)i] = random_seq(200 + (int)(rng() % 1500));
+    const size_t L = 60 + rng() % 500;
+    random_profile(mutate(refs[(size_t)i].substr(rng() % 50, std::min(L, refs[(size_t)i].size() - 60)), 0.02, 0.01), ps[(size_t)i], false);
+    pa.push_back(&ps[(size_t)i]); pb.push_back(&refs[(size_t)i]);
+  }
+  std::vector<std::string> ops1;
+  std::vector<std::pair<std::string, std::string> > rows1;
+  const std::vector<int32_t> s1 = tracy_b200::gotohBatch(g, pa, pb, ac, sc, &ops1, &rows1);
+  std::string text = random_seq(30000);
+  AnchorCfg c; c.genome = boost::filesystem::path("mem"); c.trimLeft = 50; c.trimRight = 50; c.kmer = 15; c.maxindel = 1000; c.minKmerSupport = 3;
+  std::vector<tracy::BaseCalls> bcs(19);
+  std::vector<const tracy::BaseCalls*> pbc;
+  for (int i = 0; i < 19; ++i) {
+    std::string s = mutate(text.substr(rng() % 28000, 300 + rng() % 700), 0.01, 0.003);
+    if (i % 2) tracy::reverseComplement(s);
+    if (i == 18) s = random_seq(400);
+    bcs[(size_t)i].consensus = s; pbc.push_back(&bcs[(size_t)i]);
+  }
+  std::vector<tracy::ReferenceSlice> r1(19); std::vector<tracy::ReferenceSlice*> pr1; for (auto& r : r1) pr1.push_back(&r);
+  tracy_b200::Index index(g, text);
+  std::vector<int64_t> pos1;
+  const std::vector<char> ok1 = tracy_b200::anchorBatch(g, index, c, pbc, pr1, &pos1);
+  for (size_t l = 0; l < layouts.size(); ++l) {
+    tracy_b200::MultiContext mg(layouts[l]);
+    std::vector<std::string> ops2;
+    std::vector<std::pair<std::string, std::string> > rows2;
+    const std::vector<int32_t> s2 = tracy_b200::gotohBatch(mg, pa, pb, ac, sc, &ops2, &rows2);
+    expect(s1 == s2 && ops1 == ops2 && rows1 == rows2 && mg.size() == (int)layouts[l].size(), "MultiContext gotohBatch == Context gotohBatch", (int)l);
+    const std::vector<int32_t> s3 = tracy_b200::gotohBatch(mg, pa, pb, ac, sc);
+    expect(s1 == s3, "MultiContext gotohBatch (score only)", (int)l);
+    tracy_b200::MultiIndex mi(mg, text);
+    std::vector<tracy::ReferenceSlice> r2(19); std::vector<tracy::ReferenceSlice*> pr2; for (auto& r : r2) pr2.push_back(&r);
+    std::vector<int64_t> pos2;
+    const std::vector<char> ok2 = tracy_b200::anchorBatch(mg, mi, c, pbc, pr2, &pos2);
+    bool same = ok1 == ok2 && pos1 == pos2;
+    for (int i = 0; same && i < 19; ++i) same = !ok1[(size_t)i] || (r1[(size_t)i].forward == r2[(size_t)i].forward && r1[(size_t)i].kmersupport == r2[(size_t)i].kmersupport);
+    expect(same, "MultiContext text broadcast + anchorBatch == single device", (int)l);
+  }
 }
 
 int main() {
@@ -505,6 +617,8 @@ int main() {
     distance_check(g);
     assemble_check(g);
     decompose_driver_check(g);
+    consensus_driver_check(g);
+    multi_check(g);
     // batch form: the same pairs in one call
     {
       std::vector<TProfile> ps(8);

@@ -27,6 +27,9 @@
 #include "profile.h"
 #include "decompose.h"
 #include "msa.h"
+#include "json.h"
+#include "trim.h"
+#include "consensus.h"
 
 #define TRACY_B200_WITH_BOOST
 #include "tracy_b200.hpp"
@@ -38,15 +41,20 @@ struct Ctx { long calls = 0, pairs = 0; };
 // the call shape revSeqBasedOnDist needs, found by argument-dependent lookup on Ctx
 template <typename TA, typename TB, bool H, bool V, typename TScore>
 inline std::vector<int32_t> gotohBatch(Ctx& g, std::vector<const TA*> const& a1, std::vector<const TB*> const& a2, tracy_b200::AlignConfig<H, V> const&,
-                                       TScore const& sc, std::vector<std::string>* ops = nullptr) {
+                                       TScore const& sc, std::vector<std::string>* ops = nullptr,
+                                       std::vector<std::pair<std::string, std::string> >* rows = nullptr) {
   std::vector<int32_t> s(a1.size());
   tracy::AlignConfig<H, V> ac;
   if (ops) ops->assign(a1.size(), std::string());
+  if (rows) rows->assign(a1.size(), std::pair<std::string, std::string>());
   for (std::size_t i = 0; i < a1.size(); ++i) {
-    if (!ops) { s[i] = tracy::gotohScore(*a1[i], *a2[i], ac, sc); continue; }
+    if (!ops && !rows) { s[i] = tracy::gotohScore(*a1[i], *a2[i], ac, sc); continue; }
     boost::multi_array<char, 2> al;
     s[i] = tracy::gotoh(*a1[i], *a2[i], al, ac, sc);
-    for (std::size_t j = 0; j < al.shape()[1]; ++j) (*ops)[i] += al[0][j] == '-' ? 'h' : al[1][j] == '-' ? 'v' : 's';   // start -> end, as tb_gotoh_* returns them
+    for (std::size_t j = 0; j < al.shape()[1]; ++j) {
+      if (ops) (*ops)[i] += al[0][j] == '-' ? 'h' : al[1][j] == '-' ? 'v' : 's';   // start -> end, as tb_gotoh_* returns them
+      if (rows) { (*rows)[i].first += al[0][j]; (*rows)[i].second += al[1][j]; }
+    }
   }
   ++g.calls; g.pairs += (long)a1.size();
   return s;
@@ -285,6 +293,85 @@ int main() {
       for (std::size_t j = 0; ok && j < al_ref.shape()[1]; ++j) ok = al_ref[i][j] == al_new[i][j];
     if (!ok) { ++failures; std::printf("MISMATCH assembleReference #%d (num=%d)\n", rep, num); }
     else std::printf("assembleReference #%d: num=%d, %zu kept, %zu x %zu alignment\n", rep, num, kept, (std::size_t)al_new.shape()[0], (std::size_t)al_new.shape()[1]);
+  }
+  // `tracy consensus`: gtLetter on many weight vectors, then the DP sequence of consensus() (src/consensus.h:499-577) -- orientation,
+  // global alignment, overlap gate, pairwiseConsensus -- against the same sequence made of the reference's functions
+  {
+    struct CC { bool useIUPAC, computeUnion; uint32_t minOverlap; float matchFraction; };
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    long bad = 0;
+    for (int t = 0; t < 20000; ++t) {
+      std::vector<double> cl(6, 0.0);
+      const int kind = t % 4;
+      for (int k = 0; k < 6; ++k) {
+        if (kind == 0) cl[k] = U(rng);
+        else if (kind == 1) cl[k] = (double)(float)(U(rng) * (double)(rng() % 2));
+        else if (kind == 2) cl[k] = (double)(rng() % 4) / 2;
+        else cl[k] = std::pow(10.0, -30 * U(rng));
+      }
+      for (int iu = 0; iu < 2; ++iu) {
+        tracy::ConsensusConfig rc; rc.useIUPAC = iu != 0;
+        CC nc{iu != 0, true, 0, 0};
+        std::vector<double> c1(cl), c2(cl);
+        std::string s1, s2; std::vector<uint32_t> q1, q2;
+        tracy::gtLetter(rc, c1, s1, q1);
+        tracy_b200::gtLetter(nc, c2, s2, q2);
+        if (s1 != s2 || q1 != q2) ++bad;
+      }
+    }
+    ++checks;
+    if (bad) { ++failures; std::printf("MISMATCH gtLetter: %ld of 40000\n", bad); } else std::printf("gtLetter: 40000 weight vectors equal\n");
+    for (int rep = 0; rep < 8; ++rep) {
+      const int n = 6;
+      std::vector<TProfile> p1((std::size_t)n), p2((std::size_t)n);
+      for (int i = 0; i < n; ++i) {
+        std::string gseq((std::size_t)400, 'A');
+        for (auto& ch : gseq) ch = "ACGT"[rng() % 4];
+        std::string a = gseq.substr(20, 150 + rng() % 80), b = gseq.substr(90 + rng() % 60, 150 + rng() % 90);
+        for (int e = 0; e < 4; ++e) b[rng() % b.size()] = "ACGT"[rng() % 4];
+        if (rng() % 3 == 0) b.erase(rng() % (b.size() - 6), 1 + rng() % 3);
+        if (i == n - 1) for (auto& ch : b) ch = "ACGT"[rng() % 4];
+        if (rng() % 2) { std::string r(b.rbegin(), b.rend()); for (auto& ch : r) ch = comp[ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3]; b = r; }
+        profile_of(a, p1[(std::size_t)i], 0.5f); profile_of(b, p2[(std::size_t)i], 0.5f);
+      }
+      CC nc{rep % 2 == 1, rep % 4 < 2, 25u, 0.5f};
+      tracy::ConsensusConfig rc; rc.useIUPAC = nc.useIUPAC; rc.computeUnion = nc.computeUnion;
+      tracy::DnaScore<int32_t> sc(3, -5, -10, -4);
+      std::vector<TProfile> q2(p2);
+      std::vector<const TProfile*> a((std::size_t)n); std::vector<TProfile*> b((std::size_t)n);
+      for (int i = 0; i < n; ++i) { a[(std::size_t)i] = &p1[(std::size_t)i]; b[(std::size_t)i] = &q2[(std::size_t)i]; }
+      typedef tracy_b200::ConsensusOut<boost::multi_array<char, 2> > TOut;
+      std::vector<TOut> out;
+      cpu_double::Ctx g;
+      tracy_b200::consensusBatch(g, nc, a, b, out, sc);
+      bool ok = true;
+      for (int i = 0; ok && i < n; ++i) {
+        tracy::AlignConfig<true, true> global;
+        TProfile rev, second;
+        tracy::reverseComplementProfile(p2[(std::size_t)i], rev);
+        const int32_t gf = tracy::gotohScore(p1[(std::size_t)i], p2[(std::size_t)i], global, sc), gr = tracy::gotohScore(p1[(std::size_t)i], rev, global, sc);
+        const bool forward = gf > gr;
+        tracy::copyProfile(forward ? p2[(std::size_t)i] : rev, second);
+        boost::multi_array<char, 2> fali;
+        const int32_t score = tracy::gotoh(p1[(std::size_t)i], second, fali, global, sc);
+        uint32_t na = 0, nm = 0;
+        for (std::size_t j = 0; j < fali.shape()[1]; ++j) if (fali[0][j] != '-' && fali[1][j] != '-') { ++na; if (fali[0][j] == fali[1][j]) ++nm; }
+        const double mf = na ? (double)nm / (double)na : 0.0;
+        const bool pass = !(na < nc.minOverlap || mf < nc.matchFraction);
+        TOut const& o = out[(std::size_t)i];
+        ok = o.forward == forward && o.score == score && o.numAligned == na && o.numMatch == nm && o.ok == pass && same(second, q2[(std::size_t)i]) &&
+             o.align.shape()[1] == fali.shape()[1];
+        for (std::size_t j = 0; ok && j < fali.shape()[1]; ++j) ok = o.align[0][j] == fali[0][j] && o.align[1][j] == fali[1][j];
+        if (ok && pass) {
+          std::string cons; std::vector<uint32_t> qual;
+          tracy::pairwiseConsensus(rc, fali, p1[(std::size_t)i], second, cons, qual);
+          ok = cons == o.cons && qual == o.qual;
+        }
+      }
+      ++checks;
+      if (!ok) { ++failures; std::printf("MISMATCH consensusBatch #%d\n", rep); }
+      else std::printf("consensusBatch #%d: %d pairs, union=%d iupac=%d, %ld batched calls for %ld pairs\n", rep, n, (int)nc.computeUnion, (int)nc.useIUPAC, g.calls, g.pairs);
+    }
   }
   std::printf("%d checks, %d mismatches\n", checks, failures);
   return failures ? 1 : 0;

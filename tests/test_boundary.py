@@ -79,3 +79,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "libgotoh_oracle" not in text and "libtracy_ref" not in text, f
+
+
+def test_multi_partition_balances_cost(lib):
+    """tb_multi_partition (host): contiguous pair ranges of equal DP cost for the devices of a tb_multi."""
+    import numpy as np
+    import ctypes as C
+    from tracy_b200 import capi
+    L = capi.lib()
+    L.tb_multi_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
+    rng = np.random.default_rng(1)
+    l1 = rng.integers(10, 2000, 1000).astype(np.int32)
+    l2 = rng.integers(10, 6000, 1000).astype(np.int32)
+    first = (C.c_size_t * 9)()
+    assert L.tb_multi_partition(l1.ctypes.data, l2.ctypes.data, 1000, 8, first) == 0
+    f = [int(x) for x in first]
+    cost = (l1.astype(np.float64) + 1) * (l2 + 1)
+    parts = [cost[a:b].sum() for a, b in zip(f, f[1:])]
+    assert f[0] == 0 and f[-1] == 1000 and max(parts) / (cost.sum() / 8) < 1.15, parts

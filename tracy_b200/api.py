@@ -242,10 +242,13 @@ class Context:
                         _ptr(ops_len) if ops_len is not None else None,
                         _ptr(r0) if r0 is not None else None, _ptr(r1) if r1 is not None else None, r0.shape[1] if r0 is not None else 0,
                         1 if (packed and want_ops) else 0)
-        self._check(self._fn(kind)(self._h, C.byref(b), sc.c(), ac.c(), C.byref(r)))
+        self._run_gotoh(kind, b, sc, ac, r)
         if r0 is not None:
             return scores, ops, ops_len, r0, r1
         return scores, ops, ops_len
+
+    def _run_gotoh(self, kind, b, sc, ac, r):
+        self._check(self._fn(kind)(self._h, C.byref(b), sc.c(), ac.c(), C.byref(r)))
 
     def gotoh_device(self, kind, a1_base, a1_off, a1_len, a2_base, a2_off, a2_len, n, scores, ops=None, ops_stride=0, ops_len=None,
                      sc=DnaScore(3, -5, -10, -4), ac=AlignConfig(True, False), row0=None, row1=None, rows_stride=0, packed=False):
@@ -429,6 +432,94 @@ def rows_from_ops(kind, a1, a2, ops):
     if rc != capi.TB_OK:
         raise TracyError(rc, lib.tb_strerror(rc).decode())
     return r0.raw[:L], r1.raw[:L]
+
+
+class MultiContext(Context):
+    """Several GPUs of one node behind one handle (tb_multi, csrc/multi.cu): gotoh() spreads the pairs of a HOST batch over the
+    devices in cost-balanced contiguous ranges (one host thread and one chunk pipeline per device, every device writes its slice of
+    the result arrays; no data-path collective), build_index() ships the reference text to every device (PCIe once, then GPU to
+    GPU) and indexes it there, anchor() shards the traces. devices: list of device ordinals (None = every visible device); the same
+    ordinal may appear more than once. Everything else (profiles, sweeps, ingest) runs on the first device's context."""
+
+    def __init__(self, devices=None):
+        self._lib = capi.lib()
+        L = self._lib
+        L.tb_multi_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]
+        L.tb_multi_destroy.argtypes = [C.c_void_p]
+        L.tb_multi_destroy.restype = None
+        L.tb_multi_size.argtypes = [C.c_void_p]
+        L.tb_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+        L.tb_multi_ctx.restype = C.c_void_p
+        L.tb_multi_last_error.argtypes = [C.c_void_p]
+        L.tb_multi_last_error.restype = C.c_char_p
+        L.tb_multi_gotoh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, capi.Score, capi.AlignConfig, C.c_void_p, C.POINTER(C.c_size_t)]
+        L.tb_multi_index_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+        L.tb_multi_anchor.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, capi.AnchorConfig, C.c_void_p]
+        h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices) if devices else None
+        rc = L.tb_multi_create(C.byref(h), devs, len(devices) if devices else 0)
+        if rc != capi.TB_OK:
+            raise TracyError(rc, L.tb_strerror(rc).decode() + " (tb_multi_create: are the B200s visible? there is no CPU fallback)")
+        self._m = h
+        self.size = L.tb_multi_size(h)
+        self._h = C.c_void_p(L.tb_multi_ctx(h, 0))             # single-device calls of the base class go to the first device
+        self.device = devices[0] if devices else 0
+        self.last_ranges = None
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.tb_multi_destroy(self._m)
+            self._m = None
+            self._h = None
+
+    def _mcheck(self, rc):
+        if rc != capi.TB_OK:
+            raise TracyError(rc, self._lib.tb_strerror(rc).decode() + ": " + self._lib.tb_multi_last_error(self._m).decode())
+
+    def device_stats(self):
+        out = []
+        for i in range(self.size):
+            k, a, b = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            self._lib.tb_ctx_stats(C.c_void_p(self._lib.tb_multi_ctx(self._m, i)), C.byref(k), C.byref(a), C.byref(b))
+            out.append({"kernel_launches": k.value, "h2d_bytes": a.value, "d2h_bytes": b.value})
+        return out
+
+    def _run_gotoh(self, kind, b, sc, ac, r):
+        first = (C.c_size_t * (self.size + 1))()
+        self._mcheck(self._lib.tb_multi_gotoh(self._m, {PP: 0, SS: 1, PS: 2}[kind], C.byref(b), sc.c(), ac.c(), C.byref(r), first))
+        self.last_ranges = [int(x) for x in first]
+
+    def build_index(self, text):
+        text = np.frombuffer(bytes(text), np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text, np.uint8)
+        hs = (C.c_void_p * self.size)()
+        self._mcheck(self._lib.tb_multi_index_build(self._m, _ptr(text), text.size, hs))
+        return MultiKmerIndex(self, [C.c_void_p(h) for h in hs])
+
+    def anchor(self, index, consensus, trim_left=50, trim_right=50, kmer=15, min_kmer_support=3):
+        cons = consensus if isinstance(consensus, Arena) else pack_seqs(consensus)
+        n = cons.n
+        out = dict(anchored=np.zeros(n, np.uint8), forward=np.ones(n, np.uint8), kmersupport=np.zeros(n, np.uint32),
+                   bestpos=np.zeros(n, np.int64), pass_=np.zeros(n, np.uint8))
+        a = capi.Arena(_ptr(cons.base), _ptr(cons.off), _ptr(cons.len))
+        r = capi.AnchorResult(_ptr(out["anchored"]), _ptr(out["forward"]), _ptr(out["kmersupport"]), _ptr(out["bestpos"]), _ptr(out["pass_"]))
+        hs = (C.c_void_p * self.size)(*[h.value for h in index._hs])
+        self._mcheck(self._lib.tb_multi_anchor(self._m, hs, C.byref(a), n, capi.AnchorConfig(trim_left, trim_right, kmer, min_kmer_support), C.byref(r)))
+        out["anchored"] = out["anchored"].astype(bool)
+        out["forward"] = out["forward"].astype(bool)
+        return out
+
+
+class MultiKmerIndex:
+    """One device-resident index per device of a MultiContext."""
+
+    def __init__(self, mctx, hs):
+        self._ctx, self._hs = mctx, hs
+
+    def close(self):
+        if self._hs and getattr(self._ctx, "_m", None):
+            for i, h in enumerate(self._hs):
+                self._ctx._lib.tb_index_destroy(C.c_void_p(self._ctx._lib.tb_multi_ctx(self._ctx._m, i)), h)
+        self._hs = None
 
 
 class KmerIndex:

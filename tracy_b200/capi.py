@@ -17,6 +17,9 @@ SYMBOLS = [
     "tb_rows_from_ops", "tb_unpack_ops", "tb_decompose_sweep", "tb_version", "tb_create_profile", "tb_revcomp_profile", "tb_trim_reference_slice",
     "tb_find_breakpoint", "tb_basecall", "tb_index_build", "tb_index_destroy", "tb_index_info", "tb_anchor", "tb_ctx_last_anchor_ms",
     "tb_reference_slice", "tb_allelic_fraction", "tb_ctx_last_fraction_ms", "tb_trace_scan", "tb_trace_unpack",
+    "tb_trace_set_create", "tb_trace_set_destroy", "tb_trace_set_info",
+    "tb_multi_create", "tb_multi_destroy", "tb_multi_size", "tb_multi_ctx", "tb_multi_last_error", "tb_multi_partition", "tb_multi_gotoh",
+    "tb_multi_index_build", "tb_multi_anchor",
 ]
 
 

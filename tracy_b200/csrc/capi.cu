@@ -6,8 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tracy_b200.h"
@@ -958,13 +960,171 @@ struct Staged {
 };
 }  // namespace
 
+// ---- device-resident trace samples ---------------------------------------------------------------------------------
+struct tb_trace_set {
+  int device = 0;
+  size_t n = 0;
+  int32_t* d_base = nullptr; int64_t* d_off = nullptr; int32_t* d_len = nullptr;
+  std::vector<int64_t> off; std::vector<int32_t> len;      // host copies (validation, subsets)
+  uint64_t bytes = 0;
+};
+
+int tb_trace_set_destroy(tb_ctx* ctx, tb_trace_set* set) {
+  if (!set) return TB_OK;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (set->d_base) cudaFree(set->d_base);
+  if (set->d_off) cudaFree(set->d_off);
+  if (set->d_len) cudaFree(set->d_len);
+  delete set;
+  return TB_OK;
+}
+
+int tb_trace_set_info(const tb_trace_set* set, size_t* ntraces, uint64_t* device_bytes, tb_arena* device_arena) {
+  if (!set) return TB_ERR_INVALID;
+  if (ntraces) *ntraces = set->n;
+  if (device_bytes) *device_bytes = set->bytes;
+  if (device_arena) { device_arena->base = set->d_base; device_arena->off = set->d_off; device_arena->len = set->d_len; }
+  return TB_OK;
+}
+
+int tb_trace_set_create(tb_ctx* ctx, const int32_t* const* channels, const int32_t* nsamples, size_t nt, tb_trace_set** out) {
+  if (!ctx) return TB_ERR_INVALID;
+  if (!out || (nt && (!channels || !nsamples))) return fail(ctx, TB_ERR_INVALID, "null argument");
+  if (nt > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "ntraces too large");
+  TB_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<tb_trace_set> S(new tb_trace_set);
+  S->device = ctx->device; S->n = nt; S->off.resize(nt); S->len.resize(nt);
+  int64_t total = 0, biggest = 0;
+  for (size_t t = 0; t < nt; ++t) {
+    if (nsamples[t] < 0) return fail(ctx, TB_ERR_INVALID, "negative trace length");
+    for (int k = 0; k < 4; ++k) if (nsamples[t] && !channels[4 * t + k]) return fail(ctx, TB_ERR_INVALID, "null channel pointer");
+    S->off[t] = total; S->len[t] = nsamples[t];
+    total += 4ll * nsamples[t]; biggest = std::max<int64_t>(biggest, 4ll * nsamples[t]);
+  }
+  S->bytes = (uint64_t)std::max<int64_t>(total, 1) * 4 + nt * 12;
+  cudaStream_t st = ctx->lanes[0].stream;
+  auto cleanup = [&](cudaError_t e, const char* what) { tb_trace_set* raw = S.release(); tb_trace_set_destroy(ctx, raw); return cuda_fail(ctx, e, what); };
+  cudaError_t e;
+  if ((e = cudaMalloc((void**)&S->d_base, (size_t)std::max<int64_t>(total, 1) * 4)) != cudaSuccess) return cleanup(e, "cudaMalloc(trace samples)");
+  if ((e = cudaMalloc((void**)&S->d_off, std::max<size_t>(nt, 1) * 8)) != cudaSuccess) return cleanup(e, "cudaMalloc(trace offsets)");
+  if ((e = cudaMalloc((void**)&S->d_len, std::max<size_t>(nt, 1) * 4)) != cudaSuccess) return cleanup(e, "cudaMalloc(trace lengths)");
+  if (nt) {
+    if ((e = cudaMemcpyAsync(S->d_off, S->off.data(), nt * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cleanup(e, "cudaMemcpyAsync(offsets)");
+    if ((e = cudaMemcpyAsync(S->d_len, S->len.data(), nt * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cleanup(e, "cudaMemcpyAsync(lengths)");
+  }
+  // two pinned staging buffers: host threads gather the scattered channel vectors into one while the other crosses PCIe
+  const int64_t chunk_elems = std::max<int64_t>(biggest, (int64_t)8 << 20);      // >= 32 MB, and never less than one trace
+  PinBuf pin[2];
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  auto drop = [&]() { for (int i = 0; i < 2; ++i) { pin[i].release(); if (done[i]) cudaEventDestroy(done[i]); } };
+  for (int i = 0; i < 2 && total; ++i) {
+    if ((e = pin[i].reserve((size_t)std::min<int64_t>(chunk_elems, total) * 4)) != cudaSuccess) { drop(); return cleanup(e, "cudaHostAlloc(trace staging)"); }
+    if ((e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)) != cudaSuccess) { drop(); return cleanup(e, "cudaEventCreate"); }
+  }
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  size_t t0 = 0;
+  int which = 0;
+  bool used[2] = {false, false};
+  while (t0 < nt) {
+    size_t t1 = t0;
+    int64_t elems = 0;
+    while (t1 < nt && elems + 4ll * nsamples[t1] <= chunk_elems) { elems += 4ll * nsamples[t1]; ++t1; }
+    if (elems) {
+      if (used[which] && (e = cudaEventSynchronize(done[which])) != cudaSuccess) { drop(); return cleanup(e, "cudaEventSynchronize"); }
+      int32_t* dst = static_cast<int32_t*>(pin[which].p);
+      const int64_t base_off = S->off[t0];
+      const unsigned nthr = (unsigned)std::min<size_t>(hw, t1 - t0);
+      std::vector<std::thread> pool;
+      for (unsigned w = 0; w < nthr; ++w)
+        pool.emplace_back([&, w]() {
+          for (size_t t = t0 + w; t < t1; t += nthr)
+            for (int k = 0; k < 4; ++k)
+              if (nsamples[t]) std::memcpy(dst + (S->off[t] - base_off) + (int64_t)k * nsamples[t], channels[4 * t + k], (size_t)nsamples[t] * 4);
+        });
+      for (auto& th : pool) th.join();
+      if ((e = cudaMemcpyAsync(S->d_base + base_off, dst, (size_t)elems * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) { drop(); return cleanup(e, "cudaMemcpyAsync(samples)"); }
+      if ((e = cudaEventRecord(done[which], st)) != cudaSuccess) { drop(); return cleanup(e, "cudaEventRecord"); }
+      used[which] = true;
+      which ^= 1;
+    }
+    t0 = t1;
+  }
+  e = cudaStreamSynchronize(st);
+  drop();
+  if (e != cudaSuccess) return cleanup(e, "cudaStreamSynchronize");
+  ctx->h2d += (uint64_t)total * 4 + nt * 12;
+  *out = S.release();
+  return TB_OK;
+}
+
+namespace {
+// The trace arena of a basecall / profile / fraction batch on the device: the caller's host arena uploaded (plain TB_MEM_HOST) or
+// a view into a tb_trace_set (TB_TRACE_SET). host_off / host_len: what validation and sizing read.
+struct TraceView {
+  const int32_t* base = nullptr; const int64_t* off = nullptr; const int32_t* len = nullptr;   // device
+  const int32_t* host_len = nullptr;
+  std::vector<int64_t> sub_off; std::vector<int32_t> sub_len;
+  uint64_t uploaded = 0;
+};
+int resolve_traces(tb_ctx* ctx, const tb_arena& a, int32_t mem, size_t nt, Staged& S, TraceView& V) {
+  if (mem & TB_TRACE_SET) {
+    const tb_trace_set* set = static_cast<const tb_trace_set*>(a.base);
+    if (!set) return fail(ctx, TB_ERR_INVALID, "TB_TRACE_SET without a trace set in trace.base");
+    if (set->device != ctx->device) return fail(ctx, TB_ERR_INVALID, "trace set lives on another device");
+    V.base = set->d_base;
+    if (!a.off) {
+      if (nt != set->n) return fail(ctx, TB_ERR_INVALID, "ntraces differs from the trace set's size (pass indices in trace.off for a subset)");
+      V.off = set->d_off; V.len = set->d_len; V.host_len = set->len.data();
+      return TB_OK;
+    }
+    V.sub_off.resize(nt); V.sub_len.resize(nt);
+    for (size_t i = 0; i < nt; ++i) {
+      if (a.off[i] < 0 || (size_t)a.off[i] >= set->n) return fail(ctx, TB_ERR_INVALID, "trace index outside the trace set");
+      V.sub_off[i] = set->off[(size_t)a.off[i]]; V.sub_len[i] = set->len[(size_t)a.off[i]];
+    }
+    void *d_o, *d_l;
+    TB_CUDA(ctx, S.up(&d_o, V.sub_off.data(), nt * 8)); TB_CUDA(ctx, S.up(&d_l, V.sub_len.data(), nt * 4));
+    V.off = (const int64_t*)d_o; V.len = (const int32_t*)d_l; V.host_len = V.sub_len.data();
+    V.uploaded = nt * 12;
+    return TB_OK;
+  }
+  if (!a.base || !a.off || !a.len) return fail(ctx, TB_ERR_INVALID, "null pointer in the trace arena");
+  long long tmax = 0;
+  for (size_t i = 0; i < nt; ++i) {
+    if (a.len[i] < 0 || a.off[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative trace offset/length");
+    tmax = std::max<long long>(tmax, a.off[i] + 4ll * a.len[i]);
+  }
+  void *d_tr, *d_o, *d_l;
+  TB_CUDA(ctx, S.up(&d_tr, a.base, (size_t)std::max(tmax, 1ll) * 4));
+  TB_CUDA(ctx, S.up(&d_o, a.off, nt * 8)); TB_CUDA(ctx, S.up(&d_l, a.len, nt * 4));
+  V.base = (const int32_t*)d_tr; V.off = (const int64_t*)d_o; V.len = (const int32_t*)d_l; V.host_len = a.len;
+  V.uploaded = (uint64_t)tmax * 4 + nt * 12;
+  return TB_OK;
+}
+// Outputs of a batch back to the host: one copy when the items tile the arena without holes, one per item otherwise.
+extern "C++" template <typename T>
+cudaError_t copy_items_back(T* host, const T* dev, const int64_t* off, const int32_t* cap, const int32_t* used, int mul, size_t nt, cudaStream_t st) {
+  bool dense = true;
+  int64_t at = nt ? off[0] : 0;
+  for (size_t i = 0; i < nt && dense; ++i) { dense = off[i] == at; at += (int64_t)mul * cap[i]; }
+  if (dense && nt) return cudaMemcpyAsync(host + off[0], dev + off[0], (size_t)(at - off[0]) * sizeof(T), cudaMemcpyDeviceToHost, st);
+  for (size_t i = 0; i < nt; ++i) {
+    cudaError_t e = cudaMemcpyAsync(host + off[i], dev + off[i], (size_t)mul * used[i] * sizeof(T), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+}  // namespace
+
 int tb_create_profile(tb_ctx* ctx, const tb_profile_batch* b, float* out_base, const int64_t* out_off, int32_t* out_len) {
   if (!ctx) return TB_ERR_INVALID;
   if (!b || !out_base || !out_off || !out_len) return fail(ctx, TB_ERR_INVALID, "null batch/output");
   const size_t nt = b->ntraces;
   if (nt == 0) return TB_OK;
   if (nt > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "ntraces too large");
-  if (!b->trace.base || !b->trace.off || !b->trace.len || !b->bcpos.base || !b->bcpos.off || !b->bcpos.len || !b->primary_base || !b->secondary_base)
+  const int32_t mem = b->mem & ~TB_TRACE_SET;
+  if (!b->trace.base || (!(b->mem & TB_TRACE_SET) && (!b->trace.off || !b->trace.len)) || !b->bcpos.base || !b->bcpos.off || !b->bcpos.len || !b->primary_base ||
+      !b->secondary_base)
     return fail(ctx, TB_ERR_INVALID, "null pointer in profile batch");
   TB_CUDA(ctx, cudaSetDevice(ctx->device));
   Lane& L = ctx->lanes[0];
@@ -980,21 +1140,22 @@ int tb_create_profile(tb_ctx* ctx, const tb_profile_batch* b, float* out_base, c
     TB_CUDA(ctx, cudaStreamSynchronize(st));
     return TB_OK;
   }
-  if (b->mem != TB_MEM_HOST) return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST or TB_MEM_DEVICE");
-  long long tmax = 0, bmax = 0, omax = 0;
+  if (mem != TB_MEM_HOST) return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST (optionally with TB_TRACE_SET) or TB_MEM_DEVICE");
+  long long bmax = 0, omax = 0;
   for (size_t i = 0; i < nt; ++i) {
-    if (b->trace.len[i] < 0 || b->bcpos.len[i] < 0 || b->trace.off[i] < 0 || b->bcpos.off[i] < 0 || out_off[i] < 0)
-      return fail(ctx, TB_ERR_INVALID, "negative offset/length");
-    tmax = std::max<long long>(tmax, b->trace.off[i] + 4ll * b->trace.len[i]);
+    if (b->bcpos.len[i] < 0 || b->bcpos.off[i] < 0 || out_off[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative offset/length");
     bmax = std::max<long long>(bmax, b->bcpos.off[i] + b->bcpos.len[i]);
     omax = std::max<long long>(omax, out_off[i] + 6ll * b->bcpos.len[i]);
   }
   {
     Staged S(st);
-    void *d_tr, *d_bp, *d_pri, *d_sec, *d_toff, *d_tlen, *d_boff, *d_blen, *d_tl = nullptr, *d_trr = nullptr, *d_out, *d_ooff, *d_olen;
-    TB_CUDA(ctx, S.up(&d_tr, b->trace.base, (size_t)tmax * 4)); TB_CUDA(ctx, S.up(&d_bp, b->bcpos.base, (size_t)bmax * 4));
+    TraceView V;
+    if (int rc = resolve_traces(ctx, b->trace, b->mem, nt, S, V)) return rc;
+    const void *d_tr = V.base, *d_toff = V.off, *d_tlen = V.len;
+    const long long tmax = (long long)(V.uploaded / 4);
+    void *d_bp, *d_pri, *d_sec, *d_boff, *d_blen, *d_tl = nullptr, *d_trr = nullptr, *d_out, *d_ooff, *d_olen;
+    TB_CUDA(ctx, S.up(&d_bp, b->bcpos.base, (size_t)bmax * 4));
     TB_CUDA(ctx, S.up(&d_pri, b->primary_base, (size_t)bmax)); TB_CUDA(ctx, S.up(&d_sec, b->secondary_base, (size_t)bmax));
-    TB_CUDA(ctx, S.up(&d_toff, b->trace.off, nt * 8)); TB_CUDA(ctx, S.up(&d_tlen, b->trace.len, nt * 4));
     TB_CUDA(ctx, S.up(&d_boff, b->bcpos.off, nt * 8)); TB_CUDA(ctx, S.up(&d_blen, b->bcpos.len, nt * 4));
     if (b->trim_left) TB_CUDA(ctx, S.up(&d_tl, b->trim_left, nt * 4));
     if (b->trim_right) TB_CUDA(ctx, S.up(&d_trr, b->trim_right, nt * 4));
@@ -1009,9 +1170,8 @@ int tb_create_profile(tb_ctx* ctx, const tb_profile_batch* b, float* out_base, c
     ctx->launches++;
     TB_CUDA(ctx, cudaMemcpyAsync(out_len, d_olen, nt * 4, cudaMemcpyDeviceToHost, st));
     TB_CUDA(ctx, cudaStreamSynchronize(st));
-    // items may be sparse in the caller's output arena: copy each item's 6 * sz floats back
-    for (size_t i = 0; i < nt; ++i)
-      TB_CUDA(ctx, cudaMemcpyAsync(out_base + out_off[i], (const float*)d_out + out_off[i], (size_t)6 * out_len[i] * 4, cudaMemcpyDeviceToHost, st));
+    // items may be sparse in the caller's output arena: one copy when they tile it, else each item's 6 * sz floats
+    TB_CUDA(ctx, copy_items_back(out_base, (const float*)d_out, out_off, b->bcpos.len, out_len, 6, nt, st));
     ctx->d2h += (size_t)omax * 4 + nt * 4;
     TB_CUDA(ctx, cudaStreamSynchronize(st));
   }
@@ -1025,7 +1185,8 @@ int tb_basecall(tb_ctx* ctx, const tb_basecall_batch* b, float sigratio, int32_t
   const size_t nt = b->ntraces;
   if (nt == 0) return TB_OK;
   if (nt > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "ntraces too large");
-  if (!b->trace.base || !b->trace.off || !b->trace.len || !b->ploc.base || !b->ploc.off || !b->ploc.len) return fail(ctx, TB_ERR_INVALID, "null arena pointer");
+  if (!b->trace.base || (!(b->mem & TB_TRACE_SET) && (!b->trace.off || !b->trace.len)) || !b->ploc.base || !b->ploc.off || !b->ploc.len)
+    return fail(ctx, TB_ERR_INVALID, "null arena pointer");
   TB_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->lanes[0].stream;
   tb::BasecallBatch P{};
@@ -1039,24 +1200,26 @@ int tb_basecall(tb_ctx* ctx, const tb_basecall_batch* b, float sigratio, int32_t
     TB_CUDA(ctx, cudaStreamSynchronize(st));
     return TB_OK;
   }
-  if (b->mem != TB_MEM_HOST) return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST or TB_MEM_DEVICE");
-  long long tmax = 0, pmax = 0, omax = 0;
-  for (size_t i = 0; i < nt; ++i) {
-    if (b->trace.len[i] < 2 || b->ploc.len[i] < 0 || b->trace.off[i] < 0 || b->ploc.off[i] < 0 || out_off[i] < 0)
-      return fail(ctx, TB_ERR_INVALID, "negative offset/length (a trace needs at least 2 samples)");
-    for (int32_t j = 0; j < b->ploc.len[i]; ++j) {
-      const int32_t v = ((const int32_t*)b->ploc.base)[b->ploc.off[i] + j];
-      if (v < 0 || v >= b->trace.len[i]) return fail(ctx, TB_ERR_INVALID, "basecall position outside the trace");
-    }
-    tmax = std::max<long long>(tmax, b->trace.off[i] + 4ll * b->trace.len[i]);
-    pmax = std::max<long long>(pmax, b->ploc.off[i] + b->ploc.len[i]);
-    omax = std::max<long long>(omax, out_off[i] + b->ploc.len[i]);
-  }
+  if ((b->mem & ~TB_TRACE_SET) != TB_MEM_HOST) return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST (optionally with TB_TRACE_SET) or TB_MEM_DEVICE");
   {
     Staged S(st);
-    void *d_tr, *d_pl, *d_toff, *d_tlen, *d_poff, *d_plen, *d_ooff, *d_olen, *d_pos, *d_pri, *d_sec, *d_con;
-    TB_CUDA(ctx, S.up(&d_tr, b->trace.base, (size_t)tmax * 4)); TB_CUDA(ctx, S.up(&d_pl, b->ploc.base, (size_t)pmax * 4));
-    TB_CUDA(ctx, S.up(&d_toff, b->trace.off, nt * 8)); TB_CUDA(ctx, S.up(&d_tlen, b->trace.len, nt * 4));
+    TraceView V;
+    if (int rc = resolve_traces(ctx, b->trace, b->mem, nt, S, V)) return rc;
+    long long pmax = 0, omax = 0;
+    for (size_t i = 0; i < nt; ++i) {
+      if (V.host_len[i] < 2 || b->ploc.len[i] < 0 || b->ploc.off[i] < 0 || out_off[i] < 0)
+        return fail(ctx, TB_ERR_INVALID, "negative offset/length (a trace needs at least 2 samples)");
+      for (int32_t j = 0; j < b->ploc.len[i]; ++j) {
+        const int32_t v = ((const int32_t*)b->ploc.base)[b->ploc.off[i] + j];
+        if (v < 0 || v >= V.host_len[i]) return fail(ctx, TB_ERR_INVALID, "basecall position outside the trace");
+      }
+      pmax = std::max<long long>(pmax, b->ploc.off[i] + b->ploc.len[i]);
+      omax = std::max<long long>(omax, out_off[i] + b->ploc.len[i]);
+    }
+    const void *d_tr = V.base, *d_toff = V.off, *d_tlen = V.len;
+    const long long tmax = (long long)(V.uploaded / 4);
+    void *d_pl, *d_poff, *d_plen, *d_ooff, *d_olen, *d_pos, *d_pri, *d_sec, *d_con;
+    TB_CUDA(ctx, S.up(&d_pl, b->ploc.base, (size_t)pmax * 4));
     TB_CUDA(ctx, S.up(&d_poff, b->ploc.off, nt * 8)); TB_CUDA(ctx, S.up(&d_plen, b->ploc.len, nt * 4));
     TB_CUDA(ctx, S.up(&d_ooff, out_off, nt * 8));
     TB_CUDA(ctx, S.alloc(&d_olen, nt * 4)); TB_CUDA(ctx, S.alloc(&d_pos, (size_t)omax * 4));
@@ -1069,13 +1232,10 @@ int tb_basecall(tb_ctx* ctx, const tb_basecall_batch* b, float sigratio, int32_t
     ctx->launches++;
     TB_CUDA(ctx, cudaMemcpyAsync(out_len, d_olen, nt * 4, cudaMemcpyDeviceToHost, st));
     TB_CUDA(ctx, cudaStreamSynchronize(st));
-    for (size_t i = 0; i < nt; ++i) {
-      const size_t o = (size_t)out_off[i], c = (size_t)out_len[i];
-      TB_CUDA(ctx, cudaMemcpyAsync(bcpos_out + o, (const int32_t*)d_pos + o, c * 4, cudaMemcpyDeviceToHost, st));
-      TB_CUDA(ctx, cudaMemcpyAsync(primary_out + o, (const char*)d_pri + o, c, cudaMemcpyDeviceToHost, st));
-      TB_CUDA(ctx, cudaMemcpyAsync(secondary_out + o, (const char*)d_sec + o, c, cudaMemcpyDeviceToHost, st));
-      TB_CUDA(ctx, cudaMemcpyAsync(consensus_out + o, (const char*)d_con + o, c, cudaMemcpyDeviceToHost, st));
-    }
+    TB_CUDA(ctx, copy_items_back(bcpos_out, (const int32_t*)d_pos, out_off, b->ploc.len, out_len, 1, nt, st));
+    TB_CUDA(ctx, copy_items_back(primary_out, (const char*)d_pri, out_off, b->ploc.len, out_len, 1, nt, st));
+    TB_CUDA(ctx, copy_items_back(secondary_out, (const char*)d_sec, out_off, b->ploc.len, out_len, 1, nt, st));
+    TB_CUDA(ctx, copy_items_back(consensus_out, (const char*)d_con, out_off, b->ploc.len, out_len, 1, nt, st));
     ctx->h2d += (size_t)tmax * 4 + (size_t)pmax * 4 + nt * 32; ctx->d2h += (size_t)omax * 7 + nt * 4;
     TB_CUDA(ctx, cudaStreamSynchronize(st));
   }
@@ -1418,10 +1578,12 @@ int tb_allelic_fraction(tb_ctx* ctx, const tb_fraction_batch* b, double* a1, dou
   const size_t nt = b->ntraces;
   if (nt == 0) return TB_OK;
   if (nt > (size_t)INT_MAX) return fail(ctx, TB_ERR_INVALID, "ntraces too large");
-  if (!b->trace.base || !b->trace.off || !b->trace.len || !b->bcpos.base || !b->bcpos.off || !b->bcpos.len || !b->primary_base || !b->secdecompose_base)
+  const bool tset = (b->mem & TB_TRACE_SET) != 0;
+  if (!b->trace.base || (!tset && (!b->trace.off || !b->trace.len)) || !b->bcpos.base || !b->bcpos.off || !b->bcpos.len || !b->primary_base || !b->secdecompose_base)
     return fail(ctx, TB_ERR_INVALID, "null pointer in fraction batch");
   if (b->trim_left < 0 || b->trim_right < 0) return fail(ctx, TB_ERR_INVALID, "negative trim");
-  if (b->mem != TB_MEM_HOST && b->mem != TB_MEM_DEVICE) return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST or TB_MEM_DEVICE");
+  if ((b->mem & ~TB_TRACE_SET) != TB_MEM_HOST && b->mem != TB_MEM_DEVICE)
+    return fail(ctx, TB_ERR_INVALID, "batch->mem must be TB_MEM_HOST (optionally with TB_TRACE_SET) or TB_MEM_DEVICE");
   TB_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->lanes[0].stream;
   // the grid values exactly as `for (double i = 0; i <= 1; i += 0.01)` produces them (src/decompose.h:581-585)
@@ -1432,11 +1594,16 @@ int tb_allelic_fraction(tb_ctx* ctx, const tb_fraction_batch* b, double* a1, dou
   const int32_t* bl = b->bcpos.len;
   const int32_t* tl = b->trace.len;
   std::vector<int32_t> hl2;
+  Staged S(st);
+  TraceView V;
   if (b->mem == TB_MEM_DEVICE) {
     hl.resize(nt); hl2.resize(nt);
     TB_CUDA(ctx, cudaMemcpy(hl.data(), b->bcpos.len, nt * 4, cudaMemcpyDeviceToHost));
     TB_CUDA(ctx, cudaMemcpy(hl2.data(), b->trace.len, nt * 4, cudaMemcpyDeviceToHost));
     bl = hl.data(); tl = hl2.data();
+  } else {
+    if (int rc = resolve_traces(ctx, b->trace, b->mem, nt, S, V)) return rc;
+    tl = V.host_len;
   }
   int maxD = 1;
   for (size_t i = 0; i < nt; ++i) {
@@ -1444,7 +1611,6 @@ int tb_allelic_fraction(tb_ctx* ctx, const tb_fraction_batch* b, double* a1, dou
     maxD = std::max(maxD, bl[i]);
   }
   if ((size_t)4 * maxD * 9 + 16 > 200 * 1024) return fail(ctx, TB_ERR_UNSUPPORTED, "more than 5600 basecalls in one trace");
-  Staged S(st);
   tb::FractionBatch F{};
   F.trim_left = b->trim_left; F.trim_right = b->trim_right; F.ngrid = (int)grid.size();
   void *d_grid, *d_status;
@@ -1456,16 +1622,16 @@ int tb_allelic_fraction(tb_ctx* ctx, const tb_fraction_batch* b, double* a1, dou
     F.bcpos_base = (const int32_t*)b->bcpos.base; F.bc_off = b->bcpos.off; F.bc_len = b->bcpos.len;
     F.pri_base = b->primary_base; F.sec_base = b->secdecompose_base; F.a1 = a1; F.a2 = a2;
   } else {
-    long long tmax = 0, bmax = 0;
+    long long bmax = 0;
     for (size_t i = 0; i < nt; ++i) {
-      if (b->trace.off[i] < 0 || b->bcpos.off[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative offset");
-      tmax = std::max<long long>(tmax, b->trace.off[i] + 4ll * tl[i]);
+      if (b->bcpos.off[i] < 0) return fail(ctx, TB_ERR_INVALID, "negative offset");
       bmax = std::max<long long>(bmax, b->bcpos.off[i] + bl[i]);
     }
-    void *d_tr, *d_bp, *d_pri, *d_sec, *d_toff, *d_tlen, *d_boff, *d_blen, *d_a1, *d_a2;
-    TB_CUDA(ctx, S.up(&d_tr, b->trace.base, (size_t)std::max(tmax, 1ll) * 4)); TB_CUDA(ctx, S.up(&d_bp, b->bcpos.base, (size_t)std::max(bmax, 1ll) * 4));
+    const long long tmax = (long long)(V.uploaded / 4);
+    const void *d_tr = V.base, *d_toff = V.off, *d_tlen = V.len;
+    void *d_bp, *d_pri, *d_sec, *d_boff, *d_blen, *d_a1, *d_a2;
+    TB_CUDA(ctx, S.up(&d_bp, b->bcpos.base, (size_t)std::max(bmax, 1ll) * 4));
     TB_CUDA(ctx, S.up(&d_pri, b->primary_base, (size_t)std::max(bmax, 1ll))); TB_CUDA(ctx, S.up(&d_sec, b->secdecompose_base, (size_t)std::max(bmax, 1ll)));
-    TB_CUDA(ctx, S.up(&d_toff, b->trace.off, nt * 8)); TB_CUDA(ctx, S.up(&d_tlen, b->trace.len, nt * 4));
     TB_CUDA(ctx, S.up(&d_boff, b->bcpos.off, nt * 8)); TB_CUDA(ctx, S.up(&d_blen, b->bcpos.len, nt * 4));
     TB_CUDA(ctx, S.alloc(&d_a1, nt * 8)); TB_CUDA(ctx, S.alloc(&d_a2, nt * 8));
     ctx->h2d += (size_t)tmax * 4 + (size_t)bmax * 6 + nt * 24;

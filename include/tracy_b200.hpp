@@ -18,15 +18,20 @@
 #define TRACY_B200_HPP
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <iostream>
+#include <exception>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -105,6 +110,33 @@ class MultiContext {
 };
 
 namespace detail {
+// The host glue of a batch of thousands of traces (packing, unpacking, per-trace breakpoints and row copies) on the host's cores:
+// fn(i) for i in [0, n), work handed out in grains; the first exception is rethrown on the calling thread.
+template <typename F>
+inline void parallel_for(std::size_t n, F&& fn, std::size_t grain = 32) {
+  unsigned hw = std::thread::hardware_concurrency();
+  const std::size_t nthr = std::min<std::size_t>(std::min<unsigned>(hw ? hw : 1u, 16u), n / (2 * grain));
+  if (nthr <= 1) { for (std::size_t i = 0; i < n; ++i) fn(i); return; }
+  std::atomic<std::size_t> next(0);
+  std::exception_ptr err;
+  std::atomic<bool> failed(false);
+  auto body = [&]() {
+    try {
+      for (;;) {
+        const std::size_t b = next.fetch_add(grain);
+        if (b >= n || failed.load()) break;
+        for (std::size_t i = b; i < std::min(n, b + grain); ++i) fn(i);
+      }
+    } catch (...) {
+      if (!failed.exchange(true)) err = std::current_exception();
+    }
+  };
+  std::vector<std::thread> th;
+  for (std::size_t t = 1; t < nthr; ++t) th.emplace_back(body);
+  body();
+  for (auto& t : th) t.join();
+  if (err) std::rethrow_exception(err);
+}
 template <typename T> inline void resize_align(Matrix<T>& a, std::size_t r, std::size_t c) { a.resize(r, c); }   // the header's own stand-in, with or without Boost around
 #if defined(TRACY_B200_WITH_BOOST) || defined(BOOST_MULTI_ARRAY_HPP) || defined(BOOST_MULTI_ARRAY_RG071801_HPP)
 template <typename TAlign> inline void resize_align(TAlign& a, std::size_t r, std::size_t c) { a.resize(boost::extents[r][c]); }   // src/align.h:200,277
@@ -177,40 +209,55 @@ inline std::vector<int32_t> gotohBatch(TCtx& g, std::vector<const TA*> const& a1
   constexpr bool sa = detail::is_string<TA>::value, sb = detail::is_string<TB>::value;
   typedef typename std::conditional<sa, char, float>::type EA;
   typedef typename std::conditional<sb, char, float>::type EB;
-  std::vector<EA> pa; std::vector<EB> pb;
+  // the arenas: every distinct object once (the orientation calls name each trace twice, the allele calls each reference twice),
+  // sized in one pass, filled by the host's cores
   std::vector<int64_t> oa(n), ob(n);
   std::vector<int32_t> la(n), lb(n);
-  int64_t stride = 16;
+  std::vector<std::size_t> ua, ub;
+  std::unordered_map<const void*, int64_t> seen_a, seen_b;
+  int64_t stride = 16, tot_a = 0, tot_b = 0;
   for (std::size_t i = 0; i < n; ++i) {
     la[i] = detail::item_len(*a1[i]); lb[i] = detail::item_len(*a2[i]);
-    oa[i] = (int64_t)pa.size(); ob[i] = (int64_t)pb.size();
-    const EA* xa = static_cast<const EA*>(detail::item_ptr(*a1[i]));
-    const EB* xb = static_cast<const EB*>(detail::item_ptr(*a2[i]));
-    pa.insert(pa.end(), xa, xa + (sa ? 1 : 6) * (std::size_t)la[i]);
-    pb.insert(pb.end(), xb, xb + (sb ? 1 : 6) * (std::size_t)lb[i]);
+    auto ia = seen_a.find(a1[i]);
+    if (ia != seen_a.end()) oa[i] = ia->second;
+    else { oa[i] = tot_a; seen_a.emplace(a1[i], tot_a); ua.push_back(i); tot_a += (sa ? 1 : 6) * (int64_t)la[i]; }
+    auto ib = seen_b.find(a2[i]);
+    if (ib != seen_b.end()) ob[i] = ib->second;
+    else { ob[i] = tot_b; seen_b.emplace(a2[i], tot_b); ub.push_back(i); tot_b += (sb ? 1 : 6) * (int64_t)lb[i]; }
     stride = std::max<int64_t>(stride, ((int64_t)la[i] + lb[i] + 15) / 16 * 16);
   }
-  if (pa.empty()) pa.resize(1);
-  if (pb.empty()) pb.resize(1);
-  std::vector<uint8_t> obuf(ops ? n * (std::size_t)stride : 0), r0buf(rows ? n * (std::size_t)stride : 0), r1buf(rows ? n * (std::size_t)stride : 0);
+  std::unique_ptr<EA[]> pa(new EA[(std::size_t)std::max<int64_t>(tot_a, 1)]);
+  std::unique_ptr<EB[]> pb(new EB[(std::size_t)std::max<int64_t>(tot_b, 1)]);
+  detail::parallel_for(ua.size(), [&](std::size_t k) {
+    const std::size_t i = ua[k];
+    const EA* x = static_cast<const EA*>(detail::item_ptr(*a1[i]));
+    std::copy(x, x + (sa ? 1 : 6) * (std::size_t)la[i], pa.get() + oa[i]);
+  });
+  detail::parallel_for(ub.size(), [&](std::size_t k) {
+    const std::size_t i = ub[k];
+    const EB* x = static_cast<const EB*>(detail::item_ptr(*a2[i]));
+    std::copy(x, x + (sb ? 1 : 6) * (std::size_t)lb[i], pb.get() + ob[i]);
+  });
+  std::unique_ptr<uint8_t[]> obuf(ops ? new uint8_t[n * (std::size_t)stride] : nullptr), r0buf(rows ? new uint8_t[n * (std::size_t)stride] : nullptr),
+      r1buf(rows ? new uint8_t[n * (std::size_t)stride] : nullptr);
   std::vector<int32_t> olen(ops || rows ? n : 0);
-  tb_batch b{{pa.data(), oa.data(), la.data()}, {pb.data(), ob.data(), lb.data()}, n, TB_MEM_HOST};
-  tb_result r{scores.data(), ops ? obuf.data() : nullptr, stride, (ops || rows) ? olen.data() : nullptr,
-              rows ? r0buf.data() : nullptr, rows ? r1buf.data() : nullptr, rows ? stride : 0, 0};
+  tb_batch b{{pa.get(), oa.data(), la.data()}, {pb.get(), ob.data(), lb.data()}, n, TB_MEM_HOST};
+  tb_result r{scores.data(), ops ? obuf.get() : nullptr, stride, (ops || rows) ? olen.data() : nullptr,
+              rows ? r0buf.get() : nullptr, rows ? r1buf.get() : nullptr, rows ? stride : 0, 0};
   constexpr int kind = detail::kind_of<TA, TB>();
   const tb_align_config acc = detail::ac_of(ac);
   const tb_score scc = detail::sc_of(sc);
   g.gotoh(kind, b, scc, acc, r);
   if (ops) {
     ops->resize(n);
-    for (std::size_t i = 0; i < n; ++i) (*ops)[i].assign(obuf.begin() + i * stride, obuf.begin() + i * stride + olen[i]);
+    detail::parallel_for(n, [&](std::size_t i) { (*ops)[i].assign(obuf.get() + i * stride, obuf.get() + i * stride + olen[i]); });
   }
   if (rows) {
     rows->resize(n);
-    for (std::size_t i = 0; i < n; ++i) {
-      (*rows)[i].first.assign(r0buf.begin() + i * stride, r0buf.begin() + i * stride + olen[i]);
-      (*rows)[i].second.assign(r1buf.begin() + i * stride, r1buf.begin() + i * stride + olen[i]);
-    }
+    detail::parallel_for(n, [&](std::size_t i) {
+      (*rows)[i].first.assign(r0buf.get() + i * stride, r0buf.get() + i * stride + olen[i]);
+      (*rows)[i].second.assign(r1buf.get() + i * stride, r1buf.get() + i * stride + olen[i]);
+    });
   }
   return scores;
 }
@@ -276,7 +323,7 @@ inline bool decomposeAllelesBatch(Context& g, TConfig const& c, std::vector<TIte
   std::vector<int64_t> roff(N), boff(N);
   std::vector<int32_t> rlen(N), blen(N), viEnd(N), aIdx(N), vIdx(N), ndel(N), nins(N);
   int32_t stride = 1;
-  for (std::size_t t = 0; t < N; ++t) {
+  detail::parallel_for(N, [&](std::size_t t) {
     auto const& al = *items[t].align;
     auto& bc = *items[t].bc;
     State& s = st[t];
@@ -297,15 +344,24 @@ inline bool decomposeAllelesBatch(Context& g, TConfig const& c, std::vector<TIte
     s.ndel = (int32_t)std::min<uint32_t>(c.maxindel, s.maxdel / 2);
     s.nins = (int32_t)std::max<uint32_t>(1, std::min<uint32_t>(c.maxindel, s.maxins / 2));
     s.viEnd = (int32_t)bc.consensus.size() - rtrim;
-    roff[t] = (int64_t)refrows.size(); rlen[t] = (int32_t)s.L;
-    for (std::size_t j = 0; j < s.L; ++j) refrows.push_back(al[1][j]);
-    boff[t] = (int64_t)pris.size(); blen[t] = (int32_t)bc.primary.size();
-    pris += bc.primary; secs += bc.secondary;
+    rlen[t] = (int32_t)s.L; blen[t] = (int32_t)bc.primary.size();
     viEnd[t] = s.viEnd; aIdx[t] = (int32_t)s.alignIndex; vIdx[t] = (int32_t)s.varIndex; ndel[t] = s.ndel; nins[t] = s.nins;
-    stride = std::max(stride, std::max(s.ndel, s.nins));
+  });
+  {
+    int64_t rtot = 0, btot = 0;
+    for (std::size_t t = 0; t < N; ++t) {
+      roff[t] = rtot; rtot += rlen[t]; boff[t] = btot; btot += blen[t];
+      stride = std::max(stride, std::max(ndel[t], nins[t]));
+    }
+    refrows.assign((std::size_t)std::max<int64_t>(rtot, 1), '-');
+    pris.assign((std::size_t)std::max<int64_t>(btot, 1), 'N'); secs.assign((std::size_t)std::max<int64_t>(btot, 1), 'N');
+    detail::parallel_for(N, [&](std::size_t t) {
+      auto const& al = *items[t].align;
+      for (std::size_t j = 0; j < st[t].L; ++j) refrows[(std::size_t)roff[t] + j] = al[1][j];
+      std::copy(items[t].bc->primary.begin(), items[t].bc->primary.end(), pris.begin() + boff[t]);
+      std::copy(items[t].bc->secondary.begin(), items[t].bc->secondary.begin() + std::min(items[t].bc->secondary.size(), (std::size_t)blen[t]), secs.begin() + boff[t]);
+    });
   }
-  if (refrows.empty()) refrows.push_back('-');
-  if (pris.empty()) { pris.push_back('N'); secs.push_back('N'); }
   std::vector<int32_t> fref(N * (std::size_t)stride, 0), fins(N * (std::size_t)stride, 0);
   {
     tb_sweep_batch b{{refrows.data(), roff.data(), rlen.data()}, {pris.data(), boff.data(), blen.data()}, secs.data(), viEnd.data(), aIdx.data(),
@@ -314,7 +370,7 @@ inline bool decomposeAllelesBatch(Context& g, TConfig const& c, std::vector<TIte
     g.check(tb_decompose_sweep(g.get(), &b, &r));
   }
   std::vector<std::size_t> need_grid;
-  for (std::size_t t = 0; t < N; ++t) {
+  detail::parallel_for(N, [&](std::size_t t) {
     State& s = st[t];
     s.fref.assign(fref.begin() + t * stride, fref.begin() + t * stride + s.ndel);
     s.fins.assign(fins.begin() + t * stride, fins.begin() + t * stride + s.nins);
@@ -337,8 +393,8 @@ inline bool decomposeAllelesBatch(Context& g, TConfig const& c, std::vector<TIte
     auto& dcp = *items[t].dcp;
     for (int32_t i = showDel - 1; i >= 0; --i) dcp.push_back(std::make_pair(-i, s.fref[i]));
     for (int32_t i = 1; i < showIns; ++i) dcp.push_back(std::make_pair(i, s.fins[i]));
-    if (none) need_grid.push_back(t);
-  }
+  });
+  for (std::size_t t = 0; t < N; ++t) if (st[t].del.empty() && st[t].ins.empty()) need_grid.push_back(t);
   // complex mutations: the ins x del grid of the traces without a candidate, one call
   std::vector<int32_t> grid;
   std::vector<int32_t> gIns(N, 0), gDel(N, 0);
@@ -363,11 +419,13 @@ inline bool decomposeAllelesBatch(Context& g, TConfig const& c, std::vector<TIte
     tb_sweep_result r{f1.data(), f2.data(), gstride, grid.data()};
     g.check(tb_decompose_sweep(g.get(), &b, &r));
   }
-  std::size_t gk = 0;
-  for (std::size_t t = 0; t < N; ++t) {
+  std::vector<std::size_t> grid_slot(N, 0);
+  for (std::size_t k = 0; k < need_grid.size(); ++k) grid_slot[need_grid[k]] = k;
+  auto finish = [&](std::size_t t) {
     State& s = st[t];
     auto const& al = *items[t].align;
     auto& bc = *items[t].bc;
+    const std::size_t gk = grid_slot[t];
     auto apply = [&](uint32_t j0, uint32_t vi0) {                          // :319-327, :349-357, :362-370
       uint32_t vi = vi0;
       for (std::size_t j = j0; j < s.L && vi < (uint32_t)s.viEnd; ++j, ++vi) detail::rephase(bc, vi, al[1][j]);
@@ -375,7 +433,6 @@ inline bool decomposeAllelesBatch(Context& g, TConfig const& c, std::vector<TIte
     if (s.del.empty() && s.ins.empty()) {
       int32_t bestIns = 0, bestDel = 0, bestFR = 1000;
       const int32_t* G = grid.data() + gk * (std::size_t)gstride * gstride;
-      ++gk;
       for (int32_t i = 0; i < gIns[t]; ++i) {
         int32_t prev = 0;
         for (int32_t d = 0; d < gDel[t]; ++d) {
@@ -398,7 +455,9 @@ inline bool decomposeAllelesBatch(Context& g, TConfig const& c, std::vector<TIte
     } else {
       apply(s.alignIndex + 1, s.varIndex + (uint32_t)*std::min_element(s.ins.begin(), s.ins.end()));
     }
-  }
+  };
+  if (log) for (std::size_t t = 0; t < N; ++t) finish(t);                  // the reference's messages, in trace order
+  else detail::parallel_for(N, finish);
   return true;
 }
 
@@ -542,14 +601,14 @@ inline void createProfileBatch(Context& g, std::vector<const TTrace*> const& tr,
     ooff[t] = ototal; ototal += 6ll * blen[t];
   }
   if (bpos.empty()) { bpos.push_back(0); pri.push_back('N'); sec.push_back('N'); }
-  std::vector<float> out((std::size_t)std::max<int64_t>(ototal, 1));
+  std::unique_ptr<float[]> out(new float[(std::size_t)std::max<int64_t>(ototal, 1)]);
   tb_profile_batch b{ta.arena, {bpos.data(), boff.data(), blen.data()}, pri.data(), sec.data(), tl.data(), trr.data(), n, ta.mem};
-  g.check(tb_create_profile(g.get(), &b, out.data(), ooff.data(), olen.data()));
-  for (std::size_t t = 0; t < n; ++t) {
+  g.check(tb_create_profile(g.get(), &b, out.get(), ooff.data(), olen.data()));
+  detail::parallel_for(n, [&](std::size_t t) {
     const std::size_t sz = (std::size_t)olen[t];
     detail::resize_align(*p[t], 6, sz);
-    if (sz) std::copy(out.begin() + ooff[t], out.begin() + ooff[t] + 6 * (int64_t)sz, p[t]->data());     // both sides are row-major [6][sz]
-  }
+    if (sz) std::copy(out.get() + ooff[t], out.get() + ooff[t] + 6 * (int64_t)sz, p[t]->data());     // both sides are row-major [6][sz]
+  });
 }
 template <typename TTrace, typename TBaseCalls, typename TProfile>
 inline void createProfile(Context& g, TTrace const& tr, TBaseCalls const& bc, TProfile& p, int32_t trimleft = 0, int32_t trimright = 0) {
@@ -1413,11 +1472,11 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
   std::vector<std::string> rev(n);
   std::vector<const TProfile*> pa(2 * n);
   std::vector<const std::string*> pb(2 * n);
-  for (std::size_t i = 0; i < n; ++i) {
+  detail::parallel_for(n, [&](std::size_t i) {
     findBreakpoint(prof[i], out[i].bp);                                                          // src/indigo.h:195-196
     rev[i] = rs[i]->refslice; reverseComplement(rev[i]);
     pa[i] = pa[n + i] = &prof[i]; pb[i] = &rs[i]->refslice; pb[n + i] = &rev[i];
-  }
+  });
   clk.lap("findBreakpoint + revcomp");
   const std::vector<int32_t> gs = gotohBatch(g, pa, pb, semiglobal, sc);                         // gsFwd / gsRev, src/indigo.h:235-236
   clk.lap("orientation scores");
@@ -1433,18 +1492,18 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
   typedef DecomposeItem<TAlign, TBaseCalls, TBreakpoint, TRefSlice, std::vector<std::pair<int32_t, int32_t> > > TItem;
   std::vector<TItem> items;
   std::vector<std::size_t> live;
-  for (std::size_t i = 0; i < n; ++i) {
+  detail::parallel_for(n, [&](std::size_t i) {
     const double seqsize = (double)prof[i].shape()[1], matchFraction = 0.35;
     const double scoreThreshold = seqsize * matchFraction * sc.match + seqsize * (1 - matchFraction) * sc.mismatch;   // src/indigo.h:303-305
     out[i].aliTrimScore = ali[i];
-    if (ali[i] <= scoreThreshold) continue;
+    if (ali[i] <= scoreThreshold) return;
     const std::size_t L = rows[i].first.size();
     detail::resize_align(out[i].align, 2, L);
     for (std::size_t j = 0; j < L; ++j) { out[i].align[0][j] = rows[i].first[j]; out[i].align[1][j] = rows[i].second[j]; }
-    if (!out[i].bp.indelshift && !findHomozygousBreakpoint(out[i].align, out[i].bp, nullptr)) continue;   // src/indigo.h:314-317
+    if (!out[i].bp.indelshift && !findHomozygousBreakpoint(out[i].align, out[i].bp, nullptr)) return;     // src/indigo.h:314-317
     out[i].ok = true;
-    live.push_back(i);
-  }
+  });
+  for (std::size_t i = 0; i < n; ++i) if (out[i].ok) live.push_back(i);
   items.resize(live.size());
   for (std::size_t k = 0; k < live.size(); ++k) {
     const std::size_t i = live[k];
@@ -1457,10 +1516,9 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
   // allelicFraction (src/indigo.h:350) reads bcPos[i + trimLeft] even where trimmedSeq() left a short read untrimmed (out of
   // bounds there): such reads keep the start value
   std::vector<const TTrace*> ftr; std::vector<const TBaseCalls*> fbc; std::vector<std::size_t> fit; std::vector<int64_t> fidx;
-  for (std::size_t i : live) {
-    generateSecondaryDecomposed(*tr[i], *bc[i]);                                                 // src/indigo.h:344
+  detail::parallel_for(live.size(), [&](std::size_t k) { generateSecondaryDecomposed(*tr[live[k]], *bc[live[k]]); });   // src/indigo.h:344
+  for (std::size_t i : live)
     if ((std::size_t)c.trimLeft + c.trimRight + 1 < bc[i]->primary.size()) { ftr.push_back(tr[i]); fbc.push_back(bc[i]); fit.push_back(i); fidx.push_back((int64_t)i); }
-  }
   const std::vector<std::pair<double, double> > fr = allelicFractionBatch(g, c, ftr, fbc, traces, traces ? &fidx : nullptr);
   for (std::size_t k = 0; k < fit.size(); ++k) out[fit[k]].a1a2 = fr[k];
   clk.lap("allelicFraction");
@@ -1468,16 +1526,16 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
   const std::size_t m = live.size();
   std::vector<std::string> pri(m), sec(m);
   std::vector<const std::string*> qa(2 * m), qb(2 * m);
-  for (std::size_t k = 0; k < m; ++k) {
+  detail::parallel_for(m, [&](std::size_t k) {
     const std::size_t i = live[k];
     pri[k] = trimmedSeq(bc[i]->primary, c.trimLeft, c.trimRight);
     sec[k] = trimmedSeq(bc[i]->secDecompose, c.trimLeft, c.trimRight);
     out[i].allele1 = *rs[i]; out[i].allele2 = *rs[i];
     qa[k] = &pri[k]; qa[m + k] = &sec[k]; qb[k] = qb[m + k] = &rs[i]->refslice;
-  }
+  });
   std::vector<std::string> ops;
   gotohBatch(g, qa, qb, semiglobal, sc, &ops);                                                   // gotoh(pri / sec, rs.refslice, ...)
-  for (std::size_t k = 0; k < 2 * m; ++k) {
+  detail::parallel_for(2 * m, [&](std::size_t k) {
     Matrix<char> al;
     const std::size_t L = ops[k].size();
     al.resize(2, L);                                                                             // only the gap pattern matters to trimReferenceSlice
@@ -1485,7 +1543,7 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
     TRefSlice& dst = k < m ? out[live[k]].allele1 : out[live[k - m]].allele2;
     trimReferenceSlice(c, al, dst);
     qb[k] = &dst.refslice;
-  }
+  });
   clk.lap("allele alignments 1");
   const std::vector<int32_t> s2 = gotohBatch(g, qa, qb, semiglobal, sc, nullptr, &rows);         // final1 / final2
   clk.lap("allele alignments 2");
@@ -1493,16 +1551,16 @@ inline void decomposeBatch(Context& g, TConfig const& c, std::vector<const TTrac
     detail::resize_align(dst, 2, r.first.size());
     for (std::size_t j = 0; j < r.first.size(); ++j) { dst[0][j] = r.first[j]; dst[1][j] = r.second[j]; }
   };
-  for (std::size_t k = 0; k < m; ++k) {
+  detail::parallel_for(m, [&](std::size_t k) {
     TOut& o = out[live[k]];
     o.a1Score = s2[k]; o.a2Score = s2[m + k];
     fill(o.final1, rows[k]); fill(o.final2, rows[m + k]);
     o.secrs.refslice = sec[k]; o.secrs.forward = true; o.secrs.pos = 0; o.secrs.chr = "Alt2";    // src/indigo.h:381-386
     qa[k] = &pri[k]; qb[k] = &sec[k];
-  }
+  });
   qa.resize(m); qb.resize(m);
   const std::vector<int32_t> s3 = gotohBatch(g, qa, qb, AlignConfig<false, false>(), sc, nullptr, &rows);   // allele 1 vs allele 2, global
-  for (std::size_t k = 0; k < m; ++k) { out[live[k]].a3Score = s3[k]; fill(out[live[k]].final3, rows[k]); }
+  detail::parallel_for(m, [&](std::size_t k) { out[live[k]].a3Score = s3[k]; fill(out[live[k]].final3, rows[k]); });
   clk.lap("allele 1 vs allele 2");
 }
 

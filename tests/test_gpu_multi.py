@@ -28,8 +28,9 @@ def test_multi_gotoh_equals_single(ctx):
         with tracy_b200.MultiContext(devs) as m:
             assert m.size == len(devs)
             got = m.gotoh("ps", profs, refs, sc, ac, rows=True)
-            for a, b in zip(want, got):
-                assert np.array_equal(a, b), devs
+            assert np.array_equal(want[0], got[0]) and np.array_equal(want[2], got[2]), devs              # scores, ops_len
+            for k in (1, 3, 4):                                                                               # ops, row0, row1: the valid prefixes
+                assert all(np.array_equal(want[k][i, : want[2][i]], got[k][i, : want[2][i]]) for i in range(n)), (devs, k)
             r = m.last_ranges
             assert r[0] == 0 and r[-1] == n and all(x <= y for x, y in zip(r, r[1:])) and all(y > x for x, y in zip(r, r[1:])), r
             assert np.array_equal(m.gotoh("ps", profs, refs, sc, ac, traceback=False)[0], want_s)
@@ -38,11 +39,11 @@ def test_multi_gotoh_equals_single(ctx):
             # profile x profile and string x string go the same way
             a = [synth.random_profile(rng, int(rng.integers(40, 300)), "msa") for _ in range(23)]
             b = [synth.random_profile(rng, int(rng.integers(40, 300)), "trace") for _ in range(23)]
-            for x, y in zip(ctx.gotoh("pp", a, b, sc, AlignConfig(True, True)), m.gotoh("pp", a, b, sc, AlignConfig(True, True))):
-                assert np.array_equal(x, y)
-            x, y = [synth.random_seq(rng, 80 + i) for i in range(9)], [synth.random_seq(rng, 120 - i) for i in range(9)]
-            for u, v in zip(ctx.gotoh("ss", x, y, sc, AlignConfig(False, False)), m.gotoh("ss", x, y, sc, AlignConfig(False, False))):
-                assert np.array_equal(u, v)
+            for kind, x, y, cfg in (("pp", a, b, AlignConfig(True, True)),
+                                    ("ss", [synth.random_seq(rng, 80 + i) for i in range(9)], [synth.random_seq(rng, 120 - i) for i in range(9)], AlignConfig(False, False))):
+                w, g = ctx.gotoh(kind, x, y, sc, cfg), m.gotoh(kind, x, y, sc, cfg)
+                assert np.array_equal(w[0], g[0]) and np.array_equal(w[2], g[2]), (devs, kind)
+                assert all(np.array_equal(w[1][i, : w[2][i]], g[1][i, : w[2][i]]) for i in range(len(x))), (devs, kind)
 
 
 def test_multi_broadcast_index_and_anchor(ctx):

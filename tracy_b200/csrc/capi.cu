@@ -1644,7 +1644,7 @@ int tb_allelic_fraction(tb_ctx* ctx, const tb_fraction_batch* b, double* a1, dou
   TB_CUDA(ctx, tb::launch_allelic_fraction(F, (int)nt, maxD, st));
   ctx->launches++;
   TB_CUDA(ctx, cudaEventRecord(L.k1, st));
-  if (b->mem == TB_MEM_HOST) {
+  if (b->mem != TB_MEM_DEVICE) {
     TB_CUDA(ctx, cudaMemcpyAsync(a1, F.a1, nt * 8, cudaMemcpyDeviceToHost, st));
     TB_CUDA(ctx, cudaMemcpyAsync(a2, F.a2, nt * 8, cudaMemcpyDeviceToHost, st));
     ctx->d2h += nt * 16;

@@ -91,10 +91,61 @@ __global__ void __launch_bounds__(256) allelic_fraction_kernel(const FractionBat
     return;
   }
   if (threadIdx.x == 0) s_best = (unsigned long long)__double_as_longlong(start);
+  // ---- a filter that never changes the answer ----
+  // Every cell's prediction is one of i, j, k, l or 0, so the SSE of a grid point is a sum of four one-variable functions plus a
+  // constant: s_tab[q][v] = sum over the cells of class q of (v/100 - tp)^2. Their sum is the reference's SSE in another summation
+  // order (all terms >= 0: the two agree to ~1e-12 relative), so a point whose table sum exceeds the best COMPLETED chain sum by
+  // more than 1e-9 relative (+ 1e-12 absolute, for perfect fits) has a strictly larger chain sum as well: it can neither win nor tie and is skipped unevaluated. What
+  // is left (the few points around the optimum) goes through the reference's own chain of separately rounded operations as before.
+  // A first sweep over the tables finds the point with the smallest table sum; its chain sum seeds the running minimum.
+  __shared__ double s_tab[4][kFracGrid];
+  __shared__ double s_f0;
+  for (int e = threadIdx.x; e <= 4 * kFracGrid; e += blockDim.x) {
+    const int q = e / kFracGrid, v = e % kFracGrid;
+    const double val = e == 4 * kFracGrid ? 0.0 : (q < 3 && v < F.ngrid) ? F.grid[v] : (double)v / 100.0;
+    const unsigned want = e == 4 * kFracGrid ? 0u : (unsigned)(q + 1);
+    double acc = 0.0;
+    for (int m = 0; m < 4; ++m)
+      for (int n = 0; n < D; ++n)
+        if (cls[(size_t)m * maxD + n] == want) { const double d = val - tp[(size_t)m * maxD + n]; acc += d * d; }
+    if (e == 4 * kFracGrid) s_f0 = acc; else s_tab[q][v] = acc;
+  }
   __syncthreads();
+  const int total = kFracGrid * kFracGrid * kFracGrid;
+  auto table_sum = [&](int ii, int jj, int kk) { return s_f0 + s_tab[0][ii] + s_tab[1][jj] + s_tab[2][kk] + s_tab[3][max(0, min(100, 100 - ii - jj - kk))]; };
+  {
+    double best_a = 1e300;
+    int best_c = -1;
+    for (int c = threadIdx.x; c < total; c += blockDim.x) {
+      const int ii = c / (kFracGrid * kFracGrid), jj = (c / kFracGrid) % kFracGrid, kk = c % kFracGrid;
+      if (ii >= F.ngrid || jj >= F.ngrid || kk >= F.ngrid) continue;
+      const double ij = __dadd_rn(F.grid[ii], F.grid[jj]);
+      if (!(ij <= 1.0)) continue;
+      if (!(__dadd_rn(ij, F.grid[kk]) <= 1.0)) continue;
+      const double a = table_sum(ii, jj, kk);
+      if (a < best_a) { best_a = a; best_c = c; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      const double oa = __shfl_down_sync(0xffffffffu, best_a, d);
+      const int oc = __shfl_down_sync(0xffffffffu, best_c, d);
+      if (oa < best_a) { best_a = oa; best_c = oc; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best_a; s_idx[threadIdx.x >> 5] = best_c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) if (s_val[w] < best_a) { best_a = s_val[w]; best_c = s_idx[w]; }
+      if (best_c >= 0) {
+        const double gi = F.grid[best_c / (kFracGrid * kFracGrid)], gj = F.grid[(best_c / kFracGrid) % kFracGrid], gk = F.grid[best_c % kFracGrid];
+        const double gl = __dsub_rn(1.0, __dadd_rn(__dadd_rn(gi, gj), gk));
+        bool done;
+        const double seed = sse_of(gi, gj, gk, gl, ~0ull, &done);           // a completed chain sum of an admissible point
+        if (seed == seed) atomicMin(&s_best, (unsigned long long)__double_as_longlong(seed));
+      }
+    }
+    __syncthreads();
+  }
   double my_sse = start;
   int my_idx = INT_MAX;                                                      // INT_MAX: the start value itself
-  const int total = kFracGrid * kFracGrid * kFracGrid;
   for (int c = threadIdx.x; c < total; c += blockDim.x) {
     const int ii = c / (kFracGrid * kFracGrid), jj = (c / kFracGrid) % kFracGrid, kk = c % kFracGrid;
     if (ii >= F.ngrid || jj >= F.ngrid || kk >= F.ngrid) continue;
@@ -105,6 +156,7 @@ __global__ void __launch_bounds__(256) allelic_fraction_kernel(const FractionBat
     if (!(ijk <= 1.0)) continue;
     const double gl = __dsub_rn(1.0, ijk);
     const unsigned long long bound = *(volatile unsigned long long*)&s_best;
+    if (table_sum(ii, jj, kk) * (1.0 - 1e-9) - 1e-12 > __longlong_as_double((long long)bound)) continue;   // strictly worse than a completed point
     const double sse = sse_of(gi, gj, gk, gl, bound, &full);
     if (!full) continue;
     if (sse < my_sse) { my_sse = sse; my_idx = c; }                          // c ascends per thread: ties keep the earlier point

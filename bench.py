@@ -334,6 +334,7 @@ def run_b200(args, rank, world, local_rank):
 
     # spot parity inside the bench: device leg and host leg agree, and a few pairs match the CPU oracle
     assert torch.equal(d_scores.cpu(), h_scores), "device-resident and host-buffer legs disagree"
+    assert torch.equal(d_len.cpu(), h_len), "device-resident and host-buffer legs disagree on the traceback lengths"
     chk = {"pairs_checked_vs_oracle": 0}
     if rank == 0:
         from oracle import loader

@@ -199,6 +199,37 @@ def test_host_pipeline_chunks_lanes_and_stage2(ctx, oracle_port, monkeypatch):
         assert int(s0[i]) == ws and bytes(o0[i, : l0[i]]) == wops, i
 
 
+def test_host_pipeline_ramp_schedule(ctx, oracle_port, monkeypatch):
+    """A batch large enough for the full chunk schedule of the TB_MEM_HOST pipeline (ramp up 1-2-4 waves, steady chunks in whole waves,
+    ramp down 4-2-1 waves with the remainder, inputs copied one chunk at a time): same scores, traceback lengths and rows as the plain
+    schedule (TRACY_B200_NO_RAMPDOWN) and as fixed small chunks; pairs at the chunk boundaries against the oracle."""
+    N, m, n = 60000, 300, 900
+    base_p, base_w = synth.align_batch(2048, m, n, seed=31)
+    idx = np.arange(N) % 2048
+    idx[1::3] = (idx[1::3] * 7 + 3) % 2048                                 # neighbours differ
+    prof, win = np.ascontiguousarray(base_p[idx]), np.ascontiguousarray(base_w[idx])
+    a1, a2 = tracy_b200.uniform_profiles(prof), tracy_b200.uniform_seqs(win)
+    sc, ac = DnaScore(3, -5, -10, -4), AlignConfig(True, False)
+    for k in ("TRACY_B200_CHUNK", "TRACY_B200_LANES", "TRACY_B200_NO_RAMPDOWN"):
+        monkeypatch.delenv(k, raising=False)
+    s0, o0, l0, r0, r1 = ctx.gotoh("ps", a1, a2, sc, ac, rows=True)
+    assert ctx.last_packed_pairs() == N
+    monkeypatch.setenv("TRACY_B200_NO_RAMPDOWN", "1")
+    s1, o1, l1, q0, q1 = ctx.gotoh("ps", a1, a2, sc, ac, rows=True)
+    monkeypatch.delenv("TRACY_B200_NO_RAMPDOWN")
+    monkeypatch.setenv("TRACY_B200_CHUNK", "7001")
+    s2, o2, l2 = ctx.gotoh("ps", a1, a2, sc, ac)
+    monkeypatch.delenv("TRACY_B200_CHUNK")
+    assert np.array_equal(s0, s1) and np.array_equal(l0, l1) and np.array_equal(s0, s2) and np.array_equal(l0, l2)
+    mask = np.arange(o0.shape[1])[None, :] < l0[:, None]
+    assert np.array_equal(o0 * mask, o1 * mask) and np.array_equal(o0 * mask, o2[:, : o0.shape[1]] * mask)
+    assert np.array_equal(r0 * mask, q0 * mask) and np.array_equal(r1 * mask, q1 * mask)
+    wave = 148 * 12
+    edges = sorted({0, N - 1, wave - 1, wave, 3 * wave - 1, 3 * wave, 7 * wave, N - wave, N - 3 * wave - 1, N - 7 * wave, N // 2, N - 500})
+    for i in edges:
+        ws, wops = oracle_port.gotoh_ps(prof[i], bytes(win[i]), 1, 0, (3, -5, -10, -4))
+        assert int(s0[i]) == ws and bytes(o0[i, : l0[i]]) == wops, i
+
 def test_string_pairs_through_packed_kernel(ctx, oracle_port):
     """tb_gotoh_ss: upper-case ACGTN pairs run on the packed kernel (a1's characters as one-hot profile columns); lower case,
     IUPAC codes and gaps on either side are byte-compared by the general string kernel. Same results as the reference's

@@ -92,6 +92,7 @@ struct Lane {   // one in-flight chunk of a TB_MEM_HOST batch
   cudaStream_t stream = nullptr;
   cudaEvent_t c0 = nullptr, k0 = nullptr, k1 = nullptr, k2 = nullptr;   // c0: start of a device-mode call; k*: kernel brackets
   cudaEvent_t h0 = nullptr, d1 = nullptr;                               // host-mode chunk: before its H2D, after its D2H (TRACY_B200_TRACE)
+  cudaEvent_t in_done = nullptr;                                        // host-mode chunk: its inputs have arrived (the next chunk's copy waits for it)
   DevBuf a, b, meta_d, scores, ops, ops_len, status, counter;
   DevBuf ptr, rowbuf, opsrev;
   DevBuf row0, row1, opk;                  // host-mode outputs made by post_ops.cu: gapped rows, 2-bit packed ops
@@ -522,7 +523,13 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   // A chunk is a whole number of waves of the persistent grid (pairs of one batch cost about the same, so a
   // chunk then ends without a tail of idle warp slots), about an eighth of the batch, inputs <= 768 MiB.
   const size_t wave = std::max<size_t>(plan.slots, 1);
-  size_t chunk = std::max<size_t>(2 * wave, std::min<size_t>(16384, (np + 7) / 8));
+  // steady chunks of about a sixteenth of the batch (3 waves at 100 k pairs): measured best of 3 .. 21 waves once the ramps are in
+  // (profiles/r02_e2e_chunk_probe.json: 89.3 ms against 91.4 - 91.9 ms; kernel boundaries cost nothing -- the next kernel's blocks
+  // move into the slots the previous kernel's blocks leave -- and small chunks keep the copies short)
+  size_t chunk_target = 7104, chunk_parts = 16;
+  if (const char* ce = getenv("TRACY_B200_CHUNK_TARGET")) { const long v = atol(ce); if (v > 0) chunk_target = (size_t)v; }
+  if (const char* ce = getenv("TRACY_B200_CHUNK_PARTS")) { const long v = atol(ce); if (v > 0) chunk_parts = (size_t)v; }
+  size_t chunk = std::max<size_t>(2 * wave, std::min<size_t>(chunk_target, (np + chunk_parts - 1) / chunk_parts));
   chunk = std::max<size_t>(1, chunk / wave) * wave;
   {
     const double per_pair = (double)item_elems_a(mode, all.maxm) * elem_size_a(mode) + (double)item_elems_b(mode, all.maxn) * elem_size_b(mode) +
@@ -596,12 +603,32 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   };
   // The chunk pipeline as one unit: on ANY error the lanes still hold kernels and D2H copies into the caller's buffers, so they
   // are drained before the error is returned (the caller may free those buffers right away).
+  // The chunk schedule. Ramp up: 1, 2, 4 waves, so the first kernel starts after a sub-millisecond copy. Ramp down: the last
+  // chunks are 4, 2, 1 waves, so what is left after the last kernel is the device-to-host copy of ONE wave's results. The steady
+  // chunks in between share what remains evenly in whole waves (no lone remainder chunk running on a mostly idle GPU).
+  std::vector<size_t> sched;
+  if (ramp && np >= 30 * wave && getenv("TRACY_B200_NO_RAMPDOWN") == nullptr) {
+    const size_t head[3] = {wave, 2 * wave, 4 * wave}, tail_w[3] = {4 * wave, 2 * wave, wave};
+    const size_t rest = np - 7 * wave;                    // pairs left for the steady chunks and the ramp down
+    const size_t tail_sum = 7 * wave + (rest % wave);    // the ramp down also takes the part of a wave at the very end
+    const size_t mid = rest - tail_sum;                   // a whole number of waves
+    const size_t nmid = std::max<size_t>(1, (mid + chunk - 1) / chunk);
+    for (size_t h : head) sched.push_back(h);
+    for (size_t k = 0; k < nmid; ++k) {                   // spread the middle waves over nmid chunks
+      const size_t waves = mid / wave, w = waves / nmid + (k < waves % nmid ? 1 : 0);
+      if (w) sched.push_back(w * wave);
+    }
+    sched.push_back(tail_w[0]); sched.push_back(tail_w[1]); sched.push_back(tail_w[2] + rest % wave);
+  } else {
+    for (size_t ci = 0, p0 = 0; p0 < np; ++ci) { const size_t cn = std::min(ramp && ci < 3 ? (wave << ci) : chunk, np - p0); sched.push_back(cn); p0 += cn; }
+  }
   auto pipeline = [&]() -> int {
   size_t nchunks = 0;
+  cudaEvent_t prev_in = nullptr;                          // inputs of the previous chunk have arrived
   for (size_t ci = 0, p0 = 0; p0 < np; ++ci, ++nchunks) {
     Lane& L = ctx->lanes[ci % nlanes];
     if (int rc = retire(L)) return rc;                    // chunk ci-nlanes is done; its buffers are free
-    const size_t cn = std::min(ramp && ci < 3 ? (wave << ci) : chunk, np - p0);
+    const size_t cn = std::min(sched[std::min(ci, sched.size() - 1)], np - p0);
     // extents of this chunk inside the caller's arenas
     long long amin = LLONG_MAX, amax = LLONG_MIN, bmin = LLONG_MAX, bmax = LLONG_MIN;
     for (size_t i = p0; i < p0 + cn; ++i) {
@@ -631,6 +658,9 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     for (size_t i = 0; i < cn; ++i) { hoff[i] = batch->a1.off[p0 + i] - amin; hoff[cn + i] = batch->a2.off[p0 + i] - bmin; }
     std::memcpy(hlen, l1 + p0, cn * 4); std::memcpy(hlen + cn, l2 + p0, cn * 4);
 
+    // one chunk's inputs at a time on the PCIe link: copies issued together on different streams share the bandwidth, which made the
+    // FIRST kernel wait for a third of three copies (5 ms) instead of for its own 35 MB (0.7 ms)
+    if (prev_in) TB_CUDA(ctx, cudaStreamWaitEvent(L.stream, prev_in, 0));
     if (trace) TB_CUDA(ctx, cudaEventRecord(L.h0, L.stream));
     if (a_rows5) {
       // rows 0..4 enter _score; row 5 ('-') only decides consensus characters (wanted with the gapped rows). Trace profiles made
@@ -650,6 +680,8 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     }
     TB_CUDA(ctx, cudaMemcpyAsync(L.b.p, (const char*)batch->a2.base + (size_t)bmin * esb, bbytes, cudaMemcpyHostToDevice, L.stream));
     TB_CUDA(ctx, cudaMemcpyAsync(L.meta_d.p, hoff, cn * 24, cudaMemcpyHostToDevice, L.stream));
+    TB_CUDA(ctx, cudaEventRecord(L.in_done, L.stream));
+    prev_in = L.in_done;
     ctx->h2d += bbytes + cn * 24;
 
     tb::GotohBatch C = B;
@@ -731,7 +763,8 @@ int tb_ctx_create(tb_ctx** out, int device) {
     Lane& L = c->lanes[i];
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&L.c0) != cudaSuccess ||
         cudaEventCreate(&L.k0) != cudaSuccess || cudaEventCreate(&L.h0) != cudaSuccess || cudaEventCreate(&L.d1) != cudaSuccess ||
-        cudaEventCreate(&L.k1) != cudaSuccess || cudaEventCreate(&L.k2) != cudaSuccess) {
+        cudaEventCreate(&L.k1) != cudaSuccess || cudaEventCreate(&L.k2) != cudaSuccess ||
+        cudaEventCreateWithFlags(&L.in_done, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
       tb_ctx_destroy(c);
       return TB_ERR_CUDA;
@@ -758,6 +791,7 @@ void tb_ctx_destroy(tb_ctx* c) {
     if (L.k2) cudaEventDestroy(L.k2);
     if (L.h0) cudaEventDestroy(L.h0);
     if (L.d1) cudaEventDestroy(L.d1);
+    if (L.in_done) cudaEventDestroy(L.in_done);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   delete c;

@@ -195,8 +195,28 @@ __device__ __forceinline__ char out_onehot_char(unsigned char ch) {             
   const unsigned char u = ch & 0xDFu;
   return u == 'C' ? 'C' : u == 'G' ? 'G' : u == 'T' ? 'T' : (u == 'N' || ch == '-') ? 'N' : 'A';   // 'A', and the all-zero column: index 0 wins
 }
+// the six loads of a column issued together (out_cons_char takes them one after the other)
+__device__ __forceinline__ char out_cons_char6(const float* p, int len, int pos) {
+  float v[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) v[k] = p[(size_t)k * len + pos];
+  int best = 0;
+  float bv = v[0];
+#pragma unroll
+  for (int k = 1; k < 6; ++k) if (v[k] > bv) { bv = v[k]; best = k; }
+  return best < 4 ? "ACGT"[best] : 'N';
+}
 static __device__ __noinline__ void emit_pair_outputs_impl(const void* a, int m, const void* b, int n, int mode, uint8_t* r0, uint8_t* r1, uint8_t* pk,
-                                                          const uint8_t* __restrict__ ops, int L, int lane) {
+                                                          const uint8_t* __restrict__ ops, int L, int lane, uint8_t* scratch) {
+  // The consensus characters of a profile side are made ONCE per pair, position by position with coalesced loads, into the pair's
+  // (now free) reversed-ops scratch; the op loop below then reads one byte per lane instead of six strided floats per lane behind
+  // each other -- the loop is a chain of dependent loads, and a warp sitting in it is a warp missing from the fill.
+  const uint8_t* ca = nullptr; const uint8_t* cb = nullptr;
+  if (r0 && scratch) {
+    if (mode != kModeSS) { for (int r = lane; r < m; r += 32) scratch[r] = (uint8_t)out_cons_char6((const float*)a, m, r); ca = scratch; }
+    if (mode == kModePP) { for (int c = lane; c < n; c += 32) scratch[m + c] = (uint8_t)out_cons_char6((const float*)b, n, c); cb = scratch + m; }
+    __syncwarp();
+  }
   // 32 ops per iteration, one per lane; deliberately small and rolled: the warps of an SM are in different phases (fill, walk,
   // this), and every KB of code here pushes the fill's unrolled step loop out of the 32 KB instruction cache they share --
   // wider variants (4 and 16 ops per lane, loads batched) ran the whole kernel 2 and 6 ms slower per 100 k pairs.
@@ -214,8 +234,8 @@ static __device__ __noinline__ void emit_pair_outputs_impl(const void* a, int m,
       const unsigned lt = (1u << lane) - 1u;
       const int r = rbase + __popc(mr & lt), c = cbase + __popc(mc & lt);
       char x = '-', y = '-';
-      if (adv_r && r < m) x = mode == kModeSS ? ((const char*)a)[r] : out_cons_char((const float*)a, m, r);
-      if (adv_c && c < n) y = mode == kModePP ? out_cons_char((const float*)b, n, c) : mode == kModeSS ? ((const char*)b)[c] : out_onehot_char(((const unsigned char*)b)[c]);
+      if (adv_r && r < m) x = ca ? (char)ca[r] : mode == kModeSS ? ((const char*)a)[r] : out_cons_char((const float*)a, m, r);
+      if (adv_c && c < n) y = cb ? (char)cb[c] : mode == kModePP ? out_cons_char((const float*)b, n, c) : mode == kModeSS ? ((const char*)b)[c] : out_onehot_char(((const unsigned char*)b)[c]);
       if (in) { r0[j] = (uint8_t)x; r1[j] = (uint8_t)y; }
     }
     rbase += __popc(mr); cbase += __popc(mc);
@@ -231,11 +251,12 @@ static __device__ __noinline__ void emit_pair_outputs_impl(const void* a, int m,
     }
   }
 }
-__device__ __forceinline__ void emit_pair_outputs(const GotohBatch& B, int pi, const uint8_t* ops, int L, int lane) {
+// scratch: m + n free bytes of the warp's own (the slot of the reversed ops string once it has been copied out), or nullptr
+__device__ __forceinline__ void emit_pair_outputs(const GotohBatch& B, int pi, const uint8_t* ops, int L, int lane, uint8_t* scratch = nullptr) {
   const void* const a = B.mode == kModeSS ? (const void*)((const char*)B.a_base + B.a_off[pi]) : (const void*)((const float*)B.a_base + B.a_off[pi]);
   const void* const b = B.mode == kModePP ? (const void*)((const float*)B.b_base + B.b_off[pi]) : (const void*)((const char*)B.b_base + B.b_off[pi]);
   emit_pair_outputs_impl(a, B.a_len[pi], b, B.b_len[pi], B.mode, B.row0 ? B.row0 + (long long)pi * B.rows_stride : nullptr,
-                         B.row0 ? B.row1 + (long long)pi * B.rows_stride : nullptr, B.opk ? B.opk + (long long)pi * B.opk_stride : nullptr, ops, L, lane);
+                         B.row0 ? B.row1 + (long long)pi * B.rows_stride : nullptr, B.opk ? B.opk + (long long)pi * B.opk_stride : nullptr, ops, L, lane, scratch);
 }
 
 // ---- pointer scratch layout -------------------------------------------------------------------------------

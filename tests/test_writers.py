@@ -236,3 +236,55 @@ def test_trace_fasta_fastq(oracle_ref):
         for i, (ot, tl, tr, ns, bcpos, qual, pri, sec, con) in enumerate(_fastx_cases(8, 300)):
             assert writers.trace_fasta(ot, tl, tr, pri, sec, con).encode("latin-1") == oracle_ref.trace_fastx(0, ot, tl, tr, ns, bcpos, qual, pri, sec, con), i
             assert writers.trace_fastq(ot, tl, tr, ns, bcpos, qual, pri, sec, con).encode("latin-1") == oracle_ref.trace_fastx(1, ot, tl, tr, ns, bcpos, qual, pri, sec, con), i
+
+
+def test_native_writers_equal_python_writers(tmp_path):
+    """csrc/writers.cu (tb_write_*) against the Python writers, which are pinned on the reference: random traces and alignments incl.
+    leading / trailing / inner gap runs, a single basecall, basecall positions that never come up, all four plotAlignment keys."""
+    import ctypes as C
+
+    from tracy_b200 import capi
+    L = capi.lib()
+    rng = np.random.default_rng(77)
+    for it in range(40):
+        nbc = 1 if it == 0 else int(rng.integers(2, 120))
+        ns = 12 * nbc + int(rng.integers(5, 40))
+        acgt = rng.integers(-5, 3000, size=(4, ns)).astype(np.int32)
+        bcpos = np.sort(rng.choice(np.arange(2, ns - 1), size=nbc, replace=False)).astype(np.int32)
+        if it % 7 == 3 and nbc > 4:
+            bcpos[2] = bcpos[1]                                    # a position that is never met by the forward walk
+        qual = rng.integers(0, 61, nbc).astype(np.uint8)
+        pri = bytes(rng.choice(list(b"ACGTN"), nbc).astype(np.uint8))
+        sec = bytes(rng.choice(list(b"ACGTRYKMSWN"), nbc).astype(np.uint8))
+        con = bytes(rng.choice(list(b"ACGTN"), nbc).astype(np.uint8))
+        # an alignment of the nbc trace bases against a reference: row0 carries exactly nbc non-gap characters
+        row0, row1, k = bytearray(), bytearray(), 0
+        for _ in range(int(rng.integers(0, 4))):
+            row0 += b"-"; row1 += bytes([b"ACGT"[int(rng.integers(0, 4))]])
+        while k < nbc:
+            u = rng.random()
+            if u < 0.08:
+                g = int(rng.integers(1, 5)); row0 += b"-" * g; row1 += bytes(rng.choice(list(b"ACGT"), g).astype(np.uint8))
+            elif u < 0.14:
+                row0 += bytes([pri[k]]); row1 += b"-"; k += 1
+            else:
+                row0 += bytes([pri[k]]); row1 += bytes([pri[k] if rng.random() < 0.9 else b"ACGT"[int(rng.integers(0, 4))]]); k += 1
+        for _ in range(int(rng.integers(0, 4))):
+            row0 += b"-"; row1 += b"A"
+        row0, row1 = bytes(row0), bytes(row1)
+        tl, trr = int(rng.integers(0, nbc + 3)), int(rng.integers(0, nbc + 3))
+        pos, fwd, score, ll = int(rng.integers(0, 10 ** 6)), bool(it % 2), int(rng.integers(-500, 3000)), [60, 80, 7][it % 3]
+        reflen = len(row1) - row1.count(b"-")
+        prefix = str(tmp_path / f"n{it}")
+        writers.write_align_files(prefix, "trace%d" % it, acgt, bcpos, qual, pri, sec, con, tl, trr, row0, row1, "chr%d" % it, pos, reflen, fwd, score, ll)
+        want = writers.align_files("trace%d" % it, acgt, bcpos, qual, pri, sec, con, tl, trr, row0, row1, b"chr%d" % it, pos, reflen, fwd, score, ll)
+        for sfx, text in want.items():
+            with open(prefix + sfx, "rb") as fh:
+                assert fh.read() == text.encode("latin-1"), (it, sfx)
+        for key in (1, 2, 3):
+            p = str(tmp_path / f"n{it}.k{key}")
+            assert L.tb_write_plot_alignment(p.encode(), row0, row1, len(row0), b"chrX", pos, reflen, int(fwd), score, key, 0.37, 0.6300000001, ll) == 0
+            with open(p, "rb") as fh:
+                assert fh.read() == writers.plot_alignment(row0, row1, b"chrX", pos, reflen, fwd, score, key, (0.37, 0.6300000001), ll).encode("latin-1"), (it, key)
+    # invalid arguments are refused, nothing is written
+    assert L.tb_write_trace_txt(str(tmp_path / "x").encode(), None, 0, 0) == 1

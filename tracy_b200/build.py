@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtracy_b200.so")
-SOURCES = ["capi.cu", "gotoh_general.cu", "gotoh_packed.cu", "gotoh_pp.cu", "sweep.cu", "profile_ops.cu", "anchor.cu", "fraction.cu", "trace_io.cu", "multi.cu"]
+SOURCES = ["capi.cu", "gotoh_general.cu", "gotoh_packed.cu", "gotoh_pp.cu", "sweep.cu", "profile_ops.cu", "anchor.cu", "fraction.cu", "trace_io.cu", "multi.cu", "writers.cu", "trimq.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "tracy_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

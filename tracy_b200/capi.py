@@ -20,6 +20,7 @@ SYMBOLS = [
     "tb_trace_set_create", "tb_trace_set_destroy", "tb_trace_set_info",
     "tb_multi_create", "tb_multi_destroy", "tb_multi_size", "tb_multi_ctx", "tb_multi_last_error", "tb_multi_partition", "tb_multi_gotoh",
     "tb_multi_index_build", "tb_multi_anchor",
+    "tb_write_trace_txt", "tb_write_align_fasta", "tb_write_plot_alignment", "tb_write_trace_align_json", "tb_write_align_files", "tb_trace_quality",
 ]
 
 
@@ -61,6 +62,11 @@ class ProfileBatch(C.Structure):
 
 class BasecallBatch(C.Structure):
     _fields_ = [("trace", Arena), ("ploc", Arena), ("ntraces", C.c_size_t), ("mem", C.c_int32)]
+
+
+class TraceView(C.Structure):
+    _fields_ = [("acgt", C.c_void_p), ("nsamples", C.c_int32), ("bcpos", C.c_void_p), ("qual", C.c_void_p), ("primary", C.c_void_p),
+                ("secondary", C.c_void_p), ("consensus", C.c_void_p), ("nbc", C.c_int32)]
 
 
 class AnchorConfig(C.Structure):
@@ -107,6 +113,14 @@ def lib():
     L.tb_host_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
     L.tb_host_free.argtypes = [vp, vp]
     L.tb_ctx_set_scratch_limit.argtypes = [vp, C.c_size_t]
+    L.tb_trace_quality.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_float, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.tb_write_trace_txt.argtypes = [C.c_char_p, C.POINTER(TraceView), C.c_int32, C.c_int32]
+    L.tb_write_align_files.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(TraceView), C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p,
+                                       C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    L.tb_write_plot_alignment.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_double, C.c_double, C.c_int32]
+    L.tb_write_trace_align_json.argtypes = [C.c_char_p, C.POINTER(TraceView), C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_uint32, C.c_int32]
+    L.tb_write_align_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
     L.tb_ctx_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.tb_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.tb_ctx_last_call_ms.argtypes = [vp, C.POINTER(C.c_float)]

@@ -1,0 +1,253 @@
+// The output files of `tracy align` for one trace, formatted and written by native code (host only, no kernel): P.abif
+// (traceTxtOut, reference src/abif.h:512-534), P.align.fa (src/sage.h:326-339), P.txt (plotAlignment, src/fmindex.h:329-420) and
+// P.json (alignmentTracePadding + assemblyTrace + traceAlignJsonOut, src/json.h:120-217, 383-479). ~390 KB of text per trace: as
+// Python string code this was what bounded the files-in -> files-out pipeline (46 traces/s behind GPU stages that take milliseconds);
+// here a writer thread formats one trace into one buffer and hands it to fwrite without holding any interpreter lock, so the
+// writers of a batch run on as many host cores as the caller gives them, underneath the GPU stages of the next chunk.
+// Same bytes as tracy_b200/writers.py (the Python forms stay as the readable statement; tests compare both with the reference).
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tracy_b200.h"
+
+namespace {
+
+struct Buf {
+  std::string s;
+  void ch(char c) { s.push_back(c); }
+  void str(const char* p) { s.append(p); }
+  void str(const char* p, size_t n) { s.append(p, n); }
+  void num(long long v) {
+    char tmp[24];
+    int k = 0;
+    bool neg = v < 0;
+    unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (neg) s.push_back('-');
+    while (k) s.push_back(tmp[--k]);
+  }
+  void padded(long long v, int width) {              // std::setw(width) << v
+    char tmp[32];
+    const int n = snprintf(tmp, sizeof tmp, "%*lld", width, v);
+    s.append(tmp, (size_t)n);
+  }
+};
+
+int flush_to(const char* path, const Buf& b) {
+  FILE* f = fopen(path, "wb");
+  if (!f) return TB_ERR_INVALID;
+  const size_t w = fwrite(b.s.data(), 1, b.s.size(), f);
+  const int rc = fclose(f);
+  return (w == b.s.size() && rc == 0) ? TB_OK : TB_ERR_INVALID;
+}
+
+bool view_ok(const tb_trace_view* t) {
+  return t && t->nsamples >= 0 && t->nbc > 0 && t->acgt && t->bcpos && t->qual && t->primary && t->secondary && t->consensus;
+}
+
+// the walk all of the reference's per-sample writers share: sample i carries basecall k when it equals the NEXT expected position
+template <typename F>
+void for_called(int32_t nsamples, const int32_t* bcpos, int32_t nbc, F&& f) {
+  int32_t k = 0, idx = bcpos[0];
+  for (int32_t i = 0; i < nsamples; ++i)
+    if (idx == i) {
+      f(i, k);
+      if (k < nbc - 1) idx = bcpos[++k];
+    }
+}
+
+void trace_txt(Buf& o, const tb_trace_view& t, int32_t trim_left, int32_t trim_right) {
+  const int32_t ns = t.nsamples;
+  const uint32_t rtr = (uint32_t)trim_right < (uint32_t)t.nbc ? (uint32_t)t.nbc - (uint32_t)trim_right : 0u;
+  o.s.reserve((size_t)ns * 40 + 128);
+  o.str("pos\tpeakA\tpeakC\tpeakG\tpeakT\tbasenum\tprimary\tsecondary\tconsensus\tqual\ttrim\n");
+  int32_t k = 0, idx = t.bcpos[0];
+  for (int32_t i = 0; i < ns; ++i) {
+    o.num(i + 1); o.ch('\t');
+    for (int c = 0; c < 4; ++c) { o.num(t.acgt[(size_t)c * ns + i]); o.ch('\t'); }
+    if (idx == i) {
+      o.num(k + 1); o.ch('\t');
+      o.ch(t.primary[k]); o.ch('\t'); o.ch(t.secondary[k]); o.ch('\t'); o.ch(t.consensus[k]); o.ch('\t'); o.num(t.qual[k]); o.ch('\t');
+      o.str(((uint32_t)k < (uint32_t)trim_left || (uint32_t)k >= rtr) ? "Y\n" : "N\n");
+      if (k < t.nbc - 1) idx = t.bcpos[++k];
+    } else o.str("NA\tNA\tNA\tNA\tNA\tNA\n");
+  }
+}
+
+void peaks(Buf& o, const std::vector<int32_t> (&ch)[4]) {
+  for (int c = 0; c < 4; ++c) {
+    o.str("\"peak"); o.ch("ACGT"[c]); o.str("\": [");
+    for (size_t i = 0; i < ch[c].size(); ++i) { if (i) o.str(", "); o.num(ch[c][i]); }
+    o.str("],\n");
+  }
+}
+
+// alignmentTracePadding + assemblyTrace: the gapped trace object of P.json
+void gapped_trace(Buf& o, const tb_trace_view& t, const char* row, int32_t L, const char* trace_file_name) {
+  const int32_t ns = t.nsamples, nbc = t.nbc;
+  int step = 6;
+  if (nbc > 1) {
+    long long sum = 0;
+    for (int32_t i = 1; i < nbc; ++i) sum += t.bcpos[i] - t.bcpos[i - 1];
+    step = (int)(uint32_t)((double)sum / (double)(nbc - 1));  // src/json.h:393-399: a double average, truncated
+  }
+  std::vector<int32_t> ins_pos, ins_size;
+  int32_t pos = 0, gapsize = 0, leading = 0;
+  bool ingap = false;
+  for (int32_t j = 0; j < L; ++j) {
+    if (row[j] == '-') { gapsize = ingap ? gapsize + 1 : 1; ingap = true; }
+    else {
+      if (ingap) {
+        ingap = false;
+        if (pos) { ins_pos.push_back((int32_t)((t.bcpos[pos - 1] + t.bcpos[pos]) / 2.0)); ins_size.push_back(gapsize); }
+        else leading = gapsize;
+      }
+      ++pos;
+    }
+  }
+  const int32_t trailing = ingap ? gapsize : 0;
+  std::vector<int32_t> ch[4], nbp;
+  std::vector<uint8_t> nq;
+  std::string npri, nsec;
+  for (int c = 0; c < 4; ++c) ch[c].reserve((size_t)ns + 64);
+  int32_t k = 0, idx = t.bcpos[0], offset = 0;
+  size_t q = 0;
+  int32_t ins_idx = ins_pos.empty() ? -1 : ins_pos[0];
+  for (int32_t s = 0; s < ns; ++s) {
+    for (int c = 0; c < 4; ++c) ch[c].push_back(t.acgt[(size_t)c * ns + s]);
+    if (ins_idx == s) {
+      for (int32_t g = 0; g < ins_size[q]; ++g) {
+        nbp.push_back(s + offset + (int32_t)(step / 2.0)); nq.push_back(0); npri.push_back('-'); nsec.push_back('-');
+        for (int c = 0; c < 4; ++c) ch[c].insert(ch[c].end(), (size_t)step, -99);      // EMPTY_TRACE_SIGNAL, src/json.h:12-14
+        offset += step;
+      }
+      if (q + 1 < ins_pos.size()) ins_idx = ins_pos[++q];
+    }
+    if (idx == s) {
+      nbp.push_back(idx + offset); nq.push_back(t.qual[k]); npri.push_back(t.primary[k]); nsec.push_back(t.secondary[k]);
+      if (k < nbc - 1) idx = t.bcpos[++k];
+    }
+  }
+  o.str("{\n\"traceFileName\": \""); o.str(trace_file_name); o.str("\",\n\"leadingGaps\": "); o.num(leading);
+  o.str(",\n\"trailingGaps\": "); o.num(trailing); o.str(",\n");
+  peaks(o, ch);
+  const int32_t pns = (int32_t)ch[0].size(), pnb = (int32_t)nbp.size();
+  std::vector<std::pair<int32_t, int32_t> > calls;
+  if (pnb > 0) for_called(pns, nbp.data(), pnb, [&](int32_t i, int32_t kk) { calls.push_back(std::make_pair(i, kk)); });
+  o.str("\"basecallPos\": [");
+  for (size_t i = 0; i < calls.size(); ++i) { if (i) o.str(", "); o.num(calls[i].first + 1); }
+  o.str("],\n\"basecallQual\": [");
+  for (size_t i = 0; i < calls.size(); ++i) { if (i) o.str(", "); o.num(nq[(size_t)calls[i].second]); }
+  o.str("],\n\"basecalls\": {");
+  int32_t gapless = 0;
+  for (size_t i = 0; i < calls.size(); ++i) {
+    const int32_t kk = calls[i].second;
+    if (i) o.str(", ");
+    o.ch('"'); o.num(calls[i].first + 1); o.str("\":\"");
+    if (npri[(size_t)kk] != '-') {
+      o.num(++gapless); o.ch(':'); o.ch(npri[(size_t)kk]);
+      if (npri[(size_t)kk] != nsec[(size_t)kk]) { o.ch('|'); o.ch(nsec[(size_t)kk]); }
+    } else o.ch('-');
+    o.ch('"');
+  }
+  o.str("}\n}\n");
+}
+
+void ungapped_wrapped(Buf& o, const char* row, int32_t L, int fald) {
+  int count = 0;
+  for (int32_t j = 0; j < L; ++j)
+    if (row[j] != '-') { o.ch(row[j]); if (++count % fald == 0) o.ch('\n'); }
+  if (count % fald != 0) o.ch('\n');
+}
+
+void fmt_g(Buf& o, double v) { char tmp[40]; const int n = snprintf(tmp, sizeof tmp, "%g", v); o.str(tmp, (size_t)n); }
+
+}  // namespace
+
+extern "C" {
+
+int tb_write_trace_txt(const char* path, const tb_trace_view* t, int32_t trim_left, int32_t trim_right) {
+  if (!path || !view_ok(t) || trim_left < 0 || trim_right < 0) return TB_ERR_INVALID;
+  Buf o;
+  trace_txt(o, *t, trim_left, trim_right);
+  return flush_to(path, o);
+}
+
+int tb_write_align_fasta(const char* path, const char* trace_name, const char* row0, const char* row1, int32_t L, const char* chr, int32_t forward) {
+  if (!path || !trace_name || !row0 || !row1 || !chr || L < 0) return TB_ERR_INVALID;
+  Buf o;
+  o.ch('>'); o.str(trace_name); o.ch('\n'); o.str(row0, (size_t)L); o.str("\n>"); o.str(chr); o.str(forward ? " (forward)\n" : " (reverse)\n");
+  o.str(row1, (size_t)L); o.ch('\n');
+  return flush_to(path, o);
+}
+
+int tb_write_plot_alignment(const char* path, const char* row0, const char* row1, int32_t L, const char* chr, uint32_t pos, int32_t refslice_len,
+                            int32_t forward, int32_t score, int32_t key, double a1, double a2, int32_t linelimit) {
+  if (!path || !row0 || !row1 || !chr || L < 0 || linelimit <= 0 || key < 0 || key > 3) return TB_ERR_INVALID;
+  Buf o;
+  const int fald = linelimit + 14;
+  long long ri = (long long)pos + 1, vi = 1;
+  const long long riend = (long long)pos + refslice_len;
+  if (key == 0) o.str(">Alt\n");
+  else if (key == 2) { o.str(">Alt2 (Estimated allelic Fraction: "); fmt_g(o, a2); o.str(")\n"); }
+  else { o.str(">Alt1 (Estimated allelic Fraction: "); fmt_g(o, a1); o.str(")\n"); }
+  ungapped_wrapped(o, row0, L, fald);
+  if (key != 3) {
+    o.str(">Ref "); o.str(chr); o.ch(':');
+    if (forward) { o.num(ri); o.ch('-'); o.num(riend); o.str(" forward\n"); }
+    else { o.num((long long)pos + refslice_len - (riend - pos) + 1); o.ch('-'); o.num((long long)pos + refslice_len - (ri - pos) + 1); o.str(" reversecomplement\n"); }
+  } else { o.str(">Alt2 (Estimated allelic Fraction: "); fmt_g(o, a2); o.str(")\n"); }
+  ungapped_wrapped(o, row1, L, fald);
+  o.str("\nAlignment score: "); o.num(score); o.ch('\n');
+  std::string rule = "#"; rule.append((size_t)(fald - 1), '-'); rule.push_back('\n');
+  o.str(rule.c_str()); o.ch('\n');
+  int blocks = 0;
+  for (int32_t s = 0; s < L; s += linelimit) {
+    const int32_t e = s + linelimit < L ? s + linelimit : L;
+    if (key != 3) { o.str("Alt"); o.padded(vi, 10); } else { o.str("Alt1"); o.padded(vi, 9); }
+    o.ch(' ');
+    for (int32_t j = s; j < e; ++j) { o.ch(row0[j]); if (row0[j] != '-') ++vi; }
+    o.ch('\n');
+    o.s.append(14, ' ');
+    for (int32_t j = s; j < e; ++j) o.ch(row0[j] == row1[j] ? '|' : ' ');
+    o.ch('\n');
+    if (key != 3) { o.str("Ref"); o.padded(forward ? ri : (long long)pos + refslice_len - (ri - pos) + 1, 10); } else { o.str("Alt2"); o.padded(ri, 9); }
+    o.ch(' ');
+    for (int32_t j = s; j < e; ++j) { o.ch(row1[j]); if (row1[j] != '-') ++ri; }
+    o.str("\n\n");
+    ++blocks;
+  }
+  if (blocks < 6) o.s.append((size_t)(4 * (6 - blocks)), '\n');
+  o.str(rule.c_str()); o.str(rule.c_str()); o.str("\n\n");
+  return flush_to(path, o);
+}
+
+int tb_write_trace_align_json(const char* path, const tb_trace_view* t, const char* row0, const char* row1, int32_t L, const char* chr, uint32_t pos,
+                              int32_t forward) {
+  if (!path || !view_ok(t) || !row0 || !row1 || !chr || L < 0) return TB_ERR_INVALID;
+  Buf o;
+  o.s.reserve((size_t)t->nsamples * 32 + (size_t)L * 2 + 4096);
+  o.str("{\n\"gappedTrace\":\n");
+  gapped_trace(o, *t, row0, L, "trace");
+  o.str(",\n\"refchr\": \""); o.str(chr); o.str("\",\n\"refpos\": "); o.num((long long)pos + 1);
+  o.str(",\n\"altalign\": \""); o.str(row0, (size_t)L); o.str("\",\n\"refalign\": \""); o.str(row1, (size_t)L);
+  o.str("\",\n\"forward\": "); o.num(forward ? 1 : 0); o.str("\n}\n");
+  return flush_to(path, o);
+}
+
+int tb_write_align_files(const char* prefix, const char* trace_name, const tb_trace_view* t, int32_t trim_left, int32_t trim_right, const char* row0,
+                         const char* row1, int32_t L, const char* chr, uint32_t pos, int32_t refslice_len, int32_t forward, int32_t score,
+                         int32_t linelimit) {
+  if (!prefix || !trace_name) return TB_ERR_INVALID;
+  const std::string p(prefix);
+  int rc = tb_write_trace_txt((p + ".abif").c_str(), t, trim_left, trim_right);
+  if (rc == TB_OK) rc = tb_write_align_fasta((p + ".align.fa").c_str(), trace_name, row0, row1, L, chr, forward);
+  if (rc == TB_OK) rc = tb_write_plot_alignment((p + ".txt").c_str(), row0, row1, L, chr, pos, refslice_len, forward, score, 0, 0.0, 0.0, linelimit);
+  if (rc == TB_OK) rc = tb_write_trace_align_json((p + ".json").c_str(), t, row0, row1, L, chr, pos, forward);
+  return rc;
+}
+
+}  // extern "C"

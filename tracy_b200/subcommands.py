@@ -120,13 +120,13 @@ def _load_traces(ctx, blobs, pratio):
     bc = ctx.basecall([t["traceACGT"] for _, t in good], [t["basecallpos"] for _, t in good], pratio)
     for (i, t), b in zip(good, bc):
         out[i] = dict(acgt=t["traceACGT"], ploc=t["basecallpos"], bcpos=b["bcPos"], primary=b["primary"], secondary=b["secondary"],
-                      consensus=b["consensus"], qual=trim.estimate_qualities(b["bcPos"], b["secondary"]))
+                      consensus=b["consensus"], qual=trim.trace_quality(b["bcPos"], b["secondary"])[0])
     return out
 
 
 def _trims(t, stringency, left, right):
     if stringency >= 1:
-        return trim.trim_trace(t["bcpos"], t["secondary"], stringency)
+        return trim.trace_quality(t["bcpos"], t["secondary"], stringency)[1]
     return left, right
 
 
@@ -232,14 +232,13 @@ def align(ctx, jobs, pratio=0.33, trim_stringency=0.0, trim_left=50, trim_right=
 
 
 def _abif_only(prefix, t):
-    _Writers.write(prefix, {".abif": writers.trace_txt(t["acgt"], t["bcpos"], t["qual"], t["primary"], t["secondary"], t["consensus"], t["tl"], t["tr"])})
+    writers.write_trace_txt(prefix + ".abif", t["acgt"], t["bcpos"], t["qual"], t["primary"], t["secondary"], t["consensus"], t["tl"], t["tr"])
 
 
 def _align_out(job, t, r, linelimit):
-    files = writers.align_files(_stem(job[0]), t["acgt"], t["bcpos"], t["qual"], t["primary"], t["secondary"], t["consensus"], t["tl"], t["tr"],
-                                r["row0"], r["row1"], r["chr"].encode("latin-1") if isinstance(r["chr"], str) else r["chr"], r["pos"], r["refslice_len"],
-                                r["forward"], r["score"], linelimit)
-    _Writers.write(job[2], files)
+    # native writers (csrc/writers.cu, same bytes as writers.align_files): ~390 KB of text per trace, formatted outside the interpreter
+    writers.write_align_files(job[2], _stem(job[0]), t["acgt"], t["bcpos"], t["qual"], t["primary"], t["secondary"], t["consensus"], t["tl"], t["tr"],
+                              r["row0"], r["row1"], r["chr"], r["pos"], r["refslice_len"], r["forward"], r["score"], linelimit)
 
 
 # ---- tracy consensus -----------------------------------------------------------------------------------------------------------
@@ -301,7 +300,7 @@ def consensus(ctx, jobs, label="Consensus", pratio=0.33, match_fraction=0.5, min
 
 def _cons_abif(prefix, a, b):
     for t, tag in ((a, "_1st.abif"), (b, "_2nd.abif")):
-        _Writers.write(prefix, {tag: writers.trace_txt(t["acgt"], t["bcpos"], t["qual"], t["primary"], t["secondary"], t["consensus"], t["tl"], t["tr"])})
+        writers.write_trace_txt(prefix + tag, t["acgt"], t["bcpos"], t["qual"], t["primary"], t["secondary"], t["consensus"], t["tl"], t["tr"])
 
 
 def _cons_out(job, r, p1, p2, label, union, iupac, linelimit):
@@ -353,7 +352,7 @@ def assemble(ctx, jobs, pratio=0.33, trim_stringency=4.0, match_fraction=0.5, fr
                 break
             t["tl"], t["tr"] = (0, 0)
             if trim_stringency:
-                t["tl"], t["tr"] = trim.trim_trace(t["bcpos"], t["secondary"], trim_stringency)
+                t["tl"], t["tr"] = trim.trace_quality(t["bcpos"], t["secondary"], trim_stringency)[1]
                 if t["tl"] + t["tr"] >= len(t["bcpos"]):
                     rc[ji] = -1                                                            # "Too stringent trimming parameters!"
                     break

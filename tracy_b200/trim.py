@@ -17,6 +17,17 @@ def _s(x):
     return bytes(x).decode("latin-1") if not isinstance(x, str) else x
 
 
+def _i32(v):
+    """Wrap to int32 (two's complement), as the reference's int32_t arithmetic does."""
+    v &= _U32
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
+def _cvt_i32(x):
+    """(int32_t) of a double as x86 converts it: truncation, INT_MIN for NaN and for anything out of range."""
+    return int(x) if (x == x and -2147483649.0 < x < 2147483648.0) else -2147483648
+
+
 def _tail(n, halfwin):
     """for (uint32_t i = size - halfwin; i < size; ++i): with fewer than halfwin basecalls the start wraps and nothing runs."""
     return range(n - halfwin, n) if n >= halfwin else range(0)
@@ -48,17 +59,19 @@ def find_best_trace_section(bcpos, secondary, win=10):
             dist = (pos[i + k] - old) & _U32
             old = pos[i + k] & _U32
             lo, hi = min(lo, dist), max(hi, dist)
-        peak_var = int((abs(hi - mean) + abs(lo - mean)) / 2)
-        penalty[i + halfwin] += peak_var
+        x = (abs(hi - mean) + abs(lo - mean)) / 2
+        # (int32_t) of a double: out of range (peak distances wrap where basecall positions do not increase) gives INT_MIN on x86
+        peak_var = _cvt_i32(x) & _U32
+        penalty[i + halfwin] = _i32(penalty[i + halfwin] + peak_var)             # int32 += uint32: modulo 2^32
         if i == 0:
             for k in range(halfwin):
-                penalty[k] += peak_var
+                penalty[k] = _i32(penalty[k] + peak_var)
     for i in _tail(n, halfwin):
-        penalty[i] += peak_var
+        penalty[i] = _i32(penalty[i] + peak_var)
     sourcewin = int(0.1 * n)
     best_idx, best_val = 0, 99999999
     for i in range(max(n - sourcewin, 0)):
-        v = sum(penalty[i: i + sourcewin])
+        v = _i32(sum(penalty[i: i + sourcewin]))
         if v < best_val:
             best_val, best_idx = v, i + sourcewin // 2
     per_base = best_val / sourcewin if sourcewin else (float("nan") if best_val == 0 else math.copysign(float("inf"), best_val))
@@ -74,7 +87,7 @@ def estimate_qualities(bcpos, secondary):
     if max_val == 0:
         return np.zeros(len(penalty), np.uint8)
     scaling = 60.0 / max_val
-    return np.array([min(max(int(60.0 - scaling * p), 0), 60) for p in penalty], np.uint8)
+    return np.array([min(max(_cvt_i32(60.0 - scaling * p), 0), 60) for p in penalty], np.uint8)
 
 
 def trim_trace(bcpos, secondary, trim_stringency):
@@ -170,3 +183,21 @@ def nearest_snp(primary, secondary, trim_left, trim_right, rtp):
             break
         offset += 1
     return rtp - trim_left if rtp > trim_left else trim_left
+
+
+def trace_quality(bcpos, secondary, trim_stringency=None):
+    """estimate_qualities (+ trim_trace when a stringency is given) through the native tb_trace_quality (csrc/trimq.cu): the same
+    numbers, without the interpreter in the per-basecall loops. Returns (qual uint8[n], (left, right) or None)."""
+    import ctypes as C
+    from . import capi
+    pos = np.ascontiguousarray(bcpos, np.int32)
+    sec = secondary.encode("latin-1") if isinstance(secondary, str) else bytes(secondary)
+    n = min(len(pos), len(sec))
+    qual = np.zeros(n, np.uint8)
+    left, right = C.c_uint32(0), C.c_uint32(0)
+    want = trim_stringency is not None
+    rc = capi.lib().tb_trace_quality(pos.ctypes.data, sec, n, float(trim_stringency or 0.0), qual.ctypes.data, None, C.byref(left) if want else None,
+                                     C.byref(right) if want else None)
+    if rc != capi.TB_OK:
+        raise ValueError("tb_trace_quality: %d" % rc)
+    return qual, ((int(left.value), int(right.value)) if want else None)

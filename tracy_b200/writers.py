@@ -12,6 +12,8 @@ the batch drivers return, byte-identical to the reference's writers.
   aligned_trace_by_row, assemble_files   P.align.fa / P.json / P.vertical / P.cons.fa|fq of `tracy assemble`   reference src/json.h:220-246, src/assemble.h:473-579
 The BCF writer (src/variants.h:141-266, htslib) is not covered.
 """
+import os
+
 import numpy as np
 
 EMPTY_TRACE_SIGNAL = -99          # reference src/json.h:12-14
@@ -369,3 +371,42 @@ def trace_fastq(otype, trim_left, trim_right, nsamples, bcpos, qual, primary, se
     last = len(_s(primary)) - trim_right
     quals = "".join(chr((int(qual[k]) + 33) & 0xFF) for _, k in _called(nsamples, bcpos) if trim_left <= k < last)
     return head + "+\n" + quals + "\n"
+
+
+# ---- native forms (csrc/writers.cu): the same bytes, formatted and written without the interpreter -------------------------------
+def _trace_view(acgt, bcpos, qual, primary, secondary, consensus):
+    import ctypes as C
+    from . import capi
+    acgt = np.ascontiguousarray(acgt, np.int32)
+    bcpos = np.ascontiguousarray(bcpos, np.int32)
+    qual = np.ascontiguousarray(qual, np.uint8)
+    pri, sec, con = (x.encode("latin-1") if isinstance(x, str) else bytes(x) for x in (primary, secondary, consensus))
+    keep = (acgt, bcpos, qual, pri, sec, con)
+    v = capi.TraceView(acgt.ctypes.data, acgt.shape[1], bcpos.ctypes.data, qual.ctypes.data, C.cast(C.c_char_p(pri), C.c_void_p), C.cast(C.c_char_p(sec), C.c_void_p),
+                       C.cast(C.c_char_p(con), C.c_void_p), len(bcpos))
+    return v, keep
+
+
+def write_align_files(prefix, trace_name, acgt, bcpos, qual, primary, secondary, consensus, trim_left, trim_right, row0, row1, chr_name, pos, refslice_len,
+                      forward, score, linelimit=60):
+    """The four files of `tracy align -o prefix` for one trace (what align_files returns as text), written by tb_write_align_files.
+    The call releases the GIL: a pool of writer threads runs them in parallel."""
+    import ctypes as C
+    from . import capi
+    v, keep = _trace_view(acgt, bcpos, qual, primary, secondary, consensus)
+    row0, row1 = bytes(row0), bytes(row1)
+    chr_b = chr_name.encode("latin-1") if isinstance(chr_name, str) else bytes(chr_name)
+    rc = capi.lib().tb_write_align_files(os.fsencode(prefix), trace_name.encode("latin-1"), C.byref(v), int(trim_left), int(trim_right), row0, row1, len(row0),
+                                         chr_b, int(pos), int(refslice_len), int(bool(forward)), int(score), int(linelimit))
+    if rc != capi.TB_OK:
+        raise OSError("tb_write_align_files(%s): %d" % (prefix, rc))
+
+
+def write_trace_txt(path, acgt, bcpos, qual, primary, secondary, consensus, trim_left, trim_right):
+    """P.abif written by tb_write_trace_txt (the bytes of trace_txt)."""
+    import ctypes as C
+    from . import capi
+    v, keep = _trace_view(acgt, bcpos, qual, primary, secondary, consensus)
+    rc = capi.lib().tb_write_trace_txt(os.fsencode(path), C.byref(v), int(trim_left), int(trim_right))
+    if rc != capi.TB_OK:
+        raise OSError("tb_write_trace_txt(%s): %d" % (path, rc))

@@ -16,7 +16,7 @@ with tempfile.TemporaryDirectory() as d:
     jobs = [j for j in jobs if os.path.exists(j[0]) and j[1].endswith(".fa") and "big" not in j[1] and "multi" not in j[1]][:N]
     gen = time.perf_counter() - t0
     subcommands.align(ctx, jobs[:32], chunk=32)                                   # warm-up
-    for workers in (1, 4, 16):
+    for workers in (2, 8, 16):
         st0 = ctx.stats(); t0 = time.perf_counter()
         rc = subcommands.align(ctx, jobs, chunk=256, workers=workers)
         dt = time.perf_counter() - t0
@@ -24,4 +24,12 @@ with tempfile.TemporaryDirectory() as d:
         out[f"align_workers{workers}"] = {"jobs": len(jobs), "ok": rc.count(0), "seconds": dt, "traces_per_s": len(jobs) / dt, "output_MB": nbytes / 1e6,
                                           "kernel_launches": ctx.stats()["kernel_launches"] - st0["kernel_launches"]}
     out["generate_inputs_s"] = gen
+    from oracle import loader                                                      # the reference's own `tracy align` on a sample of the same files, one core
+    ref = loader.ref()
+    if ref is not None:
+        t0 = time.perf_counter()
+        rc = [ref.subcommand("align", ["-r", g, "-o", o + ".ref", t]) for t, g, o in jobs[:24]]
+        dt = time.perf_counter() - t0
+        out["reference_one_core"] = {"jobs": 24, "ok": rc.count(0), "seconds": dt, "traces_per_s": 24 / dt,
+                                     "what": "tracy::sage(argc, argv) of the unmodified reference (oracle/_ref) on the first 24 jobs"}
 print(json.dumps(out, indent=1))

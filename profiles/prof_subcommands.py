@@ -6,6 +6,7 @@ import tracy_b200
 from tracy_b200 import subcommands
 from subcmd_cases import make_align_jobs
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+WORKERS = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 ctx = tracy_b200.Context(0)
 with tempfile.TemporaryDirectory() as d:
     jobs, _ = make_align_jobs(d, n=N, seed=7)
@@ -14,7 +15,7 @@ with tempfile.TemporaryDirectory() as d:
     pr = cProfile.Profile()
     t0 = time.perf_counter()
     pr.enable()
-    rc = subcommands.align(ctx, jobs, chunk=256, workers=8)
+    rc = subcommands.align(ctx, jobs, chunk=256, workers=WORKERS)
     pr.disable()
     dt = time.perf_counter() - t0
     print("jobs", len(jobs), "ok", rc.count(0), "seconds", round(dt, 3), "traces/s", round(len(jobs) / dt, 1))

@@ -20,16 +20,19 @@ _SEMIGLOBAL = AlignConfig(True, False)          # AlignConfig<true, false>, src/
 _COMP = {ord("A"): ord("T"), ord("C"): ord("G"), ord("G"): ord("C"), ord("T"): ord("A"), ord("N"): ord("N")}
 
 
+_UPPER_TABLE = np.frombuffer(bytes(range(256)).upper(), np.uint8)
+_COMP_TABLE = np.zeros(256, np.uint8)
+for _k, _v in _COMP.items():
+    _COMP_TABLE[_k] = _v
+
+
 def reverse_complement_seq(seq):
     """reverseComplement(std::string&), reference src/fmindex.h:11-26: upper-cased reverse, A<->T, C<->G, N kept; any other
     character leaves the ORIGINAL character of that position in place (the reference's `default: break`)."""
     seq = bytes(seq)
-    rev = seq[::-1].upper()
-    out = bytearray(seq)
-    for i, ch in enumerate(rev):
-        if ch in _COMP:
-            out[i] = _COMP[ch]
-    return bytes(out)
+    a = np.frombuffer(seq, np.uint8)
+    mapped = _COMP_TABLE[_UPPER_TABLE[a[::-1]]]
+    return np.where(mapped != 0, mapped, a).astype(np.uint8).tobytes()
 
 
 def _gap_rows(ops):

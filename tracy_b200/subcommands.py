@@ -25,7 +25,7 @@ from .api import AlignConfig, DnaScore
 PP, PS = "pp", "ps"
 MAX_SINGLE_FASTA_SIZE = 50000                        # src/fasta.h:10-12
 _FIX_NAME = "\\,'\"()[]{}<>:\t\r#"                   # _fixReferenceName, src/fasta.h:16-35
-_DEGENERATE = set(b"WSMKRYBDHV")
+_DEGENERATE_TO_N = bytes.maketrans(b"WSMKRYBDHV", b"N" * 10)        # _replaceDegenerateBases, src/fasta.h:38-53
 
 
 def _stem(path):
@@ -55,15 +55,10 @@ def load_single_fasta(data):
             name = (line[1:-1] if line.endswith(b"\r") else line[1:]).decode("latin-1")
         else:
             seq.append((line[:-1] if line.endswith(b"\r") else line).upper())
-    s = bytearray(b"".join(seq))
-    for i, ch in enumerate(s):
-        if ch in b"ACGTN":
-            continue
-        if ch in _DEGENERATE:
-            s[i] = 0x4E
-        else:
-            return None
-    return "".join(ch for ch in name if ch not in _FIX_NAME), bytes(s)
+    s = b"".join(seq).translate(_DEGENERATE_TO_N)
+    if s.translate(None, b"ACGTN"):                                  # anything left is neither a nucleotide nor an IUPAC code
+        return None
+    return "".join(ch for ch in name if ch not in _FIX_NAME), s
 
 
 def genome_type(data):

@@ -35,7 +35,16 @@
 
 namespace tb {
 
-constexpr int kPkWarps = 2;                       // warps per block (40 KB of tables per block: five blocks per SM)
+#ifndef TB_PK_WARPS
+#define TB_PK_WARPS 2         // warps per block
+#endif
+#ifndef TB_PK_MINBLOCKS4
+#define TB_PK_MINBLOCKS4 6    // resident blocks per SM the 4-class kernel is compiled for (12 warps: what registers and tables allow)
+#endif
+#ifndef TB_PK_MINBLOCKS5
+#define TB_PK_MINBLOCKS5 5
+#endif
+constexpr int kPkWarps = TB_PK_WARPS;             // warps per block (32 / 40 KB of tables per block: six / five blocks per SM)
 constexpr int kPkRows = 1024;                     // DP rows per pass (two 512-row half-bands)
 // One half-band table: [class][q][lane][4] 32-bit entries = 2 KB per class. Two instantiations: CLASSES = 4 (A,C,G,T:
 // 16 KB per warp, 12 warps per SM) for windows without N, CLASSES = 5 (A,C,G,T,N: 20 KB per warp, 10 warps per SM).
@@ -541,7 +550,7 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
 }
 
 template <int TBMODE, bool VFREE, int CLASSES, bool ASEQ>
-__global__ void __launch_bounds__(kPkWarps * 32, CLASSES == 4 ? 6 : 5)   // 12 / 10 warps per SM: what the tables allow
+__global__ void __launch_bounds__(kPkWarps * 32, CLASSES == 4 ? TB_PK_MINBLOCKS4 : TB_PK_MINBLOCKS5)   // 12 / 10 warps per SM: what the tables allow
 gotoh_packed_kernel(const GotohBatch B) {
   constexpr bool TRACEBACK = TBMODE != kTbNone, FLAGS = TBMODE == kTbFlags, CKPT = TBMODE == kTbCkpt;
   constexpr int kFillUnroll = TRACEBACK ? TB_FILL_UNROLL_TB : 4;

@@ -584,9 +584,9 @@ class _Ref:
         return pri.raw[:nbc], sec.raw[:nbc], dcp[: 2 * n].reshape(n, 2).copy()
 
     def subcommand(self, name, args):
-        """Run the reference's own subcommand entry point files-in -> files-out: name in consensus / align / assemble
-        (src/consensus.h:332, src/sage.h:58, src/assemble.h:57); args = the command line after the subcommand name. Returns its exit code."""
-        what = {"consensus": 0, "align": 1, "assemble": 2}[name]
+        """Run the reference's own subcommand entry point files-in -> files-out: name in consensus / align / assemble / decompose
+        (src/consensus.h:332, src/sage.h:58, src/assemble.h:57, src/indigo.h:42 -- decompose without -v / -a); args = the command line after the subcommand name. Returns its exit code."""
+        what = {"consensus": 0, "align": 1, "assemble": 2, "decompose": 3}[name]
         self.lib.ref_subcommand.argtypes = [C.c_int, C.c_char_p]
         self.lib.ref_subcommand.restype = C.c_int
         return self.lib.ref_subcommand(what, "\n".join([name] + [str(a) for a in args]).encode())

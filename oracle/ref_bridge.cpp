@@ -10,6 +10,7 @@
 // Nothing here restates an algorithm: every function marshals plain C buffers into the reference's
 // own types and calls the reference's own templates.
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <sstream>
@@ -36,6 +37,7 @@
 #include "consensus.h" // gtLetter, pairwiseConsensus, plotClustalPairwise, int consensus(argc, argv) (reference, unmodified)
 #include "sage.h"      // int sage(argc, argv) = `tracy align` (reference, unmodified)
 #include "assemble.h"  // int assemble(argc, argv) = `tracy assemble` (reference, unmodified)
+#include "indigo.h"    // int indigo(argc, argv) = `tracy decompose` (reference, unmodified; its Ensembl client and BCF writer only compile here)
 
 namespace {
 typedef boost::multi_array<float, 2> TProfile;
@@ -674,7 +676,8 @@ int ref_get_reference_slice(void* h, int filetype, const char* cons, int len, in
 }
 
 // The reference's own subcommand entry points, files in -> files out (src/tracy.cpp:66-81 hands them argc-1, argv+1):
-// what 0 = `tracy consensus` (src/consensus.h:332), 1 = `tracy align` (src/sage.h:58), 2 = `tracy assemble` (src/assemble.h:57).
+// what 0 = `tracy consensus` (src/consensus.h:332), 1 = `tracy align` (src/sage.h:58), 2 = `tracy assemble` (src/assemble.h:57),
+// 3 = `tracy decompose` (src/indigo.h:42; without -v / -a: the BCF writer and the Ensembl client are not reachable here).
 // args is a '\n'-joined argument list whose first entry is the subcommand name. The progress lines on stdout/stderr are dropped.
 int ref_subcommand(int what, const char* args) {
   std::vector<std::string> a; { std::stringstream ss(args); std::string x; while (std::getline(ss, x)) a.push_back(x); }
@@ -685,6 +688,7 @@ int ref_subcommand(int what, const char* args) {
     if (what == 0) rc = tracy::consensus((int)argv.size(), argv.data());
     else if (what == 1) rc = tracy::sage((int)argv.size(), argv.data());
     else if (what == 2) rc = tracy::assemble((int)argv.size(), argv.data());
+    else if (what == 3) rc = tracy::indigo((int)argv.size(), argv.data());
   } catch (std::exception const&) { rc = -98; }
   std::cout.clear(); std::cerr.clear();
   std::cout.rdbuf(o1); std::cerr.rdbuf(o2);
@@ -714,3 +718,28 @@ int ref_pairwise_consensus(const char* row0, const char* row1, int L, const floa
 }
 
 }  // extern "C"
+
+// htslib's BCF writer cannot be built in this container; vcfOutput (src/variants.h:141-266) is only reachable through `tracy decompose
+// -v`, which the oracle never passes. These definitions exist so that the library LOADS with indigo() inside; every one of them stops
+// the process if it is ever reached, so no test can pass on a silently missing P.bcf.
+namespace { [[noreturn]] void no_htslib(const char* fn) { std::fprintf(stderr, "oracle/_ref: %s called, but htslib is not part of this build\n", fn); std::abort(); } }
+extern "C" {
+void bcf_clear(bcf1_t*) { no_htslib("bcf_clear"); }
+void bcf_destroy(bcf1_t*) { no_htslib("bcf_destroy"); }
+int bcf_hdr_add_sample(bcf_hdr_t*, const char*) { no_htslib("bcf_hdr_add_sample"); }
+int bcf_hdr_append(bcf_hdr_t*, const char*) { no_htslib("bcf_hdr_append"); }
+void bcf_hdr_destroy(bcf_hdr_t*) { no_htslib("bcf_hdr_destroy"); }
+int bcf_hdr_id2int(const bcf_hdr_t*, int, const char*) { no_htslib("bcf_hdr_id2int"); }
+bcf_hdr_t* bcf_hdr_init(const char*) { no_htslib("bcf_hdr_init"); }
+int bcf_hdr_write(htsFile*, bcf_hdr_t*) { no_htslib("bcf_hdr_write"); }
+int bcf_index_build(const char*, int) { no_htslib("bcf_index_build"); }
+bcf1_t* bcf_init(void) { no_htslib("bcf_init"); }
+int bcf_update_alleles_str(const bcf_hdr_t*, bcf1_t*, const char*) { no_htslib("bcf_update_alleles_str"); }
+int bcf_update_filter(const bcf_hdr_t*, bcf1_t*, int*, int) { no_htslib("bcf_update_filter"); }
+int bcf_update_format(const bcf_hdr_t*, bcf1_t*, const char*, const void*, int, int) { no_htslib("bcf_update_format"); }
+int bcf_update_id(const bcf_hdr_t*, bcf1_t*, const char*) { no_htslib("bcf_update_id"); }
+int bcf_update_info(const bcf_hdr_t*, bcf1_t*, const char*, const void*, int, int) { no_htslib("bcf_update_info"); }
+int bcf_write(htsFile*, bcf_hdr_t*, bcf1_t*) { no_htslib("bcf_write"); }
+int hts_close(htsFile*) { no_htslib("hts_close"); }
+htsFile* hts_open(const char*, const char*) { no_htslib("hts_open"); }
+}

@@ -11,6 +11,7 @@ inline void erase_all(std::string& s, const std::string& what) {
   if (what.empty()) return;
   for (std::size_t p = s.find(what); p != std::string::npos; p = s.find(what, p)) s.erase(p, what.size());
 }
+inline std::string to_lower_copy(const std::string& s) { std::string r(s); for (auto& ch : r) ch = (char)std::tolower((unsigned char)ch); return r; }
 inline std::string to_upper_copy(const std::string& s) { std::string r(s); for (auto& ch : r) ch = (char)std::toupper((unsigned char)ch); return r; }
 template <typename T, typename S> inline T lexical_cast(const S& x) { std::stringstream ss; ss << x; T v; ss >> v; return v; }
 namespace filesystem {

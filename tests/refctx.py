@@ -67,3 +67,25 @@ class RefContext:
             ops[i, : len(o)] = np.frombuffer(o, np.uint8)
             ol[i] = len(o)
         return scores, ops, ol
+
+    def decompose_sweep(self, refrows, primaries, secondaries, vi_end, align_index, var_index, ndel, nins, grid=False):
+        """The sweeps live inside decomposeAlleles in the reference; the C restatement (oracle/gotoh_oracle.c, pinned on
+        decomposeAlleles' goldens) serves them one trace at a time."""
+        port = loader.port()
+        n = len(refrows)
+        S = int(max(1, max(ndel, default=1), max(nins, default=1)))
+        fref, fins = np.zeros((n, S), np.int32), np.zeros((n, S), np.int32)
+        g = np.zeros((n, S, S), np.int32) if grid else None
+        for t in range(n):
+            a, b, c = port.decompose_sweep(bytes(refrows[t]), bytes(primaries[t]), bytes(secondaries[t]), int(vi_end[t]), int(align_index[t]), int(var_index[t]),
+                                           int(ndel[t]), int(nins[t]), grid)
+            fref[t, : len(a)] = a
+            fins[t, : len(b)] = b
+            if grid and c is not None:
+                c = np.asarray(c)
+                g[t, : c.shape[0], : c.shape[1]] = c
+        return fref, fins, g
+
+    def allelic_fraction(self, traces, bcpos, primary, secdecompose, trim_left=50, trim_right=50):
+        return np.array([self.ref.allelic_fraction(traces[i], bcpos[i], bytes(primary[i]), bytes(secdecompose[i]), trim_left, trim_right)
+                         for i in range(len(traces))], np.float64).reshape(-1, 2)

@@ -174,3 +174,63 @@ def make_assemble_jobs(root, n=6, seed=3):
     jobs.append((far, other, os.path.join(root, "asx2.out")))
     argv.append([]); kws.append({})
     return jobs, dict(argv=argv, groups=_group(kws))
+
+
+DEC_SUFFIXES = (".abif", ".decomp", ".align1", ".align2", ".align3", ".json")
+
+
+def het_file(rng, a1, a2, frac=0.6, scf=False):
+    """A trace file with two alleles mixed frac : 1 - frac in signal space (the second allele shifted against the first behind an indel)."""
+    nbc = min(len(a1), len(a2))
+    ns = 12 * nbc + 40
+    tr = rng.integers(0, 20, size=(4, ns)).astype(np.int64)
+    pos = (12 * np.arange(nbc) + 10 + rng.integers(-2, 3, nbc)).astype(np.int64)
+    shape = np.array([0.15, 0.55, 1.0, 0.55, 0.15])
+    for j in range(nbc):
+        h = int(rng.integers(700, 1300))
+        tr[b"ACGT".index(a1[j]), pos[j] - 2: pos[j] + 3] += (h * frac * shape).astype(np.int64)
+        tr[b"ACGT".index(a2[j]), pos[j] - 2: pos[j] + 3] += (h * (1 - frac) * shape).astype(np.int64)
+    if scf:
+        return synth.scf_bytes([tr[k] for k in range(4)], pos)
+    order = b"GATC"
+    return synth.abif_bytes([tr[b"ACGT".index(c)] for c in order], order, pos, bytes(a1[:nbc]), rng.integers(5, 60, nbc))
+
+
+def make_decompose_jobs(root, n=20, seed=4):
+    """n + 3 `tracy decompose` command lines: heterozygous insertions and deletions of 1-25 bp on either strand, homozygous traces (no
+    shift: the homozygous breakpoint search and the nearest-SNP viewport), SNVs, option variants (-i, -t, -q/-u, -l, -c), SCF files,
+    an unrelated trace (exit code -1 with P.abif left behind), a reference that is no FASTA, a missing file."""
+    rng = np.random.default_rng(seed)
+    jobs, argv, kws = [], [], []
+    for i in range(n):
+        g = synth.random_seq(rng, int(rng.integers(1400, 2400)))
+        st, L, bp, ln = int(rng.integers(100, 400)), int(rng.integers(560, 760)), int(rng.integers(180, 380)), int(rng.integers(1, 26))
+        a1 = bytearray(g[st: st + L])
+        if i % 4 == 3:
+            a2 = bytearray(a1)                                                 # homozygous
+        elif i % 2:
+            a2 = bytearray((g[st: st + bp] + g[st + bp + ln:])[:L])             # deletion on the second allele
+        else:
+            a2 = bytearray((g[st: st + bp] + synth.random_seq(rng, ln) + g[st + bp:])[:L])
+        for _ in range(int(rng.integers(0, 4))):
+            a2[int(rng.integers(0, len(a2)))] = b"ACGT"[int(rng.integers(0, 4))]
+        a1, a2 = bytes(a1), bytes(a2)
+        if i % 3 == 1:
+            a1, a2 = a1.translate(COMP)[::-1], a2.translate(COMP)[::-1]
+        if i == n - 1:
+            a1 = a2 = synth.random_seq(rng, 600)                               # matches nothing: alignment below the threshold
+        t = _write(os.path.join(root, f"d{i}.{'scf' if i % 6 == 4 else 'ab1'}"), het_file(rng, a1, a2, [0.6, 0.5, 0.7][i % 3], scf=(i % 6 == 4)))
+        gp = _write(os.path.join(root, f"d{i}.fa"), b">locus%d\n" % i + g + b"\n")
+        kw, av = dict(maxindel=30), ["-i", "30"]
+        if i % 5 == 1:
+            kw, av = dict(maxindel=40, trim_stringency=4.0, linelimit=70), ["-i", "40", "-t", "4", "-l", "70"]
+        elif i % 5 == 2:
+            kw, av = dict(maxindel=30, trim_left=30, trim_right=70, madc=4), ["-i", "30", "-q", "30", "-u", "70", "-c", "4"]
+        jobs.append((t, gp, os.path.join(root, f"d{i}.out")))
+        argv.append(av); kws.append(kw)
+    junk = _write(os.path.join(root, "djunk.txt"), b"not a reference\n")
+    for k, (t, g_, kw, av) in enumerate(((jobs[0][0], junk, dict(maxindel=30), ["-i", "30"]), (os.path.join(root, "dgone.ab1"), jobs[0][1], dict(maxindel=30), ["-i", "30"]),
+                                         (jobs[0][0], jobs[0][1], dict(maxindel=30, trim_left=350, trim_right=350), ["-i", "30", "-q", "350", "-u", "350"]))):
+        jobs.append((t, g_, os.path.join(root, f"dx{k}.out")))
+        argv.append(av); kws.append(kw)
+    return jobs, dict(argv=argv, groups=_group(kws))

@@ -1,12 +1,13 @@
 """Files in -> files out on the GPU: tracy_b200.subcommands (decode, basecall, createProfile and every DP stage as batched CUDA
 calls; readers / writers on host threads) against the reference's OWN subcommand entry points run on the same files behind
 oracle/_ref -- `tracy align` (src/sage.h:58), `tracy consensus` (src/consensus.h:332), `tracy assemble` (src/assemble.h:57) --
-byte for byte over every output file, plus the exit codes. 29 + 22 + 11 command lines."""
+`tracy decompose` (src/indigo.h:42) -- byte for byte over every output file, plus the exit codes. 29 + 22 + 11 + 27 command lines."""
 import pytest
 
 from tracy_b200 import subcommands
 
-from subcmd_cases import ALIGN_SUFFIXES, ASM_SUFFIXES, CONS_SUFFIXES, compare_dirs, make_align_jobs, make_assemble_jobs, make_consensus_jobs
+from subcmd_cases import (ALIGN_SUFFIXES, ASM_SUFFIXES, CONS_SUFFIXES, DEC_SUFFIXES, compare_dirs, make_align_jobs, make_assemble_jobs, make_consensus_jobs,
+                          make_decompose_jobs)
 
 pytestmark = pytest.mark.gpu
 
@@ -47,3 +48,14 @@ def test_assemble_files_gpu(ctx, oracle_ref, tmp_path):
         assert got == [want[i] for i in idx], (kw, got, [want[i] for i in idx])
     assert want.count(0) >= 8 and -1 in want and 1 in want
     assert compare_dirs([o for _, _, o in jobs], ASM_SUFFIXES) >= 4 * 8
+
+
+def test_decompose_files_gpu(ctx, oracle_ref, tmp_path):
+    _need_ref(oracle_ref)
+    jobs, opts = make_decompose_jobs(str(tmp_path), n=24, seed=104)
+    want = [oracle_ref.subcommand("decompose", ["-r", g, "-o", o + ".ref"] + extra + [t]) for (t, g, o), extra in zip(jobs, opts["argv"])]
+    for kw, idx in opts["groups"]:
+        got = subcommands.decompose(ctx, [jobs[i] for i in idx], chunk=5, **kw)
+        assert got == [want[i] for i in idx], (kw, got, [want[i] for i in idx])
+    assert want.count(0) >= 20 and -1 in want and 1 in want
+    assert compare_dirs([o for _, _, o in jobs], DEC_SUFFIXES) >= 6 * 20

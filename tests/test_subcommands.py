@@ -1,5 +1,6 @@
 """Files in -> files out: tracy_b200.subcommands against the reference's OWN subcommand entry points (`int sage(argc, argv)`,
-`int consensus(argc, argv)`, `int assemble(argc, argv)`, src/sage.h:58 / src/consensus.h:332 / src/assemble.h:57, run unmodified behind oracle/_ref on the same input files),
+`int consensus(argc, argv)`, `int assemble(argc, argv)`, `int indigo(argc, argv)`, src/sage.h:58 / src/consensus.h:332 /
+src/assemble.h:57 / src/indigo.h:42, run unmodified behind oracle/_ref on the same input files),
 byte for byte over every output file plus the exit codes. CPU suite: the pipeline's DP calls are served by the reference's
 functions (tests/refctx.py), so what is checked here is the file plumbing, option handling, exit codes, pairwiseConsensus and
 the writers; tests/test_gpu_subcommands.py runs the same comparison on the CUDA kernels."""
@@ -10,7 +11,8 @@ import pytest
 
 from tracy_b200 import subcommands, synth
 
-from subcmd_cases import ALIGN_SUFFIXES, ASM_SUFFIXES, CONS_SUFFIXES, compare_dirs, make_align_jobs, make_assemble_jobs, make_consensus_jobs
+from subcmd_cases import (ALIGN_SUFFIXES, ASM_SUFFIXES, CONS_SUFFIXES, DEC_SUFFIXES, compare_dirs, make_align_jobs, make_assemble_jobs, make_consensus_jobs,
+                          make_decompose_jobs)
 
 
 @pytest.fixture(scope="module")
@@ -49,6 +51,16 @@ def test_assemble_files_vs_reference_main(refctx, oracle_ref, tmp_path):
         assert got == [want[i] for i in idx], (kw, got, [want[i] for i in idx])
     assert 0 in want and -1 in want and 1 in want
     assert compare_dirs([o for _, _, o in jobs], ASM_SUFFIXES) >= 12
+
+
+def test_decompose_files_vs_reference_main(refctx, oracle_ref, tmp_path):
+    jobs, opts = make_decompose_jobs(str(tmp_path), n=8, seed=14)
+    want = [oracle_ref.subcommand("decompose", ["-r", g, "-o", o + ".ref"] + extra + [t]) for (t, g, o), extra in zip(jobs, opts["argv"])]
+    for kw, idx in opts["groups"]:
+        got = subcommands.decompose(refctx, [jobs[i] for i in idx], chunk=3, **kw)
+        assert got == [want[i] for i in idx], (kw, got, [want[i] for i in idx])
+    assert want.count(0) >= 6 and -1 in want and 1 in want
+    assert compare_dirs([o for _, _, o in jobs], DEC_SUFFIXES) >= 6 * 6
 
 
 def test_load_single_fasta_rules():

@@ -399,3 +399,84 @@ def _assemble_out(prefix, names, fwd, rows, row_of, r, ts, inc_cons, fmt, refere
             acgt, nbc = rv["acgt"], rv
         padded.append(writers.alignment_trace_padding(rows[row_of[q]], acgt, nbc["bcpos"], nbc["qual"], nbc["primary"], nbc["secondary"], nbc["consensus"]))
     _Writers.write(prefix, writers.assemble_files(names, fwd, rows, r["gapped"], r["consensus"], r["quality"], padded, inc_cons, fmt, reference_last))
+
+
+# ---- tracy decompose -----------------------------------------------------------------------------------------------------------
+def decompose(ctx, jobs, pratio=0.33, trim_stringency=0.0, trim_left=50, trim_right=50, maxindel=1000, madc=5, qual_cut=45, linelimit=60,
+              sc=DnaScore(3, -5, -10, -4), chunk=256, workers=4):
+    """`tracy decompose -r <reference.fa> -o <outprefix> <trace>` (reference src/indigo.h:42-455, without -v / -a) for every job =
+    (trace path, single-FASTA reference path, outprefix). Writes outprefix.abif, .decomp, .align1, .align2, .align3 and .json; returns the
+    reference's exit codes (0; 1 missing file; -1 unreadable trace, trims larger than the trace, reference that is no single FASTA of at
+    most 50 kbp, alignment below the score threshold, no usable breakpoint). Every DP / sweep / fit stage of a chunk of jobs is one
+    batched GPU call (drivers.decompose_batch); P.bcf (-v) needs htslib and is not written. Wildtype-trace and indexed-genome
+    references are not file formats of this function (drivers.align_genome_batch anchors traces in a genome)."""
+    rc = [0] * len(jobs)
+    wr = _Writers(workers)
+    trim_stringency = min(float(trim_stringency), 9.0)                       # src/indigo.h:106
+    maxindel = max(int(maxindel), 1)                                         # :103
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as readers, ThreadPoolExecutor(max_workers=1) as lookahead:
+        parts = _chunks(len(jobs), chunk)
+        ahead = None
+
+        def fetch(part):
+            return list(readers.map(_read, [jobs[i][0] for i in part] + [jobs[i][1] for i in part]))
+
+        for pi, part in enumerate(parts):
+            blobs = ahead.result() if ahead is not None else fetch(part)
+            ahead = lookahead.submit(fetch, parts[pi + 1]) if pi + 1 < len(parts) else None
+            k = len(part)
+            tblob, gblob = blobs[:k], blobs[k:]
+            for j, i in enumerate(part):                                     # trace first, then the reference: src/indigo.h:124-134
+                if not tblob[j] or not gblob[j]:
+                    rc[i] = 1
+            traces = _load_traces(ctx, [b if rc[i] == 0 else None for b, i in zip(tblob, part)], pratio)
+            groups = {}
+            for j, i in enumerate(part):
+                if rc[i]:
+                    continue
+                t = traces[j]
+                if t is None:
+                    rc[i] = -1
+                    continue
+                t["tl"], t["tr"] = _trims(t, trim_stringency, trim_left, trim_right)
+                if t["tl"] + t["tr"] >= len(t["bcpos"]):
+                    rc[i] = -1
+                    continue
+                wr.submit(_abif_only, jobs[i][2], t)                         # traceTxtOut with the ORIGINAL basecalls, src/indigo.h:187
+                fa = load_single_fasta(gblob[j]) if genome_type(gblob[j]) == 1 else None
+                if fa is None or len(fa[1]) > MAX_SINGLE_FASTA_SIZE:
+                    rc[i] = -1
+                    continue
+                t["fa"] = fa
+                groups.setdefault((t["tl"], t["tr"]), []).append(j)
+            for (tl, trr), idx in groups.items():
+                ts = [traces[j] for j in idx]
+                res = drivers.decompose_batch(ctx, [t["acgt"] for t in ts], [t["bcpos"] for t in ts], [t["primary"] for t in ts], [t["secondary"] for t in ts],
+                                              [t["fa"][1] for t in ts], sc, tl, trr, maxindel, madc)
+                for j, t, r in zip(idx, ts, res):
+                    i = part[j]
+                    if r is None:
+                        rc[i] = -1                                           # "Alignment of trace to reference failed!" / no breakpoint
+                        continue
+                    wr.submit(_decompose_out, jobs[i], t, r, dict(trim_left=tl, trim_right=trr, qual_cut=qual_cut, pratio=pratio, input=jobs[i][0], genome=jobs[i][1]),
+                              linelimit)
+    wr.drain()
+    return rc
+
+
+def _decompose_out(job, t, r, cfg, linelimit):
+    tl, trr = cfg["trim_left"], cfg["trim_right"]
+    chr_name = t["fa"][0].encode("latin-1")
+    bp = r["breakpoint"]
+    breakpoint = bp["breakpoint"]
+    if not bp["indelshift"]:                                                 # centre the viewport on the first SNP, src/indigo.h:391-395
+        _, _, best = trim.trace_quality(t["bcpos"], r["secondary"], None, best=True)
+        breakpoint = trim.nearest_snp(r["primary"], r["secondary"], tl, trr, best)
+    a1, a2, a3 = r["align1"], r["align2"], r["align3"]
+    allele1 = (a1["row0"], a1["row1"], chr_name, a1["pos"], r["forward"], a1["score"])
+    allele2 = (a2["row0"], a2["row1"], chr_name, a2["pos"], r["forward"], a2["score"])
+    files = writers.decompose_files(cfg, t["acgt"], t["bcpos"], t["qual"], r["primary"], r["secondary"], t["consensus"], r["decomp"], [], allele1, allele2,
+                                    (a3["row0"], a3["row1"], a3["score"]), (len(a1["refslice"]), len(a2["refslice"])), bp["indelshift"], breakpoint,
+                                    r["allele_fractions"], linelimit)
+    files.pop(".abif")                                                       # already written with the basecalls as they were before the decomposition
+    _Writers.write(job[2], files)

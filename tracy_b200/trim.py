@@ -185,9 +185,10 @@ def nearest_snp(primary, secondary, trim_left, trim_right, rtp):
     return rtp - trim_left if rtp > trim_left else trim_left
 
 
-def trace_quality(bcpos, secondary, trim_stringency=None):
+def trace_quality(bcpos, secondary, trim_stringency=None, best=False):
     """estimate_qualities (+ trim_trace when a stringency is given) through the native tb_trace_quality (csrc/trimq.cu): the same
-    numbers, without the interpreter in the per-basecall loops. Returns (qual uint8[n], (left, right) or None)."""
+    numbers, without the interpreter in the per-basecall loops. Returns (qual uint8[n], (left, right) or None); with best=True a
+    third value, findBestTraceSection(bc) (src/abif.h:221-229)."""
     import ctypes as C
     from . import capi
     pos = np.ascontiguousarray(bcpos, np.int32)
@@ -196,8 +197,10 @@ def trace_quality(bcpos, secondary, trim_stringency=None):
     qual = np.zeros(n, np.uint8)
     left, right = C.c_uint32(0), C.c_uint32(0)
     want = trim_stringency is not None
-    rc = capi.lib().tb_trace_quality(pos.ctypes.data, sec, n, float(trim_stringency or 0.0), qual.ctypes.data, None, C.byref(left) if want else None,
+    bs = C.c_uint32(0)
+    rc = capi.lib().tb_trace_quality(pos.ctypes.data, sec, n, float(trim_stringency or 0.0), qual.ctypes.data, C.byref(bs), C.byref(left) if want else None,
                                      C.byref(right) if want else None)
     if rc != capi.TB_OK:
         raise ValueError("tb_trace_quality: %d" % rc)
-    return qual, ((int(left.value), int(right.value)) if want else None)
+    lr = (int(left.value), int(right.value)) if want else None
+    return (qual, lr, int(bs.value)) if best else (qual, lr)

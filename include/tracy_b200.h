@@ -341,6 +341,20 @@ int tb_write_align_files(const char* prefix, const char* trace_name, const tb_tr
                          const char* row1, int32_t L, const char* chr, uint32_t pos, int32_t refslice_len, int32_t forward, int32_t score,
                          int32_t linelimit);
 
+/* P.json of `tracy decompose` (traceAlleleAlignJsonOut, reference src/json.h:260-381; the variant table stays empty: -v needs the BCF
+ * writer) and P.decomp (writeDecomposition, src/decompose.h:621-627). t: the trace with the basecalls AFTER decomposeAlleles.
+ * viewport_basecall: the basecall the chart is centred on (trimLeft + bp.breakpoint); decomp: ndecomp (indel, count) pairs. */
+typedef struct {
+  int32_t trim_left, trim_right; float pratio; const char* genome; const char* input;     /* the "meta" block: file NAMES, no directories */
+  int32_t viewport_basecall;
+  const char* chr1; uint32_t pos1; const char* alt1; const char* ref1; int32_t L1, forward1, score1;   /* allele 1 vs its reference slice */
+  const char* chr2; uint32_t pos2; const char* alt2; const char* ref2; int32_t L2, forward2, score2;   /* allele 2 */
+  double a1, a2; const char* a3row0; const char* a3row1; int32_t L3, score3;                           /* fractions; allele 1 vs allele 2 */
+  int32_t hetindel; const int32_t* decomp; int32_t ndecomp;
+} tb_decompose_json;
+int tb_write_decompose_json(const char* path, const tb_trace_view* t, const tb_decompose_json* d);
+int tb_write_decomposition(const char* path, const int32_t* decomp, int32_t n);
+
 /* ---- several GPUs of one node behind one handle (BASELINE.json configs[4]; csrc/multi.cu) ----------------------------------------
  * One context per device, owned by the handle; each call cuts its batch into contiguous ranges of equal DP cost, runs every range
  * through its device's own pipeline on its own host thread and lets each device write its slice of the caller's result arrays (the

@@ -288,3 +288,41 @@ def test_native_writers_equal_python_writers(tmp_path):
                 assert fh.read() == writers.plot_alignment(row0, row1, b"chrX", pos, reflen, fwd, score, key, (0.37, 0.6300000001), ll).encode("latin-1"), (it, key)
     # invalid arguments are refused, nothing is written
     assert L.tb_write_trace_txt(str(tmp_path / "x").encode(), None, 0, 0) == 1
+
+
+def test_native_decompose_writers_equal_python_writers(tmp_path):
+    """tb_write_decompose_json / tb_write_decomposition / tb_write_plot_alignment (keys 1-3) against writers.decompose_files (pinned on the
+    reference's traceAlleleAlignJsonOut, writeDecomposition, plotAlignment) with an empty variant list."""
+    rng = np.random.default_rng(78)
+    for it in range(25):
+        nbc = int(rng.integers(2, 150))
+        ns = 12 * nbc + int(rng.integers(5, 40))
+        acgt = rng.integers(0, 3000, size=(4, ns)).astype(np.int32)
+        bcpos = np.sort(rng.choice(np.arange(2, ns - 1), size=nbc, replace=False)).astype(np.int32)
+        qual = rng.integers(0, 61, nbc).astype(np.uint8)
+        pri = bytes(rng.choice(list(b"ACGTN"), nbc).astype(np.uint8))
+        sec = bytes(rng.choice(list(b"ACGTRYKMSWNB"), nbc).astype(np.uint8))
+        con = bytes(rng.choice(list(b"ACGTN"), nbc).astype(np.uint8))
+
+        def rows(n):
+            a = bytes(rng.choice(list(b"ACGT-"), n, p=[.23, .23, .23, .23, .08]).astype(np.uint8))
+            b = bytes(rng.choice(list(b"ACGT-"), n, p=[.23, .23, .23, .23, .08]).astype(np.uint8))
+            return a, b
+        r10, r11 = rows(int(rng.integers(1, 400)))
+        r20, r21 = rows(int(rng.integers(1, 400)))
+        r30, r31 = rows(int(rng.integers(1, 300)))
+        tl, trr = int(rng.integers(0, max(nbc // 3, 1))), int(rng.integers(0, max(nbc // 3, 1)))
+        bp = int(rng.integers(0, max(nbc - tl, 1)))
+        decomp = [(int(-i), int(rng.integers(0, 300))) for i in range(int(rng.integers(0, 30)), -1, -1)] + [(i, int(rng.integers(0, 300))) for i in range(1, int(rng.integers(1, 30)))]
+        cfg = dict(trim_left=tl, trim_right=trr, qual_cut=45, pratio=[0.33, 0.5, 0.1][it % 3], input="/some/dir/trace%d.ab1" % it, genome="ref%d.fa" % it)
+        a1 = (r10, r11, b"chr%d" % it, int(rng.integers(0, 10 ** 6)), bool(it % 2), int(rng.integers(-100, 3000)))
+        a2 = (r20, r21, b"chr%d" % it, int(rng.integers(0, 10 ** 6)), bool(it % 2), int(rng.integers(-100, 3000)))
+        a3 = (r30, r31, int(rng.integers(-100, 3000)))
+        fr = (float(rng.integers(0, 101)) / 100, float(rng.integers(0, 101)) / 100 + 1e-9 * it)
+        lens = (len(r11) - r11.count(b"-"), len(r21) - r21.count(b"-"))
+        prefix = str(tmp_path / f"d{it}")
+        writers.write_decompose_files(prefix, cfg, acgt, bcpos, qual, pri, sec, con, decomp, a1, a2, a3, lens, bool(it % 3), bp, fr, [60, 75][it % 2])
+        want = writers.decompose_files(cfg, acgt, bcpos, qual, pri, sec, con, decomp, [], a1, a2, a3, lens, bool(it % 3), bp, fr, [60, 75][it % 2])
+        for sfx in (".decomp", ".align1", ".align2", ".align3", ".json"):
+            with open(prefix + sfx, "rb") as fh:
+                assert fh.read() == want[sfx].encode("latin-1"), (it, sfx)

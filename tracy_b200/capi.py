@@ -21,6 +21,7 @@ SYMBOLS = [
     "tb_multi_create", "tb_multi_destroy", "tb_multi_size", "tb_multi_ctx", "tb_multi_last_error", "tb_multi_partition", "tb_multi_gotoh",
     "tb_multi_index_build", "tb_multi_anchor",
     "tb_write_trace_txt", "tb_write_align_fasta", "tb_write_plot_alignment", "tb_write_trace_align_json", "tb_write_align_files", "tb_trace_quality",
+    "tb_write_decompose_json", "tb_write_decomposition",
 ]
 
 
@@ -69,6 +70,15 @@ class TraceView(C.Structure):
                 ("secondary", C.c_void_p), ("consensus", C.c_void_p), ("nbc", C.c_int32)]
 
 
+class DecomposeJson(C.Structure):
+    _fields_ = [("trim_left", C.c_int32), ("trim_right", C.c_int32), ("pratio", C.c_float), ("genome", C.c_char_p), ("input", C.c_char_p),
+                ("viewport_basecall", C.c_int32),
+                ("chr1", C.c_char_p), ("pos1", C.c_uint32), ("alt1", C.c_char_p), ("ref1", C.c_char_p), ("L1", C.c_int32), ("forward1", C.c_int32), ("score1", C.c_int32),
+                ("chr2", C.c_char_p), ("pos2", C.c_uint32), ("alt2", C.c_char_p), ("ref2", C.c_char_p), ("L2", C.c_int32), ("forward2", C.c_int32), ("score2", C.c_int32),
+                ("a1", C.c_double), ("a2", C.c_double), ("a3row0", C.c_char_p), ("a3row1", C.c_char_p), ("L3", C.c_int32), ("score3", C.c_int32),
+                ("hetindel", C.c_int32), ("decomp", C.c_void_p), ("ndecomp", C.c_int32)]
+
+
 class AnchorConfig(C.Structure):
     _fields_ = [("trim_left", C.c_int32), ("trim_right", C.c_int32), ("kmer", C.c_int32), ("min_kmer_support", C.c_int32)]
 
@@ -114,6 +124,8 @@ def lib():
     L.tb_host_free.argtypes = [vp, vp]
     L.tb_ctx_set_scratch_limit.argtypes = [vp, C.c_size_t]
     L.tb_trace_quality.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_float, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.tb_write_decompose_json.argtypes = [C.c_char_p, C.POINTER(TraceView), C.POINTER(DecomposeJson)]
+    L.tb_write_decomposition.argtypes = [C.c_char_p, C.c_void_p, C.c_int32]
     L.tb_write_trace_txt.argtypes = [C.c_char_p, C.POINTER(TraceView), C.c_int32, C.c_int32]
     L.tb_write_align_files.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(TraceView), C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p,
                                        C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]

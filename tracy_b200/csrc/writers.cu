@@ -1,6 +1,7 @@
 // The output files of `tracy align` for one trace, formatted and written by native code (host only, no kernel): P.abif
 // (traceTxtOut, reference src/abif.h:512-534), P.align.fa (src/sage.h:326-339), P.txt (plotAlignment, src/fmindex.h:329-420) and
-// P.json (alignmentTracePadding + assemblyTrace + traceAlignJsonOut, src/json.h:120-217, 383-479). ~390 KB of text per trace: as
+// P.json (alignmentTracePadding + assemblyTrace + traceAlignJsonOut, src/json.h:120-217, 383-479); for `tracy decompose` P.decomp
+// (writeDecomposition, src/decompose.h:621-627) and P.json without variant rows (traceAlleleAlignJsonOut, src/json.h:260-381). ~390 KB of text per trace: as
 // Python string code this was what bounded the files-in -> files-out pipeline (46 traces/s behind GPU stages that take milliseconds);
 // here a writer thread formats one trace into one buffer and hands it to fwrite without holding any interpreter lock, so the
 // writers of a batch run on as many host cores as the caller gives them, underneath the GPU stages of the next chunk.
@@ -156,6 +157,49 @@ void gapped_trace(Buf& o, const tb_trace_view& t, const char* row, int32_t L, co
   o.str("}\n}\n");
 }
 
+const char* iupac_expanded(char c) {              // the "|"-joined bases of an ambiguity code as the basecall JSON prints them (src/json.h:86-100)
+  switch (c) {
+    case 'A': return "A"; case 'C': return "C"; case 'G': return "G"; case 'T': return "T"; case 'N': return "N";
+    case 'R': return "A|G"; case 'Y': return "C|T"; case 'S': return "C|G"; case 'W': return "A|T"; case 'K': return "G|T"; case 'M': return "A|C";
+  }
+  return "N";
+}
+
+// the body of traceJsonOut (src/json.h:32-117) between its braces: pos, peaks, basecallPos, basecallQual, basecalls, the two sequences
+void trace_json_body(Buf& o, const tb_trace_view& t) {
+  const int32_t ns = t.nsamples;
+  o.str("\"pos\": [");
+  for (int32_t i = 0; i < ns; ++i) { if (i) o.str(", "); o.num(i + 1); }
+  o.str("],\n");
+  for (int c = 0; c < 4; ++c) {
+    o.str("\"peak"); o.ch("ACGT"[c]); o.str("\": [");
+    for (int32_t i = 0; i < ns; ++i) { if (i) o.str(", "); o.num(t.acgt[(size_t)c * ns + i]); }
+    o.str("],\n");
+  }
+  std::vector<std::pair<int32_t, int32_t> > calls;
+  for_called(ns, t.bcpos, t.nbc, [&](int32_t i, int32_t k) { calls.push_back(std::make_pair(i, k)); });
+  o.str("\"basecallPos\": [");
+  for (size_t i = 0; i < calls.size(); ++i) { if (i) o.str(", "); o.num(calls[i].first + 1); }
+  o.str("],\n\"basecallQual\": [");
+  for (size_t i = 0; i < calls.size(); ++i) { if (i) o.str(", "); o.num(t.qual[calls[i].second]); }
+  o.str("],\n\"basecalls\": {");
+  for (size_t i = 0; i < calls.size(); ++i) {
+    const int32_t k = calls[i].second;
+    if (i) o.str(", ");
+    o.ch('"'); o.num(calls[i].first + 1); o.str("\":\""); o.num(k + 1); o.ch(':'); o.ch(t.primary[k]);
+    if (t.primary[k] != t.secondary[k]) { o.ch('|'); o.str(iupac_expanded(t.secondary[k])); }
+    o.ch('"');
+  }
+  o.str("},\n\"primarySeq\": \""); o.str(t.primary, (size_t)t.nbc); o.str("\",\n\"secondarySeq\": \""); o.str(t.secondary, (size_t)t.nbc); o.str("\"\n");
+}
+
+void viewport(const tb_trace_view& t, int32_t k, long long* lb, long long* ub) {   // xWindowViewport, src/json.h:249-258
+  long long l = (long long)t.bcpos[k] + 1, u = l;
+  const long long last = t.bcpos[t.nbc - 1];
+  *lb = l <= 150 ? 1 : l - 150;
+  *ub = u + 150 < last ? u + 150 : last;
+}
+
 void ungapped_wrapped(Buf& o, const char* row, int32_t L, int fald) {
   int count = 0;
   for (int32_t j = 0; j < L; ++j)
@@ -248,6 +292,51 @@ int tb_write_align_files(const char* prefix, const char* trace_name, const tb_tr
   if (rc == TB_OK) rc = tb_write_plot_alignment((p + ".txt").c_str(), row0, row1, L, chr, pos, refslice_len, forward, score, 0, 0.0, 0.0, linelimit);
   if (rc == TB_OK) rc = tb_write_trace_align_json((p + ".json").c_str(), t, row0, row1, L, chr, pos, forward);
   return rc;
+}
+
+int tb_write_decompose_json(const char* path, const tb_trace_view* t, const tb_decompose_json* d) {
+  if (!path || !view_ok(t) || !d || !d->genome || !d->input || !d->chr1 || !d->chr2 || !d->alt1 || !d->ref1 || !d->alt2 || !d->ref2 || !d->a3row0 || !d->a3row1 ||
+      d->L1 < 0 || d->L2 < 0 || d->L3 < 0 || d->ndecomp < 0 || (d->ndecomp && !d->decomp) || d->viewport_basecall < 0 || d->viewport_basecall >= t->nbc)
+    return TB_ERR_INVALID;
+  Buf o;
+  o.s.reserve((size_t)t->nsamples * 36 + 8192);
+  o.str("{\n\"meta\": {\"program\": \"tracy\", \"version\": \"0.9.1\", \"arguments\": {\"trimLeft\": "); o.num(d->trim_left);
+  o.str(", \"trimRight\": "); o.num(d->trim_right); o.str(", \"pratio\": "); fmt_g(o, (double)d->pratio);
+  o.str(", \"genome\": \""); o.str(d->genome); o.str("\", \"input\": \""); o.str(d->input); o.str("\"}},\n");
+  trace_json_body(o, *t);
+  o.str(",\n");
+  long long lb, ub;
+  viewport(*t, d->viewport_basecall, &lb, &ub);
+  o.str("\"chartConfig\": { \"x\": { \"axis\": { \"range\": ["); o.num(lb); o.str(", "); o.num(ub); o.str("] }}},\n");
+  const char* chr[2] = {d->chr1, d->chr2};
+  const char* alt[2] = {d->alt1, d->alt2};
+  const char* ref[2] = {d->ref1, d->ref2};
+  const int32_t LL[2] = {d->L1, d->L2}, fw[2] = {d->forward1, d->forward2}, sc[2] = {d->score1, d->score2};
+  const uint32_t ps[2] = {d->pos1, d->pos2};
+  for (int n = 0; n < 2; ++n) {
+    const char tag = (char)('1' + n);
+    o.str("\"ref"); o.ch(tag); o.str("chr\": \""); o.str(chr[n]); o.str("\",\n\"ref"); o.ch(tag); o.str("pos\": "); o.num((long long)ps[n] + 1);
+    o.str(",\n\"alt"); o.ch(tag); o.str("align\": \""); o.str(alt[n], (size_t)LL[n]); o.str("\",\n\"ref"); o.ch(tag); o.str("align\": \""); o.str(ref[n], (size_t)LL[n]);
+    o.str("\",\n\"ref"); o.ch(tag); o.str("forward\": "); o.num(fw[n] ? 1 : 0); o.str(",\n\"align"); o.ch(tag); o.str("score\": "); o.num(sc[n]); o.str(",\n");
+  }
+  o.str("\"allele1fraction\": "); fmt_g(o, d->a1); o.str(",\n\"allele1align\": \""); o.str(d->a3row0, (size_t)d->L3);
+  o.str("\",\n\"allele2fraction\": "); fmt_g(o, d->a2); o.str(",\n\"allele2align\": \""); o.str(d->a3row1, (size_t)d->L3);
+  o.str("\",\n\"align3score\": "); o.num(d->score3); o.str(",\n\"hetindel\": "); o.num(d->hetindel ? 1 : 0);
+  o.str(",\n\"decomposition\": {\n\"x\": [");
+  for (int32_t i = 0; i < d->ndecomp; ++i) { if (i) o.str(", "); o.num(d->decomp[2 * i]); }
+  o.str("],\n\"y\": [");
+  for (int32_t i = 0; i < d->ndecomp; ++i) { if (i) o.str(", "); o.num(d->decomp[2 * i + 1]); }
+  o.str("]\n},\n\"variants\": {\n\"columns\": [\"chr\", \"pos\", \"id\", \"ref\", \"alt\", \"qual\", \"filter\", \"type\", \"genotype\", \"basepos\", \"signalpos\"],\n\"rows\": [\n");
+  o.str("],\n\"xranges\": [\n]\n}\n}\n");         // no -v: the variant table is empty
+  return flush_to(path, o);
+}
+
+int tb_write_decomposition(const char* path, const int32_t* decomp, int32_t n) {
+  if (!path || n < 0 || (n && !decomp)) return TB_ERR_INVALID;
+  Buf o;
+  o.str("indel\tdecomp\n");
+  for (int32_t i = 0; i < n; ++i) { o.num(decomp[2 * i]); o.ch('\t'); o.num(decomp[2 * i + 1]); o.ch('\n'); }
+  return flush_to(path, o);
 }
 
 }  // extern "C"

@@ -475,8 +475,8 @@ def _decompose_out(job, t, r, cfg, linelimit):
     a1, a2, a3 = r["align1"], r["align2"], r["align3"]
     allele1 = (a1["row0"], a1["row1"], chr_name, a1["pos"], r["forward"], a1["score"])
     allele2 = (a2["row0"], a2["row1"], chr_name, a2["pos"], r["forward"], a2["score"])
-    files = writers.decompose_files(cfg, t["acgt"], t["bcpos"], t["qual"], r["primary"], r["secondary"], t["consensus"], r["decomp"], [], allele1, allele2,
-                                    (a3["row0"], a3["row1"], a3["score"]), (len(a1["refslice"]), len(a2["refslice"])), bp["indelshift"], breakpoint,
-                                    r["allele_fractions"], linelimit)
-    files.pop(".abif")                                                       # already written with the basecalls as they were before the decomposition
-    _Writers.write(job[2], files)
+    # P.abif was written with the basecalls as they were before the decomposition; the rest through the native writers (same bytes as
+    # writers.decompose_files with an empty variant list)
+    writers.write_decompose_files(job[2], cfg, t["acgt"], t["bcpos"], t["qual"], r["primary"], r["secondary"], t["consensus"], r["decomp"], allele1, allele2,
+                                  (a3["row0"], a3["row1"], a3["score"]), (len(a1["refslice"]), len(a2["refslice"])), bp["indelshift"], breakpoint,
+                                  r["allele_fractions"], linelimit)

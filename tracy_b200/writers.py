@@ -410,3 +410,33 @@ def write_trace_txt(path, acgt, bcpos, qual, primary, secondary, consensus, trim
     rc = capi.lib().tb_write_trace_txt(os.fsencode(path), C.byref(v), int(trim_left), int(trim_right))
     if rc != capi.TB_OK:
         raise OSError("tb_write_trace_txt(%s): %d" % (path, rc))
+
+
+def write_decompose_files(prefix, cfg, acgt, bcpos, qual, primary, secondary, consensus, decomp, allele1, allele2, align3, refslice_lens, indelshift, breakpoint, a1a2,
+                          linelimit=60):
+    """P.decomp, P.align1 / .align2 / .align3 and P.json of `tracy decompose -o prefix` (the files decompose_files returns as text, without
+    P.abif and with an empty variant table), written by the native writers. Arguments as decompose_files."""
+    import ctypes as C
+    from . import capi
+    L = capi.lib()
+    b = lambda x: x.encode("latin-1") if isinstance(x, str) else bytes(x)
+    v, keep = _trace_view(acgt, bcpos, qual, primary, secondary, consensus)
+    dc = np.ascontiguousarray(np.asarray(decomp, np.int32).reshape(-1, 2))
+    pre = os.fsencode(prefix)
+    ok = L.tb_write_decomposition(pre + b".decomp", dc.ctypes.data, dc.shape[0]) == 0
+    for key, (al, rl) in enumerate(((allele1, refslice_lens[0]), (allele2, refslice_lens[1])), start=1):
+        r0, r1 = b(al[0]), b(al[1])
+        ok = ok and L.tb_write_plot_alignment(pre + (".align%d" % key).encode(), r0, r1, len(r0), b(al[2]), int(al[3]), int(rl), int(bool(al[4])), int(al[5]), key,
+                                              float(a1a2[0]), float(a1a2[1]), int(linelimit)) == 0
+    x0, x1 = b(align3[0]), b(align3[1])
+    ok = ok and L.tb_write_plot_alignment(pre + b".align3", x0, x1, len(x0), b"Alt2", 0, len(x1.replace(b"-", b"")), 1, int(align3[2]), 3, float(a1a2[0]),
+                                          float(a1a2[1]), int(linelimit)) == 0
+    a1r0, a1r1, a2r0, a2r1 = b(allele1[0]), b(allele1[1]), b(allele2[0]), b(allele2[1])
+    d = capi.DecomposeJson(int(cfg["trim_left"]), int(cfg["trim_right"]), float(cfg["pratio"]), str(cfg["genome"]).rsplit("/", 1)[-1].encode("latin-1"),
+                           str(cfg["input"]).rsplit("/", 1)[-1].encode("latin-1"), int(cfg["trim_left"]) + int(breakpoint),
+                           b(allele1[2]), int(allele1[3]), a1r0, a1r1, len(a1r0), int(bool(allele1[4])), int(allele1[5]),
+                           b(allele2[2]), int(allele2[3]), a2r0, a2r1, len(a2r0), int(bool(allele2[4])), int(allele2[5]),
+                           float(a1a2[0]), float(a1a2[1]), x0, x1, len(x0), int(align3[2]), int(bool(indelshift)), dc.ctypes.data, dc.shape[0])
+    ok = ok and L.tb_write_decompose_json(pre + b".json", C.byref(v), C.byref(d)) == 0
+    if not ok:
+        raise OSError("native decompose writers failed for %s" % prefix)

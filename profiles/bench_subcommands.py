@@ -24,6 +24,17 @@ with tempfile.TemporaryDirectory() as d:
         out[f"align_workers{workers}"] = {"jobs": len(jobs), "ok": rc.count(0), "seconds": dt, "traces_per_s": len(jobs) / dt, "output_MB": nbytes / 1e6,
                                           "kernel_launches": ctx.stats()["kernel_launches"] - st0["kernel_launches"]}
     out["generate_inputs_s"] = gen
+    # tracy decompose: heterozygous traces (indels of 1-25 bp) against ~2 kb FASTA references, -i 30; six output files per trace
+    from subcmd_cases import make_decompose_jobs
+    djobs, _ = make_decompose_jobs(d, n=min(N, 1200), seed=9)
+    djobs = [j for j in djobs if os.path.exists(j[0]) and j[1].endswith(".fa")]
+    subcommands.decompose(ctx, djobs[:32], maxindel=30, chunk=32)
+    for workers in (8,):
+        st0 = ctx.stats(); t0 = time.perf_counter()
+        rc = subcommands.decompose(ctx, djobs, maxindel=30, chunk=512, workers=workers)
+        dt = time.perf_counter() - t0
+        out[f"decompose_workers{workers}"] = {"jobs": len(djobs), "ok": rc.count(0), "seconds": dt, "traces_per_s": len(djobs) / dt,
+                                              "kernel_launches": ctx.stats()["kernel_launches"] - st0["kernel_launches"]}
     from oracle import loader                                                      # the reference's own `tracy align` on a sample of the same files, one core
     ref = loader.ref()
     if ref is not None:
@@ -32,4 +43,10 @@ with tempfile.TemporaryDirectory() as d:
         dt = time.perf_counter() - t0
         out["reference_one_core"] = {"jobs": 24, "ok": rc.count(0), "seconds": dt, "traces_per_s": 24 / dt,
                                      "what": "tracy::sage(argc, argv) of the unmodified reference (oracle/_ref) on the first 24 jobs"}
+    if ref is not None:
+        t0 = time.perf_counter()
+        rc = [ref.subcommand("decompose", ["-r", g, "-o", o + ".ref", "-i", "30", t]) for t, g, o in djobs[:12]]
+        dt = time.perf_counter() - t0
+        out["reference_decompose_one_core"] = {"jobs": 12, "ok": rc.count(0), "seconds": dt, "traces_per_s": 12 / dt,
+                                               "what": "tracy::indigo(argc, argv) of the unmodified reference on the first 12 jobs"}
 print(json.dumps(out, indent=1))

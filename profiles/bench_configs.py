@@ -25,6 +25,13 @@ a1, a2 = tracy_b200.uniform_profiles(prof), tracy_b200.uniform_seqs(win)
 t = timed(lambda: ctx.gotoh("ps", a1, a2, sc, AlignConfig(True, False), traceback=False))
 k = ctx.last_kernel_ms()
 out["ps_score_only_1000x4000"] = {"pairs": N, "host_call_gcups": N * m * n / t / 1e9, "kernel_gcups": N * m * n / ((k["packed_ms"] + k["general_ms"]) * 1e-3) / 1e9}
+# the same call with the batch in page-locked memory (Context.pinned_empty = tb_host_alloc)
+pp_, pw_ = ctx.pinned_empty(prof.shape, np.float32), ctx.pinned_empty(win.shape, np.uint8)
+pp_[:] = prof; pw_[:] = win
+b1, b2 = tracy_b200.uniform_profiles(pp_), tracy_b200.uniform_seqs(pw_)
+ps_ = ctx.pinned_empty((N,), np.int32)
+t = timed(lambda: ctx.gotoh("ps", b1, b2, sc, AlignConfig(True, False), traceback=False, out=(ps_, None, None)))
+out["ps_score_only_1000x4000"]["host_call_gcups_pinned"] = N * m * n / t / 1e9
 
 # string x string with traceback (allele alignments of decompose)
 N2 = 4000

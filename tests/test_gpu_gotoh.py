@@ -184,3 +184,28 @@ def test_single_pair_mirrors(ctx, oracle_port):
     s, rows = tracy_b200.gotoh("ACGTACGT", "ACGACGT", AlignConfig(), DnaScore(), ctx=ctx)
     ws, wops = oracle_port.gotoh_ss(b"ACGTACGT", b"ACGACGT", 0, 0, (5, -4, -10, -1))
     assert s == ws and rows == oracle_port.rows_from_ops(b"ACGTACGT", b"ACGACGT", wops)
+
+
+def test_pinned_arrays_from_the_context(ctx, oracle_port):
+    """Context.pinned_empty (tb_host_alloc / tb_host_free): batches and results in page-locked memory give the same answers; the block
+    is handed back when the last view goes."""
+    import gc
+    prof, win = synth.align_batch(64, 120, 300, seed=3)
+    pp, pw = ctx.pinned_empty(prof.shape, np.float32), ctx.pinned_empty(win.shape, np.uint8)
+    pp[:] = prof
+    pw[:] = win
+    s_out = ctx.pinned_empty((64,), np.int32)
+    want = ctx.gotoh("ps", tracy_b200.uniform_profiles(prof), tracy_b200.uniform_seqs(win), DnaScore(3, -5, -10, -4), AlignConfig(True, False))
+    got = ctx.gotoh("ps", tracy_b200.uniform_profiles(pp), tracy_b200.uniform_seqs(pw), DnaScore(3, -5, -10, -4), AlignConfig(True, False))
+    assert np.array_equal(want[0], got[0]) and np.array_equal(want[2], got[2])
+    s2 = ctx.gotoh("ps", tracy_b200.uniform_profiles(pp), tracy_b200.uniform_seqs(pw), DnaScore(3, -5, -10, -4), AlignConfig(True, False), traceback=False,
+                   out=(s_out, None, None))[0]
+    assert s2 is s_out and np.array_equal(s_out, want[0])
+    ws, _ = oracle_port.gotoh_ps(prof[5], bytes(win[5]), 1, 0, (3, -5, -10, -4))
+    assert int(s_out[5]) == ws
+    view = pp[3]
+    del pp
+    gc.collect()
+    assert float(view.sum()) == float(prof[3].sum())                  # the block lives as long as a view does
+    del view, pw, s_out, s2
+    gc.collect()

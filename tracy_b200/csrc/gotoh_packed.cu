@@ -689,7 +689,14 @@ gotoh_packed_kernel(const GotohBatch B) {
         const uint4* const pb = reinterpret_cast<const uint4*>(tabB_lane + (cur >> 16));
         uint4 xa[4], xb[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { xa[j] = pa[j * 32]; xb[j] = pb[j * 32]; }
+        for (int j = 0; j < 4; ++j) {
+          xa[j] = pa[j * 32];
+#ifdef TB_PK_EXPERIMENT_HALF_LDS     // timing experiment only (results are wrong): what the fill costs with half the table reads
+          xb[j] = make_uint4(xa[j].y, xa[j].x, xa[j].w, xa[j].z);
+#else
+          xb[j] = pb[j * 32];
+#endif
+        }
 
         const unsigned fsv = __shfl_sync(kFull, tchunk, st & 31);
         unsigned us = __byte_perm(fsv, __shfl_sync(kFull, bs, src), sel_us);    // lane 0: lo = top row S, hi = lane 31's half-band-A bottom S

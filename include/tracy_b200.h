@@ -355,6 +355,19 @@ typedef struct {
 int tb_write_decompose_json(const char* path, const tb_trace_view* t, const tb_decompose_json* d);
 int tb_write_decomposition(const char* path, const int32_t* decomp, int32_t n);
 
+/* The output section of assemble() (reference src/assemble.h:284-376 reference-guided, :473-600 de novo): P.align.fa, P.json (msa rows through
+ * alignedTraceByRow + one gapped trace per row: the hard trim of trimTrace(tr, bc, l, r, nbc), reverseComplementTrace for flipped traces,
+ * alignmentTracePadding, assemblyTrace), P.vertical and P.cons.fa | P.cons.fq. rows: the alignment, nrow x ncol bytes row-major; traces in
+ * OUTPUT order, each with the row it sits in and its UNTRIMMED trace (estQual in qual) + trims; reference_last: the reference is the row
+ * behind the traces (reference-guided assembly). gapped / consensus / quality: NUL-terminated, what consensus() returns. fastq: 1 writes
+ * P.cons.fq, 0 P.cons.fa, -1 neither (any other --format). The traces are formatted on the host's cores in parallel. */
+typedef struct {
+  const char* name; int32_t forward; int32_t row;
+  tb_trace_view trace; int32_t trim_left, trim_right;
+} tb_assemble_trace;
+int tb_write_assemble_files(const char* prefix, const uint8_t* rows, int32_t nrow, int32_t ncol, const tb_assemble_trace* traces, int32_t ntraces,
+                            const char* gapped, const char* consensus, const char* quality, int32_t include_consensus, int32_t fastq, int32_t reference_last);
+
 /* ---- several GPUs of one node behind one handle (BASELINE.json configs[4]; csrc/multi.cu) ----------------------------------------
  * One context per device, owned by the handle; each call cuts its batch into contiguous ranges of equal DP cost, runs every range
  * through its device's own pipeline on its own host thread and lets each device write its slice of the caller's result arrays (the

@@ -326,3 +326,63 @@ def test_native_decompose_writers_equal_python_writers(tmp_path):
         for sfx in (".decomp", ".align1", ".align2", ".align3", ".json"):
             with open(prefix + sfx, "rb") as fh:
                 assert fh.read() == want[sfx].encode("latin-1"), (it, sfx)
+
+
+def test_native_assemble_writer_equals_python_writers(tmp_path):
+    """tb_write_assemble_files against writers.assemble_files over trim.trim_basecalls / trim.reverse_complement_trace /
+    writers.alignment_trace_padding (each pinned on the reference): random alignments with leading / trailing / inner gaps, trims, flipped
+    traces with IUPAC calls, reference-guided layout, both consensus formats and none."""
+    from tracy_b200 import trim
+    rng = np.random.default_rng(79)
+    for it in range(12):
+        nt = int(rng.integers(1, 7))
+        ncol = int(rng.integers(30, 260))
+        ref_last = it % 3 == 2
+        nrow = nt + (1 if ref_last else 0)
+        rows = np.full((nrow, ncol), ord("-"), np.uint8)
+        traces, fwd, names = [], [], []
+        for i in range(nt):
+            nbc_kept = int(rng.integers(1, ncol - 5))
+            start = int(rng.integers(0, ncol - nbc_kept))
+            cols = np.sort(rng.choice(np.arange(start, ncol), size=nbc_kept, replace=False)) if rng.random() < 0.5 else np.arange(start, start + nbc_kept)
+            tl, trr = int(rng.integers(0, 6)), int(rng.integers(0, 6))
+            nbc = nbc_kept + tl + trr
+            ns = 12 * nbc + int(rng.integers(5, 30))
+            acgt = rng.integers(0, 2500, size=(4, ns)).astype(np.int32)
+            bcpos = np.sort(rng.choice(np.arange(2, ns - 1), size=nbc, replace=False)).astype(np.int32)
+            qual = rng.integers(0, 61, nbc).astype(np.uint8)
+            pri = bytes(rng.choice(list(b"ACGTN"), nbc).astype(np.uint8))
+            sec = bytes(rng.choice(list(b"ACGTRYKMSWHVDBN"), nbc).astype(np.uint8))
+            con = bytes(rng.choice(list(b"ACGTN"), nbc).astype(np.uint8))
+            f = bool(rng.random() < 0.5)
+            kept = pri[tl: nbc - trr]
+            shown = kept if f else bytes(trim._COMPLEMENT.get(chr(c), chr(c)).encode()[0] for c in kept[::-1])
+            rows[i, cols] = np.frombuffer(shown, np.uint8)
+            traces.append(dict(acgt=acgt, bcpos=bcpos, qual=qual, primary=pri, secondary=sec, consensus=con, tl=tl, tr=trr))
+            fwd.append(f); names.append("trace_%d" % i)
+        if ref_last:
+            rows[nt] = rng.choice(list(b"ACGT-"), ncol).astype(np.uint8)
+        row_of = [nt - 1 - i for i in range(nt)] if ref_last else list(range(nt))
+        if ref_last:                                              # trace i sits in row nt-1-i: put its characters there
+            rows[:nt] = rows[:nt][::-1].copy()
+        gapped = bytes(rng.choice(list(b"ACGT-"), ncol).astype(np.uint8))
+        cs = gapped.replace(b"-", b"")
+        qs = bytes(rng.integers(33, 100, len(cs)).astype(np.uint8))
+        fmt = ["fasta", "fastq", "other"][it % 3]
+        padded = []
+        for i, t in enumerate(traces):
+            nb = trim.trim_basecalls(t["acgt"].shape[1], t["bcpos"], t["qual"], t["primary"], t["secondary"], t["consensus"], t["tl"], t["tr"])
+            a = t["acgt"]
+            if not fwd[i]:
+                rv = trim.reverse_complement_trace(a, nb["bcpos"], nb["qual"], nb["primary"], nb["secondary"], nb["consensus"])
+                a, nb = rv["acgt"], rv
+            padded.append(writers.alignment_trace_padding(bytes(rows[row_of[i]]), a, nb["bcpos"], nb["qual"], nb["primary"], nb["secondary"], nb["consensus"]))
+        want = writers.assemble_files(names, fwd, rows, gapped, cs, qs, padded, include_consensus=bool(it % 2), fmt=fmt, reference_last=ref_last)
+        prefix = str(tmp_path / f"a{it}")
+        writers.write_assemble_files(prefix, names, fwd, rows, row_of, gapped, cs, qs, traces, include_consensus=bool(it % 2), fmt=fmt, reference_last=ref_last)
+        for sfx in (".align.fa", ".json", ".vertical", ".cons.fa", ".cons.fq"):
+            assert os.path.exists(prefix + sfx) == (sfx in want), (it, sfx)
+            if sfx in want:
+                with open(prefix + sfx, "rb") as fh:
+                    got = fh.read()
+                assert got == want[sfx].encode("latin-1"), (it, sfx)

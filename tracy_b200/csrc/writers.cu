@@ -9,7 +9,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tracy_b200.h"
@@ -155,6 +158,86 @@ void gapped_trace(Buf& o, const tb_trace_view& t, const char* row, int32_t L, co
     o.ch('"');
   }
   o.str("}\n}\n");
+}
+
+// ---- tracy assemble: one gapped trace per alignment row -------------------------------------------------------------------------
+char complement_iupac(char c) {                    // reverseComplement(char), src/trim.h:102-123
+  switch (c) {
+    case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; case 'N': return 'N'; case 'H': return 'D';
+    case 'V': return 'B'; case 'M': return 'K'; case 'Y': return 'R'; case 'D': return 'H'; case 'B': return 'V'; case 'K': return 'M';
+    case 'R': return 'Y'; case 'U': return 'A'; case 'S': return 'S'; case 'W': return 'W';
+  }
+  return c;
+}
+
+struct OwnedTrace {                                // a trace after the hard trim / the reverse complement, with its own storage
+  std::vector<int32_t> acgt, bcpos;
+  std::vector<uint8_t> qual;
+  std::string pri, sec, con;
+  int32_t ns = 0;
+  tb_trace_view view() const {
+    tb_trace_view v;
+    v.acgt = acgt.data(); v.nsamples = ns; v.bcpos = bcpos.data(); v.qual = qual.data(); v.primary = pri.data(); v.secondary = sec.data(); v.consensus = con.data();
+    v.nbc = (int32_t)bcpos.size();
+    return v;
+  }
+};
+
+// trimTrace(tr, bc, trimLeft, trimRight, nbc), src/trim.h:76-99: the basecalls between the trims that the forward walk meets; samples stay
+void hard_trim(const tb_trace_view& t, int32_t trim_left, int32_t trim_right, OwnedTrace& o, bool copy_samples) {
+  const uint32_t last = (uint32_t)t.nbc - (uint32_t)trim_right;
+  o.ns = t.nsamples;
+  if (copy_samples) o.acgt.assign(t.acgt, t.acgt + (size_t)4 * t.nsamples);
+  int32_t k = 0, idx = t.bcpos[0];
+  for (int32_t s = 0; s < t.nsamples; ++s)
+    if (idx == s) {
+      if ((uint32_t)k >= (uint32_t)trim_left && (uint32_t)k < last) {
+        o.bcpos.push_back(t.bcpos[k]); o.qual.push_back(t.qual[k]); o.pri.push_back(t.primary[k]); o.sec.push_back(t.secondary[k]); o.con.push_back(t.consensus[k]);
+      }
+      if (k < t.nbc - 1) idx = t.bcpos[++k];
+    }
+}
+
+// reverseComplementTrace, src/trim.h:124-151: samples reversed with channels A<->T, C<->G swapped; basecalls walked from the last one down
+void revcomp_trace(const int32_t* acgt, int32_t ns, const OwnedTrace& in, OwnedTrace& o) {
+  o.ns = ns;
+  o.acgt.resize((size_t)4 * ns);
+  for (int c = 0; c < 4; ++c)
+    for (int32_t s = 0; s < ns; ++s) o.acgt[(size_t)c * ns + s] = acgt[(size_t)(3 - c) * ns + (ns - 1 - s)];
+  if (in.bcpos.empty()) return;
+  int32_t k = (int32_t)in.bcpos.size() - 1, idx = in.bcpos[(size_t)k];
+  for (int32_t np = 0, s = ns; s > 0; --s, ++np)
+    if (idx == s - 1) {
+      o.bcpos.push_back(np); o.qual.push_back(in.qual[(size_t)k]);
+      o.pri.push_back(complement_iupac(in.pri[(size_t)k])); o.sec.push_back(complement_iupac(in.sec[(size_t)k])); o.con.push_back(complement_iupac(in.con[(size_t)k]));
+      if (k > 0) idx = in.bcpos[(size_t)--k];
+    }
+}
+
+// alignedTraceByRow, src/json.h:220-246
+void aligned_row(Buf& o, const uint8_t* row, int32_t ncol, const char* name, bool forward, bool ref) {
+  int32_t lead = 0;
+  while (lead < ncol && row[lead] == '-') ++lead;
+  int32_t trail = 0;
+  for (int32_t j = 0; j < ncol; ++j) trail = row[j] != '-' ? 0 : trail + 1;
+  o.str("{\n\"reference\": "); o.str(ref ? "true" : "false"); o.str(",\n\"forward\": "); o.str(forward ? "true" : "false");
+  o.str(",\n\"traceFileName\": \""); o.str(name); o.str("\",\n\"leadingGaps\": \""); o.num(lead); o.str("\",\n\"trailingGaps\": \""); o.num(trail);
+  o.str("\",\n\"align\": \"");
+  if (lead < ncol - trail) o.str((const char*)row + lead, (size_t)(ncol - trail - lead));
+  o.str("\"\n}\n");
+}
+
+template <typename F>
+void parallel_over(int32_t n, F&& fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nthr = (int)std::min<unsigned>(std::min<unsigned>(hw ? hw : 1u, 16u), (unsigned)std::max(n, 1));
+  if (nthr <= 1) { for (int32_t i = 0; i < n; ++i) fn(i); return; }
+  std::atomic<int32_t> next(0);
+  std::vector<std::thread> th;
+  auto body = [&]() { for (;;) { const int32_t i = next.fetch_add(1); if (i >= n) break; fn(i); } };
+  for (int t = 1; t < nthr; ++t) th.emplace_back(body);
+  body();
+  for (auto& x : th) x.join();
 }
 
 const char* iupac_expanded(char c) {              // the "|"-joined bases of an ambiguity code as the basecall JSON prints them (src/json.h:86-100)
@@ -337,6 +420,88 @@ int tb_write_decomposition(const char* path, const int32_t* decomp, int32_t n) {
   o.str("indel\tdecomp\n");
   for (int32_t i = 0; i < n; ++i) { o.num(decomp[2 * i]); o.ch('\t'); o.num(decomp[2 * i + 1]); o.ch('\n'); }
   return flush_to(path, o);
+}
+
+int tb_write_assemble_files(const char* prefix, const uint8_t* rows, int32_t nrow, int32_t ncol, const tb_assemble_trace* traces, int32_t ntraces,
+                            const char* gapped, const char* consensus, const char* quality, int32_t include_consensus, int32_t fastq, int32_t reference_last) {
+  if (!prefix || !rows || nrow <= 0 || ncol < 0 || !traces || ntraces < 0 || !gapped || !consensus || !quality) return TB_ERR_INVALID;
+  if (ntraces + (reference_last ? 1 : 0) > nrow) return TB_ERR_INVALID;
+  for (int32_t i = 0; i < ntraces; ++i)
+    if (!traces[i].name || traces[i].row < 0 || traces[i].row >= nrow || !view_ok(&traces[i].trace) || traces[i].trim_left < 0 || traces[i].trim_right < 0) return TB_ERR_INVALID;
+  const std::string p(prefix);
+  // the gapped traces: hard trim, reverse complement where the trace was flipped, padding along its alignment row -- one thread per trace
+  std::vector<Buf> parts((size_t)ntraces), msa((size_t)ntraces);
+  parallel_over(ntraces, [&](int32_t i) {
+    const tb_assemble_trace& a = traces[i];
+    const uint8_t* row = rows + (size_t)a.row * (size_t)ncol;
+    OwnedTrace trimmed;
+    hard_trim(a.trace, a.trim_left, a.trim_right, trimmed, false);
+    parts[(size_t)i].s.reserve((size_t)a.trace.nsamples * 32 + (size_t)ncol * 8);
+    if (a.forward) {
+      tb_trace_view v = trimmed.view();
+      v.acgt = a.trace.acgt; v.nsamples = a.trace.nsamples;
+      if (v.nbc > 0) gapped_trace(parts[(size_t)i], v, (const char*)row, ncol, a.name);
+    } else {
+      OwnedTrace rc;
+      revcomp_trace(a.trace.acgt, a.trace.nsamples, trimmed, rc);
+      const tb_trace_view v = rc.view();
+      if (v.nbc > 0) gapped_trace(parts[(size_t)i], v, (const char*)row, ncol, a.name);
+    }
+    aligned_row(msa[(size_t)i], row, ncol, a.name, a.forward != 0, false);
+  });
+  for (int32_t i = 0; i < ntraces; ++i) if (parts[(size_t)i].s.empty()) return TB_ERR_INVALID;      // a trace whose trims left no basecall
+  int rc = TB_OK;
+  {
+    Buf o;
+    o.s.reserve((size_t)(ntraces + 2) * ((size_t)ncol + 64));
+    for (int32_t i = 0; i < ntraces; ++i) {
+      o.ch('>'); o.str(traces[i].name); o.str(traces[i].forward ? " (forward)\n" : " (reverse)\n");
+      o.str((const char*)rows + (size_t)traces[i].row * (size_t)ncol, (size_t)ncol); o.ch('\n');
+    }
+    if (reference_last) { o.str(">Reference\n"); o.str((const char*)rows + (size_t)ntraces * (size_t)ncol, (size_t)ncol); o.ch('\n'); }
+    if (include_consensus) { o.str(">Consensus\n"); o.str(gapped); o.ch('\n'); }
+    rc = flush_to((p + ".align.fa").c_str(), o);
+  }
+  if (rc == TB_OK) {
+    Buf o;
+    size_t total = 4096 + std::strlen(consensus) + std::strlen(gapped);
+    for (int32_t i = 0; i < ntraces; ++i) total += parts[(size_t)i].s.size() + msa[(size_t)i].s.size() + 4;
+    o.s.reserve(total + (size_t)ncol + 256);
+    o.str("{\n\"gapFreeConsensus\": \""); o.str(consensus); o.str("\",\n\"gappedConsensus\": \""); o.str(gapped); o.str("\",\n\"msa\": \n[\n");
+    for (int32_t i = 0; i < ntraces; ++i) { if (i) o.str(",\n"); o.s.append(msa[(size_t)i].s); }
+    if (reference_last) { o.str(",\n"); aligned_row(o, rows + (size_t)ntraces * (size_t)ncol, ncol, "", true, true); }
+    o.str("],\n\"gappedTraces\": \n[\n");
+    for (int32_t i = 0; i < ntraces; ++i) { if (i) o.str(", "); o.s.append(parts[(size_t)i].s); }
+    o.str("]\n}\n");
+    rc = flush_to((p + ".json").c_str(), o);
+  }
+  if (rc == TB_OK) {                                   // P.vertical: one line per alignment column, every row's character, '|', the consensus
+    Buf o;
+    const size_t line = (size_t)nrow + 2;
+    o.s.resize(line * (size_t)ncol);
+    char* out = &o.s[0];
+    const int32_t blocks = (ncol + 255) / 256;
+    parallel_over(blocks, [&](int32_t b) {             // blocked transpose: 256 columns at a time stay in cache
+      const int32_t j0 = b * 256, j1 = std::min(ncol, j0 + 256);
+      for (int32_t r = 0; r < nrow; ++r) {
+        const uint8_t* src = rows + (size_t)r * (size_t)ncol;
+        for (int32_t j = j0; j < j1; ++j) out[(size_t)j * line + (size_t)r] = (char)src[j];
+      }
+      for (int32_t j = j0; j < j1; ++j) { out[(size_t)j * line + (size_t)nrow] = '|'; out[(size_t)j * line + (size_t)nrow + 1] = gapped[j]; }
+    });
+    // the line ends: every line is nrow characters + '|' + consensus + newline
+    Buf w;
+    w.s.resize((line + 1) * (size_t)ncol);
+    for (int32_t j = 0; j < ncol; ++j) { std::memcpy(&w.s[(size_t)j * (line + 1)], out + (size_t)j * line, line); w.s[(size_t)j * (line + 1) + line] = '\n'; }
+    rc = flush_to((p + ".vertical").c_str(), w);
+  }
+  if (rc == TB_OK) {
+    Buf o;
+    if (fastq < 0) { /* --format names neither fasta nor fastq: the reference writes no consensus file */ }
+    else if (fastq) { o.str("@Consensus\n"); o.str(consensus); o.str("\n+\n"); o.str(quality); o.ch('\n'); rc = flush_to((p + ".cons.fq").c_str(), o); }
+    else { o.str(">Consensus\n"); o.str(consensus); o.ch('\n'); rc = flush_to((p + ".cons.fa").c_str(), o); }
+  }
+  return rc;
 }
 
 }  // extern "C"

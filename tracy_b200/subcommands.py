@@ -390,15 +390,9 @@ def _assemble_empty(prefix, fmt):
 
 
 def _assemble_out(prefix, names, fwd, rows, row_of, r, ts, inc_cons, fmt, reference_last):
-    padded = []
-    for q, t in enumerate(ts):
-        nbc = trim.trim_basecalls(t["acgt"].shape[1], t["bcpos"], t["qual"], t["primary"], t["secondary"], t["consensus"], t["tl"], t["tr"])
-        acgt = t["acgt"]
-        if not fwd[q]:
-            rv = trim.reverse_complement_trace(acgt, nbc["bcpos"], nbc["qual"], nbc["primary"], nbc["secondary"], nbc["consensus"])
-            acgt, nbc = rv["acgt"], rv
-        padded.append(writers.alignment_trace_padding(rows[row_of[q]], acgt, nbc["bcpos"], nbc["qual"], nbc["primary"], nbc["secondary"], nbc["consensus"]))
-    _Writers.write(prefix, writers.assemble_files(names, fwd, rows, r["gapped"], r["consensus"], r["quality"], padded, inc_cons, fmt, reference_last))
+    # native (csrc/writers.cu): hard trim, reverse complement of flipped traces, padding along the alignment row and the four files -- the
+    # same bytes as writers.assemble_files over trim.trim_basecalls / reverse_complement_trace / writers.alignment_trace_padding
+    writers.write_assemble_files(prefix, names, fwd, rows, row_of, r["gapped"], r["consensus"], r["quality"], ts, inc_cons, fmt, reference_last)
 
 
 # ---- tracy decompose -----------------------------------------------------------------------------------------------------------

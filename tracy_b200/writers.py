@@ -440,3 +440,27 @@ def write_decompose_files(prefix, cfg, acgt, bcpos, qual, primary, secondary, co
     ok = ok and L.tb_write_decompose_json(pre + b".json", C.byref(v), C.byref(d)) == 0
     if not ok:
         raise OSError("native decompose writers failed for %s" % prefix)
+
+
+def write_assemble_files(prefix, names, forward, rows, row_of, gapped, consensus, quality, traces, include_consensus=False, fmt="fasta", reference_last=False):
+    """The files of `tracy assemble -o prefix` (what assemble_files returns as text) written by tb_write_assemble_files: names / forward /
+    row_of per trace in output order, traces: per trace a dict with the UNTRIMMED acgt / bcpos / qual / primary / secondary / consensus and
+    the trims tl / tr -- the hard trim, the reverse complement of flipped traces and the padding along the alignment row happen natively,
+    one host thread per trace."""
+    import ctypes as C
+    from . import capi
+    a = np.ascontiguousarray(rows, np.uint8)
+    nt = len(names)
+    arr = (capi.AssembleTrace * max(nt, 1))()
+    keep = []
+    for i in range(nt):
+        t = traces[i]
+        v, k = _trace_view(t["acgt"], t["bcpos"], t["qual"], t["primary"], t["secondary"], t["consensus"])
+        nm = names[i].encode("latin-1")
+        keep.append((k, nm))
+        arr[i] = capi.AssembleTrace(nm, int(bool(forward[i])), int(row_of[i]), v, int(t["tl"]), int(t["tr"]))
+    b = lambda x: x.encode("latin-1") if isinstance(x, str) else bytes(x)
+    rc = capi.lib().tb_write_assemble_files(os.fsencode(prefix), a.ctypes.data, a.shape[0], a.shape[1], arr, nt, b(gapped), b(consensus), b(quality),
+                                            int(bool(include_consensus)), 1 if fmt == "fastq" else 0 if fmt == "fasta" else -1, int(bool(reference_last)))
+    if rc != capi.TB_OK:
+        raise OSError("tb_write_assemble_files(%s): %d" % (prefix, rc))

@@ -318,6 +318,12 @@ int tb_trace_unpack(tb_ctx* ctx, const uint8_t* files, const int64_t* off, const
 int tb_trace_quality(const int32_t* bcpos, const char* secondary, int32_t n, float trim_stringency, uint8_t* qual, uint32_t* best_section,
                      uint32_t* trim_left, uint32_t* trim_right);
 
+/* pairwiseConsensus (with gtLetter / consLetter), reference src/consensus.h:94-238, for one aligned trace pair (host, double): row0 / row1 =
+ * the gapped rows (L columns) of the global alignment of the trimmed profiles p1 (float[6][m]) and p2 (float[6][n], oriented as aligned).
+ * cons / qual: capacity 2 * L each; *len receives the number of consensus letters. */
+int tb_pairwise_consensus(const char* row0, const char* row1, int32_t L, const float* p1, int32_t m, const float* p2, int32_t n,
+                          int32_t compute_union, int32_t use_iupac, char* cons, uint32_t* qual, int32_t* len);
+
 /* ---- the output files of `tracy align`, written by native code (host only; csrc/writers.cu) ---------------------------------------
  * One trace as the writers see it: Trace::traceACGT as int32 [4][nsamples] row-major, BaseCalls::bcPos / estQual / primary / secondary /
  * consensus with nbc entries each (nbc >= 1: the reference reads bcPos[0] unconditionally). The functions format into one buffer and

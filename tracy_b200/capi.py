@@ -21,7 +21,7 @@ SYMBOLS = [
     "tb_multi_create", "tb_multi_destroy", "tb_multi_size", "tb_multi_ctx", "tb_multi_last_error", "tb_multi_partition", "tb_multi_gotoh",
     "tb_multi_index_build", "tb_multi_anchor",
     "tb_write_trace_txt", "tb_write_align_fasta", "tb_write_plot_alignment", "tb_write_trace_align_json", "tb_write_align_files", "tb_trace_quality",
-    "tb_write_decompose_json", "tb_write_decomposition", "tb_write_assemble_files",
+    "tb_write_decompose_json", "tb_write_decomposition", "tb_write_assemble_files", "tb_pairwise_consensus",
 ]
 
 
@@ -132,6 +132,8 @@ def lib():
     L.tb_write_decomposition.argtypes = [C.c_char_p, C.c_void_p, C.c_int32]
     L.tb_write_assemble_files.argtypes = [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(AssembleTrace), C.c_int32, C.c_char_p, C.c_char_p, C.c_char_p,
                                           C.c_int32, C.c_int32, C.c_int32]
+    L.tb_pairwise_consensus.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p,
+                                        C.c_void_p, C.POINTER(C.c_int32)]
     L.tb_write_trace_txt.argtypes = [C.c_char_p, C.POINTER(TraceView), C.c_int32, C.c_int32]
     L.tb_write_align_files.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(TraceView), C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p,
                                        C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]

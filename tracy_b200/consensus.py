@@ -152,3 +152,21 @@ def plot_clustal_pairwise(stem1, stem2, row0, row1, forward, score, linelimit=60
         out.append("\n" * (4 * (6 - blocks)))
     out.append(bar + bar + "\n\n")
     return "".join(out)
+
+
+def pairwise_consensus_native(row0, row1, p1, p2, compute_union=True, use_iupac=False):
+    """pairwise_consensus through tb_pairwise_consensus (csrc/trimq.cu): the same letters and qualities, without the per-column
+    interpreter loop. Returns (consensus bytes, uint32 array)."""
+    import ctypes as C
+    from . import capi
+    row0, row1 = bytes(row0), bytes(row1)
+    a, b = np.ascontiguousarray(p1, np.float32), np.ascontiguousarray(p2, np.float32)
+    cap = 2 * len(row0) + 1
+    cons = C.create_string_buffer(cap)
+    qual = np.zeros(cap, np.uint32)
+    n = C.c_int32(0)
+    rc = capi.lib().tb_pairwise_consensus(row0, row1, len(row0), a.ctypes.data, a.shape[1], b.ctypes.data, b.shape[1], int(bool(compute_union)), int(bool(use_iupac)),
+                                          cons, qual.ctypes.data, C.byref(n))
+    if rc != capi.TB_OK:
+        raise ValueError("tb_pairwise_consensus: %d" % rc)
+    return cons.raw[: n.value], qual[: n.value].copy()

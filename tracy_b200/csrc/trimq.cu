@@ -107,3 +107,59 @@ int tb_trace_quality(const int32_t* bcpos, const char* secondary, int32_t n, flo
 }
 
 }  // extern "C"
+
+// ---- tracy consensus: the consensus letters of a pairwise alignment (host only) ------------------------------------------------------
+// gtLetter + consLetter + pairwiseConsensus, reference src/consensus.h:94-238, for one trace pair: double arithmetic with libm's
+// log10 / pow in the reference's operation order (the results are rounded to integers). The same statement as tracy_b200.hpp's
+// templates and tracy_b200/consensus.py; here so that the files pipeline does not spend its time in per-column interpreter loops.
+namespace {
+void gt_letter(const double* w, bool use_iupac, char* letter, uint32_t* quality) {
+  const double smallest = -1000;
+  double cl[6], gl[6], total = 0;
+  for (int k = 0; k < 6; ++k) { cl[k] = w[k]; total += cl[k]; }
+  for (int k = 0; k < 6; ++k) {
+    cl[k] = total > 0 ? cl[k] / total : 0;
+    if (cl[k] > 0) { gl[k] = std::log10(cl[k]); if (gl[k] < smallest) gl[k] = smallest; }
+    else gl[k] = smallest;
+  }
+  uint32_t first = gl[0] < gl[1] ? 1 : 0, second = 1 - first;
+  for (uint32_t k = 2; k < 6; ++k) {
+    if (gl[k] > gl[first]) { second = first; first = k; }
+    else if (gl[k] > gl[second]) second = k;
+  }
+  const bool two = use_iupac && gl[second] > -1 && first <= 3 && second <= 3;
+  const double top = gl[first];
+  for (int k = 0; k < 6; ++k) gl[k] -= top;
+  const uint32_t pl1 = (uint32_t)std::round(-10 * gl[first]), pl2 = (uint32_t)std::round(-10 * gl[second]);
+  double like = std::log10(1 - 1 / (std::pow((double)10, -((double)pl1 / (double)10)) + std::pow((double)10, -((double)pl2 / (double)10))));
+  if (!(like > smallest)) like = smallest;
+  int32_t gq = (int32_t)std::round(-10 * like);
+  if (gq < 0) gq = 0;
+  if (two) {
+    static const char code[4][5] = {"NMRW", "MNSY", "RSNK", "WYKN"};
+    *letter = code[first][second];
+  } else *letter = first <= 3 ? "ACGT"[first] : first == 4 ? 'N' : '-';
+  *quality = (uint32_t)gq;
+}
+}  // namespace
+
+extern "C" int tb_pairwise_consensus(const char* row0, const char* row1, int32_t L, const float* p1, int32_t m, const float* p2, int32_t n,
+                                     int32_t compute_union, int32_t use_iupac, char* cons, uint32_t* qual, int32_t* len) {
+  if (!row0 || !row1 || L < 0 || !p1 || !p2 || m < 0 || n < 0 || !cons || !qual || !len) return TB_ERR_INVALID;
+  int32_t s1 = 0, s2 = 0, k = 0;
+  double w[6];
+  for (int32_t j = 0; j < L; ++j) {
+    const bool g1 = row0[j] == '-', g2 = row1[j] == '-';
+    if ((!g1 && s1 >= m) || (!g2 && s2 >= n)) return TB_ERR_INVALID;           // the rows name more columns than the profiles have
+    if (!g1 && !g2) {
+      for (int c = 0; c < 6; ++c) w[c] = p1[(size_t)c * m + s1] + p2[(size_t)c * n + s2];       // float + float, then widened (consLetter)
+      gt_letter(w, use_iupac != 0, &cons[k], &qual[k]); ++k;
+    } else if (compute_union) {
+      if (!g1) { for (int c = 0; c < 6; ++c) w[c] = p1[(size_t)c * m + s1]; gt_letter(w, use_iupac != 0, &cons[k], &qual[k]); ++k; }
+      if (!g2) { for (int c = 0; c < 6; ++c) w[c] = p2[(size_t)c * n + s2]; gt_letter(w, use_iupac != 0, &cons[k], &qual[k]); ++k; }
+    }
+    s1 += g1 ? 0 : 1; s2 += g2 ? 0 : 1;
+  }
+  *len = k;
+  return TB_OK;
+}

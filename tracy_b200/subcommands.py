@@ -300,7 +300,7 @@ def _cons_abif(prefix, a, b):
 
 def _cons_out(job, r, p1, p2, label, union, iupac, linelimit):
     s1, s2 = _stem(job[0]), _stem(job[1])
-    cs, qual = cons_mod.pairwise_consensus(r["row0"], r["row1"], p1, p2, union, iupac)
+    cs, qual = cons_mod.pairwise_consensus_native(r["row0"], r["row1"], p1, p2, union, iupac)
     _Writers.write(job[2], {".align.fa": cons_mod.consensus_align_fasta(s1, s2, r["row0"], r["row1"], r["forward"]),
                             ".fa": cons_mod.consensus_fasta(label, cs), ".fq": cons_mod.consensus_fastq(label, cs, qual),
                             ".txt": cons_mod.plot_clustal_pairwise(s1, s2, r["row0"], r["row1"], r["forward"], r["score"], linelimit)})

@@ -35,6 +35,15 @@ with tempfile.TemporaryDirectory() as d:
         dt = time.perf_counter() - t0
         out[f"decompose_workers{workers}"] = {"jobs": len(djobs), "ok": rc.count(0), "seconds": dt, "traces_per_s": len(djobs) / dt,
                                               "kernel_launches": ctx.stats()["kernel_launches"] - st0["kernel_launches"]}
+    # tracy consensus: overlapping trace pairs, six output files per pair
+    cjobs, _ = make_consensus_jobs(d, n=min(N, 800), seed=10)
+    cjobs = [j for j in cjobs if os.path.exists(j[0]) and os.path.exists(j[1])]
+    subcommands.consensus(ctx, cjobs[:32], chunk=32)
+    st0 = ctx.stats(); t0 = time.perf_counter()
+    rc = subcommands.consensus(ctx, cjobs, chunk=512, workers=8)
+    dt = time.perf_counter() - t0
+    out["consensus_workers8"] = {"jobs": len(cjobs), "ok": rc.count(0), "seconds": dt, "pairs_per_s": len(cjobs) / dt,
+                                 "kernel_launches": ctx.stats()["kernel_launches"] - st0["kernel_launches"]}
     from oracle import loader                                                      # the reference's own `tracy align` on a sample of the same files, one core
     ref = loader.ref()
     if ref is not None:
@@ -47,6 +56,9 @@ with tempfile.TemporaryDirectory() as d:
         t0 = time.perf_counter()
         rc = [ref.subcommand("decompose", ["-r", g, "-o", o + ".ref", "-i", "30", t]) for t, g, o in djobs[:12]]
         dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        rc2 = [ref.subcommand("consensus", ["-o", o + ".ref", a, b]) for a, b, o in cjobs[:12]]
+        out["reference_consensus_one_core"] = {"jobs": 12, "ok": rc2.count(0), "seconds": time.perf_counter() - t1, "pairs_per_s": 12 / (time.perf_counter() - t1)}
         out["reference_decompose_one_core"] = {"jobs": 12, "ok": rc.count(0), "seconds": dt, "traces_per_s": 12 / dt,
                                                "what": "tracy::indigo(argc, argv) of the unmodified reference on the first 12 jobs"}
 print(json.dumps(out, indent=1))

@@ -382,6 +382,18 @@ __device__ __noinline__ int walk_traceback_ckpt(const PkPair& P, const uint2* __
       const int cc = min(max(col, 1), n);
       return top_base[(unsigned long long)(cc - 1) * 32ull];
     };
+    // The top-edge entries of a span are 64 reads of 8 bytes, 256 bytes apart, out of checkpoints written a whole pair ago: DRAM, one
+    // sector per lane and column, and the tile loop needs one per iteration -- it ran at DRAM latency (the first use of the loaded value
+    // held 4.4 % of the kernel's warp time in the round-2 ncu source view). Ask L2 for all of them before the loop starts.
+#ifndef TB_NO_TOP_PREFETCH
+    if (R0 > 0) {
+#pragma unroll 1
+      for (int u = 1; u <= kPkSpan; ++u) {
+        const int cc = min(max(cA + u, 1), n);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(top_base + (unsigned long long)(cc - 1) * 32ull));
+      }
+    }
+#endif
     auto top_fix = [&](uint2 e, int col, unsigned& ts, unsigned& tv) {
       if (R0 == 0) { ts = (unsigned)((col == 0 ? 0 : (hfree ? 0 : go + col * ge)) + bias); tv = (unsigned)kPkNeg; }   // src/gotoh.h:109-118
       else if (col == 0) { ts = (unsigned)((vfree ? 0 : go + R0 * ge) + bias); tv = (unsigned)kPkNeg; }
@@ -669,10 +681,13 @@ gotoh_packed_kernel(const GotohBatch B) {
         return cc <= n ? top[cc] : pk_dpx(kPkNeg, bias);
       };
       auto feed_cls = [&](int cc) -> unsigned { return cc <= n ? (unsigned)base_class(b[cc - 1]) << 11 : 0u; };   // byte offset of the class's 2 KB table block
+      // the window character of a column as loaded ('A' = class 0 outside 1..n); classified one chunk later, when the load has long landed --
+      // classifying it at once made every 32nd step wait for the load (2.6 % of the kernel's warp time in the round-2 ncu source view)
+      auto feed_raw = [&](int cc) -> unsigned { return cc <= n ? (unsigned)b[cc - 1] : (unsigned)'A'; };
       // chunk q of the boundary row covers columns 32q+1.., chunk q of the classes covers columns 32q+2.. (the class a step
       // fetches is the one of its NEXT column), so both chunks roll over together after every 32nd step
       unsigned tchunk = feed_sv(1 + lane), cchunk = feed_cls(2 + lane);
-      unsigned tnext = feed_sv(33 + lane), cnext = feed_cls(34 + lane);
+      unsigned tnext = feed_sv(33 + lane), craw = feed_raw(34 + lane);
       // table offsets of this lane's two column classes for the coming step (lo16: half-band A, hi16: half-band B);
       // columns outside 1..n use class 0 (never read back)
       unsigned cur = lane == 0 ? feed_cls(1) : 0u;
@@ -795,7 +810,7 @@ gotoh_packed_kernel(const GotohBatch B) {
           for (int st = st0; st < st1; ++st) do_step(st, std::false_type(), std::false_type());
         }
         // roll the feed chunks over; checkpoint the lane's 16 rows (S, H) every 32 columns
-        tchunk = tnext; cchunk = cnext; tnext = feed_sv(st0 + 65 + lane); cnext = feed_cls(st0 + 66 + lane);
+        tchunk = tnext; cchunk = (unsigned)base_class((unsigned char)craw) << 11; tnext = feed_sv(st0 + 65 + lane); craw = feed_raw(st0 + 66 + lane);
         if (CKPT && st1 == st0 + 32) {
           uint4* pc = colck + (((unsigned long long)pass * (unsigned)NQ + (unsigned)(st0 >> 5)) * 8ull) * 32ull + (unsigned)lane;
 #pragma unroll

@@ -41,8 +41,12 @@ def run(tag, env):
         del os.environ[k]
 
 
-run("fp32x2_sel", {})
-run("fp32x2_arr", {"TRACY_B200_PP_VARIANT": "arr"})
+run("fp32x2_arr", {})
+if os.environ.get("PP_PROBE_QUICK"):
+    print(json.dumps(out, indent=1)); sys.exit(0)
+run("fp32x2_sel", {"TRACY_B200_PP_VARIANT": "sel"})
+run("fp32x2_arr_literal_only", {"TRACY_B200_PP_SCREEN": "0"})
+run("fp32x2_sel_literal_only", {"TRACY_B200_PP_SCREEN": "0", "TRACY_B200_PP_VARIANT": "sel"})
 run("general", {"TRACY_B200_NO_PPFAST": "1"})
 
 # big pairs: MSA-like profiles of growing length, one pair per call, with traceback

@@ -1,10 +1,6 @@
 mkdir -p gpurun_out
-nvidia-smi -L | head -4
-timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_cpp_binding.py -m gpu -q 2>&1 | tail -5 > gpurun_out/r02_gpu_tests_multi_n2.log; cat gpurun_out/r02_gpu_tests_multi_n2.log
-oracle/_ref/dropin_test | tail -3
-python profiles/bench_multi.py 100000 > gpurun_out/r02_bench_multi_n2.json 2> gpurun_out/r02_bench_multi_n2.err; cat gpurun_out/r02_bench_multi_n2.json; tail -3 gpurun_out/r02_bench_multi_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r02_bench_n2.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','e2e','n_gpus','reference_broadcast')})
-PY
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/r02_gpu_tests_g.log; cat gpurun_out/r02_gpu_tests_g.log
+oracle/_ref/dropin_test | tail -2
+g++ -std=c++17 -O2 -I include profiles/bench_assemble.cpp -o /tmp/bench_assemble -Ltracy_b200 -ltracy_b200 -Wl,-rpath,$PWD/tracy_b200 && /tmp/bench_assemble 512 > gpurun_out/r02_bench_assemble_cpp.json 2> gpurun_out/r02_bench_assemble_cpp.err; cat gpurun_out/r02_bench_assemble_cpp.json
+timeout 600 python profiles/prof_assemble_stages.py > gpurun_out/r02_assemble_stages.json 2>&1; tail -c 900 gpurun_out/r02_assemble_stages.json
+timeout 900 python profiles/bench_assemble_files.py > gpurun_out/r02_bench_assemble_files.json 2> gpurun_out/r02_bench_assemble_files.err; tail -c 600 gpurun_out/r02_bench_assemble_files.json

@@ -130,7 +130,7 @@ def test_huge_pair(ctx, oracle_port):
 
 
 def test_pp_variants_agree(ctx, oracle_port, monkeypatch):
-    """The register-array variant of the kernel and the general int32 kernel give the same answers."""
+    """The select variant of the kernel and the general int32 kernel give the same answers as the default (register arrays)."""
     rng = np.random.default_rng(340)
     A, B = [], []
     for k in range(24):
@@ -138,9 +138,55 @@ def test_pp_variants_agree(ctx, oracle_port, monkeypatch):
         A.append(a); B.append(b)
     s0, o0, l0 = ctx.gotoh("pp", A, B, DnaScore(*SC), AlignConfig(True, True))
     for env in ("TRACY_B200_PP_VARIANT", "TRACY_B200_NO_PPFAST"):
-        monkeypatch.setenv(env, "arr" if env.endswith("VARIANT") else "1")
+        monkeypatch.setenv(env, "sel" if env.endswith("VARIANT") else "1")
         s1, o1, l1 = ctx.gotoh("pp", A, B, DnaScore(*SC), AlignConfig(True, True))
         monkeypatch.delenv(env)
         assert np.array_equal(s0, s1) and np.array_equal(l0, l1)
         for i in range(len(A)):
             assert bytes(o0[i, : l0[i]]) == bytes(o1[i, : l1[i]])
+
+
+# ---- the screened substitution score (gotoh_pp.cu header, 3.; the rule itself is attacked on the CPU in test_pp_screen.py) ----
+def family_profile(rng, kind, n, with_n=False):
+    from test_pp_screen import family
+    p = np.zeros((6, n), np.float32)
+    p[:5] = family(rng, kind, 5, n) if with_n else np.concatenate([family(rng, kind, 4, n), np.zeros((1, n), np.float32)])
+    return p
+
+
+@pytest.mark.parametrize("sc", [SC, (5, -4, -10, -1), (1, -1, -2, -1), (300, -500, -600, -100)])
+def test_screen_value_families_vs_oracle(ctx, oracle_port, sc):
+    """Columns whose float sums land ON integers (one-hot, dyadic), next to them (k/d fractions) or anywhere (blends), on both
+    sides and mixed inside one profile: the short form, the literal fallback and the switch between them."""
+    rng = np.random.default_rng(350 + sc[0])
+    kinds = ["onehot", "dyadic", "fractions", "blend", "uniform", "tiny"]
+    A, B = [], []
+    for ka in kinds:
+        for kb in kinds:
+            m, n = int(rng.integers(120, 330)), int(rng.integers(120, 330))
+            A.append(family_profile(rng, ka, m)); B.append(family_profile(rng, kb, n))
+    for k in range(6):                                           # families interleaved column by column, some with N mass
+        m, n = int(rng.integers(200, 700)), int(rng.integers(200, 700))
+        a = np.concatenate([family_profile(rng, kinds[(k + i) % 5], 40, with_n=k % 2 == 1) for i in range(m // 40 + 1)], 1)[:, :m]
+        b = np.concatenate([family_profile(rng, kinds[(k + 2 * i) % 5], 64) for i in range(n // 64 + 1)], 1)[:, :n]
+        A.append(np.ascontiguousarray(a)); B.append(np.ascontiguousarray(b))
+    check(ctx, oracle_port, A, B, 1, 1, sc=sc)
+    check(ctx, oracle_port, A[:12], B[:12], 1, 0, sc=sc)
+
+
+def test_screen_on_off_agree_at_scale(ctx, monkeypatch):
+    """6 000 pairs of trace-like and MSA-like profiles: the screened kernel and the literal-only kernel (TRACY_B200_PP_SCREEN=0)
+    return the same scores and the same s/h/v strings."""
+    rng = np.random.default_rng(360)
+    A, B = [], []
+    for k in range(6000):
+        a, b = related_pair(rng, int(rng.integers(150, 420)), int(rng.integers(150, 420)), ["trace", "trace", "msa", "msaN"][k % 4])
+        A.append(a); B.append(b)
+    s1, o1, l1 = ctx.gotoh("pp", A, B, DnaScore(*SC), AlignConfig(True, True))
+    monkeypatch.setenv("TRACY_B200_PP_SCREEN", "0")
+    s0, o0, l0 = ctx.gotoh("pp", A, B, DnaScore(*SC), AlignConfig(True, True))
+    monkeypatch.delenv("TRACY_B200_PP_SCREEN")
+    assert np.array_equal(s0, s1) and np.array_equal(l0, l1)
+    w = int(l0.max())
+    mask = np.arange(w)[None, :] < l0[:, None]
+    assert np.array_equal(np.where(mask, o0[:, :w], 0), np.where(mask, o1[:, :w], 0))

@@ -185,8 +185,10 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
   unsigned long long warps_pp = 0;
   const int wpb_pp = tb::gotoh_pp_warps_per_block();
   if (mode == tb::kModePP && getenv("TRACY_B200_NO_PPFAST") == nullptr) {
-    const char* v = getenv("TRACY_B200_PP_VARIANT");          // "arr": free-row costs in register arrays (2 blocks / SM) instead of selects (3 blocks / SM)
-    p.pp_harr = v && std::strcmp(v, "arr") == 0;
+    // free-row costs in register arrays (2 blocks / SM; the default: with the screened score the cell loop is bound by the
+    // integer pipe, and the selects were a third of its instructions) or, "sel", as selects (3 blocks / SM)
+    const char* v = getenv("TRACY_B200_PP_VARIANT");
+    p.pp_harr = !(v && std::strcmp(v, "sel") == 0);
     int& o4 = ctx->occ_pp[0][traceback ? 1 : 0][p.pp_harr ? 1 : 0];
     int& o5 = ctx->occ_pp[1][traceback ? 1 : 0][p.pp_harr ? 1 : 0];
     if (o4 < 0) TB_CUDA(ctx, tb::gotoh_pp_blocks_per_sm(4, traceback, p.pp_harr, &o4));
@@ -291,6 +293,7 @@ size_t classify_pp(const tb_ctx* ctx, const int32_t* l1, const int32_t* l2, size
 int build_pp_work(tb_ctx* ctx, Lane& L, const int32_t* l1, const int32_t* l2, const uint8_t* big, size_t cn, bool traceback) {
   tb::PPWork W{};
   W.one = 1.0f; W.nsmall = (int)cn;
+  { const char* v = std::getenv("TRACY_B200_PP_SCREEN"); W.screen = (v && v[0] == '0') ? 0 : 1; }
   size_t nbig = 0, nunits = 0;
   if (big) for (size_t i = 0; i < cn; ++i) if (big[i]) { ++nbig; nunits += (size_t)pp_bands(l1[i]); }
   if (nbig == 0) { L.ppw = W; return TB_OK; }

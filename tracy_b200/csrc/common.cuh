@@ -55,6 +55,7 @@ struct PPWork {
   unsigned long long* big_ptr;                 // per big pair: nb x (n + 31) x 32 pointer words (traceback only)
   int* big_flags;                              // per big pair: nb progress words (columns of the bottom row published), zeroed per call
   float one;                                   // 1.0f, as a run-time value (see gotoh_pp.cu)
+  int screen;                                  // 1: short-form substitution score with the literal one behind it (gotoh_pp.cu, 3.)
 };
 
 // Device view of a decompose-sweep batch (sweep.cu).

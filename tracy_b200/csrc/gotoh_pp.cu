@@ -23,13 +23,31 @@
 //    warp that is resident and running, so the wait cannot deadlock whatever the grid size. The warp that finishes the
 //    last band walks the pointers. Small pairs are still one warp per pair (all bands in sequence).
 //
+// 3. Screening. The reference truncates the float sum to an int, so all the DP needs is floor-toward-zero of a number that
+//    the 16/25-term sequence pins to within a few ulps. Algebraically the sum is  sum_k p1[k] * c[k]  with the per-COLUMN
+//    constants c[k] = (match - mismatch) * p2[k] + mismatch * sum(p2): 4-5 fused multiply-adds per cell instead of 48-75
+//    float instructions. Both evaluations differ from the real-number value by at most
+//        u * A * B * ((NCH^2 + 1) * max(|match|, |mismatch|) + 11 |mismatch| + 6 |match - mismatch|),   u = 2^-24,
+//    (A, B: the absolute row sums of the two profile columns; standard forward error of a recursive sum / dot product),
+//    so whenever the short form lies further than that bound (doubled here) from the nearest integer, its truncation IS the
+//    reference's. The distance comes from the 1.5 * 2^23 rounding constant (three float adds). The few cells that fail
+//    the test -- and every cell with a NaN/infinite/huge operand, for which the comparison is false -- are evaluated with
+//    the literal sequence of 1. A warp whose cells keep failing (one-hot or dyadic profiles: exact integers) drops the
+//    screen for the rest of the band. TRACY_B200_PP_SCREEN=0 disables it (timing / cross-checks).
+//
 // Pairs whose N rows (channel 4) are not all zero need the 25-term sum: the NCH = 5 instantiation. The NCH = 4 kernel
 // declines them (GotohBatch::status stays 0); degenerate shapes (m == 0 or n == 0) are left to the general kernel.
 #include "common.cuh"
 
 namespace tb {
 
-constexpr int kPPWarps = 4;
+#ifndef TB_PP_WARPS
+#define TB_PP_WARPS 4
+#endif
+#ifndef TB_PP_MINBLOCKS_ARR
+#define TB_PP_MINBLOCKS_ARR 2
+#endif
+constexpr int kPPWarps = TB_PP_WARPS;
 constexpr int kPPBand = 32 * kRowsPerLane;                 // 512 rows
 
 // ---- packed fp32x2 helpers ------------------------------------------------------------------------------------------
@@ -120,7 +138,7 @@ __device__ __forceinline__ int walk_traceback_cg(const unsigned long long* __res
 // HARR: the free-end-gap row's horizontal costs as per-row register arrays (32 registers, no per-cell selects) or as two
 // selects per cell on the one row index that can be row m (fewer registers, one more warp per scheduler).
 template <int NCH, bool TRACEBACK, bool HARR>
-__global__ void __launch_bounds__(kPPWarps * 32, HARR ? 2 : 3)
+__global__ void __launch_bounds__(kPPWarps * 32, HARR ? TB_PP_MINBLOCKS_ARR : 3)
 gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned slot = blockIdx.x * kPPWarps + wib;
@@ -128,6 +146,14 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
   const bool hfree = B.hfree != 0, vfree = B.vfree != 0;
   const unsigned long long wm = f2_pack((float)B.match, (float)B.match), wx = f2_pack((float)B.mismatch, (float)B.mismatch);
   const unsigned long long one2 = f2_pack(W.one, W.one);
+  // screening constants (header, 3.)
+  const float wxf = (float)B.mismatch, wdf = (float)(B.match - B.mismatch);
+  const float kMagic = 12582912.0f;                               // 1.5 * 2^23: x + kMagic - kMagic = rint(x) for |x| < 2^22
+  const unsigned long long magic2 = f2_pack(kMagic * W.one, kMagic * W.one), nmagic2 = f2_pack(-kMagic * W.one, -kMagic * W.one);
+  const unsigned long long mone2 = f2_pack(-W.one, -W.one);
+  const bool screen_ok = W.screen != 0 && abs(B.match) <= (1 << 16) && abs(B.mismatch) <= (1 << 16);
+  const float ecoef = 2.0f * 5.9604645e-8f * ((float)(NCH * NCH + 1) * (float)max(abs(B.match), abs(B.mismatch)) +
+                                               11.0f * fabsf(wxf) + 6.0f * fabsf(wdf));
 
   unsigned long long* const slot_ptr = TRACEBACK ? B.ptr_scratch + (unsigned long long)slot * B.ptr_slot_words : nullptr;
   int2* const slot_rowbuf = B.rowbuf + (unsigned long long)slot * B.rowbuf_slot;
@@ -181,17 +207,25 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
       const bool more = band + 1 < nb;
       const int rtop = band * kPPBand + lane * kRowsPerLane;      // DP row just above this lane's rows
 
-      // a1 channels of the lane's 16 rows as row pairs (rows past m: zeros, their cells are never read)
+      // a1 channels of the lane's 16 rows as row pairs (rows past m repeat row m: their cells are never read, and a copy of
+      // a real row passes or fails the screen exactly as often as that row does)
       unsigned long long p1[NCH][kRowsPerLane / 2];
+      float ea = 0.0f;                                            // ecoef x the largest absolute row sum of the lane's rows
 #pragma unroll
-      for (int k = 0; k < NCH; ++k)
+      for (int j = 0; j < kRowsPerLane / 2; ++j) {
+        const int r0 = min(rtop + 2 * j, m - 1), r1 = min(rtop + 2 * j + 1, m - 1);
+        float ax = 0.0f, ay = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kRowsPerLane / 2; ++j) {
-          const int r0 = rtop + 2 * j;
-          const float x = r0 < m ? a[(size_t)k * m + r0] : 0.0f;
-          const float y = r0 + 1 < m ? a[(size_t)k * m + r0 + 1] : 0.0f;
+        for (int k = 0; k < NCH; ++k) {
+          const float x = a[(size_t)k * m + r0], y = a[(size_t)k * m + r1];
           p1[k][j] = f2_pack(x, y);
+          ax += fabsf(x); ay += fabsf(y);
         }
+        ea = fmaxf(ea, fmaxf(ax, ay));
+      }
+      ea *= ecoef;
+      bool fast = screen_ok;                                      // warp-uniform
+      int nbad = 0;
       int hh[kRowsPerLane];
       [[maybe_unused]] int hgo[HARR ? kRowsPerLane : 1], hge[HARR ? kRowsPerLane : 1];
       const int im = hfree ? m - 1 - rtop : -1;                   // the lane's row index that is DP row m (free horizontal gaps, src/align.h:67-80)
@@ -233,9 +267,24 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
         int us = __shfl_up_sync(kFull, bs, 1), uv = __shfl_up_sync(kFull, bv, 1);
         const int fs = __shfl_sync(kFull, tchunk.x, st & 31), fv = __shfl_sync(kFull, tchunk.y, st & 31);
         if (lane == 0) { us = fs; uv = fv; }
-        unsigned long long q2[NCH];
+        if ((st & 63) == 63 && fast) {                            // 64 steps x 8 row pairs x 32 lanes screened: more than 1 in 8 failed?
+          fast = __reduce_add_sync(kFull, nbad) <= 64 * 8 * 32 / 8;
+          nbad = 0;
+        }
+        float pc[NCH];
+        unsigned long long c2[NCH];
+        float ecol = 0.0f;
 #pragma unroll
-        for (int k = 0; k < NCH; ++k) q2[k] = f2_pack(pn[k], pn[k]);
+        for (int k = 0; k < NCH; ++k) pc[k] = pn[k];
+        if (fast) {
+          float psum = pc[0], pabs = fabsf(pc[0]);
+#pragma unroll
+          for (int k = 1; k < NCH; ++k) { psum += pc[k]; pabs += fabsf(pc[k]); }
+          const float z = wxf * psum;
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) { const float ck = fmaf(wdf, pc[k], z); c2[k] = f2_pack(ck, ck); }
+          ecol = fmaf(ea, pabs, 1e-30f);
+        }
         {
           const int c1 = st - lane + 2;                           // next step's column
 #pragma unroll
@@ -249,18 +298,56 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
           const int next_diag = us;
           int d = diag;
           unsigned wlo = 0, whi = 0;
+          // substitution scores of the lane's 16 rows against this column (src/align.h:112-116): first the screened short
+          // form of every row pair -- eight independent chains, no branch --, one test for all of them ...
+          int sub[kRowsPerLane];
+          bool lit = true;
+          if (fast) {
+            lit = false;
+#pragma unroll
+            for (int j = 0; j < kRowsPerLane / 2; ++j) {
+              unsigned long long ap = f2_mul(p1[0][j], c2[0]);
+#pragma unroll
+              for (int k = 1; k < NCH; ++k) ap = f2_fma(p1[k][j], c2[k], ap);
+              const unsigned long long rn = f2_fma(f2_fma(ap, one2, magic2), one2, nmagic2);   // rint of both halves
+              const unsigned long long rem = f2_fma(rn, mone2, ap);                            // ap - rint(ap), exact
+              float s0, s1, e0, e1;
+              f2_unpack(ap, s0, s1);
+              f2_unpack(rem, e0, e1);
+              sub[2 * j] = __float2int_rz(s0); sub[2 * j + 1] = __float2int_rz(s1);
+              lit |= !(fabsf(e0) > ecol) || !(fabsf(e1) > ecol);  // true for NaN too
+            }
+          }
+          if (lit) {   // ... then, for the row pairs that failed it (all of them without the screen), the literal sequence:
+                       // k1 outer, k2 inner, every product and sum rounded as the reference rounds it
+#pragma unroll
+            for (int j = 0; j < kRowsPerLane / 2; ++j) {
+              bool need = true;
+              if (fast) {
+                unsigned long long ap = f2_mul(p1[0][j], c2[0]);
+#pragma unroll
+                for (int k = 1; k < NCH; ++k) ap = f2_fma(p1[k][j], c2[k], ap);
+                const unsigned long long rem = f2_fma(f2_fma(f2_fma(ap, one2, magic2), one2, nmagic2), mone2, ap);
+                float e0, e1;
+                f2_unpack(rem, e0, e1);
+                need = !(fabsf(e0) > ecol) || !(fabsf(e1) > ecol);
+              }
+              if (need) {
+                unsigned long long acc = 0ull;                    // (+0.0f, +0.0f)
+#pragma unroll
+                for (int k1 = 0; k1 < NCH; ++k1)
+#pragma unroll
+                  for (int k2 = 0; k2 < NCH; ++k2)
+                    acc = f2_fma(f2_mul(f2_mul(p1[k1][j], f2_pack(pc[k2], pc[k2])), k1 == k2 ? wm : wx), one2, acc);
+                float s0, s1;
+                f2_unpack(acc, s0, s1);
+                sub[2 * j] = __float2int_rz(s0); sub[2 * j + 1] = __float2int_rz(s1);
+                ++nbad;
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < kRowsPerLane / 2; ++j) {
-            // substitution scores of rows 2j, 2j+1 against this column: src/align.h:112-116, k1 outer, k2 inner
-            unsigned long long acc = 0ull;                        // (+0.0f, +0.0f)
-#pragma unroll
-            for (int k1 = 0; k1 < NCH; ++k1)
-#pragma unroll
-              for (int k2 = 0; k2 < NCH; ++k2)
-                acc = f2_fma(f2_mul(f2_mul(p1[k1][j], q2[k2]), k1 == k2 ? wm : wx), one2, acc);
-            float s0, s1;
-            f2_unpack(acc, s0, s1);
-            const int sub2[2] = {__float2int_rz(s0), __float2int_rz(s1)};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int i = 2 * j + h;
@@ -270,7 +357,7 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
               const int hn = max(sl[i] + hgo_i, hext);            // src/gotoh.h:129
               const int vext = uv + vge;
               const int vn = max(us + vgo, vext);                 // src/gotoh.h:130
-              const int s = max(max(d + sub2[h], hn), vn);        // src/gotoh.h:131
+              const int s = max(max(d + sub[i], hn), vn);         // src/gotoh.h:131
               if (TRACEBACK) {
                 unsigned f = 0;
                 if (hn != hext) f |= kHOpen;                      // src/gotoh.h:137
@@ -309,7 +396,7 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
       const int rr = (m - 1) % kPPBand;
       int val = 0;
 #pragma unroll
-      for (int i = 0; i < kRowsPerLane; ++i) if (i == (rr & 15)) val = sl[i];
+      for (int i = 0; i < kRowsPerLane; ++i) val |= sl[i] & -(int)(i == (rr & 15));   // (a select chain becomes an indexed local array, stored every step)
       score = __shfl_sync(kFull, val, rr >> 4);
     }
     if (TRACEBACK) {

@@ -184,7 +184,8 @@ int make_plan(tb_ctx* ctx, int mode, bool traceback, const Shape& sh, size_t npa
                  getenv("TRACY_B200_NO_PACKED") == nullptr;
   unsigned long long warps_pp = 0;
   const int wpb_pp = tb::gotoh_pp_warps_per_block();
-  if (mode == tb::kModePP && getenv("TRACY_B200_NO_PPFAST") == nullptr) {
+  // (the pp kernel carries the vertical state in a form that needs gap open <= 0; anything else goes to the general kernel)
+  if (mode == tb::kModePP && sc.gap_open <= 0 && getenv("TRACY_B200_NO_PPFAST") == nullptr) {
     // free-row costs in register arrays (2 blocks / SM; the default: with the screened score the cell loop is bound by the
     // integer pipe, and the selects were a third of its instructions) or, "sel", as selects (3 blocks / SM)
     const char* v = getenv("TRACY_B200_PP_VARIANT");

@@ -303,7 +303,9 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
           int sub[kRowsPerLane];
           bool lit = true;
           if (fast) {
-            lit = false;
+            // (the smallest distance of the 16 to an integer is tested once: fminf drops a NaN, but a NaN or an infinity in
+            // either profile makes ecol itself NaN or infinite, and the comparison false)
+            float emin = 1.0f;
 #pragma unroll
             for (int j = 0; j < kRowsPerLane / 2; ++j) {
               unsigned long long ap = f2_mul(p1[0][j], c2[0]);
@@ -315,8 +317,9 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
               f2_unpack(ap, s0, s1);
               f2_unpack(rem, e0, e1);
               sub[2 * j] = __float2int_rz(s0); sub[2 * j + 1] = __float2int_rz(s1);
-              lit |= !(fabsf(e0) > ecol) || !(fabsf(e1) > ecol);  // true for NaN too
+              emin = fminf(fminf(emin, fabsf(e0)), fabsf(e1));
             }
+            lit = !(emin > ecol);
           }
           if (lit) {   // ... then, for the row pairs that failed it (all of them without the screen), the literal sequence:
                        // k1 outer, k2 inner, every product and sum rounded as the reference rounds it
@@ -346,11 +349,9 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
               }
             }
           }
+          if constexpr (TRACEBACK) {
 #pragma unroll
-          for (int j = 0; j < kRowsPerLane / 2; ++j) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int i = 2 * j + h;
+            for (int i = 0; i < kRowsPerLane; ++i) {
               const int hge_i = HARR ? hge[HARR ? i : 0] : (i == im ? 0 : ge);
               const int hgo_i = HARR ? hgo[HARR ? i : 0] : (i == im ? 0 : goe);
               const int hext = hh[i] + hge_i;
@@ -358,17 +359,33 @@ gotoh_pp_kernel(const GotohBatch B, const PPWork W) {
               const int vext = uv + vge;
               const int vn = max(us + vgo, vext);                 // src/gotoh.h:130
               const int s = max(max(d + sub[i], hn), vn);         // src/gotoh.h:131
-              if (TRACEBACK) {
-                unsigned f = 0;
-                if (hn != hext) f |= kHOpen;                      // src/gotoh.h:137
-                if (vn != vext) f |= kVOpen;                      // src/gotoh.h:138
-                if (s == hn) f |= kFromH;                         // src/gotoh.h:134
-                if (s == vn) f |= kVCand;                         // src/gotoh.h:135 (walker applies the else)
-                if (i < 8) wlo |= f << (4 * i); else whi |= f << (4 * (i - 8));
-              }
+              unsigned f = 0;
+              if (hn != hext) f |= kHOpen;                        // src/gotoh.h:137
+              if (vn != vext) f |= kVOpen;                        // src/gotoh.h:138
+              if (s == hn) f |= kFromH;                           // src/gotoh.h:134
+              if (s == vn) f |= kVCand;                           // src/gotoh.h:135 (walker applies the else)
+              if (i < 8) wlo |= f << (4 * i); else whi |= f << (4 * (i - 8));
               d = sl[i];
               sl[i] = s; hh[i] = hn; us = s; uv = vn;
             }
+          } else {
+            // Score only: the vertical state travels down the lane's rows as y = V - vgo. V[r] = max(S[r-1] + vgo, V[r-1] + vge)
+            // and S[r-1] = max(x[r-1], V[r-1]), x = max(diag + sub, H), give y[r] = max(x[r-1], y[r-1] + vge) whenever
+            // vgo <= vge (gap open <= 0; the host sends other scorings to the general kernel): ONE dependent instruction
+            // per row, S and the x of every row hang off the chain. Same values as src/gotoh.h:129-131.
+            int xp = us, y = uv - vgo;
+#pragma unroll
+            for (int i = 0; i < kRowsPerLane; ++i) {
+              const int hge_i = HARR ? hge[HARR ? i : 0] : (i == im ? 0 : ge);
+              const int hgo_i = HARR ? hgo[HARR ? i : 0] : (i == im ? 0 : goe);
+              const int hn = max(sl[i] + hgo_i, hh[i] + hge_i);   // src/gotoh.h:129
+              const int x = max(d + sub[i], hn);
+              y = max(xp, y + vge);                               // src/gotoh.h:130, less vgo
+              const int s = max(x, y + vgo);                      // src/gotoh.h:131
+              d = sl[i];
+              sl[i] = s; hh[i] = hn; xp = x; us = s;
+            }
+            uv = y + vgo;
           }
           diag = next_diag;
           bs = us; bv = uv;

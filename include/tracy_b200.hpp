@@ -890,22 +890,26 @@ template <typename TProfile> inline char profile_cons_char(TProfile const& p, st
 template <typename TProfile> inline void profile_of_alignment(std::vector<std::string> const& rows, TProfile& p) {
   const std::size_t ncol = rows.empty() ? 0 : rows[0].size();
   resize_align(p, 6, ncol);
-  std::vector<long> first(rows.size(), -1), last(rows.size(), (long)ncol);
-  for (std::size_t i = 0; i < rows.size(); ++i)
-    for (std::size_t j = 0; j < ncol; ++j)
-      if (rows[i][j] != '-') { if (first[i] < 0) first[i] = (long)j; last[i] = (long)j; }
-  for (std::size_t j = 0; j < ncol; ++j) {
-    float cnt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int sum = 0;
-    for (std::size_t i = 0; i < rows.size(); ++i) {
-      if ((long)j < first[i] || (long)j > last[i]) continue;          // a row of gaps only keeps first = -1, last = ncol: like the reference it then covers every column
-      const char ch = rows[i][j];
+  // counted row by row over each row's own span (a trace covers ~1 000 of the tens of thousands of columns of a large
+  // assembly); the counts are small integers, so float(count) / sum is the reference's `cnt += 1` ... `cnt / sum`
+  std::vector<int32_t> cnt(6 * ncol, 0), sum(ncol, 0);
+  for (std::size_t i = 0; i < rows.size(); ++i) {
+    std::string const& r = rows[i];
+    const std::size_t f = r.find_first_not_of('-');
+    std::size_t lo = 0, hi = ncol;                                    // a row of gaps only covers every column, like the reference's first = -1, last = ncol
+    if (f != std::string::npos) { lo = f; hi = r.find_last_not_of('-') + 1; }
+    for (std::size_t j = lo; j < hi; ++j) {
+      const char ch = r[j];
       const int k = (ch == 'A' || ch == 'a') ? 0 : (ch == 'C' || ch == 'c') ? 1 : (ch == 'G' || ch == 'g') ? 2 : (ch == 'T' || ch == 't') ? 3
                     : (ch == 'N' || ch == 'n') ? 4 : ch == '-' ? 5 : -1;
-      if (k >= 0) { cnt[k] += 1; ++sum; }
+      if (k >= 0) { ++cnt[(std::size_t)k * ncol + j]; ++sum[j]; }
     }
-    for (int k = 0; k < 6; ++k) p[k][j] = sum > 0 ? cnt[k] / sum : cnt[k];
   }
+  for (int k = 0; k < 6; ++k)
+    for (std::size_t j = 0; j < ncol; ++j) {
+      const float c = (float)cnt[(std::size_t)k * ncol + j];
+      p[k][j] = sum[j] > 0 ? c / sum[j] : c;
+    }
 }
 // UPGMA guide tree over a SCORE matrix (reference src/msa.h:44-87: the largest score joins first, first maximum in row-major
 // order wins; the score of a new node against an open node is the mean of its children's, C++ integer division; joined nodes
@@ -982,11 +986,20 @@ inline void msa(TCtx& g, TConfig const& c, TSeqProfiles const& sps, TAlign& alig
       Node& r = node[(std::size_t)p[level[q]][2]];
       const std::string& o = ops[q];                                    // 's' both advance, 'h' gap in the left rows, 'v' gap in the right rows
       nd.rows.assign(l.rows.size() + r.rows.size(), std::string(o.size(), '-'));
-      std::size_t a1p = 0, a2p = 0;
+      std::vector<uint32_t> lpos, rpos;                                 // output column of every column of the left / right block
+      lpos.reserve(o.size()); rpos.reserve(o.size());
       for (std::size_t j = 0; j < o.size(); ++j) {
-        if (o[j] != 'h') { for (std::size_t k = 0; k < l.rows.size(); ++k) nd.rows[k][j] = l.rows[k][a1p]; ++a1p; }
-        if (o[j] != 'v') { for (std::size_t k = 0; k < r.rows.size(); ++k) nd.rows[l.rows.size() + k][j] = r.rows[k][a2p]; ++a2p; }
+        if (o[j] != 'h') lpos.push_back((uint32_t)j);
+        if (o[j] != 'v') rpos.push_back((uint32_t)j);
       }
+      auto scatter = [](std::string const& from, std::vector<uint32_t> const& pos, std::string& to) {   // row by row, only over the row's own span
+        const std::size_t f = from.find_first_not_of('-');
+        if (f == std::string::npos) return;
+        const std::size_t e = std::min(from.find_last_not_of('-') + 1, pos.size());
+        for (std::size_t t = f; t < e; ++t) to[pos[t]] = from[t];
+      };
+      for (std::size_t k = 0; k < l.rows.size(); ++k) scatter(l.rows[k], lpos, nd.rows[k]);
+      for (std::size_t k = 0; k < r.rows.size(); ++k) scatter(r.rows[k], rpos, nd.rows[l.rows.size() + k]);
       detail::profile_of_alignment(nd.rows, nd.prof);
       nd.idx = l.idx;
       nd.idx.insert(nd.idx.end(), r.idx.begin(), r.idx.end());

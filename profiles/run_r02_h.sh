@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-python profiles/bench_multi.py 100000 > gpurun_out/r02_bench_multi_n8.json 2> gpurun_out/r02_bench_multi_n8.err; cat gpurun_out/r02_bench_multi_n8.json; tail -3 gpurun_out/r02_bench_multi_n8.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err; tail -c 1500 gpurun_out/r02_bench_n8.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 3 --warmup 3 --total-pairs 1000000 > gpurun_out/r02_bench_n8_strong.json 2> gpurun_out/r02_bench_n8_strong.err; tail -c 1500 gpurun_out/r02_bench_n8_strong.json
-timeout 300 python -m pytest tests/test_gpu_multi.py -m gpu -q 2>&1 | tail -3
+oracle/_ref/dropin_test | tail -2
+g++ -std=c++17 -O2 -I include profiles/bench_assemble.cpp -o /tmp/bench_assemble -Ltracy_b200 -ltracy_b200 -Wl,-rpath,$PWD/tracy_b200 && for i in 1 2; do /tmp/bench_assemble 512 > gpurun_out/r02_bench_assemble_cpp.json 2> gpurun_out/r02_bench_assemble_cpp.err; cat gpurun_out/r02_bench_assemble_cpp.json; done
+timeout 600 python profiles/prof_assemble_stages.py > gpurun_out/r02_assemble_stages.json 2>&1; tail -c 900 gpurun_out/r02_assemble_stages.json
+timeout 900 python profiles/bench_assemble_files.py > gpurun_out/r02_bench_assemble_files.json 2> gpurun_out/r02_bench_assemble_files.err; head -c 300 gpurun_out/r02_bench_assemble_files.json

@@ -1,6 +1,7 @@
 // C ABI of tracy_b200 (include/tracy_b200.h): context, scratch sizing, host<->device staging, launches.
 // Host code only; the kernels live in gotoh_general.cu / gotoh_packed.cu / sweep.cu.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <climits>
 #include <cstdio>
@@ -55,8 +56,11 @@ struct DevBuf {
   size_t cap = 0;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    // grow geometrically: a series of calls with growing shapes (the levels of a guide tree: each merge about twice the
+    // last) would otherwise free and allocate hundreds of MB per call -- 145 ms for 0.5 GB on the pool's boxes
+    const size_t old = cap;
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
-    size_t want = bytes + bytes / 8 + 256;
+    size_t want = std::max(bytes + bytes / 8 + 256, std::min<size_t>(2 * old, (size_t)4 << 30));
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
     if (e == cudaSuccess) cap = want;
@@ -70,9 +74,12 @@ struct PinBuf {
   size_t cap = 0;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    const size_t old = cap;
     if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
-    cudaError_t e = cudaHostAlloc(&p, bytes + 256, cudaHostAllocDefault);
-    if (e == cudaSuccess) cap = bytes + 256;
+    size_t want = std::max(bytes + 256, std::min<size_t>(2 * old, (size_t)1 << 30));
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); want = bytes + 256; e = cudaHostAlloc(&p, want, cudaHostAllocDefault); }
+    if (e == cudaSuccess) cap = want;
     return e;
   }
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
@@ -642,14 +649,19 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
       bmin = std::min(bmin, bo); bmax = std::max(bmax, bo + item_elems_b(mode, l2[i]));
     }
     const size_t abytes = (size_t)(amax - amin) * esa, bbytes = (size_t)(bmax - bmin) * esb;
+    const auto hc0 = std::chrono::steady_clock::now();
+    auto hms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hc0).count(); };
     Plan cp = plan;                                       // scratch per slot sized for the batch maxima, once
     if (cn < (size_t)plan.slots) {
       size_t tickets = cn;
       if (bigp) for (size_t i = p0; i < p0 + cn; ++i) if (bigp[i]) tickets += (size_t)pp_bands(l1[i]) - 1;
       if (int rc = make_plan(ctx, mode, traceback, all, cn, sc, &cp, tickets)) return rc;
     }
+    const double h_plan = hms();
     if (int rc = reserve_scratch(ctx, L, cp)) return rc;
+    const double h_scratch = hms();
     if (cp.use_pp) if (int rc = build_pp_work(ctx, L, l1 + p0, l2 + p0, bigp ? bigp + p0 : nullptr, cn, traceback)) return rc;
+    const double h_pp = hms();
     TB_CUDA(ctx, L.a.reserve(abytes + 16)); TB_CUDA(ctx, L.b.reserve(bbytes + 16));
     TB_CUDA(ctx, L.scores.reserve(cn * 4)); TB_CUDA(ctx, L.status.reserve(cn));
     if (traceback) { TB_CUDA(ctx, L.ops.reserve(cn * (size_t)ustride)); TB_CUDA(ctx, L.ops_len.reserve(cn * 4)); }
@@ -657,6 +669,9 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     if (packed_ops) TB_CUDA(ctx, L.opk.reserve(cn * (size_t)res->ops_stride));
     // offsets and lengths of the chunk go through ONE pinned block and one copy: [a_off | b_off | a_len | b_len]
     TB_CUDA(ctx, L.meta.reserve(cn * 24)); TB_CUDA(ctx, L.meta_d.reserve(cn * 24));
+    if (trace && hms() > 2.0)
+      fprintf(stderr, "tracy_b200 chunk %zu host: plan %.2f scratch %.2f pp work %.2f buffers %.2f ms (ptr %zu MB, pp_ptr %zu MB)\n", ci, h_plan, h_scratch - h_plan,
+              h_pp - h_scratch, hms() - h_pp, L.ptr.cap >> 20, L.pp_ptr.cap >> 20);
     int64_t* hoff = static_cast<int64_t*>(L.meta.p);
     int32_t* hlen = reinterpret_cast<int32_t*>(hoff + 2 * cn);
     for (size_t i = 0; i < cn; ++i) { hoff[i] = batch->a1.off[p0 + i] - amin; hoff[cn + i] = batch->a2.off[p0 + i] - bmin; }

@@ -57,7 +57,7 @@ def profile_cons_chars(p):
     """_profileConsChar for every column (src/align.h:254-270): first strict maximum over the six rows; index >= 4 -> 'N'."""
     p = np.asarray(p, np.float32)
     idx = np.argmax(p.astype(np.float64), axis=0)          # argmax returns the first maximum, like the strict '>' scan
-    return bytes(b"ACGTNN"[int(k)] for k in idx)
+    return np.frombuffer(b"ACGTNN", np.uint8)[idx].tobytes()
 
 
 def profile_from_alignment(rows):

@@ -300,3 +300,43 @@ def test_config2_1024_pairs_vs_reference_headers(ctx, oracle_ref, oracle_port):
     assert not bad, bad[:10]
     for i in range(0, N, 64):      # the s/h/v strings say the same as the rows
         assert tracy_b200.rows_from_ops("ps", prof[i], bytes(win[i]), bytes(ops[i, : ol[i]])) == (want[i][1], want[i][2])
+
+
+def test_streamed_batch_equals_chunk_pipeline(ctx, oracle_port, monkeypatch):
+    """The streamed form of a large host batch (ONE launch of the packed kernel, inputs gated chunk by chunk, results sent off as the
+    chunks finish; capi.cu run_gotoh `streamed`) against the launch-per-chunk pipeline (TRACY_B200_NO_STREAM): scores, lengths,
+    plain ops, 2-bit packed ops and both gapped rows; score only; and a batch in which every 97th window carries a character the packed
+    kernel leaves to the second stage (which then runs on the resident batch)."""
+    N, m, n = 60000, 300, 900
+    base_p, base_w = synth.align_batch(2048, m, n, seed=77)
+    idx = (np.arange(N) * 13 + 5) % 2048
+    prof, win = np.ascontiguousarray(base_p[idx]), np.ascontiguousarray(base_w[idx])
+    sc, ac = DnaScore(3, -5, -10, -4), AlignConfig(True, False)
+    for k in ("TRACY_B200_CHUNK", "TRACY_B200_LANES", "TRACY_B200_NO_RAMPDOWN", "TRACY_B200_NO_STREAM"):
+        monkeypatch.delenv(k, raising=False)
+
+    def both(fn):
+        got = fn()
+        monkeypatch.setenv("TRACY_B200_NO_STREAM", "1")
+        want = fn()
+        monkeypatch.delenv("TRACY_B200_NO_STREAM")
+        return got, want
+
+    for variant in range(2):
+        if variant == 1:
+            win = win.copy()
+            win[::97, 450] = ord("R")                                     # IUPAC code: not a packed-kernel pair
+        a1, a2 = tracy_b200.uniform_profiles(prof), tracy_b200.uniform_seqs(win)
+        (s0, o0, l0, r0, r1), (s1, o1, l1, q0, q1) = both(lambda: ctx.gotoh("ps", a1, a2, sc, ac, rows=True))
+        assert np.array_equal(s0, s1) and np.array_equal(l0, l1)
+        mask = np.arange(o0.shape[1])[None, :] < l0[:, None]
+        assert np.array_equal(o0 * mask, o1 * mask) and np.array_equal(r0 * mask, q0 * mask) and np.array_equal(r1 * mask, q1 * mask)
+        (s2, p2, l2), (s3, p3, l3) = both(lambda: ctx.gotoh("ps", a1, a2, sc, ac, packed=True))
+        assert np.array_equal(s0, s2) and np.array_equal(s0, s3) and np.array_equal(l0, l2) and np.array_equal(l0, l3)
+        pm = np.arange(p2.shape[1])[None, :] < ((l0 + 3) // 4)[:, None]
+        assert np.array_equal(p2 * pm, p3 * pm)
+        (s4, _, _), (s5, _, _) = both(lambda: ctx.gotoh("ps", a1, a2, sc, ac, traceback=False))
+        assert np.array_equal(s0, s4) and np.array_equal(s0, s5)
+        for i in (0, 1, 97, 1775, 1776, 5328, N // 2, N - 1777, N - 1):
+            ws, wops = oracle_port.gotoh_ps(prof[i], bytes(win[i]), 1, 0, (3, -5, -10, -4))
+            assert int(s0[i]) == ws and bytes(o0[i, : l0[i]]) == wops, (variant, i)

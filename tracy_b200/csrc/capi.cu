@@ -105,6 +105,7 @@ struct Lane {   // one in-flight chunk of a TB_MEM_HOST batch
   DevBuf row0, row1, opk;                  // host-mode outputs made by post_ops.cu: gapped rows, 2-bit packed ops
   DevBuf pp_units, pp_small, pp_big, pp_rowbuf, pp_ptr, pp_flags;   // big-pair work list and scratch of the profile x profile kernel
   PinBuf pp_stage;
+  DevBuf gate; PinBuf gate_host;           // streamed host batches: gate words of the packed kernel, and their host side
   tb::PPWork ppw{};
   PinBuf meta, cnt;
   bool timed = false, timed2 = false;
@@ -632,6 +633,212 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     sched.push_back(tail_w[0]); sched.push_back(tail_w[1]); sched.push_back(tail_w[2] + rest % wave);
   } else {
     for (size_t ci = 0, p0 = 0; p0 < np; ++ci) { const size_t cn = std::min(ramp && ci < 3 ? (wave << ci) : chunk, np - p0); sched.push_back(cn); p0 += cn; }
+  }
+  // ---- Streamed form: ONE launch of the packed kernel for the whole batch (GotohBatch::gate_*, gotoh_packed.cu). The copy
+  // stream brings the chunks in one after the other and raises the count of pairs that have landed after each; the kernel's
+  // warps take pairs in index order and wait at that count; the warp that finishes the last pair of a chunk sets the chunk's
+  // word in page-locked host memory, and the host then sends that chunk's results off on a third stream. What a launch per
+  // chunk loses at every boundary -- the warps of a block idling until its slowest one is through -- is paid once, at the
+  // end. Needs the whole batch resident (2.4 GB in, 1.1 GB out for 100 k pairs of 1000 x 4000: HBM has room), chunks that
+  // occupy disjoint, increasing arena ranges, and the packed kernel; anything else takes the chunk pipeline below.
+  const auto call_t0 = std::chrono::steady_clock::now();
+  auto streamed = [&](bool* took) -> int {
+    *took = false;
+    auto decline = [&](const char* why) { if (trace) fprintf(stderr, "tracy_b200 streamed form not taken: %s\n", why); return TB_OK; };
+    if (getenv("TRACY_B200_NO_STREAM")) return TB_OK;
+    if (!plan.use_packed) return decline("not a packed-kernel batch");
+    if (np < 16 * wave) return decline("fewer than 16 waves");
+    // its own chunk schedule, in whole waves: 1, 1, 2, 4 to start the kernel after a short first copy, 4 in the middle, 2 and 1 (plus
+    // the part of a wave at the very end) so that little is left to send when the kernel ends
+    std::vector<size_t> sched;
+    {
+      const size_t rem = np % wave, waves = np / wave;    // waves >= 16
+      for (size_t w : {(size_t)1, (size_t)1, (size_t)2, (size_t)4}) sched.push_back(w * wave);
+      size_t mid = waves - 8 - 3;
+      while (mid >= 8) { sched.push_back(4 * wave); mid -= 4; }
+      if (mid) sched.push_back(mid * wave);
+      sched.push_back(2 * wave); sched.push_back(wave + rem);
+    }
+    const size_t nch = sched.size();
+    std::vector<long long> ca0(nch), ca1(nch), cb0(nch), cb1(nch);
+    std::vector<size_t> cp0(nch + 1, 0);
+    for (size_t c = 0, p0 = 0; c < nch; ++c) {
+      const size_t cn = std::min(sched[c], np - p0);
+      long long amin = LLONG_MAX, amax = LLONG_MIN, bmin = LLONG_MAX, bmax = LLONG_MIN;
+      for (size_t i = p0; i < p0 + cn; ++i) {
+        const long long ao = batch->a1.off[i], bo = batch->a2.off[i];
+        if (ao < 0 || bo < 0) return fail(ctx, TB_ERR_INVALID, "negative arena offset");
+        amin = std::min(amin, ao); amax = std::max(amax, ao + item_elems_a(mode, l1[i]));
+        bmin = std::min(bmin, bo); bmax = std::max(bmax, bo + item_elems_b(mode, l2[i]));
+      }
+      if (c && (amin < ca1[c - 1] || bmin < cb1[c - 1])) return decline("chunks share arena ranges");   // or use them out of order: chunk pipeline
+      ca0[c] = amin; ca1[c] = amax; cb0[c] = bmin; cb1[c] = bmax;
+      p0 += cn; cp0[c + 1] = p0;
+    }
+    if (cp0[nch] != np) return decline("schedule does not cover the batch");
+    const long long a_lo = ca0[0], b_lo = cb0[0];
+    const size_t abytes = (size_t)(ca1[nch - 1] - a_lo) * esa, bbytes = (size_t)(cb1[nch - 1] - b_lo) * esb;
+    const size_t out_per_pair = 4 + 1 + (traceback ? (size_t)ustride + 4 : 0) + (want_rows ? 2 * (size_t)res->rows_stride : 0) + (packed_ops ? (size_t)res->ops_stride : 0);
+    if (ctx->lanes[0].a.cap < abytes + 16 || ctx->lanes[0].b.cap < bbytes + 16 || ctx->lanes[0].row0.cap < (want_rows ? np * (size_t)res->rows_stride : 0) ||
+        ctx->lanes[0].ops.cap < (traceback ? np * (size_t)ustride : 0)) {
+      size_t fr = 0, tot = 0;
+      TB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+      const size_t held = ctx->lanes[0].a.cap + ctx->lanes[0].b.cap + ctx->lanes[0].ops.cap + ctx->lanes[0].row0.cap + ctx->lanes[0].row1.cap + ctx->lanes[0].opk.cap;
+      if (abytes + bbytes + np * (out_per_pair + 24) > (fr + held) / 2) return decline("batch does not fit in half of the free HBM");
+    }
+    Lane& K = ctx->lanes[0];                              // kernel stream; lanes[1].stream: copies in, lanes[2].stream: copies out
+    cudaStream_t s_in = ctx->lanes[1].stream, s_out = ctx->lanes[2].stream;
+    if (int rc = reserve_scratch(ctx, K, plan)) return rc;
+    TB_CUDA(ctx, K.a.reserve(abytes + 16)); TB_CUDA(ctx, K.b.reserve(bbytes + 16));
+    TB_CUDA(ctx, K.scores.reserve(np * 4)); TB_CUDA(ctx, K.status.reserve(np));
+    if (traceback) { TB_CUDA(ctx, K.ops.reserve(np * (size_t)ustride)); TB_CUDA(ctx, K.ops_len.reserve(np * 4)); }
+    if (want_rows) { TB_CUDA(ctx, K.row0.reserve(np * (size_t)res->rows_stride)); TB_CUDA(ctx, K.row1.reserve(np * (size_t)res->rows_stride)); }
+    if (packed_ops) TB_CUDA(ctx, K.opk.reserve(np * (size_t)res->ops_stride));
+    TB_CUDA(ctx, K.meta.reserve(np * 24)); TB_CUDA(ctx, K.meta_d.reserve(np * 24));
+    // gate words: device [ready | pad .. 64 | done[nch] | end[nch]], host (page-locked) [flag[nch] | ready value per chunk [nch] | end[nch]]
+    const size_t gate_dev = 64 + nch * 8;
+    TB_CUDA(ctx, K.gate.reserve(gate_dev)); TB_CUDA(ctx, K.gate_host.reserve(nch * 12));
+    volatile int32_t* hflag = static_cast<volatile int32_t*>(K.gate_host.p);
+    uint32_t* hready = reinterpret_cast<uint32_t*>(const_cast<int32_t*>(hflag) + nch);
+    int32_t* hend = reinterpret_cast<int32_t*>(hready + nch);
+    for (size_t c = 0; c < nch; ++c) { hflag[c] = 0; hready[c] = (uint32_t)cp0[c + 1]; hend[c] = (int32_t)cp0[c + 1]; }
+    void* hflag_dev = nullptr;
+    TB_CUDA(ctx, cudaHostGetDevicePointer(&hflag_dev, K.gate_host.p, 0));
+    unsigned int* g_ready = K.gate.as<unsigned int>();
+    unsigned int* g_done = g_ready + 16;
+    int32_t* g_end = reinterpret_cast<int32_t*>(g_done + nch);
+
+    int64_t* hoff = static_cast<int64_t*>(K.meta.p);
+    int32_t* hlen = reinterpret_cast<int32_t*>(hoff + 2 * np);
+    for (size_t i = 0; i < np; ++i) { hoff[i] = batch->a1.off[i] - a_lo; hoff[np + i] = batch->a2.off[i] - b_lo; }
+    std::memcpy(hlen, l1, np * 4); std::memcpy(hlen + np, l2, np * 4);
+
+    TB_CUDA(ctx, cudaEventRecord(ctx->t0, K.stream));
+    // Nothing that runs as a kernel may be queued behind the launch on the copy streams: the persistent grid holds every SM
+    // while it waits at the gate, and a memset queued ahead of the gate's update would never start. Rows 4 and 5 of a
+    // 4-row upload are therefore zeroed for the whole batch up front.
+    const int up_rows = !a_rows5 ? 6 : (!no_rows4 && a1_trace_profiles) ? 4 : want_rows ? 6 : 5;
+    if (a_rows5 && up_rows == 4) {
+      const size_t len = (size_t)l1[0], pitch = 6 * len * 4;
+      TB_CUDA(ctx, cudaMemset2DAsync((char*)K.a.p + 4 * len * 4, pitch, 0, 2 * len * 4, np, s_in));
+    }
+    TB_CUDA(ctx, cudaMemsetAsync(K.gate.p, 0, gate_dev, s_in));
+    TB_CUDA(ctx, cudaMemcpyAsync(g_end, hend, nch * 4, cudaMemcpyHostToDevice, s_in));
+    TB_CUDA(ctx, cudaMemcpyAsync(K.meta_d.p, hoff, np * 24, cudaMemcpyHostToDevice, s_in));
+    TB_CUDA(ctx, cudaEventRecord(K.in_done, s_in));
+    TB_CUDA(ctx, cudaStreamWaitEvent(K.stream, K.in_done, 0));
+    ctx->h2d += np * 24 + nch * 4;
+
+    tb::GotohBatch C = B;
+    int64_t* doff = K.meta_d.as<int64_t>();
+    int32_t* dlen = reinterpret_cast<int32_t*>(doff + 2 * np);
+    C.a_base = K.a.p; C.a_off = doff; C.a_len = dlen;
+    C.b_base = K.b.p; C.b_off = doff + np; C.b_len = dlen + np;
+    C.scores = K.scores.as<int32_t>(); C.ops = traceback ? K.ops.as<uint8_t>() : nullptr;
+    C.ops_stride = ustride; C.ops_len = traceback ? K.ops_len.as<int32_t>() : nullptr;
+    C.status = K.status.as<uint8_t>(); C.npairs = (int)np;
+    C.row0 = want_rows ? K.row0.as<uint8_t>() : nullptr; C.row1 = want_rows ? K.row1.as<uint8_t>() : nullptr; C.rows_stride = res->rows_stride;
+    C.opk = packed_ops ? K.opk.as<uint8_t>() : nullptr; C.opk_stride = packed_ops ? res->ops_stride : 0;
+    C.gate_ready = g_ready; C.gate_done = g_done; C.gate_end = g_end; C.gate_host = static_cast<volatile int32_t*>(hflag_dev);
+    if (int rc = enqueue_gotoh(ctx, K, mode, traceback, C, plan)) return rc;
+    K.view.gate_ready = nullptr; K.view.gate_done = nullptr; K.view.gate_end = nullptr; K.view.gate_host = nullptr;   // a second stage runs ungated
+    *took = true;
+
+    auto send_out = [&](size_t p0, size_t cn) -> int {
+      TB_CUDA(ctx, cudaMemcpyAsync(res->scores + p0, K.scores.as<int32_t>() + p0, cn * 4, cudaMemcpyDeviceToHost, s_out));
+      ctx->d2h += cn * 4;
+      if (traceback) {
+        if (plain_ops) TB_CUDA(ctx, cudaMemcpyAsync(res->ops + p0 * (size_t)ustride, K.ops.as<uint8_t>() + p0 * (size_t)ustride, cn * (size_t)ustride, cudaMemcpyDeviceToHost, s_out));
+        if (packed_ops) TB_CUDA(ctx, cudaMemcpyAsync(res->ops + p0 * (size_t)res->ops_stride, K.opk.as<uint8_t>() + p0 * (size_t)res->ops_stride, cn * (size_t)res->ops_stride, cudaMemcpyDeviceToHost, s_out));
+        if (want_rows) {
+          TB_CUDA(ctx, cudaMemcpyAsync(res->row0 + p0 * (size_t)res->rows_stride, K.row0.as<uint8_t>() + p0 * (size_t)res->rows_stride, cn * (size_t)res->rows_stride, cudaMemcpyDeviceToHost, s_out));
+          TB_CUDA(ctx, cudaMemcpyAsync(res->row1 + p0 * (size_t)res->rows_stride, K.row1.as<uint8_t>() + p0 * (size_t)res->rows_stride, cn * (size_t)res->rows_stride, cudaMemcpyDeviceToHost, s_out));
+        }
+        TB_CUDA(ctx, cudaMemcpyAsync(res->ops_len + p0, K.ops_len.as<int32_t>() + p0, cn * 4, cudaMemcpyDeviceToHost, s_out));
+        ctx->d2h += (plain_ops ? cn * (size_t)ustride : 0) + (packed_ops ? cn * (size_t)res->ops_stride : 0) + (want_rows ? 2 * cn * (size_t)res->rows_stride : 0) + cn * 4;
+      }
+      return TB_OK;
+    };
+    const auto w0 = std::chrono::steady_clock::now();
+    auto wall_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(); };
+    if (trace) fprintf(stderr, "tracy_b200 streamed batch: %zu pairs in %zu chunks, launched %.2f ms into the call\n", np, nch,
+                       std::chrono::duration<double, std::milli>(w0 - call_t0).count());
+    auto after_launch = [&]() -> int {
+    size_t sent = 0;                                      // chunks whose results are on their way
+    auto drain = [&](bool wait) -> int {                  // send off every chunk the kernel has finished (wait: block for the next one)
+      double idle0 = wall_ms();
+      while (sent < nch) {
+        if (!hflag[sent]) {
+          if (!wait) return TB_OK;
+          const cudaError_t q = cudaStreamQuery(K.stream);
+          if (q != cudaSuccess && q != cudaErrorNotReady) { ctx->err = std::string("streamed batch: ") + cudaGetErrorString(q); cudaGetLastError(); return TB_ERR_CUDA; }
+          if (q == cudaSuccess && !hflag[sent]) {         // the kernel is gone: its count is final (pairs left to a second stage are counted too)
+            hflag[sent] = 1; continue;
+          }
+          if (wall_ms() - idle0 > 60000.0) return fail(ctx, TB_ERR_CUDA, "streamed batch: no chunk finished for 60 s");
+          std::this_thread::yield();
+          continue;
+        }
+        if (trace) fprintf(stderr, "tracy_b200 streamed chunk %zu (%zu pairs) finished at %.2f ms\n", sent, cp0[sent + 1] - cp0[sent], wall_ms());
+        if (int rc = send_out(cp0[sent], cp0[sent + 1] - cp0[sent])) return rc;
+        ++sent; idle0 = wall_ms();
+      }
+      return TB_OK;
+    };
+    for (size_t c = 0; c < nch; ++c) {                    // inputs, chunk by chunk, each followed by the new count
+      const size_t p0 = cp0[c], cn = cp0[c + 1] - p0;
+      const size_t ab = (size_t)(ca1[c] - ca0[c]) * esa, bb = (size_t)(cb1[c] - cb0[c]) * esb;
+      char* da = (char*)K.a.p + (size_t)(ca0[c] - a_lo) * esa;
+      if (a_rows5) {
+        const size_t len = (size_t)l1[0], pitch = 6 * len * 4;
+        const float* src = (const float*)batch->a1.base + ca0[c];
+        TB_CUDA(ctx, cudaMemcpy2DAsync(da, pitch, src, pitch, (size_t)up_rows * len * 4, cn, cudaMemcpyHostToDevice, s_in));
+        ctx->h2d += (size_t)up_rows * len * 4 * cn;
+      } else {
+        TB_CUDA(ctx, cudaMemcpyAsync(da, (const char*)batch->a1.base + (size_t)ca0[c] * esa, ab, cudaMemcpyHostToDevice, s_in));
+        ctx->h2d += ab;
+      }
+      TB_CUDA(ctx, cudaMemcpyAsync((char*)K.b.p + (size_t)(cb0[c] - b_lo) * esb, (const char*)batch->a2.base + (size_t)cb0[c] * esb, bb, cudaMemcpyHostToDevice, s_in));
+      TB_CUDA(ctx, cudaMemcpyAsync(g_ready, hready + c, 4, cudaMemcpyHostToDevice, s_in));
+      ctx->h2d += bb + 4;
+      if (int rc = drain(false)) return rc;               // (pageable inputs block in the copies above: results leave meanwhile)
+    }
+    if (int rc = drain(true)) return rc;
+    TB_CUDA(ctx, cudaStreamSynchronize(K.stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(s_in));
+    bool again = false;
+    if (int rc = finish_gotoh(ctx, K, &again)) return rc;
+    if (again) {                                          // pairs the packed kernel left: the second stage ran on the resident batch, fetch everything again
+      TB_CUDA(ctx, cudaStreamSynchronize(K.stream));
+      if (int rc = send_out(0, np)) return rc;
+    }
+    TB_CUDA(ctx, cudaStreamSynchronize(s_out));
+    if (trace) fprintf(stderr, "tracy_b200 streamed batch: last result landed at %.2f ms\n", wall_ms());
+    TB_CUDA(ctx, cudaEventElapsedTime(&ctx->last_call_ms, K.c0, K.kend));
+    return collect_timing(ctx, K);
+    };
+    const int arc = after_launch();
+    if (arc != TB_OK) {                                   // whatever went wrong, the kernel must not wait at the gate for ever
+      const std::string keep = ctx->err;
+      const uint32_t all = (uint32_t)np;
+      cudaMemcpy(g_ready, &all, 4, cudaMemcpyHostToDevice);
+      cudaGetLastError();
+      ctx->err = keep;
+    }
+    return arc;
+  };
+  {
+    bool took = false;
+    const int src = streamed(&took);
+    if (src != TB_OK || took) {
+      if (src != TB_OK) {
+        const std::string keep = ctx->err;
+        for (int i = 0; i < kLanes; ++i) { cudaStreamSynchronize(ctx->lanes[i].stream); ctx->lanes[i].chunk = -1; ctx->lanes[i].timed = ctx->lanes[i].timed2 = false; }
+        cudaGetLastError();
+        ctx->err = keep;
+      }
+      return src;
+    }
   }
   auto pipeline = [&]() -> int {
   size_t nchunks = 0;

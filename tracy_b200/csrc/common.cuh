@@ -41,6 +41,12 @@ struct GotohBatch {
   uint8_t* row0; uint8_t* row1; int64_t rows_stride;                   // gapped alignment rows; nullptr: not wanted
   uint8_t* opk; int64_t opk_stride;                                    // ops at 2 bits each; nullptr: not wanted
   int mode;                                                            // kModePS / kModePP / kModeSS: how a1 / a2 read
+  // Streamed host batches (capi.cu: run_gotoh_streamed; packed kernel only): ONE launch works through the whole batch while
+  // its inputs are still arriving and its results are already leaving. gate_ready: number of pairs (a prefix, in index order)
+  // whose inputs have landed, written by the copy stream after each chunk; gate_done[c]: pairs of chunk c the kernel is
+  // through with; gate_end[c]: index one past chunk c's last pair; gate_host[c] (page-locked host memory): set by the
+  // warp that finishes chunk c's last pair, after which the host sends the chunk's results on their way. nullptr: no gates.
+  const unsigned int* gate_ready; unsigned int* gate_done; const int32_t* gate_end; volatile int32_t* gate_host;
 };
 
 // Work list of the profile x profile kernel (gotoh_pp.cu). Tickets 0 .. nunits-1 are (pair, band) units of "big" pairs

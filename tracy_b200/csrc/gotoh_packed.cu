@@ -586,12 +586,36 @@ gotoh_packed_kernel(const GotohBatch B) {
   unsigned* const rowbuf0 = reinterpret_cast<unsigned*>(B.rowbuf + (unsigned long long)slot * B.rowbuf_slot);
   uint8_t* const ops_rev = TRACEBACK ? B.ops_scratch + (unsigned long long)slot * B.ops_slot : nullptr;
 
+  int gate_prev = -1, gate_c = 0;                        // streamed batches: the ticket this warp has yet to report, its chunk
   for (;;) {
+    if (B.gate_ready && gate_prev >= 0) {                // through with a pair (finished or left to a later kernel): count it
+      __syncwarp();
+      if (lane == 0) {
+        while (gate_prev >= B.gate_end[gate_c]) ++gate_c;
+        __threadfence();                                 // the pair's results before the count
+        const unsigned int seen = atomicAdd(B.gate_done + gate_c, 1u);
+        const int size = B.gate_end[gate_c] - (gate_c ? B.gate_end[gate_c - 1] : 0);
+        if ((int)seen + 1 == size) { __threadfence_system(); B.gate_host[gate_c] = 1; }   // the chunk is complete: tell the host
+      }
+      gate_prev = -1;
+    }
     int q = 0;
     if (lane == 0) q = (int)atomicAdd(B.counter, 1u);
     q = __shfl_sync(kFull, q, 0);
     if (q >= B.npairs) break;
     const int pi = B.order ? B.order[q] : q;
+    if (B.gate_ready) {                                  // wait for the pair's inputs (tickets and arrivals both go in index order)
+      gate_prev = q;
+      if (lane == 0) {
+        unsigned int have;
+        for (;;) {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(B.gate_ready) : "memory");
+          if (have > (unsigned int)pi) break;
+          __nanosleep(500);
+        }
+      }
+      __syncwarp();
+    }
     if (B.status[pi]) continue;                          // finished by an earlier kernel of this call
     const int m = B.a_len[pi], n = B.b_len[pi];
     if (m == 0 || n == 0) continue;                      // degenerate shapes: general kernel

@@ -15,6 +15,7 @@ ctx = tracy_b200.Context(0)
 a1, a2 = tracy_b200.uniform_profiles(prof), tracy_b200.uniform_seqs(win)
 sc, ac = DnaScore(3, -5, -10, -4), AlignConfig(True, False)
 os.environ["TRACY_B200_TRACE"] = "1"
+os.environ["TRACY_B200_FORCE_STREAM"] = "1"
 s0, o0, l0, r0, r1 = ctx.gotoh("ps", a1, a2, sc, ac, rows=True)
 os.environ["TRACY_B200_NO_STREAM"] = "1"
 s1, o1, l1, q0, q1 = ctx.gotoh("ps", a1, a2, sc, ac, rows=True)

@@ -314,6 +314,7 @@ def test_streamed_batch_equals_chunk_pipeline(ctx, oracle_port, monkeypatch):
     sc, ac = DnaScore(3, -5, -10, -4), AlignConfig(True, False)
     for k in ("TRACY_B200_CHUNK", "TRACY_B200_LANES", "TRACY_B200_NO_RAMPDOWN", "TRACY_B200_NO_STREAM"):
         monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("TRACY_B200_FORCE_STREAM", "1")      # pageable inputs arrive slowly: without it the context would fall back after the first call
 
     def both(fn):
         got = fn()

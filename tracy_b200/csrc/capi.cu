@@ -653,6 +653,15 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     // moves the same bytes ~6 % sooner (8 x B200: 172 against 183 ms per step): a streamed call whose last input landed
     // in the last 15 % of the kernel's run sends the next 31 eligible calls down the other road.
     const bool force_stream = getenv("TRACY_B200_FORCE_STREAM") != nullptr;   // tests: always streamed when eligible
+    bool inputs_pinned = false;
+    {
+      cudaPointerAttributes pa{}, pb{};
+      inputs_pinned = cudaPointerGetAttributes(&pa, batch->a1.base) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                      cudaPointerGetAttributes(&pb, batch->a2.base) == cudaSuccess && pb.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+    }
+    if (!inputs_pinned && (getenv("CUDA_LAUNCH_BLOCKING") || getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")))
+      return decline("pageable inputs go in after the launch, and this process may not return from a launch before the kernel ends");
     if (ctx->stream_backoff > 0 && !force_stream) { --ctx->stream_backoff; return decline("the host link was the limit last time: launch per chunk"); }
     // its own chunk schedule, in whole waves: 1, 1, 2, 4 to start the kernel after a short first copy, 4 in the middle, 2 and 1 (plus
     // the part of a wave at the very end) so that little is left to send when the kernel ends
@@ -735,6 +744,33 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     TB_CUDA(ctx, cudaStreamWaitEvent(K.stream, K.in_done, 0));
     ctx->h2d += np * 24 + nch * 4;
 
+    // Inputs, chunk by chunk, each followed by the new count. Page-locked inputs: every copy is queued BEFORE the launch, so
+    // the kernel's progress never depends on what this thread does after it -- a launch call that does not return until the
+    // kernel has finished (a profiler serialising launches, CUDA_LAUNCH_BLOCKING) then costs the overlap, not the call.
+    // Pageable inputs block in cudaMemcpyAsync: they are sent after the launch, results leaving in between.
+    auto send_in = [&](size_t c) -> int {
+      const size_t p0 = cp0[c], cn = cp0[c + 1] - p0;
+      const size_t ab = (size_t)(ca1[c] - ca0[c]) * esa, bb = (size_t)(cb1[c] - cb0[c]) * esb;
+      char* da = (char*)K.a.p + (size_t)(ca0[c] - a_lo) * esa;
+      if (a_rows5) {
+        const size_t len = (size_t)l1[0], pitch = 6 * len * 4;
+        const float* src = (const float*)batch->a1.base + ca0[c];
+        TB_CUDA(ctx, cudaMemcpy2DAsync(da, pitch, src, pitch, (size_t)up_rows * len * 4, cn, cudaMemcpyHostToDevice, s_in));
+        ctx->h2d += (size_t)up_rows * len * 4 * cn;
+      } else {
+        TB_CUDA(ctx, cudaMemcpyAsync(da, (const char*)batch->a1.base + (size_t)ca0[c] * esa, ab, cudaMemcpyHostToDevice, s_in));
+        ctx->h2d += ab;
+      }
+      TB_CUDA(ctx, cudaMemcpyAsync((char*)K.b.p + (size_t)(cb0[c] - b_lo) * esb, (const char*)batch->a2.base + (size_t)cb0[c] * esb, bb, cudaMemcpyHostToDevice, s_in));
+      TB_CUDA(ctx, cudaMemcpyAsync(g_ready, hready + c, 4, cudaMemcpyHostToDevice, s_in));
+      ctx->h2d += bb + 4;
+      return TB_OK;
+    };
+    if (inputs_pinned) {
+      for (size_t c = 0; c < nch; ++c) if (int rc = send_in(c)) return rc;
+      TB_CUDA(ctx, cudaEventRecord(ctx->lanes[1].h0, s_in));
+    }
+
     tb::GotohBatch C = B;
     int64_t* doff = K.meta_d.as<int64_t>();
     int32_t* dlen = reinterpret_cast<int32_t*>(doff + 2 * np);
@@ -791,25 +827,13 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
       }
       return TB_OK;
     };
-    for (size_t c = 0; c < nch; ++c) {                    // inputs, chunk by chunk, each followed by the new count
-      const size_t p0 = cp0[c], cn = cp0[c + 1] - p0;
-      const size_t ab = (size_t)(ca1[c] - ca0[c]) * esa, bb = (size_t)(cb1[c] - cb0[c]) * esb;
-      char* da = (char*)K.a.p + (size_t)(ca0[c] - a_lo) * esa;
-      if (a_rows5) {
-        const size_t len = (size_t)l1[0], pitch = 6 * len * 4;
-        const float* src = (const float*)batch->a1.base + ca0[c];
-        TB_CUDA(ctx, cudaMemcpy2DAsync(da, pitch, src, pitch, (size_t)up_rows * len * 4, cn, cudaMemcpyHostToDevice, s_in));
-        ctx->h2d += (size_t)up_rows * len * 4 * cn;
-      } else {
-        TB_CUDA(ctx, cudaMemcpyAsync(da, (const char*)batch->a1.base + (size_t)ca0[c] * esa, ab, cudaMemcpyHostToDevice, s_in));
-        ctx->h2d += ab;
+    if (!inputs_pinned) {
+      for (size_t c = 0; c < nch; ++c) {
+        if (int rc = send_in(c)) return rc;
+        if (int rc = drain(false)) return rc;
       }
-      TB_CUDA(ctx, cudaMemcpyAsync((char*)K.b.p + (size_t)(cb0[c] - b_lo) * esb, (const char*)batch->a2.base + (size_t)cb0[c] * esb, bb, cudaMemcpyHostToDevice, s_in));
-      TB_CUDA(ctx, cudaMemcpyAsync(g_ready, hready + c, 4, cudaMemcpyHostToDevice, s_in));
-      ctx->h2d += bb + 4;
-      if (int rc = drain(false)) return rc;               // (pageable inputs block in the copies above: results leave meanwhile)
+      TB_CUDA(ctx, cudaEventRecord(ctx->lanes[1].h0, s_in));
     }
-    TB_CUDA(ctx, cudaEventRecord(ctx->lanes[1].h0, s_in));
     if (int rc = drain(true)) return rc;
     TB_CUDA(ctx, cudaStreamSynchronize(K.stream));
     TB_CUDA(ctx, cudaStreamSynchronize(s_in));

@@ -215,15 +215,28 @@ inline std::vector<int32_t> gotohBatch(TCtx& g, std::vector<const TA*> const& a1
   std::vector<int32_t> la(n), lb(n);
   std::vector<std::size_t> ua, ub;
   std::unordered_map<const void*, int64_t> seen_a, seen_b;
+  // (an all-pairs list names a thousand objects a million times: a direct-mapped front of 4 096 slots answers those without hashing)
+  struct Slot { const void* p; int64_t off; };
+  std::vector<Slot> front_a(4096, Slot{nullptr, 0}), front_b(4096, Slot{nullptr, 0});
+  auto known = [](std::vector<Slot>& front, std::unordered_map<const void*, int64_t>& seen, const void* p, int64_t& off) -> bool {
+    Slot& s = front[(reinterpret_cast<std::uintptr_t>(p) >> 5) & 4095u];
+    if (s.p == p) { off = s.off; return true; }
+    auto it = seen.find(p);
+    if (it == seen.end()) return false;
+    s.p = p; s.off = it->second; off = it->second;
+    return true;
+  };
   int64_t stride = 16, tot_a = 0, tot_b = 0;
   for (std::size_t i = 0; i < n; ++i) {
     la[i] = detail::item_len(*a1[i]); lb[i] = detail::item_len(*a2[i]);
-    auto ia = seen_a.find(a1[i]);
-    if (ia != seen_a.end()) oa[i] = ia->second;
-    else { oa[i] = tot_a; seen_a.emplace(a1[i], tot_a); ua.push_back(i); tot_a += (sa ? 1 : 6) * (int64_t)la[i]; }
-    auto ib = seen_b.find(a2[i]);
-    if (ib != seen_b.end()) ob[i] = ib->second;
-    else { ob[i] = tot_b; seen_b.emplace(a2[i], tot_b); ub.push_back(i); tot_b += (sb ? 1 : 6) * (int64_t)lb[i]; }
+    if (!known(front_a, seen_a, a1[i], oa[i])) {
+      oa[i] = tot_a; seen_a.emplace(a1[i], tot_a); front_a[(reinterpret_cast<std::uintptr_t>((const void*)a1[i]) >> 5) & 4095u] = Slot{a1[i], tot_a};
+      ua.push_back(i); tot_a += (sa ? 1 : 6) * (int64_t)la[i];
+    }
+    if (!known(front_b, seen_b, a2[i], ob[i])) {
+      ob[i] = tot_b; seen_b.emplace(a2[i], tot_b); front_b[(reinterpret_cast<std::uintptr_t>((const void*)a2[i]) >> 5) & 4095u] = Slot{a2[i], tot_b};
+      ub.push_back(i); tot_b += (sb ? 1 : 6) * (int64_t)lb[i];
+    }
     stride = std::max<int64_t>(stride, ((int64_t)la[i] + lb[i] + 15) / 16 * 16);
   }
   std::unique_ptr<EA[]> pa(new EA[(std::size_t)std::max<int64_t>(tot_a, 1)]);
@@ -915,21 +928,39 @@ template <typename TProfile> inline void profile_of_alignment(std::vector<std::s
 // order wins; the score of a new node against an open node is the mean of its children's, C++ integer division; joined nodes
 // leave the matrix). d: (2 num + 1)^2 ints, upper triangle, -1 = closed. p[v] = {parent, left, right}, -1 = none. Returns the root.
 inline long upgma_tree(std::vector<std::vector<int> >& d, std::vector<std::vector<int> >& p, long num) {
+  // The reference scans the whole upper triangle for every join (O(n^3)); here every row keeps its maximum and the FIRST column
+  // that holds it, so the first maximum in row-major order is the first row whose maximum beats the running one: same joins,
+  // same ties, O(n^2) plus the rescans of rows whose maximum sat in a column that closes.
+  const long cap = 2 * num + 1;
+  std::vector<int> rmax((std::size_t)cap, -1);
+  std::vector<long> rarg((std::size_t)cap, 0);
+  auto rescan = [&](long i, long hi) {                                  // row i over columns i+1 .. hi-1
+    int top = -1; long arg = 0;
+    for (long j = i + 1; j < hi; ++j) if (d[(std::size_t)i][(std::size_t)j] > top) { top = d[(std::size_t)i][(std::size_t)j]; arg = j; }
+    rmax[(std::size_t)i] = top; rarg[(std::size_t)i] = arg;
+  };
+  for (long i = 0; i < num; ++i) rescan(i, num);
   long nn = num;
-  for (; nn < 2 * num + 1; ++nn) {
+  for (; nn < cap; ++nn) {
     long bi = 0, bj = 0;
     int top = -1;
-    for (long i = 0; i < nn; ++i)
-      for (long j = i + 1; j < nn; ++j) if (d[i][j] > top) { top = d[i][j]; bi = i; bj = j; }
+    for (long i = 0; i < nn; ++i) if (rmax[(std::size_t)i] > top) { top = rmax[(std::size_t)i]; bi = i; bj = rarg[(std::size_t)i]; }
     if (top == -1) break;
-    p[bi][0] = p[bj][0] = (int)nn;
-    p[nn][1] = (int)bi; p[nn][2] = (int)bj;
+    p[(std::size_t)bi][0] = p[(std::size_t)bj][0] = (int)nn;
+    p[(std::size_t)nn][1] = (int)bi; p[(std::size_t)nn][2] = (int)bj;
     for (long i = 0; i < nn; ++i)
-      if (p[i][0] == -1) d[i][nn] = ((bi < i ? d[bi][i] : d[i][bi]) + (bj < i ? d[bj][i] : d[i][bj])) / 2;
-    for (long i = 0; i < bi; ++i) d[i][bi] = -1;
-    for (long i = bi + 1; i < nn + 1; ++i) d[bi][i] = -1;
-    for (long i = 0; i < bj; ++i) d[i][bj] = -1;
-    for (long i = bj + 1; i < nn + 1; ++i) d[bj][i] = -1;
+      if (p[(std::size_t)i][0] == -1) {
+        const int v = ((bi < i ? d[(std::size_t)bi][(std::size_t)i] : d[(std::size_t)i][(std::size_t)bi]) + (bj < i ? d[(std::size_t)bj][(std::size_t)i] : d[(std::size_t)i][(std::size_t)bj])) / 2;
+        d[(std::size_t)i][(std::size_t)nn] = v;
+        if (v > rmax[(std::size_t)i]) { rmax[(std::size_t)i] = v; rarg[(std::size_t)i] = nn; }
+      }
+    for (long x : {bi, bj}) {                                           // the joined nodes leave the matrix
+      for (long i = 0; i < x; ++i) d[(std::size_t)i][(std::size_t)x] = -1;
+      for (long i = x + 1; i < nn + 1; ++i) d[(std::size_t)x][(std::size_t)i] = -1;
+      rmax[(std::size_t)x] = -1; rarg[(std::size_t)x] = 0;
+    }
+    for (long i = 0; i < nn; ++i)
+      if (rmax[(std::size_t)i] > -1 && (rarg[(std::size_t)i] == bi || rarg[(std::size_t)i] == bj)) rescan(i, nn + 1);
   }
   return nn > 0 ? nn - 1 : 0;
 }
@@ -953,7 +984,10 @@ inline void msa(TCtx& g, TConfig const& c, TSeqProfiles const& sps, TAlign& alig
   if (table && keep && keep->size() == (std::size_t)num) orientedDistance(*table, *keep, d);
   else distanceMatrix(g, c, sps, d);
   std::vector<std::vector<int> > p((std::size_t)(2 * num + 1), std::vector<int>(3, -1));
+  detail::StageClock clk;
   const long root = detail::upgma_tree(d, p, num);
+  clk.lap("  msa: upgma");
+  double t_gpu = 0, t_host = 0;
 
   struct Node { std::vector<std::string> rows; TProfile prof; std::vector<uint32_t> idx; int height = 0; };
   std::vector<Node> node((std::size_t)(2 * num + 1));
@@ -979,7 +1013,10 @@ inline void msa(TCtx& g, TConfig const& c, TSeqProfiles const& sps, TAlign& alig
     for (long v = num; v <= root; ++v)
       if (node[(std::size_t)v].height == h) { level.push_back(v); a.push_back(&node[(std::size_t)p[v][1]].prof); b.push_back(&node[(std::size_t)p[v][2]].prof); }
     std::vector<std::string> ops;
+    const auto tg0 = std::chrono::steady_clock::now();
     gotohBatch(g, a, b, AlignConfig<true, true>(), c.aliscore, &ops);
+    const auto tg1 = std::chrono::steady_clock::now();
+    t_gpu += std::chrono::duration<double, std::milli>(tg1 - tg0).count();
     for (std::size_t q = 0; q < level.size(); ++q) {
       Node& nd = node[(std::size_t)level[q]];
       Node& l = node[(std::size_t)p[level[q]][1]];
@@ -1005,7 +1042,9 @@ inline void msa(TCtx& g, TConfig const& c, TSeqProfiles const& sps, TAlign& alig
       nd.idx.insert(nd.idx.end(), r.idx.begin(), r.idx.end());
       l.rows.clear(); r.rows.clear();                                   // children are not needed again
     }
+    t_host += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tg1).count();
   }
+  if (clk.on) std::fprintf(stderr, "[tracy_b200]   msa: %d levels, gotohBatch %.1f ms, row merges + column profiles %.1f ms\n", top, t_gpu, t_host);
   const Node& rt = node[(std::size_t)root];
   const std::size_t ncol = rt.rows.empty() ? 0 : rt.rows[0].size();
   detail::resize_align(align, rt.rows.size(), ncol);
@@ -1067,8 +1106,11 @@ inline int assembleDenovo(TCtx& g, TConfig const& c, TSeqProfiles& inputProfiles
                           std::ostream* log = &std::cout) {
   OrientationTable table;
   std::vector<std::vector<int32_t> > dist;
+  detail::StageClock clk;
   revSeqBasedOnDist(g, c, inputProfiles, fwdProfiles, log, &table, &dist);
+  clk.lap("orientation table + replay");
   const std::vector<bool> keep = matchingTraces(g, c, inputProfiles, &dist);
+  clk.lap("exclusion");
   TSeqProfiles seqProfiles;
   idxMap.clear();
   for (std::size_t i = 0; i < inputProfiles.size(); ++i) {
@@ -1077,6 +1119,7 @@ inline int assembleDenovo(TCtx& g, TConfig const& c, TSeqProfiles& inputProfiles
   }
   if (idxMap.size() < 2) return -1;
   msa(g, c, seqProfiles, align, seqidx, &table, &idxMap);               // the distance matrix comes from the orientation table
+  clk.lap("msa");
   return 0;
 }
 

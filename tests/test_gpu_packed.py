@@ -317,10 +317,13 @@ def test_streamed_batch_equals_chunk_pipeline(ctx, oracle_port, monkeypatch):
     monkeypatch.setenv("TRACY_B200_FORCE_STREAM", "1")      # pageable inputs arrive slowly: without it the context would fall back after the first call
 
     def both(fn):
+        k0 = ctx.stats()["kernel_launches"]
         got = fn()
+        k1 = ctx.stats()["kernel_launches"]
         monkeypatch.setenv("TRACY_B200_NO_STREAM", "1")
         want = fn()
         monkeypatch.delenv("TRACY_B200_NO_STREAM")
+        assert k1 - k0 <= 3, "the streamed form is one launch (plus a second stage)"
         return got, want
 
     for variant in range(2):
@@ -341,3 +344,48 @@ def test_streamed_batch_equals_chunk_pipeline(ctx, oracle_port, monkeypatch):
         for i in (0, 1, 97, 1775, 1776, 5328, N // 2, N - 1777, N - 1):
             ws, wops = oracle_port.gotoh_ps(prof[i], bytes(win[i]), 1, 0, (3, -5, -10, -4))
             assert int(s0[i]) == ws and bytes(o0[i, : l0[i]]) == wops, (variant, i)
+
+
+def test_streamed_batch_other_shapes(ctx, monkeypatch):
+    """The streamed form on the other packed-kernel inputs: string x string pairs, the 4-row upload of trace profiles
+    (TB_A1_TRACE_PROFILES), pinned arenas and result arrays, global alignment (no free end gaps) -- each against the launch-per-chunk
+    pipeline."""
+    N = 45000
+    rng = np.random.default_rng(9)
+    sc = DnaScore(3, -5, -10, -4)
+    monkeypatch.setenv("TRACY_B200_FORCE_STREAM", "1")
+
+    def both(fn):
+        monkeypatch.delenv("TRACY_B200_NO_STREAM", raising=False)
+        k0 = ctx.stats()["kernel_launches"]
+        got = fn()
+        k1 = ctx.stats()["kernel_launches"]
+        monkeypatch.setenv("TRACY_B200_NO_STREAM", "1")
+        want = fn()
+        monkeypatch.delenv("TRACY_B200_NO_STREAM")
+        assert k1 - k0 <= 3, "the streamed form is one launch (plus a second stage)"
+        return got, want
+
+    def same(got, want):
+        (s0, o0, l0), (s1, o1, l1) = got[:3], want[:3]
+        assert np.array_equal(s0, s1) and np.array_equal(l0, l1)
+        mask = np.arange(o0.shape[1])[None, :] < l0[:, None]
+        assert np.array_equal(o0 * mask, o1 * mask)
+        for r, q in zip(got[3:], want[3:]):
+            assert np.array_equal(r * mask, q * mask)
+
+    # string x string
+    s1 = rng.choice(np.frombuffer(b"ACGT", np.uint8), (N, 40))
+    s2 = rng.choice(np.frombuffer(b"ACGTN", np.uint8), (N, 70))
+    a1, a2 = tracy_b200.uniform_seqs(s1), tracy_b200.uniform_seqs(s2)
+    same(*both(lambda: ctx.gotoh("ss", a1, a2, sc, AlignConfig(False, False), rows=True)))
+    assert ctx.last_packed_pairs() == N
+    # trace profiles (rows 4, 5 zero): 4-row upload, pinned buffers on both sides, free horizontal end gaps
+    base_p, base_w = synth.align_batch(1024, 60, 150, seed=3)
+    idx = (np.arange(N) * 5 + 2) % 1024
+    prof = ctx.pinned_empty((N, 6, 60), np.float32); prof[:] = base_p[idx]
+    win = ctx.pinned_empty((N, 150), np.uint8); win[:] = base_w[idx]
+    assert not prof[:, 4:].any()
+    p1, p2 = tracy_b200.uniform_profiles(prof, trace_profiles=True), tracy_b200.uniform_seqs(win)
+    same(*both(lambda: ctx.gotoh("ps", p1, p2, sc, AlignConfig(True, False), rows=True)))
+    same(*both(lambda: ctx.gotoh("ps", p1, p2, sc, AlignConfig(False, False))))

@@ -830,9 +830,9 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     if (!inputs_pinned) {
       for (size_t c = 0; c < nch; ++c) {
         if (int rc = send_in(c)) return rc;
+        if (c + 1 == nch) TB_CUDA(ctx, cudaEventRecord(ctx->lanes[1].h0, s_in));
         if (int rc = drain(false)) return rc;
       }
-      TB_CUDA(ctx, cudaEventRecord(ctx->lanes[1].h0, s_in));
     }
     if (int rc = drain(true)) return rc;
     TB_CUDA(ctx, cudaStreamSynchronize(K.stream));

@@ -871,6 +871,10 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
     if (src != TB_OK || took) {
       if (src != TB_OK) {
         const std::string keep = ctx->err;
+        if (ctx->lanes[0].gate.p) {                       // whatever failed: a kernel that may be waiting at the gate must be able to leave
+          const uint32_t open = 0xffffffffu;
+          cudaMemcpy(ctx->lanes[0].gate.p, &open, 4, cudaMemcpyHostToDevice);
+        }
         for (int i = 0; i < kLanes; ++i) { cudaStreamSynchronize(ctx->lanes[i].stream); ctx->lanes[i].chunk = -1; ctx->lanes[i].timed = ctx->lanes[i].timed2 = false; }
         cudaGetLastError();
         ctx->err = keep;

@@ -137,6 +137,14 @@ inline void parallel_for(std::size_t n, F&& fn, std::size_t grain = 32) {
   for (auto& t : th) t.join();
   if (err) std::rethrow_exception(err);
 }
+// First touch of a fresh result buffer on the host's cores: a device-to-host copy into pageable memory that has never been
+// written takes its page faults one by one inside the driver's copy loop (hundreds of MB: tens of ms).
+inline void prefault(void* p, std::size_t bytes) {
+  if (bytes < (std::size_t)8 << 20) return;
+  const std::size_t block = (std::size_t)1 << 21, nblk = (bytes + block - 1) / block;
+  volatile char* c = static_cast<volatile char*>(p);
+  parallel_for(nblk, [&](std::size_t k) { for (std::size_t o = k * block; o < std::min(bytes, (k + 1) * block); o += 4096) c[o] = 0; }, 1);
+}
 template <typename T> inline void resize_align(Matrix<T>& a, std::size_t r, std::size_t c) { a.resize(r, c); }   // the header's own stand-in, with or without Boost around
 #if defined(TRACY_B200_WITH_BOOST) || defined(BOOST_MULTI_ARRAY_HPP) || defined(BOOST_MULTI_ARRAY_RG071801_HPP)
 template <typename TAlign> inline void resize_align(TAlign& a, std::size_t r, std::size_t c) { a.resize(boost::extents[r][c]); }   // src/align.h:200,277
@@ -253,6 +261,7 @@ inline std::vector<int32_t> gotohBatch(TCtx& g, std::vector<const TA*> const& a1
   });
   std::unique_ptr<uint8_t[]> obuf(ops ? new uint8_t[n * (std::size_t)stride] : nullptr), r0buf(rows ? new uint8_t[n * (std::size_t)stride] : nullptr),
       r1buf(rows ? new uint8_t[n * (std::size_t)stride] : nullptr);
+  for (uint8_t* q : {obuf.get(), r0buf.get(), r1buf.get()}) if (q) detail::prefault(q, n * (std::size_t)stride);
   std::vector<int32_t> olen(ops || rows ? n : 0);
   tb_batch b{{pa.get(), oa.data(), la.data()}, {pb.get(), ob.data(), lb.data()}, n, TB_MEM_HOST};
   tb_result r{scores.data(), ops ? obuf.get() : nullptr, stride, (ops || rows) ? olen.data() : nullptr,
@@ -615,6 +624,7 @@ inline void createProfileBatch(Context& g, std::vector<const TTrace*> const& tr,
   }
   if (bpos.empty()) { bpos.push_back(0); pri.push_back('N'); sec.push_back('N'); }
   std::unique_ptr<float[]> out(new float[(std::size_t)std::max<int64_t>(ototal, 1)]);
+  detail::prefault(out.get(), (std::size_t)std::max<int64_t>(ototal, 1) * sizeof(float));
   tb_profile_batch b{ta.arena, {bpos.data(), boff.data(), blen.data()}, pri.data(), sec.data(), tl.data(), trr.data(), n, ta.mem};
   g.check(tb_create_profile(g.get(), &b, out.get(), ooff.data(), olen.data()));
   detail::parallel_for(n, [&](std::size_t t) {

@@ -66,6 +66,10 @@ int main(int argc, char** argv) {
       for (int i = 0; i < 64; ++i) { rs[i] = RefSlice(); rs[i].refslice = refs[i % B]; rs[i].chr = "ref"; }
     }
     uint64_t k0 = 0, k1 = 0, h0 = 0, h1 = 0, d0 = 0, d1 = 0;
+    const auto rs_fresh = rs;                                       // decomposeBatch trims the slices in place: the second batch starts from these
+    double first_batch = 0;
+    for (int rep = 0; rep < 2; ++rep) {                             // batch 1 pays the context's buffer growth, batch 2 is what a service sees
+    if (rep) { rs = rs_fresh; for (int i = 0; i < N; ++i) { bc[i] = BaseCalls(); prs[i] = &rs[i]; pbc[i] = &bc[i]; } out.clear(); }
     tb_ctx_stats(g.get(), &k0, &h0, &d0);
     const auto t0 = std::chrono::steady_clock::now();
     tracy_b200::TraceSet resident(g, ptr);                          // the samples cross PCIe once for basecall, createProfile, allelicFraction
@@ -77,12 +81,14 @@ int main(int argc, char** argv) {
     const double s_up = std::chrono::duration<double>(tu - t0).count();
     tb_ctx_stats(g.get(), &k1, &h1, &d1);
     const double s_bc = std::chrono::duration<double>(t1 - t0).count(), s_dc = std::chrono::duration<double>(t2 - t1).count();
+    if (rep == 0) { first_batch = s_bc + s_dc; if (std::getenv("TRACY_B200_TIMING")) std::fprintf(stderr, "[tracy_b200] ---- second batch ----\n"); continue; }
     int ok = 0, shift = 0; long dcp = 0;
     for (int i = 0; i < N; ++i) { ok += out[i].ok; shift += out[i].ok && out[i].bp.indelshift; dcp += (long)out[i].dcp.size(); }
     std::printf("{\"workload\": \"tracy decompose, %d synthetic heterozygous traces (~900 bp, indel 1-25 bp) vs 4 kb references, maxindel 30 (BASELINE.json configs[2])\", "
-                "\"traces\": %d, \"seconds\": %.4f, \"traces_per_s\": %.1f, \"upload_seconds\": %.4f, \"basecall_seconds\": %.4f, \"decompose_seconds\": %.4f, \"decomposed\": %d, "
+                "\"traces\": %d, \"seconds_first_batch\": %.4f, \"seconds\": %.4f, \"traces_per_s\": %.1f, \"upload_seconds\": %.4f, \"basecall_seconds\": %.4f, \"decompose_seconds\": %.4f, \"decomposed\": %d, "
                 "\"heterozygous_shift_found\": %d, \"decomp_rows\": %ld, \"kernel_launches\": %llu, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"host\": \"C++ (tracy_b200.hpp decomposeBatch)\"}\n",
-                N, N, s_bc + s_dc, N / (s_bc + s_dc), s_up, s_bc - s_up, s_dc, ok, shift, dcp, (unsigned long long)(k1 - k0), (unsigned long long)(h1 - h0), (unsigned long long)(d1 - d0));
+                N, N, first_batch, s_bc + s_dc, N / (s_bc + s_dc), s_up, s_bc - s_up, s_dc, ok, shift, dcp, (unsigned long long)(k1 - k0), (unsigned long long)(h1 - h0), (unsigned long long)(d1 - d0));
+    }
   } catch (std::exception const& e) {
     std::printf("{\"error\": \"%s\"}\n", e.what());
     return 1;

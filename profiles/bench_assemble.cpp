@@ -37,29 +37,42 @@ int main(int argc, char** argv) {
     }
   };
   try {
-    tracy_b200::Context g(0);
+    auto run = [&](auto& g, tb_ctx* stat, int ngpu) {
     Cfg c;
     {   // warm-up on 16 traces
       std::vector<TProfile> p; make(16, p);
       std::vector<bool> f(16, true); tracy_b200::Matrix<char> al; std::vector<uint32_t> si, im;
       tracy_b200::assembleDenovo(g, c, p, f, al, si, im, nullptr, nullptr);
     }
-    std::vector<TProfile> prof; make(N, prof);
+    std::vector<TProfile> prof0; make(N, prof0);
+    double first_run = 0;
+    for (int rep = 0; rep < 2; ++rep) {                               // run 1 pays the buffer growth of the context(s), run 2 is what a service sees
+    std::vector<TProfile> prof = prof0;
     std::vector<bool> fwd((size_t)N, true);
     tracy_b200::Matrix<char> align;
     std::vector<uint32_t> seqidx, idxMap;
     uint64_t k0 = 0, k1 = 0, a = 0, b = 0;
-    tb_ctx_stats(g.get(), &k0, &a, &b);
+    tb_ctx_stats(stat, &k0, &a, &b);
     const auto t0 = std::chrono::steady_clock::now();
     const int rc = tracy_b200::assembleDenovo(g, c, prof, fwd, align, seqidx, idxMap, nullptr, nullptr);
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    tb_ctx_stats(g.get(), &k1, &a, &b);
+    tb_ctx_stats(stat, &k1, &a, &b);
+    if (rep == 0) { first_run = dt; if (std::getenv("TRACY_B200_TIMING")) std::fprintf(stderr, "[tracy_b200] ---- second run ----\n"); continue; }
     int flipped = 0;
     for (bool f : fwd) flipped += !f;
     std::printf("{\"workload\": \"tracy assemble de novo, %d trace profiles of 900 bp tiling a contig, every other one reverse-complemented (BASELINE.json configs[3])\", "
-                "\"traces\": %d, \"rc\": %d, \"seconds\": %.3f, \"kernel_launches\": %llu, \"kept\": %zu, \"flipped\": %d, \"msa_rows\": %zu, \"msa_columns\": %zu, "
-                "\"host\": \"C++ (tracy_b200.hpp assembleDenovo)\"}\n",
-                N, N, rc, dt, (unsigned long long)(k1 - k0), idxMap.size(), flipped, (size_t)align.shape()[0], (size_t)align.shape()[1]);
+                "\"traces\": %d, \"rc\": %d, \"seconds_first_run\": %.3f, \"seconds\": %.3f, \"kernel_launches\": %llu, \"kept\": %zu, \"flipped\": %d, \"msa_rows\": %zu, \"msa_columns\": %zu, "
+                "\"host\": \"C++ (tracy_b200.hpp assembleDenovo)\", \"gpus\": %d}\n",
+                N, N, rc, first_run, dt, (unsigned long long)(k1 - k0), idxMap.size(), flipped, (size_t)align.shape()[0], (size_t)align.shape()[1], ngpu);
+    }
+    };
+    if (argc > 2 && std::string(argv[2]) == "multi") {               // every visible GPU behind one handle: gotohBatch spreads each call's pairs
+      tracy_b200::MultiContext g;
+      run(g, g.device_context(0), g.size());
+    } else {
+      tracy_b200::Context g(0);
+      run(g, g.get(), 1);
+    }
   } catch (std::exception const& e) {
     std::printf("{\"error\": \"%s\"}\n", e.what());
     return 1;

@@ -537,8 +537,9 @@ int run_gotoh(tb_ctx* ctx, int mode, const tb_batch* batch, tb_score sc, tb_alig
   // chunk then ends without a tail of idle warp slots), about an eighth of the batch, inputs <= 768 MiB.
   const size_t wave = std::max<size_t>(plan.slots, 1);
   // steady chunks of about a sixteenth of the batch (3 waves at 100 k pairs): measured best of 3 .. 21 waves once the ramps are in
-  // (profiles/r02_e2e_chunk_probe.json: 89.3 ms against 91.4 - 91.9 ms; kernel boundaries cost nothing -- the next kernel's blocks
-  // move into the slots the previous kernel's blocks leave -- and small chunks keep the copies short)
+  // (profiles/r02_e2e_chunk_probe.json: 89.3 ms against 91.4 - 91.9 ms; the chunk size hardly matters -- the next kernel's blocks
+  // move into the slots the previous kernel's blocks leave, what a boundary costs is the warps of a block idling until its
+  // slowest one is through, which the streamed form below pays only once -- and small chunks keep the copies short)
   size_t chunk_target = 7104, chunk_parts = 16;
   if (const char* ce = getenv("TRACY_B200_CHUNK_TARGET")) { const long v = atol(ce); if (v > 0) chunk_target = (size_t)v; }
   if (const char* ce = getenv("TRACY_B200_CHUNK_PARTS")) { const long v = atol(ce); if (v > 0) chunk_parts = (size_t)v; }

@@ -376,6 +376,32 @@ int main() {
       else std::printf("consensusBatch #%d: %d pairs, union=%d iupac=%d, %ld batched calls for %ld pairs\n", rep, n, (int)nc.computeUnion, (int)nc.useIUPAC, g.calls, g.pairs);
     }
   }
+  // upgma_tree keeps row maxima where the reference rescans the triangle for every join: same joins and same ties on score matrices
+  // full of equal values, zeros, -1 (the "closed" sentinel as a score) and negative scores
+  for (int rep = 0; rep < 40; ++rep) {
+    const long num = 2 + (long)(rng() % 60);
+    const int span = rep % 4 == 0 ? 3 : rep % 4 == 1 ? 40 : 2000;      // few distinct values: ties everywhere
+    typedef boost::multi_array<int, 2> TD;
+    TD dr(boost::extents[2 * num + 1][2 * num + 1]), pr(boost::extents[2 * num + 1][3]);
+    std::vector<std::vector<int> > dn((std::size_t)(2 * num + 1), std::vector<int>((std::size_t)(2 * num + 1), 0)), pn((std::size_t)(2 * num + 1), std::vector<int>(3, -1));
+    for (long i = 0; i < 2 * num + 1; ++i) {
+      for (long j = 0; j < 2 * num + 1; ++j) { dr[i][j] = j > i ? -1 : 0; dn[(std::size_t)i][(std::size_t)j] = j > i ? -1 : 0; }
+      for (int k = 0; k < 3; ++k) pr[i][k] = -1;
+    }
+    for (long i = 0; i < num; ++i)
+      for (long j = i + 1; j < num; ++j) {
+        const int v = (int)(rng() % (unsigned)span) - (rep % 3 == 0 ? span / 4 : 0);
+        dr[i][j] = v; dn[(std::size_t)i][(std::size_t)j] = v;
+      }
+    const long root_ref = tracy::upgma(dr, pr, (TD::index)num);
+    const long root_new = tracy_b200::detail::upgma_tree(dn, pn, num);
+    bool ok = root_ref == root_new;
+    for (long i = 0; ok && i < 2 * num + 1; ++i)
+      for (int k = 0; k < 3; ++k) ok = ok && pr[i][k] == pn[(std::size_t)i][(std::size_t)k];
+    ++checks;
+    if (!ok) { ++failures; std::printf("MISMATCH upgma #%d (num=%ld, %d values)\n", rep, num, span); }
+  }
+  std::printf("upgma: 40 random score matrices, guide trees equal\n");
   std::printf("%d checks, %d mismatches\n", checks, failures);
   return failures ? 1 : 0;
 }

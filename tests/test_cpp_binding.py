@@ -36,7 +36,7 @@ def test_host_logic_against_reference(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "49 checks, 0 mismatches" in r.stdout, r.stdout[-3000:]
+    assert r.returncode == 0 and "89 checks, 0 mismatches" in r.stdout, r.stdout[-3000:]
 
 
 @pytest.mark.gpu
